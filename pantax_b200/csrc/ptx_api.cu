@@ -1,0 +1,1066 @@
+// Context + C ABI (include/pantax_gpu.h) of the B200-native PanTax hot path.
+// Host-side orchestration only: buffers, streams, kernel sequencing, getters.  All
+// arithmetic on GAF records, nodes, paths and trios happens in ptx_kernels.cu.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pantax_gpu.h"
+#include "ptx_internal.h"
+
+using namespace ptx;
+
+namespace {
+
+// ---- minimal NCCL surface, resolved with dlopen so that single-GPU use has no NCCL dependency
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclInt8 = 0, ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5 };
+enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 };
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (h) return true;
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
+        GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather;
+    }
+};
+NcclApi g_nccl;
+
+struct SpeciesHost {
+    std::string taxid;
+    int64_t start = 0, end = 0;
+    bool uploaded = false;   // host copy present (before commit)
+    bool has_graph = false;  // on device
+    int64_t n_nodes = 0, n_paths = 0;
+    int64_t node_base = -1, hap_base = -1, trio_base = 0, n_trios = 0;
+    std::vector<uint32_t> len;
+    std::vector<uint64_t> path_off;
+    std::vector<uint32_t> path_nodes;  // local ids
+};
+
+struct Chunk {
+    uint8_t* buf = nullptr;  // cudaMalloc'ed: [PRE][text][padding]
+    size_t cap = 0;          // text capacity (bytes) the buffer was padded for
+    size_t n = 0;            // text bytes
+    uint32_t n_tiles = 0;
+    uint32_t* tile_count = nullptr;
+    uint32_t* tile_base = nullptr;
+    uint32_t* labels = nullptr;
+    int64_t n_records = 0;
+    bool ingested = false;  // classify pass done
+    bool covered = false;   // coverage pass done against the current graph
+    cudaEvent_t copied = nullptr;
+};
+
+struct EvPair { cudaEvent_t a, b; };
+
+}  // namespace
+
+struct ptx_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr, copy_st = nullptr;
+    std::string err;
+    // ranges
+    std::vector<SpeciesHost> sp;
+    int64_t* d_rstart = nullptr; int64_t* d_rend = nullptr; int64_t* d_node_base = nullptr; uint32_t* d_order = nullptr;
+    int disjoint = 0;
+    // graph
+    GraphDev g;
+    bool graphs_committed = false;
+    // accumulators independent of the graph
+    unsigned long long* d_hist = nullptr;
+    unsigned long long* d_hist_g = nullptr;  // all-reduced copy (multi-GPU)
+    bool cov_reduced = false;               // coverage accumulators already hold the cross-rank sum
+    uint32_t* d_flags = nullptr;  // [0] dup, [1] mixed
+    uint32_t* d_err = nullptr;    // [S]
+    ulonglong2* d_ds = nullptr;
+    uint64_t ds_cap = 0;
+    int64_t ds_records = 0;  // upper bound of ids inserted
+    int64_t reserve_records = 0;
+    uint64_t* d_total = nullptr;  // scratch scalar
+    // records
+    std::vector<Chunk> chunks;
+    std::vector<uint8_t> carry;
+    int64_t total_records = 0;
+    bool dirty = false;          // something ingested / committed since the last finalize
+    uint32_t h_flags[2] = {0, 0};
+    std::vector<uint32_t> h_err;
+    // timing
+    std::vector<EvPair> ev_ingest, ev_final;
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1, rank = 0;
+};
+
+namespace {
+
+int fail(ptx_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+
+#define CU(call)                                                                                               \
+    do {                                                                                                       \
+        cudaError_t e_ = (call);                                                                               \
+        if (e_ != cudaSuccess)                                                                                 \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? PTX_E_NOMEM : PTX_E_CUDA, "%s failed: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                           \
+    } while (0)
+
+template <class T>
+int dalloc(ptx_ctx* ctx, T** p, size_t n, bool zero = true) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    CU(cudaMalloc((void**)p, n * sizeof(T)));
+    if (zero) CU(cudaMemsetAsync(*p, 0, n * sizeof(T), ctx->st));
+    return PTX_OK;
+}
+template <class T>
+void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+void ev_begin(ptx_ctx* ctx, std::vector<EvPair>& v) {
+    EvPair e;
+    cudaEventCreate(&e.a);
+    cudaEventCreate(&e.b);
+    cudaEventRecord(e.a, ctx->st);
+    v.push_back(e);
+}
+void ev_end(ptx_ctx* ctx, std::vector<EvPair>& v) { cudaEventRecord(v.back().b, ctx->st); }
+double ev_sum(std::vector<EvPair>& v) {
+    double ms = 0;
+    for (auto& e : v) {
+        float f = 0;
+        if (cudaEventElapsedTime(&f, e.a, e.b) == cudaSuccess) ms += f;
+    }
+    return ms;
+}
+void ev_clear(std::vector<EvPair>& v) {
+    for (auto& e : v) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    v.clear();
+}
+
+RangesView ranges_view(const ptx_ctx* ctx) {
+    RangesView R;
+    R.start = ctx->d_rstart;
+    R.end = ctx->d_rend;
+    R.node_base = ctx->d_node_base;
+    R.order = ctx->d_order;
+    R.S = (int)ctx->sp.size();
+    R.disjoint = ctx->disjoint;
+    return R;
+}
+
+uint32_t log2_ceil(uint64_t v) {
+    uint32_t l = 0;
+    while ((1ull << l) < v) ++l;
+    return l;
+}
+
+int ds_ensure(ptx_ctx* ctx, int64_t more_records) {
+    const int64_t need = std::max<int64_t>(ctx->ds_records + more_records, ctx->reserve_records);
+    uint64_t want = 1ull << std::max<uint32_t>(16, log2_ceil((uint64_t)need * 2 + 1));
+    if (want <= ctx->ds_cap) return PTX_OK;
+    ulonglong2* nd = nullptr;
+    CU(cudaMalloc((void**)&nd, want * sizeof(ulonglong2)));
+    CU(cudaMemsetAsync(nd, 0, want * sizeof(ulonglong2), ctx->st));
+    if (ctx->d_ds && ctx->ds_records > 0)
+        launch_ds_rehash(ctx->d_ds, ctx->ds_cap, nd, 64 - log2_ceil(want), want - 1, ctx->st);
+    if (ctx->d_ds) {
+        CU(cudaStreamSynchronize(ctx->st));
+        cudaFree(ctx->d_ds);
+    }
+    ctx->d_ds = nd;
+    ctx->ds_cap = want;
+    return PTX_OK;
+}
+
+IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
+    IngestArgs a;
+    memset(&a, 0, sizeof a);
+    a.text = ch.buf + PRE;
+    a.n_bytes = ch.n;
+    a.n_tiles = ch.n_tiles;
+    a.tile_base = ch.tile_base;
+    a.labels = ch.labels;
+    a.ranges = ranges_view(ctx);
+    a.hist = ctx->d_hist;
+    a.ds = ctx->d_ds;
+    a.ds_shift = 64 - log2_ceil(ctx->ds_cap);
+    a.ds_mask = ctx->ds_cap - 1;
+    a.flags = ctx->d_flags;
+    a.err = ctx->d_err;
+    const GraphDev& g = ctx->g;
+    a.len = g.len;
+    a.bit_off = g.bit_off;
+    a.bases = g.bases;
+    a.full = g.full;
+    a.bits = g.bits;
+    a.tt = g.T > 0 ? g.tt : nullptr;
+    a.tt_mask = g.tt_mask;
+    a.trio_mid = g.trio_mid;
+    a.trio_bases = g.trio_bases;
+    return a;
+}
+
+size_t padded_text_bytes(size_t n) {
+    size_t tiles = (n + TILE - 1) / TILE;
+    if (tiles == 0) tiles = 1;
+    return tiles * (size_t)TILE + OVER;
+}
+
+// allocate a chunk buffer able to hold `cap` text bytes; PRE bytes of '\n' in front
+int chunk_alloc(ptx_ctx* ctx, Chunk& ch, size_t cap) {
+    ch.cap = cap;
+    const size_t total = PRE + padded_text_bytes(cap);
+    CU(cudaMalloc((void**)&ch.buf, total));
+    CU(cudaMemsetAsync(ch.buf, '\n', PRE, ctx->st));
+    return PTX_OK;
+}
+
+void chunk_free(Chunk& ch) {
+    dfree(ch.buf);
+    dfree(ch.tile_count);
+    dfree(ch.tile_base);
+    dfree(ch.labels);
+    if (ch.copied) cudaEventDestroy(ch.copied);
+    ch.copied = nullptr;
+}
+
+// classify (+ optimistic coverage) pass over one chunk whose text is resident
+int chunk_process(ptx_ctx* ctx, Chunk& ch) {
+    if (ctx->cov_reduced) return fail(ctx, PTX_E_STATE, "multi-GPU: coverage already reduced by ptx_finalize; ptx_reset before ingesting more");
+    ch.n_tiles = (uint32_t)((ch.n + TILE - 1) / TILE);
+    if (ch.n_tiles == 0) { ch.ingested = true; ch.covered = true; return PTX_OK; }
+    // pad the tail of the last tile (+ overhang) with newlines
+    const size_t pad_to = (size_t)ch.n_tiles * TILE + OVER;
+    CU(cudaMemsetAsync(ch.buf + PRE + ch.n, '\n', pad_to - ch.n, ctx->st));
+    CU(cudaMalloc((void**)&ch.tile_count, ch.n_tiles * sizeof(uint32_t)));
+    CU(cudaMalloc((void**)&ch.tile_base, ch.n_tiles * sizeof(uint32_t)));
+    ev_begin(ctx, ctx->ev_ingest);
+    launch_count_records(ch.buf + PRE, ch.n, ch.n_tiles, ch.tile_count, ctx->st);
+    launch_scan_tiles(ch.tile_count, ch.tile_base, ch.n_tiles, ctx->d_total, ctx->st);
+    ev_end(ctx, ctx->ev_ingest);
+    uint64_t total = 0;
+    CU(cudaMemcpyAsync(&total, ctx->d_total, sizeof total, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ch.n_records = (int64_t)total;
+    if (total > 0xFFFFFFF0ull) return fail(ctx, PTX_E_INVALID, "more than 2^32 records in one chunk");
+    CU(cudaMalloc((void**)&ch.labels, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
+    int rc = ds_ensure(ctx, ch.n_records);
+    if (rc) return rc;
+    ctx->ds_records += ch.n_records;
+    IngestArgs a = make_args(ctx, ch);
+    const bool cover = ctx->graphs_committed && ctx->g.N > 0;
+    ev_begin(ctx, ctx->ev_ingest);
+    launch_ingest(a, MODE_CLASSIFY | (cover ? MODE_COVER : 0), ctx->st);
+    ev_end(ctx, ctx->ev_ingest);
+    CU(cudaGetLastError());
+    ch.ingested = true;
+    ch.covered = cover;
+    ctx->total_records += ch.n_records;
+    ctx->dirty = true;
+    return PTX_OK;
+}
+
+int zero_coverage(ptx_ctx* ctx) {
+    GraphDev& g = ctx->g;
+    if (g.N <= 0) return PTX_OK;
+    CU(cudaMemsetAsync(g.bases, 0, g.N * sizeof(unsigned long long), ctx->st));
+    CU(cudaMemsetAsync(g.full, 0, g.N, ctx->st));
+    CU(cudaMemsetAsync(g.bits, 0, g.n_bit_words * sizeof(uint32_t), ctx->st));
+    if (g.T > 0) CU(cudaMemsetAsync(g.trio_bases, 0, g.T * sizeof(unsigned long long), ctx->st));
+    CU(cudaMemsetAsync(ctx->d_err, 0, std::max<size_t>(ctx->sp.size(), 1) * sizeof(uint32_t), ctx->st));
+    return PTX_OK;
+}
+
+void free_graph(ptx_ctx* ctx) {
+    GraphDev& g = ctx->g;
+    dfree(g.len); dfree(g.bit_off); dfree(g.bases); dfree(g.full); dfree(g.bits); dfree(g.cov);
+    dfree(g.pnode); dfree(g.poff); dfree(g.path_len_sum); dfree(g.path_cov_sum);
+    dfree(g.trio_key); dfree(g.trio_len); dfree(g.trio_owner); dfree(g.trio_bases); dfree(g.trio_start);
+    dfree(g.hap_nz); dfree(g.tt); dfree(g.trio_mid);
+    g = GraphDev();
+}
+
+int check_species(ptx_ctx* ctx, int s, bool need_graph) {
+    if (!ctx) return PTX_E_INVALID;
+    if (s < 0 || s >= (int)ctx->sp.size()) return fail(ctx, PTX_E_RANGE, "species index %d out of range", s);
+    if (need_graph && !ctx->sp[s].has_graph) return fail(ctx, PTX_E_NO_GRAPH, "species %d has no committed graph", s);
+    return PTX_OK;
+}
+
+int check_results(ptx_ctx* ctx, int s) {
+    int rc = check_species(ctx, s, true);
+    if (rc) return rc;
+    if (ctx->dirty) return fail(ctx, PTX_E_STATE, "call ptx_finalize before reading results");
+    if (s < (int)ctx->h_err.size() && (ctx->h_err[s] & 1u))
+        return fail(ctx, PTX_E_START_GT_LEN, "species %s: read start is bigger than node len (profile.rs:854)",
+                    ctx->sp[s].taxid.c_str());
+    return PTX_OK;
+}
+
+int nccl_check(ptx_ctx* ctx, int r, const char* what) {
+    if (r == 0) return PTX_OK;
+    return fail(ctx, PTX_E_NCCL, "%s failed: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ptx_version(void) { return "pantax_b200 0.1 (sm_100a)"; }
+
+int ptx_create(int device, ptx_ctx** out) {
+    if (!out) return PTX_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return PTX_E_CUDA;  // no CPU fallback by design
+    if (cudaSetDevice(device) != cudaSuccess) return PTX_E_CUDA;
+    ptx_ctx* ctx = new (std::nothrow) ptx_ctx;
+    if (!ctx) return PTX_E_NOMEM;
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return PTX_E_CUDA;
+    }
+    if (cudaMalloc((void**)&ctx->d_flags, 2 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_total, sizeof(uint64_t)) != cudaSuccess) {
+        delete ctx;
+        return PTX_E_NOMEM;
+    }
+    cudaMemsetAsync(ctx->d_flags, 0, 2 * sizeof(uint32_t), ctx->st);
+    *out = ctx;
+    return PTX_OK;
+}
+
+void ptx_destroy(ptx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& ch : ctx->chunks) chunk_free(ch);
+    free_graph(ctx);
+    dfree(ctx->d_rstart); dfree(ctx->d_rend); dfree(ctx->d_node_base); dfree(ctx->d_order);
+    dfree(ctx->d_hist); dfree(ctx->d_hist_g); dfree(ctx->d_flags); dfree(ctx->d_err); dfree(ctx->d_ds); dfree(ctx->d_total);
+    ev_clear(ctx->ev_ingest);
+    ev_clear(ctx->ev_final);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
+    delete ctx;
+}
+
+const char* ptx_last_error(const ptx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int ptx_set_ranges(ptx_ctx* ctx, int S, const char* const* taxid, const int64_t* start, const int64_t* end) {
+    if (!ctx || S <= 0 || !taxid || !start || !end) return fail(ctx, PTX_E_INVALID, "ptx_set_ranges: bad arguments");
+    if (!ctx->chunks.empty() || ctx->graphs_committed) return fail(ctx, PTX_E_STATE, "ranges must be set before graphs and GAF");
+    cudaSetDevice(ctx->device);
+    ctx->sp.assign(S, SpeciesHost());
+    std::vector<uint32_t> order(S);
+    for (int s = 0; s < S; ++s) {
+        ctx->sp[s].taxid = taxid[s] ? taxid[s] : "";
+        ctx->sp[s].start = start[s];
+        ctx->sp[s].end = end[s];
+        order[s] = (uint32_t)s;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return start[a] < start[b]; });
+    ctx->disjoint = 1;
+    for (int i = 0; i < S; ++i) {
+        if (end[order[i]] < start[order[i]]) ctx->disjoint = 0;
+        if (i + 1 < S && end[order[i]] >= start[order[i + 1]]) ctx->disjoint = 0;
+    }
+    dfree(ctx->d_rstart); dfree(ctx->d_rend); dfree(ctx->d_node_base); dfree(ctx->d_order); dfree(ctx->d_hist); dfree(ctx->d_err);
+    int rc;
+    if ((rc = dalloc(ctx, &ctx->d_rstart, S)) || (rc = dalloc(ctx, &ctx->d_rend, S)) || (rc = dalloc(ctx, &ctx->d_node_base, S)) ||
+        (rc = dalloc(ctx, &ctx->d_order, S)) || (rc = dalloc(ctx, &ctx->d_hist, (size_t)S * 4)) || (rc = dalloc(ctx, &ctx->d_err, S)))
+        return rc;
+    std::vector<int64_t> nb(S, -1);
+    CU(cudaMemcpyAsync(ctx->d_rstart, start, S * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->d_rend, end, S * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->d_node_base, nb.data(), S * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->d_order, order.data(), S * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->h_err.assign(S, 0);
+    return PTX_OK;
+}
+
+int ptx_upload_graph(ptx_ctx* ctx, int s, const int64_t* nodes_len, int64_t n, const uint64_t* path_off, const uint64_t* path_nodes,
+                     int64_t H) {
+    int rc = check_species(ctx, s, false);
+    if (rc) return rc;
+    if (ctx->graphs_committed) return fail(ctx, PTX_E_STATE, "graphs already committed");
+    if (!nodes_len || n <= 0 || H < 0 || (H > 0 && (!path_off || !path_nodes))) return fail(ctx, PTX_E_INVALID, "ptx_upload_graph: bad arguments");
+    SpeciesHost& sp = ctx->sp[s];
+    if (sp.end - sp.start + 1 != n)  // profile.rs:2938: nvert = end - start + 1 indexes nodes_len
+        return fail(ctx, PTX_E_NVERT_MISMATCH, "species %s: range %lld..%lld has %lld ids but the graph has %lld nodes", sp.taxid.c_str(),
+                    (long long)sp.start, (long long)sp.end, (long long)(sp.end - sp.start + 1), (long long)n);
+    sp.len.resize(n);
+    for (int64_t i = 0; i < n; ++i) {
+        if (nodes_len[i] <= 0) return fail(ctx, PTX_E_ZERO_LEN, "species %s: node %lld has length %lld (profile.rs:494)", sp.taxid.c_str(), (long long)i, (long long)nodes_len[i]);
+        if (nodes_len[i] > 0x7FFFFFFFll) return fail(ctx, PTX_E_INVALID, "node length exceeds 2^31");
+        sp.len[i] = (uint32_t)nodes_len[i];
+    }
+    sp.path_off.assign(H + 1, 0);
+    if (H > 0) {
+        if (path_off[0] != 0) return fail(ctx, PTX_E_INVALID, "path_off[0] must be 0");
+        for (int64_t h = 0; h <= H; ++h) {
+            if (h && path_off[h] < path_off[h - 1]) return fail(ctx, PTX_E_INVALID, "path_off must be non-decreasing");
+            sp.path_off[h] = path_off[h];
+        }
+    }
+    const uint64_t P = H > 0 ? path_off[H] : 0;
+    sp.path_nodes.resize(P);
+    for (uint64_t k = 0; k < P; ++k) {
+        if (path_nodes[k] >= (uint64_t)n) return fail(ctx, PTX_E_INVALID, "species %s: path node id %llu >= %lld nodes", sp.taxid.c_str(), (unsigned long long)path_nodes[k], (long long)n);
+        sp.path_nodes[k] = (uint32_t)path_nodes[k];
+    }
+    sp.n_nodes = n;
+    sp.n_paths = H;
+    sp.uploaded = true;
+    return PTX_OK;
+}
+
+int ptx_commit_graphs(ptx_ctx* ctx) {
+    if (!ctx) return PTX_E_INVALID;
+    if (ctx->graphs_committed) return fail(ctx, PTX_E_STATE, "graphs already committed");
+    cudaSetDevice(ctx->device);
+    const int S = (int)ctx->sp.size();
+    GraphDev& g = ctx->g;
+    int64_t N = 0, Htot = 0, P = 0;
+    for (auto& sp : ctx->sp)
+        if (sp.uploaded) {
+            sp.node_base = N;
+            sp.hap_base = Htot;
+            N += sp.n_nodes;
+            Htot += sp.n_paths;
+            P += (int64_t)sp.path_nodes.size();
+        }
+    if (N == 0) return fail(ctx, PTX_E_STATE, "no graph uploaded");
+    if (N >= 0x7FFFFFFFll) return fail(ctx, PTX_E_UNSUPPORTED, "more than 2^31 nodes on one GPU");
+    // ---- host-side concatenation (graph setup, outside the timed hot path)
+    std::vector<uint32_t> len((size_t)N);
+    std::vector<uint64_t> bit_off((size_t)N + 1);
+    std::vector<uint32_t> pnode((size_t)P);
+    std::vector<uint64_t> poff((size_t)Htot + 1);
+    std::vector<int64_t> node_base(S, -1);
+    uint64_t bits = 0;
+    int64_t max_paths = 0;
+    {
+        int64_t h = 0;
+        uint64_t k = 0;
+        for (int s = 0; s < S; ++s) {
+            SpeciesHost& sp = ctx->sp[s];
+            if (!sp.uploaded) continue;
+            node_base[s] = sp.node_base;
+            max_paths = std::max(max_paths, sp.n_paths);
+            for (int64_t i = 0; i < sp.n_nodes; ++i) {
+                len[sp.node_base + i] = sp.len[i];
+                bit_off[sp.node_base + i] = bits;
+                bits += sp.len[i];
+            }
+            for (int64_t p = 0; p < sp.n_paths; ++p) {
+                poff[h++] = k;
+                for (uint64_t q = sp.path_off[p]; q < sp.path_off[p + 1]; ++q) pnode[k++] = (uint32_t)(sp.node_base + sp.path_nodes[q]);
+            }
+        }
+        poff[Htot] = k;
+        bit_off[N] = bits;
+    }
+    g.N = N; g.Htot = Htot; g.P = P;
+    g.n_bit_words = (bits + 31) / 32 + 1;
+    int rc;
+    if ((rc = dalloc(ctx, &g.len, N, false)) || (rc = dalloc(ctx, &g.bit_off, N + 1, false)) || (rc = dalloc(ctx, &g.bases, N)) ||
+        (rc = dalloc(ctx, &g.full, N)) || (rc = dalloc(ctx, &g.bits, g.n_bit_words)) || (rc = dalloc(ctx, &g.cov, N)) ||
+        (rc = dalloc(ctx, &g.pnode, P, false)) || (rc = dalloc(ctx, &g.poff, Htot + 1, false)) || (rc = dalloc(ctx, &g.path_len_sum, Htot)) ||
+        (rc = dalloc(ctx, &g.path_cov_sum, Htot)) || (rc = dalloc(ctx, &g.hap_nz, Htot)) || (rc = dalloc(ctx, &g.trio_start, Htot + 1)) ||
+        (rc = dalloc(ctx, &g.trio_mid, (N + 31) / 32)))
+        return rc;
+    CU(cudaMemcpyAsync(g.len, len.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(g.bit_off, bit_off.data(), (N + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->st));
+    if (P) CU(cudaMemcpyAsync(g.pnode, pnode.data(), P * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(g.poff, poff.data(), (Htot + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->d_node_base, node_base.data(), S * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
+
+    // ---- distinct-node marks per path: round r handles the r-th path of every species
+    uint32_t* stamp = nullptr;
+    uint32_t* d_round = nullptr;
+    if ((rc = dalloc(ctx, &stamp, N)) || (rc = dalloc(ctx, &d_round, std::max<int64_t>(Htot, 1), false))) return rc;
+    {
+        std::vector<uint32_t> round_list;
+        std::vector<std::pair<uint32_t, uint32_t>> rounds;  // offset, count
+        std::vector<uint64_t> round_max;
+        for (int64_t r = 0; r < max_paths; ++r) {
+            uint32_t off = (uint32_t)round_list.size();
+            uint64_t mx = 0;
+            for (auto& sp : ctx->sp)
+                if (sp.uploaded && r < sp.n_paths) {
+                    round_list.push_back((uint32_t)(sp.hap_base + r));
+                    mx = std::max<uint64_t>(mx, sp.path_off[r + 1] - sp.path_off[r]);
+                }
+            rounds.push_back({off, (uint32_t)round_list.size() - off});
+            round_max.push_back(mx);
+        }
+        if (!round_list.empty()) CU(cudaMemcpyAsync(d_round, round_list.data(), round_list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));  // host vectors above must outlive the copies
+        for (size_t r = 0; r < rounds.size(); ++r) {
+            // gridDim.y <= 65535
+            for (uint32_t o = 0; o < rounds[r].second; o += 65535u) {
+                uint32_t cnt = std::min<uint32_t>(65535u, rounds[r].second - o);
+                if (round_max[r] > 0) launch_mark_path_dups(g.pnode, g.poff, d_round + rounds[r].first + o, cnt, round_max[r], stamp, ctx->st);
+            }
+        }
+    }
+    launch_path_len_sum(g.pnode, g.poff, Htot, P, g.len, g.path_len_sum, ctx->st);
+
+    // ---- unique trios (profile.rs:658-740)
+    int64_t n_windows = 0;
+    for (auto& sp : ctx->sp)
+        if (sp.uploaded)
+            for (int64_t p = 0; p < sp.n_paths; ++p) {
+                uint64_t l = sp.path_off[p + 1] - sp.path_off[p];
+                if (l >= 3) n_windows += (int64_t)l - 2;
+            }
+    g.T = 0;
+    if (n_windows > 0) {
+        const uint64_t kcap = 1ull << std::max<uint32_t>(10, log2_ceil((uint64_t)n_windows * 2));
+        if (kcap > 0x80000000ull) return fail(ctx, PTX_E_UNSUPPORTED, "trio window table too large");
+        uint4* keys = nullptr;
+        uint32_t* cnt = nullptr;
+        uint32_t* flag = nullptr;
+        uint64_t* scan = nullptr;
+        uint64_t* scratch = nullptr;
+        CU(cudaMalloc((void**)&keys, kcap * sizeof(uint4)));
+        CU(cudaMemsetAsync(keys, 0xFF, kcap * sizeof(uint4), ctx->st));
+        if ((rc = dalloc(ctx, &cnt, kcap)) || (rc = dalloc(ctx, &flag, P, false)) || (rc = dalloc(ctx, &scan, P + 1, false)) ||
+            (rc = dalloc(ctx, &scratch, P / 2048 + 4, false)))
+            return rc;
+        launch_trio_count(g.pnode, g.poff, Htot, P, keys, cnt, (uint32_t)(kcap - 1), ctx->st);
+        launch_trio_flag(g.pnode, g.poff, Htot, P, keys, cnt, (uint32_t)(kcap - 1), flag, ctx->st);
+        launch_scan_u32(flag, scan, (uint64_t)P, scratch, ctx->st);
+        uint64_t T = 0;
+        CU(cudaMemcpyAsync(&T, scan + P, sizeof T, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        g.T = (int64_t)T;
+        if (T > 0) {
+            const uint64_t tcap = 1ull << std::max<uint32_t>(10, log2_ceil(T * 2));
+            if ((rc = dalloc(ctx, &g.trio_key, T * 3, false)) || (rc = dalloc(ctx, &g.trio_len, T, false)) ||
+                (rc = dalloc(ctx, &g.trio_owner, T, false)) || (rc = dalloc(ctx, &g.trio_bases, T)))
+                return rc;
+            CU(cudaMalloc((void**)&g.tt, tcap * sizeof(uint4)));
+            CU(cudaMemsetAsync(g.tt, 0xFF, tcap * sizeof(uint4), ctx->st));
+            g.tt_mask = (uint32_t)(tcap - 1);
+        }
+        if (T > 0)
+            launch_trio_emit(g.pnode, g.poff, Htot, P, flag, scan, g.len, g.trio_key, g.trio_len, g.trio_owner, g.tt, g.tt_mask, g.trio_mid,
+                             g.trio_start, ctx->st);
+        CU(cudaStreamSynchronize(ctx->st));
+        CU(cudaGetLastError());
+        dfree(keys); dfree(cnt); dfree(flag); dfree(scan); dfree(scratch);
+    }
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    dfree(stamp);
+    dfree(d_round);
+    // per-species trio slices: trios are ordered by (global hap, position) and haps are grouped by species
+    std::vector<uint64_t> tstart((size_t)Htot + 1, 0);
+    if (g.T > 0) CU(cudaMemcpy(tstart.data(), g.trio_start, (Htot + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    for (auto& sp : ctx->sp)
+        if (sp.uploaded) {
+            sp.trio_base = (int64_t)tstart[sp.hap_base];
+            sp.n_trios = (int64_t)tstart[sp.hap_base + sp.n_paths] - sp.trio_base;
+            sp.has_graph = true;
+            sp.uploaded = false;
+            std::vector<uint32_t>().swap(sp.len);
+            std::vector<uint32_t>().swap(sp.path_nodes);
+            // path_off is kept (tiny) for ptx_species_paths consumers
+        }
+    ctx->graphs_committed = true;
+    for (auto& ch : ctx->chunks) ch.covered = false;
+    if (!ctx->chunks.empty()) ctx->dirty = true;
+    return PTX_OK;
+}
+
+int ptx_reserve(ptx_ctx* ctx, int64_t expected_records) {
+    if (!ctx || expected_records < 0) return PTX_E_INVALID;
+    ctx->reserve_records = expected_records;
+    return PTX_OK;
+}
+
+int ptx_host_alloc(size_t bytes, void** out) {
+    if (!out) return PTX_E_INVALID;
+    return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? PTX_OK : PTX_E_NOMEM;
+}
+int ptx_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? PTX_OK : PTX_E_CUDA; }
+
+int ptx_ingest_gaf(ptx_ctx* ctx, const uint8_t* bytes, size_t n, int is_last) {
+    if (!ctx || (!bytes && n)) return fail(ctx, PTX_E_INVALID, "ptx_ingest_gaf: bad arguments");
+    if (ctx->sp.empty()) return fail(ctx, PTX_E_STATE, "call ptx_set_ranges first");
+    cudaSetDevice(ctx->device);
+    // usable part: up to and including the last '\n' (everything if is_last)
+    size_t usable = n;
+    if (!is_last) {
+        const void* nl = n ? memrchr(bytes, '\n', n) : nullptr;
+        usable = nl ? (size_t)((const uint8_t*)nl - bytes) + 1 : 0;
+    }
+    if (usable == 0 && !(is_last && !ctx->carry.empty())) {
+        ctx->carry.insert(ctx->carry.end(), bytes, bytes + n);
+        return PTX_OK;
+    }
+    // split into pieces of <= PIECE bytes at line boundaries so H2D of piece k+1 overlaps the kernels of piece k
+    const size_t PIECE = 64ull << 20;
+    size_t off = 0;
+    bool first = true;
+    std::vector<size_t> piece_idx;
+    while (off < usable || (first && !ctx->carry.empty())) {
+        size_t take = std::min(PIECE, usable - off);
+        if (off + take < usable) {
+            const void* nl = memrchr(bytes + off, '\n', take);
+            if (nl) take = (size_t)((const uint8_t*)nl - (bytes + off)) + 1;
+            else {  // a single line longer than PIECE: extend to its end
+                const void* e = memchr(bytes + off + take, '\n', usable - off - take);
+                take = e ? (size_t)((const uint8_t*)e - (bytes + off)) + 1 : usable - off;
+            }
+        }
+        Chunk ch;
+        const size_t c0 = first ? ctx->carry.size() : 0;
+        int rc = chunk_alloc(ctx, ch, c0 + take);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(ctx->st));  // PRE memset done before the copy stream touches the buffer
+        if (c0) CU(cudaMemcpyAsync(ch.buf + PRE, ctx->carry.data(), c0, cudaMemcpyHostToDevice, ctx->copy_st));
+        if (take) CU(cudaMemcpyAsync(ch.buf + PRE + c0, bytes + off, take, cudaMemcpyHostToDevice, ctx->copy_st));
+        ch.n = c0 + take;
+        CU(cudaEventCreateWithFlags(&ch.copied, cudaEventDisableTiming));
+        CU(cudaEventRecord(ch.copied, ctx->copy_st));
+        ctx->chunks.push_back(ch);
+        piece_idx.push_back(ctx->chunks.size() - 1);
+        off += take;
+        first = false;
+    }
+    // carry for the next call (the copy above read ctx->carry asynchronously from pageable memory: it is staged by the
+    // runtime before cudaMemcpyAsync returns, so it is safe to overwrite now)
+    ctx->carry.assign(bytes + usable, bytes + n);
+    for (size_t pi : piece_idx) {
+        Chunk& ch = ctx->chunks[pi];
+        CU(cudaStreamWaitEvent(ctx->st, ch.copied, 0));
+        int rc = chunk_process(ctx, ch);
+        if (rc) return rc;
+    }
+    return PTX_OK;
+}
+
+int ptx_gaf_buffer_alloc(ptx_ctx* ctx, size_t capacity, int* buffer_id, void** device_ptr) {
+    if (!ctx || !buffer_id || !device_ptr) return PTX_E_INVALID;
+    cudaSetDevice(ctx->device);
+    Chunk ch;
+    int rc = chunk_alloc(ctx, ch, capacity);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->chunks.push_back(ch);
+    *buffer_id = (int)ctx->chunks.size() - 1;
+    *device_ptr = ch.buf + PRE;
+    return PTX_OK;
+}
+
+int ptx_ingest_gaf_device(ptx_ctx* ctx, int buffer_id, size_t n) {
+    if (!ctx || buffer_id < 0 || buffer_id >= (int)ctx->chunks.size()) return fail(ctx, PTX_E_RANGE, "bad buffer id");
+    Chunk& ch = ctx->chunks[buffer_id];
+    if (ch.ingested) return fail(ctx, PTX_E_STATE, "buffer already ingested");
+    if (n > ch.cap) return fail(ctx, PTX_E_INVALID, "n exceeds the buffer capacity");
+    if (ctx->sp.empty()) return fail(ctx, PTX_E_STATE, "call ptx_set_ranges first");
+    cudaSetDevice(ctx->device);
+    ch.n = n;
+    return chunk_process(ctx, ch);
+}
+
+int ptx_finalize(ptx_ctx* ctx) {
+    if (!ctx) return PTX_E_INVALID;
+    cudaSetDevice(ctx->device);
+    if (!ctx->carry.empty()) return fail(ctx, PTX_E_STATE, "a partial line is pending: pass is_last=1 on the final chunk");
+    for (auto& ch : ctx->chunks)
+        if (!ch.ingested && ch.n_tiles == 0 && ch.n == 0) { ch.ingested = true; ch.covered = true; }  // unused device buffers
+    if (!ctx->dirty) return PTX_OK;
+    GraphDev& g = ctx->g;
+    const int S = (int)ctx->sp.size();
+    ev_begin(ctx, ctx->ev_final);
+    if (ctx->comm) {  // a mixed id group / error seen on any rank is seen by all
+        int rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 2, ncclUint32, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(flags)");
+        if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    const bool mixed = ctx->h_flags[1] != 0;
+    if (ctx->graphs_committed && g.N > 0) {
+        if (mixed) {
+            // profile.rs:406-437: some id group spans species -> its reads must not contribute.  The optimistic
+            // pass counted them: start over and replay the retained text with the keep mask.
+            bool any_optimistic = false;
+            for (auto& ch : ctx->chunks) any_optimistic |= (ch.ingested && ch.covered);
+            if (any_optimistic) {
+                int rc = zero_coverage(ctx);
+                if (rc) return rc;
+                for (auto& ch : ctx->chunks) ch.covered = false;
+            }
+        }
+        for (auto& ch : ctx->chunks) {
+            if (!ch.ingested || ch.covered || ch.n_tiles == 0) continue;
+            IngestArgs a = make_args(ctx, ch);
+            launch_ingest(a, MODE_COVER | (mixed ? MODE_KEEPMASK : 0), ctx->st);
+            ch.covered = true;
+        }
+        if (ctx->comm) {
+            // int64 sums and flag maxima are order-free: bit-exact for any shard count
+            if (ctx->cov_reduced) return fail(ctx, PTX_E_STATE, "multi-GPU: coverage already reduced");
+            ctx->cov_reduced = true;
+            int rc;
+            if ((rc = nccl_check(ctx, g_nccl.AllReduce(g.bases, g.bases, g.N, ncclUint64, ncclSum, ctx->comm, ctx->st), "ncclAllReduce(bases)"))) return rc;
+            if (g.T > 0 && (rc = nccl_check(ctx, g_nccl.AllReduce(g.trio_bases, g.trio_bases, g.T, ncclUint64, ncclSum, ctx->comm, ctx->st), "ncclAllReduce(trio_bases)"))) return rc;
+            if ((rc = nccl_check(ctx, g_nccl.AllReduce(g.full, g.full, g.N, ncclUint8, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(full)"))) return rc;
+            if ((rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_err, ctx->d_err, S, ncclUint32, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(err)"))) return rc;
+            // bitmap OR: all-gather the packed words, OR locally (NCCL has no bitwise-or reduction)
+            uint32_t* all = nullptr;
+            CU(cudaMalloc((void**)&all, (size_t)ctx->n_ranks * g.n_bit_words * sizeof(uint32_t)));
+            if ((rc = nccl_check(ctx, g_nccl.AllGather(g.bits, all, g.n_bit_words, ncclUint32, ctx->comm, ctx->st), "ncclAllGather(bits)"))) return rc;
+            for (int r = 0; r < ctx->n_ranks; ++r)
+                if (r != ctx->rank) launch_or_words(g.bits, all + (size_t)r * g.n_bit_words, g.n_bit_words, ctx->st);
+            CU(cudaStreamSynchronize(ctx->st));
+            cudaFree(all);
+        }
+        CU(cudaMemsetAsync(g.path_cov_sum, 0, std::max<int64_t>(g.Htot, 1) * sizeof(unsigned long long), ctx->st));
+        CU(cudaMemsetAsync(g.hap_nz, 0, std::max<int64_t>(g.Htot, 1) * sizeof(unsigned long long), ctx->st));
+        launch_cov(g, ctx->st);
+        launch_path_cov_sum(g, ctx->st);
+        launch_hap_nz(g, ctx->st);
+    }
+    if (ctx->comm) {
+        if (!ctx->d_hist_g) { int rc = dalloc(ctx, &ctx->d_hist_g, (size_t)S * 4); if (rc) return rc; }
+        int rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_hist, ctx->d_hist_g, (size_t)S * 4, ncclUint64, ncclSum, ctx->comm, ctx->st), "ncclAllReduce(hist)");
+        if (rc) return rc;
+    }
+    ctx->h_err.assign(S, 0);
+    CU(cudaMemcpyAsync(ctx->h_err.data(), ctx->d_err, S * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st));
+    ev_end(ctx, ctx->ev_final);
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    ctx->dirty = false;
+    return PTX_OK;
+}
+
+int ptx_reset(ptx_ctx* ctx) {
+    if (!ctx) return PTX_E_INVALID;
+    cudaSetDevice(ctx->device);
+    CU(cudaDeviceSynchronize());
+    for (auto& ch : ctx->chunks) chunk_free(ch);
+    ctx->chunks.clear();
+    ctx->carry.clear();
+    ctx->total_records = 0;
+    ctx->ds_records = 0;
+    ctx->cov_reduced = false;
+    ctx->h_flags[0] = ctx->h_flags[1] = 0;
+    const size_t S = std::max<size_t>(ctx->sp.size(), 1);
+    if (ctx->d_hist) CU(cudaMemsetAsync(ctx->d_hist, 0, S * 4 * sizeof(unsigned long long), ctx->st));
+    CU(cudaMemsetAsync(ctx->d_flags, 0, 2 * sizeof(uint32_t), ctx->st));
+    if (ctx->d_ds) CU(cudaMemsetAsync(ctx->d_ds, 0, ctx->ds_cap * sizeof(ulonglong2), ctx->st));
+    if (ctx->d_err) {
+        int rc = zero_coverage(ctx);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(ctx->d_err, 0, S * sizeof(uint32_t), ctx->st));
+    }
+    if (ctx->g.Htot > 0) {
+        CU(cudaMemsetAsync(ctx->g.path_cov_sum, 0, ctx->g.Htot * sizeof(unsigned long long), ctx->st));
+        CU(cudaMemsetAsync(ctx->g.hap_nz, 0, ctx->g.Htot * sizeof(unsigned long long), ctx->st));
+        CU(cudaMemsetAsync(ctx->g.cov, 0, ctx->g.N * sizeof(uint32_t), ctx->st));
+    }
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->h_err.assign(ctx->sp.size(), 0);
+    ev_clear(ctx->ev_ingest);
+    ev_clear(ctx->ev_final);
+    ctx->dirty = false;
+    return PTX_OK;
+}
+
+int64_t ptx_num_records(const ptx_ctx* ctx) { return ctx ? ctx->total_records : PTX_E_INVALID; }
+int ptx_num_species(const ptx_ctx* ctx) { return ctx ? (int)ctx->sp.size() : PTX_E_INVALID; }
+int ptx_ids_unique(const ptx_ctx* ctx) { return ctx ? (ctx->h_flags[0] == 0 ? 1 : 0) : PTX_E_INVALID; }
+
+int ptx_read_labels(ptx_ctx* ctx, uint32_t* labels) {
+    if (!ctx || !labels) return PTX_E_INVALID;
+    cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->st));
+    int64_t off = 0;
+    for (auto& ch : ctx->chunks) {
+        if (!ch.ingested || ch.n_records == 0) continue;
+        CU(cudaMemcpy(labels + off, ch.labels, ch.n_records * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        off += ch.n_records;
+    }
+    return PTX_OK;
+}
+
+int ptx_species_counts(ptx_ctx* ctx, int64_t* counts) {
+    if (!ctx || !counts) return PTX_E_INVALID;
+    if (ctx->sp.empty()) return fail(ctx, PTX_E_STATE, "no ranges");
+    if (ctx->dirty && ctx->comm) return fail(ctx, PTX_E_STATE, "call ptx_finalize first");
+    cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaMemcpy(counts, ctx->comm ? ctx->d_hist_g : ctx->d_hist, ctx->sp.size() * 4 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return PTX_OK;
+}
+
+// profile.rs:311-322, on the host: needs only the first ~1000 rows of the first chunk(s)
+int ptx_equal_length(ptx_ctx* ctx, int* is_equal, int64_t* read_len) {
+    if (!ctx || !is_equal || !read_len) return PTX_E_INVALID;
+    cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->st));
+    std::vector<int64_t> distinct;  // a null read_len (NULL_I64) counts as a value, as in polars' unique()
+    int64_t seen = 0;
+    for (auto& ch : ctx->chunks) {
+        if (seen >= 1000) break;
+        if (!ch.ingested || ch.n_records == 0) continue;
+        size_t text_off = 0, win = 1u << 20;
+        int64_t rec = 0;
+        std::vector<uint8_t> text;
+        std::vector<uint32_t> lab;
+        while (seen < 1000 && rec < ch.n_records && text_off < ch.n) {
+            const size_t want = std::min<size_t>(ch.n - text_off, win);
+            const bool to_end = text_off + want >= ch.n;
+            text.resize(want + 1);
+            CU(cudaMemcpy(text.data(), ch.buf + PRE + text_off, want, cudaMemcpyDeviceToHost));
+            text[want] = '\n';  // terminates an unterminated last line when the window reaches the end of the chunk
+            std::vector<std::pair<size_t, size_t>> lines;  // start, length incl. '\n'
+            size_t i = 0, consumed = 0;
+            while (i < want) {
+                const void* nl = memchr(text.data() + i, '\n', want - i);
+                if (!nl && !to_end) break;  // partial line: refetch from its start
+                const size_t e = nl ? (size_t)((const uint8_t*)nl - text.data()) : want;
+                size_t l = e - i;
+                if (l && text[i + l - 1] == '\r') --l;
+                if (l && text[i] != '@') lines.push_back({i, e - i + 1});
+                i = e + 1;
+                consumed = std::min(i, want);
+            }
+            if (consumed == 0) { win *= 2; continue; }  // one line longer than the window
+            lab.resize(lines.size());
+            if (!lines.empty()) CU(cudaMemcpy(lab.data(), ch.labels + rec, lines.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            for (size_t k = 0; k < lines.size() && seen < 1000; ++k) {
+                if (lab[k] == LABEL_U) continue;
+                RecParse r;
+                parse_record(text.data() + lines[k].first, 0, (uint32_t)lines[k].second, r);  // same column rules as the kernel
+                if (std::find(distinct.begin(), distinct.end(), r.qlen) == distinct.end()) distinct.push_back(r.qlen);
+                ++seen;
+            }
+            rec += (int64_t)lines.size();
+            text_off += consumed;
+        }
+    }
+    *is_equal = distinct.size() == 1 ? 1 : 0;
+    *read_len = distinct.size() == 1 ? distinct[0] : 0;
+    return PTX_OK;
+}
+
+int64_t ptx_species_nodes(const ptx_ctx* ctx, int s) {
+    if (!ctx || s < 0 || s >= (int)ctx->sp.size()) return PTX_E_RANGE;
+    return ctx->sp[s].has_graph || ctx->sp[s].uploaded ? ctx->sp[s].n_nodes : PTX_E_NO_GRAPH;
+}
+int64_t ptx_species_paths(const ptx_ctx* ctx, int s) {
+    if (!ctx || s < 0 || s >= (int)ctx->sp.size()) return PTX_E_RANGE;
+    return ctx->sp[s].has_graph || ctx->sp[s].uploaded ? ctx->sp[s].n_paths : PTX_E_NO_GRAPH;
+}
+int64_t ptx_species_trios(const ptx_ctx* ctx, int s) {
+    if (!ctx || s < 0 || s >= (int)ctx->sp.size()) return PTX_E_RANGE;
+    return ctx->sp[s].has_graph ? ctx->sp[s].n_trios : PTX_E_NO_GRAPH;
+}
+
+int ptx_node_bases(ptx_ctx* ctx, int s, int64_t* out) {
+    int rc = check_results(ctx, s);
+    if (rc) return rc;
+    if (!out) return PTX_E_INVALID;
+    cudaSetDevice(ctx->device);
+    const SpeciesHost& sp = ctx->sp[s];
+    CU(cudaMemcpy(out, ctx->g.bases + sp.node_base, sp.n_nodes * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return PTX_OK;
+}
+
+int ptx_node_cov(ptx_ctx* ctx, int s, uint64_t* out) {
+    int rc = check_results(ctx, s);
+    if (rc) return rc;
+    if (!out) return PTX_E_INVALID;
+    cudaSetDevice(ctx->device);
+    const SpeciesHost& sp = ctx->sp[s];
+    std::vector<uint32_t> tmp((size_t)sp.n_nodes);
+    CU(cudaMemcpy(tmp.data(), ctx->g.cov + sp.node_base, sp.n_nodes * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < sp.n_nodes; ++i) out[i] = tmp[i];
+    return PTX_OK;
+}
+
+int ptx_node_depth(ptx_ctx* ctx, int s, double* out) {
+    int rc = check_results(ctx, s);
+    if (rc) return rc;
+    if (!out) return PTX_E_INVALID;
+    cudaSetDevice(ctx->device);
+    const SpeciesHost& sp = ctx->sp[s];
+    double* d = nullptr;
+    CU(cudaMalloc((void**)&d, sp.n_nodes * sizeof(double)));
+    launch_depth(ctx->g.bases + sp.node_base, ctx->g.len + sp.node_base, nullptr, d, (uint64_t)sp.n_nodes, ctx->st);
+    CU(cudaMemcpyAsync(out, d, sp.n_nodes * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    cudaFree(d);
+    return PTX_OK;
+}
+
+int ptx_trio_bases(ptx_ctx* ctx, int s, int64_t* out) {
+    int rc = check_results(ctx, s);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    const SpeciesHost& sp = ctx->sp[s];
+    if (sp.n_trios == 0) return PTX_OK;
+    if (!out) return PTX_E_INVALID;
+    CU(cudaMemcpy(out, ctx->g.trio_bases + sp.trio_base, sp.n_trios * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return PTX_OK;
+}
+
+int ptx_trio_depth(ptx_ctx* ctx, int s, double* out) {
+    int rc = check_results(ctx, s);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    const SpeciesHost& sp = ctx->sp[s];
+    if (sp.n_trios == 0) return PTX_OK;
+    if (!out) return PTX_E_INVALID;
+    double* d = nullptr;
+    CU(cudaMalloc((void**)&d, sp.n_trios * sizeof(double)));
+    launch_depth(ctx->g.trio_bases + sp.trio_base, nullptr, ctx->g.trio_len + sp.trio_base, d, (uint64_t)sp.n_trios, ctx->st);
+    CU(cudaMemcpyAsync(out, d, sp.n_trios * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    cudaFree(d);
+    return PTX_OK;
+}
+
+int ptx_trio_table(ptx_ctx* ctx, int s, uint64_t* keys3, int64_t* len, uint32_t* owner) {
+    int rc = check_species(ctx, s, true);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    const SpeciesHost& sp = ctx->sp[s];
+    const int64_t T = sp.n_trios;
+    if (T == 0) return PTX_OK;
+    if (keys3) {
+        std::vector<uint32_t> k((size_t)T * 3);
+        CU(cudaMemcpy(k.data(), ctx->g.trio_key + 3 * sp.trio_base, T * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < T * 3; ++i) keys3[i] = (uint64_t)k[i] - (uint64_t)sp.node_base;
+    }
+    if (len) CU(cudaMemcpy(len, ctx->g.trio_len + sp.trio_base, T * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (owner) {
+        CU(cudaMemcpy(owner, ctx->g.trio_owner + sp.trio_base, T * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < T; ++i) owner[i] -= (uint32_t)sp.hap_base;
+    }
+    return PTX_OK;
+}
+
+int ptx_path_sums(ptx_ctx* ctx, int s, int64_t* sum_cov, int64_t* sum_len) {
+    int rc = check_results(ctx, s);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    const SpeciesHost& sp = ctx->sp[s];
+    if (sp.n_paths == 0) return PTX_OK;
+    if (sum_cov) CU(cudaMemcpy(sum_cov, ctx->g.path_cov_sum + sp.hap_base, sp.n_paths * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (sum_len) CU(cudaMemcpy(sum_len, ctx->g.path_len_sum + sp.hap_base, sp.n_paths * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return PTX_OK;
+}
+
+int ptx_hap_trio_counts(ptx_ctx* ctx, int s, int64_t* U, int64_t* nz) {
+    int rc = check_results(ctx, s);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    const SpeciesHost& sp = ctx->sp[s];
+    if (sp.n_paths == 0) return PTX_OK;
+    if (U) {
+        std::vector<uint64_t> ts((size_t)sp.n_paths + 1, 0);
+        if (ctx->g.T > 0) CU(cudaMemcpy(ts.data(), ctx->g.trio_start + sp.hap_base, (sp.n_paths + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        for (int64_t h = 0; h < sp.n_paths; ++h) U[h] = (int64_t)(ts[h + 1] - ts[h]);
+    }
+    if (nz) CU(cudaMemcpy(nz, ctx->g.hap_nz + sp.hap_base, sp.n_paths * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return PTX_OK;
+}
+
+int ptx_filter_gaf(ptx_ctx* ctx, const uint8_t*, size_t, uint64_t*, int64_t, int64_t*) {
+    return fail(ctx, PTX_E_UNSUPPORTED, "ptx_filter_gaf: not built yet (SURVEY.md section 8 row a11 / K10)");
+}
+
+int ptx_comm_unique_id(void* out128) {
+    if (!out128) return PTX_E_INVALID;
+    if (!g_nccl.load()) return PTX_E_NCCL;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != 0) return PTX_E_NCCL;
+    memcpy(out128, &id, sizeof id);
+    return PTX_OK;
+}
+
+int ptx_comm_init(ptx_ctx* ctx, int n_ranks, int rank, const void* id128) {
+    if (!ctx || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(ctx, PTX_E_INVALID, "ptx_comm_init: bad arguments");
+    if (!g_nccl.load()) return fail(ctx, PTX_E_NCCL, "libnccl.so.2 not found");
+    cudaSetDevice(ctx->device);
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    int rc = nccl_check(ctx, g_nccl.CommInitRank(&ctx->comm, n_ranks, id, rank), "ncclCommInitRank");
+    if (rc) return rc;
+    ctx->n_ranks = n_ranks;
+    ctx->rank = rank;
+    return PTX_OK;
+}
+
+int ptx_timing(ptx_ctx* ctx, double* ingest_ms, double* finalize_ms, int64_t* kernel_launches) {
+    if (!ctx) return PTX_E_INVALID;
+    cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->st));
+    if (ingest_ms) *ingest_ms = ev_sum(ctx->ev_ingest);
+    if (finalize_ms) *finalize_ms = ev_sum(ctx->ev_final);
+    if (kernel_launches) *kernel_launches = kernel_launch_count();
+    return PTX_OK;
+}
+
+int ptx_stats_json(ptx_ctx* ctx, char* buf, size_t cap) {
+    if (!ctx || !buf || cap == 0) return PTX_E_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    size_t text = 0;
+    for (auto& ch : ctx->chunks) text += ch.n;
+    snprintf(buf, cap,
+             "{\"records\": %lld, \"chunks\": %zu, \"text_bytes\": %zu, \"nodes\": %lld, \"paths\": %lld, \"path_steps\": %lld, "
+             "\"unique_trios\": %lld, \"bit_words\": %llu, \"id_set_slots\": %llu, \"ids_unique\": %d, \"mixed_groups\": %d, "
+             "\"ingest_ms\": %.4f, \"finalize_ms\": %.4f, \"kernel_launches\": %lld, \"ranks\": %d}",
+             (long long)ctx->total_records, ctx->chunks.size(), text, (long long)ctx->g.N, (long long)ctx->g.Htot, (long long)ctx->g.P,
+             (long long)ctx->g.T, (unsigned long long)ctx->g.n_bit_words, (unsigned long long)ctx->ds_cap, ctx->h_flags[0] == 0 ? 1 : 0,
+             ctx->h_flags[1] != 0 ? 1 : 0, ev_sum(ctx->ev_ingest), ev_sum(ctx->ev_final), (long long)kernel_launch_count(), ctx->n_ranks);
+    return PTX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+// Internal structs shared by ptx_kernels.cu (device code + launchers) and ptx_api.cu
+// (context, C ABI).  Not installed; the public surface is include/pantax_gpu.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptx_core.cuh"
+
+namespace ptx {
+
+// ---- tile geometry of the GAF scan -------------------------------------------------
+// A chunk buffer is  [PRE '\n' bytes][text, whole lines][ '\n' padding to n_tiles*TILE + OVER ].
+// Tile t owns the newlines in text[t*TILE, (t+1)*TILE); the record FOLLOWING an owned
+// newline belongs to the tile, so a record starts in (t*TILE, (t+1)*TILE].  The first
+// record of the chunk (text[0], preceded by the PRE padding) belongs to tile 0.
+// The tile is staged in shared memory as text[t*TILE, t*TILE + STAGE).
+constexpr uint32_t TILE = 32768;
+constexpr uint32_t OVER = 2048;
+constexpr uint32_t STAGE = TILE + OVER;  // multiple of 16
+constexpr uint32_t PRE = 256;            // keeps `text` 256-byte aligned inside a cudaMalloc'ed buffer
+constexpr int INGEST_THREADS = 256;
+constexpr uint32_t REC_CAP = 4096;  // record starts kept in smem per round
+
+// mode flags of the ingest kernel
+constexpr int MODE_CLASSIFY = 1;  // labels, species counts, read-id set insert
+constexpr int MODE_COVER = 2;     // node coverage / trio accumulation
+constexpr int MODE_KEEPMASK = 4;  // skip reads whose id group is DS_MIXED (replay pass)
+
+struct GraphDev {
+    // nodes (all uploaded species concatenated; g = node_base[s] + local id)
+    int64_t N = 0;
+    uint32_t* len = nullptr;          // [N]
+    uint64_t* bit_off = nullptr;      // [N+1] exclusive prefix of len
+    unsigned long long* bases = nullptr;  // [N] int64 accumulators
+    uint8_t* full = nullptr;          // [N] node fully covered by some read
+    uint32_t* bits = nullptr;         // [ceil(total_bits/32)+1] packed per-base covered bitmap
+    uint64_t n_bit_words = 0;
+    uint32_t* cov = nullptr;          // [N] covered bases (finalize)
+    // paths
+    int64_t Htot = 0, P = 0;          // paths, total steps
+    uint32_t* pnode = nullptr;        // [P] global node idx, bit31 = node already seen earlier in this path
+    uint64_t* poff = nullptr;         // [Htot+1]
+    unsigned long long* path_len_sum = nullptr;  // [Htot] sum len over distinct nodes
+    unsigned long long* path_cov_sum = nullptr;  // [Htot] sum cov over distinct nodes (finalize)
+    // unique trios
+    int64_t T = 0;
+    uint32_t* trio_key = nullptr;     // [T*3] canonical global node idx
+    int64_t* trio_len = nullptr;      // [T]
+    uint32_t* trio_owner = nullptr;   // [T] global hap idx
+    unsigned long long* trio_bases = nullptr;  // [T]
+    uint64_t* trio_start = nullptr;   // [Htot+1] first trio idx of each hap
+    unsigned long long* hap_nz = nullptr;  // [Htot]
+    uint4* tt = nullptr;              // probe table {a,b,c,idx}, a == TT_EMPTY: empty
+    uint32_t tt_mask = 0;
+    uint32_t* trio_mid = nullptr;     // [ceil(N/32)] bit g: g is the middle node of some unique trio
+};
+
+struct IngestArgs {
+    const uint8_t* text;   // chunk text (buffer + PRE)
+    uint64_t n_bytes;      // text bytes (whole lines)
+    uint32_t n_tiles;
+    const uint32_t* tile_base;  // [n_tiles] exclusive record prefix within the chunk (MODE_CLASSIFY)
+    uint32_t* labels;           // [chunk records]
+    RangesView ranges;
+    unsigned long long* hist;   // [S*4]
+    ulonglong2* ds;             // read-id set slots
+    uint32_t ds_shift;          // 64 - log2(capacity)
+    uint64_t ds_mask;
+    uint32_t* flags;            // [0] dup id seen, [1] mixed-species id group seen
+    uint32_t* err;              // [S] bit0: profile.rs:854 tripped
+    // coverage
+    const uint32_t* len;
+    const uint64_t* bit_off;
+    unsigned long long* bases;
+    uint8_t* full;
+    uint32_t* bits;
+    const uint4* tt;
+    uint32_t tt_mask;
+    const uint32_t* trio_mid;
+    unsigned long long* trio_bases;
+};
+
+// launchers (ptx_kernels.cu); all asynchronous on `st`
+void launch_count_records(const uint8_t* text, uint64_t n_bytes, uint32_t n_tiles, uint32_t* tile_count, cudaStream_t st);
+void launch_scan_tiles(const uint32_t* tile_count, uint32_t* tile_base, uint32_t n_tiles, uint64_t* total, cudaStream_t st);
+void launch_ingest(const IngestArgs& a, int mode, cudaStream_t st);
+void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2* new_slots, uint32_t new_shift,
+                      uint64_t new_mask, cudaStream_t st);
+void launch_fill_u8(uint8_t* p, uint8_t v, uint64_t n, cudaStream_t st);
+
+// graph commit
+void launch_mark_path_dups(uint32_t* pnode, const uint64_t* poff, const uint32_t* round_paths, uint32_t n_round_paths,
+                           uint64_t max_len, uint32_t* stamp, cudaStream_t st);
+void launch_path_len_sum(const uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, const uint32_t* len,
+                         unsigned long long* out, cudaStream_t st);
+void launch_trio_count(const uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, uint4* keys, uint32_t* cnt,
+                       uint32_t mask, cudaStream_t st);
+void launch_trio_flag(const uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, const uint4* keys,
+                      const uint32_t* cnt, uint32_t mask, uint32_t* flag, cudaStream_t st);
+// exclusive scan of n uint32 -> uint64 prefix (out[n] = total); scratch >= (n/2048+2) uint64
+void launch_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* scratch, cudaStream_t st);
+void launch_trio_emit(const uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, const uint32_t* flag,
+                      const uint64_t* scan, const uint32_t* len, uint32_t* trio_key, int64_t* trio_len,
+                      uint32_t* trio_owner, uint4* tt, uint32_t tt_mask, uint32_t* trio_mid, uint64_t* trio_start,
+                      cudaStream_t st);
+
+// finalize
+void launch_cov(const GraphDev& g, cudaStream_t st);
+void launch_path_cov_sum(const GraphDev& g, cudaStream_t st);
+void launch_hap_nz(const GraphDev& g, cudaStream_t st);
+void launch_depth(const unsigned long long* num, const uint32_t* den32, const int64_t* den64, double* out, uint64_t n,
+                  cudaStream_t st);
+// OR-merge a peer's bitmap / full flags into ours (multi-GPU finalize)
+void launch_or_words(uint32_t* dst, const uint32_t* src, uint64_t n_words, cudaStream_t st);
+
+int64_t kernel_launch_count();
+
+}  // namespace ptx

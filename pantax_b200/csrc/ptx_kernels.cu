@@ -1,0 +1,841 @@
+// sm_100a kernels of the PanTax alignment-to-abundance hot path.
+//
+//   K1  k_count_records / k_scan_tiles  newline index: records per 32 KB tile -> record numbering
+//   K2+ k_ingest<MODE>                  one CTA per tile: TMA bulk copy of the tile's text into
+//                                       shared memory, record-start compaction, then one thread per
+//                                       GAF record: column split + integer parse + walk decode
+//                                       (rcls.rs:119-146,237-258), species label, species counts
+//                                       (profile.rs:208-297), read-id set insert (profile.rs:361-437)
+//                                       and the node-coverage scatter (profile.rs:787-919)
+//   K7  k_trio_*                        unique-trio table build (profile.rs:658-740)
+//   K6  k_cov                           covered bases per node (profile.rs:1018-1023)
+//   K9  k_path_cov_sum / k_hap_nz / k_depth   per-path / per-hap statistics (profile.rs:980-1016,
+//                                       1112-1135, 2705-2729)
+// All HBM-bound integer/byte work: no tensor cores.  See DESIGN.md for the data layout and the
+// algorithmic bytes each kernel is measured against.
+#include <atomic>
+
+#include "ptx_internal.h"
+
+namespace ptx {
+
+static std::atomic<int64_t> g_launches{0};
+int64_t kernel_launch_count() { return g_launches.load(); }
+#define PTX_LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+// =====================================================================================
+// PTX helpers: mbarrier + TMA 1-D bulk copy (global -> shared), 128-bit CAS
+// =====================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ ulonglong2 atomic_cas128(ulonglong2* addr, ulonglong2 cmp, ulonglong2 val) {
+    ulonglong2 old;
+    asm volatile(
+        "{\n"
+        ".reg .b128 c, v, o;\n"
+        "mov.b128 c, {%2, %3};\n"
+        "mov.b128 v, {%4, %5};\n"
+        "atom.relaxed.gpu.global.cas.b128 o, [%6], c, v;\n"
+        "mov.b128 {%0, %1}, o;\n"
+        "}\n"
+        : "=l"(old.x), "=l"(old.y)
+        : "l"(cmp.x), "l"(cmp.y), "l"(val.x), "l"(val.y), "l"(addr)
+        : "memory");
+    return old;
+}
+__device__ __forceinline__ ulonglong2 ld128(const ulonglong2* p) {
+    ulonglong2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+// 0x80 in every byte of w that equals '\n'
+__device__ __forceinline__ uint32_t nl_mask4(uint32_t w) {
+    uint32_t y = w ^ 0x0a0a0a0au;
+    return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y) & 0x80808080u;
+}
+// Does a GAF record start at b[q]?  (not an empty line, not an '@' comment; rcls.rs:123)
+__device__ __forceinline__ bool valid_first(const uint8_t* b, uint32_t q) {
+    uint8_t c = b[q];
+    if (c == '\n' || c == '@') return false;
+    if (c == '\r' && b[q + 1] == '\n') return false;
+    return true;
+}
+
+// =====================================================================================
+// K1: records per tile
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_count_records(const uint8_t* __restrict__ text, uint32_t* __restrict__ tile_count) {
+    const uint64_t t0 = (uint64_t)blockIdx.x * TILE;
+    const uint8_t* tb = text + t0;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < (int)(TILE / 16 / 256); ++k) {
+        uint32_t v = k * 256 + threadIdx.x;
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(tb) + v);
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t m = nl_mask4(w[i]);
+            while (m) {
+                uint32_t byte = (__ffs(m) - 1) >> 3;
+                m &= m - 1;
+                cnt += valid_first(tb, v * 16 + i * 4 + byte + 1) ? 1u : 0u;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt += valid_first(tb, 0) ? 1u : 0u;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    __shared__ uint32_t ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int i = 0; i < 8; ++i) s += ws[i];
+        tile_count[blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
+                                                     uint64_t* __restrict__ total) {
+    __shared__ uint32_t ws[32];
+    __shared__ uint64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < n ? in[i] : 0;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if ((threadIdx.x & 31) >= d) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t s = ws[threadIdx.x];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, s, d);
+                if (threadIdx.x >= d) s += y;
+            }
+            ws[threadIdx.x] = s;
+        }
+        __syncthreads();
+        uint64_t carry = carry_s;
+        uint32_t wbase = (threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0;
+        if (i < n) out[i] = (uint32_t)(carry + wbase + x - v);
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + wbase + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry_s;
+}
+
+// =====================================================================================
+// read-id set (open addressing, 16-byte slots {hash.lo, hash.hi<<32 | state}, 128-bit CAS)
+// =====================================================================================
+__device__ __forceinline__ uint64_t ds_home(const IdHash& h, uint32_t shift) {
+    return ((h.lo ^ ((uint64_t)h.hi << 17)) * 0x9E3779B97F4A7C15ull) >> shift;
+}
+
+// profile.rs:369-378 (uniqueness over all non-U rows) + :406-437 (species set per id group,
+// over coverage-eligible rows only).
+__device__ __forceinline__ void ds_insert(ulonglong2* slots, uint32_t shift, uint64_t mask, const IdHash& h, bool eligible,
+                                          uint32_t label, uint32_t* flags) {
+    const uint64_t hi_part = (uint64_t)h.hi << 32;
+    const ulonglong2 mine = make_ulonglong2(h.lo, hi_part | (eligible ? label : DS_NONE));
+    uint64_t i = ds_home(h, shift);
+    for (;;) {
+        ulonglong2 cur = ld128(slots + i);
+        if (cur.x == 0ull && cur.y == 0ull) {
+            cur = atomic_cas128(slots + i, make_ulonglong2(0ull, 0ull), mine);
+            if (cur.x == 0ull && cur.y == 0ull) return;  // inserted
+        }
+        if (cur.x == h.lo && (cur.y >> 32) == (uint64_t)h.hi) {  // same read id seen before
+            if (flags[0] == 0u) atomicOr(flags + 0, 1u);
+            if (!eligible) return;
+            for (;;) {
+                uint32_t st = (uint32_t)cur.y;
+                uint32_t nst;
+                if (st == DS_NONE) nst = label;
+                else if (st == label || st == DS_MIXED) return;
+                else nst = DS_MIXED;
+                ulonglong2 want = make_ulonglong2(cur.x, hi_part | nst);
+                ulonglong2 prev = atomic_cas128(slots + i, cur, want);
+                if (prev.x == cur.x && prev.y == cur.y) {
+                    if (nst == DS_MIXED) atomicOr(flags + 1, 1u);
+                    return;
+                }
+                cur = prev;
+            }
+        }
+        i = (i + 1) & mask;
+    }
+}
+
+__device__ __forceinline__ uint32_t ds_lookup(const ulonglong2* slots, uint32_t shift, uint64_t mask, const IdHash& h) {
+    uint64_t i = ds_home(h, shift);
+    for (;;) {
+        ulonglong2 cur = ld128(slots + i);
+        if (cur.x == 0ull && cur.y == 0ull) return DS_NONE;
+        if (cur.x == h.lo && (cur.y >> 32) == (uint64_t)h.hi) return (uint32_t)cur.y;
+        i = (i + 1) & mask;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ds_rehash(const ulonglong2* __restrict__ old_slots, uint64_t old_cap, ulonglong2* new_slots,
+                                                   uint32_t new_shift, uint64_t new_mask) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < old_cap; k += (uint64_t)gridDim.x * blockDim.x) {
+        ulonglong2 e = old_slots[k];
+        if (e.x == 0ull && e.y == 0ull) continue;
+        IdHash h;
+        h.lo = e.x;
+        h.hi = (uint32_t)(e.y >> 32);
+        uint64_t i = ds_home(h, new_shift);
+        for (;;) {
+            ulonglong2 cur = atomic_cas128(new_slots + i, make_ulonglong2(0ull, 0ull), e);
+            if (cur.x == 0ull && cur.y == 0ull) break;
+            i = (i + 1) & new_mask;
+        }
+    }
+}
+
+// =====================================================================================
+// K2..K6/K8: the fused ingest kernel
+// =====================================================================================
+struct DevSink {
+    const IngestArgs& a;
+    __device__ __forceinline__ uint32_t len(uint32_t g) const { return __ldg(a.len + g); }
+    __device__ __forceinline__ void add_bases(uint32_t g, int64_t v) { atomicAdd(a.bases + g, (unsigned long long)v); }
+    __device__ __forceinline__ void set_bits(uint32_t g, int64_t lo, int64_t hi, uint32_t ln) {
+        if (lo == 0 && hi == (int64_t)ln) {  // whole node: one idempotent byte store
+            a.full[g] = 1;
+            return;
+        }
+        const uint64_t base = __ldg(a.bit_off + g);
+        const uint64_t b0 = base + (uint64_t)lo, b1 = base + (uint64_t)hi - 1;  // inclusive last bit
+        const uint64_t w0 = b0 >> 5, w1 = b1 >> 5;
+        const uint32_t m0 = 0xFFFFFFFFu << (b0 & 31u), m1 = 0xFFFFFFFFu >> (31u - (uint32_t)(b1 & 31u));
+        if (w0 == w1) {
+            atomicOr(a.bits + w0, m0 & m1);
+        } else {
+            atomicOr(a.bits + w0, m0);
+            for (uint64_t w = w0 + 1; w < w1; ++w) atomicOr(a.bits + w, 0xFFFFFFFFu);
+            atomicOr(a.bits + w1, m1);
+        }
+    }
+    __device__ __forceinline__ void trio(uint32_t x, uint32_t y, uint32_t z, int64_t s) {
+        if (a.tt == nullptr) return;
+        if (!((__ldg(a.trio_mid + (y >> 5)) >> (y & 31u)) & 1u)) return;  // y is not the middle of any unique trio
+        const uint32_t lo = x < z ? x : z, hi = x < z ? z : x;            // profile.rs:672-678 / :902-904
+        uint32_t i = trio_hash(lo, y, hi) & a.tt_mask;
+        for (;;) {
+            uint4 e = __ldg(a.tt + i);
+            if (e.x == TT_EMPTY) return;
+            if (e.x == lo && e.y == y && e.z == hi) {
+                atomicAdd(a.trio_bases + e.w, (unsigned long long)s);
+                return;
+            }
+            i = (i + 1) & a.tt_mask;
+        }
+    }
+    __device__ __forceinline__ void error_start_gt_len(uint32_t label) { atomicOr(a.err + label, 1u); }
+};
+
+// rare path: the record did not fit in the staged window - parse it from global memory
+__device__ __noinline__ bool parse_record_global(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r) {
+    return parse_record(b, p, lim, r);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest(const IngestArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* stage = smem;
+    uint16_t* rec_start = reinterpret_cast<uint16_t*>(smem + STAGE);
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t warp_tot[INGEST_THREADS / 32];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint64_t t0 = (uint64_t)blockIdx.x * TILE;
+    const uint8_t* gtile = a.text + t0;
+
+    // ---- stage the tile: one TMA bulk copy, completion on an mbarrier
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&mbar, STAGE);
+        bulk_g2s(stage, gtile, STAGE, &mbar);
+    }
+    mbar_wait(&mbar, 0);
+
+    // ---- record starts: warp w scans stage[w*4096, +4096) as 8 rows of 32 x 16 B
+    constexpr int ROWS = TILE / (INGEST_THREADS / 32) / 512;  // 8
+    uint32_t c[ROWS];
+    const uint32_t wbase_byte = warp * (TILE / (INGEST_THREADS / 32));
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        const uint32_t off = wbase_byte + (uint32_t)j * 512u + lane * 16u;
+        uint4 q = *reinterpret_cast<const uint4*>(stage + off);
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t n = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t m = nl_mask4(w[i]);
+            while (m) {
+                uint32_t byte = (__ffs(m) - 1) >> 3;
+                m &= m - 1;
+                n += valid_first(stage, off + i * 4 + byte + 1) ? 1u : 0u;
+            }
+        }
+        c[j] = n;
+    }
+    const bool first_rec = (blockIdx.x == 0 && tid == 0 && valid_first(stage, 0));
+    if (first_rec) c[0] += 1;
+    // exclusive position of (row j, lane) inside the warp, rows first
+    uint32_t pre[ROWS];
+    uint32_t run = 0;
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        uint32_t x = c[j];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= (uint32_t)d) x += y;
+        }
+        pre[j] = run + x - c[j];
+        run += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0) warp_tot[warp] = run;
+    __syncthreads();
+    uint32_t my_base = 0, n_rec = 0;
+#pragma unroll
+    for (int w = 0; w < INGEST_THREADS / 32; ++w) {
+        uint32_t t = warp_tot[w];
+        if ((uint32_t)w < warp) my_base += t;
+        n_rec += t;
+    }
+    const uint32_t rec_base = (MODE & MODE_CLASSIFY) ? a.tile_base[blockIdx.x] : 0u;
+    const uint32_t glim = (uint32_t)min((uint64_t)0xFFFF0000ull, (uint64_t)a.n_tiles * TILE + OVER - t0);
+    const RangesView& R = a.ranges;
+
+    for (uint32_t round = 0; round < n_rec; round += REC_CAP) {
+        // ---- compact this round's record starts into shared memory
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+            if (c[j] == 0) continue;
+            uint32_t idx = my_base + pre[j];
+            if (j == 0 && first_rec) {
+                if (idx >= round && idx < round + REC_CAP) rec_start[idx - round] = 0;
+                ++idx;
+            }
+            const uint32_t off = wbase_byte + (uint32_t)j * 512u + lane * 16u;
+            uint4 q = *reinterpret_cast<const uint4*>(stage + off);
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint32_t m = nl_mask4(w[i]);
+                while (m) {
+                    uint32_t byte = (__ffs(m) - 1) >> 3;
+                    m &= m - 1;
+                    uint32_t qpos = off + i * 4 + byte + 1;
+                    if (valid_first(stage, qpos)) {
+                        if (idx >= round && idx < round + REC_CAP) rec_start[idx - round] = (uint16_t)qpos;
+                        ++idx;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t n_round = min(REC_CAP, n_rec - round);
+
+        // ---- one thread per record
+        for (uint32_t k0 = 0; k0 < n_round; k0 += INGEST_THREADS) {
+            const uint32_t k = k0 + tid;
+            const bool has = k < n_round;
+            RecParse r;
+            uint32_t label = LABEL_U;
+            const uint8_t* b = stage;
+            if (has) {
+                const uint32_t p = rec_start[k];
+                if (!parse_record(stage, p, STAGE, r)) {
+                    b = gtile;
+                    parse_record_global(gtile, p, glim, r);
+                }
+                label = classify(R, r.W ? r.vmin : -1, r.W ? r.vmax : -1);
+                if (MODE & MODE_CLASSIFY) a.labels[rec_base + round + k] = label;
+            }
+            if (MODE & MODE_CLASSIFY) {
+                // ---- species counts (profile.rs:219-232, 264-277), warp-aggregated when the warp is one species
+                const bool cnt = has && label != LABEL_U;
+                const unsigned mm = __ballot_sync(0xffffffffu, cnt);
+                if (mm) {
+                    const int leader = __ffs(mm) - 1;
+                    const uint32_t lab0 = __shfl_sync(0xffffffffu, label, leader);
+                    const bool uniform = __all_sync(0xffffffffu, !cnt || label == lab0);
+                    const bool mq_ok = cnt && r.mapq != NULL_I64 && r.mapq >= 3 && r.mapq <= 60;
+                    const uint32_t lm = mq_ok ? 1u : 0u;
+                    const uint32_t uq = (mq_ok && r.mapq == 60) ? 1u : 0u;
+                    const unsigned long long ql = (cnt && r.qlen != NULL_I64) ? (unsigned long long)r.qlen : 0ull;
+                    if (uniform) {
+                        uint32_t n1 = __popc(mm);
+                        uint32_t n3 = __reduce_add_sync(0xffffffffu, lm);
+                        uint32_t n4 = __reduce_add_sync(0xffffffffu, uq);
+                        unsigned long long s = ql;
+#pragma unroll
+                        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+                        if ((int)lane == leader) {
+                            unsigned long long* hp = a.hist + 4ull * lab0;
+                            atomicAdd(hp + 0, (unsigned long long)n1);
+                            atomicAdd(hp + 1, s);
+                            if (n3) atomicAdd(hp + 2, (unsigned long long)n3);
+                            if (n4) atomicAdd(hp + 3, (unsigned long long)n4);
+                        }
+                    } else if (cnt) {
+                        unsigned long long* hp = a.hist + 4ull * label;
+                        atomicAdd(hp + 0, 1ull);
+                        atomicAdd(hp + 1, ql);
+                        if (lm) atomicAdd(hp + 2, 1ull);
+                        if (uq) atomicAdd(hp + 3, 1ull);
+                    }
+                }
+            }
+            if (has && label != LABEL_U) {
+                const bool eligible = !r.path_null && r.c7 != NULL_I64 && r.c8 != NULL_I64 && r.c9 != NULL_I64;  // profile.rs:380-399
+                if (MODE & MODE_CLASSIFY) ds_insert(a.ds, a.ds_shift, a.ds_mask, r.h, eligible, label, a.flags);
+                if ((MODE & MODE_COVER) && eligible) {
+                    const int64_t nb = R.node_base[label];
+                    bool keep = nb >= 0;
+                    if ((MODE & MODE_KEEPMASK) && keep) keep = ds_lookup(a.ds, a.ds_shift, a.ds_mask, r.h) != DS_MIXED;  // :415-416
+                    if (keep) {
+                        DevSink sink{a};
+                        cover_record(b, r, label, R.start[label], nb, sink);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =====================================================================================
+// K7: unique trio table (profile.rs:658-740)
+// =====================================================================================
+__device__ __forceinline__ int64_t path_of_step(const uint64_t* __restrict__ poff, int64_t Htot, uint64_t k) {
+    int64_t a = 0, b = Htot;  // last h with poff[h] <= k
+    while (a < b) {
+        int64_t m = (a + b) >> 1;
+        if (poff[m] <= k) a = m + 1; else b = m;
+    }
+    return a - 1;
+}
+
+// One launch handles at most one path per species, so the stamps of different paths never mix.
+__global__ void __launch_bounds__(256) k_mark_path_dups(uint32_t* pnode, const uint64_t* __restrict__ poff,
+                                                        const uint32_t* __restrict__ round_paths, uint32_t* stamp) {
+    const uint32_t h = round_paths[blockIdx.y];
+    const uint64_t s = poff[h], e = poff[h + 1];
+    for (uint64_t k = s + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < e; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t g = pnode[k] & 0x7FFFFFFFu;
+        const uint32_t old = atomicExch(stamp + g, h + 1u);
+        if (old == h + 1u) pnode[k] = g | 0x80000000u;  // node already met in this path
+    }
+}
+
+__global__ void __launch_bounds__(256) k_path_len_sum(const uint32_t* __restrict__ pnode, const uint64_t* __restrict__ poff, int64_t Htot,
+                                                      int64_t P, const uint32_t* __restrict__ val, unsigned long long* out) {
+    // block handles 256*8 consecutive steps; per-path partial sums via a warp-aggregated atomic
+    const uint64_t k0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8ull;
+    if (k0 >= (uint64_t)P) return;
+    int64_t h = path_of_step(poff, Htot, k0);
+    unsigned long long acc = 0;
+    for (int i = 0; i < 8; ++i) {
+        const uint64_t k = k0 + i;
+        if (k >= (uint64_t)P) break;
+        while (k >= poff[h + 1]) {
+            if (acc) atomicAdd(out + h, acc);
+            acc = 0;
+            ++h;
+        }
+        const uint32_t g = pnode[k];
+        if (!(g & 0x80000000u)) acc += val[g];
+    }
+    if (acc) atomicAdd(out + h, acc);
+}
+
+__device__ __forceinline__ bool window_at(const uint32_t* __restrict__ pnode, const uint64_t* __restrict__ poff, int64_t Htot, uint64_t k,
+                                          int64_t& h, uint32_t& lo, uint32_t& mid, uint32_t& hi) {
+    h = path_of_step(poff, Htot, k);
+    if (k + 2 >= poff[h + 1]) return false;
+    const uint32_t x = pnode[k] & 0x7FFFFFFFu, y = pnode[k + 1] & 0x7FFFFFFFu, z = pnode[k + 2] & 0x7FFFFFFFu;
+    lo = x < z ? x : z;
+    hi = x < z ? z : x;
+    mid = y;
+    return true;
+}
+
+__device__ __forceinline__ uint4 ld_key(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// claim-or-find the slot of key (lo,mid,hi); empty slot = {TT_EMPTY,...}
+__device__ __forceinline__ uint32_t key_slot(uint4* keys, uint32_t mask, uint32_t lo, uint32_t mid, uint32_t hi, bool insert) {
+    uint32_t i = trio_hash(lo, mid, hi) & mask;
+    const ulonglong2 empty = make_ulonglong2(0xFFFFFFFFFFFFFFFFull, 0xFFFFFFFFFFFFFFFFull);
+    const ulonglong2 mine = make_ulonglong2(((uint64_t)mid << 32) | lo, (uint64_t)hi);
+    for (;;) {
+        uint4 e = ld_key(keys + i);
+        if (e.x == TT_EMPTY) {
+            if (!insert) return 0xFFFFFFFFu;
+            ulonglong2 prev = atomic_cas128(reinterpret_cast<ulonglong2*>(keys + i), empty, mine);
+            if (prev.x == empty.x && prev.y == empty.y) return i;
+            e.x = (uint32_t)prev.x;
+            e.y = (uint32_t)(prev.x >> 32);
+            e.z = (uint32_t)prev.y;
+        }
+        if (e.x == lo && e.y == mid && e.z == hi) return i;
+        i = (i + 1) & mask;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_trio_count(const uint32_t* __restrict__ pnode, const uint64_t* __restrict__ poff, int64_t Htot,
+                                                    int64_t P, uint4* keys, uint32_t* cnt, uint32_t mask) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < (uint64_t)P; k += (uint64_t)gridDim.x * blockDim.x) {
+        int64_t h;
+        uint32_t lo, mid, hi;
+        if (!window_at(pnode, poff, Htot, k, h, lo, mid, hi)) continue;
+        const uint32_t s = key_slot(keys, mask, lo, mid, hi, true);
+        atomicAdd(cnt + s, 1u);  // occurrences with multiplicity over all paths (profile.rs:689-702)
+    }
+}
+
+__global__ void __launch_bounds__(256) k_trio_flag(const uint32_t* __restrict__ pnode, const uint64_t* __restrict__ poff, int64_t Htot,
+                                                   int64_t P, uint4* keys, const uint32_t* __restrict__ cnt, uint32_t mask,
+                                                   uint32_t* __restrict__ flag) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < (uint64_t)P; k += (uint64_t)gridDim.x * blockDim.x) {
+        int64_t h;
+        uint32_t lo, mid, hi;
+        uint32_t f = 0;
+        if (window_at(pnode, poff, Htot, k, h, lo, mid, hi)) {
+            const uint32_t s = key_slot(keys, mask, lo, mid, hi, false);
+            f = (s != 0xFFFFFFFFu && cnt[s] == 1u) ? 1u : 0u;  // profile.rs:709
+        }
+        flag[k] = f;
+    }
+}
+
+// ---- exclusive scan uint32 -> uint64 (three kernels; block = 1024 threads x 2 items)
+constexpr int SCAN_ITEMS = 2048;
+__global__ void __launch_bounds__(1024) k_scan_block_sums(const uint32_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ bsum) {
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_ITEMS;
+    uint32_t v = 0;
+    for (int i = 0; i < 2; ++i) {
+        uint64_t k = base + threadIdx.x + i * 1024;
+        if (k < n) v += in[k];
+    }
+    v = __reduce_add_sync(0xffffffffu, v);
+    __shared__ uint32_t ws[32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t s = __reduce_add_sync(0xffffffffu, ws[threadIdx.x]);
+        if (threadIdx.x == 0) bsum[blockIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(1024) k_scan_bsums(uint64_t* bsum, uint64_t nb) {
+    // single block: exclusive scan of nb uint64 in place, bsum[nb] = total
+    __shared__ uint64_t ws[32];
+    __shared__ uint64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < nb; base += 1024) {
+        uint64_t i = base + threadIdx.x;
+        uint64_t v = i < nb ? bsum[i] : 0;
+        uint64_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if ((threadIdx.x & 31) >= d) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint64_t s = ws[threadIdx.x];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint64_t y = __shfl_up_sync(0xffffffffu, s, d);
+                if (threadIdx.x >= d) s += y;
+            }
+            ws[threadIdx.x] = s;
+        }
+        __syncthreads();
+        uint64_t carry = carry_s;
+        uint64_t wbase = (threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0;
+        if (i < nb) bsum[i] = carry + wbase + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + wbase + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bsum[nb] = carry_s;
+}
+__global__ void __launch_bounds__(1024) k_scan_final(const uint32_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ bsum,
+                                                     uint64_t nb, uint64_t* __restrict__ out) {
+    // block-local exclusive scan of 2048 items (thread t owns items 2t, 2t+1) + block offset
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_ITEMS;
+    const uint64_t k0 = base + 2ull * threadIdx.x;
+    uint32_t a = k0 < n ? in[k0] : 0, b = (k0 + 1) < n ? in[k0 + 1] : 0;
+    uint32_t v = a + b, x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if ((threadIdx.x & 31) >= d) x += y;
+    }
+    __shared__ uint32_t ws[32];
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t s = ws[threadIdx.x];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, s, d);
+            if (threadIdx.x >= d) s += y;
+        }
+        ws[threadIdx.x] = s;
+    }
+    __syncthreads();
+    const uint32_t wbase = (threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0;
+    const uint64_t ex = bsum[blockIdx.x] + wbase + x - v;
+    if (k0 < n) out[k0] = ex;
+    if (k0 + 1 < n) out[k0 + 1] = ex + a;
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = bsum[nb];
+}
+
+__global__ void __launch_bounds__(256) k_trio_emit(const uint32_t* __restrict__ pnode, const uint64_t* __restrict__ poff, int64_t Htot,
+                                                   int64_t P, const uint32_t* __restrict__ flag, const uint64_t* __restrict__ scan,
+                                                   const uint32_t* __restrict__ len, uint32_t* __restrict__ trio_key,
+                                                   int64_t* __restrict__ trio_len, uint32_t* __restrict__ trio_owner, uint4* tt,
+                                                   uint32_t tt_mask, uint32_t* trio_mid, uint64_t* __restrict__ trio_start) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < (uint64_t)P; k += (uint64_t)gridDim.x * blockDim.x) {
+        if (!flag[k]) continue;
+        int64_t h;
+        uint32_t lo, mid, hi;
+        window_at(pnode, poff, Htot, k, h, lo, mid, hi);
+        const uint64_t t = scan[k];
+        trio_key[3 * t + 0] = lo;
+        trio_key[3 * t + 1] = mid;
+        trio_key[3 * t + 2] = hi;
+        trio_len[t] = (int64_t)len[lo] + (int64_t)len[mid] + (int64_t)len[hi];  // profile.rs:712
+        trio_owner[t] = (uint32_t)h;
+        atomicOr(trio_mid + (mid >> 5), 1u << (mid & 31u));
+        // unique keys: plain claim of an empty slot, then publish idx
+        uint32_t i = trio_hash(lo, mid, hi) & tt_mask;
+        const ulonglong2 empty = make_ulonglong2(0xFFFFFFFFFFFFFFFFull, 0xFFFFFFFFFFFFFFFFull);
+        const ulonglong2 mine = make_ulonglong2(((uint64_t)mid << 32) | lo, ((uint64_t)(uint32_t)t << 32) | hi);
+        for (;;) {
+            ulonglong2 prev = atomic_cas128(reinterpret_cast<ulonglong2*>(tt + i), empty, mine);
+            if (prev.x == empty.x && prev.y == empty.y) break;
+            i = (i + 1) & tt_mask;
+        }
+    }
+    // first trio index of every hap (+ sentinel)
+    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h <= (uint64_t)Htot; h += (uint64_t)gridDim.x * blockDim.x)
+        trio_start[h] = scan[poff[h]];
+}
+
+// =====================================================================================
+// finalize kernels
+// =====================================================================================
+// profile.rs:844/:874 -> :1018-1023: covered bases per node = popcount of its bit range, or len if fully covered
+__global__ void __launch_bounds__(256) k_cov(const uint32_t* __restrict__ len, const uint64_t* __restrict__ bit_off, const uint8_t* __restrict__ full,
+                                             const uint32_t* __restrict__ bits, uint32_t* __restrict__ cov, int64_t N) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    const uint32_t ln = len[g];
+    if (full[g]) {
+        cov[g] = ln;
+        return;
+    }
+    const uint64_t b0 = bit_off[g], b1 = b0 + ln - 1;
+    const uint64_t w0 = b0 >> 5, w1 = b1 >> 5;
+    const uint32_t m0 = 0xFFFFFFFFu << (b0 & 31u), m1 = 0xFFFFFFFFu >> (31u - (uint32_t)(b1 & 31u));
+    uint32_t c;
+    if (w0 == w1) {
+        c = __popc(bits[w0] & m0 & m1);
+    } else {
+        c = __popc(bits[w0] & m0) + __popc(bits[w1] & m1);
+        for (uint64_t w = w0 + 1; w < w1; ++w) c += __popc(bits[w]);
+    }
+    cov[g] = c;
+}
+
+__global__ void __launch_bounds__(256) k_hap_nz(const unsigned long long* __restrict__ trio_bases, const uint32_t* __restrict__ owner, int64_t T,
+                                                unsigned long long* hap_nz) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool nz = t < T && (long long)trio_bases[t] > 0;  // abundance > 0 (profile.rs:1132)
+    const uint32_t h = t < T ? owner[t] : 0xFFFFFFFFu;
+    // trios of one hap are contiguous: aggregate lanes sharing the hap
+    const unsigned peers = __match_any_sync(0xffffffffu, h);
+    const unsigned votes = __ballot_sync(0xffffffffu, nz) & peers;
+    if (t < T && votes && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(hap_nz + h, (unsigned long long)__popc(votes));
+}
+
+__global__ void __launch_bounds__(256) k_depth(const unsigned long long* __restrict__ num, const uint32_t* __restrict__ den32,
+                                               const int64_t* __restrict__ den64, double* __restrict__ out, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d = den32 ? (double)den32[i] : (double)den64[i];
+    out[i] = (double)(long long)num[i] / d;  // profile.rs:988 / :1014 (IEEE division, identical on host)
+}
+
+__global__ void __launch_bounds__(256) k_or_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] |= src[i];
+}
+
+__global__ void __launch_bounds__(256) k_fill_u8(uint8_t* p, uint8_t v, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// =====================================================================================
+// launchers
+// =====================================================================================
+static inline uint32_t grid_for(uint64_t n, uint32_t per_block, uint32_t cap = 148u * 32u) {
+    uint64_t g = (n + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (uint32_t)g;
+}
+
+void launch_count_records(const uint8_t* text, uint64_t, uint32_t n_tiles, uint32_t* tile_count, cudaStream_t st) {
+    k_count_records<<<n_tiles, 256, 0, st>>>(text, tile_count);
+    PTX_LAUNCHED();
+}
+void launch_scan_tiles(const uint32_t* tile_count, uint32_t* tile_base, uint32_t n_tiles, uint64_t* total, cudaStream_t st) {
+    k_scan_tiles<<<1, 1024, 0, st>>>(tile_count, tile_base, n_tiles, total);
+    PTX_LAUNCHED();
+}
+
+template <int MODE>
+static void launch_ingest_mode(const IngestArgs& a, cudaStream_t st) {
+    const size_t smem = STAGE + REC_CAP * sizeof(uint16_t);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_ingest<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    k_ingest<MODE><<<a.n_tiles, INGEST_THREADS, smem, st>>>(a);
+    PTX_LAUNCHED();
+}
+void launch_ingest(const IngestArgs& a, int mode, cudaStream_t st) {
+    switch (mode) {
+        case MODE_CLASSIFY: launch_ingest_mode<MODE_CLASSIFY>(a, st); break;
+        case MODE_CLASSIFY | MODE_COVER: launch_ingest_mode<MODE_CLASSIFY | MODE_COVER>(a, st); break;
+        case MODE_COVER: launch_ingest_mode<MODE_COVER>(a, st); break;
+        case MODE_COVER | MODE_KEEPMASK: launch_ingest_mode<MODE_COVER | MODE_KEEPMASK>(a, st); break;
+        default: break;
+    }
+}
+void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2* new_slots, uint32_t new_shift, uint64_t new_mask,
+                      cudaStream_t st) {
+    k_ds_rehash<<<grid_for(old_cap, 256), 256, 0, st>>>(old_slots, old_cap, new_slots, new_shift, new_mask);
+    PTX_LAUNCHED();
+}
+void launch_fill_u8(uint8_t* p, uint8_t v, uint64_t n, cudaStream_t st) {
+    k_fill_u8<<<grid_for(n, 256 * 16), 256, 0, st>>>(p, v, n);
+    PTX_LAUNCHED();
+}
+void launch_mark_path_dups(uint32_t* pnode, const uint64_t* poff, const uint32_t* round_paths, uint32_t n_round_paths, uint64_t max_len,
+                           uint32_t* stamp, cudaStream_t st) {
+    dim3 grid(grid_for(max_len, 256, 1024), n_round_paths);
+    k_mark_path_dups<<<grid, 256, 0, st>>>(pnode, poff, round_paths, stamp);
+    PTX_LAUNCHED();
+}
+void launch_path_len_sum(const uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, const uint32_t* val, unsigned long long* out,
+                         cudaStream_t st) {
+    if (P <= 0) return;
+    uint64_t nb = ((uint64_t)P + 256 * 8 - 1) / (256 * 8);
+    k_path_len_sum<<<(uint32_t)nb, 256, 0, st>>>(pnode, poff, Htot, P, val, out);
+    PTX_LAUNCHED();
+}
+void launch_trio_count(const uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, uint4* keys, uint32_t* cnt, uint32_t mask,
+                       cudaStream_t st) {
+    k_trio_count<<<grid_for(P, 256), 256, 0, st>>>(pnode, poff, Htot, P, keys, cnt, mask);
+    PTX_LAUNCHED();
+}
+void launch_trio_flag(const uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, const uint4* keys, const uint32_t* cnt,
+                      uint32_t mask, uint32_t* flag, cudaStream_t st) {
+    k_trio_flag<<<grid_for(P, 256), 256, 0, st>>>(pnode, poff, Htot, P, const_cast<uint4*>(keys), cnt, mask, flag);
+    PTX_LAUNCHED();
+}
+void launch_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* scratch, cudaStream_t st) {
+    const uint64_t nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    k_scan_block_sums<<<(uint32_t)std::max<uint64_t>(nb, 1), 1024, 0, st>>>(in, n, scratch);
+    k_scan_bsums<<<1, 1024, 0, st>>>(scratch, std::max<uint64_t>(nb, 1));
+    k_scan_final<<<(uint32_t)std::max<uint64_t>(nb, 1), 1024, 0, st>>>(in, n, scratch, std::max<uint64_t>(nb, 1), out);
+    PTX_LAUNCHED();
+    PTX_LAUNCHED();
+    PTX_LAUNCHED();
+}
+void launch_trio_emit(const uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, const uint32_t* flag, const uint64_t* scan,
+                      const uint32_t* len, uint32_t* trio_key, int64_t* trio_len, uint32_t* trio_owner, uint4* tt, uint32_t tt_mask,
+                      uint32_t* trio_mid, uint64_t* trio_start, cudaStream_t st) {
+    k_trio_emit<<<grid_for(std::max<int64_t>(P, Htot + 1), 256), 256, 0, st>>>(pnode, poff, Htot, P, flag, scan, len, trio_key, trio_len,
+                                                                               trio_owner, tt, tt_mask, trio_mid, trio_start);
+    PTX_LAUNCHED();
+}
+void launch_cov(const GraphDev& g, cudaStream_t st) {
+    if (g.N <= 0) return;
+    k_cov<<<(uint32_t)((g.N + 255) / 256), 256, 0, st>>>(g.len, g.bit_off, g.full, g.bits, g.cov, g.N);
+    PTX_LAUNCHED();
+}
+void launch_path_cov_sum(const GraphDev& g, cudaStream_t st) {
+    launch_path_len_sum(g.pnode, g.poff, g.Htot, g.P, g.cov, g.path_cov_sum, st);
+}
+void launch_hap_nz(const GraphDev& g, cudaStream_t st) {
+    if (g.T <= 0) return;
+    k_hap_nz<<<(uint32_t)((g.T + 255) / 256), 256, 0, st>>>(g.trio_bases, g.trio_owner, g.T, g.hap_nz);
+    PTX_LAUNCHED();
+}
+void launch_depth(const unsigned long long* num, const uint32_t* den32, const int64_t* den64, double* out, uint64_t n, cudaStream_t st) {
+    if (n == 0) return;
+    k_depth<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(num, den32, den64, out, n);
+    PTX_LAUNCHED();
+}
+void launch_or_words(uint32_t* dst, const uint32_t* src, uint64_t n_words, cudaStream_t st) {
+    if (n_words == 0) return;
+    k_or_words<<<grid_for(n_words, 256 * 4), 256, 0, st>>>(dst, src, n_words);
+    PTX_LAUNCHED();
+}
+
+}  // namespace ptx

@@ -1,0 +1,133 @@
+// CPU instantiation of pantax_b200/csrc/ptx_core.cuh (the per-record logic the CUDA
+// kernels run) with a plain-array sink.  TEST HARNESS ONLY: lets `-m "not gpu"` tests
+// check column parsing, classification, span arithmetic and the id hash against the
+// oracle without a GPU.  It is not part of, nor linked into, libpantax_gpu.so.
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+#include "../pantax_b200/csrc/ptx_core.cuh"
+
+using namespace ptx;
+
+namespace {
+struct HostSink {
+    const uint32_t* len_;
+    const uint64_t* bit_off;
+    int64_t* bases;
+    uint8_t* bytes;  // one byte per base
+    const std::map<std::tuple<uint32_t, uint32_t, uint32_t>, uint32_t>* tmap;
+    int64_t* trio_bases;
+    uint32_t* err;
+    uint32_t len(uint32_t g) const { return len_[g]; }
+    void add_bases(uint32_t g, int64_t v) { bases[g] += v; }
+    void set_bits(uint32_t g, int64_t lo, int64_t hi, uint32_t) {
+        for (int64_t j = lo; j < hi; ++j) bytes[bit_off[g] + j] = 1;
+    }
+    void trio(uint32_t x, uint32_t y, uint32_t z, int64_t s) {
+        uint32_t lo = x < z ? x : z, hi = x < z ? z : x;
+        auto it = tmap->find(std::make_tuple(lo, y, hi));
+        if (it != tmap->end()) trio_bases[it->second] += s;
+    }
+    void error_start_gt_len(uint32_t label) { err[label] |= 1u; }
+};
+struct HashKey {
+    uint64_t lo; uint32_t hi;
+    bool operator<(const HashKey& o) const { return lo != o.lo ? lo < o.lo : hi < o.hi; }
+};
+}  // namespace
+
+extern "C" {
+
+// Runs the whole per-record path on the CPU with the shared core.
+// trio_keys: T x 3 canonical GLOBAL node idx.  Outputs are caller-allocated.
+// `stage_lim`: if > 0, records are first parsed with that byte limit (emulating the
+// shared-memory window) and re-parsed unbounded when parse_record reports overflow.
+int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, const int64_t* rend, const int64_t* node_base,
+                  const uint32_t* order, int disjoint, int64_t N, const uint32_t* len, int64_t T, const uint32_t* trio_keys,
+                  uint32_t stage_lim, uint32_t* labels, int64_t* n_records, int64_t* hist, int64_t* bases, uint64_t* cov,
+                  int64_t* trio_bases, uint32_t* err, int* ids_unique, int64_t* n_overflow) {
+    RangesView R{rstart, rend, node_base, order, S, disjoint};
+    std::vector<uint64_t> bit_off(N + 1, 0);
+    for (int64_t i = 0; i < N; ++i) bit_off[i + 1] = bit_off[i] + len[i];
+    std::vector<uint8_t> bytes(bit_off[N] + 1, 0);
+    std::map<std::tuple<uint32_t, uint32_t, uint32_t>, uint32_t> tmap;
+    for (int64_t t = 0; t < T; ++t) tmap[std::make_tuple(trio_keys[3 * t], trio_keys[3 * t + 1], trio_keys[3 * t + 2])] = (uint32_t)t;
+    std::vector<uint8_t> buf(gaf, gaf + n);
+    buf.insert(buf.end(), 64, '\n');  // padding, as the chunk buffers have
+    struct Parsed { RecParse r; uint32_t label; uint32_t pos; bool eligible; };
+    std::vector<Parsed> recs;
+    *n_overflow = 0;
+    uint64_t i = 0;
+    while (i < n) {
+        const uint8_t* nl = (const uint8_t*)memchr(buf.data() + i, '\n', buf.size() - i);
+        uint64_t e = (uint64_t)(nl - buf.data());
+        uint8_t c = buf[i];
+        bool rec = c != '\n' && c != '@' && !(c == '\r' && buf[i + 1] == '\n');
+        if (rec) {
+            Parsed p;
+            p.pos = (uint32_t)i;
+            bool ok = false;
+            if (stage_lim) {
+                uint32_t lim = (uint32_t)std::min<uint64_t>(buf.size(), i + stage_lim);
+                ok = parse_record(buf.data(), (uint32_t)i, lim, p.r);
+                if (!ok) ++*n_overflow;
+            }
+            if (!ok) parse_record(buf.data(), (uint32_t)i, (uint32_t)buf.size(), p.r);
+            p.label = classify(R, p.r.W ? p.r.vmin : -1, p.r.W ? p.r.vmax : -1);
+            p.eligible = p.label != LABEL_U && !p.r.path_null && p.r.c7 != NULL_I64 && p.r.c8 != NULL_I64 && p.r.c9 != NULL_I64;
+            recs.push_back(p);
+        }
+        i = e + 1;
+    }
+    *n_records = (int64_t)recs.size();
+    std::map<HashKey, uint32_t> ds;
+    bool dup = false, mixed = false;
+    for (size_t k = 0; k < recs.size(); ++k) {
+        const Parsed& p = recs[k];
+        labels[k] = p.label;
+        if (p.label == LABEL_U) continue;
+        int64_t* h = hist + 4 * (int64_t)p.label;
+        h[0] += 1;
+        h[1] += p.r.qlen == NULL_I64 ? 0 : p.r.qlen;
+        if (p.r.mapq != NULL_I64 && p.r.mapq >= 3 && p.r.mapq <= 60) { h[2] += 1; if (p.r.mapq == 60) h[3] += 1; }
+        HashKey key{p.r.h.lo, p.r.h.hi};
+        auto it = ds.find(key);
+        if (it == ds.end()) ds[key] = p.eligible ? p.label : DS_NONE;
+        else {
+            dup = true;
+            if (p.eligible) {
+                if (it->second == DS_NONE) it->second = p.label;
+                else if (it->second != p.label) { it->second = DS_MIXED; mixed = true; }
+            }
+        }
+    }
+    *ids_unique = dup ? 0 : 1;
+    HostSink sink{len, bit_off.data(), bases, bytes.data(), &tmap, trio_bases, err};
+    for (const Parsed& p : recs) {
+        if (!p.eligible || node_base[p.label] < 0) continue;
+        if (mixed && ds[HashKey{p.r.h.lo, p.r.h.hi}] == DS_MIXED) continue;
+        cover_record(buf.data(), p.r, p.label, rstart[p.label], node_base[p.label], sink);
+    }
+    for (int64_t g = 0; g < N; ++g) {
+        uint64_t c = 0;
+        for (uint64_t j = bit_off[g]; j < bit_off[g + 1]; ++j) c += bytes[j];
+        cov[g] = c;
+    }
+    return 0;
+}
+
+// id hash of one string (for collision / avalanche checks)
+void hostcheck_idhash(const uint8_t* s, uint32_t n, uint64_t* lo, uint32_t* hi) {
+    IdHasher H;
+    for (uint32_t i = 0; i < n; ++i) H.byte(s[i]);
+    IdHash h = H.finish();
+    *lo = h.lo;
+    *hi = h.hi;
+}
+uint32_t hostcheck_trio_hash(uint32_t a, uint32_t b, uint32_t c) { return trio_hash(a, b, c); }
+
+}  // extern "C"

@@ -1,0 +1,187 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle."""
+import numpy as np
+import pytest
+
+from common import LABEL_U, NASTY, NASTY_DUP, dataset_graphs, opy, run_cpu_oracle, synth
+from test_oracle import kat_inputs, load_kats
+
+pytestmark = pytest.mark.gpu
+
+
+def _api():
+    from pantax_b200 import api
+    return api
+
+
+@pytest.mark.parametrize("case", load_kats(), ids=lambda c: c["name"])
+@pytest.mark.parametrize("flow", ["fused", "late"])
+def test_gpu_matches_hand_derived_kats(case, flow):
+    from gpu_common import gpu_vs_oracle
+    ranges, graphs, gaf = kat_inputs(case)
+    ctx, o = gpu_vs_oracle(ranges, graphs, gaf, flow=flow)
+    exp = case["expect"]
+    idx = {r[0]: i for i, r in enumerate(ranges)}
+    assert ctx.read_labels().tolist() == [idx.get(l, LABEL_U) for l in exp["labels"]]
+    for name, _s, _e in ranges:
+        if name in exp:
+            s = idx[name]
+            assert ctx.node_bases(s).tolist() == exp[name]["bases"]
+            assert ctx.node_cov(s).tolist() == exp[name]["cov"]
+            assert ctx.trio_bases(s).tolist() == exp[name]["trio_bases"]
+            assert ctx.path_sums(s)[0].tolist() == exp[name]["path_sum_cov"]
+            assert ctx.hap_trio_counts(s)[1].tolist() == exp[name]["hap_nz"]
+
+
+@pytest.mark.parametrize("params,seed", [(synth.GafParams(), 1), (NASTY, 2), (NASTY_DUP, 3)])
+@pytest.mark.parametrize("flow", ["fused", "late"])
+def test_gpu_short_reads_multi_species(params, seed, flow):
+    from gpu_common import gpu_vs_oracle
+    ds = synth.Dataset(300 + seed, [30000, 8000, 12000, 400], [8, 1, 3, 2])
+    gaf = ds.gaf(seed, 0, 60000, params)
+    ctx, o = gpu_vs_oracle(ds.ranges(), dataset_graphs(ds), gaf, flow=flow)
+    if params is NASTY_DUP:
+        assert not ctx.ids_unique and o.mixed_dropped > 0
+
+
+def test_gpu_long_reads_hifi_dialect():
+    from gpu_common import gpu_vs_oracle
+    ds = synth.Dataset(8, [40000, 25000, 9000], [4, 2, 3], backbone_mean=400)
+    gaf = ds.gaf(6, 0, 3000, synth.GafParams(long_reads=True, id_pair_suffix=False, p_secondary=0.1))
+    gpu_vs_oracle(ds.ranges(), dataset_graphs(ds), gaf)
+
+
+def test_gpu_chunked_ingest_splits_lines_anywhere():
+    from gpu_common import assert_gpu_matches_oracle, run_gpu
+    ds = synth.Dataset(21, [20000, 5000], [6, 2])
+    gaf = ds.gaf(2, 0, 20000, NASTY)
+    graphs = dataset_graphs(ds)
+    o = run_cpu_oracle(ds.ranges(), graphs, gaf)
+    rng = np.random.default_rng(5)
+    for n_cuts in (1, 7, 40):
+        cuts = rng.integers(1, len(gaf) - 1, size=n_cuts).tolist()
+        ctx = run_gpu(ds.ranges(), graphs, gaf, split=cuts)
+        assert_gpu_matches_oracle(ctx, o, graphs)
+    # a chunk with no newline at all, and a final line without '\n'
+    g2 = gaf[:-1]
+    o2 = run_cpu_oracle(ds.ranges(), graphs, g2)
+    ctx = run_gpu(ds.ranges(), graphs, g2, split=[10, 20, 30, len(g2) - 5])
+    assert_gpu_matches_oracle(ctx, o2, graphs)
+
+
+def test_gpu_partial_graphs_and_species_only():
+    from gpu_common import assert_gpu_matches_oracle, run_gpu
+    api = _api()
+    ds = synth.Dataset(31, [10000, 5000, 3000], [5, 2, 1])
+    gaf = ds.gaf(3, 0, 20000, NASTY)
+    graphs = dataset_graphs(ds)
+    graphs[1] = None
+    o = run_cpu_oracle(ds.ranges(), graphs, gaf)
+    ctx = run_gpu(ds.ranges(), graphs, gaf)
+    assert_gpu_matches_oracle(ctx, o, graphs)
+    with pytest.raises(api.PantaxGpuError) as e:
+        ctx.node_bases(1)
+    assert e.value.name == "PTX_E_NO_GRAPH"
+    # species-level only: no graph at all
+    ctx = run_gpu(ds.ranges(), [None, None, None], gaf)
+    np.testing.assert_array_equal(ctx.species_counts(), o.species_counts())
+    np.testing.assert_array_equal(ctx.read_labels(), o.labels())
+    eq, rl = ctx.equal_length()
+    rows = opy.rcls_profile(gaf, ds.ranges())
+    assert (eq, rl if eq else None) == opy.equal_length_test(rows)
+
+
+def test_gpu_equal_length_rule_long_reads():
+    from gpu_common import run_gpu
+    ds = synth.Dataset(8, [40000, 25000], [4, 2], backbone_mean=400)
+    gaf = ds.gaf(6, 0, 1500, synth.GafParams(long_reads=True, id_pair_suffix=False))
+    ctx = run_gpu(ds.ranges(), [None, None], gaf)
+    eq, _ = ctx.equal_length()
+    assert eq is False
+
+
+def test_gpu_dialect_edges_and_start_beyond_node_error():
+    from gpu_common import gpu_vs_oracle
+    from test_core_host import test_core_handcrafted_dialect_edges  # noqa: F401  (same inputs)
+    ranges = [("a", 1, 50), ("b", 51, 80)]
+    graphs = [(np.full(50, 7, dtype=np.int64), [np.arange(50, dtype=np.uint64), np.array([3, 2, 1, 2, 3, 9], dtype=np.uint64)], ["p", "q"]),
+              (np.full(30, 5, dtype=np.int64), [np.arange(30, dtype=np.uint64)], ["r"])]
+    lines = [
+        b"r1\t50\t0\t50\t+\t>3>4>5\t21\t2\t18\t16\t16\t60\ttp:A:P",
+        b"r2\t50\t0\t50\t+\t>4>3>2>3>4\t35\t1\t30\t29\t29\t60",
+        b"r3\t50\t0\t50\t+\t<10<9\t14\t0\t14\t14\t14\t5\r",
+        b"r4\t+50\t0\t50\t+\t>60>61\t10\t-1\t4\t4\t4\t60",
+        b"r5\t5x\t0\t50\t+\t>7\t7\t1\t3\t2\t2\tabc",
+        b"r6\t50\t0\t50\t+\t>8>9",
+        b"", b"\r", b"@HD\tVN:1.0",
+        b"r7\t50\t0\t50\t+\t>0000000000000000000012>13\t14\t0\t9\t9\t9\t60",
+        b"r8\t50\t0\t50\t+\t>49>50>51\t19\t0\t19\t19\t19\t60",
+        b"r9\t50\t0\t50\t+\tchr1_12\t7\t0\t5\t5\t5\t3",
+        b"*\t50\t0\t50\t+\t>20>21>22\t21\t7\t20\t13\t13\t60",
+    ]
+    gaf_ok = b"\n".join(lines) + b"\n"
+    gpu_vs_oracle(ranges, graphs, gaf_ok)
+    gaf_bad = gaf_ok + b"r10\t50\t0\t50\t+\t>30>31\t14\t8\t20\t12\t12\t60"  # start 8 > len 7: profile.rs:854
+    ctx, o = gpu_vs_oracle(ranges, graphs, gaf_bad)
+    assert o.species_error(0) == 1
+
+
+def test_gpu_overlapping_ranges_use_first_match_in_file_order():
+    from gpu_common import gpu_vs_oracle
+    # rcls.rs:253-257 takes the FIRST matching row; with overlapping rows the binary search is not used
+    ranges = [("wide", 1, 100), ("narrow", 10, 20), ("tail", 101, 140)]
+    graphs = [(np.full(100, 9, dtype=np.int64), [np.arange(100, dtype=np.uint64)], ["p"]), None,
+              (np.full(40, 3, dtype=np.int64), [np.arange(40, dtype=np.uint64)], ["q"])]
+    lines = [b"x%d\t20\t0\t20\t+\t>%d>%d\t18\t1\t15\t14\t14\t60" % (i, a, a + 1) for i, a in enumerate([12, 15, 99, 100, 101, 120, 5])]
+    ctx, o = gpu_vs_oracle(ranges, graphs, b"\n".join(lines) + b"\n")
+    assert ctx.read_labels().tolist() == [0, 0, 0, LABEL_U, 2, 2, 0]
+
+
+def test_gpu_device_resident_buffer_and_reset():
+    import torch
+    from gpu_common import assert_gpu_matches_oracle
+    api = _api()
+    ds = synth.Dataset(41, [50000], [10])
+    gaf = ds.gaf(9, 0, 100000)
+    graphs = dataset_graphs(ds)
+    o = run_cpu_oracle(ds.ranges(), graphs, gaf)
+    ctx = api.PantaxGpu(0)
+    ctx.set_ranges(ds.ranges())
+    ctx.upload_graph(0, graphs[0][0], graphs[0][1])
+    ctx.commit_graphs()
+    for _rep in range(2):
+        bid, dptr = ctx.gaf_buffer_alloc(len(gaf))
+        src = torch.frombuffer(bytearray(gaf), dtype=torch.uint8).cuda()
+        # device-to-device copy into the library's padded buffer
+        import ctypes as C
+        cudart = C.CDLL("libcudart.so")
+        assert cudart.cudaMemcpy(C.c_void_p(dptr), C.c_void_p(src.data_ptr()), C.c_size_t(len(gaf)), 3) == 0
+        ctx.ingest_gaf_device(bid, len(gaf))
+        ctx.finalize()
+        assert_gpu_matches_oracle(ctx, o, graphs)
+        ctx.reset()
+
+
+def test_gpu_medium_single_species_config2_shape():
+    """BASELINE config 2 scaled 1/20: 50k nodes, 50 strain paths, 500k short-read records."""
+    from gpu_common import gpu_vs_oracle
+    ds = synth.Dataset(20261019, [50000], [50])
+    gaf = ds.gaf(2, 0, 500000)
+    ctx, o = gpu_vs_oracle(ds.ranges(), dataset_graphs(ds), gaf)
+    assert ctx.n_trios(0) > 0 and ctx.trio_bases(0).sum() > 0
+
+
+def test_gpu_result_is_invariant_under_record_permutation():
+    from gpu_common import run_gpu
+    ds = synth.Dataset(51, [20000, 6000], [6, 3])
+    gaf = ds.gaf(4, 0, 50000, NASTY_DUP)
+    lines = gaf.split(b"\n")[:-1]
+    perm = np.random.default_rng(1).permutation(len(lines))
+    gaf2 = b"\n".join(lines[i] for i in perm) + b"\n"
+    graphs = dataset_graphs(ds)
+    a = run_gpu(ds.ranges(), graphs, gaf)
+    b = run_gpu(ds.ranges(), graphs, gaf2)
+    np.testing.assert_array_equal(a.species_counts(), b.species_counts())
+    for s in range(2):
+        np.testing.assert_array_equal(a.node_bases(s), b.node_bases(s))
+        np.testing.assert_array_equal(a.node_cov(s), b.node_cov(s))
+        np.testing.assert_array_equal(a.trio_bases(s), b.trio_bases(s))
