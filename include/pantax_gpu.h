@@ -102,6 +102,9 @@ int ptx_finalize(ptx_ctx* ctx);
 
 /* Forget all ingested records and accumulators; ranges and graphs stay. */
 int ptx_reset(ptx_ctx* ctx);
+/* Same, but the device GAF buffers (ptx_gaf_buffer_alloc) and their text are kept and may be
+ * ingested again with ptx_ingest_gaf_device: another pass over text already resident in HBM. */
+int ptx_rewind(ptx_ctx* ctx);
 
 /* ---- outputs (caller-allocated buffers) -------------------------------------------- */
 int64_t ptx_num_records(const ptx_ctx* ctx);   /* GAF rows (non-comment, non-empty lines), this rank */

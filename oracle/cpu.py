@@ -47,6 +47,7 @@ def lib():
         L.orc_mixed_dropped.restype = C.c_int64
         L.orc_mixed_dropped.argtypes = [vp]
         L.orc_times.argtypes = [vp, C.POINTER(C.c_double)]
+        L.orc_workload_stats.argtypes = [vp, i64p]
         L.orc_labels.argtypes = [vp, u32p]
         L.orc_record_fields.argtypes = [vp, i64p, i64p]
         L.orc_species_counts.argtypes = [vp, i64p]
@@ -142,6 +143,11 @@ class CpuOracle:
     @property
     def mixed_dropped(self) -> int:
         return self._L.orc_mixed_dropped(self._h)
+
+    def workload_stats(self):
+        a = np.zeros(4, dtype=np.int64)
+        self._L.orc_workload_stats(self._h, _p(a, C.c_int64))
+        return dict(cover_reads=int(a[0]), walk_nodes=int(a[1]), trio_windows=int(a[2]), trio_hits=int(a[3]))
 
     def labels(self) -> np.ndarray:
         out = np.empty(self.n_records, dtype=np.uint32)

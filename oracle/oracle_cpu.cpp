@@ -94,6 +94,7 @@ struct Oracle {
     bool ids_unique = true;
     int64_t n_mixed_dropped = 0;
     double t_parse = 0, t_group = 0, t_cov = 0, t_stats = 0;
+    std::atomic<int64_t> st_reads{0}, st_nodes{0}, st_windows{0}, st_hits{0};  // workload statistics for the roofline
 };
 
 template <class F>
@@ -222,11 +223,13 @@ void trio_nodes_info(SpeciesGraph& G) {
 
 // profile.rs:787-919 for one read
 void cover_read(SpeciesGraph& G, int64_t range_start, const Rec& r, std::vector<int64_t>& nodes,
-                std::vector<int64_t>& aln_of, std::vector<int64_t>& rl) {
+                std::vector<int64_t>& aln_of, std::vector<int64_t>& rl, int64_t* stats) {
     nodes.clear();
     for_digit_runs(r.path, r.path_len, [&](int64_t v) { nodes.push_back(v - range_start); });  // :788-792
     if (nodes.empty()) return;                                                                  // :794
     const size_t W = nodes.size();
+    stats[0] += 1;
+    stats[1] += (int64_t)W;
     int64_t target = r.c9 - r.c8;  // :800
     const int64_t ps = r.c8, pe = r.c9;
     auto setbits = [&](int64_t nd, int64_t lo, int64_t hi) {  // [lo,hi) clipped as `as usize` ranges do
@@ -274,7 +277,8 @@ void cover_read(SpeciesGraph& G, int64_t range_start, const Rec& r, std::vector<
         int64_t s = rl[i] + rl[i + 1] + rl[i + 2];  // :897-900
         if (k.a > k.c) std::swap(k.a, k.c);         // :902-904 (keys are canonical)
         auto it = G.trio_map.find(k);
-        if (it != G.trio_map.end()) G.trio_bases[it->second].fetch_add(s, std::memory_order_relaxed);
+        stats[2] += 1;
+        if (it != G.trio_map.end()) { stats[3] += 1; G.trio_bases[it->second].fetch_add(s, std::memory_order_relaxed); }
     }
 }
 
@@ -427,9 +431,11 @@ int orc_run(void* h, const uint8_t* data, size_t n) {
         G.err_start_gt_len = 0;
     }
     std::atomic<int64_t> dropped{0};
+    O.st_reads = 0; O.st_nodes = 0; O.st_windows = 0; O.st_hits = 0;
     parallel_for(nt, R, [&](int, size_t a, size_t b) {
         std::hash<std::string_view> H;
         std::vector<int64_t> nodes, aln_of, rl;
+        int64_t stats[4] = {0, 0, 0, 0};
         for (size_t i = a; i < b; ++i) {
             const Rec& r = O.recs[i];
             if (r.label == LABEL_U) continue;
@@ -441,8 +447,9 @@ int orc_run(void* h, const uint8_t* data, size_t n) {
                 Shard& sh = shards[H(id) % NSH];
                 if (sh.first_species.find(id)->second == MIXED) { dropped.fetch_add(1); continue; }  // :415-416
             }
-            cover_read(G, O.rstart[r.label], r, nodes, aln_of, rl);
+            cover_read(G, O.rstart[r.label], r, nodes, aln_of, rl, stats);
         }
+        O.st_reads += stats[0]; O.st_nodes += stats[1]; O.st_windows += stats[2]; O.st_hits += stats[3];
     });
     O.n_mixed_dropped = dropped.load();
     O.t_cov = now() - t0;
@@ -492,6 +499,11 @@ int64_t orc_mixed_dropped(void* h) { return ((Oracle*)h)->n_mixed_dropped; }
 void orc_times(void* h, double* t4) {
     Oracle& O = *(Oracle*)h;
     t4[0] = O.t_parse; t4[1] = O.t_group; t4[2] = O.t_cov; t4[3] = O.t_stats;
+}
+// [covered reads, their walk nodes, trio windows probed, probes that hit a unique trio]
+void orc_workload_stats(void* h, int64_t* out4) {
+    Oracle& O = *(Oracle*)h;
+    out4[0] = O.st_reads; out4[1] = O.st_nodes; out4[2] = O.st_windows; out4[3] = O.st_hits;
 }
 void orc_labels(void* h, uint32_t* out) {
     Oracle& O = *(Oracle*)h;

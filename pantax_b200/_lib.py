@@ -41,6 +41,7 @@ SIGNATURES = {
     "ptx_ingest_gaf_device": (i32, [vp, i32, C.c_size_t]),
     "ptx_finalize": (i32, [vp]),
     "ptx_reset": (i32, [vp]),
+    "ptx_rewind": (i32, [vp]),
     "ptx_num_records": (i64, [vp]),
     "ptx_num_species": (i32, [vp]),
     "ptx_ids_unique": (i32, [vp]),

@@ -141,6 +141,9 @@ class PantaxGpu:
     def reset(self):
         self._ck(self._L.ptx_reset(self._h))
 
+    def rewind(self):
+        self._ck(self._L.ptx_rewind(self._h))
+
     def comm_init(self, n_ranks: int, rank: int, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)
         self._ck(self._L.ptx_comm_init(self._h, n_ranks, rank, buf))

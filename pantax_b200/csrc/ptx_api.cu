@@ -66,6 +66,8 @@ struct Chunk {
     uint32_t* tile_count = nullptr;
     uint32_t* tile_base = nullptr;
     uint32_t* labels = nullptr;
+    uint32_t tiles_cap = 0;
+    int64_t labels_cap = 0;
     int64_t n_records = 0;
     bool ingested = false;  // classify pass done
     bool covered = false;   // coverage pass done against the current graph
@@ -106,7 +108,7 @@ struct ptx_ctx {
     uint32_t h_flags[2] = {0, 0};
     std::vector<uint32_t> h_err;
     // timing
-    std::vector<EvPair> ev_ingest, ev_final;
+    std::vector<EvPair> ev_count, ev_ingest, ev_final;
     // multi-GPU
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
@@ -264,18 +266,27 @@ int chunk_process(ptx_ctx* ctx, Chunk& ch) {
     // pad the tail of the last tile (+ overhang) with newlines
     const size_t pad_to = (size_t)ch.n_tiles * TILE + OVER;
     CU(cudaMemsetAsync(ch.buf + PRE + ch.n, '\n', pad_to - ch.n, ctx->st));
-    CU(cudaMalloc((void**)&ch.tile_count, ch.n_tiles * sizeof(uint32_t)));
-    CU(cudaMalloc((void**)&ch.tile_base, ch.n_tiles * sizeof(uint32_t)));
-    ev_begin(ctx, ctx->ev_ingest);
+    if (ch.tiles_cap < ch.n_tiles) {
+        dfree(ch.tile_count);
+        dfree(ch.tile_base);
+        CU(cudaMalloc((void**)&ch.tile_count, ch.n_tiles * sizeof(uint32_t)));
+        CU(cudaMalloc((void**)&ch.tile_base, ch.n_tiles * sizeof(uint32_t)));
+        ch.tiles_cap = ch.n_tiles;
+    }
+    ev_begin(ctx, ctx->ev_count);
     launch_count_records(ch.buf + PRE, ch.n, ch.n_tiles, ch.tile_count, ctx->st);
     launch_scan_tiles(ch.tile_count, ch.tile_base, ch.n_tiles, ctx->d_total, ctx->st);
-    ev_end(ctx, ctx->ev_ingest);
+    ev_end(ctx, ctx->ev_count);
     uint64_t total = 0;
     CU(cudaMemcpyAsync(&total, ctx->d_total, sizeof total, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     ch.n_records = (int64_t)total;
     if (total > 0xFFFFFFF0ull) return fail(ctx, PTX_E_INVALID, "more than 2^32 records in one chunk");
-    CU(cudaMalloc((void**)&ch.labels, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
+    if (!ch.labels || ch.labels_cap < (int64_t)total) {
+        dfree(ch.labels);
+        CU(cudaMalloc((void**)&ch.labels, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
+        ch.labels_cap = (int64_t)std::max<uint64_t>(total, 1);
+    }
     int rc = ds_ensure(ctx, ch.n_records);
     if (rc) return rc;
     ctx->ds_records += ch.n_records;
@@ -373,6 +384,7 @@ void ptx_destroy(ptx_ctx* ctx) {
     free_graph(ctx);
     dfree(ctx->d_rstart); dfree(ctx->d_rend); dfree(ctx->d_node_base); dfree(ctx->d_order);
     dfree(ctx->d_hist); dfree(ctx->d_hist_g); dfree(ctx->d_flags); dfree(ctx->d_err); dfree(ctx->d_ds); dfree(ctx->d_total);
+    ev_clear(ctx->ev_count);
     ev_clear(ctx->ev_ingest);
     ev_clear(ctx->ev_final);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
@@ -777,12 +789,17 @@ int ptx_finalize(ptx_ctx* ctx) {
     return PTX_OK;
 }
 
-int ptx_reset(ptx_ctx* ctx) {
+static int reset_impl(ptx_ctx* ctx, bool keep_buffers) {
     if (!ctx) return PTX_E_INVALID;
     cudaSetDevice(ctx->device);
-    CU(cudaDeviceSynchronize());
-    for (auto& ch : ctx->chunks) chunk_free(ch);
-    ctx->chunks.clear();
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaStreamSynchronize(ctx->copy_st));
+    if (keep_buffers) {
+        for (auto& ch : ctx->chunks) { ch.ingested = false; ch.covered = false; ch.n_records = 0; }
+    } else {
+        for (auto& ch : ctx->chunks) chunk_free(ch);
+        ctx->chunks.clear();
+    }
     ctx->carry.clear();
     ctx->total_records = 0;
     ctx->ds_records = 0;
@@ -797,18 +814,24 @@ int ptx_reset(ptx_ctx* ctx) {
         if (rc) return rc;
         CU(cudaMemsetAsync(ctx->d_err, 0, S * sizeof(uint32_t), ctx->st));
     }
-    if (ctx->g.Htot > 0) {
-        CU(cudaMemsetAsync(ctx->g.path_cov_sum, 0, ctx->g.Htot * sizeof(unsigned long long), ctx->st));
-        CU(cudaMemsetAsync(ctx->g.hap_nz, 0, ctx->g.Htot * sizeof(unsigned long long), ctx->st));
-        CU(cudaMemsetAsync(ctx->g.cov, 0, ctx->g.N * sizeof(uint32_t), ctx->st));
-    }
-    CU(cudaStreamSynchronize(ctx->st));
     ctx->h_err.assign(ctx->sp.size(), 0);
+    ev_clear(ctx->ev_count);
     ev_clear(ctx->ev_ingest);
     ev_clear(ctx->ev_final);
     ctx->dirty = false;
     return PTX_OK;
 }
+
+int ptx_reset(ptx_ctx* ctx) {
+    int rc = reset_impl(ctx, false);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->st));
+    return PTX_OK;
+}
+
+// Zero every accumulator (stream-ordered, no host sync) but keep the device GAF buffers, which
+// can then be ingested again with ptx_ingest_gaf_device: one more pass over the same resident text.
+int ptx_rewind(ptx_ctx* ctx) { return reset_impl(ctx, true); }
 
 int64_t ptx_num_records(const ptx_ctx* ctx) { return ctx ? ctx->total_records : PTX_E_INVALID; }
 int ptx_num_species(const ptx_ctx* ctx) { return ctx ? (int)ctx->sp.size() : PTX_E_INVALID; }
@@ -1041,7 +1064,7 @@ int ptx_timing(ptx_ctx* ctx, double* ingest_ms, double* finalize_ms, int64_t* ke
     if (!ctx) return PTX_E_INVALID;
     cudaSetDevice(ctx->device);
     CU(cudaStreamSynchronize(ctx->st));
-    if (ingest_ms) *ingest_ms = ev_sum(ctx->ev_ingest);
+    if (ingest_ms) *ingest_ms = ev_sum(ctx->ev_count) + ev_sum(ctx->ev_ingest);
     if (finalize_ms) *finalize_ms = ev_sum(ctx->ev_final);
     if (kernel_launches) *kernel_launches = kernel_launch_count();
     return PTX_OK;
@@ -1056,10 +1079,10 @@ int ptx_stats_json(ptx_ctx* ctx, char* buf, size_t cap) {
     snprintf(buf, cap,
              "{\"records\": %lld, \"chunks\": %zu, \"text_bytes\": %zu, \"nodes\": %lld, \"paths\": %lld, \"path_steps\": %lld, "
              "\"unique_trios\": %lld, \"bit_words\": %llu, \"id_set_slots\": %llu, \"ids_unique\": %d, \"mixed_groups\": %d, "
-             "\"ingest_ms\": %.4f, \"finalize_ms\": %.4f, \"kernel_launches\": %lld, \"ranks\": %d}",
+             "\"count_ms\": %.4f, \"ingest_ms\": %.4f, \"ingest_launches\": %zu, \"finalize_ms\": %.4f, \"kernel_launches\": %lld, \"ranks\": %d}",
              (long long)ctx->total_records, ctx->chunks.size(), text, (long long)ctx->g.N, (long long)ctx->g.Htot, (long long)ctx->g.P,
              (long long)ctx->g.T, (unsigned long long)ctx->g.n_bit_words, (unsigned long long)ctx->ds_cap, ctx->h_flags[0] == 0 ? 1 : 0,
-             ctx->h_flags[1] != 0 ? 1 : 0, ev_sum(ctx->ev_ingest), ev_sum(ctx->ev_final), (long long)kernel_launch_count(), ctx->n_ranks);
+             ctx->h_flags[1] != 0 ? 1 : 0, ev_sum(ctx->ev_count), ev_sum(ctx->ev_ingest), ctx->ev_ingest.size(), ev_sum(ctx->ev_final), (long long)kernel_launch_count(), ctx->n_ranks);
     return PTX_OK;
 }
 
