@@ -62,9 +62,12 @@ struct Chunk {
     uint8_t* buf = nullptr;  // cudaMalloc'ed: [PRE][text][padding]
     size_t cap = 0;          // text capacity (bytes) the buffer was padded for
     size_t n = 0;            // text bytes
+    size_t padded = 0;       // bytes readable from text (text + '\n' padding)
+    uint32_t n_micro = 0;    // 4 KB micro-tiles counted by K1 (multiple of 8, covers every ingest tile)
     uint32_t n_tiles = 0;
-    uint32_t* tile_count = nullptr;
-    uint32_t* tile_base = nullptr;
+    uint32_t rows = 8;       // ingest tile = rows * 4096 bytes
+    uint32_t* tile_count = nullptr;  // [n_micro]
+    uint32_t* tile_base = nullptr;   // [n_micro]
     uint32_t* labels = nullptr;
     uint32_t tiles_cap = 0;
     int64_t labels_cap = 0;
@@ -99,6 +102,7 @@ struct ptx_ctx {
     uint64_t ds_cap = 0;
     int64_t ds_records = 0;  // upper bound of ids inserted
     int64_t reserve_records = 0;
+    int force_rows = 0;  // PTX_TILE_ROWS env override (tests exercise every tile size)
     uint64_t* d_total = nullptr;  // scratch scalar
     // records
     std::vector<Chunk> chunks;
@@ -211,8 +215,10 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     memset(&a, 0, sizeof a);
     a.text = ch.buf + PRE;
     a.n_bytes = ch.n;
+    a.padded_bytes = ch.padded;
     a.n_tiles = ch.n_tiles;
-    a.tile_base = ch.tile_base;
+    a.rows_per_warp = ch.rows;
+    a.micro_base = ch.tile_base;
     a.labels = ch.labels;
     a.ranges = ranges_view(ctx);
     a.hist = ctx->d_hist;
@@ -234,10 +240,11 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     return a;
 }
 
+// bytes readable after `text`: whole 32 KB blocks covering n, one spare block (a tile of any size that
+// starts inside the text ends before it), and the staging overhang
 size_t padded_text_bytes(size_t n) {
-    size_t tiles = (n + TILE - 1) / TILE;
-    if (tiles == 0) tiles = 1;
-    return tiles * (size_t)TILE + OVER;
+    size_t blocks = (n + MAX_TILE - 1) / MAX_TILE;
+    return (blocks + 1) * (size_t)MAX_TILE + OVER;
 }
 
 // allocate a chunk buffer able to hold `cap` text bytes; PRE bytes of '\n' in front
@@ -261,27 +268,36 @@ void chunk_free(Chunk& ch) {
 // classify (+ optimistic coverage) pass over one chunk whose text is resident
 int chunk_process(ptx_ctx* ctx, Chunk& ch) {
     if (ctx->cov_reduced) return fail(ctx, PTX_E_STATE, "multi-GPU: coverage already reduced by ptx_finalize; ptx_reset before ingesting more");
-    ch.n_tiles = (uint32_t)((ch.n + TILE - 1) / TILE);
-    if (ch.n_tiles == 0) { ch.ingested = true; ch.covered = true; return PTX_OK; }
-    // pad the tail of the last tile (+ overhang) with newlines
-    const size_t pad_to = (size_t)ch.n_tiles * TILE + OVER;
-    CU(cudaMemsetAsync(ch.buf + PRE + ch.n, '\n', pad_to - ch.n, ctx->st));
-    if (ch.tiles_cap < ch.n_tiles) {
+    if (ch.n == 0) { ch.n_tiles = 0; ch.ingested = true; ch.covered = true; return PTX_OK; }
+    // pad behind the text with newlines (terminates an unterminated last line; padding holds no records)
+    ch.padded = padded_text_bytes(ch.n);
+    CU(cudaMemsetAsync(ch.buf + PRE + ch.n, '\n', ch.padded - ch.n, ctx->st));
+    ch.n_micro = (uint32_t)((ch.padded - OVER) / MICRO);
+    if (ch.tiles_cap < ch.n_micro) {
         dfree(ch.tile_count);
         dfree(ch.tile_base);
-        CU(cudaMalloc((void**)&ch.tile_count, ch.n_tiles * sizeof(uint32_t)));
-        CU(cudaMalloc((void**)&ch.tile_base, ch.n_tiles * sizeof(uint32_t)));
-        ch.tiles_cap = ch.n_tiles;
+        CU(cudaMalloc((void**)&ch.tile_count, ch.n_micro * sizeof(uint32_t)));
+        CU(cudaMalloc((void**)&ch.tile_base, ch.n_micro * sizeof(uint32_t)));
+        ch.tiles_cap = ch.n_micro;
     }
     ev_begin(ctx, ctx->ev_count);
-    launch_count_records(ch.buf + PRE, ch.n, ch.n_tiles, ch.tile_count, ctx->st);
-    launch_scan_tiles(ch.tile_count, ch.tile_base, ch.n_tiles, ctx->d_total, ctx->st);
+    launch_count_records(ch.buf + PRE, ch.n_micro, ch.tile_count, ctx->st);
+    launch_scan_tiles(ch.tile_count, ch.tile_base, ch.n_micro, ctx->d_total, ctx->st);
     ev_end(ctx, ctx->ev_count);
     uint64_t total = 0;
     CU(cudaMemcpyAsync(&total, ctx->d_total, sizeof total, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     ch.n_records = (int64_t)total;
     if (total > 0xFFFFFFF0ull) return fail(ctx, PTX_E_INVALID, "more than 2^32 records in one chunk");
+    // tile size: about one record per thread (mean line length measured by K1), 4 KB granularity
+    {
+        const double mean_line = (double)ch.n / (double)std::max<uint64_t>(total, 1);
+        int rows = (int)(0.97 * INGEST_THREADS * mean_line / MICRO);
+        ch.rows = (uint32_t)std::min(8, std::max(1, rows));
+        if (ctx->force_rows > 0) ch.rows = (uint32_t)std::min(8, ctx->force_rows);
+        const size_t tile = (size_t)ch.rows * MICRO;
+        ch.n_tiles = (uint32_t)((ch.n + tile - 1) / tile);
+    }
     if (!ch.labels || ch.labels_cap < (int64_t)total) {
         dfree(ch.labels);
         CU(cudaMalloc((void**)&ch.labels, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
@@ -361,6 +377,7 @@ int ptx_create(int device, ptx_ctx** out) {
     ptx_ctx* ctx = new (std::nothrow) ptx_ctx;
     if (!ctx) return PTX_E_NOMEM;
     ctx->device = device;
+    if (const char* e = getenv("PTX_TILE_ROWS")) ctx->force_rows = atoi(e);
     if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
@@ -721,7 +738,7 @@ int ptx_finalize(ptx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (!ctx->carry.empty()) return fail(ctx, PTX_E_STATE, "a partial line is pending: pass is_last=1 on the final chunk");
     for (auto& ch : ctx->chunks)
-        if (!ch.ingested && ch.n_tiles == 0 && ch.n == 0) { ch.ingested = true; ch.covered = true; }  // unused device buffers
+        if (!ch.ingested && ch.n == 0) { ch.ingested = true; ch.covered = true; }  // unused device buffers
     if (!ctx->dirty) return PTX_OK;
     GraphDev& g = ctx->g;
     const int S = (int)ctx->sp.size();
@@ -898,7 +915,7 @@ int ptx_equal_length(ptx_ctx* ctx, int* is_equal, int64_t* read_len) {
             for (size_t k = 0; k < lines.size() && seen < 1000; ++k) {
                 if (lab[k] == LABEL_U) continue;
                 RecParse r;
-                parse_record(text.data() + lines[k].first, 0, (uint32_t)lines[k].second, r);  // same column rules as the kernel
+                parse_record(text.data() + lines[k].first, 0, (uint32_t)lines[k].second, r, 1u, nullptr, 0, 0);  // same column rules as the kernel
                 if (std::find(distinct.begin(), distinct.end(), r.qlen) == distinct.end()) distinct.push_back(r.qlen);
                 ++seen;
             }

@@ -122,9 +122,22 @@ struct RecParse {
     int64_t vmin, vmax;
     bool path_null;
     bool monotone;                    // strictly increasing or strictly decreasing ids => no repeats
+    bool stashed;                     // all W node ids were saved in the caller's stash (W <= cap, ids < 2^32)
 };
 
-// Is b[p] (== c, not a digit) a field/line terminator?  -1: ordinary byte.
+// Warp reconvergence points.  The per-column loops below have data-dependent trip counts; without an
+// explicit __syncwarp after each column the lanes of a warp drift apart for the rest of the record
+// (measured: 9.9 of 32 lanes active, profiles/r1a_ingest_ncu_summary.md).  `mask` = lanes that are
+// parsing a record in this pass; every one of them executes every PTX_RECONVERGE.
+#if defined(__CUDA_ARCH__)
+#define PTX_RECONVERGE(m) __syncwarp(m)
+#define PTX_WARP_MAX_U32(m, v) __reduce_max_sync((m), (v))
+#else
+#define PTX_RECONVERGE(m) ((void)(m))
+#define PTX_WARP_MAX_U32(m, v) (v)
+#endif
+
+// Is b[p] (== c, a byte <= '\r') a field/line terminator?  -1: ordinary byte.
 PTX_HD int term_at(const uint8_t* b, uint32_t p, uint32_t lim, uint8_t c) {
     if (c == '\t') return T_TAB;
     if (c == '\n') return T_EOL;
@@ -137,16 +150,17 @@ PTX_HD int term_at(const uint8_t* b, uint32_t p, uint32_t lim, uint8_t c) {
 
 // Advance to the end of the current field.  On T_TAB the tab is consumed.
 PTX_HD int skip_field(const uint8_t* b, uint32_t& p, uint32_t lim) {
-    for (;;) {
-        if (p >= lim) return T_LIMIT;
-        uint8_t c = b[p];
+    int t = T_LIMIT;
+    while (p < lim) {
+        const uint8_t c = b[p];
         if (c <= '\r') {  // '\t'=9 '\n'=10 '\r'=13
-            int t = term_at(b, p, lim, c);
-            if (t == T_TAB) { ++p; return T_TAB; }
-            if (t >= 0) return t;
+            const int q = term_at(b, p, lim, c);
+            if (q >= 0) { t = q; break; }
         }
         ++p;
     }
+    if (t == T_TAB) ++p;
+    return t;
 }
 
 // `[+-]?[0-9]{1,18}` over the whole field, else null (rcls.rs:132-134 non-strict cast).
@@ -163,15 +177,17 @@ PTX_HD int parse_int_field(const uint8_t* b, uint32_t& p, uint32_t lim, int64_t&
     }
     uint64_t v = 0;
     uint32_t nd = 0;
+    bool hit_lim = false;
     for (;;) {
-        uint32_t d = (uint32_t)c - (uint32_t)'0';
+        const uint32_t d = (uint32_t)c - (uint32_t)'0';
         if (d > 9u) break;
         v = v * 10u + d;
         ++nd;
         ++p;
-        if (p >= lim) return T_LIMIT;
+        if (p >= lim) { hit_lim = true; break; }
         c = b[p];
     }
+    if (hit_lim) return T_LIMIT;
     int t = term_at(b, p, lim, c);
     if (t == T_LIMIT) return T_LIMIT;
     if (t >= 0) {
@@ -182,10 +198,11 @@ PTX_HD int parse_int_field(const uint8_t* b, uint32_t& p, uint32_t lim, int64_t&
     return skip_field(b, p, lim);  // junk in an integer column -> null
 }
 
-// Parses columns 1..12 of the line starting at b[p].  Returns false if `lim` was hit
-// before column 12 (or the end of line) was reached; the caller retries on the
-// global-memory copy of the line.
-PTX_HD bool parse_record(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r) {
+// Parses columns 1..12 of the line starting at b[p].  Returns false if `lim` was hit before column 12
+// (or the end of line) was reached; the caller retries on the global-memory copy of the line.
+// `stash` (may be null): node ids of the walk are saved at stash[i * stash_stride], i < stash_cap.
+PTX_HD bool parse_record(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r, uint32_t mask, uint32_t* stash,
+                         uint32_t stash_stride, uint32_t stash_cap) {
     r.qlen = r.c7 = r.c8 = r.c9 = r.mapq = NULL_I64;
     r.path_pos = r.path_end = p;
     r.W = 0;
@@ -193,42 +210,41 @@ PTX_HD bool parse_record(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r
     r.vmax = -1;
     r.path_null = true;
     r.monotone = true;
-    int t;
+    r.stashed = false;
+    int st = T_TAB;  // T_TAB: more columns follow; T_EOL: line ended; T_LIMIT: window exhausted
     {  // column 1: read id -> 96-bit hash
         IdHasher H;
-        for (;;) {
-            if (p >= lim) return false;
-            uint8_t c = b[p];
+        st = T_LIMIT;
+        while (p < lim) {
+            const uint8_t c = b[p];
             if (c <= '\r') {
-                t = term_at(b, p, lim, c);
-                if (t == T_LIMIT) return false;
-                if (t >= 0) break;
+                const int q = term_at(b, p, lim, c);
+                if (q >= 0) { st = q; break; }
             }
             H.byte(c);
             ++p;
         }
         r.h = H.finish();
-        if (t == T_EOL) return true;
-        ++p;
+        if (st == T_TAB) ++p;
     }
-    t = parse_int_field(b, p, lim, r.qlen);  // column 2
-    if (t == T_LIMIT) return false;
-    if (t == T_EOL) return true;
+    PTX_RECONVERGE(mask);
+    if (st == T_TAB) st = parse_int_field(b, p, lim, r.qlen);  // column 2
+    PTX_RECONVERGE(mask);
+#pragma unroll 1
     for (int k = 0; k < 3; ++k) {  // columns 3,4,5
-        t = skip_field(b, p, lim);
-        if (t == T_LIMIT) return false;
-        if (t == T_EOL) return true;
+        if (st == T_TAB) st = skip_field(b, p, lim);
+        PTX_RECONVERGE(mask);
     }
-    {  // column 6: walk
+    if (st == T_TAB) {  // column 6: walk
         r.path_pos = p;
         uint64_t v = 0;
         uint32_t nd = 0;
         int64_t prev = 0;
-        bool inc = true, dec = true;
-        for (;;) {
-            if (p >= lim) return false;
-            uint8_t c = b[p];
-            uint32_t d = (uint32_t)c - (uint32_t)'0';
+        bool inc = true, dec = true, fits = true;
+        st = T_LIMIT;
+        while (p < lim) {
+            const uint8_t c = b[p];
+            const uint32_t d = (uint32_t)c - (uint32_t)'0';
             if (d <= 9u) {
                 v = v * 10u + d;
                 ++nd;
@@ -237,7 +253,7 @@ PTX_HD bool parse_record(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r
             }
             if (nd) {
                 if (nd <= 18) {
-                    int64_t m = (int64_t)v;
+                    const int64_t m = (int64_t)v;
                     if (r.W) {
                         if (m <= prev) inc = false;
                         if (m >= prev) dec = false;
@@ -245,39 +261,43 @@ PTX_HD bool parse_record(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r
                     prev = m;
                     if (m < r.vmin) r.vmin = m;
                     if (m > r.vmax) r.vmax = m;
+                    if (stash && r.W < stash_cap && v <= 0xFFFFFFFFull) stash[r.W * stash_stride] = (uint32_t)v;
+                    else fits = false;
                     ++r.W;
                 }
                 v = 0;
                 nd = 0;
             }
-            t = term_at(b, p, lim, c);
-            if (t == T_LIMIT) return false;
-            if (t >= 0) break;
+            if (c <= '\r') {
+                const int q = term_at(b, p, lim, c);
+                if (q >= 0) { st = q; break; }
+            }
             ++p;
         }
         r.path_end = p;
         r.monotone = inc || dec;
+        r.stashed = fits && stash != nullptr;
         r.path_null = (r.path_end - r.path_pos == 1u) && (b[r.path_pos] == '*');
-        if (t == T_EOL) return true;
-        ++p;
+        if (st == T_TAB) ++p;
     }
-    t = parse_int_field(b, p, lim, r.c7);
-    if (t == T_LIMIT) return false;
-    if (t == T_EOL) return true;
-    t = parse_int_field(b, p, lim, r.c8);
-    if (t == T_LIMIT) return false;
-    if (t == T_EOL) return true;
-    t = parse_int_field(b, p, lim, r.c9);
-    if (t == T_LIMIT) return false;
-    if (t == T_EOL) return true;
+    PTX_RECONVERGE(mask);
+    if (st == T_TAB) st = parse_int_field(b, p, lim, r.c7);
+    PTX_RECONVERGE(mask);
+    if (st == T_TAB) st = parse_int_field(b, p, lim, r.c8);
+    PTX_RECONVERGE(mask);
+    if (st == T_TAB) st = parse_int_field(b, p, lim, r.c9);
+    PTX_RECONVERGE(mask);
+#pragma unroll 1
     for (int k = 0; k < 2; ++k) {  // columns 10, 11
-        t = skip_field(b, p, lim);
-        if (t == T_LIMIT) return false;
-        if (t == T_EOL) return true;
+        if (st == T_TAB) st = skip_field(b, p, lim);
+        PTX_RECONVERGE(mask);
     }
-    t = parse_int_field(b, p, lim, r.mapq);  // column 12
-    if (t == T_LIMIT) return false;
-    return true;
+    if (st == T_TAB) {
+        st = parse_int_field(b, p, lim, r.mapq);  // column 12
+        if (st == T_TAB) st = T_EOL;               // anything after column 12 is ignored
+    }
+    PTX_RECONVERGE(mask);
+    return st != T_LIMIT;
 }
 
 // Iterates the digit runs (<= 18 digits) of b[p,end).
@@ -308,66 +328,80 @@ struct WalkIter {
 //   void set_bits(uint32_t g, int64_t lo, int64_t hi, uint32_t ln);   0 <= lo < hi <= ln
 //   void trio(uint32_t a, uint32_t b, uint32_t c, int64_t s);         global node indices, read order
 //   void error_start_gt_len(uint32_t label);
+// `mask`: lanes of the warp that call this together (lock-step over the node index).
 template <class Sink>
 PTX_HD void cover_record(const uint8_t* b, const RecParse& r, uint32_t label, int64_t range_start, int64_t node_base,
-                         Sink& sink) {
-    if (r.W == 0) return;  // profile.rs:794
+                         Sink& sink, uint32_t mask, const uint32_t* stash, uint32_t stash_stride) {
     const int64_t ps = r.c8, pe = r.c9;
     int64_t target = pe - ps;  // :800
     WalkIter it{b, r.path_pos, r.path_end};
-    int64_t m;
-    if (r.W == 1) {  // :811
-        it.next(m);
-        const uint32_t g = (uint32_t)(node_base + (m - range_start));
-        if (target < 0) return;  // :821-827
-        sink.add_bases(g, target);  // :829
-        const uint32_t ln = sink.len(g);
-        if (ps >= 0 && ps < pe && pe <= (int64_t)ln) sink.set_bits(g, ps, pe, ln);  // :832-835
-        return;
-    }
+    const bool stashed = r.stashed;
+    uint32_t W = r.W;               // W == 0: profile.rs:794 (nothing to do, but stay in lock-step)
+    const bool single = (W == 1);   // :811
     int64_t seen = 0;
     uint32_t ga = 0, gb = 0;
     int64_t rla = 0, rlb = 0;
-    for (uint32_t i = 0; i < r.W; ++i) {
-        it.next(m);
-        const uint32_t g = (uint32_t)(node_base + (m - range_start));
-        const int64_t ln = (int64_t)sink.len(g);
-        int64_t aln, lo, hi;
-        if (i == 0) {
-            if (ps > ln) { sink.error_start_gt_len(label); return; }  // :854 (a panic in the reference)
-            aln = ln - ps;
-            lo = ps;
-            hi = ln;  // min(ps + aln, ln) == ln
-        } else if (i == r.W - 1) {
-            if (target < seen) target = seen;  // :858
-            aln = target - seen;
-            lo = 0;
-            hi = aln < ln ? aln : ln;  // :871
-        } else {
-            aln = ln;  // :861
-            lo = 0;
-            hi = ln;
-        }
-        if (lo >= 0 && hi > lo) sink.set_bits(g, lo, hi, (uint32_t)ln);  // negative start wraps `as usize` -> empty
-        seen += aln;                                                      // :878
-        bool first = true;
-        int64_t rl = aln;
-        if (!r.monotone) {  // exact first-occurrence test (:879) against earlier walk positions
-            WalkIter jt{b, r.path_pos, r.path_end};
-            int64_t mj;
-            for (uint32_t j = 0; j < i; ++j) {
-                jt.next(mj);
-                if (mj == m) {
-                    first = false;
-                    rl = (j == 0) ? (ln - ps) : ln;  // what the first occurrence added (:880)
-                    break;
+    const uint32_t Wmax = PTX_WARP_MAX_U32(mask, W);
+    for (uint32_t i = 0; i < Wmax; ++i) {
+        if (i < W) {
+            int64_t m;
+            if (stashed) m = (int64_t)stash[i * stash_stride];
+            else it.next(m);
+            const uint32_t g = (uint32_t)(node_base + (m - range_start));
+            const int64_t ln = (int64_t)sink.len(g);
+            if (single) {
+                if (target >= 0) {              // :821-827 (target < 0: the read is skipped)
+                    sink.add_bases(g, target);  // :829
+                    if (ps >= 0 && ps < pe && pe <= ln) sink.set_bits(g, ps, pe, (uint32_t)ln);  // :832-835
+                }
+            } else {
+                int64_t aln, lo, hi;
+                bool ok = true;
+                if (i == 0) {
+                    if (ps > ln) {  // :854 (a panic in the reference): flag the species, drop the read
+                        sink.error_start_gt_len(label);
+                        ok = false;
+                        W = 0;
+                    }
+                    aln = ln - ps;
+                    lo = ps;
+                    hi = ln;  // min(ps + aln, ln) == ln
+                } else if (i == W - 1) {
+                    if (target < seen) target = seen;  // :858
+                    aln = target - seen;
+                    lo = 0;
+                    hi = aln < ln ? aln : ln;  // :871
+                } else {
+                    aln = ln;  // :861
+                    lo = 0;
+                    hi = ln;
+                }
+                if (ok) {
+                    if (lo >= 0 && hi > lo) sink.set_bits(g, lo, hi, (uint32_t)ln);  // negative start wraps `as usize` -> empty
+                    seen += aln;                                                      // :878
+                    bool first = true;
+                    int64_t rl = aln;
+                    if (!r.monotone) {  // exact first-occurrence test (:879) against earlier walk positions
+                        WalkIter jt{b, r.path_pos, r.path_end};
+                        for (uint32_t j = 0; j < i; ++j) {
+                            int64_t mj;
+                            if (stashed) mj = (int64_t)stash[j * stash_stride];
+                            else jt.next(mj);
+                            if (mj == m) {
+                                first = false;
+                                rl = (j == 0) ? (ln - ps) : ln;  // what the first occurrence added (:880)
+                                break;
+                            }
+                        }
+                    }
+                    if (first) sink.add_bases(g, aln);                  // :881
+                    if (i >= 2) sink.trio(ga, gb, g, rla + rlb + rl);   // :890-906
+                    ga = gb; rla = rlb;
+                    gb = g;  rlb = rl;
                 }
             }
         }
-        if (first) sink.add_bases(g, aln);  // :881
-        if (i >= 2) sink.trio(ga, gb, g, rla + rlb + rl);  // :890-906
-        ga = gb; rla = rlb;
-        gb = g;  rlb = rl;
+        PTX_RECONVERGE(mask);
     }
 }
 

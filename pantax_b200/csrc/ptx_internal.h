@@ -9,17 +9,20 @@
 namespace ptx {
 
 // ---- tile geometry of the GAF scan -------------------------------------------------
-// A chunk buffer is  [PRE '\n' bytes][text, whole lines][ '\n' padding to n_tiles*TILE + OVER ].
-// Tile t owns the newlines in text[t*TILE, (t+1)*TILE); the record FOLLOWING an owned
-// newline belongs to the tile, so a record starts in (t*TILE, (t+1)*TILE].  The first
-// record of the chunk (text[0], preceded by the PRE padding) belongs to tile 0.
-// The tile is staged in shared memory as text[t*TILE, t*TILE + STAGE).
-constexpr uint32_t TILE = 32768;
+// A chunk buffer is  [PRE '\n' bytes][text, whole lines][ '\n' padding ].
+// The text is cut into 4 KB micro-tiles; K1 counts the records of each (a record belongs to the
+// micro-tile that holds the newline BEFORE it; the first record of the chunk, preceded by the PRE
+// padding, belongs to micro-tile 0).  An ingest tile is a run of `rows_per_warp` (1..8) micro-tiles
+// (each of the CTA's 8 warps scans rows_per_warp rows of 512 B), chosen per chunk from the measured
+// mean line length so that a tile holds about one record per thread.  A record therefore starts in
+// (t*tile, (t+1)*tile]; the tile is staged in shared memory as text[t*tile, t*tile + tile + OVER).
+constexpr uint32_t MICRO = 4096;
+constexpr uint32_t MAX_TILE = 32768;
 constexpr uint32_t OVER = 2048;
-constexpr uint32_t STAGE = TILE + OVER;  // multiple of 16
-constexpr uint32_t PRE = 256;            // keeps `text` 256-byte aligned inside a cudaMalloc'ed buffer
+constexpr uint32_t PRE = 256;  // keeps `text` 256-byte aligned inside a cudaMalloc'ed buffer
 constexpr int INGEST_THREADS = 256;
-constexpr uint32_t REC_CAP = 4096;  // record starts kept in smem per round
+constexpr uint32_t REC_CAP = 1024;  // record starts kept in smem per round
+constexpr uint32_t STASH_CAP = 8;   // walk nodes per record kept in smem between the parse and the coverage pass
 
 // mode flags of the ingest kernel
 constexpr int MODE_CLASSIFY = 1;  // labels, species counts, read-id set insert
@@ -58,8 +61,10 @@ struct GraphDev {
 struct IngestArgs {
     const uint8_t* text;   // chunk text (buffer + PRE)
     uint64_t n_bytes;      // text bytes (whole lines)
+    uint64_t padded_bytes; // bytes readable from `text` (text + newline padding)
     uint32_t n_tiles;
-    const uint32_t* tile_base;  // [n_tiles] exclusive record prefix within the chunk (MODE_CLASSIFY)
+    uint32_t rows_per_warp;      // tile = rows_per_warp * 4096 bytes
+    const uint32_t* micro_base;  // [n_micro] exclusive record prefix per micro-tile within the chunk (MODE_CLASSIFY)
     uint32_t* labels;           // [chunk records]
     RangesView ranges;
     unsigned long long* hist;   // [S*4]
@@ -81,7 +86,7 @@ struct IngestArgs {
 };
 
 // launchers (ptx_kernels.cu); all asynchronous on `st`
-void launch_count_records(const uint8_t* text, uint64_t n_bytes, uint32_t n_tiles, uint32_t* tile_count, cudaStream_t st);
+void launch_count_records(const uint8_t* text, uint32_t n_micro, uint32_t* micro_count, cudaStream_t st);
 void launch_scan_tiles(const uint32_t* tile_count, uint32_t* tile_base, uint32_t n_tiles, uint64_t* total, cudaStream_t st);
 void launch_ingest(const IngestArgs& a, int mode, cudaStream_t st);
 void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2* new_slots, uint32_t new_shift,

@@ -1,6 +1,6 @@
 // sm_100a kernels of the PanTax alignment-to-abundance hot path.
 //
-//   K1  k_count_records / k_scan_tiles  newline index: records per 32 KB tile -> record numbering
+//   K1  k_count_records / k_scan_tiles  newline index: records per 4 KB micro-tile -> record numbering
 //   K2+ k_ingest<MODE>                  one CTA per tile: TMA bulk copy of the tile's text into
 //                                       shared memory, record-start compaction, then one thread per
 //                                       GAF record: column split + integer parse + walk decode
@@ -90,16 +90,19 @@ __device__ __forceinline__ bool valid_first(const uint8_t* b, uint32_t q) {
 }
 
 // =====================================================================================
-// K1: records per tile
+// K1: records per 4 KB micro-tile (one warp each); tiles of the ingest kernel are runs of micro-tiles
 // =====================================================================================
-__global__ void __launch_bounds__(256) k_count_records(const uint8_t* __restrict__ text, uint32_t* __restrict__ tile_count) {
-    const uint64_t t0 = (uint64_t)blockIdx.x * TILE;
-    const uint8_t* tb = text + t0;
+__global__ void __launch_bounds__(256) k_count_records(const uint8_t* __restrict__ text, uint32_t n_micro,
+                                                       uint32_t* __restrict__ micro_count) {
+    const uint32_t mt = blockIdx.x * 8u + (threadIdx.x >> 5);
+    if (mt >= n_micro) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint8_t* tb = text + (uint64_t)mt * MICRO;
     uint32_t cnt = 0;
 #pragma unroll
-    for (int k = 0; k < (int)(TILE / 16 / 256); ++k) {
-        uint32_t v = k * 256 + threadIdx.x;
-        uint4 q = __ldg(reinterpret_cast<const uint4*>(tb) + v);
+    for (int j = 0; j < (int)(MICRO / 512); ++j) {
+        const uint32_t off = (uint32_t)j * 512u + lane * 16u;
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(tb + off));
         uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -107,20 +110,13 @@ __global__ void __launch_bounds__(256) k_count_records(const uint8_t* __restrict
             while (m) {
                 uint32_t byte = (__ffs(m) - 1) >> 3;
                 m &= m - 1;
-                cnt += valid_first(tb, v * 16 + i * 4 + byte + 1) ? 1u : 0u;
+                cnt += valid_first(tb, off + i * 4 + byte + 1) ? 1u : 0u;
             }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) cnt += valid_first(tb, 0) ? 1u : 0u;
+    if (mt == 0 && lane == 0) cnt += valid_first(tb, 0) ? 1u : 0u;
     cnt = __reduce_add_sync(0xffffffffu, cnt);
-    __shared__ uint32_t ws[8];
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t s = 0;
-        for (int i = 0; i < 8; ++i) s += ws[i];
-        tile_count[blockIdx.x] = s;
-    }
+    if (lane == 0) micro_count[mt] = cnt;
 }
 
 __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
@@ -271,21 +267,28 @@ struct DevSink {
     __device__ __forceinline__ void error_start_gt_len(uint32_t label) { atomicOr(a.err + label, 1u); }
 };
 
-// rare path: the record did not fit in the staged window - parse it from global memory
-__device__ __noinline__ bool parse_record_global(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r) {
-    return parse_record(b, p, lim, r);
+// rare path: the record did not fit in the staged window - parse it from global memory.
+// Works on its own RecParse so that the caller's stays in registers.
+__device__ __noinline__ void parse_record_global(const uint8_t* b, uint32_t p, uint32_t lim, RecParse* out) {
+    RecParse r;
+    parse_record(b, p, lim, r, 1u << (threadIdx.x & 31u), nullptr, 0, 0);
+    *out = r;
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest(const IngestArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* stage = smem;
-    uint16_t* rec_start = reinterpret_cast<uint16_t*>(smem + STAGE);
+    uint8_t* stage = smem;                                                      // tile_bytes + OVER
+    uint32_t* stash = reinterpret_cast<uint32_t*>(smem + MAX_TILE + OVER);      // [STASH_CAP][INGEST_THREADS]
+    uint16_t* rec_start = reinterpret_cast<uint16_t*>(stash + STASH_CAP * INGEST_THREADS);  // [REC_CAP]
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t warp_tot[INGEST_THREADS / 32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint64_t t0 = (uint64_t)blockIdx.x * TILE;
+    const uint32_t rows = a.rows_per_warp;             // 1..8 rows of 512 B per warp
+    const uint32_t tile_bytes = rows * (INGEST_THREADS / 32u) * 512u;  // multiple of 4096
+    const uint32_t stage_bytes = tile_bytes + OVER;
+    const uint64_t t0 = (uint64_t)blockIdx.x * tile_bytes;
     const uint8_t* gtile = a.text + t0;
 
     // ---- stage the tile: one TMA bulk copy, completion on an mbarrier
@@ -295,28 +298,29 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest(const IngestArgs a
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(&mbar, STAGE);
-        bulk_g2s(stage, gtile, STAGE, &mbar);
+        mbar_expect_tx(&mbar, stage_bytes);
+        bulk_g2s(stage, gtile, stage_bytes, &mbar);
     }
     mbar_wait(&mbar, 0);
 
-    // ---- record starts: warp w scans stage[w*4096, +4096) as 8 rows of 32 x 16 B
-    constexpr int ROWS = TILE / (INGEST_THREADS / 32) / 512;  // 8
-    uint32_t c[ROWS];
-    const uint32_t wbase_byte = warp * (TILE / (INGEST_THREADS / 32));
+    // ---- record starts: warp w scans stage[w*rows*512, +rows*512) as `rows` rows of 32 x 16 B
+    uint32_t c[8];
+    const uint32_t wbase_byte = warp * rows * 512u;
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j) {
-        const uint32_t off = wbase_byte + (uint32_t)j * 512u + lane * 16u;
-        uint4 q = *reinterpret_cast<const uint4*>(stage + off);
-        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    for (int j = 0; j < 8; ++j) {
         uint32_t n = 0;
+        if ((uint32_t)j < rows) {
+            const uint32_t off = wbase_byte + (uint32_t)j * 512u + lane * 16u;
+            uint4 q = *reinterpret_cast<const uint4*>(stage + off);
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            uint32_t m = nl_mask4(w[i]);
-            while (m) {
-                uint32_t byte = (__ffs(m) - 1) >> 3;
-                m &= m - 1;
-                n += valid_first(stage, off + i * 4 + byte + 1) ? 1u : 0u;
+            for (int i = 0; i < 4; ++i) {
+                uint32_t m = nl_mask4(w[i]);
+                while (m) {
+                    uint32_t byte = (__ffs(m) - 1) >> 3;
+                    m &= m - 1;
+                    n += valid_first(stage, off + i * 4 + byte + 1) ? 1u : 0u;
+                }
             }
         }
         c[j] = n;
@@ -324,10 +328,10 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest(const IngestArgs a
     const bool first_rec = (blockIdx.x == 0 && tid == 0 && valid_first(stage, 0));
     if (first_rec) c[0] += 1;
     // exclusive position of (row j, lane) inside the warp, rows first
-    uint32_t pre[ROWS];
+    uint32_t pre[8];
     uint32_t run = 0;
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j) {
+    for (int j = 0; j < 8; ++j) {
         uint32_t x = c[j];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -346,14 +350,14 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest(const IngestArgs a
         if ((uint32_t)w < warp) my_base += t;
         n_rec += t;
     }
-    const uint32_t rec_base = (MODE & MODE_CLASSIFY) ? a.tile_base[blockIdx.x] : 0u;
-    const uint32_t glim = (uint32_t)min((uint64_t)0xFFFF0000ull, (uint64_t)a.n_tiles * TILE + OVER - t0);
+    const uint32_t rec_base = (MODE & MODE_CLASSIFY) ? a.micro_base[(uint64_t)blockIdx.x * rows] : 0u;
+    const uint32_t glim = (uint32_t)min((uint64_t)0xFFFF0000ull, a.padded_bytes - t0);
     const RangesView& R = a.ranges;
 
     for (uint32_t round = 0; round < n_rec; round += REC_CAP) {
         // ---- compact this round's record starts into shared memory
 #pragma unroll
-        for (int j = 0; j < ROWS; ++j) {
+        for (int j = 0; j < 8; ++j) {
             if (c[j] == 0) continue;
             uint32_t idx = my_base + pre[j];
             if (j == 0 && first_rec) {
@@ -380,22 +384,28 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest(const IngestArgs a
         __syncthreads();
         const uint32_t n_round = min(REC_CAP, n_rec - round);
 
-        // ---- one thread per record
+        // ---- one thread per record; the lanes of a warp move through the columns in lock-step
         for (uint32_t k0 = 0; k0 < n_round; k0 += INGEST_THREADS) {
             const uint32_t k = k0 + tid;
             const bool has = k < n_round;
+            const uint32_t pmask = __ballot_sync(0xffffffffu, has);
             RecParse r;
+            r.W = 0; r.mapq = NULL_I64; r.qlen = NULL_I64; r.stashed = false;
             uint32_t label = LABEL_U;
             const uint8_t* b = stage;
             if (has) {
                 const uint32_t p = rec_start[k];
-                if (!parse_record(stage, p, STAGE, r)) {
+                if (!parse_record(stage, p, stage_bytes, r, pmask, stash + tid, INGEST_THREADS, STASH_CAP)) {
+                    // the columns run past the staged window (at most one record per tile; long lines only)
+                    RecParse tmp;
                     b = gtile;
-                    parse_record_global(gtile, p, glim, r);
+                    parse_record_global(gtile, p, glim, &tmp);
+                    r = tmp;
                 }
                 label = classify(R, r.W ? r.vmin : -1, r.W ? r.vmax : -1);
                 if (MODE & MODE_CLASSIFY) a.labels[rec_base + round + k] = label;
             }
+            __syncwarp();
             if (MODE & MODE_CLASSIFY) {
                 // ---- species counts (profile.rs:219-232, 264-277), warp-aggregated when the warp is one species
                 const bool cnt = has && label != LABEL_U;
@@ -431,19 +441,24 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest(const IngestArgs a
                     }
                 }
             }
-            if (has && label != LABEL_U) {
-                const bool eligible = !r.path_null && r.c7 != NULL_I64 && r.c8 != NULL_I64 && r.c9 != NULL_I64;  // profile.rs:380-399
-                if (MODE & MODE_CLASSIFY) ds_insert(a.ds, a.ds_shift, a.ds_mask, r.h, eligible, label, a.flags);
-                if ((MODE & MODE_COVER) && eligible) {
-                    const int64_t nb = R.node_base[label];
-                    bool keep = nb >= 0;
+            const bool labelled = has && label != LABEL_U;
+            const bool eligible = labelled && !r.path_null && r.c7 != NULL_I64 && r.c8 != NULL_I64 && r.c9 != NULL_I64;  // profile.rs:380-399
+            if ((MODE & MODE_CLASSIFY) && labelled) ds_insert(a.ds, a.ds_shift, a.ds_mask, r.h, eligible, label, a.flags);
+            if (MODE & MODE_COVER) {
+                int64_t nb = -1;
+                bool keep = false;
+                if (eligible) {
+                    nb = R.node_base[label];
+                    keep = nb >= 0;
                     if ((MODE & MODE_KEEPMASK) && keep) keep = ds_lookup(a.ds, a.ds_shift, a.ds_mask, r.h) != DS_MIXED;  // :415-416
-                    if (keep) {
-                        DevSink sink{a};
-                        cover_record(b, r, label, R.start[label], nb, sink);
-                    }
+                }
+                const uint32_t cmask = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    DevSink sink{a};
+                    cover_record(b, r, label, R.start[label], nb, sink, cmask, stash + tid, INGEST_THREADS);
                 }
             }
+            __syncwarp();
         }
         __syncthreads();
     }
@@ -475,23 +490,41 @@ __global__ void __launch_bounds__(256) k_mark_path_dups(uint32_t* pnode, const u
 
 __global__ void __launch_bounds__(256) k_path_len_sum(const uint32_t* __restrict__ pnode, const uint64_t* __restrict__ poff, int64_t Htot,
                                                       int64_t P, const uint32_t* __restrict__ val, unsigned long long* out) {
-    // block handles 256*8 consecutive steps; per-path partial sums via a warp-aggregated atomic
-    const uint64_t k0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8ull;
-    if (k0 >= (uint64_t)P) return;
-    int64_t h = path_of_step(poff, Htot, k0);
-    unsigned long long acc = 0;
-    for (int i = 0; i < 8; ++i) {
-        const uint64_t k = k0 + i;
-        if (k >= (uint64_t)P) break;
-        while (k >= poff[h + 1]) {
-            if (acc) atomicAdd(out + h, acc);
-            acc = 0;
-            ++h;
-        }
-        const uint32_t g = pnode[k];
-        if (!(g & 0x80000000u)) acc += val[g];
+    // A block covers 256*16 consecutive steps (coalesced, strided by 256).  Steps of the block's first path
+    // are reduced in shared memory; the (rare) steps of later paths go straight to their accumulators.
+    constexpr int ITEMS = 16;
+    const uint64_t base = (uint64_t)blockIdx.x * 256ull * ITEMS;
+    __shared__ int64_t h0_s;
+    __shared__ uint64_t h0_end_s;
+    __shared__ unsigned long long ws[8];
+    if (threadIdx.x == 0) {
+        const int64_t h0 = path_of_step(poff, Htot, base);
+        h0_s = h0;
+        h0_end_s = poff[h0 + 1];
     }
-    if (acc) atomicAdd(out + h, acc);
+    __syncthreads();
+    const int64_t h0 = h0_s;
+    const uint64_t h0_end = h0_end_s;
+    unsigned long long acc = 0;
+#pragma unroll 4
+    for (int i = 0; i < ITEMS; ++i) {
+        const uint64_t k = base + (uint64_t)i * 256ull + threadIdx.x;
+        if (k >= (uint64_t)P) break;
+        const uint32_t g = pnode[k];
+        if (g & 0x80000000u) continue;  // node already counted for this path
+        const unsigned long long v = val[g];
+        if (k < h0_end) acc += v;
+        else atomicAdd(out + path_of_step(poff, Htot, k), v);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < 8; ++i) t += ws[i];
+        if (t) atomicAdd(out + h0, t);
+    }
 }
 
 __device__ __forceinline__ bool window_at(const uint32_t* __restrict__ pnode, const uint64_t* __restrict__ poff, int64_t Htot, uint64_t k,
@@ -737,8 +770,8 @@ static inline uint32_t grid_for(uint64_t n, uint32_t per_block, uint32_t cap = 1
     return (uint32_t)g;
 }
 
-void launch_count_records(const uint8_t* text, uint64_t, uint32_t n_tiles, uint32_t* tile_count, cudaStream_t st) {
-    k_count_records<<<n_tiles, 256, 0, st>>>(text, tile_count);
+void launch_count_records(const uint8_t* text, uint32_t n_micro, uint32_t* micro_count, cudaStream_t st) {
+    k_count_records<<<(n_micro + 7) / 8, 256, 0, st>>>(text, n_micro, micro_count);
     PTX_LAUNCHED();
 }
 void launch_scan_tiles(const uint32_t* tile_count, uint32_t* tile_base, uint32_t n_tiles, uint64_t* total, cudaStream_t st) {
@@ -748,7 +781,7 @@ void launch_scan_tiles(const uint32_t* tile_count, uint32_t* tile_base, uint32_t
 
 template <int MODE>
 static void launch_ingest_mode(const IngestArgs& a, cudaStream_t st) {
-    const size_t smem = STAGE + REC_CAP * sizeof(uint16_t);
+    const size_t smem = MAX_TILE + OVER + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + REC_CAP * sizeof(uint16_t);
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(k_ingest<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -784,7 +817,7 @@ void launch_mark_path_dups(uint32_t* pnode, const uint64_t* poff, const uint32_t
 void launch_path_len_sum(const uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, const uint32_t* val, unsigned long long* out,
                          cudaStream_t st) {
     if (P <= 0) return;
-    uint64_t nb = ((uint64_t)P + 256 * 8 - 1) / (256 * 8);
+    uint64_t nb = ((uint64_t)P + 256 * 16 - 1) / (256 * 16);
     k_path_len_sum<<<(uint32_t)nb, 256, 0, st>>>(pnode, poff, Htot, P, val, out);
     PTX_LAUNCHED();
 }

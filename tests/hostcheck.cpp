@@ -48,7 +48,7 @@ extern "C" {
 // shared-memory window) and re-parsed unbounded when parse_record reports overflow.
 int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, const int64_t* rend, const int64_t* node_base,
                   const uint32_t* order, int disjoint, int64_t N, const uint32_t* len, int64_t T, const uint32_t* trio_keys,
-                  uint32_t stage_lim, uint32_t* labels, int64_t* n_records, int64_t* hist, int64_t* bases, uint64_t* cov,
+                  uint32_t stage_lim, int use_stash, uint32_t* labels, int64_t* n_records, int64_t* hist, int64_t* bases, uint64_t* cov,
                   int64_t* trio_bases, uint32_t* err, int* ids_unique, int64_t* n_overflow) {
     RangesView R{rstart, rend, node_base, order, S, disjoint};
     std::vector<uint64_t> bit_off(N + 1, 0);
@@ -58,7 +58,7 @@ int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, 
     for (int64_t t = 0; t < T; ++t) tmap[std::make_tuple(trio_keys[3 * t], trio_keys[3 * t + 1], trio_keys[3 * t + 2])] = (uint32_t)t;
     std::vector<uint8_t> buf(gaf, gaf + n);
     buf.insert(buf.end(), 64, '\n');  // padding, as the chunk buffers have
-    struct Parsed { RecParse r; uint32_t label; uint32_t pos; bool eligible; };
+    struct Parsed { RecParse r; uint32_t label; uint32_t pos; bool eligible; uint32_t stash[8]; };
     std::vector<Parsed> recs;
     *n_overflow = 0;
     uint64_t i = 0;
@@ -73,10 +73,10 @@ int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, 
             bool ok = false;
             if (stage_lim) {
                 uint32_t lim = (uint32_t)std::min<uint64_t>(buf.size(), i + stage_lim);
-                ok = parse_record(buf.data(), (uint32_t)i, lim, p.r);
+                ok = parse_record(buf.data(), (uint32_t)i, lim, p.r, 1u, use_stash ? p.stash : nullptr, 1, 8);
                 if (!ok) ++*n_overflow;
             }
-            if (!ok) parse_record(buf.data(), (uint32_t)i, (uint32_t)buf.size(), p.r);
+            if (!ok) parse_record(buf.data(), (uint32_t)i, (uint32_t)buf.size(), p.r, 1u, use_stash ? p.stash : nullptr, 1, 8);
             p.label = classify(R, p.r.W ? p.r.vmin : -1, p.r.W ? p.r.vmax : -1);
             p.eligible = p.label != LABEL_U && !p.r.path_null && p.r.c7 != NULL_I64 && p.r.c8 != NULL_I64 && p.r.c9 != NULL_I64;
             recs.push_back(p);
@@ -110,7 +110,7 @@ int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, 
     for (const Parsed& p : recs) {
         if (!p.eligible || node_base[p.label] < 0) continue;
         if (mixed && ds[HashKey{p.r.h.lo, p.r.h.hi}] == DS_MIXED) continue;
-        cover_record(buf.data(), p.r, p.label, rstart[p.label], node_base[p.label], sink);
+        cover_record(buf.data(), p.r, p.label, rstart[p.label], node_base[p.label], sink, 1u, p.stash, 1);
     }
     for (int64_t g = 0; g < N; ++g) {
         uint64_t c = 0;

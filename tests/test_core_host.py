@@ -27,7 +27,7 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def run_hostcheck(ranges, graphs, gaf: bytes, oracle, stage_lim=0):
+def run_hostcheck(ranges, graphs, gaf: bytes, oracle, stage_lim=0, use_stash=1):
     """Feeds hostcheck the graph + the oracle's trio table (trio build is a separate kernel)."""
     L = lib()
     S = len(ranges)
@@ -66,15 +66,17 @@ def run_hostcheck(ranges, graphs, gaf: bytes, oracle, stage_lim=0):
     buf = (C.c_char * len(gaf)).from_buffer_copy(gaf)
     L.hostcheck_run(buf, C.c_uint64(len(gaf)), S, _p(rstart, C.c_int64), _p(rend, C.c_int64), _p(node_base, C.c_int64),
                     _p(order, C.c_uint32), disjoint, C.c_int64(N), _p(ln, C.c_uint32), C.c_int64(T), _p(tk, C.c_uint32),
-                    C.c_uint32(stage_lim), _p(labels, C.c_uint32), C.byref(nrec), _p(hist, C.c_int64), _p(bases, C.c_int64),
+                    C.c_uint32(stage_lim), use_stash, _p(labels, C.c_uint32), C.byref(nrec), _p(hist, C.c_int64), _p(bases, C.c_int64),
                     _p(cov, C.c_uint64), _p(tb, C.c_int64), _p(err, C.c_uint32), C.byref(uniq), C.byref(nover))
     return dict(labels=labels[:nrec.value], hist=hist, bases=bases, cov=cov, trio_bases=tb, err=err,
                 ids_unique=bool(uniq.value), node_base=node_base, tbase=tbase, n_overflow=nover.value)
 
 
-def assert_hostcheck_matches(ranges, graphs, gaf, stage_lim=0):
+def assert_hostcheck_matches(ranges, graphs, gaf, stage_lim=0, use_stash=1):
     o = run_cpu_oracle(ranges, graphs, gaf, threads=2)
-    h = run_hostcheck(ranges, graphs, gaf, o, stage_lim)
+    if use_stash:  # the re-parse path (no stash) must give the same answer
+        assert_hostcheck_matches(ranges, graphs, gaf, stage_lim, use_stash=0)
+    h = run_hostcheck(ranges, graphs, gaf, o, stage_lim, use_stash)
     np.testing.assert_array_equal(h["labels"], o.labels())
     np.testing.assert_array_equal(h["hist"], o.species_counts())
     assert h["ids_unique"] == o.ids_unique

@@ -185,3 +185,16 @@ def test_gpu_result_is_invariant_under_record_permutation():
         np.testing.assert_array_equal(a.node_bases(s), b.node_bases(s))
         np.testing.assert_array_equal(a.node_cov(s), b.node_cov(s))
         np.testing.assert_array_equal(a.trio_bases(s), b.trio_bases(s))
+
+
+@pytest.mark.parametrize("rows", [1, 3, 8])
+def test_gpu_every_tile_size_gives_the_same_answer(rows, monkeypatch):
+    """The ingest tile is rows*4 KB (chosen from the mean line length); force the extremes.  rows=1 makes
+    tiles with ~37 records, rows=8 tiles with more records than threads (second pass)."""
+    from gpu_common import gpu_vs_oracle
+    monkeypatch.setenv("PTX_TILE_ROWS", str(rows))
+    ds = synth.Dataset(61, [20000, 6000], [6, 3])
+    gaf = ds.gaf(4, 0, 40000, NASTY_DUP)
+    gpu_vs_oracle(ds.ranges(), dataset_graphs(ds), gaf)
+    gl = ds.gaf(6, 0, 2000, synth.GafParams(long_reads=True, id_pair_suffix=False))
+    gpu_vs_oracle(ds.ranges(), dataset_graphs(ds), gl)
