@@ -67,7 +67,8 @@ struct Chunk {
     uint32_t n_tiles = 0;
     uint32_t rows = 8;       // ingest tile = rows * 4096 bytes
     uint32_t* tile_count = nullptr;  // [n_micro]
-    uint32_t* tile_base = nullptr;   // [n_micro]
+    uint64_t* tile_base = nullptr;   // [n_micro + 1] exclusive record prefix, last = total
+    uint64_t* scan_scratch = nullptr;
     uint32_t* labels = nullptr;
     uint32_t tiles_cap = 0;
     int64_t labels_cap = 0;
@@ -260,6 +261,7 @@ void chunk_free(Chunk& ch) {
     dfree(ch.buf);
     dfree(ch.tile_count);
     dfree(ch.tile_base);
+    dfree(ch.scan_scratch);
     dfree(ch.labels);
     if (ch.copied) cudaEventDestroy(ch.copied);
     ch.copied = nullptr;
@@ -276,16 +278,18 @@ int chunk_process(ptx_ctx* ctx, Chunk& ch) {
     if (ch.tiles_cap < ch.n_micro) {
         dfree(ch.tile_count);
         dfree(ch.tile_base);
+        dfree(ch.scan_scratch);
         CU(cudaMalloc((void**)&ch.tile_count, ch.n_micro * sizeof(uint32_t)));
-        CU(cudaMalloc((void**)&ch.tile_base, ch.n_micro * sizeof(uint32_t)));
+        CU(cudaMalloc((void**)&ch.tile_base, ((size_t)ch.n_micro + 1) * sizeof(uint64_t)));
+        CU(cudaMalloc((void**)&ch.scan_scratch, ((size_t)ch.n_micro / 2048 + 4) * sizeof(uint64_t)));
         ch.tiles_cap = ch.n_micro;
     }
     ev_begin(ctx, ctx->ev_count);
     launch_count_records(ch.buf + PRE, ch.n_micro, ch.tile_count, ctx->st);
-    launch_scan_tiles(ch.tile_count, ch.tile_base, ch.n_micro, ctx->d_total, ctx->st);
+    launch_scan_u32(ch.tile_count, ch.tile_base, ch.n_micro, ch.scan_scratch, ctx->st);
     ev_end(ctx, ctx->ev_count);
     uint64_t total = 0;
-    CU(cudaMemcpyAsync(&total, ctx->d_total, sizeof total, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&total, ch.tile_base + ch.n_micro, sizeof total, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     ch.n_records = (int64_t)total;
     if (total > 0xFFFFFFF0ull) return fail(ctx, PTX_E_INVALID, "more than 2^32 records in one chunk");
@@ -894,7 +898,8 @@ int ptx_equal_length(ptx_ctx* ctx, int* is_equal, int64_t* read_len) {
         while (seen < 1000 && rec < ch.n_records && text_off < ch.n) {
             const size_t want = std::min<size_t>(ch.n - text_off, win);
             const bool to_end = text_off + want >= ch.n;
-            text.resize(want + 1);
+            text.resize(want + 2);
+            text[want + 1] = '\n';
             CU(cudaMemcpy(text.data(), ch.buf + PRE + text_off, want, cudaMemcpyDeviceToHost));
             text[want] = '\n';  // terminates an unterminated last line when the window reaches the end of the chunk
             std::vector<std::pair<size_t, size_t>> lines;  // start, length incl. '\n'
@@ -915,7 +920,7 @@ int ptx_equal_length(ptx_ctx* ctx, int* is_equal, int64_t* read_len) {
             for (size_t k = 0; k < lines.size() && seen < 1000; ++k) {
                 if (lab[k] == LABEL_U) continue;
                 RecParse r;
-                parse_record(text.data() + lines[k].first, 0, (uint32_t)lines[k].second, r, 1u, nullptr, 0, 0);  // same column rules as the kernel
+                parse_record(text.data() + lines[k].first, 0, 0xFFFFFFF0u, r, 1u, nullptr, 0, 0);  // the line's own '\n' stops the scanners;  // same column rules as the kernel
                 if (std::find(distinct.begin(), distinct.end(), r.qlen) == distinct.end()) distinct.push_back(r.qlen);
                 ++seen;
             }

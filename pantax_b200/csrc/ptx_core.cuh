@@ -128,34 +128,38 @@ struct RecParse {
 // Warp reconvergence points.  The per-column loops below have data-dependent trip counts; without an
 // explicit __syncwarp after each column the lanes of a warp drift apart for the rest of the record
 // (measured: 9.9 of 32 lanes active, profiles/r1a_ingest_ncu_summary.md).  `mask` = lanes that are
-// parsing a record in this pass; every one of them executes every PTX_RECONVERGE.
+// parsing a record in this pass; every one of them executes every PTX_RECONVERGE / PTX_WARP_*.
 #if defined(__CUDA_ARCH__)
 #define PTX_RECONVERGE(m) __syncwarp(m)
 #define PTX_WARP_MAX_U32(m, v) __reduce_max_sync((m), (v))
+#define PTX_WARP_ALL(m, p) __all_sync((m), (p))
 #else
 #define PTX_RECONVERGE(m) ((void)(m))
 #define PTX_WARP_MAX_U32(m, v) (v)
+#define PTX_WARP_ALL(m, p) (p)
 #endif
 
-// Is b[p] (== c, a byte <= '\r') a field/line terminator?  -1: ordinary byte.
-PTX_HD int term_at(const uint8_t* b, uint32_t p, uint32_t lim, uint8_t c) {
+// All scanning loops below stop at a '\n' and never test a byte limit: the caller guarantees that
+// b[lim] and b[lim+1] are '\n' (a sentinel behind the staged window / the newline padding of the chunk
+// buffer).  A line end found at p >= lim-1 is therefore reported as T_LIMIT ("window exhausted") and
+// the caller re-parses the record from global memory.
+
+// terminator class of byte c at b[p] (c <= '\r'): T_TAB, T_EOL or -1
+PTX_HD int term_at(const uint8_t* b, uint32_t p, uint8_t c) {
     if (c == '\t') return T_TAB;
     if (c == '\n') return T_EOL;
-    if (c == '\r') {
-        if (p + 1 >= lim) return T_LIMIT;
-        if (b[p + 1] == '\n') return T_EOL;
-    }
+    if (c == '\r' && b[p + 1] == '\n') return T_EOL;
     return -1;
 }
 
 // Advance to the end of the current field.  On T_TAB the tab is consumed.
-PTX_HD int skip_field(const uint8_t* b, uint32_t& p, uint32_t lim) {
-    int t = T_LIMIT;
-    while (p < lim) {
+PTX_HD int skip_field(const uint8_t* b, uint32_t& p) {
+    int t;
+    for (;;) {
         const uint8_t c = b[p];
         if (c <= '\r') {  // '\t'=9 '\n'=10 '\r'=13
-            const int q = term_at(b, p, lim, c);
-            if (q >= 0) { t = q; break; }
+            t = term_at(b, p, c);
+            if (t >= 0) break;
         }
         ++p;
     }
@@ -164,42 +168,40 @@ PTX_HD int skip_field(const uint8_t* b, uint32_t& p, uint32_t lim) {
 }
 
 // `[+-]?[0-9]{1,18}` over the whole field, else null (rcls.rs:132-134 non-strict cast).
-PTX_HD int parse_int_field(const uint8_t* b, uint32_t& p, uint32_t lim, int64_t& out) {
+PTX_HD int parse_int_field(const uint8_t* b, uint32_t& p, int64_t& out) {
     out = NULL_I64;
-    if (p >= lim) return T_LIMIT;
     uint8_t c = b[p];
     bool neg = false;
     if (c == '-' || c == '+') {
         neg = (c == '-');
-        ++p;
-        if (p >= lim) return T_LIMIT;
-        c = b[p];
+        c = b[++p];
     }
-    uint64_t v = 0;
-    uint32_t nd = 0;
-    bool hit_lim = false;
-    for (;;) {
-        const uint32_t d = (uint32_t)c - (uint32_t)'0';
-        if (d > 9u) break;
+    uint32_t d = (uint32_t)c - (uint32_t)'0';
+    uint32_t v32 = 0, nd = 0;
+    while (d <= 9u && nd < 9u) {  // up to 9 digits fit 32-bit arithmetic
+        v32 = v32 * 10u + d;
+        ++nd;
+        c = b[++p];
+        d = (uint32_t)c - (uint32_t)'0';
+    }
+    uint64_t v = v32;
+    while (d <= 9u) {  // long numbers: rare
         v = v * 10u + d;
         ++nd;
-        ++p;
-        if (p >= lim) { hit_lim = true; break; }
-        c = b[p];
+        c = b[++p];
+        d = (uint32_t)c - (uint32_t)'0';
     }
-    if (hit_lim) return T_LIMIT;
-    int t = term_at(b, p, lim, c);
-    if (t == T_LIMIT) return T_LIMIT;
+    const int t = term_at(b, p, c);
     if (t >= 0) {
         if (nd >= 1 && nd <= 18) out = neg ? -(int64_t)v : (int64_t)v;
         if (t == T_TAB) ++p;
         return t;
     }
-    return skip_field(b, p, lim);  // junk in an integer column -> null
+    return skip_field(b, p);  // junk in an integer column -> null
 }
 
-// Parses columns 1..12 of the line starting at b[p].  Returns false if `lim` was hit before column 12
-// (or the end of line) was reached; the caller retries on the global-memory copy of the line.
+// Parses columns 1..12 of the line starting at b[p].  Returns false if the columns do not end inside
+// the window b[0, lim) - the caller retries on the global-memory copy of the line.
 // `stash` (may be null): node ids of the walk are saved at stash[i * stash_stride], i < stash_cap.
 PTX_HD bool parse_record(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r, uint32_t mask, uint32_t* stash,
                          uint32_t stash_stride, uint32_t stash_cap) {
@@ -211,92 +213,115 @@ PTX_HD bool parse_record(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r
     r.path_null = true;
     r.monotone = true;
     r.stashed = false;
-    int st = T_TAB;  // T_TAB: more columns follow; T_EOL: line ended; T_LIMIT: window exhausted
+    int st;  // T_TAB: more columns follow; T_EOL: line ended; T_LIMIT: window exhausted
+#define PTX_CHECK_WINDOW()                                     \
+    do {                                                       \
+        if (st == T_EOL && p + 1u >= lim) st = T_LIMIT;        \
+        if (st == T_TAB && p >= lim) st = T_LIMIT;             \
+    } while (0)
     {  // column 1: read id -> 96-bit hash
         IdHasher H;
-        st = T_LIMIT;
-        while (p < lim) {
+        for (;;) {
             const uint8_t c = b[p];
             if (c <= '\r') {
-                const int q = term_at(b, p, lim, c);
-                if (q >= 0) { st = q; break; }
+                st = term_at(b, p, c);
+                if (st >= 0) break;
             }
             H.byte(c);
             ++p;
         }
         r.h = H.finish();
         if (st == T_TAB) ++p;
+        PTX_CHECK_WINDOW();
     }
     PTX_RECONVERGE(mask);
-    if (st == T_TAB) st = parse_int_field(b, p, lim, r.qlen);  // column 2
+    if (st == T_TAB) { st = parse_int_field(b, p, r.qlen); PTX_CHECK_WINDOW(); }  // column 2
     PTX_RECONVERGE(mask);
 #pragma unroll 1
     for (int k = 0; k < 3; ++k) {  // columns 3,4,5
-        if (st == T_TAB) st = skip_field(b, p, lim);
+        if (st == T_TAB) { st = skip_field(b, p); PTX_CHECK_WINDOW(); }
         PTX_RECONVERGE(mask);
     }
-    if (st == T_TAB) {  // column 6: walk
-        r.path_pos = p;
-        uint64_t v = 0;
-        uint32_t nd = 0;
+    {  // column 6: walk.  The lanes of the warp advance one NODE per iteration, in lock-step.
+        const bool had6 = (st == T_TAB);
+        bool done = !had6;
+        bool inc = true, dec = true, fits = (stash != nullptr);
         int64_t prev = 0;
-        bool inc = true, dec = true, fits = true;
-        st = T_LIMIT;
-        while (p < lim) {
-            const uint8_t c = b[p];
-            const uint32_t d = (uint32_t)c - (uint32_t)'0';
-            if (d <= 9u) {
-                v = v * 10u + d;
-                ++nd;
-                ++p;
-                continue;
-            }
-            if (nd) {
-                if (nd <= 18) {
-                    const int64_t m = (int64_t)v;
-                    if (r.W) {
-                        if (m <= prev) inc = false;
-                        if (m >= prev) dec = false;
+        if (had6) r.path_pos = p;
+        for (;;) {
+            if (!done) {
+                uint8_t c;
+                uint32_t d;
+                for (;;) {  // separator bytes ('>' '<' ...) up to the next digit or the end of the column
+                    c = b[p];
+                    d = (uint32_t)c - (uint32_t)'0';
+                    if (d <= 9u) break;
+                    if (c <= '\r') {
+                        st = term_at(b, p, c);
+                        if (st >= 0) { done = true; break; }
                     }
-                    prev = m;
-                    if (m < r.vmin) r.vmin = m;
-                    if (m > r.vmax) r.vmax = m;
-                    if (stash && r.W < stash_cap && v <= 0xFFFFFFFFull) stash[r.W * stash_stride] = (uint32_t)v;
-                    else fits = false;
-                    ++r.W;
+                    ++p;
                 }
-                v = 0;
-                nd = 0;
+                if (!done) {
+                    uint32_t v32 = 0, nd = 0;
+                    while (d <= 9u && nd < 9u) {
+                        v32 = v32 * 10u + d;
+                        ++nd;
+                        c = b[++p];
+                        d = (uint32_t)c - (uint32_t)'0';
+                    }
+                    uint64_t v = v32;
+                    while (d <= 9u) {  // ids of 10+ digits: rare
+                        v = v * 10u + d;
+                        ++nd;
+                        c = b[++p];
+                        d = (uint32_t)c - (uint32_t)'0';
+                    }
+                    if (nd <= 18) {  // longer runs are dropped (rcls.rs:244 parse().ok())
+                        const int64_t m = (int64_t)v;
+                        if (r.W) {
+                            if (m <= prev) inc = false;
+                            if (m >= prev) dec = false;
+                        }
+                        prev = m;
+                        if (m < r.vmin) r.vmin = m;
+                        if (m > r.vmax) r.vmax = m;
+                        if (fits && r.W < stash_cap && v <= 0xFFFFFFFFull) stash[r.W * stash_stride] = (uint32_t)v;
+                        else fits = false;
+                        ++r.W;
+                    }
+                }
             }
-            if (c <= '\r') {
-                const int q = term_at(b, p, lim, c);
-                if (q >= 0) { st = q; break; }
-            }
-            ++p;
+            if (PTX_WARP_ALL(mask, done)) break;
         }
-        r.path_end = p;
-        r.monotone = inc || dec;
-        r.stashed = fits && stash != nullptr;
-        r.path_null = (r.path_end - r.path_pos == 1u) && (b[r.path_pos] == '*');
-        if (st == T_TAB) ++p;
+        if (had6) {
+            r.path_end = p;
+            r.monotone = inc || dec;
+            r.stashed = fits;
+            r.path_null = (r.path_end - r.path_pos == 1u) && (b[r.path_pos] == '*');
+            if (st == T_TAB) ++p;
+            PTX_CHECK_WINDOW();
+        }
     }
     PTX_RECONVERGE(mask);
-    if (st == T_TAB) st = parse_int_field(b, p, lim, r.c7);
+    if (st == T_TAB) { st = parse_int_field(b, p, r.c7); PTX_CHECK_WINDOW(); }
     PTX_RECONVERGE(mask);
-    if (st == T_TAB) st = parse_int_field(b, p, lim, r.c8);
+    if (st == T_TAB) { st = parse_int_field(b, p, r.c8); PTX_CHECK_WINDOW(); }
     PTX_RECONVERGE(mask);
-    if (st == T_TAB) st = parse_int_field(b, p, lim, r.c9);
+    if (st == T_TAB) { st = parse_int_field(b, p, r.c9); PTX_CHECK_WINDOW(); }
     PTX_RECONVERGE(mask);
 #pragma unroll 1
     for (int k = 0; k < 2; ++k) {  // columns 10, 11
-        if (st == T_TAB) st = skip_field(b, p, lim);
+        if (st == T_TAB) { st = skip_field(b, p); PTX_CHECK_WINDOW(); }
         PTX_RECONVERGE(mask);
     }
     if (st == T_TAB) {
-        st = parse_int_field(b, p, lim, r.mapq);  // column 12
-        if (st == T_TAB) st = T_EOL;               // anything after column 12 is ignored
+        st = parse_int_field(b, p, r.mapq);  // column 12
+        PTX_CHECK_WINDOW();
+        if (st == T_TAB) st = T_EOL;  // anything after column 12 is ignored
     }
     PTX_RECONVERGE(mask);
+#undef PTX_CHECK_WINDOW
     return st != T_LIMIT;
 }
 

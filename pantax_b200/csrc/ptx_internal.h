@@ -22,7 +22,7 @@ constexpr uint32_t OVER = 2048;
 constexpr uint32_t PRE = 256;  // keeps `text` 256-byte aligned inside a cudaMalloc'ed buffer
 constexpr int INGEST_THREADS = 256;
 constexpr uint32_t REC_CAP = 1024;  // record starts kept in smem per round
-constexpr uint32_t STASH_CAP = 8;   // walk nodes per record kept in smem between the parse and the coverage pass
+constexpr uint32_t STASH_CAP = 16;  // walk nodes per record kept in smem between the parse and the coverage pass
 
 // mode flags of the ingest kernel
 constexpr int MODE_CLASSIFY = 1;  // labels, species counts, read-id set insert
@@ -64,7 +64,7 @@ struct IngestArgs {
     uint64_t padded_bytes; // bytes readable from `text` (text + newline padding)
     uint32_t n_tiles;
     uint32_t rows_per_warp;      // tile = rows_per_warp * 4096 bytes
-    const uint32_t* micro_base;  // [n_micro] exclusive record prefix per micro-tile within the chunk (MODE_CLASSIFY)
+    const uint64_t* micro_base;  // [n_micro] exclusive record prefix per micro-tile within the chunk (MODE_CLASSIFY)
     uint32_t* labels;           // [chunk records]
     RangesView ranges;
     unsigned long long* hist;   // [S*4]

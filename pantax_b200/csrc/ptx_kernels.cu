@@ -278,8 +278,8 @@ __device__ __noinline__ void parse_record_global(const uint8_t* b, uint32_t p, u
 template <int MODE>
 __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest(const IngestArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* stage = smem;                                                      // tile_bytes + OVER
-    uint32_t* stash = reinterpret_cast<uint32_t*>(smem + MAX_TILE + OVER);      // [STASH_CAP][INGEST_THREADS]
+    uint8_t* stage = smem;  // tile_bytes + OVER, then 16 sentinel '\n' (the column scanners stop at a newline)
+    uint32_t* stash = reinterpret_cast<uint32_t*>(smem + MAX_TILE + OVER + 16);  // [STASH_CAP][INGEST_THREADS]
     uint16_t* rec_start = reinterpret_cast<uint16_t*>(stash + STASH_CAP * INGEST_THREADS);  // [REC_CAP]
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t warp_tot[INGEST_THREADS / 32];
@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest(const IngestArgs a
         mbar_expect_tx(&mbar, stage_bytes);
         bulk_g2s(stage, gtile, stage_bytes, &mbar);
     }
+    if (tid < 4) reinterpret_cast<uint32_t*>(stage + stage_bytes)[tid] = 0x0a0a0a0au;  // sentinel behind the window
     mbar_wait(&mbar, 0);
 
     // ---- record starts: warp w scans stage[w*rows*512, +rows*512) as `rows` rows of 32 x 16 B
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest(const IngestArgs a
         if ((uint32_t)w < warp) my_base += t;
         n_rec += t;
     }
-    const uint32_t rec_base = (MODE & MODE_CLASSIFY) ? a.micro_base[(uint64_t)blockIdx.x * rows] : 0u;
+    const uint32_t rec_base = (MODE & MODE_CLASSIFY) ? (uint32_t)a.micro_base[(uint64_t)blockIdx.x * rows] : 0u;
     const uint32_t glim = (uint32_t)min((uint64_t)0xFFFF0000ull, a.padded_bytes - t0);
     const RangesView& R = a.ranges;
 
@@ -781,7 +782,7 @@ void launch_scan_tiles(const uint32_t* tile_count, uint32_t* tile_base, uint32_t
 
 template <int MODE>
 static void launch_ingest_mode(const IngestArgs& a, cudaStream_t st) {
-    const size_t smem = MAX_TILE + OVER + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + REC_CAP * sizeof(uint16_t);
+    const size_t smem = MAX_TILE + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + REC_CAP * sizeof(uint16_t);
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(k_ingest<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

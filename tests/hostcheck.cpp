@@ -71,12 +71,19 @@ int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, 
             Parsed p;
             p.pos = (uint32_t)i;
             bool ok = false;
-            if (stage_lim) {
-                uint32_t lim = (uint32_t)std::min<uint64_t>(buf.size(), i + stage_lim);
-                ok = parse_record(buf.data(), (uint32_t)i, lim, p.r, 1u, use_stash ? p.stash : nullptr, 1, 8);
-                if (!ok) ++*n_overflow;
+            if (stage_lim) {  // emulate the staged window: stage_lim bytes followed by the '\n' sentinel
+                std::vector<uint8_t> win(buf.begin() + i, buf.begin() + std::min<uint64_t>(buf.size(), i + stage_lim));
+                const uint32_t wl = (uint32_t)win.size();
+                win.insert(win.end(), 16, '\n');
+                ok = parse_record(win.data(), 0, wl, p.r, 1u, use_stash ? p.stash : nullptr, 1, 8);
+                if (ok) {  // positions are relative to the window: rebase onto buf
+                    p.r.path_pos += (uint32_t)i;
+                    p.r.path_end += (uint32_t)i;
+                } else {
+                    ++*n_overflow;
+                }
             }
-            if (!ok) parse_record(buf.data(), (uint32_t)i, (uint32_t)buf.size(), p.r, 1u, use_stash ? p.stash : nullptr, 1, 8);
+            if (!ok) parse_record(buf.data(), (uint32_t)i, (uint32_t)buf.size() - 2, p.r, 1u, use_stash ? p.stash : nullptr, 1, 8);
             p.label = classify(R, p.r.W ? p.r.vmin : -1, p.r.W ? p.r.vmax : -1);
             p.eligible = p.label != LABEL_U && !p.r.path_null && p.r.c7 != NULL_I64 && p.r.c8 != NULL_I64 && p.r.c9 != NULL_I64;
             recs.push_back(p);
