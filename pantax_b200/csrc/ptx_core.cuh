@@ -152,6 +152,22 @@ PTX_HD int term_at(const uint8_t* b, uint32_t p, uint8_t c) {
     return -1;
 }
 
+// Skip `n` whole fields in one loop (columns 3-5 and 10-11).  Returns T_TAB if n tabs were consumed.
+PTX_HD int skip_fields(const uint8_t* b, uint32_t& p, int n) {
+    for (;;) {
+        const uint8_t c = b[p];
+        if (c <= '\r') {  // '\t'=9 '\n'=10 '\r'=13
+            if (c == '\t') {
+                ++p;
+                if (--n == 0) return T_TAB;
+                continue;
+            }
+            if (c == '\n' || (c == '\r' && b[p + 1] == '\n')) return T_EOL;
+        }
+        ++p;
+    }
+}
+
 // Advance to the end of the current field.  On T_TAB the tab is consumed.
 PTX_HD int skip_field(const uint8_t* b, uint32_t& p) {
     int t;
@@ -213,12 +229,10 @@ PTX_HD bool parse_record(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r
     r.path_null = true;
     r.monotone = true;
     r.stashed = false;
-    int st;  // T_TAB: more columns follow; T_EOL: line ended; T_LIMIT: window exhausted
-#define PTX_CHECK_WINDOW()                                     \
-    do {                                                       \
-        if (st == T_EOL && p + 1u >= lim) st = T_LIMIT;        \
-        if (st == T_TAB && p >= lim) st = T_LIMIT;             \
-    } while (0)
+    int st;  // T_TAB: more columns follow; T_EOL: line ended
+    // No per-column window test: every scanner stops at the sentinel newline behind the window, and after
+    // a line end no further column is read - so p is compared with lim once, at the end.
+#define PTX_CHECK_WINDOW() ((void)0)
     {  // column 1: read id -> 96-bit hash
         IdHasher H;
         for (;;) {
@@ -237,11 +251,8 @@ PTX_HD bool parse_record(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r
     PTX_RECONVERGE(mask);
     if (st == T_TAB) { st = parse_int_field(b, p, r.qlen); PTX_CHECK_WINDOW(); }  // column 2
     PTX_RECONVERGE(mask);
-#pragma unroll 1
-    for (int k = 0; k < 3; ++k) {  // columns 3,4,5
-        if (st == T_TAB) { st = skip_field(b, p); PTX_CHECK_WINDOW(); }
-        PTX_RECONVERGE(mask);
-    }
+    if (st == T_TAB) st = skip_fields(b, p, 3);  // columns 3,4,5
+    PTX_RECONVERGE(mask);
     {  // column 6: walk.  The lanes of the warp advance one NODE per iteration, in lock-step.
         const bool had6 = (st == T_TAB);
         bool done = !had6;
@@ -310,11 +321,8 @@ PTX_HD bool parse_record(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r
     PTX_RECONVERGE(mask);
     if (st == T_TAB) { st = parse_int_field(b, p, r.c9); PTX_CHECK_WINDOW(); }
     PTX_RECONVERGE(mask);
-#pragma unroll 1
-    for (int k = 0; k < 2; ++k) {  // columns 10, 11
-        if (st == T_TAB) { st = skip_field(b, p); PTX_CHECK_WINDOW(); }
-        PTX_RECONVERGE(mask);
-    }
+    if (st == T_TAB) st = skip_fields(b, p, 2);  // columns 10, 11
+    PTX_RECONVERGE(mask);
     if (st == T_TAB) {
         st = parse_int_field(b, p, r.mapq);  // column 12
         PTX_CHECK_WINDOW();
@@ -322,7 +330,7 @@ PTX_HD bool parse_record(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r
     }
     PTX_RECONVERGE(mask);
 #undef PTX_CHECK_WINDOW
-    return st != T_LIMIT;
+    return p + 1u < lim;
 }
 
 // Iterates the digit runs (<= 18 digits) of b[p,end).

@@ -276,7 +276,7 @@ __device__ __noinline__ void parse_record_global(const uint8_t* b, uint32_t p, u
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest(const IngestArgs a) {
+__global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stage = smem;  // tile_bytes + OVER, then 16 sentinel '\n' (the column scanners stop at a newline)
     uint32_t* stash = reinterpret_cast<uint32_t*>(smem + MAX_TILE + OVER + 16);  // [STASH_CAP][INGEST_THREADS]
@@ -304,80 +304,87 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest(const IngestArgs a
     if (tid < 4) reinterpret_cast<uint32_t*>(stage + stage_bytes)[tid] = 0x0a0a0a0au;  // sentinel behind the window
     mbar_wait(&mbar, 0);
 
-    // ---- record starts: warp w scans stage[w*rows*512, +rows*512) as `rows` rows of 32 x 16 B
-    uint32_t c[8];
     const uint32_t wbase_byte = warp * rows * 512u;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        uint32_t n = 0;
-        if ((uint32_t)j < rows) {
-            const uint32_t off = wbase_byte + (uint32_t)j * 512u + lane * 16u;
-            uint4 q = *reinterpret_cast<const uint4*>(stage + off);
-            uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                uint32_t m = nl_mask4(w[i]);
-                while (m) {
-                    uint32_t byte = (__ffs(m) - 1) >> 3;
-                    m &= m - 1;
-                    n += valid_first(stage, off + i * 4 + byte + 1) ? 1u : 0u;
-                }
-            }
-        }
-        c[j] = n;
-    }
-    const bool first_rec = (blockIdx.x == 0 && tid == 0 && valid_first(stage, 0));
-    if (first_rec) c[0] += 1;
-    // exclusive position of (row j, lane) inside the warp, rows first
-    uint32_t pre[8];
-    uint32_t run = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        uint32_t x = c[j];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-            if (lane >= (uint32_t)d) x += y;
-        }
-        pre[j] = run + x - c[j];
-        run += __shfl_sync(0xffffffffu, x, 31);
-    }
-    if (lane == 0) warp_tot[warp] = run;
-    __syncthreads();
-    uint32_t my_base = 0, n_rec = 0;
-#pragma unroll
-    for (int w = 0; w < INGEST_THREADS / 32; ++w) {
-        uint32_t t = warp_tot[w];
-        if ((uint32_t)w < warp) my_base += t;
-        n_rec += t;
-    }
     const uint32_t rec_base = (MODE & MODE_CLASSIFY) ? (uint32_t)a.micro_base[(uint64_t)blockIdx.x * rows] : 0u;
     const uint32_t glim = (uint32_t)min((uint64_t)0xFFFF0000ull, a.padded_bytes - t0);
     const RangesView& R = a.ranges;
+    __syncthreads();  // sentinel visible
 
-    for (uint32_t round = 0; round < n_rec; round += REC_CAP) {
-        // ---- compact this round's record starts into shared memory
+    uint32_t n_rec = 0;
+    for (uint32_t round = 0; round == 0 || round < n_rec; round += REC_CAP) {
+        // ---- record starts: warp w scans stage[w*rows*512, +rows*512) as `rows` rows of 32 x 16 B.
+        // (Recomputed in the rare extra rounds of a tile with more than REC_CAP records, so that the
+        // per-row counters do not stay live in registers while the records are processed.)
+        {
+            uint32_t c[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (c[j] == 0) continue;
-            uint32_t idx = my_base + pre[j];
-            if (j == 0 && first_rec) {
-                if (idx >= round && idx < round + REC_CAP) rec_start[idx - round] = 0;
-                ++idx;
+            for (int j = 0; j < 8; ++j) {
+                uint32_t n = 0;
+                if ((uint32_t)j < rows) {
+                    const uint32_t off = wbase_byte + (uint32_t)j * 512u + lane * 16u;
+                    uint4 q = *reinterpret_cast<const uint4*>(stage + off);
+                    uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t m = nl_mask4(w[i]);
+                        while (m) {
+                            uint32_t byte = (__ffs(m) - 1) >> 3;
+                            m &= m - 1;
+                            n += valid_first(stage, off + i * 4 + byte + 1) ? 1u : 0u;
+                        }
+                    }
+                }
+                c[j] = n;
             }
-            const uint32_t off = wbase_byte + (uint32_t)j * 512u + lane * 16u;
-            uint4 q = *reinterpret_cast<const uint4*>(stage + off);
-            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            const bool first_rec = (blockIdx.x == 0 && tid == 0 && valid_first(stage, 0));
+            if (first_rec) c[0] += 1;
+            // exclusive position of (row j, lane) inside the warp, rows first
+            uint32_t pre[8];
+            uint32_t run = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                uint32_t m = nl_mask4(w[i]);
-                while (m) {
-                    uint32_t byte = (__ffs(m) - 1) >> 3;
-                    m &= m - 1;
-                    uint32_t qpos = off + i * 4 + byte + 1;
-                    if (valid_first(stage, qpos)) {
-                        if (idx >= round && idx < round + REC_CAP) rec_start[idx - round] = (uint16_t)qpos;
-                        ++idx;
+            for (int j = 0; j < 8; ++j) {
+                uint32_t x = c[j];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                    if (lane >= (uint32_t)d) x += y;
+                }
+                pre[j] = run + x - c[j];
+                run += __shfl_sync(0xffffffffu, x, 31);
+            }
+            if (lane == 0) warp_tot[warp] = run;
+            __syncthreads();
+            uint32_t my_base = 0;
+            n_rec = 0;
+#pragma unroll
+            for (int w = 0; w < INGEST_THREADS / 32; ++w) {
+                uint32_t t = warp_tot[w];
+                if ((uint32_t)w < warp) my_base += t;
+                n_rec += t;
+            }
+            // ---- compact this round's record starts into shared memory
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (c[j] == 0) continue;
+                uint32_t idx = my_base + pre[j];
+                if (j == 0 && first_rec) {
+                    if (idx >= round && idx < round + REC_CAP) rec_start[idx - round] = 0;
+                    ++idx;
+                }
+                const uint32_t off = wbase_byte + (uint32_t)j * 512u + lane * 16u;
+                uint4 q = *reinterpret_cast<const uint4*>(stage + off);
+                uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t m = nl_mask4(w[i]);
+                    while (m) {
+                        uint32_t byte = (__ffs(m) - 1) >> 3;
+                        m &= m - 1;
+                        uint32_t qpos = off + i * 4 + byte + 1;
+                        if (valid_first(stage, qpos)) {
+                            if (idx >= round && idx < round + REC_CAP) rec_start[idx - round] = (uint16_t)qpos;
+                            ++idx;
+                        }
                     }
                 }
             }
