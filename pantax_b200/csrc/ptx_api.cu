@@ -29,6 +29,10 @@ struct NcclApi {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     bool load() {
         if (h) return true;
@@ -41,7 +45,11 @@ struct NcclApi {
         AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
         AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
         GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
-        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather;
+        Send = (decltype(Send))dlsym(h, "ncclSend");
+        Recv = (decltype(Recv))dlsym(h, "ncclRecv");
+        GroupStart = (decltype(GroupStart))dlsym(h, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(h, "ncclGroupEnd");
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather && Send && Recv && GroupStart && GroupEnd;
     }
 };
 NcclApi g_nccl;
@@ -363,6 +371,85 @@ int check_results(ptx_ctx* ctx, int s) {
 int nccl_check(ptx_ctx* ctx, int r, const char* what) {
     if (r == 0) return PTX_OK;
     return fail(ctx, PTX_E_NCCL, "%s failed: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+}
+
+
+// profile.rs:369-378 / 406-437 across ranks: route every id-set entry to the rank owning its hash, merge the
+// per-rank states there, and tell every rank which ids ended up DS_MIXED.  Sets d_flags[0/1] on the ranks
+// that detect a repeat / a mixed group (the caller max-reduces the flags afterwards).
+int exchange_id_groups(ptx_ctx* ctx) {
+    const int P = ctx->n_ranks;
+    if (P <= 1 || !ctx->d_ds) return PTX_OK;
+    cudaStream_t st = ctx->st;
+    unsigned long long* d_cnt = nullptr;
+    int rc;
+    if ((rc = dalloc(ctx, &d_cnt, (size_t)P * 2 + 2))) return rc;
+    launch_ds_owner_count(ctx->d_ds, ctx->ds_cap, (uint32_t)P, d_cnt, st);
+    std::vector<unsigned long long> send_cnt(P), cursor(P);
+    CU(cudaMemcpyAsync(send_cnt.data(), d_cnt, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    unsigned long long n_send = 0;
+    for (int r = 0; r < P; ++r) { cursor[r] = n_send; n_send += send_cnt[r]; }
+    ulonglong2* sendbuf = nullptr;
+    if ((rc = dalloc(ctx, &sendbuf, (size_t)n_send + 1, false))) return rc;
+    unsigned long long* d_cursor = d_cnt + P;
+    CU(cudaMemcpyAsync(d_cursor, cursor.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    launch_ds_owner_scatter(ctx->d_ds, ctx->ds_cap, (uint32_t)P, d_cursor, sendbuf, st);
+    // counts matrix: all[r][q] = entries rank r sends to rank q
+    unsigned long long* d_all = nullptr;
+    if ((rc = dalloc(ctx, &d_all, (size_t)P * P))) return rc;
+    if ((rc = nccl_check(ctx, g_nccl.AllGather(d_cnt, d_all, P, ncclUint64, ctx->comm, st), "ncclAllGather(id counts)"))) return rc;
+    std::vector<unsigned long long> all((size_t)P * P);
+    CU(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    unsigned long long n_recv = 0;
+    std::vector<unsigned long long> roff(P);
+    for (int r = 0; r < P; ++r) { roff[r] = n_recv; n_recv += all[(size_t)r * P + ctx->rank]; }
+    ulonglong2* recvbuf = nullptr;
+    if ((rc = dalloc(ctx, &recvbuf, (size_t)n_recv + 1, false))) return rc;
+    g_nccl.GroupStart();
+    for (int r = 0; r < P; ++r) {
+        if (r == ctx->rank) continue;
+        if (send_cnt[r]) g_nccl.Send(sendbuf + cursor[r], send_cnt[r] * 2, ncclUint64, r, ctx->comm, st);
+        const unsigned long long nr = all[(size_t)r * P + ctx->rank];
+        if (nr) g_nccl.Recv(recvbuf + roff[r], nr * 2, ncclUint64, r, ctx->comm, st);
+    }
+    if ((rc = nccl_check(ctx, g_nccl.GroupEnd(), "ncclSend/Recv(id entries)"))) return rc;
+    if (send_cnt[ctx->rank])
+        CU(cudaMemcpyAsync(recvbuf + roff[ctx->rank], sendbuf + cursor[ctx->rank], send_cnt[ctx->rank] * sizeof(ulonglong2),
+                           cudaMemcpyDeviceToDevice, st));
+    // owner-side merge
+    const uint64_t ocap = 1ull << std::max<uint32_t>(10, log2_ceil(n_recv * 2 + 1));
+    ulonglong2* own = nullptr;
+    if ((rc = dalloc(ctx, &own, ocap))) return rc;
+    launch_ds_merge_insert(recvbuf, n_recv, own, 64 - log2_ceil(ocap), ocap - 1, ctx->d_flags, st);
+    // mixed ids -> everyone
+    unsigned long long* d_nmix = d_cnt + 2 * P;
+    CU(cudaMemsetAsync(d_nmix, 0, sizeof(unsigned long long), st));
+    launch_ds_collect_mixed(own, ocap, d_nmix, nullptr, 0, st);
+    unsigned long long* d_allmix = nullptr;
+    if ((rc = dalloc(ctx, &d_allmix, P))) return rc;
+    if ((rc = nccl_check(ctx, g_nccl.AllGather(d_nmix, d_allmix, 1, ncclUint64, ctx->comm, st), "ncclAllGather(mixed counts)"))) return rc;
+    std::vector<unsigned long long> nmix(P);
+    CU(cudaMemcpyAsync(nmix.data(), d_allmix, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    unsigned long long mx = 0;
+    for (auto v : nmix) mx = std::max(mx, v);
+    if (mx > 0) {
+        ulonglong2* mine = nullptr;
+        ulonglong2* everyone = nullptr;
+        if ((rc = dalloc(ctx, &mine, (size_t)mx)) || (rc = dalloc(ctx, &everyone, (size_t)mx * P))) return rc;
+        CU(cudaMemsetAsync(d_nmix, 0, sizeof(unsigned long long), st));
+        launch_ds_collect_mixed(own, ocap, d_nmix, mine, mx, st);
+        if ((rc = nccl_check(ctx, g_nccl.AllGather(mine, everyone, mx * 2, ncclUint64, ctx->comm, st), "ncclAllGather(mixed ids)"))) return rc;
+        launch_ds_apply_mixed(everyone, mx * P, ctx->d_ds, 64 - log2_ceil(ctx->ds_cap), ctx->ds_cap - 1, st);
+        CU(cudaStreamSynchronize(st));
+        cudaFree(mine);
+        cudaFree(everyone);
+    }
+    CU(cudaStreamSynchronize(st));
+    cudaFree(d_cnt); cudaFree(sendbuf); cudaFree(d_all); cudaFree(recvbuf); cudaFree(own); cudaFree(d_allmix);
+    return PTX_OK;
 }
 
 }  // namespace
@@ -747,8 +834,10 @@ int ptx_finalize(ptx_ctx* ctx) {
     GraphDev& g = ctx->g;
     const int S = (int)ctx->sp.size();
     ev_begin(ctx, ctx->ev_final);
-    if (ctx->comm) {  // a mixed id group / error seen on any rank is seen by all
-        int rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 2, ncclUint32, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(flags)");
+    if (ctx->comm) {  // id groups may span ranks; a mixed id group / error seen on any rank is seen by all
+        int rc = exchange_id_groups(ctx);
+        if (rc) return rc;
+        rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 2, ncclUint32, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(flags)");
         if (rc) return rc;
     }
     CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));

@@ -92,6 +92,12 @@ void launch_ingest(const IngestArgs& a, int mode, cudaStream_t st);
 void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2* new_slots, uint32_t new_shift,
                       uint64_t new_mask, cudaStream_t st);
 void launch_fill_u8(uint8_t* p, uint8_t v, uint64_t n, cudaStream_t st);
+// cross-rank id groups (multi-GPU finalize)
+void launch_ds_owner_count(const ulonglong2* slots, uint64_t cap, uint32_t P, unsigned long long* cnt, cudaStream_t st);
+void launch_ds_owner_scatter(const ulonglong2* slots, uint64_t cap, uint32_t P, unsigned long long* cursor, ulonglong2* out, cudaStream_t st);
+void launch_ds_merge_insert(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags, cudaStream_t st);
+void launch_ds_collect_mixed(const ulonglong2* slots, uint64_t cap, unsigned long long* cursor, ulonglong2* out, uint64_t out_cap, cudaStream_t st);
+void launch_ds_apply_mixed(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, cudaStream_t st);
 
 // graph commit
 void launch_mark_path_dups(uint32_t* pnode, const uint64_t* poff, const uint32_t* round_paths, uint32_t n_round_paths,

@@ -225,6 +225,106 @@ __global__ void __launch_bounds__(256) k_ds_rehash(const ulonglong2* __restrict_
     }
 }
 
+// ---- cross-rank id groups (multi-GPU): an id may repeat on ANOTHER rank's read batch ----------------
+// Every id-set entry is routed to the rank that owns its hash (owner = f(hash) % P); the owner merges the
+// per-rank states, and the hashes whose merged state is DS_MIXED are broadcast back.
+__device__ __forceinline__ uint32_t ds_owner(const ulonglong2& e, uint32_t P) {
+    return ((uint32_t)(e.y >> 32) ^ (uint32_t)(e.x >> 40)) % P;
+}
+__global__ void __launch_bounds__(256) k_ds_owner_count(const ulonglong2* __restrict__ slots, uint64_t cap, uint32_t P,
+                                                        unsigned long long* cnt) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cap; k += (uint64_t)gridDim.x * blockDim.x) {
+        ulonglong2 e = slots[k];
+        if (e.x == 0ull && e.y == 0ull) continue;
+        atomicAdd(cnt + ds_owner(e, P), 1ull);
+    }
+}
+__global__ void __launch_bounds__(256) k_ds_owner_scatter(const ulonglong2* __restrict__ slots, uint64_t cap, uint32_t P,
+                                                          unsigned long long* cursor, ulonglong2* __restrict__ out) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cap; k += (uint64_t)gridDim.x * blockDim.x) {
+        ulonglong2 e = slots[k];
+        if (e.x == 0ull && e.y == 0ull) continue;
+        out[atomicAdd(cursor + ds_owner(e, P), 1ull)] = e;
+    }
+}
+__device__ __forceinline__ uint32_t ds_merge_state(uint32_t l, uint32_t f) {
+    if (l == DS_NONE) return f;
+    if (f == DS_NONE || l == f) return l;
+    return DS_MIXED;
+}
+__global__ void __launch_bounds__(256) k_ds_merge_insert(const ulonglong2* __restrict__ in, uint64_t n, ulonglong2* slots, uint32_t shift,
+                                                         uint64_t mask, uint32_t* flags) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        const ulonglong2 e = in[k];
+        IdHash h;
+        h.lo = e.x;
+        h.hi = (uint32_t)(e.y >> 32);
+        const uint32_t fst = (uint32_t)e.y;
+        uint64_t i = ds_home(h, shift);
+        for (;;) {
+            ulonglong2 cur = ld128(slots + i);
+            if (cur.x == 0ull && cur.y == 0ull) {
+                cur = atomic_cas128(slots + i, make_ulonglong2(0ull, 0ull), e);
+                if (cur.x == 0ull && cur.y == 0ull) {
+                    if (fst == DS_MIXED) atomicOr(flags + 1, 1u);
+                    break;
+                }
+            }
+            if (cur.x == e.x && (cur.y >> 32) == (e.y >> 32)) {  // same id on two ranks (or twice on one)
+                atomicOr(flags + 0, 1u);
+                for (;;) {
+                    const uint32_t nst = ds_merge_state((uint32_t)cur.y, fst);
+                    if (nst == (uint32_t)cur.y) break;
+                    const ulonglong2 want = make_ulonglong2(cur.x, (cur.y & 0xFFFFFFFF00000000ull) | nst);
+                    const ulonglong2 prev = atomic_cas128(slots + i, cur, want);
+                    if (prev.x == cur.x && prev.y == cur.y) {
+                        if (nst == DS_MIXED) atomicOr(flags + 1, 1u);
+                        break;
+                    }
+                    cur = prev;
+                }
+                break;
+            }
+            i = (i + 1) & mask;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_ds_collect_mixed(const ulonglong2* __restrict__ slots, uint64_t cap, unsigned long long* cursor,
+                                                          ulonglong2* __restrict__ out, uint64_t out_cap) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cap; k += (uint64_t)gridDim.x * blockDim.x) {
+        ulonglong2 e = slots[k];
+        if ((e.x == 0ull && e.y == 0ull) || (uint32_t)e.y != DS_MIXED) continue;
+        const unsigned long long j = atomicAdd(cursor, 1ull);
+        if (out && j < out_cap) out[j] = e;
+    }
+}
+__global__ void __launch_bounds__(256) k_ds_apply_mixed(const ulonglong2* __restrict__ in, uint64_t n, ulonglong2* slots, uint32_t shift,
+                                                        uint64_t mask) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        const ulonglong2 e = in[k];
+        if (e.x == 0ull && e.y == 0ull) continue;  // padding of the all-gather
+        IdHash h;
+        h.lo = e.x;
+        h.hi = (uint32_t)(e.y >> 32);
+        uint64_t i = ds_home(h, shift);
+        for (;;) {
+            ulonglong2 cur = ld128(slots + i);
+            if (cur.x == 0ull && cur.y == 0ull) break;  // this rank never saw the id
+            if (cur.x == e.x && (cur.y >> 32) == (e.y >> 32)) {
+                for (;;) {
+                    if ((uint32_t)cur.y == DS_MIXED) break;
+                    const ulonglong2 want = make_ulonglong2(cur.x, (cur.y & 0xFFFFFFFF00000000ull) | DS_MIXED);
+                    const ulonglong2 prev = atomic_cas128(slots + i, cur, want);
+                    if (prev.x == cur.x && prev.y == cur.y) break;
+                    cur = prev;
+                }
+                break;
+            }
+            i = (i + 1) & mask;
+        }
+    }
+}
+
 // =====================================================================================
 // K2..K6/K8: the fused ingest kernel
 // =====================================================================================
@@ -810,6 +910,28 @@ void launch_ingest(const IngestArgs& a, int mode, cudaStream_t st) {
 void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2* new_slots, uint32_t new_shift, uint64_t new_mask,
                       cudaStream_t st) {
     k_ds_rehash<<<grid_for(old_cap, 256), 256, 0, st>>>(old_slots, old_cap, new_slots, new_shift, new_mask);
+    PTX_LAUNCHED();
+}
+void launch_ds_owner_count(const ulonglong2* slots, uint64_t cap, uint32_t P, unsigned long long* cnt, cudaStream_t st) {
+    k_ds_owner_count<<<grid_for(cap, 256), 256, 0, st>>>(slots, cap, P, cnt);
+    PTX_LAUNCHED();
+}
+void launch_ds_owner_scatter(const ulonglong2* slots, uint64_t cap, uint32_t P, unsigned long long* cursor, ulonglong2* out, cudaStream_t st) {
+    k_ds_owner_scatter<<<grid_for(cap, 256), 256, 0, st>>>(slots, cap, P, cursor, out);
+    PTX_LAUNCHED();
+}
+void launch_ds_merge_insert(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags, cudaStream_t st) {
+    if (n == 0) return;
+    k_ds_merge_insert<<<grid_for(n, 256), 256, 0, st>>>(in, n, slots, shift, mask, flags);
+    PTX_LAUNCHED();
+}
+void launch_ds_collect_mixed(const ulonglong2* slots, uint64_t cap, unsigned long long* cursor, ulonglong2* out, uint64_t out_cap, cudaStream_t st) {
+    k_ds_collect_mixed<<<grid_for(cap, 256), 256, 0, st>>>(slots, cap, cursor, out, out_cap);
+    PTX_LAUNCHED();
+}
+void launch_ds_apply_mixed(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, cudaStream_t st) {
+    if (n == 0) return;
+    k_ds_apply_mixed<<<grid_for(n, 256), 256, 0, st>>>(in, n, slots, shift, mask);
     PTX_LAUNCHED();
 }
 void launch_fill_u8(uint8_t* p, uint8_t v, uint64_t n, cudaStream_t st) {

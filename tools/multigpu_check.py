@@ -1,0 +1,62 @@
+"""Run under torchrun on N GPUs of one box: every rank ingests its read-batch shard, ptx_finalize reduces over
+NCCL, and every rank's result must equal the oracle's on the WHOLE input bit for bit (shard-count invariance)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import synth
+from common import NASTY, NASTY_DUP, dataset_graphs, run_cpu_oracle
+from gpu_common import assert_gpu_matches_oracle
+from pantax_b200 import api
+from pantax_b200.shard import shard_bounds_bytes
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    for name, params, n in (("unique ids", NASTY, 200000), ("duplicate ids across shards", NASTY_DUP, 100000)):
+        ds = synth.Dataset(91, [60000, 20000, 5000], [10, 3, 1])
+        gaf = ds.gaf(4, 0, n, params)
+        graphs = dataset_graphs(ds)
+        ctx = api.PantaxGpu(local)
+        ctx.set_ranges(ds.ranges())
+        for s, g in enumerate(graphs):
+            ctx.upload_graph(s, g[0], g[1])
+        ctx.commit_graphs()
+        uid = [api.PantaxGpu.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(world, rank, uid[0])
+        lo, hi = shard_bounds_bytes(gaf, world)[rank]
+        ctx.ingest_gaf(gaf[lo:hi], is_last=True)
+        ctx.finalize()
+        o = run_cpu_oracle(ds.ranges(), graphs, gaf)
+        n_rec = torch.tensor([ctx.num_records], device="cuda")
+        dist.all_reduce(n_rec)
+        assert int(n_rec.item()) == o.n_records, (int(n_rec.item()), o.n_records)
+        # labels are per-rank (row order of the shard); everything else is global
+        class View:  # adapts num_records for the shared assertion helper
+            pass
+        try:
+            orig = ctx.num_records
+            api.PantaxGpu.num_records = property(lambda self: o.n_records)
+            assert_gpu_matches_oracle(ctx, o, graphs, check_labels=False)
+        finally:
+            api.PantaxGpu.num_records = property(lambda self: self._L.ptx_num_records(self._h))
+        if rank == 0:
+            print(f"[multigpu_check] {name}: {world} ranks, {o.n_records} records, ids_unique={o.ids_unique}, "
+                  f"mixed-group reads dropped={o.mixed_dropped}: bit-exact on every rank", flush=True)
+        dist.barrier()
+        ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
