@@ -244,6 +244,21 @@ class PantaxGpu:
         self._ck(self._L.ptx_hap_trio_counts(self._h, s, _p(a, C.c_int64), _p(b, C.c_int64)))
         return a[:n], b[:n]
 
+    def filter_gaf(self, data: bytes):
+        """gaf_filter.rs:44-97: returns the kept lines (file order, first qualifying line per read id)."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        cap = data.count(b"\n") + 1
+        off = np.zeros(cap, dtype=np.uint64)
+        n_out = C.c_int64()
+        self._ck(self._L.ptx_filter_gaf(self._h, buf.ctypes.data, buf.size, _p(off, C.c_uint64), cap, C.byref(n_out)))
+        out = []
+        for o in off[: n_out.value]:
+            o = int(o)
+            e = data.find(b"\n", o)
+            line = data[o:e if e >= 0 else len(data)]
+            out.append(line[:-1] if line.endswith(b"\r") else line)
+        return out
+
     def timing(self):
         a, b, n = C.c_double(), C.c_double(), C.c_int64()
         self._ck(self._L.ptx_timing(self._h, C.byref(a), C.byref(b), C.byref(n)))
@@ -288,6 +303,11 @@ def path_cov_ratio(ctx: PantaxGpu, species: int, f32: bool = True) -> np.ndarray
     if f32:
         return (sc.astype(np.float32) / sl.astype(np.float32)).astype(np.float64)
     return sc.astype(np.float64) / sl.astype(np.float64)
+
+
+def filter_max_alignment_mt(ctx: PantaxGpu, gaf: bytes):
+    """gaf_filter.rs:44-97 (long-read pre-filter): the lines the reference writes to *_filtered.gaf."""
+    return ctx.filter_gaf(gaf)
 
 
 def hap_trio_counts(ctx: PantaxGpu, species: int):

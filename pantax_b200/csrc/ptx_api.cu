@@ -120,6 +120,10 @@ struct ptx_ctx {
     bool dirty = false;          // something ingested / committed since the last finalize
     uint32_t h_flags[2] = {0, 0};
     std::vector<uint32_t> h_err;
+    // reuse: chunk buffers released by ptx_reset, and one grow-only scratch arena for ptx_finalize
+    std::vector<Chunk> pool;
+    uint8_t* scratch = nullptr;
+    size_t scratch_cap = 0, scratch_off = 0;
     // timing
     std::vector<EvPair> ev_count, ev_ingest, ev_final;
     // multi-GPU
@@ -258,11 +262,41 @@ size_t padded_text_bytes(size_t n) {
 
 // allocate a chunk buffer able to hold `cap` text bytes; PRE bytes of '\n' in front
 int chunk_alloc(ptx_ctx* ctx, Chunk& ch, size_t cap) {
+    // reuse a released buffer of similar size (ptx_reset keeps them): no cudaMalloc on the steady-state path
+    int best = -1;
+    for (size_t i = 0; i < ctx->pool.size(); ++i)
+        if (ctx->pool[i].cap >= cap && ctx->pool[i].cap <= 2 * cap + (1u << 20) && (best < 0 || ctx->pool[i].cap < ctx->pool[best].cap)) best = (int)i;
+    if (best >= 0) {
+        ch = ctx->pool[best];
+        ctx->pool.erase(ctx->pool.begin() + best);
+        ch.n = 0; ch.n_records = 0; ch.ingested = false; ch.covered = false;
+        return PTX_OK;
+    }
+    ch = Chunk();
     ch.cap = cap;
     const size_t total = PRE + padded_text_bytes(cap);
     CU(cudaMalloc((void**)&ch.buf, total));
     CU(cudaMemsetAsync(ch.buf, '\n', PRE, ctx->st));
+    CU(cudaEventCreateWithFlags(&ch.copied, cudaEventDisableTiming));
     return PTX_OK;
+}
+
+// bump allocation from the grow-only finalize scratch arena (256-byte aligned); reset with scratch_off = 0
+int scratch_reserve(ptx_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_cap) return PTX_OK;
+    CU(cudaStreamSynchronize(ctx->st));
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_cap = 0;
+    CU(cudaMalloc((void**)&ctx->scratch, bytes));
+    ctx->scratch_cap = bytes;
+    return PTX_OK;
+}
+template <class T>
+T* scratch_take(ptx_ctx* ctx, size_t n) {
+    size_t off = (ctx->scratch_off + 255) & ~(size_t)255;
+    ctx->scratch_off = off + n * sizeof(T);
+    return reinterpret_cast<T*>(ctx->scratch + off);
 }
 
 void chunk_free(Chunk& ch) {
@@ -381,32 +415,37 @@ int exchange_id_groups(ptx_ctx* ctx) {
     const int P = ctx->n_ranks;
     if (P <= 1 || !ctx->d_ds) return PTX_OK;
     cudaStream_t st = ctx->st;
-    unsigned long long* d_cnt = nullptr;
     int rc;
-    if ((rc = dalloc(ctx, &d_cnt, (size_t)P * 2 + 2))) return rc;
+    // small counters live at the head of the arena; the big buffers are carved once their sizes are known
+    if ((rc = scratch_reserve(ctx, (size_t)64 << 20))) return rc;
+    ctx->scratch_off = 0;
+    unsigned long long* d_cnt = scratch_take<unsigned long long>(ctx, (size_t)P * 2 + 2);
+    unsigned long long* d_all = scratch_take<unsigned long long>(ctx, (size_t)P * P);
+    unsigned long long* d_allmix = scratch_take<unsigned long long>(ctx, P);
+    const size_t head = ctx->scratch_off;
+    CU(cudaMemsetAsync(d_cnt, 0, ((size_t)P * 2 + 2) * sizeof(unsigned long long), st));
     launch_ds_owner_count(ctx->d_ds, ctx->ds_cap, (uint32_t)P, d_cnt, st);
-    std::vector<unsigned long long> send_cnt(P), cursor(P);
-    CU(cudaMemcpyAsync(send_cnt.data(), d_cnt, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if ((rc = nccl_check(ctx, g_nccl.AllGather(d_cnt, d_all, P, ncclUint64, ctx->comm, st), "ncclAllGather(id counts)"))) return rc;
+    std::vector<unsigned long long> all((size_t)P * P), cursor(P), roff(P);
+    CU(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    unsigned long long n_send = 0;
+    const unsigned long long* send_cnt = &all[(size_t)ctx->rank * P];  // all[r][q] = entries rank r sends to rank q
+    unsigned long long n_send = 0, n_recv = 0;
     for (int r = 0; r < P; ++r) { cursor[r] = n_send; n_send += send_cnt[r]; }
-    ulonglong2* sendbuf = nullptr;
-    if ((rc = dalloc(ctx, &sendbuf, (size_t)n_send + 1, false))) return rc;
+    for (int r = 0; r < P; ++r) { roff[r] = n_recv; n_recv += all[(size_t)r * P + ctx->rank]; }
+    const uint64_t ocap = 1ull << std::max<uint32_t>(10, log2_ceil(n_recv * 2 + 1));
+    const size_t need = head + ((size_t)n_send + n_recv + ocap + 64) * sizeof(ulonglong2) + 4096;
+    if (need > ctx->scratch_cap) {  // grow once; the counters are recomputed cheaply
+        if ((rc = scratch_reserve(ctx, need + need / 4))) return rc;
+        return exchange_id_groups(ctx);
+    }
+    ulonglong2* sendbuf = scratch_take<ulonglong2>(ctx, (size_t)n_send + 1);
+    ulonglong2* recvbuf = scratch_take<ulonglong2>(ctx, (size_t)n_recv + 1);
+    ulonglong2* own = scratch_take<ulonglong2>(ctx, ocap);
     unsigned long long* d_cursor = d_cnt + P;
     CU(cudaMemcpyAsync(d_cursor, cursor.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
     launch_ds_owner_scatter(ctx->d_ds, ctx->ds_cap, (uint32_t)P, d_cursor, sendbuf, st);
-    // counts matrix: all[r][q] = entries rank r sends to rank q
-    unsigned long long* d_all = nullptr;
-    if ((rc = dalloc(ctx, &d_all, (size_t)P * P))) return rc;
-    if ((rc = nccl_check(ctx, g_nccl.AllGather(d_cnt, d_all, P, ncclUint64, ctx->comm, st), "ncclAllGather(id counts)"))) return rc;
-    std::vector<unsigned long long> all((size_t)P * P);
-    CU(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    unsigned long long n_recv = 0;
-    std::vector<unsigned long long> roff(P);
-    for (int r = 0; r < P; ++r) { roff[r] = n_recv; n_recv += all[(size_t)r * P + ctx->rank]; }
-    ulonglong2* recvbuf = nullptr;
-    if ((rc = dalloc(ctx, &recvbuf, (size_t)n_recv + 1, false))) return rc;
+    CU(cudaMemsetAsync(own, 0, ocap * sizeof(ulonglong2), st));
     g_nccl.GroupStart();
     for (int r = 0; r < P; ++r) {
         if (r == ctx->rank) continue;
@@ -419,16 +458,10 @@ int exchange_id_groups(ptx_ctx* ctx) {
         CU(cudaMemcpyAsync(recvbuf + roff[ctx->rank], sendbuf + cursor[ctx->rank], send_cnt[ctx->rank] * sizeof(ulonglong2),
                            cudaMemcpyDeviceToDevice, st));
     // owner-side merge
-    const uint64_t ocap = 1ull << std::max<uint32_t>(10, log2_ceil(n_recv * 2 + 1));
-    ulonglong2* own = nullptr;
-    if ((rc = dalloc(ctx, &own, ocap))) return rc;
     launch_ds_merge_insert(recvbuf, n_recv, own, 64 - log2_ceil(ocap), ocap - 1, ctx->d_flags, st);
     // mixed ids -> everyone
     unsigned long long* d_nmix = d_cnt + 2 * P;
-    CU(cudaMemsetAsync(d_nmix, 0, sizeof(unsigned long long), st));
     launch_ds_collect_mixed(own, ocap, d_nmix, nullptr, 0, st);
-    unsigned long long* d_allmix = nullptr;
-    if ((rc = dalloc(ctx, &d_allmix, P))) return rc;
     if ((rc = nccl_check(ctx, g_nccl.AllGather(d_nmix, d_allmix, 1, ncclUint64, ctx->comm, st), "ncclAllGather(mixed counts)"))) return rc;
     std::vector<unsigned long long> nmix(P);
     CU(cudaMemcpyAsync(nmix.data(), d_allmix, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -436,6 +469,7 @@ int exchange_id_groups(ptx_ctx* ctx) {
     unsigned long long mx = 0;
     for (auto v : nmix) mx = std::max(mx, v);
     if (mx > 0) {
+        // rare: few ids are mixed; these two small buffers are allocated ad hoc
         ulonglong2* mine = nullptr;
         ulonglong2* everyone = nullptr;
         if ((rc = dalloc(ctx, &mine, (size_t)mx)) || (rc = dalloc(ctx, &everyone, (size_t)mx * P))) return rc;
@@ -447,8 +481,6 @@ int exchange_id_groups(ptx_ctx* ctx) {
         cudaFree(mine);
         cudaFree(everyone);
     }
-    CU(cudaStreamSynchronize(st));
-    cudaFree(d_cnt); cudaFree(sendbuf); cudaFree(d_all); cudaFree(recvbuf); cudaFree(own); cudaFree(d_allmix);
     return PTX_OK;
 }
 
@@ -489,6 +521,8 @@ void ptx_destroy(ptx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto& ch : ctx->chunks) chunk_free(ch);
+    for (auto& ch : ctx->pool) chunk_free(ch);
+    dfree(ctx->scratch);
     free_graph(ctx);
     dfree(ctx->d_rstart); dfree(ctx->d_rend); dfree(ctx->d_node_base); dfree(ctx->d_order);
     dfree(ctx->d_hist); dfree(ctx->d_hist_g); dfree(ctx->d_flags); dfree(ctx->d_err); dfree(ctx->d_ds); dfree(ctx->d_total);
@@ -781,7 +815,6 @@ int ptx_ingest_gaf(ptx_ctx* ctx, const uint8_t* bytes, size_t n, int is_last) {
         if (c0) CU(cudaMemcpyAsync(ch.buf + PRE, ctx->carry.data(), c0, cudaMemcpyHostToDevice, ctx->copy_st));
         if (take) CU(cudaMemcpyAsync(ch.buf + PRE + c0, bytes + off, take, cudaMemcpyHostToDevice, ctx->copy_st));
         ch.n = c0 + take;
-        CU(cudaEventCreateWithFlags(&ch.copied, cudaEventDisableTiming));
         CU(cudaEventRecord(ch.copied, ctx->copy_st));
         ctx->chunks.push_back(ch);
         piece_idx.push_back(ctx->chunks.size() - 1);
@@ -871,13 +904,12 @@ int ptx_finalize(ptx_ctx* ctx) {
             if ((rc = nccl_check(ctx, g_nccl.AllReduce(g.full, g.full, g.N, ncclUint8, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(full)"))) return rc;
             if ((rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_err, ctx->d_err, S, ncclUint32, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(err)"))) return rc;
             // bitmap OR: all-gather the packed words, OR locally (NCCL has no bitwise-or reduction)
-            uint32_t* all = nullptr;
-            CU(cudaMalloc((void**)&all, (size_t)ctx->n_ranks * g.n_bit_words * sizeof(uint32_t)));
+            if ((rc = scratch_reserve(ctx, (size_t)ctx->n_ranks * g.n_bit_words * sizeof(uint32_t) + 4096))) return rc;
+            ctx->scratch_off = 0;
+            uint32_t* all = scratch_take<uint32_t>(ctx, (size_t)ctx->n_ranks * g.n_bit_words);
             if ((rc = nccl_check(ctx, g_nccl.AllGather(g.bits, all, g.n_bit_words, ncclUint32, ctx->comm, ctx->st), "ncclAllGather(bits)"))) return rc;
             for (int r = 0; r < ctx->n_ranks; ++r)
                 if (r != ctx->rank) launch_or_words(g.bits, all + (size_t)r * g.n_bit_words, g.n_bit_words, ctx->st);
-            CU(cudaStreamSynchronize(ctx->st));
-            cudaFree(all);
         }
         CU(cudaMemsetAsync(g.path_cov_sum, 0, std::max<int64_t>(g.Htot, 1) * sizeof(unsigned long long), ctx->st));
         CU(cudaMemsetAsync(g.hap_nz, 0, std::max<int64_t>(g.Htot, 1) * sizeof(unsigned long long), ctx->st));
@@ -907,7 +939,12 @@ static int reset_impl(ptx_ctx* ctx, bool keep_buffers) {
     if (keep_buffers) {
         for (auto& ch : ctx->chunks) { ch.ingested = false; ch.covered = false; ch.n_records = 0; }
     } else {
-        for (auto& ch : ctx->chunks) chunk_free(ch);
+        size_t pooled = 0;
+        for (auto& c : ctx->pool) pooled += c.cap;
+        for (auto& ch : ctx->chunks) {
+            if (pooled + ch.cap <= ((size_t)48 << 30) && ctx->pool.size() < 4096) { pooled += ch.cap; ctx->pool.push_back(ch); }
+            else chunk_free(ch);
+        }
         ctx->chunks.clear();
     }
     ctx->carry.clear();
@@ -1145,8 +1182,75 @@ int ptx_hap_trio_counts(ptx_ctx* ctx, int s, int64_t* U, int64_t* nz) {
     return PTX_OK;
 }
 
-int ptx_filter_gaf(ptx_ctx* ctx, const uint8_t*, size_t, uint64_t*, int64_t, int64_t*) {
-    return fail(ctx, PTX_E_UNSUPPORTED, "ptx_filter_gaf: not built yet (SURVEY.md section 8 row a11 / K10)");
+// gaf_filter.rs:44-97 on the GPU: newline index -> one thread per line (column split, i32/f64 parse) -> best
+// (matches, identity) per read id in a 128-bit-CAS hash table -> first qualifying line per id -> compaction.
+int ptx_filter_gaf(ptx_ctx* ctx, const uint8_t* bytes, size_t n, uint64_t* out_line_off, int64_t cap, int64_t* n_out) {
+    if (!ctx || (!bytes && n) || !n_out || (cap > 0 && !out_line_off)) return fail(ctx, PTX_E_INVALID, "ptx_filter_gaf: bad arguments");
+    cudaSetDevice(ctx->device);
+    *n_out = 0;
+    if (n == 0) return PTX_OK;
+    cudaStream_t st = ctx->st;
+    const bool add_nl = bytes[n - 1] != '\n';
+    const uint64_t nn = n + (add_nl ? 1 : 0);
+    const uint32_t n_micro = (uint32_t)((nn + MICRO - 1) / MICRO);
+    uint8_t* d_text = nullptr;
+    uint32_t* d_cnt = nullptr;
+    uint64_t *d_base = nullptr, *d_scratch = nullptr, *d_line = nullptr, *d_scan = nullptr, *d_out = nullptr;
+    uint32_t *d_sel = nullptr, *d_flags = nullptr;
+    uint8_t* d_qual = nullptr;
+    uint8_t* d_recs = nullptr;
+    ulonglong2 *d_keys = nullptr, *d_best = nullptr;
+    unsigned long long* d_first = nullptr;
+    int rc = PTX_OK;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(st);
+        cudaFree(d_text); cudaFree(d_cnt); cudaFree(d_base); cudaFree(d_scratch); cudaFree(d_line); cudaFree(d_scan); cudaFree(d_out);
+        cudaFree(d_sel); cudaFree(d_flags); cudaFree(d_qual); cudaFree(d_recs); cudaFree(d_keys); cudaFree(d_best); cudaFree(d_first);
+    };
+#define FLT(call) do { if ((rc = (call)) != PTX_OK) { cleanup(); return rc; } } while (0)
+    FLT(dalloc(ctx, &d_text, (size_t)n_micro * MICRO + 64, false));
+    if (cudaMemcpyAsync(d_text, bytes, n, cudaMemcpyHostToDevice, st) != cudaSuccess) { cleanup(); return fail(ctx, PTX_E_CUDA, "H2D copy failed"); }
+    cudaMemsetAsync(d_text + n, '\n', (size_t)n_micro * MICRO + 64 - n, st);
+    FLT(dalloc(ctx, &d_cnt, n_micro, false));
+    FLT(dalloc(ctx, &d_base, (size_t)n_micro + 1, false));
+    FLT(dalloc(ctx, &d_scratch, (size_t)n_micro / 2048 + 4, false));
+    launch_flt_count_nl(d_text, nn, n_micro, d_cnt, st);
+    launch_scan_u32(d_cnt, d_base, n_micro, d_scratch, st);
+    uint64_t n_lines = 0;
+    cudaMemcpyAsync(&n_lines, d_base + n_micro, sizeof n_lines, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) { cleanup(); return fail(ctx, PTX_E_CUDA, "filter: newline index failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    FLT(dalloc(ctx, &d_line, (size_t)n_lines + 2, false));
+    launch_flt_line_starts(d_text, nn, n_micro, d_base, d_line, st);
+    const uint64_t tcap = 1ull << std::max<uint32_t>(10, log2_ceil(n_lines * 2 + 1));
+    FLT(dalloc(ctx, &d_recs, (size_t)n_lines * flt_rec_bytes() + 64, false));
+    FLT(dalloc(ctx, &d_keys, tcap));
+    FLT(dalloc(ctx, &d_best, tcap));
+    FLT(dalloc(ctx, &d_first, tcap, false));
+    cudaMemsetAsync(d_first, 0xFF, tcap * sizeof(unsigned long long), st);
+    FLT(dalloc(ctx, &d_qual, (size_t)n_lines + 1, false));
+    FLT(dalloc(ctx, &d_sel, (size_t)n_lines + 1, false));
+    FLT(dalloc(ctx, &d_flags, 4));
+    FLT(dalloc(ctx, &d_scan, (size_t)n_lines + 2, false));
+    launch_flt_pipeline(d_text, nn, d_line, n_lines, d_recs, d_keys, d_best, d_first, tcap - 1, 64 - log2_ceil(tcap), d_qual, d_sel, d_flags, st);
+    dfree(d_scratch);
+    FLT(dalloc(ctx, &d_scratch, (size_t)n_lines / 2048 + 4, false));
+    launch_scan_u32(d_sel, d_scan, n_lines, d_scratch, st);
+    uint64_t n_sel = 0;
+    uint32_t h_flags[4] = {0, 0, 0, 0};
+    cudaMemcpyAsync(&n_sel, d_scan + n_lines, sizeof n_sel, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) { cleanup(); return fail(ctx, PTX_E_CUDA, "filter kernels failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    if (h_flags[2]) { cleanup(); return fail(ctx, PTX_E_UNSUPPORTED, "identity field outside the exactly-representable range (more than 15 significant digits, |exp10| > 22, inf or nan)"); }
+    *n_out = (int64_t)n_sel;
+    const uint64_t ncopy = std::min<uint64_t>(n_sel, cap > 0 ? (uint64_t)cap : 0);
+    if (ncopy) {
+        FLT(dalloc(ctx, &d_out, (size_t)ncopy, false));
+        launch_flt_compact(d_sel, d_scan, d_line, n_lines, d_out, ncopy, st);
+        cudaMemcpyAsync(out_line_off, d_out, ncopy * sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+    }
+#undef FLT
+    cleanup();
+    return PTX_OK;
 }
 
 int ptx_comm_unique_id(void* out128) {

@@ -124,6 +124,16 @@ void launch_depth(const unsigned long long* num, const uint32_t* den32, const in
 // OR-merge a peer's bitmap / full flags into ours (multi-GPU finalize)
 void launch_or_words(uint32_t* dst, const uint32_t* src, uint64_t n_words, cudaStream_t st);
 
+// K10 long-read filter
+void launch_flt_count_nl(const uint8_t* text, uint64_t n, uint32_t n_micro, uint32_t* cnt, cudaStream_t st);
+void launch_flt_line_starts(const uint8_t* text, uint64_t n, uint32_t n_micro, const uint64_t* micro_base, uint64_t* line_off, cudaStream_t st);
+size_t flt_rec_bytes();
+void launch_flt_pipeline(const uint8_t* text, uint64_t n, const uint64_t* line_off, uint64_t n_lines, void* recs, ulonglong2* keys,
+                         ulonglong2* best, unsigned long long* first, uint64_t mask, uint32_t shift, uint8_t* qual, uint32_t* sel,
+                         uint32_t* flags, cudaStream_t st);
+void launch_flt_compact(const uint32_t* sel, const uint64_t* scan, const uint64_t* line_off, uint64_t n_lines, uint64_t* out, uint64_t cap,
+                        cudaStream_t st);
+
 int64_t kernel_launch_count();
 
 }  // namespace ptx

@@ -869,6 +869,287 @@ __global__ void __launch_bounds__(256) k_fill_u8(uint8_t* p, uint8_t v, uint64_t
 }
 
 // =====================================================================================
+// K10: long-read best-alignment filter (gaf_filter.rs:22-97)
+// =====================================================================================
+// newlines per 4 KB micro-tile (one warp each)
+__global__ void __launch_bounds__(256) k_flt_count_nl(const uint8_t* __restrict__ text, uint64_t n, uint32_t n_micro, uint32_t* __restrict__ cnt) {
+    const uint32_t mt = blockIdx.x * 8u + (threadIdx.x >> 5);
+    if (mt >= n_micro) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t base = (uint64_t)mt * MICRO;
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < (int)(MICRO / 512); ++j) {
+        const uint64_t off = base + (uint64_t)j * 512u + lane * 16u;
+        if (off >= n) break;
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(text + off));
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t m = nl_mask4(w[i]);
+            const uint64_t wo = off + i * 4;
+            if (wo + 4 > n) {  // the last word may reach into the padding
+                uint32_t keep = 0;
+                for (int k = 0; k < 4; ++k)
+                    if (wo + k < n) keep |= 0x80u << (8 * k);
+                m &= keep;
+            }
+            c += __popc(m);
+        }
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) cnt[mt] = c;
+}
+// line i+1 starts behind the i-th newline; line 0 starts at 0
+__global__ void __launch_bounds__(256) k_flt_line_starts(const uint8_t* __restrict__ text, uint64_t n, uint32_t n_micro,
+                                                         const uint64_t* __restrict__ micro_base, uint64_t* __restrict__ line_off) {
+    const uint32_t mt = blockIdx.x * 8u + (threadIdx.x >> 5);
+    if (mt >= n_micro) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t base = (uint64_t)mt * MICRO;
+    uint64_t idx = micro_base[mt];
+    if (mt == 0 && lane == 0) line_off[0] = 0;
+    for (int j = 0; j < (int)(MICRO / 512); ++j) {
+        const uint64_t off = base + (uint64_t)j * 512u + lane * 16u;
+        uint32_t c = 0;
+        uint32_t msk[4] = {0, 0, 0, 0};
+        if (off < n) {
+            uint4 q = __ldg(reinterpret_cast<const uint4*>(text + off));
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint32_t m = nl_mask4(w[i]);
+                const uint64_t wo = off + i * 4;
+                if (wo + 4 > n) {
+                    uint32_t keep = 0;
+                    for (int k = 0; k < 4; ++k)
+                        if (wo + k < n) keep |= 0x80u << (8 * k);
+                    m &= keep;
+                }
+                msk[i] = m;
+                c += __popc(m);
+            }
+        }
+        uint32_t x = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= (uint32_t)d) x += y;
+        }
+        uint64_t my = idx + x - c;
+        idx += __shfl_sync(0xffffffffu, x, 31);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t m = msk[i];
+            while (m) {
+                uint32_t byte = (__ffs(m) - 1) >> 3;
+                m &= m - 1;
+                line_off[++my] = off + i * 4 + byte + 1;
+            }
+        }
+    }
+}
+
+struct FltRec {  // one parsed line (gaf_filter.rs:12-20)
+    ulonglong2 key;   // read-id hash, {0,0} = line rejected by parse_line
+    long long matches;
+    double ident;
+    int mapq, span;
+};
+
+__device__ __forceinline__ bool flt_ws(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }
+
+// Rust `str::parse::<i32>`: [+-]?digits, no whitespace, must fit i32
+__device__ bool flt_parse_i32(const uint8_t* p, uint32_t n, int& out) {
+    if (n == 0) return false;
+    uint32_t i = 0;
+    bool neg = false;
+    if (p[0] == '+' || p[0] == '-') { neg = p[0] == '-'; i = 1; }
+    if (i == n) return false;
+    long long v = 0;
+    for (; i < n; ++i) {
+        uint32_t d = (uint32_t)p[i] - '0';
+        if (d > 9u) return false;
+        v = v * 10 + d;
+        if (v > 2147483648ll) return false;
+    }
+    v = neg ? -v : v;
+    if (v < -2147483648ll || v > 2147483647ll) return false;
+    out = (int)v;
+    return true;
+}
+
+// Decimal -> double for [+-]?digits[.digits][e[+-]digits] with <= 15 significant digits and a decimal exponent in
+// [-22, 22]: both factors are exact doubles, so one IEEE multiply/divide is correctly rounded (the same value
+// Rust's f64::from_str returns).  status: 0 ok, 1 not a number (line rejected), 2 outside the exact range.
+__device__ int flt_parse_f64(const uint8_t* p, uint32_t n, double& out) {
+    const double P10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    if (n == 0) return 1;
+    uint32_t i = 0;
+    bool neg = false;
+    if (p[0] == '+' || p[0] == '-') { neg = p[0] == '-'; i = 1; }
+    unsigned long long mant = 0;
+    int sig = 0, exp10 = 0, nd = 0;
+    bool dot = false;
+    for (; i < n; ++i) {
+        uint8_t c = p[i];
+        uint32_t d = (uint32_t)c - '0';
+        if (d <= 9u) {
+            ++nd;
+            if (mant == 0 && d == 0) { if (dot) --exp10; continue; }  // leading zeros
+            if (sig < 19) { mant = mant * 10 + d; ++sig; if (dot) --exp10; }
+            else { if (d != 0) return 2; if (!dot) ++exp10; }
+        } else if (c == '.' && !dot) {
+            dot = true;
+        } else {
+            break;
+        }
+    }
+    if (nd == 0) return (n - i >= 3) ? 2 : 1;  // "inf"/"nan" spellings: outside the exact range; anything else: not a number
+    if (i < n) {
+        if (p[i] != 'e' && p[i] != 'E') return 1;
+        ++i;
+        bool eneg = false;
+        if (i < n && (p[i] == '+' || p[i] == '-')) { eneg = p[i] == '-'; ++i; }
+        if (i == n) return 1;
+        int e = 0;
+        for (; i < n; ++i) {
+            uint32_t d = (uint32_t)p[i] - '0';
+            if (d > 9u) return 1;
+            if (e < 100000) e = e * 10 + (int)d;
+        }
+        exp10 += eneg ? -e : e;
+    }
+    if (mant == 0) { out = neg ? -0.0 : 0.0; return 0; }
+    while (sig > 15 && mant % 10 == 0) { mant /= 10; ++exp10; --sig; }
+    if (sig > 15 || exp10 < -22 || exp10 > 22) return 2;
+    double v = (double)mant;
+    v = exp10 >= 0 ? v * P10[exp10] : v / P10[-exp10];
+    out = neg ? -v : v;
+    return 0;
+}
+
+__global__ void __launch_bounds__(128) k_flt_parse(const uint8_t* __restrict__ text, uint64_t n, const uint64_t* __restrict__ line_off,
+                                                   uint64_t n_lines, FltRec* __restrict__ recs, uint32_t* flags) {
+    const uint64_t li = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_lines) return;
+    FltRec r;
+    r.key = make_ulonglong2(0ull, 0ull);
+    r.matches = 0; r.ident = 0; r.mapq = 0; r.span = 0;
+    uint64_t a = line_off[li], b = line_off[li + 1] - 1;  // [a,b): the line without its '\n'
+    while (a < b && flt_ws(text[a])) ++a;                 // gaf_filter.rs:23 line.trim()
+    while (b > a && flt_ws(text[b - 1])) --b;
+    // fields 1..16: [fs[k], fe[k])
+    uint64_t fs[16], fe[16];
+    int nf = 0;
+    uint64_t s0 = a;
+    for (uint64_t k = a; k <= b; ++k) {
+        if (k == b || text[k] == '\t') {
+            if (nf < 16) { fs[nf] = s0; fe[nf] = k; }
+            ++nf;
+            s0 = k + 1;
+        }
+    }
+    if (nf >= 16) {
+        int m, q, c4, c3;
+        bool ok = flt_parse_i32(text + fs[9], (uint32_t)(fe[9] - fs[9]), m);
+        uint64_t c = fe[15];
+        while (c > fs[15] && text[c - 1] != ':') --c;  // rsplit(':').next(): text behind the last ':'
+        double id = 0;
+        int fst = ok ? flt_parse_f64(text + c, (uint32_t)(fe[15] - c), id) : 1;
+        if (fst == 2) atomicOr(flags + 2, 1u);
+        ok = ok && fst == 0 && flt_parse_i32(text + fs[11], (uint32_t)(fe[11] - fs[11]), q) &&
+             flt_parse_i32(text + fs[3], (uint32_t)(fe[3] - fs[3]), c4) && flt_parse_i32(text + fs[2], (uint32_t)(fe[2] - fs[2]), c3);
+        if (ok) {
+            IdHasher H;
+            for (uint64_t k = fs[0]; k < fe[0]; ++k) H.byte(text[k]);
+            IdHash h = H.finish();
+            r.key = make_ulonglong2(h.lo, ((uint64_t)h.hi << 32) | 1u);
+            r.matches = m;
+            r.ident = id;
+            r.mapq = q;
+            r.span = c4 - c3;  // i32 wrap-around is a debug-only panic in Rust; release builds wrap
+        }
+    }
+    recs[li] = r;
+}
+
+__device__ __forceinline__ uint64_t flt_slot(ulonglong2* keys, uint64_t mask, uint32_t shift, const ulonglong2& key) {
+    IdHash h;
+    h.lo = key.x;
+    h.hi = (uint32_t)(key.y >> 32);
+    uint64_t i = ds_home(h, shift);
+    for (;;) {
+        ulonglong2 cur = ld128(keys + i);
+        if (cur.x == 0ull && cur.y == 0ull) {
+            cur = atomic_cas128(keys + i, make_ulonglong2(0ull, 0ull), key);
+            if (cur.x == 0ull && cur.y == 0ull) return i;
+        }
+        if (cur.x == key.x && cur.y == key.y) return i;
+        i = (i + 1) & mask;
+    }
+}
+// best (matches, identity) per read id over ALL parsed lines (gaf_filter.rs:65-74)
+__global__ void __launch_bounds__(256) k_flt_best(const FltRec* __restrict__ recs, uint64_t n_lines, ulonglong2* keys, ulonglong2* best,
+                                                  uint64_t mask, uint32_t shift) {
+    const uint64_t li = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_lines) return;
+    const FltRec r = recs[li];
+    if (r.key.x == 0ull && r.key.y == 0ull) return;
+    const uint64_t i = flt_slot(keys, mask, shift, r.key);
+    // slot value {matches + 2^40 (0 = unset), identity bits}
+    const ulonglong2 mine = make_ulonglong2((unsigned long long)(r.matches + (1ll << 40)), (unsigned long long)__double_as_longlong(r.ident));
+    ulonglong2 cur = ld128(best + i);
+    for (;;) {
+        bool better = cur.x == 0ull;
+        if (!better) {
+            const long long cm = (long long)cur.x - (1ll << 40);
+            const double ci = __longlong_as_double((long long)cur.y);
+            better = r.matches > cm || (r.matches == cm && r.ident > ci);
+        }
+        if (!better) break;
+        const ulonglong2 prev = atomic_cas128(best + i, cur, mine);
+        if (prev.x == cur.x && prev.y == cur.y) break;
+        cur = prev;
+    }
+}
+// first qualifying line per id in file order (the reference's choice is a race, gaf_filter.rs:80-93)
+__global__ void __launch_bounds__(256) k_flt_first(const FltRec* __restrict__ recs, uint64_t n_lines, ulonglong2* keys,
+                                                   const ulonglong2* __restrict__ best, unsigned long long* first, uint64_t mask, uint32_t shift,
+                                                   uint8_t* __restrict__ qual) {
+    const uint64_t li = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_lines) return;
+    const FltRec r = recs[li];
+    bool q = false;
+    if (!(r.key.x == 0ull && r.key.y == 0ull) && r.mapq > 20 && r.span > 1000) {
+        const uint64_t i = flt_slot(keys, mask, shift, r.key);
+        const ulonglong2 b = best[i];
+        q = ((long long)b.x - (1ll << 40)) == r.matches && __longlong_as_double((long long)b.y) == r.ident;
+        if (q) atomicMin(first + i, (unsigned long long)li);
+    }
+    qual[li] = q ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) k_flt_select(const FltRec* __restrict__ recs, uint64_t n_lines, ulonglong2* keys,
+                                                    const unsigned long long* __restrict__ first, uint64_t mask, uint32_t shift,
+                                                    const uint8_t* __restrict__ qual, uint32_t* __restrict__ sel) {
+    const uint64_t li = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_lines) return;
+    uint32_t s = 0;
+    if (qual[li]) {
+        const uint64_t i = flt_slot(keys, mask, shift, recs[li].key);
+        s = first[i] == li ? 1u : 0u;
+    }
+    sel[li] = s;
+}
+__global__ void __launch_bounds__(256) k_flt_compact(const uint32_t* __restrict__ sel, const uint64_t* __restrict__ scan,
+                                                     const uint64_t* __restrict__ line_off, uint64_t n_lines, uint64_t* __restrict__ out, uint64_t cap) {
+    const uint64_t li = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_lines || !sel[li]) return;
+    const uint64_t j = scan[li];
+    if (j < cap) out[j] = line_off[li];
+}
+
+// =====================================================================================
 // launchers
 // =====================================================================================
 static inline uint32_t grid_for(uint64_t n, uint32_t per_block, uint32_t cap = 148u * 32u) {
@@ -932,6 +1213,33 @@ void launch_ds_collect_mixed(const ulonglong2* slots, uint64_t cap, unsigned lon
 void launch_ds_apply_mixed(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, cudaStream_t st) {
     if (n == 0) return;
     k_ds_apply_mixed<<<grid_for(n, 256), 256, 0, st>>>(in, n, slots, shift, mask);
+    PTX_LAUNCHED();
+}
+void launch_flt_count_nl(const uint8_t* text, uint64_t n, uint32_t n_micro, uint32_t* cnt, cudaStream_t st) {
+    k_flt_count_nl<<<(n_micro + 7) / 8, 256, 0, st>>>(text, n, n_micro, cnt);
+    PTX_LAUNCHED();
+}
+void launch_flt_line_starts(const uint8_t* text, uint64_t n, uint32_t n_micro, const uint64_t* micro_base, uint64_t* line_off, cudaStream_t st) {
+    k_flt_line_starts<<<(n_micro + 7) / 8, 256, 0, st>>>(text, n, n_micro, micro_base, line_off);
+    PTX_LAUNCHED();
+}
+size_t flt_rec_bytes() { return sizeof(FltRec); }
+void launch_flt_pipeline(const uint8_t* text, uint64_t n, const uint64_t* line_off, uint64_t n_lines, void* recs, ulonglong2* keys,
+                         ulonglong2* best, unsigned long long* first, uint64_t mask, uint32_t shift, uint8_t* qual, uint32_t* sel,
+                         uint32_t* flags, cudaStream_t st) {
+    if (n_lines == 0) return;
+    FltRec* r = reinterpret_cast<FltRec*>(recs);
+    const uint32_t g128 = (uint32_t)((n_lines + 127) / 128), g256 = (uint32_t)((n_lines + 255) / 256);
+    k_flt_parse<<<g128, 128, 0, st>>>(text, n, line_off, n_lines, r, flags);
+    k_flt_best<<<g256, 256, 0, st>>>(r, n_lines, keys, best, mask, shift);
+    k_flt_first<<<g256, 256, 0, st>>>(r, n_lines, keys, best, first, mask, shift, qual);
+    k_flt_select<<<g256, 256, 0, st>>>(r, n_lines, keys, first, mask, shift, qual, sel);
+    for (int i = 0; i < 4; ++i) PTX_LAUNCHED();
+}
+void launch_flt_compact(const uint32_t* sel, const uint64_t* scan, const uint64_t* line_off, uint64_t n_lines, uint64_t* out, uint64_t cap,
+                        cudaStream_t st) {
+    if (n_lines == 0) return;
+    k_flt_compact<<<(uint32_t)((n_lines + 255) / 256), 256, 0, st>>>(sel, scan, line_off, n_lines, out, cap);
     PTX_LAUNCHED();
 }
 void launch_fill_u8(uint8_t* p, uint8_t v, uint64_t n, cudaStream_t st) {

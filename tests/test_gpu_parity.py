@@ -198,3 +198,61 @@ def test_gpu_every_tile_size_gives_the_same_answer(rows, monkeypatch):
     gpu_vs_oracle(ds.ranges(), dataset_graphs(ds), gaf)
     gl = ds.gaf(6, 0, 2000, synth.GafParams(long_reads=True, id_pair_suffix=False))
     gpu_vs_oracle(ds.ranges(), dataset_graphs(ds), gl)
+
+
+def test_gpu_long_read_filter_matches_oracle():
+    """K10 / gaf_filter.rs:44-97: best (matches, identity) per read id, mapq > 20, span > 1000, one line per id."""
+    from common import ocpu
+    api = _api()
+    ds = synth.Dataset(8, [40000, 25000], [4, 2], backbone_mean=400)
+    gl = ds.gaf(6, 0, 4000, synth.GafParams(long_reads=True, id_pair_suffix=False, p_secondary=0.3))
+    ctx = api.PantaxGpu(0)
+    exp = opy.filter_max_alignment(gl)
+    got = api.filter_max_alignment_mt(ctx, gl)
+    assert got == exp and 0 < len(got) < gl.count(b"\n")
+    assert ocpu.filter_gaf(gl) == exp
+    # no trailing newline, and the filtered file is a fixed point
+    assert ctx.filter_gaf(gl[:-1]) == exp
+    again = b"\n".join(exp) + b"\n"
+    assert ctx.filter_gaf(again) == exp
+
+
+def test_gpu_long_read_filter_handcrafted_edges():
+    api = _api()
+
+    def line(rid, qs, qe, matches, mapq, ident, extra=b""):
+        f = [rid, b"20000", qs, qe, b"+", b">1>2", b"30000", b"5", b"9000", matches, b"9000", mapq, b"NM:i:3", b"AS:f:1", b"dv:f:0.01",
+             b"id:f:" + ident]
+        return b"\t".join(f) + extra
+    lines = [
+        line(b"a", b"0", b"5000", b"4000", b"60", b"0.99"),          # a: best by matches is the next line
+        line(b"a", b"0", b"5000", b"4500", b"60", b"0.90"),
+        line(b"b", b"0", b"5000", b"4000", b"60", b"0.95"),          # b: tie on matches -> higher identity wins
+        line(b"b", b"0", b"5000", b"4000", b"60", b"9.6e-1"),
+        line(b"c", b"0", b"5000", b"4000", b"20", b"0.99"),          # c: best line fails mapq > 20 -> nothing for c
+        line(b"c", b"0", b"5000", b"3000", b"60", b"0.99"),
+        line(b"d", b"0", b"1000", b"900", b"60", b"0.99"),           # d: span 1000 is not > 1000
+        line(b"e", b"0", b"5000", b"4000", b"60", b"0.99"),          # e: two identical best lines -> first in file order
+        line(b"e", b"10", b"5010", b"4000", b"60", b"0.990"),
+        line(b"f", b"0", b"5000", b"40x0", b"60", b"0.99"),          # f: unparsable matches -> line ignored entirely
+        line(b"f", b"0", b"5000", b"10", b"60", b"0.5"),
+        b"  " + line(b"g", b"0", b"5000", b"4000", b"60", b"1") + b"  ",   # trim(): leading/trailing blanks
+        line(b"h", b"0", b"5000", b"4000", b"60", b"0.99", b"\textra:Z:tag:with:colons"),  # > 16 columns: still column 16
+        b"short\tline",
+        b"",
+        line(b"i", b"-5", b"+5000", b"4000", b"+60", b"+.75"),       # signs; ".75"
+        line(b"j", b"0", b"5000", b"4000", b"60", b"abc"),           # identity not a number -> ignored
+    ]
+    data = b"\n".join(lines) + b"\n"
+    exp = opy.filter_max_alignment(data)
+    ctx = api.PantaxGpu(0)
+    got = ctx.filter_gaf(data)
+    assert got == exp
+    ids = [l.strip().split(b"\t")[0] for l in got]
+    assert ids == [b"a", b"b", b"e", b"f", b"g", b"h", b"i"]
+    assert got[1].endswith(b"9.6e-1") and got[2].split(b"\t")[2] == b"0"
+    # an identity that cannot be represented exactly is refused, not guessed
+    bad = line(b"k", b"0", b"5000", b"4000", b"60", b"0.12345678901234567890")
+    with pytest.raises(api.PantaxGpuError) as e:
+        ctx.filter_gaf(bad + b"\n")
+    assert e.value.name == "PTX_E_UNSUPPORTED"
