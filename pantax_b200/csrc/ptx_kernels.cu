@@ -1005,7 +1005,13 @@ __device__ int flt_parse_f64(const uint8_t* p, uint32_t n, double& out) {
             break;
         }
     }
-    if (nd == 0) return (n - i >= 3) ? 2 : 1;  // "inf"/"nan" spellings: outside the exact range; anything else: not a number
+    if (nd == 0) {  // Rust also accepts inf / infinity / nan (any case): representable, but outside this exact path
+        const uint32_t rem = n - i;
+        auto lc = [&](uint32_t k) { return (uint8_t)(p[i + k] | 0x20); };
+        if (!dot && rem == 3 && ((lc(0) == 'i' && lc(1) == 'n' && lc(2) == 'f') || (lc(0) == 'n' && lc(1) == 'a' && lc(2) == 'n'))) return 2;
+        if (!dot && rem == 8 && lc(0) == 'i' && lc(1) == 'n' && lc(2) == 'f' && lc(3) == 'i' && lc(4) == 'n' && lc(5) == 'i' && lc(6) == 't' && lc(7) == 'y') return 2;
+        return 1;
+    }
     if (i < n) {
         if (p[i] != 'e' && p[i] != 'E') return 1;
         ++i;
