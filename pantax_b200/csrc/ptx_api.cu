@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -132,6 +133,20 @@ struct ptx_ctx {
 };
 
 namespace {
+
+struct Trace {  // PTX_TRACE=1: wall time of the finalize phases (synchronising; debugging aid only)
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t;
+    explicit Trace(cudaStream_t s) : on(getenv("PTX_TRACE") != nullptr), st(s) { if (on) { cudaStreamSynchronize(st); t = std::chrono::steady_clock::now(); } }
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ptx trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
 
 int fail(ptx_ctx* c, int code, const char* fmt, ...) {
     if (c) {
@@ -424,7 +439,9 @@ int exchange_id_groups(ptx_ctx* ctx) {
     unsigned long long* d_allmix = scratch_take<unsigned long long>(ctx, P);
     const size_t head = ctx->scratch_off;
     CU(cudaMemsetAsync(d_cnt, 0, ((size_t)P * 2 + 2) * sizeof(unsigned long long), st));
+    Trace tr(st);
     launch_ds_owner_count(ctx->d_ds, ctx->ds_cap, (uint32_t)P, d_cnt, st);
+    tr.mark("xchg owner_count");
     if ((rc = nccl_check(ctx, g_nccl.AllGather(d_cnt, d_all, P, ncclUint64, ctx->comm, st), "ncclAllGather(id counts)"))) return rc;
     std::vector<unsigned long long> all((size_t)P * P), cursor(P), roff(P);
     CU(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -444,8 +461,11 @@ int exchange_id_groups(ptx_ctx* ctx) {
     ulonglong2* own = scratch_take<ulonglong2>(ctx, ocap);
     unsigned long long* d_cursor = d_cnt + P;
     CU(cudaMemcpyAsync(d_cursor, cursor.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    tr.mark("xchg counts allgather+sync");
     launch_ds_owner_scatter(ctx->d_ds, ctx->ds_cap, (uint32_t)P, d_cursor, sendbuf, st);
+    tr.mark("xchg owner_scatter");
     CU(cudaMemsetAsync(own, 0, ocap * sizeof(ulonglong2), st));
+    tr.mark("xchg memset own");
     g_nccl.GroupStart();
     for (int r = 0; r < P; ++r) {
         if (r == ctx->rank) continue;
@@ -457,8 +477,10 @@ int exchange_id_groups(ptx_ctx* ctx) {
     if (send_cnt[ctx->rank])
         CU(cudaMemcpyAsync(recvbuf + roff[ctx->rank], sendbuf + cursor[ctx->rank], send_cnt[ctx->rank] * sizeof(ulonglong2),
                            cudaMemcpyDeviceToDevice, st));
+    tr.mark("xchg send/recv");
     // owner-side merge
     launch_ds_merge_insert(recvbuf, n_recv, own, 64 - log2_ceil(ocap), ocap - 1, ctx->d_flags, st);
+    tr.mark("xchg merge_insert");
     // mixed ids -> everyone
     unsigned long long* d_nmix = d_cnt + 2 * P;
     launch_ds_collect_mixed(own, ocap, d_nmix, nullptr, 0, st);
@@ -466,6 +488,7 @@ int exchange_id_groups(ptx_ctx* ctx) {
     std::vector<unsigned long long> nmix(P);
     CU(cudaMemcpyAsync(nmix.data(), d_allmix, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    tr.mark("xchg collect mixed");
     unsigned long long mx = 0;
     for (auto v : nmix) mx = std::max(mx, v);
     if (mx > 0) {
@@ -867,6 +890,7 @@ int ptx_finalize(ptx_ctx* ctx) {
     GraphDev& g = ctx->g;
     const int S = (int)ctx->sp.size();
     ev_begin(ctx, ctx->ev_final);
+    Trace tr(ctx->st);
     if (ctx->comm) {  // id groups may span ranks; a mixed id group / error seen on any rank is seen by all
         int rc = exchange_id_groups(ctx);
         if (rc) return rc;
@@ -876,6 +900,7 @@ int ptx_finalize(ptx_ctx* ctx) {
     CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     const bool mixed = ctx->h_flags[1] != 0;
+    tr.mark("final id groups + flags");
     if (ctx->graphs_committed && g.N > 0) {
         if (mixed) {
             // profile.rs:406-437: some id group spans species -> its reads must not contribute.  The optimistic
@@ -894,6 +919,7 @@ int ptx_finalize(ptx_ctx* ctx) {
             launch_ingest(a, MODE_COVER | (mixed ? MODE_KEEPMASK : 0), ctx->st);
             ch.covered = true;
         }
+        tr.mark("final replay/cover");
         if (ctx->comm) {
             // int64 sums and flag maxima are order-free: bit-exact for any shard count
             if (ctx->cov_reduced) return fail(ctx, PTX_E_STATE, "multi-GPU: coverage already reduced");
@@ -911,6 +937,7 @@ int ptx_finalize(ptx_ctx* ctx) {
             for (int r = 0; r < ctx->n_ranks; ++r)
                 if (r != ctx->rank) launch_or_words(g.bits, all + (size_t)r * g.n_bit_words, g.n_bit_words, ctx->st);
         }
+        tr.mark("final reductions");
         CU(cudaMemsetAsync(g.path_cov_sum, 0, std::max<int64_t>(g.Htot, 1) * sizeof(unsigned long long), ctx->st));
         CU(cudaMemsetAsync(g.hap_nz, 0, std::max<int64_t>(g.Htot, 1) * sizeof(unsigned long long), ctx->st));
         launch_cov(g, ctx->st);
@@ -922,6 +949,7 @@ int ptx_finalize(ptx_ctx* ctx) {
         int rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_hist, ctx->d_hist_g, (size_t)S * 4, ncclUint64, ncclSum, ctx->comm, ctx->st), "ncclAllReduce(hist)");
         if (rc) return rc;
     }
+    tr.mark("final cov/path/hap stats");
     ctx->h_err.assign(S, 0);
     CU(cudaMemcpyAsync(ctx->h_err.data(), ctx->d_err, S * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st));
     ev_end(ctx, ctx->ev_final);
