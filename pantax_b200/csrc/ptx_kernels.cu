@@ -231,20 +231,42 @@ __global__ void __launch_bounds__(256) k_ds_rehash(const ulonglong2* __restrict_
 __device__ __forceinline__ uint32_t ds_owner(const ulonglong2& e, uint32_t P) {
     return ((uint32_t)(e.y >> 32) ^ (uint32_t)(e.x >> 40)) % P;
 }
+// Both kernels aggregate per warp (one atomic per distinct owner per warp): 10 M same-address atomics took
+// 4 ms each in the first version (profiles/r1_multigpu_trace.md).
 __global__ void __launch_bounds__(256) k_ds_owner_count(const ulonglong2* __restrict__ slots, uint64_t cap, uint32_t P,
                                                         unsigned long long* cnt) {
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cap; k += (uint64_t)gridDim.x * blockDim.x) {
-        ulonglong2 e = slots[k];
-        if (e.x == 0ull && e.y == 0ull) continue;
-        atomicAdd(cnt + ds_owner(e, P), 1ull);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (cap + stride - 1) / stride;
+    for (uint64_t it = 0; it < rounds; ++it) {
+        const uint64_t k = it * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        uint32_t owner = 0xFFFFFFFFu;
+        if (k < cap) {
+            ulonglong2 e = slots[k];
+            if (!(e.x == 0ull && e.y == 0ull)) owner = ds_owner(e, P);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, owner);
+        if (owner != 0xFFFFFFFFu && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(cnt + owner, (unsigned long long)__popc(peers));
     }
 }
 __global__ void __launch_bounds__(256) k_ds_owner_scatter(const ulonglong2* __restrict__ slots, uint64_t cap, uint32_t P,
                                                           unsigned long long* cursor, ulonglong2* __restrict__ out) {
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cap; k += (uint64_t)gridDim.x * blockDim.x) {
-        ulonglong2 e = slots[k];
-        if (e.x == 0ull && e.y == 0ull) continue;
-        out[atomicAdd(cursor + ds_owner(e, P), 1ull)] = e;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (cap + stride - 1) / stride;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint64_t it = 0; it < rounds; ++it) {
+        const uint64_t k = it * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        uint32_t owner = 0xFFFFFFFFu;
+        ulonglong2 e = make_ulonglong2(0ull, 0ull);
+        if (k < cap) {
+            e = slots[k];
+            if (!(e.x == 0ull && e.y == 0ull)) owner = ds_owner(e, P);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, owner);
+        const int leader = __ffs(peers) - 1;
+        unsigned long long base = 0;
+        if (owner != 0xFFFFFFFFu && (int)lane == leader) base = atomicAdd(cursor + owner, (unsigned long long)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (owner != 0xFFFFFFFFu) out[base + __popc(peers & ((1u << lane) - 1u))] = e;
     }
 }
 __device__ __forceinline__ uint32_t ds_merge_state(uint32_t l, uint32_t f) {
