@@ -125,6 +125,9 @@ struct ptx_ctx {
     std::vector<Chunk> pool;
     uint8_t* scratch = nullptr;
     size_t scratch_cap = 0, scratch_off = 0;
+    uint8_t* scratch2 = nullptr;
+    size_t scratch2_cap = 0;
+    uint64_t xchg_box_cap = 0;  // per-owner outbox capacity of the id-group exchange (sticky)
     // timing
     std::vector<EvPair> ev_count, ev_ingest, ev_final;
     // multi-GPU
@@ -431,41 +434,55 @@ int exchange_id_groups(ptx_ctx* ctx) {
     if (P <= 1 || !ctx->d_ds) return PTX_OK;
     cudaStream_t st = ctx->st;
     int rc;
-    // small counters live at the head of the arena; the big buffers are carved once their sizes are known
-    if ((rc = scratch_reserve(ctx, (size_t)64 << 20))) return rc;
-    ctx->scratch_off = 0;
-    unsigned long long* d_cnt = scratch_take<unsigned long long>(ctx, (size_t)P * 2 + 2);
-    unsigned long long* d_all = scratch_take<unsigned long long>(ctx, (size_t)P * P);
-    unsigned long long* d_allmix = scratch_take<unsigned long long>(ctx, P);
-    const size_t head = ctx->scratch_off;
-    CU(cudaMemsetAsync(d_cnt, 0, ((size_t)P * 2 + 2) * sizeof(unsigned long long), st));
     Trace tr(st);
-    launch_ds_owner_count(ctx->d_ds, ctx->ds_cap, (uint32_t)P, d_cnt, st);
-    tr.mark("xchg owner_count");
-    if ((rc = nccl_check(ctx, g_nccl.AllGather(d_cnt, d_all, P, ncclUint64, ctx->comm, st), "ncclAllGather(id counts)"))) return rc;
+    // Outboxes of fixed capacity per owner (the hash spreads ids uniformly), so one pass over the id set both
+    // counts and scatters; if an outbox would overflow, the capacities are raised and the pass repeated.
+    const uint64_t n_mine = (uint64_t)std::max<int64_t>(ctx->ds_records, 1);
+    uint64_t box_cap = ctx->xchg_box_cap ? ctx->xchg_box_cap : (n_mine / P + n_mine / (4 * P) + 4096);
     std::vector<unsigned long long> all((size_t)P * P), cursor(P), roff(P);
-    CU(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    const unsigned long long* send_cnt = &all[(size_t)ctx->rank * P];  // all[r][q] = entries rank r sends to rank q
-    unsigned long long n_send = 0, n_recv = 0;
-    for (int r = 0; r < P; ++r) { cursor[r] = n_send; n_send += send_cnt[r]; }
-    for (int r = 0; r < P; ++r) { roff[r] = n_recv; n_recv += all[(size_t)r * P + ctx->rank]; }
-    const uint64_t ocap = 1ull << std::max<uint32_t>(10, log2_ceil(n_recv * 2 + 1));
-    const size_t need = head + ((size_t)n_send + n_recv + ocap + 64) * sizeof(ulonglong2) + 4096;
-    if (need > ctx->scratch_cap) {  // grow once; the counters are recomputed cheaply
-        if ((rc = scratch_reserve(ctx, need + need / 4))) return rc;
-        return exchange_id_groups(ctx);
+    unsigned long long *d_cnt = nullptr, *d_all = nullptr;
+    ulonglong2* sendbuf = nullptr;
+    for (;;) {
+        const size_t need = ((size_t)3 * P + (size_t)P * P + 64) * sizeof(unsigned long long) + ((size_t)box_cap * P + 64) * sizeof(ulonglong2) + 8192;
+        if ((rc = scratch_reserve(ctx, need))) return rc;
+        ctx->scratch_off = 0;
+        d_cnt = scratch_take<unsigned long long>(ctx, (size_t)P * 3 + 2);  // [0,P) cursors, [P,2P) counts, [2P] mixed count
+        d_all = scratch_take<unsigned long long>(ctx, (size_t)P * P);
+        sendbuf = scratch_take<ulonglong2>(ctx, (size_t)box_cap * P + 1);
+        for (int r = 0; r < P; ++r) cursor[r] = (unsigned long long)r * box_cap;
+        CU(cudaMemcpyAsync(d_cnt, cursor.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+        launch_ds_owner_scatter(ctx->d_ds, ctx->ds_cap, (uint32_t)P, d_cnt, sendbuf, box_cap, st);
+        launch_sub_u64(d_cnt + P, d_cnt, box_cap, P, st);  // counts[r] = cursor[r] - r*box_cap
+        if ((rc = nccl_check(ctx, g_nccl.AllGather(d_cnt + P, d_all, P, ncclUint64, ctx->comm, st), "ncclAllGather(id counts)"))) return rc;
+        CU(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        unsigned long long worst = 0;
+        for (auto v : all) worst = std::max(worst, v);  // every rank sees every count: all ranks retry together
+        if (worst <= box_cap) break;
+        box_cap = worst + worst / 8 + 4096;
     }
-    ulonglong2* sendbuf = scratch_take<ulonglong2>(ctx, (size_t)n_send + 1);
-    ulonglong2* recvbuf = scratch_take<ulonglong2>(ctx, (size_t)n_recv + 1);
-    ulonglong2* own = scratch_take<ulonglong2>(ctx, ocap);
-    unsigned long long* d_cursor = d_cnt + P;
-    CU(cudaMemcpyAsync(d_cursor, cursor.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-    tr.mark("xchg counts allgather+sync");
-    launch_ds_owner_scatter(ctx->d_ds, ctx->ds_cap, (uint32_t)P, d_cursor, sendbuf, st);
-    tr.mark("xchg owner_scatter");
+    ctx->xchg_box_cap = box_cap;
+    tr.mark("xchg scatter + counts");
+    const unsigned long long* send_cnt = &all[(size_t)ctx->rank * P];  // all[r][q] = entries rank r sends to rank q
+    unsigned long long n_recv = 0;
+    for (int r = 0; r < P; ++r) { roff[r] = n_recv; n_recv += all[(size_t)r * P + ctx->rank]; }
+    const uint64_t ocap = 1ull << std::max<uint32_t>(10, log2_ceil(n_recv + n_recv / 2 + 1));
+    // receive buffer + owner table: a second grow-only arena (growing it must not move the outboxes, and no
+    // rank may repeat a collective the others do not)
+    {
+        const size_t need = ((size_t)n_recv + ocap + 64) * sizeof(ulonglong2) + 8192;
+        if (need > ctx->scratch2_cap) {
+            CU(cudaStreamSynchronize(st));
+            if (ctx->scratch2) cudaFree(ctx->scratch2);
+            ctx->scratch2 = nullptr;
+            ctx->scratch2_cap = 0;
+            CU(cudaMalloc((void**)&ctx->scratch2, need + need / 8));
+            ctx->scratch2_cap = need + need / 8;
+        }
+    }
+    ulonglong2* recvbuf = reinterpret_cast<ulonglong2*>(ctx->scratch2);
+    ulonglong2* own = recvbuf + (((size_t)n_recv + 16) & ~(size_t)15);
     CU(cudaMemsetAsync(own, 0, ocap * sizeof(ulonglong2), st));
-    tr.mark("xchg memset own");
     g_nccl.GroupStart();
     for (int r = 0; r < P; ++r) {
         if (r == ctx->rank) continue;
@@ -480,15 +497,22 @@ int exchange_id_groups(ptx_ctx* ctx) {
     tr.mark("xchg send/recv");
     // owner-side merge
     launch_ds_merge_insert(recvbuf, n_recv, own, 64 - log2_ceil(ocap), ocap - 1, ctx->d_flags, st);
-    tr.mark("xchg merge_insert");
+    // a mixed group needs a repeated id: if no rank saw one, nothing has to be sent back
+    if ((rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 2, ncclUint32, ncclMax, ctx->comm, st), "ncclAllReduce(flags)"))) return rc;
+    uint32_t fl[2] = {0, 0};
+    CU(cudaMemcpyAsync(fl, ctx->d_flags, sizeof fl, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    tr.mark("xchg merge_insert + flags");
+    if (fl[1] == 0) return PTX_OK;
     // mixed ids -> everyone
     unsigned long long* d_nmix = d_cnt + 2 * P;
+    unsigned long long* d_allmix = d_all;  // reuse: P entries
+    CU(cudaMemsetAsync(d_nmix, 0, sizeof(unsigned long long), st));
     launch_ds_collect_mixed(own, ocap, d_nmix, nullptr, 0, st);
     if ((rc = nccl_check(ctx, g_nccl.AllGather(d_nmix, d_allmix, 1, ncclUint64, ctx->comm, st), "ncclAllGather(mixed counts)"))) return rc;
     std::vector<unsigned long long> nmix(P);
     CU(cudaMemcpyAsync(nmix.data(), d_allmix, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    tr.mark("xchg collect mixed");
     unsigned long long mx = 0;
     for (auto v : nmix) mx = std::max(mx, v);
     if (mx > 0) {
@@ -504,6 +528,7 @@ int exchange_id_groups(ptx_ctx* ctx) {
         cudaFree(mine);
         cudaFree(everyone);
     }
+    tr.mark("xchg mixed ids back");
     return PTX_OK;
 }
 
@@ -546,6 +571,7 @@ void ptx_destroy(ptx_ctx* ctx) {
     for (auto& ch : ctx->chunks) chunk_free(ch);
     for (auto& ch : ctx->pool) chunk_free(ch);
     dfree(ctx->scratch);
+    dfree(ctx->scratch2);
     free_graph(ctx);
     dfree(ctx->d_rstart); dfree(ctx->d_rend); dfree(ctx->d_node_base); dfree(ctx->d_order);
     dfree(ctx->d_hist); dfree(ctx->d_hist_g); dfree(ctx->d_flags); dfree(ctx->d_err); dfree(ctx->d_ds); dfree(ctx->d_total);
@@ -892,9 +918,7 @@ int ptx_finalize(ptx_ctx* ctx) {
     ev_begin(ctx, ctx->ev_final);
     Trace tr(ctx->st);
     if (ctx->comm) {  // id groups may span ranks; a mixed id group / error seen on any rank is seen by all
-        int rc = exchange_id_groups(ctx);
-        if (rc) return rc;
-        rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 2, ncclUint32, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(flags)");
+        int rc = exchange_id_groups(ctx);  // also max-reduces the flags
         if (rc) return rc;
     }
     CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));

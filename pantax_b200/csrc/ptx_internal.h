@@ -94,7 +94,9 @@ void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2*
 void launch_fill_u8(uint8_t* p, uint8_t v, uint64_t n, cudaStream_t st);
 // cross-rank id groups (multi-GPU finalize)
 void launch_ds_owner_count(const ulonglong2* slots, uint64_t cap, uint32_t P, unsigned long long* cnt, cudaStream_t st);
-void launch_ds_owner_scatter(const ulonglong2* slots, uint64_t cap, uint32_t P, unsigned long long* cursor, ulonglong2* out, cudaStream_t st);
+void launch_ds_owner_scatter(const ulonglong2* slots, uint64_t cap, uint32_t P, unsigned long long* cursor, ulonglong2* out, uint64_t box_cap,
+                             cudaStream_t st);
+void launch_sub_u64(unsigned long long* out, const unsigned long long* in, unsigned long long step, int n, cudaStream_t st);
 void launch_ds_merge_insert(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags, cudaStream_t st);
 void launch_ds_collect_mixed(const ulonglong2* slots, uint64_t cap, unsigned long long* cursor, ulonglong2* out, uint64_t out_cap, cudaStream_t st);
 void launch_ds_apply_mixed(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, cudaStream_t st);

@@ -248,8 +248,14 @@ __global__ void __launch_bounds__(256) k_ds_owner_count(const ulonglong2* __rest
         if (owner != 0xFFFFFFFFu && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(cnt + owner, (unsigned long long)__popc(peers));
     }
 }
+__global__ void __launch_bounds__(64) k_sub_u64(unsigned long long* out, const unsigned long long* in, unsigned long long step, int n) {
+    const int i = threadIdx.x;
+    if (i < n) out[i] = in[i] - (unsigned long long)i * step;
+}
+// out = P outboxes of box_cap entries; cursor[r] starts at r*box_cap.  Entries beyond an outbox's end are
+// counted but not written (the host then enlarges the outboxes and repeats the pass).
 __global__ void __launch_bounds__(256) k_ds_owner_scatter(const ulonglong2* __restrict__ slots, uint64_t cap, uint32_t P,
-                                                          unsigned long long* cursor, ulonglong2* __restrict__ out) {
+                                                          unsigned long long* cursor, ulonglong2* __restrict__ out, uint64_t box_cap) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t rounds = (cap + stride - 1) / stride;
     const uint32_t lane = threadIdx.x & 31u;
@@ -266,7 +272,10 @@ __global__ void __launch_bounds__(256) k_ds_owner_scatter(const ulonglong2* __re
         unsigned long long base = 0;
         if (owner != 0xFFFFFFFFu && (int)lane == leader) base = atomicAdd(cursor + owner, (unsigned long long)__popc(peers));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (owner != 0xFFFFFFFFu) out[base + __popc(peers & ((1u << lane) - 1u))] = e;
+        if (owner != 0xFFFFFFFFu) {
+            const unsigned long long pos = base + __popc(peers & ((1u << lane) - 1u));
+            if (pos < (unsigned long long)(owner + 1) * box_cap) out[pos] = e;
+        }
     }
 }
 __device__ __forceinline__ uint32_t ds_merge_state(uint32_t l, uint32_t f) {
@@ -1225,8 +1234,13 @@ void launch_ds_owner_count(const ulonglong2* slots, uint64_t cap, uint32_t P, un
     k_ds_owner_count<<<grid_for(cap, 256), 256, 0, st>>>(slots, cap, P, cnt);
     PTX_LAUNCHED();
 }
-void launch_ds_owner_scatter(const ulonglong2* slots, uint64_t cap, uint32_t P, unsigned long long* cursor, ulonglong2* out, cudaStream_t st) {
-    k_ds_owner_scatter<<<grid_for(cap, 256), 256, 0, st>>>(slots, cap, P, cursor, out);
+void launch_ds_owner_scatter(const ulonglong2* slots, uint64_t cap, uint32_t P, unsigned long long* cursor, ulonglong2* out, uint64_t box_cap,
+                             cudaStream_t st) {
+    k_ds_owner_scatter<<<grid_for(cap, 256), 256, 0, st>>>(slots, cap, P, cursor, out, box_cap);
+    PTX_LAUNCHED();
+}
+void launch_sub_u64(unsigned long long* out, const unsigned long long* in, unsigned long long step, int n, cudaStream_t st) {
+    k_sub_u64<<<1, 64, 0, st>>>(out, in, step, n);
     PTX_LAUNCHED();
 }
 void launch_ds_merge_insert(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags, cudaStream_t st) {
