@@ -361,7 +361,9 @@ struct WalkIter {
 //   void set_bits(uint32_t g, int64_t lo, int64_t hi, uint32_t ln);   0 <= lo < hi <= ln
 //   void trio(uint32_t a, uint32_t b, uint32_t c, int64_t s);         global node indices, read order
 //   void error_start_gt_len(uint32_t label);
-// `mask`: lanes of the warp that call this together (lock-step over the node index).
+// `mask`: lanes of the warp that call this together.  The walk is processed in three phases so that the lanes
+// execute the same code at the same time: the first node of every read, then the middle nodes in lock-step,
+// then the last node of every read (walk order is preserved, which the non-stashed re-parse needs).
 template <class Sink>
 PTX_HD void cover_record(const uint8_t* b, const RecParse& r, uint32_t label, int64_t range_start, int64_t node_base,
                          Sink& sink, uint32_t mask, const uint32_t* stash, uint32_t stash_stride) {
@@ -369,73 +371,89 @@ PTX_HD void cover_record(const uint8_t* b, const RecParse& r, uint32_t label, in
     int64_t target = pe - ps;  // :800
     WalkIter it{b, r.path_pos, r.path_end};
     const bool stashed = r.stashed;
-    uint32_t W = r.W;               // W == 0: profile.rs:794 (nothing to do, but stay in lock-step)
-    const bool single = (W == 1);   // :811
-    int64_t seen = 0;
-    uint32_t ga = 0, gb = 0;
-    int64_t rla = 0, rlb = 0;
-    const uint32_t Wmax = PTX_WARP_MAX_U32(mask, W);
-    for (uint32_t i = 0; i < Wmax; ++i) {
-        if (i < W) {
+    const uint32_t W = r.W;  // W == 0: profile.rs:794
+    // rl of node i as the trio loop sees it (:897-900): what its FIRST occurrence in this read added
+    auto first_occurrence = [&](uint32_t i, int64_t m, int64_t ln, int64_t aln, int64_t& rl) -> bool {
+        rl = aln;
+        if (r.monotone) return true;  // strictly monotone ids cannot repeat
+        WalkIter jt{b, r.path_pos, r.path_end};
+        for (uint32_t j = 0; j < i; ++j) {
+            int64_t mj;
+            if (stashed) mj = (int64_t)stash[j * stash_stride];
+            else jt.next(mj);
+            if (mj == m) {
+                rl = (j == 0) ? (ln - ps) : ln;  // :880
+                return false;
+            }
+        }
+        return true;
+    };
+    // ---- first node
+    bool ok = W >= 1;
+    uint32_t gb = 0, ga = 0;
+    int64_t rlb = 0, rla = 0, seen = 0;
+    if (ok) {
+        int64_t m;
+        if (stashed) m = (int64_t)stash[0];
+        else it.next(m);
+        const uint32_t g = (uint32_t)(node_base + (m - range_start));
+        const int64_t ln = (int64_t)sink.len(g);
+        if (W == 1) {  // :811
+            if (target >= 0) {              // :821-827 (target < 0: the read is skipped)
+                sink.add_bases(g, target);  // :829
+                if (ps >= 0 && ps < pe && pe <= ln) sink.set_bits(g, ps, pe, (uint32_t)ln);  // :832-835
+            }
+        } else if (ps > ln) {  // :854 (a panic in the reference): flag the species, drop the read
+            sink.error_start_gt_len(label);
+            ok = false;
+        } else {
+            const int64_t aln = ln - ps;                                    // :856
+            if (ps >= 0 && ln > ps) sink.set_bits(g, ps, ln, (uint32_t)ln);  // negative start wraps `as usize` -> empty
+            seen = aln;
+            sink.add_bases(g, aln);  // :881 (position 0 is always a first occurrence)
+            gb = g;
+            rlb = aln;
+        }
+    }
+    PTX_RECONVERGE(mask);
+    // ---- middle nodes 1 .. W-2: fully covered (:861)
+    const uint32_t nmid = (ok && W >= 3) ? W - 2 : 0;
+    const uint32_t nmax = PTX_WARP_MAX_U32(mask, nmid);
+    for (uint32_t j = 0; j < nmax; ++j) {
+        if (j < nmid) {
+            const uint32_t i = j + 1;
             int64_t m;
             if (stashed) m = (int64_t)stash[i * stash_stride];
             else it.next(m);
             const uint32_t g = (uint32_t)(node_base + (m - range_start));
             const int64_t ln = (int64_t)sink.len(g);
-            if (single) {
-                if (target >= 0) {              // :821-827 (target < 0: the read is skipped)
-                    sink.add_bases(g, target);  // :829
-                    if (ps >= 0 && ps < pe && pe <= ln) sink.set_bits(g, ps, pe, (uint32_t)ln);  // :832-835
-                }
-            } else {
-                int64_t aln, lo, hi;
-                bool ok = true;
-                if (i == 0) {
-                    if (ps > ln) {  // :854 (a panic in the reference): flag the species, drop the read
-                        sink.error_start_gt_len(label);
-                        ok = false;
-                        W = 0;
-                    }
-                    aln = ln - ps;
-                    lo = ps;
-                    hi = ln;  // min(ps + aln, ln) == ln
-                } else if (i == W - 1) {
-                    if (target < seen) target = seen;  // :858
-                    aln = target - seen;
-                    lo = 0;
-                    hi = aln < ln ? aln : ln;  // :871
-                } else {
-                    aln = ln;  // :861
-                    lo = 0;
-                    hi = ln;
-                }
-                if (ok) {
-                    if (lo >= 0 && hi > lo) sink.set_bits(g, lo, hi, (uint32_t)ln);  // negative start wraps `as usize` -> empty
-                    seen += aln;                                                      // :878
-                    bool first = true;
-                    int64_t rl = aln;
-                    if (!r.monotone) {  // exact first-occurrence test (:879) against earlier walk positions
-                        WalkIter jt{b, r.path_pos, r.path_end};
-                        for (uint32_t j = 0; j < i; ++j) {
-                            int64_t mj;
-                            if (stashed) mj = (int64_t)stash[j * stash_stride];
-                            else jt.next(mj);
-                            if (mj == m) {
-                                first = false;
-                                rl = (j == 0) ? (ln - ps) : ln;  // what the first occurrence added (:880)
-                                break;
-                            }
-                        }
-                    }
-                    if (first) sink.add_bases(g, aln);                  // :881
-                    if (i >= 2) sink.trio(ga, gb, g, rla + rlb + rl);   // :890-906
-                    ga = gb; rla = rlb;
-                    gb = g;  rlb = rl;
-                }
-            }
+            sink.set_bits(g, 0, ln, (uint32_t)ln);
+            seen += ln;  // :878
+            int64_t rl;
+            if (first_occurrence(i, m, ln, ln, rl)) sink.add_bases(g, ln);  // :879-882
+            if (i >= 2) sink.trio(ga, gb, g, rla + rlb + rl);               // :890-906
+            ga = gb; rla = rlb;
+            gb = g;  rlb = rl;
         }
         PTX_RECONVERGE(mask);
     }
+    // ---- last node
+    if (ok && W >= 2) {
+        const uint32_t i = W - 1;
+        int64_t m;
+        if (stashed) m = (int64_t)stash[i * stash_stride];
+        else it.next(m);
+        const uint32_t g = (uint32_t)(node_base + (m - range_start));
+        const int64_t ln = (int64_t)sink.len(g);
+        if (target < seen) target = seen;  // :858
+        const int64_t aln = target - seen;
+        const int64_t hi = aln < ln ? aln : ln;  // :871
+        if (hi > 0) sink.set_bits(g, 0, hi, (uint32_t)ln);
+        int64_t rl;
+        if (first_occurrence(i, m, ln, aln, rl)) sink.add_bases(g, aln);
+        if (W >= 3) sink.trio(ga, gb, g, rla + rlb + rl);
+    }
+    PTX_RECONVERGE(mask);
 }
 
 }  // namespace ptx

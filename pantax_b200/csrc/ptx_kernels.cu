@@ -409,16 +409,19 @@ __device__ __noinline__ void parse_record_global(const uint8_t* b, uint32_t p, u
 template <int MODE>
 __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* stage = smem;  // tile_bytes + OVER, then 16 sentinel '\n' (the column scanners stop at a newline)
-    uint32_t* stash = reinterpret_cast<uint32_t*>(smem + MAX_TILE + OVER + 16);  // [STASH_CAP][INGEST_THREADS]
-    uint16_t* rec_start = reinterpret_cast<uint16_t*>(stash + STASH_CAP * INGEST_THREADS);  // [REC_CAP]
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t warp_tot[INGEST_THREADS / 32];
-
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t rows = a.rows_per_warp;             // 1..8 rows of 512 B per warp
     const uint32_t tile_bytes = rows * (INGEST_THREADS / 32u) * 512u;  // multiple of 4096
     const uint32_t stage_bytes = tile_bytes + OVER;
+    uint8_t* stage = smem;  // tile_bytes + OVER, then 16 sentinel '\n' (the column scanners stop at a newline)
+    uint32_t* stash = reinterpret_cast<uint32_t*>(smem + stage_bytes + 16);                  // [STASH_CAP][INGEST_THREADS]
+    uint16_t* rec_start = reinterpret_cast<uint16_t*>(stash + STASH_CAP * INGEST_THREADS);  // [REC_CAP] record starts
+    uint16_t* rec_tmp = rec_start + REC_CAP;                                                 // [REC_CAP] (bin, rank in bin)
+    uint16_t* order = rec_tmp + REC_CAP;                                                     // [REC_CAP] records by line length
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t warp_tot[INGEST_THREADS / 32];
+    __shared__ uint32_t bin_cnt[64];
+
     const uint64_t t0 = (uint64_t)blockIdx.x * tile_bytes;
     const uint8_t* gtile = a.text + t0;
 
@@ -523,10 +526,40 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
         __syncthreads();
         const uint32_t n_round = min(REC_CAP, n_rec - round);
 
+        // ---- order the round's records by line length (a proxy for the walk length: 4-byte bins) so that the
+        // lanes of a warp carry walks of similar length; the lock-step node loops then idle much less
+        if (tid < 64) bin_cnt[tid] = 0;
+        __syncthreads();
+        for (uint32_t k = tid; k < n_round; k += INGEST_THREADS) {
+            const uint32_t s0 = rec_start[k];
+            const uint32_t e0 = (k + 1 < n_round) ? rec_start[k + 1] : s0 + 112u;
+            const uint32_t len = e0 - s0;
+            const uint32_t bin = len < 64u ? 0u : min((len - 64u) >> 2, 63u);
+            rec_tmp[k] = (uint16_t)((bin << 10) | atomicAdd(&bin_cnt[bin], 1u));
+        }
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of the 64 bin counts
+            const uint32_t c0 = bin_cnt[2 * lane], c1 = bin_cnt[2 * lane + 1];
+            uint32_t x = c0 + c1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= (uint32_t)d) x += y;
+            }
+            bin_cnt[2 * lane] = x - c0 - c1;
+            bin_cnt[2 * lane + 1] = x - c1;
+        }
+        __syncthreads();
+        for (uint32_t k = tid; k < n_round; k += INGEST_THREADS) {
+            const uint32_t t = rec_tmp[k];
+            order[bin_cnt[t >> 10] + (t & 1023u)] = (uint16_t)k;
+        }
+        __syncthreads();
+
         // ---- one thread per record; the lanes of a warp move through the columns in lock-step
         for (uint32_t k0 = 0; k0 < n_round; k0 += INGEST_THREADS) {
-            const uint32_t k = k0 + tid;
-            const bool has = k < n_round;
+            const bool has = k0 + tid < n_round;
+            const uint32_t k = has ? order[k0 + tid] : 0u;
             const uint32_t pmask = __ballot_sync(0xffffffffu, has);
             RecParse r;
             r.W = 0; r.mapq = NULL_I64; r.qlen = NULL_I64; r.stashed = false;
@@ -1207,10 +1240,11 @@ void launch_scan_tiles(const uint32_t* tile_count, uint32_t* tile_base, uint32_t
 
 template <int MODE>
 static void launch_ingest_mode(const IngestArgs& a, cudaStream_t st) {
-    const size_t smem = MAX_TILE + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + REC_CAP * sizeof(uint16_t);
+    const size_t smem_max = MAX_TILE + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 3 * REC_CAP * sizeof(uint16_t);
+    const size_t smem = (size_t)a.rows_per_warp * 4096 + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 3 * REC_CAP * sizeof(uint16_t);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_ingest<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_ingest<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         configured = true;
     }
     k_ingest<MODE><<<a.n_tiles, INGEST_THREADS, smem, st>>>(a);
