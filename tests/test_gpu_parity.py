@@ -256,3 +256,44 @@ def test_gpu_long_read_filter_handcrafted_edges():
     with pytest.raises(api.PantaxGpuError) as e:
         ctx.filter_gaf(bad + b"\n")
     assert e.value.name == "PTX_E_UNSUPPORTED"
+
+
+def test_gpu_full_size_config2_bit_exact_and_chunk_invariant():
+    """BASELINE.json configs[1] at FULL size (1 M nodes, 50 strain paths, 10 M short-read records, 1.1 GB of GAF):
+    every integer output equals the multithreaded oracle's bit for bit, and splitting the input into uneven
+    host chunks (lines cut anywhere) does not change a single value."""
+    import ctypes as C
+    from gpu_common import assert_gpu_matches_oracle
+    from common import ocpu
+    api = _api()
+    ds = synth.Dataset(20261017 + 2, [1_000_000], [50])
+    graphs = dataset_graphs(ds)
+    buf, nbytes = ds.gaf_raw(20261017 + 2, 0, 10_000_000)
+    try:
+        o = ocpu.CpuOracle(0)
+        o.set_ranges(ds.ranges())
+        o.set_graph(0, graphs[0][0], graphs[0][1])
+        o.prepare_graphs()
+        o.run(buf.value, nbytes)
+        assert o.n_records == 10_000_000
+        ctx = api.PantaxGpu(0)
+        ctx.set_ranges(ds.ranges())
+        ctx.upload_graph(0, graphs[0][0], graphs[0][1])
+        ctx.commit_graphs()
+        ctx.ingest_gaf(buf.value, nbytes, is_last=True)
+        ctx.finalize()
+        assert_gpu_matches_oracle(ctx, o, graphs)
+        ref_bases, ref_cov, ref_trio = ctx.node_bases(0), ctx.node_cov(0), ctx.trio_bases(0)
+        assert int(ref_bases.sum()) > 10_000_000 * 100
+        # same bytes in three uneven chunks that split lines
+        ctx.reset()
+        cuts = [0, 333_333_337, 333_333_337 + 700_000_001, nbytes]
+        for i in range(3):
+            ctx.ingest_gaf(buf.value + cuts[i], cuts[i + 1] - cuts[i], is_last=(i == 2))
+        ctx.finalize()
+        np.testing.assert_array_equal(ctx.node_bases(0), ref_bases)
+        np.testing.assert_array_equal(ctx.node_cov(0), ref_cov)
+        np.testing.assert_array_equal(ctx.trio_bases(0), ref_trio)
+        np.testing.assert_array_equal(ctx.species_counts(), o.species_counts())
+    finally:
+        synth.lib().synth_free(buf)
