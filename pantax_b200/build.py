@@ -28,7 +28,9 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__), os.path.join(HERE, "host", "pantax_gpu_profile.cpp")]
+    if not os.path.exists(os.path.join(HERE, "pantax-gpu-profile")):
+        return True
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -41,7 +43,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
+    build_host(verbose)
     return LIB
+
+
+HOST_SRC = os.path.join(HERE, "host", "pantax_gpu_profile.cpp")
+HOST_BIN = os.path.join(HERE, "pantax-gpu-profile")
+
+
+def build_host(verbose: bool = False) -> str:
+    """The C++ host driver over the C ABI (file formats, f64 tail, TSV writers)."""
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", HOST_SRC, "-o", HOST_BIN, "-L" + HERE, "-lpantax_gpu", "-Wl,-rpath,$ORIGIN",
+           "-Wl,-rpath-link," + "/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-lcudart"]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+    return HOST_BIN
 
 
 if __name__ == "__main__":

@@ -1,0 +1,449 @@
+// pantax-gpu-profile: host driver of the PanTax profiling stage over the C ABI (include/pantax_gpu.h).
+//
+// The reference's host side is Rust (profile.rs::profile, profile.rs:3325-3436); no Rust toolchain exists in
+// the build image, so the host glue is C++17.  It honours the reference's intermediate FILE FORMATS:
+//   <db>/species_range.txt            taxid \t start \t end \t is_pan        (sort_range.rs:35-38, zip.rs:308)
+//   <db>/species_genomes_stats.txt    taxid \t avg_len                      (stat.rs:131-139)
+//   <db>/species_graph_info/<t>.bin   bincode 1.3 of types.rs:51-55 Graph   (zip.rs:185, read at zip.rs:236-247)
+//   <db>/species_gfa/<t>.gfa          text GFA fallback                     (profile.rs:466-545, 2923-2927)
+//   <gaf>                             gfa_mapped.gaf                        (utils.rs:52)
+// and writes
+//   <wd>/reads_classification.tsv     read_id \t mapq \t species \t read_len, no header   (profile.rs:3337-3351)
+//   <wd>/species_abundance.txt        species_taxid predicted_abundance predicted_coverage  (profile.rs:338-347)
+//   <wd>/strain_inputs/<t>.nodes.tsv / .paths.tsv   what optimize_otu hands to the ILP (profile.rs:2936-2967):
+//        node depth, covered bases; per path: unique-trio fraction, frequencies_mean, path_cov_ratio, kept by
+//        first_filter_paths.  The ILP itself (profile.rs:1297-2882) stays in the reference's solvers.
+// All arithmetic on reads/nodes/paths runs in libpantax_gpu.so; this file does file I/O, the f64 tail and TSVs.
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+#include "../../include/pantax_gpu.h"
+
+namespace {
+
+struct Options {
+    std::string db, gaf, wd = ".", report, range_file, len_file, designated;
+    bool species = false, strain = false, filtered = true, long_read = false, shift = false, force = false;
+    double min_species_abundance = 1e-4, fr = -1, min_depth = 0;
+    int mode = 2, device = 0;
+};
+
+[[noreturn]] void die(const std::string& m) {
+    fprintf(stderr, "pantax-gpu-profile: %s\n", m.c_str());
+    exit(1);
+}
+void ck(ptx_ctx* ctx, int rc, const char* what) {
+    if (rc != PTX_OK) die(std::string(what) + ": " + (ctx ? ptx_last_error(ctx) : "error") + " (code " + std::to_string(rc) + ")");
+}
+bool exists(const std::string& p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0;
+}
+std::vector<std::string> split(const std::string& s, char d) {
+    std::vector<std::string> out;
+    size_t a = 0;
+    for (;;) {
+        size_t b = s.find(d, a);
+        out.push_back(s.substr(a, b == std::string::npos ? std::string::npos : b - a));
+        if (b == std::string::npos) break;
+        a = b + 1;
+    }
+    return out;
+}
+// shortest round-trip decimal like polars' CSV writer (ryu); whole numbers keep a ".0"
+std::string fmt_f64(double v) {
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, v);
+    std::string s(buf, r.ptr);
+    if (s.find_first_of(".en") == std::string::npos) s += ".0";
+    return s;
+}
+
+struct Range { std::string taxid; int64_t start, end; int is_pan; };
+
+std::vector<Range> read_ranges(const std::string& path) {
+    std::ifstream f(path);
+    if (!f) die("cannot open species range file " + path);
+    std::vector<Range> out;
+    std::string line;
+    while (std::getline(f, line)) {
+        if (line.empty()) continue;
+        auto p = split(line, '\t');
+        if (p.size() < 3) die("species range file: expected taxid<TAB>start<TAB>end[<TAB>is_pan]: " + line);  // sort_range.rs:15
+        out.push_back({p[0], std::stoll(p[1]), std::stoll(p[2]), p.size() > 3 ? std::stoi(p[3]) : 1});
+    }
+    return out;
+}
+
+struct Graph {  // types.rs:51-55
+    std::vector<int64_t> nodes_len;
+    std::map<std::string, std::vector<uint64_t>> paths;  // BTreeMap: name order
+};
+
+// bincode 1.3 default options: little-endian, fixed-width ints, u64 lengths (zip.rs:185 serialize_into)
+bool read_bin_graph(const std::string& path, Graph& g) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    auto rd64 = [&](uint64_t& v) { f.read(reinterpret_cast<char*>(&v), 8); return (bool)f; };
+    uint64_t n = 0;
+    if (!rd64(n)) return false;
+    g.nodes_len.resize(n);
+    f.read(reinterpret_cast<char*>(g.nodes_len.data()), (std::streamsize)(n * 8));
+    uint64_t np = 0;
+    if (!rd64(np)) return false;
+    for (uint64_t i = 0; i < np; ++i) {
+        uint64_t kl = 0, pl = 0;
+        if (!rd64(kl)) return false;
+        std::string key(kl, '\0');
+        f.read(key.data(), (std::streamsize)kl);
+        if (!rd64(pl)) return false;
+        std::vector<uint64_t> p(pl);
+        f.read(reinterpret_cast<char*>(p.data()), (std::streamsize)(pl * 8));
+        if (!f) return false;
+        g.paths[key] = std::move(p);
+    }
+    return true;
+}
+
+template <class F>
+void for_digit_runs(const std::string& s, bool allow_minus, F fn) {
+    size_t i = 0;
+    while (i < s.size()) {
+        if (isdigit((unsigned char)s[i])) {
+            bool neg = allow_minus && i > 0 && s[i - 1] == '-';
+            int64_t v = 0;
+            while (i < s.size() && isdigit((unsigned char)s[i])) v = v * 10 + (s[i++] - '0');
+            fn(neg ? -v : v);
+        } else {
+            ++i;
+        }
+    }
+}
+
+// profile.rs:466-545 (previous = 0)
+bool read_gfa_graph(const std::string& path, Graph& g) {
+    std::ifstream f(path);
+    if (!f) return false;
+    std::string line;
+    size_t idx = 0;
+    while (std::getline(f, line)) {
+        if (line.empty()) continue;
+        if (line[0] == 'S') {
+            auto p = split(line, '\t');
+            if (p.size() < 3) continue;
+            size_t id = std::stoull(p[1]) - 1;
+            if (id != idx) die("Node ID out of order or mismatch (profile.rs:489) in " + path);
+            ++idx;
+            if (p[2].empty()) die("Node length 0 appears in the GFA (profile.rs:494): " + path);
+            g.nodes_len.push_back((int64_t)p[2].size());
+        } else if (line[0] == 'W' || line[0] == 'P') {
+            while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
+            auto p = split(line, '\t');
+            std::string hap;
+            std::vector<uint64_t> nodes;
+            if (p[0] == "W") {
+                hap = p.size() > 1 ? p[1] : "";
+                for_digit_runs(p.back(), true, [&](int64_t v) { nodes.push_back((uint64_t)(v - 1)); });
+            } else {
+                hap = p.size() > 1 ? split(p[1], '#')[0] : "";
+                for_digit_runs(p.size() > 2 ? p[2] : "", false, [&](int64_t v) { nodes.push_back((uint64_t)(v - 1)); });
+            }
+            auto& dst = g.paths[hap];  // same hap id: chromosomes are concatenated (profile.rs:540)
+            dst.insert(dst.end(), nodes.begin(), nodes.end());
+        }
+    }
+    return true;
+}
+
+// profile.rs:1028-1051
+std::vector<double> zscore_filter(const std::vector<double>& d, double thr) {
+    if (d.empty()) return {};
+    double mean = 0;
+    for (double x : d) mean += x;
+    mean /= (double)d.size();
+    double var = 0;
+    for (double x : d) var += (x - mean) * (x - mean);
+    double sd = std::sqrt(var / (double)d.size());
+    if (sd == 0.0) return {};
+    std::vector<double> out;
+    for (double x : d)
+        if (std::fabs((x - mean) / sd) < thr) out.push_back(x);
+    return out;
+}
+double round2(double x) { return std::round(x * 100.0) / 100.0; }
+
+void usage() {
+    puts("pantax-gpu-profile --db DIR --gaf FILE [--wd DIR] [--species] [--strain] [-R reads_classification.tsv]\n"
+         "                   [-a MIN_SPECIES_ABUND=1e-4] [--fr F] [--long-read] [--shift] [--no-filter] [--smode 0|1|2]\n"
+         "                   [--ds TAXID,TAXID] [--range-file F] [--len-file F] [--min-depth D] [--device N]\n"
+         "GPU implementation of PanTax's profiling stage (read classification, species abundance, node coverage and\n"
+         "strain statistics).  Needs a CUDA device; there is no CPU fallback.");
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    Options o;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&]() -> std::string { if (i + 1 >= argc) die("missing value for " + a); return argv[++i]; };
+        if (a == "--db") o.db = next();
+        else if (a == "--gaf") o.gaf = next();
+        else if (a == "--wd" || a == "-T") o.wd = next();
+        else if (a == "--species") o.species = true;
+        else if (a == "--strain") o.strain = true;
+        else if (a == "-R" || a == "--report") o.report = next();
+        else if (a == "-a") o.min_species_abundance = std::stod(next());
+        else if (a == "--fr") o.fr = std::stod(next());
+        else if (a == "--long-read") o.long_read = true;
+        else if (a == "--shift") o.shift = true;
+        else if (a == "--no-filter") o.filtered = false;
+        else if (a == "--smode") o.mode = std::stoi(next());
+        else if (a == "--ds") o.designated = next();
+        else if (a == "--range-file") o.range_file = next();
+        else if (a == "--len-file") o.len_file = next();
+        else if (a == "--min-depth") o.min_depth = std::stod(next());
+        else if (a == "--device") o.device = std::stoi(next());
+        else if (a == "--force") o.force = true;
+        else if (a == "-h" || a == "--help") { usage(); return 0; }
+        else die("unknown option " + a);
+    }
+    if (!o.species && !o.strain) die("Please choose profiling level with --species or/and --strain.");  // profile.rs:73-75
+    if (o.db.empty() || o.gaf.empty()) { usage(); return 1; }
+    if (o.fr < 0) o.fr = o.long_read ? 0.5 : 0.3;  // main.rs:107-113
+    if (o.range_file.empty()) o.range_file = o.db + "/species_range.txt";
+    if (o.len_file.empty()) o.len_file = o.db + "/species_genomes_stats.txt";
+    mkdir(o.wd.c_str(), 0755);
+
+    const std::vector<Range> ranges = read_ranges(o.range_file);
+    if (ranges.empty()) die("species range file is empty");
+    ptx_ctx* ctx = nullptr;
+    if (ptx_create(o.device, &ctx) != PTX_OK) die("no usable CUDA device (this tool has no CPU fallback)");
+    {
+        std::vector<const char*> names;
+        std::vector<int64_t> st, en;
+        for (auto& r : ranges) { names.push_back(r.taxid.c_str()); st.push_back(r.start); en.push_back(r.end); }
+        ck(ctx, ptx_set_ranges(ctx, (int)ranges.size(), names.data(), st.data(), en.data()), "ptx_set_ranges");
+    }
+
+    // ---- read classification + species counts: stream the GAF through the library in 256 MB host chunks
+    FILE* gf = fopen(o.gaf.c_str(), "rb");
+    if (!gf) die("cannot open GAF mapping file " + o.gaf);
+    const size_t CH = (size_t)256 << 20;
+    void* pin = nullptr;
+    if (ptx_host_alloc(CH, &pin) != PTX_OK) die("pinned allocation failed");
+    std::vector<std::string> gaf_keep;  // only needed for reads_classification.tsv
+    const bool want_report = !o.report.empty();
+    for (;;) {
+        size_t n = fread(pin, 1, CH, gf);
+        const bool last = n < CH;
+        if (want_report) gaf_keep.emplace_back((const char*)pin, n);
+        ck(ctx, ptx_ingest_gaf(ctx, (const uint8_t*)pin, n, last ? 1 : 0), "ptx_ingest_gaf");
+        if (last) break;
+    }
+    fclose(gf);
+    ck(ctx, ptx_finalize(ctx), "ptx_finalize");
+    const int64_t R = ptx_num_records(ctx);
+    const int S = (int)ranges.size();
+    std::vector<int64_t> counts((size_t)S * 4);
+    ck(ctx, ptx_species_counts(ctx, counts.data()), "ptx_species_counts");
+    fprintf(stderr, "- Read classification: %lld GAF records, ids unique: %s\n", (long long)R, ptx_ids_unique(ctx) ? "yes" : "NO (duplicate read ids, profile.rs:460)");
+
+    if (want_report) {  // profile.rs:3337-3351
+        std::vector<uint32_t> labels((size_t)std::max<int64_t>(R, 1));
+        ck(ctx, ptx_read_labels(ctx, labels.data()), "ptx_read_labels");
+        FILE* rf = fopen(o.report.c_str(), "wb");
+        if (!rf) die("cannot write " + o.report);
+        std::string all;
+        for (auto& s : gaf_keep) all += s;
+        std::vector<std::string>().swap(gaf_keep);
+        size_t i = 0;
+        int64_t rec = 0;
+        auto is_int = [](const std::string& f) {
+            size_t k = (!f.empty() && (f[0] == '+' || f[0] == '-')) ? 1 : 0;
+            if (k == f.size() || f.size() - k > 18) return false;
+            for (; k < f.size(); ++k) if (!isdigit((unsigned char)f[k])) return false;
+            return true;
+        };
+        while (i < all.size()) {
+            size_t e = all.find('\n', i);
+            if (e == std::string::npos) e = all.size();
+            size_t l = e - i;
+            if (l && all[i + l - 1] == '\r') --l;
+            if (l && all[i] != '@') {
+                std::string line = all.substr(i, l);
+                auto f = split(line, '\t');
+                const uint32_t lab = rec < R ? labels[(size_t)rec] : PTX_LABEL_UNCLASSIFIED;
+                const std::string mapq = f.size() > 11 && is_int(f[11]) ? f[11] : "";
+                const std::string rlen = f.size() > 1 && is_int(f[1]) ? f[1] : "";
+                fprintf(rf, "%s\t%s\t%s\t%s\n", f[0].c_str(), mapq.c_str(), lab == PTX_LABEL_UNCLASSIFIED ? "U" : ranges[lab].taxid.c_str(), rlen.c_str());
+                ++rec;
+            }
+            i = e + 1;
+        }
+        fclose(rf);
+    }
+
+    // ---- species abundance (float tail of profile.rs:299-349)
+    std::map<std::string, double> species_len;
+    {
+        std::ifstream f(o.len_file);
+        if (!f) die("cannot open species length file " + o.len_file);
+        std::string line;
+        while (std::getline(f, line)) {
+            auto p = split(line, '\t');
+            if (p.size() >= 2) species_len[p[0]] = std::stod(p[1]);
+        }
+    }
+    int eq = 0;
+    int64_t rl0 = 0;
+    ck(ctx, ptx_equal_length(ctx, &eq, &rl0), "ptx_equal_length");
+    struct Row { std::string taxid; double rel, abs; };
+    std::vector<Row> table;
+    double total = 0;
+    for (int s = 0; s < S; ++s) {
+        const int64_t rc = counts[4 * s], sl = counts[4 * s + 1], lm = counts[4 * s + 2], uq = counts[4 * s + 3];
+        if (rc == 0) continue;
+        if (o.filtered && !(uq > 0 && (double)lm > (double)rc / 10.0)) continue;  // profile.rs:239-245
+        const double base = eq ? (double)(rc * rl0) : (double)sl;                 // :246 / :291
+        auto it = species_len.find(ranges[s].taxid);
+        const double ab = it == species_len.end() ? NAN : base / it->second;      // :333-337 (left join)
+        table.push_back({ranges[s].taxid, 0, ab});
+        if (!std::isnan(ab)) total += ab;
+    }
+    for (auto& r : table) r.rel = r.abs / total;
+    std::stable_sort(table.begin(), table.end(), [](const Row& a, const Row& b) { return a.rel > b.rel; });
+    {
+        FILE* f = fopen((o.wd + "/species_abundance.txt").c_str(), "wb");
+        if (!f) die("cannot write species_abundance.txt");
+        fprintf(f, "species_taxid\tpredicted_abundance\tpredicted_coverage\n");
+        for (auto& r : table) fprintf(f, "%s\t%s\t%s\n", r.taxid.c_str(), fmt_f64(r.rel).c_str(), fmt_f64(r.abs).c_str());
+        fclose(f);
+    }
+    fprintf(stderr, "- Species level profiling: %zu species\n", table.size());
+    if (!o.strain) { ptx_host_free(pin); ptx_destroy(ctx); return 0; }
+
+    // ---- strain level: graphs of the species that pass load_species_range (profile.rs:553-656)
+    std::set<std::string> wanted;
+    if (!o.designated.empty() && o.designated != "None")
+        for (auto& t : split(o.designated, ',')) if (!t.empty()) wanted.insert(t);
+    std::map<std::string, double> rel_of;
+    for (auto& r : table) rel_of[r.taxid] = r.rel;
+    std::vector<int> chosen;
+    for (int s = 0; s < S; ++s) {
+        if (o.mode == 0 && ranges[s].is_pan != 0) continue;
+        if (o.mode == 1 && ranges[s].is_pan != 1) continue;
+        if (!wanted.empty() && !wanted.count(ranges[s].taxid)) continue;
+        auto it = rel_of.find(ranges[s].taxid);
+        if (it == rel_of.end() || !(it->second > o.min_species_abundance)) continue;
+        chosen.push_back(s);
+    }
+    std::map<int, Graph> graphs;
+    for (int s : chosen) {
+        Graph g;
+        const std::string bin = o.db + "/species_graph_info/" + ranges[s].taxid + ".bin";
+        const std::string gfa = o.db + "/species_gfa/" + ranges[s].taxid + ".gfa";
+        if (!(exists(bin) && read_bin_graph(bin, g)) && !(exists(gfa) && read_gfa_graph(gfa, g)))
+            die("gfa information file for " + ranges[s].taxid + " does not exist. Please check database.");  // profile.rs:2929
+        std::vector<uint64_t> off{0}, flat;
+        for (auto& kv : g.paths) { flat.insert(flat.end(), kv.second.begin(), kv.second.end()); off.push_back(flat.size()); }
+        if (flat.empty()) flat.push_back(0);
+        ck(ctx, ptx_upload_graph(ctx, s, g.nodes_len.data(), (int64_t)g.nodes_len.size(), off.data(), flat.data(), (int64_t)g.paths.size()), "ptx_upload_graph");
+        graphs[s] = std::move(g);
+    }
+    if (chosen.empty()) { fprintf(stderr, "The filtering before strain profiling has removed all species.\n"); ptx_host_free(pin); ptx_destroy(ctx); return 0; }
+    ck(ctx, ptx_commit_graphs(ctx), "ptx_commit_graphs");
+    ck(ctx, ptx_finalize(ctx), "ptx_finalize (coverage)");  // replays the GAF text kept on the device
+
+    mkdir((o.wd + "/strain_inputs").c_str(), 0755);
+    for (int s : chosen) {
+        const Graph& g = graphs[s];
+        const int64_t n = (int64_t)g.nodes_len.size(), H = (int64_t)g.paths.size(), T = ptx_species_trios(ctx, s);
+        std::vector<double> depth((size_t)n), tdepth((size_t)std::max<int64_t>(T, 1));
+        std::vector<uint64_t> cov((size_t)n);
+        std::vector<uint32_t> owner((size_t)std::max<int64_t>(T, 1));
+        std::vector<int64_t> sc((size_t)std::max<int64_t>(H, 1)), sl((size_t)std::max<int64_t>(H, 1)), U((size_t)std::max<int64_t>(H, 1)), nz((size_t)std::max<int64_t>(H, 1));
+        int rc = ptx_node_depth(ctx, s, depth.data());
+        if (rc == PTX_E_START_GT_LEN) die(std::string("read start is bigger than node len (profile.rs:854) in species ") + ranges[s].taxid);
+        ck(ctx, rc, "ptx_node_depth");
+        ck(ctx, ptx_node_cov(ctx, s, cov.data()), "ptx_node_cov");
+        ck(ctx, ptx_trio_depth(ctx, s, tdepth.data()), "ptx_trio_depth");
+        ck(ctx, ptx_trio_table(ctx, s, nullptr, nullptr, owner.data()), "ptx_trio_table");
+        ck(ctx, ptx_path_sums(ctx, s, sc.data(), sl.data()), "ptx_path_sums");
+        ck(ctx, ptx_hap_trio_counts(ctx, s, U.data(), nz.data()), "ptx_hap_trio_counts");
+        {
+            FILE* f = fopen((o.wd + "/strain_inputs/" + ranges[s].taxid + ".nodes.tsv").c_str(), "wb");
+            fprintf(f, "node\tlen\tdepth\tcovered_bases\n");
+            for (int64_t i = 0; i < n; ++i)
+                if (depth[(size_t)i] > 0) fprintf(f, "%lld\t%lld\t%s\t%llu\n", (long long)i, (long long)g.nodes_len[(size_t)i], fmt_f64(depth[(size_t)i]).c_str(), (unsigned long long)cov[(size_t)i]);
+            fclose(f);
+        }
+        // first_filter_paths (profile.rs:1080-1227)
+        std::vector<std::string> hap_names;
+        for (auto& kv : g.paths) hap_names.push_back(kv.first);
+        FILE* f = fopen((o.wd + "/strain_inputs/" + ranges[s].taxid + ".paths.tsv").c_str(), "wb");
+        fprintf(f, "hap_id\tunique_trios\tunique_trios_covered\tunique_trio_fraction\tuniq_trio_cov_mean\tpath_base_cov\tsum_cov\tsum_len\tpossible\n");
+        std::vector<std::vector<double>> per_hap((size_t)H);
+        for (int64_t t = 0; t < T; ++t)
+            if (tdepth[(size_t)t] > 0.0) per_hap[owner[(size_t)t]].push_back(tdepth[(size_t)t]);  // trio index order within a hap
+        bool all_same = true;
+        if (H > 1 && T == 0) {
+            auto it0 = g.paths.begin();
+            for (auto it = std::next(it0); it != g.paths.end(); ++it) all_same = all_same && (it->second == it0->second);
+        }
+        double nz_mean = 0;
+        {
+            double sum = 0;
+            size_t c = 0;
+            for (double d : depth) { double x = d > o.min_depth ? d : 0.0; if (x > 0) { sum += x; ++c; } }  // profile.rs:2941-2944, 1212-1221
+            nz_mean = c ? sum / (double)c : 0.0;
+        }
+        for (int64_t h = 0; h < H; ++h) {
+            std::string frac_s = "", mean_s = "";
+            bool possible = false;
+            if (H != 1 && T != 0) {
+                if (U[(size_t)h] > 0) {  // :1119
+                    const double frac = (double)nz[(size_t)h] / (double)U[(size_t)h];
+                    frac_s = fmt_f64(round2(frac));
+                    auto zf = zscore_filter(per_hap[(size_t)h], 3.0);
+                    double fm = 0;
+                    for (double x : zf) fm += x;
+                    fm = zf.empty() ? 0.0 : fm / (double)zf.size();
+                    double thr = o.fr;
+                    if (o.shift) thr = fm >= 1.0 ? std::min(o.fr + (0.8 - o.fr) * fm / 100.0, 0.8) : o.fr * fm;  // :1148-1157
+                    if (!(frac < thr)) { possible = true; mean_s = fmt_f64(fm); }
+                }
+            } else if (H != 1) {
+                if (all_same) { if (h == 0) { possible = true; mean_s = fmt_f64(round2(nz_mean)); } }
+                else possible = true;  // :1206-1209
+            } else {
+                possible = true;
+                mean_s = fmt_f64(round2(nz_mean));
+            }
+            const float ratio = (float)sc[(size_t)h] / (float)sl[(size_t)h];  // profile.rs:2714-2728 (f32)
+            fprintf(f, "%s\t%lld\t%lld\t%s\t%s\t%s\t%lld\t%lld\t%d\n", hap_names[(size_t)h].c_str(), (long long)U[(size_t)h], (long long)nz[(size_t)h],
+                    frac_s.c_str(), mean_s.c_str(), fmt_f64((double)ratio).c_str(), (long long)sc[(size_t)h], (long long)sl[(size_t)h], possible ? 1 : 0);
+        }
+        fclose(f);
+    }
+    fprintf(stderr, "- Strain level statistics: %zu species written to %s/strain_inputs/\n", chosen.size(), o.wd.c_str());
+    char stats[2048];
+    if (ptx_stats_json(ctx, stats, sizeof stats) == PTX_OK) fprintf(stderr, "- device: %s\n", stats);
+    ptx_host_free(pin);
+    ptx_destroy(ctx);
+    return 0;
+}

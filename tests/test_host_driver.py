@@ -1,0 +1,120 @@
+"""The C++ host driver (pantax_b200/pantax-gpu-profile) on a synthetic PanTax database directory: the reference's
+file formats in (species_range.txt, species_genomes_stats.txt, bincode .bin graphs, a GFA fallback, a GAF), its
+output tables out - compared with the oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import NASTY, dataset_graphs, opy, py_graph, run_cpu_oracle, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "pantax_b200", "pantax-gpu-profile")
+
+
+def write_bin(path, nodes_len, paths, names):
+    """bincode 1.3 default (little-endian, fixed ints, u64 lengths) of types.rs:51-55 Graph, keys in byte order."""
+    with open(path, "wb") as f:
+        f.write(struct.pack("<Q", len(nodes_len)))
+        f.write(np.asarray(nodes_len, dtype="<i8").tobytes())
+        f.write(struct.pack("<Q", len(paths)))
+        for n, p in sorted(zip(names, paths), key=lambda t: t[0].encode()):
+            k = n.encode()
+            f.write(struct.pack("<Q", len(k)) + k + struct.pack("<Q", len(p)))
+            f.write(np.asarray(p, dtype="<u8").tobytes())
+
+
+def write_gfa(path, nodes_len, paths, names):
+    with open(path, "w") as f:
+        f.write("H\tVN:Z:1.1\n")
+        for i, l in enumerate(nodes_len):
+            f.write(f"S\t{i + 1}\t{'A' * int(l)}\n")
+        for n, p in zip(names, paths):
+            f.write(f"W\t{n}\t0\tchr1\t0\t100\t" + "".join(f">{int(v) + 1}" for v in p) + "\n")
+
+
+def make_db(tmp, ds, graphs, gaf):
+    db = os.path.join(tmp, "db")
+    os.makedirs(os.path.join(db, "species_graph_info"))
+    os.makedirs(os.path.join(db, "species_gfa"))
+    with open(os.path.join(db, "species_range.txt"), "w") as f:
+        for s, (t, a, b) in enumerate(ds.ranges()):
+            f.write(f"{t}\t{a}\t{b}\t{1 if len(graphs[s][1]) > 1 else 0}\n")
+    lens = {}
+    with open(os.path.join(db, "species_genomes_stats.txt"), "w") as f:
+        for s, (t, _a, _b) in enumerate(ds.ranges()):
+            lens[t] = float(int(graphs[s][0].sum()) // max(1, len(graphs[s][1]))) + 0.5
+            f.write(f"{t}\t{lens[t]}\n")
+    for s, (t, _a, _b) in enumerate(ds.ranges()):
+        if s == 1:  # one species only as text GFA: exercises the fallback reader (profile.rs:2923-2927)
+            write_gfa(os.path.join(db, "species_gfa", f"{t}.gfa"), *graphs[s])
+        else:
+            write_bin(os.path.join(db, "species_graph_info", f"{t}.bin"), *graphs[s])
+    gp = os.path.join(tmp, "gfa_mapped.gaf")
+    with open(gp, "wb") as f:
+        f.write(gaf)
+    return db, gp, lens
+
+
+def test_host_driver_help_runs_without_gpu():
+    out = subprocess.run([BIN, "--help"], capture_output=True, text=True)
+    assert out.returncode == 0 and "--strain" in out.stdout
+
+
+@pytest.mark.gpu
+def test_host_driver_end_to_end_against_oracle(tmp_path):
+    ds = synth.Dataset(404, [30000, 9000, 4000], [6, 3, 1])
+    graphs = dataset_graphs(ds)
+    gaf = ds.gaf(8, 0, 60000, NASTY)
+    db, gp, lens = make_db(str(tmp_path), ds, graphs, gaf)
+    wd = os.path.join(str(tmp_path), "wd")
+    rep = os.path.join(wd, "reads_classification.tsv")
+    os.makedirs(wd)
+    r = subprocess.run([BIN, "--db", db, "--gaf", gp, "--wd", wd, "--species", "--strain", "-R", rep, "-a", "0"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ranges = ds.ranges()
+    rows = opy.rcls_profile(gaf, ranges)
+    # reads_classification.tsv (profile.rs:3337-3351): read_id, mapq, species, read_len
+    got = [l.split("\t") for l in open(rep).read().split("\n")[:-1]]
+    assert len(got) == len(rows)
+    for g, row in zip(got, rows):
+        assert g[0].encode() == row.read_id and g[2] == row.species
+        assert g[1] == ("" if row.mapq is None else str(row.mapq)) and g[3] == ("" if row.read_len is None else str(row.read_len))
+    # species_abundance.txt (profile.rs:299-349)
+    exp = opy.species_profiling(rows, lens, filtered=True)
+    lines = open(os.path.join(wd, "species_abundance.txt")).read().split("\n")
+    assert lines[0] == "species_taxid\tpredicted_abundance\tpredicted_coverage"
+    tab = [l.split("\t") for l in lines[1:] if l]
+    assert [t[0] for t in tab] == [e[0] for e in exp]
+    for t, e in zip(tab, exp):
+        assert float(t[1]) == pytest.approx(e[1], rel=1e-13) and float(t[2]) == e[2]
+    # strain inputs: integers bit-exact, single divisions identical, first_filter_paths decisions identical
+    o = run_cpu_oracle(ranges, graphs, gaf)
+    for s, (t, _a, _b) in enumerate(ranges):
+        nodes = [l.split("\t") for l in open(os.path.join(wd, "strain_inputs", f"{t}.nodes.tsv")).read().split("\n")[1:] if l]
+        bases, cov = o.node_bases(s), o.node_cov(s)
+        nz = np.nonzero(bases)[0]
+        assert [int(n[0]) for n in nodes] == nz.tolist()
+        for n in nodes:
+            i = int(n[0])
+            assert float(n[2]) == bases[i] / graphs[s][0][i] and int(n[3]) == cov[i]
+        paths = [l.split("\t") for l in open(os.path.join(wd, "strain_inputs", f"{t}.paths.tsv")).read().split("\n")[1:] if l]
+        U, nzc = o.hap_trio_counts(s)
+        sc, sl = o.path_sums(s)
+        assert [int(p[1]) for p in paths] == U.tolist() and [int(p[2]) for p in paths] == nzc.tolist()
+        assert [int(p[6]) for p in paths] == sc.tolist() and [int(p[7]) for p in paths] == sl.tolist()
+        _k, tlen, owner = o.trio_table(s)
+        trio_ab = (o.trio_bases(s) / np.maximum(tlen, 1)).tolist()
+        node_ab = (bases / graphs[s][0]).tolist()
+        possible, metrics, _same = opy.first_filter_paths(py_graph(*graphs[s]), owner.tolist(), trio_ab, node_ab, fr=0.3)
+        assert [h for h, p in enumerate(paths) if p[8] == "1"] == possible
+        for h, p in enumerate(paths):
+            m = metrics[h]
+            if m["unique_trio_nodes_fraction"] is not None:
+                assert float(p[3]) == m["unique_trio_nodes_fraction"]
+            if m["frequencies_mean"] is not None and p[4]:
+                assert float(p[4]) == pytest.approx(m["frequencies_mean"], rel=1e-12)
+            assert float(p[5]) == float(np.float32(sc[h]) / np.float32(sl[h]))
