@@ -17,7 +17,8 @@ namespace ptx {
 // mean line length so that a tile holds about one record per thread.  A record therefore starts in
 // (t*tile, (t+1)*tile]; the tile is staged in shared memory as text[t*tile, t*tile + tile + OVER).
 constexpr uint32_t MICRO = 4096;
-constexpr uint32_t MAX_TILE = 32768;
+constexpr uint32_t MAX_ROWS = 8;  // rows of 512 B a warp scans per tile
+constexpr uint32_t MAX_TILE = MAX_ROWS * MICRO;
 constexpr uint32_t OVER = 2048;
 constexpr uint32_t PRE = 256;  // keeps `text` 256-byte aligned inside a cudaMalloc'ed buffer
 constexpr int INGEST_THREADS = 256;

@@ -418,9 +418,11 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
     uint16_t* rec_start = reinterpret_cast<uint16_t*>(stash + STASH_CAP * INGEST_THREADS);  // [REC_CAP] record starts
     uint16_t* rec_tmp = rec_start + REC_CAP;                                                 // [REC_CAP] (bin, rank in bin)
     uint16_t* order = rec_tmp + REC_CAP;                                                     // [REC_CAP] records by line length
+    uint16_t* inv_pre = order + REC_CAP;                                                     // [REC_CAP] invalid line slots before slot k
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t warp_tot[INGEST_THREADS / 32];
     __shared__ uint32_t bin_cnt[64];
+    __shared__ uint32_t inv_flag, inv_tot_s;
 
     const uint64_t t0 = (uint64_t)blockIdx.x * tile_bytes;
     const uint8_t* gtile = a.text + t0;
@@ -444,49 +446,42 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
     const RangesView& R = a.ranges;
     __syncthreads();  // sentinel visible
 
-    uint32_t n_rec = 0;
+    uint32_t n_rec = 0;       // line slots of the tile: every line start behind an owned newline (valid record or not)
+    uint32_t valid_prev = 0;  // valid records in the previous rounds of this tile
     for (uint32_t round = 0; round == 0 || round < n_rec; round += REC_CAP) {
-        // ---- record starts: warp w scans stage[w*rows*512, +rows*512) as `rows` rows of 32 x 16 B.
-        // (Recomputed in the rare extra rounds of a tile with more than REC_CAP records, so that the
-        // per-row counters do not stay live in registers while the records are processed.)
+        // ---- line starts: warp w scans stage[w*rows*512, +rows*512) as `rows` rows of 32 x 16 B.  Per 16-byte
+        // piece the 16 newline flags are packed into one word (bit = word + 8*byte); no per-newline loop.
+        // (Recomputed in the rare extra rounds of a tile with more than REC_CAP lines, so that the per-row
+        // words do not stay live in registers while the records are processed.)
         {
-            uint32_t c[8];
+            uint32_t mmv[MAX_ROWS];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                uint32_t n = 0;
+            for (int j = 0; j < (int)MAX_ROWS; ++j) {
+                uint32_t mm = 0;
                 if ((uint32_t)j < rows) {
-                    const uint32_t off = wbase_byte + (uint32_t)j * 512u + lane * 16u;
-                    uint4 q = *reinterpret_cast<const uint4*>(stage + off);
-                    uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint32_t m = nl_mask4(w[i]);
-                        while (m) {
-                            uint32_t byte = (__ffs(m) - 1) >> 3;
-                            m &= m - 1;
-                            n += valid_first(stage, off + i * 4 + byte + 1) ? 1u : 0u;
-                        }
-                    }
+                    const uint4 q = *reinterpret_cast<const uint4*>(stage + wbase_byte + (uint32_t)j * 512u + lane * 16u);
+                    mm = (nl_mask4(q.x) >> 7) | (nl_mask4(q.y) >> 6) | (nl_mask4(q.z) >> 5) | (nl_mask4(q.w) >> 4);
                 }
-                c[j] = n;
+                mmv[j] = mm;
             }
-            const bool first_rec = (blockIdx.x == 0 && tid == 0 && valid_first(stage, 0));
-            if (first_rec) c[0] += 1;
+            const uint32_t first_slot = (blockIdx.x == 0 && tid == 0) ? 1u : 0u;  // the line at text[0] (behind the PRE padding)
             // exclusive position of (row j, lane) inside the warp, rows first
-            uint32_t pre[8];
+            uint32_t pre[MAX_ROWS];
             uint32_t run = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                uint32_t x = c[j];
+            for (int j = 0; j < (int)MAX_ROWS; ++j) {
+                const uint32_t cj = __popc(mmv[j]) + (j == 0 ? first_slot : 0u);
+                uint32_t x = cj;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
                     if (lane >= (uint32_t)d) x += y;
                 }
-                pre[j] = run + x - c[j];
+                pre[j] = run + x - cj;
                 run += __shfl_sync(0xffffffffu, x, 31);
             }
             if (lane == 0) warp_tot[warp] = run;
+            if (tid == 0) inv_flag = 0;
             __syncthreads();
             uint32_t my_base = 0;
             n_rec = 0;
@@ -496,27 +491,24 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
                 if ((uint32_t)w < warp) my_base += t;
                 n_rec += t;
             }
-            // ---- compact this round's record starts into shared memory
+            // ---- compact this round's line starts into shared memory
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (c[j] == 0) continue;
+            for (int j = 0; j < (int)MAX_ROWS; ++j) {
+                const uint32_t mm = mmv[j];
                 uint32_t idx = my_base + pre[j];
-                if (j == 0 && first_rec) {
+                if (j == 0 && first_slot) {
                     if (idx >= round && idx < round + REC_CAP) rec_start[idx - round] = 0;
                     ++idx;
                 }
-                const uint32_t off = wbase_byte + (uint32_t)j * 512u + lane * 16u;
-                uint4 q = *reinterpret_cast<const uint4*>(stage + off);
-                uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint32_t m = nl_mask4(w[i]);
-                    while (m) {
-                        uint32_t byte = (__ffs(m) - 1) >> 3;
-                        m &= m - 1;
-                        uint32_t qpos = off + i * 4 + byte + 1;
-                        if (valid_first(stage, qpos)) {
-                            if (idx >= round && idx < round + REC_CAP) rec_start[idx - round] = (uint16_t)qpos;
+                if (mm == 0) continue;
+                const uint32_t off = wbase_byte + (uint32_t)j * 512u + lane * 16u + 1u;
+                if ((mm & (mm - 1)) == 0) {  // one newline in the piece (lines are longer than 16 bytes)
+                    const uint32_t bit = __ffs(mm) - 1;
+                    if (idx >= round && idx < round + REC_CAP) rec_start[idx - round] = (uint16_t)(off + ((bit & 7u) << 2) + (bit >> 3));
+                } else {  // several very short lines: emit in byte order
+                    for (uint32_t pos = 0; pos < 16; ++pos) {
+                        if ((mm >> ((pos >> 2) + 8u * (pos & 3u))) & 1u) {
+                            if (idx >= round && idx < round + REC_CAP) rec_start[idx - round] = (uint16_t)(off + pos);
                             ++idx;
                         }
                     }
@@ -525,6 +517,31 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
         }
         __syncthreads();
         const uint32_t n_round = min(REC_CAP, n_rec - round);
+
+        // ---- empty lines and '@' comments are line slots but not records: they are rare and only shift the record
+        // numbering (labels[]); inv_pre[k] = invalid slots before slot k is built only if the tile has any
+        uint32_t inv_total = 0;
+        if (MODE & MODE_CLASSIFY) {
+            bool inv = false;
+            for (uint32_t k = tid; k < n_round; k += INGEST_THREADS) inv |= !valid_first(stage, rec_start[k]);
+            if (inv) inv_flag = 1;
+            __syncthreads();
+            if (inv_flag) {
+                if (warp == 0) {
+                    uint32_t base = 0;
+                    for (uint32_t k0 = 0; k0 < n_round; k0 += 32) {
+                        const uint32_t k = k0 + lane;
+                        const bool bad = k < n_round && !valid_first(stage, rec_start[k]);
+                        const unsigned bm = __ballot_sync(0xffffffffu, bad);
+                        if (k < n_round) inv_pre[k] = (uint16_t)(base + __popc(bm & ((1u << lane) - 1u)));
+                        base += __popc(bm);
+                    }
+                    if (lane == 0) inv_tot_s = base;
+                }
+                __syncthreads();
+                inv_total = inv_tot_s;
+            }
+        }
 
         // ---- order the round's records by line length (a proxy for the walk length: 4-byte bins) so that the
         // lanes of a warp carry walks of similar length; the lock-step node loops then idle much less
@@ -558,15 +575,16 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
 
         // ---- one thread per record; the lanes of a warp move through the columns in lock-step
         for (uint32_t k0 = 0; k0 < n_round; k0 += INGEST_THREADS) {
-            const bool has = k0 + tid < n_round;
-            const uint32_t k = has ? order[k0 + tid] : 0u;
+            const bool slot = k0 + tid < n_round;
+            const uint32_t k = slot ? order[k0 + tid] : 0u;
+            const uint32_t p = slot ? rec_start[k] : 0u;
+            const bool has = slot && valid_first(stage, p);  // not an empty line / '@' comment (rcls.rs:123)
             const uint32_t pmask = __ballot_sync(0xffffffffu, has);
             RecParse r;
             r.W = 0; r.mapq = NULL_I64; r.qlen = NULL_I64; r.stashed = false;
             uint32_t label = LABEL_U;
             const uint8_t* b = stage;
             if (has) {
-                const uint32_t p = rec_start[k];
                 if (!parse_record(stage, p, stage_bytes, r, pmask, stash + tid, INGEST_THREADS, STASH_CAP)) {
                     // the columns run past the staged window (at most one record per tile; long lines only)
                     RecParse tmp;
@@ -575,7 +593,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
                     r = tmp;
                 }
                 label = classify(R, r.W ? r.vmin : -1, r.W ? r.vmax : -1);
-                if (MODE & MODE_CLASSIFY) a.labels[rec_base + round + k] = label;
+                if (MODE & MODE_CLASSIFY) a.labels[rec_base + valid_prev + k - (inv_total ? (uint32_t)inv_pre[k] : 0u)] = label;
             }
             __syncwarp();
             if (MODE & MODE_CLASSIFY) {
@@ -632,6 +650,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
             }
             __syncwarp();
         }
+        valid_prev += n_round - inv_total;
         __syncthreads();
     }
 }
@@ -1240,8 +1259,8 @@ void launch_scan_tiles(const uint32_t* tile_count, uint32_t* tile_base, uint32_t
 
 template <int MODE>
 static void launch_ingest_mode(const IngestArgs& a, cudaStream_t st) {
-    const size_t smem_max = MAX_TILE + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 3 * REC_CAP * sizeof(uint16_t);
-    const size_t smem = (size_t)a.rows_per_warp * 4096 + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 3 * REC_CAP * sizeof(uint16_t);
+    const size_t smem_max = MAX_TILE + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 4 * REC_CAP * sizeof(uint16_t);
+    const size_t smem = (size_t)a.rows_per_warp * 4096 + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 4 * REC_CAP * sizeof(uint16_t);
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(k_ingest<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
