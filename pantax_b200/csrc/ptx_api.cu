@@ -79,6 +79,14 @@ struct Chunk {
     uint64_t* tile_base = nullptr;   // [n_micro + 1] exclusive record prefix, last = total
     uint64_t* scan_scratch = nullptr;
     uint32_t* labels = nullptr;
+    // record table + CSR walks (k_ingest -> k_apply)
+    uint4* meta_b = nullptr;
+    longlong2* meta_a = nullptr;
+    unsigned long long* hash_lo = nullptr;
+    uint32_t* nodes = nullptr;
+    unsigned long long* cursors = nullptr;  // [0] total line slots (K1), then reused as 2 x uint32 cursors
+    int64_t slots_cap = 0, nodes_cap = 0;
+    int64_t n_slots = 0;
     uint32_t tiles_cap = 0;
     int64_t labels_cap = 0;
     int64_t n_records = 0;
@@ -129,7 +137,7 @@ struct ptx_ctx {
     size_t scratch2_cap = 0;
     uint64_t xchg_box_cap = 0;  // per-owner outbox capacity of the id-group exchange (sticky)
     // timing
-    std::vector<EvPair> ev_count, ev_ingest, ev_final;
+    std::vector<EvPair> ev_count, ev_ingest, ev_apply, ev_final;
     // multi-GPU
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
@@ -251,6 +259,11 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.rows_per_warp = ch.rows;
     a.micro_base = ch.tile_base;
     a.labels = ch.labels;
+    a.meta_b = ch.meta_b;
+    a.meta_a = ch.meta_a;
+    a.hash_lo = ch.hash_lo;
+    a.nodes = ch.nodes;
+    a.cursors = reinterpret_cast<uint32_t*>(ch.cursors + 1);
     a.ranges = ranges_view(ctx);
     a.hist = ctx->d_hist;
     a.ds = ctx->d_ds;
@@ -323,6 +336,7 @@ void chunk_free(Chunk& ch) {
     dfree(ch.tile_base);
     dfree(ch.scan_scratch);
     dfree(ch.labels);
+    dfree(ch.meta_b); dfree(ch.meta_a); dfree(ch.hash_lo); dfree(ch.nodes); dfree(ch.cursors);
     if (ch.copied) cudaEventDestroy(ch.copied);
     ch.copied = nullptr;
 }
@@ -344,15 +358,33 @@ int chunk_process(ptx_ctx* ctx, Chunk& ch) {
         CU(cudaMalloc((void**)&ch.scan_scratch, ((size_t)ch.n_micro / 2048 + 4) * sizeof(uint64_t)));
         ch.tiles_cap = ch.n_micro;
     }
+    if (ch.n >= (1ull << 32)) return fail(ctx, PTX_E_INVALID, "a chunk must be smaller than 4 GiB (split the input)");
+    if (!ch.cursors) CU(cudaMalloc((void**)&ch.cursors, 2 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(ch.cursors, 0, 2 * sizeof(unsigned long long), ctx->st));
     ev_begin(ctx, ctx->ev_count);
-    launch_count_records(ch.buf + PRE, ch.n_micro, ch.tile_count, ctx->st);
+    launch_count_records(ch.buf + PRE, ch.n, ch.n_micro, ch.tile_count, ch.cursors, ctx->st);
     launch_scan_u32(ch.tile_count, ch.tile_base, ch.n_micro, ch.scan_scratch, ctx->st);
     ev_end(ctx, ctx->ev_count);
-    uint64_t total = 0;
+    uint64_t total = 0, slots = 0;
     CU(cudaMemcpyAsync(&total, ch.tile_base + ch.n_micro, sizeof total, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&slots, ch.cursors, sizeof slots, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     ch.n_records = (int64_t)total;
-    if (total > 0xFFFFFFF0ull) return fail(ctx, PTX_E_INVALID, "more than 2^32 records in one chunk");
+    ch.n_slots = (int64_t)slots;
+    if (slots > 0xFFFFFFF0ull) return fail(ctx, PTX_E_INVALID, "more than 2^32 lines in one chunk");
+    if (ch.slots_cap < ch.n_slots) {
+        dfree(ch.meta_b); dfree(ch.meta_a); dfree(ch.hash_lo);
+        const size_t cap = (size_t)std::max<int64_t>(ch.n_slots, 1);
+        CU(cudaMalloc((void**)&ch.meta_b, cap * sizeof(uint4)));
+        CU(cudaMalloc((void**)&ch.meta_a, cap * sizeof(longlong2)));
+        CU(cudaMalloc((void**)&ch.hash_lo, cap * sizeof(unsigned long long)));
+        ch.slots_cap = (int64_t)cap;
+    }
+    if (ch.nodes_cap < (int64_t)(ch.n / 2 + 16)) {  // a walk node takes at least two bytes of text
+        dfree(ch.nodes);
+        ch.nodes_cap = (int64_t)(ch.n / 2 + 16);
+        CU(cudaMalloc((void**)&ch.nodes, (size_t)ch.nodes_cap * sizeof(uint32_t)));
+    }
     // tile size: about one record per thread (mean line length measured by K1), 4 KB granularity
     {
         const double mean_line = (double)ch.n / (double)std::max<uint64_t>(total, 1);
@@ -373,8 +405,11 @@ int chunk_process(ptx_ctx* ctx, Chunk& ch) {
     IngestArgs a = make_args(ctx, ch);
     const bool cover = ctx->graphs_committed && ctx->g.N > 0;
     ev_begin(ctx, ctx->ev_ingest);
-    launch_ingest(a, MODE_CLASSIFY | (cover ? MODE_COVER : 0), ctx->st);
+    launch_ingest(a, ctx->st);
     ev_end(ctx, ctx->ev_ingest);
+    ev_begin(ctx, ctx->ev_apply);
+    launch_apply(a, (uint32_t)ch.n_slots, MODE_CLASSIFY | (cover ? MODE_COVER : 0), ctx->st);
+    ev_end(ctx, ctx->ev_apply);
     CU(cudaGetLastError());
     ch.ingested = true;
     ch.covered = cover;
@@ -577,6 +612,7 @@ void ptx_destroy(ptx_ctx* ctx) {
     dfree(ctx->d_hist); dfree(ctx->d_hist_g); dfree(ctx->d_flags); dfree(ctx->d_err); dfree(ctx->d_ds); dfree(ctx->d_total);
     ev_clear(ctx->ev_count);
     ev_clear(ctx->ev_ingest);
+    ev_clear(ctx->ev_apply);
     ev_clear(ctx->ev_final);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     if (ctx->st) cudaStreamDestroy(ctx->st);
@@ -940,7 +976,7 @@ int ptx_finalize(ptx_ctx* ctx) {
         for (auto& ch : ctx->chunks) {
             if (!ch.ingested || ch.covered || ch.n_tiles == 0) continue;
             IngestArgs a = make_args(ctx, ch);
-            launch_ingest(a, MODE_COVER | (mixed ? MODE_KEEPMASK : 0), ctx->st);
+            launch_apply(a, (uint32_t)ch.n_slots, MODE_COVER | (mixed ? MODE_KEEPMASK : 0), ctx->st);  // from the record table: no text is re-read
             ch.covered = true;
         }
         tr.mark("final replay/cover");
@@ -1016,6 +1052,7 @@ static int reset_impl(ptx_ctx* ctx, bool keep_buffers) {
     ctx->h_err.assign(ctx->sp.size(), 0);
     ev_clear(ctx->ev_count);
     ev_clear(ctx->ev_ingest);
+    ev_clear(ctx->ev_apply);
     ev_clear(ctx->ev_final);
     ctx->dirty = false;
     return PTX_OK;
@@ -1331,7 +1368,7 @@ int ptx_timing(ptx_ctx* ctx, double* ingest_ms, double* finalize_ms, int64_t* ke
     if (!ctx) return PTX_E_INVALID;
     cudaSetDevice(ctx->device);
     CU(cudaStreamSynchronize(ctx->st));
-    if (ingest_ms) *ingest_ms = ev_sum(ctx->ev_count) + ev_sum(ctx->ev_ingest);
+    if (ingest_ms) *ingest_ms = ev_sum(ctx->ev_count) + ev_sum(ctx->ev_ingest) + ev_sum(ctx->ev_apply);
     if (finalize_ms) *finalize_ms = ev_sum(ctx->ev_final);
     if (kernel_launches) *kernel_launches = kernel_launch_count();
     return PTX_OK;
@@ -1346,10 +1383,10 @@ int ptx_stats_json(ptx_ctx* ctx, char* buf, size_t cap) {
     snprintf(buf, cap,
              "{\"records\": %lld, \"chunks\": %zu, \"text_bytes\": %zu, \"nodes\": %lld, \"paths\": %lld, \"path_steps\": %lld, "
              "\"unique_trios\": %lld, \"bit_words\": %llu, \"id_set_slots\": %llu, \"ids_unique\": %d, \"mixed_groups\": %d, "
-             "\"count_ms\": %.4f, \"ingest_ms\": %.4f, \"ingest_launches\": %zu, \"finalize_ms\": %.4f, \"kernel_launches\": %lld, \"ranks\": %d}",
+             "\"count_ms\": %.4f, \"ingest_ms\": %.4f, \"apply_ms\": %.4f, \"ingest_launches\": %zu, \"finalize_ms\": %.4f, \"kernel_launches\": %lld, \"ranks\": %d}",
              (long long)ctx->total_records, ctx->chunks.size(), text, (long long)ctx->g.N, (long long)ctx->g.Htot, (long long)ctx->g.P,
              (long long)ctx->g.T, (unsigned long long)ctx->g.n_bit_words, (unsigned long long)ctx->ds_cap, ctx->h_flags[0] == 0 ? 1 : 0,
-             ctx->h_flags[1] != 0 ? 1 : 0, ev_sum(ctx->ev_count), ev_sum(ctx->ev_ingest), ctx->ev_ingest.size(), ev_sum(ctx->ev_final), (long long)kernel_launch_count(), ctx->n_ranks);
+             ctx->h_flags[1] != 0 ? 1 : 0, ev_sum(ctx->ev_count), ev_sum(ctx->ev_ingest), ev_sum(ctx->ev_apply), ctx->ev_ingest.size(), ev_sum(ctx->ev_final), (long long)kernel_launch_count(), ctx->n_ranks);
     return PTX_OK;
 }
 

@@ -25,7 +25,13 @@ constexpr int INGEST_THREADS = 256;
 constexpr uint32_t REC_CAP = 1024;  // record starts kept in smem per round
 constexpr uint32_t STASH_CAP = 16;  // walk nodes per record kept in smem between the parse and the coverage pass
 
-// mode flags of the ingest kernel
+// record-table flags (IngestArgs::meta_b[e].y): walk length in the low 24 bits
+constexpr uint32_t RM_W_MASK = 0x00FFFFFFu;
+constexpr uint32_t RM_LABELLED = 0x80000000u;  // species label != U
+constexpr uint32_t RM_ELIGIBLE = 0x40000000u;  // path, c7, c8, c9 all non-null (profile.rs:380-399)
+constexpr uint32_t RM_MONOTONE = 0x20000000u;  // strictly monotone node ids: no node repeats in the walk
+
+// mode flags of k_apply
 constexpr int MODE_CLASSIFY = 1;  // labels, species counts, read-id set insert
 constexpr int MODE_COVER = 2;     // node coverage / trio accumulation
 constexpr int MODE_KEEPMASK = 4;  // skip reads whose id group is DS_MIXED (replay pass)
@@ -67,6 +73,12 @@ struct IngestArgs {
     uint32_t rows_per_warp;      // tile = rows_per_warp * 4096 bytes
     const uint64_t* micro_base;  // [n_micro] exclusive record prefix per micro-tile within the chunk (MODE_CLASSIFY)
     uint32_t* labels;           // [chunk records]
+    // record table + CSR walks written by k_ingest, consumed by k_apply (entries in length-sorted tile order)
+    uint4* meta_b;              // [line slots] {node_off, flags|W, label, id hash hi}
+    longlong2* meta_a;          // [line slots] {c8, c9} of eligible records
+    unsigned long long* hash_lo;  // [line slots] id hash lo of labelled records
+    uint32_t* nodes;            // [<= text bytes / 2] raw node ids of eligible records' walks
+    uint32_t* cursors;          // [0] next record-table entry, [1] next node slot
     RangesView ranges;
     unsigned long long* hist;   // [S*4]
     ulonglong2* ds;             // read-id set slots
@@ -87,9 +99,11 @@ struct IngestArgs {
 };
 
 // launchers (ptx_kernels.cu); all asynchronous on `st`
-void launch_count_records(const uint8_t* text, uint32_t n_micro, uint32_t* micro_count, cudaStream_t st);
+void launch_count_records(const uint8_t* text, uint64_t n_bytes, uint32_t n_micro, uint32_t* micro_count, unsigned long long* total_slots,
+                          cudaStream_t st);
 void launch_scan_tiles(const uint32_t* tile_count, uint32_t* tile_base, uint32_t n_tiles, uint64_t* total, cudaStream_t st);
-void launch_ingest(const IngestArgs& a, int mode, cudaStream_t st);
+void launch_ingest(const IngestArgs& a, cudaStream_t st);
+void launch_apply(const IngestArgs& a, uint32_t n_entries, int mode, cudaStream_t st);
 void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2* new_slots, uint32_t new_shift,
                       uint64_t new_mask, cudaStream_t st);
 void launch_fill_u8(uint8_t* p, uint8_t v, uint64_t n, cudaStream_t st);

@@ -92,31 +92,46 @@ __device__ __forceinline__ bool valid_first(const uint8_t* b, uint32_t q) {
 // =====================================================================================
 // K1: records per 4 KB micro-tile (one warp each); tiles of the ingest kernel are runs of micro-tiles
 // =====================================================================================
-__global__ void __launch_bounds__(256) k_count_records(const uint8_t* __restrict__ text, uint32_t n_micro,
-                                                       uint32_t* __restrict__ micro_count) {
+__global__ void __launch_bounds__(256) k_count_records(const uint8_t* __restrict__ text, uint64_t n_bytes, uint32_t n_micro,
+                                                       uint32_t* __restrict__ micro_count, unsigned long long* __restrict__ total_slots) {
     const uint32_t mt = blockIdx.x * 8u + (threadIdx.x >> 5);
-    if (mt >= n_micro) return;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint8_t* tb = text + (uint64_t)mt * MICRO;
-    uint32_t cnt = 0;
+    uint32_t cnt = 0, slots = 0;
+    if (mt < n_micro) {
+        const uint8_t* tb = text + (uint64_t)mt * MICRO;
+        const uint64_t base = (uint64_t)mt * MICRO;
 #pragma unroll
-    for (int j = 0; j < (int)(MICRO / 512); ++j) {
-        const uint32_t off = (uint32_t)j * 512u + lane * 16u;
-        uint4 q = __ldg(reinterpret_cast<const uint4*>(tb + off));
-        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        for (int j = 0; j < (int)(MICRO / 512); ++j) {
+            const uint32_t off = (uint32_t)j * 512u + lane * 16u;
+            uint4 q = __ldg(reinterpret_cast<const uint4*>(tb + off));
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            uint32_t m = nl_mask4(w[i]);
-            while (m) {
-                uint32_t byte = (__ffs(m) - 1) >> 3;
-                m &= m - 1;
-                cnt += valid_first(tb, off + i * 4 + byte + 1) ? 1u : 0u;
+            for (int i = 0; i < 4; ++i) {
+                uint32_t m = nl_mask4(w[i]);
+                while (m) {
+                    uint32_t byte = (__ffs(m) - 1) >> 3;
+                    m &= m - 1;
+                    const uint32_t qpos = off + i * 4 + byte + 1;
+                    if (base + qpos < n_bytes) {  // a line starts behind this newline (not in the padding)
+                        ++slots;
+                        cnt += valid_first(tb, qpos) ? 1u : 0u;
+                    }
+                }
             }
         }
+        if (mt == 0 && lane == 0 && n_bytes > 0) { ++slots; cnt += valid_first(tb, 0) ? 1u : 0u; }
     }
-    if (mt == 0 && lane == 0) cnt += valid_first(tb, 0) ? 1u : 0u;
     cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if (lane == 0) micro_count[mt] = cnt;
+    slots = __reduce_add_sync(0xffffffffu, slots);
+    if (lane == 0 && mt < n_micro) micro_count[mt] = cnt;
+    __shared__ uint32_t ws[8];
+    if (lane == 0) ws[threadIdx.x >> 5] = slots;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 8; ++i) t += ws[i];
+        if (t) atomicAdd(total_slots, (unsigned long long)t);
+    }
 }
 
 __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
@@ -406,8 +421,8 @@ __device__ __noinline__ void parse_record_global(const uint8_t* b, uint32_t p, u
     *out = r;
 }
 
-template <int MODE>
 __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a) {
+    constexpr int MODE = MODE_CLASSIFY;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t rows = a.rows_per_warp;             // 1..8 rows of 512 B per warp
@@ -422,7 +437,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t warp_tot[INGEST_THREADS / 32];
     __shared__ uint32_t bin_cnt[64];
-    __shared__ uint32_t inv_flag, inv_tot_s;
+    __shared__ uint32_t inv_flag, inv_tot_s, slot_base_s;
 
     const uint64_t t0 = (uint64_t)blockIdx.x * tile_bytes;
     const uint8_t* gtile = a.text + t0;
@@ -441,6 +456,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
     mbar_wait(&mbar, 0);
 
     const uint32_t wbase_byte = warp * rows * 512u;
+    const bool last_tile = t0 + tile_bytes + 1u >= a.n_bytes;
     const uint32_t rec_base = (MODE & MODE_CLASSIFY) ? (uint32_t)a.micro_base[(uint64_t)blockIdx.x * rows] : 0u;
     const uint32_t glim = (uint32_t)min((uint64_t)0xFFFF0000ull, a.padded_bytes - t0);
     const RangesView& R = a.ranges;
@@ -461,6 +477,11 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
                 if ((uint32_t)j < rows) {
                     const uint4 q = *reinterpret_cast<const uint4*>(stage + wbase_byte + (uint32_t)j * 512u + lane * 16u);
                     mm = (nl_mask4(q.x) >> 7) | (nl_mask4(q.y) >> 6) | (nl_mask4(q.z) >> 5) | (nl_mask4(q.w) >> 4);
+                    if (mm && last_tile) {  // a line start at or beyond the end of the text is padding, not a line
+                        const uint64_t off = t0 + wbase_byte + (uint32_t)j * 512u + lane * 16u + 1u;
+                        for (uint32_t pos = 0; pos < 16; ++pos)
+                            if (off + pos >= a.n_bytes) mm &= ~(1u << ((pos >> 2) + 8u * (pos & 3u)));
+                    }
                 }
                 mmv[j] = mm;
             }
@@ -546,6 +567,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
         // ---- order the round's records by line length (a proxy for the walk length: 4-byte bins) so that the
         // lanes of a warp carry walks of similar length; the lock-step node loops then idle much less
         if (tid < 64) bin_cnt[tid] = 0;
+        if (tid == 64) slot_base_s = atomicAdd(a.cursors + 0, n_round);  // this round's entries in the record table
         __syncthreads();
         for (uint32_t k = tid; k < n_round; k += INGEST_THREADS) {
             const uint32_t s0 = rec_start[k];
@@ -631,27 +653,93 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
                     }
                 }
             }
+            // ---- emit the record for k_apply: id hash, label, alignment interval and the walk as CSR node ids.
+            // Table entries follow the length-sorted thread order, so k_apply's warps also see similar walks.
             const bool labelled = has && label != LABEL_U;
             const bool eligible = labelled && !r.path_null && r.c7 != NULL_I64 && r.c8 != NULL_I64 && r.c9 != NULL_I64;  // profile.rs:380-399
-            if ((MODE & MODE_CLASSIFY) && labelled) ds_insert(a.ds, a.ds_shift, a.ds_mask, r.h, eligible, label, a.flags);
-            if (MODE & MODE_COVER) {
-                int64_t nb = -1;
-                bool keep = false;
-                if (eligible) {
-                    nb = R.node_base[label];
-                    keep = nb >= 0;
-                    if ((MODE & MODE_KEEPMASK) && keep) keep = ds_lookup(a.ds, a.ds_shift, a.ds_mask, r.h) != DS_MIXED;  // :415-416
+            const uint32_t wcnt = eligible ? r.W : 0u;
+            uint32_t x = wcnt;  // node slots: warp scan, one atomicAdd per warp on the chunk's node cursor
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= (uint32_t)d) x += y;
+            }
+            const uint32_t wtot = __shfl_sync(0xffffffffu, x, 31);
+            uint32_t nbase = 0;
+            if (lane == 0 && wtot) nbase = atomicAdd(a.cursors + 1, wtot);
+            nbase = __shfl_sync(0xffffffffu, nbase, 0);
+            const uint32_t node_off = nbase + x - wcnt;
+            if (slot) {
+                const uint32_t e = slot_base_s + k0 + tid;
+                uint32_t wf = wcnt & RM_W_MASK;
+                if (labelled) wf |= RM_LABELLED;
+                if (eligible) wf |= RM_ELIGIBLE;
+                if (r.monotone) wf |= RM_MONOTONE;
+                a.meta_b[e] = make_uint4(node_off, wf, label, labelled ? r.h.hi : 0u);
+                if (labelled) {
+                    a.hash_lo[e] = r.h.lo;
+                    if (eligible) a.meta_a[e] = make_longlong2(r.c8, r.c9);
                 }
-                const uint32_t cmask = __ballot_sync(0xffffffffu, keep);
-                if (keep) {
-                    DevSink sink{a};
-                    cover_record(b, r, label, R.start[label], nb, sink, cmask, stash + tid, INGEST_THREADS);
+            }
+            if (wcnt) {
+                uint32_t* dst = a.nodes + node_off;
+                if (r.stashed) {
+                    for (uint32_t i = 0; i < wcnt; ++i) dst[i] = stash[i * INGEST_THREADS + tid];
+                } else {  // walk longer than the stash: decode it again (long reads)
+                    WalkIter it{b, r.path_pos, r.path_end};
+                    int64_t m;
+                    for (uint32_t i = 0; i < wcnt; ++i) { it.next(m); dst[i] = (uint32_t)m; }
                 }
             }
             __syncwarp();
         }
         valid_prev += n_round - inv_total;
         __syncthreads();
+    }
+}
+
+// =====================================================================================
+// k_apply<MODE>: one thread per record-table entry written by k_ingest.  MODE_CLASSIFY: read-id set insert
+// (profile.rs:361-437).  MODE_COVER: node coverage / trio accumulation from the CSR walk (profile.rs:787-919),
+// MODE_KEEPMASK: skipping reads whose id group is DS_MIXED.  Small register state, no text: runs at high occupancy,
+// and it is also the replay pass (mixed id groups, graphs committed after the ingest) - no text is re-read.
+// =====================================================================================
+template <int MODE>
+__global__ void __launch_bounds__(256) k_apply(const IngestArgs a, uint32_t n_entries) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool has = e < n_entries;
+    uint4 mb = make_uint4(0u, 0u, LABEL_U, 0u);
+    if (has) mb = a.meta_b[e];
+    const bool labelled = has && (mb.y & RM_LABELLED);
+    const bool eligible = has && (mb.y & RM_ELIGIBLE);
+    const uint32_t label = mb.z;
+    IdHash h;
+    h.lo = 0;
+    h.hi = mb.w;
+    if (labelled && (MODE & (MODE_CLASSIFY | MODE_KEEPMASK))) h.lo = a.hash_lo[e];
+    if ((MODE & MODE_CLASSIFY) && labelled) ds_insert(a.ds, a.ds_shift, a.ds_mask, h, eligible, label, a.flags);
+    if (MODE & MODE_COVER) {
+        const RangesView& R = a.ranges;
+        int64_t nb = -1;
+        bool keep = false;
+        if (eligible) {
+            nb = R.node_base[label];
+            keep = nb >= 0;
+            if ((MODE & MODE_KEEPMASK) && keep) keep = ds_lookup(a.ds, a.ds_shift, a.ds_mask, h) != DS_MIXED;  // :415-416
+        }
+        const uint32_t cmask = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const longlong2 se = a.meta_a[e];
+            RecParse r;
+            r.W = mb.y & RM_W_MASK;
+            r.c8 = se.x;
+            r.c9 = se.y;
+            r.monotone = (mb.y & RM_MONOTONE) != 0;
+            r.stashed = true;
+            r.path_pos = r.path_end = 0;
+            DevSink sink{a};
+            cover_record(nullptr, r, label, R.start[label], nb, sink, cmask, a.nodes + mb.x, 1u);
+        }
     }
 }
 
@@ -1248,8 +1336,9 @@ static inline uint32_t grid_for(uint64_t n, uint32_t per_block, uint32_t cap = 1
     return (uint32_t)g;
 }
 
-void launch_count_records(const uint8_t* text, uint32_t n_micro, uint32_t* micro_count, cudaStream_t st) {
-    k_count_records<<<(n_micro + 7) / 8, 256, 0, st>>>(text, n_micro, micro_count);
+void launch_count_records(const uint8_t* text, uint64_t n_bytes, uint32_t n_micro, uint32_t* micro_count, unsigned long long* total_slots,
+                          cudaStream_t st) {
+    k_count_records<<<(n_micro + 7) / 8, 256, 0, st>>>(text, n_bytes, n_micro, micro_count, total_slots);
     PTX_LAUNCHED();
 }
 void launch_scan_tiles(const uint32_t* tile_count, uint32_t* tile_base, uint32_t n_tiles, uint64_t* total, cudaStream_t st) {
@@ -1257,26 +1346,28 @@ void launch_scan_tiles(const uint32_t* tile_count, uint32_t* tile_base, uint32_t
     PTX_LAUNCHED();
 }
 
-template <int MODE>
-static void launch_ingest_mode(const IngestArgs& a, cudaStream_t st) {
+void launch_ingest(const IngestArgs& a, cudaStream_t st) {
     const size_t smem_max = MAX_TILE + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 4 * REC_CAP * sizeof(uint16_t);
-    const size_t smem = (size_t)a.rows_per_warp * 4096 + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 4 * REC_CAP * sizeof(uint16_t);
+    const size_t smem = (size_t)a.rows_per_warp * MICRO + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 4 * REC_CAP * sizeof(uint16_t);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_ingest<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        cudaFuncSetAttribute(k_ingest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         configured = true;
     }
-    k_ingest<MODE><<<a.n_tiles, INGEST_THREADS, smem, st>>>(a);
+    k_ingest<<<a.n_tiles, INGEST_THREADS, smem, st>>>(a);
     PTX_LAUNCHED();
 }
-void launch_ingest(const IngestArgs& a, int mode, cudaStream_t st) {
+void launch_apply(const IngestArgs& a, uint32_t n_entries, int mode, cudaStream_t st) {
+    if (n_entries == 0) return;
+    const uint32_t grid = (n_entries + 255u) / 256u;
     switch (mode) {
-        case MODE_CLASSIFY: launch_ingest_mode<MODE_CLASSIFY>(a, st); break;
-        case MODE_CLASSIFY | MODE_COVER: launch_ingest_mode<MODE_CLASSIFY | MODE_COVER>(a, st); break;
-        case MODE_COVER: launch_ingest_mode<MODE_COVER>(a, st); break;
-        case MODE_COVER | MODE_KEEPMASK: launch_ingest_mode<MODE_COVER | MODE_KEEPMASK>(a, st); break;
-        default: break;
+        case MODE_CLASSIFY: k_apply<MODE_CLASSIFY><<<grid, 256, 0, st>>>(a, n_entries); break;
+        case MODE_CLASSIFY | MODE_COVER: k_apply<MODE_CLASSIFY | MODE_COVER><<<grid, 256, 0, st>>>(a, n_entries); break;
+        case MODE_COVER: k_apply<MODE_COVER><<<grid, 256, 0, st>>>(a, n_entries); break;
+        case MODE_COVER | MODE_KEEPMASK: k_apply<MODE_COVER | MODE_KEEPMASK><<<grid, 256, 0, st>>>(a, n_entries); break;
+        default: return;
     }
+    PTX_LAUNCHED();
 }
 void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2* new_slots, uint32_t new_shift, uint64_t new_mask,
                       cudaStream_t st) {
