@@ -272,14 +272,11 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.flags = ctx->d_flags;
     a.err = ctx->d_err;
     const GraphDev& g = ctx->g;
-    a.len = g.len;
-    a.bit_off = g.bit_off;
+    a.ninfo = g.ninfo;
     a.bases = g.bases;
-    a.full = g.full;
     a.bits = g.bits;
     a.tt = g.T > 0 ? g.tt : nullptr;
     a.tt_mask = g.tt_mask;
-    a.trio_mid = g.trio_mid;
     a.trio_bases = g.trio_bases;
     return a;
 }
@@ -422,7 +419,7 @@ int zero_coverage(ptx_ctx* ctx) {
     GraphDev& g = ctx->g;
     if (g.N <= 0) return PTX_OK;
     CU(cudaMemsetAsync(g.bases, 0, g.N * sizeof(unsigned long long), ctx->st));
-    CU(cudaMemsetAsync(g.full, 0, g.N, ctx->st));
+    launch_ninfo_full(g.ninfo, g.full, g.N, 1, ctx->st);
     CU(cudaMemsetAsync(g.bits, 0, g.n_bit_words * sizeof(uint32_t), ctx->st));
     if (g.T > 0) CU(cudaMemsetAsync(g.trio_bases, 0, g.T * sizeof(unsigned long long), ctx->st));
     CU(cudaMemsetAsync(ctx->d_err, 0, std::max<size_t>(ctx->sp.size(), 1) * sizeof(uint32_t), ctx->st));
@@ -431,10 +428,10 @@ int zero_coverage(ptx_ctx* ctx) {
 
 void free_graph(ptx_ctx* ctx) {
     GraphDev& g = ctx->g;
-    dfree(g.len); dfree(g.bit_off); dfree(g.bases); dfree(g.full); dfree(g.bits); dfree(g.cov);
+    dfree(g.len); dfree(g.bit_off); dfree(g.bases); dfree(g.full); dfree(g.ninfo); dfree(g.bits); dfree(g.cov);
     dfree(g.pnode); dfree(g.poff); dfree(g.path_len_sum); dfree(g.path_cov_sum);
     dfree(g.trio_key); dfree(g.trio_len); dfree(g.trio_owner); dfree(g.trio_bases); dfree(g.trio_start);
-    dfree(g.hap_nz); dfree(g.tt); dfree(g.trio_mid);
+    dfree(g.hap_nz); dfree(g.tt);
     g = GraphDev();
 }
 
@@ -744,10 +741,11 @@ int ptx_commit_graphs(ptx_ctx* ctx) {
         (rc = dalloc(ctx, &g.full, N)) || (rc = dalloc(ctx, &g.bits, g.n_bit_words)) || (rc = dalloc(ctx, &g.cov, N)) ||
         (rc = dalloc(ctx, &g.pnode, P, false)) || (rc = dalloc(ctx, &g.poff, Htot + 1, false)) || (rc = dalloc(ctx, &g.path_len_sum, Htot)) ||
         (rc = dalloc(ctx, &g.path_cov_sum, Htot)) || (rc = dalloc(ctx, &g.hap_nz, Htot)) || (rc = dalloc(ctx, &g.trio_start, Htot + 1)) ||
-        (rc = dalloc(ctx, &g.trio_mid, (N + 31) / 32)))
+        (rc = dalloc(ctx, &g.ninfo, N, false)))
         return rc;
     CU(cudaMemcpyAsync(g.len, len.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(g.bit_off, bit_off.data(), (N + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->st));
+    launch_ninfo_build(g.len, g.bit_off, g.ninfo, N, ctx->st);
     if (P) CU(cudaMemcpyAsync(g.pnode, pnode.data(), P * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(g.poff, poff.data(), (Htot + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(ctx->d_node_base, node_base.data(), S * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
@@ -822,7 +820,7 @@ int ptx_commit_graphs(ptx_ctx* ctx) {
             g.tt_mask = (uint32_t)(tcap - 1);
         }
         if (T > 0)
-            launch_trio_emit(g.pnode, g.poff, Htot, P, flag, scan, g.len, g.trio_key, g.trio_len, g.trio_owner, g.tt, g.tt_mask, g.trio_mid,
+            launch_trio_emit(g.pnode, g.poff, Htot, P, flag, scan, g.len, g.trio_key, g.trio_len, g.trio_owner, g.tt, g.tt_mask, g.ninfo,
                              g.trio_start, ctx->st);
         CU(cudaStreamSynchronize(ctx->st));
         CU(cudaGetLastError());
@@ -980,6 +978,7 @@ int ptx_finalize(ptx_ctx* ctx) {
             ch.covered = true;
         }
         tr.mark("final replay/cover");
+        launch_ninfo_full(g.ninfo, g.full, g.N, 0, ctx->st);
         if (ctx->comm) {
             // int64 sums and flag maxima are order-free: bit-exact for any shard count
             if (ctx->cov_reduced) return fail(ctx, PTX_E_STATE, "multi-GPU: coverage already reduced");

@@ -87,6 +87,14 @@ PTX_HD uint32_t trio_hash(uint32_t a, uint32_t b, uint32_t c) {
     return fmix32(h);
 }
 
+// One 16-byte gather per walk node: everything the coverage pass needs to know about a node.
+struct NodeInfo {
+    uint32_t len;      // node length in bases
+    uint32_t flags;    // NI_FULL: fully covered by some read; NI_TRIO_MID: middle node of at least one unique trio
+    uint64_t bit_off;  // first bit of the node in the packed covered-base bitmap
+};
+constexpr uint32_t NI_FULL = 1u, NI_TRIO_MID = 2u;
+
 struct RangesView {
     const int64_t* start;      // [S] 1-based inclusive, file order (species_range.txt)
     const int64_t* end;        // [S]
@@ -357,9 +365,10 @@ struct WalkIter {
 
 // profile.rs:787-919 for one coverage-eligible read of species `label`.
 // Sink concept:
-//   uint32_t len(uint32_t g);  void add_bases(uint32_t g, int64_t v);
-//   void set_bits(uint32_t g, int64_t lo, int64_t hi, uint32_t ln);   0 <= lo < hi <= ln
-//   void trio(uint32_t a, uint32_t b, uint32_t c, int64_t s);         global node indices, read order
+//   NodeInfo info(uint32_t g);  void add_bases(uint32_t g, int64_t v);
+//   void set_bits(uint32_t g, const NodeInfo& ni, int64_t lo, int64_t hi);   0 <= lo < hi <= ni.len
+//   void trio(uint32_t a, uint32_t b, uint32_t c, int64_t s);   global node indices in read order; only called
+//                                                               when b carries NI_TRIO_MID
 //   void error_start_gt_len(uint32_t label);
 // `mask`: lanes of the warp that call this together.  The walk is processed in three phases so that the lanes
 // execute the same code at the same time: the first node of every read, then the middle nodes in lock-step,
@@ -392,27 +401,30 @@ PTX_HD void cover_record(const uint8_t* b, const RecParse& r, uint32_t label, in
     bool ok = W >= 1;
     uint32_t gb = 0, ga = 0;
     int64_t rlb = 0, rla = 0, seen = 0;
+    bool mid_b = false;  // gb is the middle node of some unique trio
     if (ok) {
         int64_t m;
         if (stashed) m = (int64_t)stash[0];
         else it.next(m);
         const uint32_t g = (uint32_t)(node_base + (m - range_start));
-        const int64_t ln = (int64_t)sink.len(g);
+        const NodeInfo ni = sink.info(g);
+        const int64_t ln = (int64_t)ni.len;
         if (W == 1) {  // :811
             if (target >= 0) {              // :821-827 (target < 0: the read is skipped)
                 sink.add_bases(g, target);  // :829
-                if (ps >= 0 && ps < pe && pe <= ln) sink.set_bits(g, ps, pe, (uint32_t)ln);  // :832-835
+                if (ps >= 0 && ps < pe && pe <= ln) sink.set_bits(g, ni, ps, pe);  // :832-835
             }
         } else if (ps > ln) {  // :854 (a panic in the reference): flag the species, drop the read
             sink.error_start_gt_len(label);
             ok = false;
         } else {
-            const int64_t aln = ln - ps;                                    // :856
-            if (ps >= 0 && ln > ps) sink.set_bits(g, ps, ln, (uint32_t)ln);  // negative start wraps `as usize` -> empty
+            const int64_t aln = ln - ps;                      // :856
+            if (ps >= 0 && ln > ps) sink.set_bits(g, ni, ps, ln);  // negative start wraps `as usize` -> empty
             seen = aln;
             sink.add_bases(g, aln);  // :881 (position 0 is always a first occurrence)
             gb = g;
             rlb = aln;
+            mid_b = (ni.flags & NI_TRIO_MID) != 0;
         }
     }
     PTX_RECONVERGE(mask);
@@ -426,14 +438,16 @@ PTX_HD void cover_record(const uint8_t* b, const RecParse& r, uint32_t label, in
             if (stashed) m = (int64_t)stash[i * stash_stride];
             else it.next(m);
             const uint32_t g = (uint32_t)(node_base + (m - range_start));
-            const int64_t ln = (int64_t)sink.len(g);
-            sink.set_bits(g, 0, ln, (uint32_t)ln);
+            const NodeInfo ni = sink.info(g);
+            const int64_t ln = (int64_t)ni.len;
+            sink.set_bits(g, ni, 0, ln);
             seen += ln;  // :878
             int64_t rl;
-            if (first_occurrence(i, m, ln, ln, rl)) sink.add_bases(g, ln);  // :879-882
-            if (i >= 2) sink.trio(ga, gb, g, rla + rlb + rl);               // :890-906
+            if (first_occurrence(i, m, ln, ln, rl)) sink.add_bases(g, ln);     // :879-882
+            if (i >= 2 && mid_b) sink.trio(ga, gb, g, rla + rlb + rl);         // :890-906
             ga = gb; rla = rlb;
             gb = g;  rlb = rl;
+            mid_b = (ni.flags & NI_TRIO_MID) != 0;
         }
         PTX_RECONVERGE(mask);
     }
@@ -444,14 +458,15 @@ PTX_HD void cover_record(const uint8_t* b, const RecParse& r, uint32_t label, in
         if (stashed) m = (int64_t)stash[i * stash_stride];
         else it.next(m);
         const uint32_t g = (uint32_t)(node_base + (m - range_start));
-        const int64_t ln = (int64_t)sink.len(g);
+        const NodeInfo ni = sink.info(g);
+        const int64_t ln = (int64_t)ni.len;
         if (target < seen) target = seen;  // :858
         const int64_t aln = target - seen;
         const int64_t hi = aln < ln ? aln : ln;  // :871
-        if (hi > 0) sink.set_bits(g, 0, hi, (uint32_t)ln);
+        if (hi > 0) sink.set_bits(g, ni, 0, hi);
         int64_t rl;
         if (first_occurrence(i, m, ln, aln, rl)) sink.add_bases(g, aln);
-        if (W >= 3) sink.trio(ga, gb, g, rla + rlb + rl);
+        if (W >= 3 && mid_b) sink.trio(ga, gb, g, rla + rlb + rl);
     }
     PTX_RECONVERGE(mask);
 }

@@ -42,7 +42,8 @@ struct GraphDev {
     uint32_t* len = nullptr;          // [N]
     uint64_t* bit_off = nullptr;      // [N+1] exclusive prefix of len
     unsigned long long* bases = nullptr;  // [N] int64 accumulators
-    uint8_t* full = nullptr;          // [N] node fully covered by some read
+    uint4* ninfo = nullptr;           // [N] {len, flags (NI_FULL | NI_TRIO_MID), bit_off lo, hi}: the one gather of the coverage pass
+    uint8_t* full = nullptr;          // [N] NI_FULL extracted at finalize (staging for k_cov and the cross-rank max)
     uint32_t* bits = nullptr;         // [ceil(total_bits/32)+1] packed per-base covered bitmap
     uint64_t n_bit_words = 0;
     uint32_t* cov = nullptr;          // [N] covered bases (finalize)
@@ -62,7 +63,6 @@ struct GraphDev {
     unsigned long long* hap_nz = nullptr;  // [Htot]
     uint4* tt = nullptr;              // probe table {a,b,c,idx}, a == TT_EMPTY: empty
     uint32_t tt_mask = 0;
-    uint32_t* trio_mid = nullptr;     // [ceil(N/32)] bit g: g is the middle node of some unique trio
 };
 
 struct IngestArgs {
@@ -87,14 +87,11 @@ struct IngestArgs {
     uint32_t* flags;            // [0] dup id seen, [1] mixed-species id group seen
     uint32_t* err;              // [S] bit0: profile.rs:854 tripped
     // coverage
-    const uint32_t* len;
-    const uint64_t* bit_off;
+    uint4* ninfo;
     unsigned long long* bases;
-    uint8_t* full;
     uint32_t* bits;
     const uint4* tt;
     uint32_t tt_mask;
-    const uint32_t* trio_mid;
     unsigned long long* trio_bases;
 };
 
@@ -107,6 +104,8 @@ void launch_apply(const IngestArgs& a, uint32_t n_entries, int mode, cudaStream_
 void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2* new_slots, uint32_t new_shift,
                       uint64_t new_mask, cudaStream_t st);
 void launch_fill_u8(uint8_t* p, uint8_t v, uint64_t n, cudaStream_t st);
+void launch_ninfo_build(const uint32_t* len, const uint64_t* bit_off, uint4* ninfo, int64_t N, cudaStream_t st);
+void launch_ninfo_full(uint4* ninfo, uint8_t* full, int64_t N, int mode, cudaStream_t st);
 // cross-rank id groups (multi-GPU finalize)
 void launch_ds_owner_count(const ulonglong2* slots, uint64_t cap, uint32_t P, unsigned long long* cnt, cudaStream_t st);
 void launch_ds_owner_scatter(const ulonglong2* slots, uint64_t cap, uint32_t P, unsigned long long* cursor, ulonglong2* out, uint64_t box_cap,
@@ -129,7 +128,7 @@ void launch_trio_flag(const uint32_t* pnode, const uint64_t* poff, int64_t Htot,
 void launch_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* scratch, cudaStream_t st);
 void launch_trio_emit(const uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, const uint32_t* flag,
                       const uint64_t* scan, const uint32_t* len, uint32_t* trio_key, int64_t* trio_len,
-                      uint32_t* trio_owner, uint4* tt, uint32_t tt_mask, uint32_t* trio_mid, uint64_t* trio_start,
+                      uint32_t* trio_owner, uint4* tt, uint32_t tt_mask, uint4* ninfo, uint64_t* trio_start,
                       cudaStream_t st);
 
 // finalize

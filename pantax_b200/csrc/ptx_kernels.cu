@@ -376,15 +376,25 @@ __global__ void __launch_bounds__(256) k_ds_apply_mixed(const ulonglong2* __rest
 // =====================================================================================
 struct DevSink {
     const IngestArgs& a;
-    __device__ __forceinline__ uint32_t len(uint32_t g) const { return __ldg(a.len + g); }
+    // one 16-byte gather: {len, flags, bit_off}.  The flags word is updated by atomics while we read it with a
+    // plain load: a stale "not full" only costs a redundant atomicOr.
+    __device__ __forceinline__ NodeInfo info(uint32_t g) const {
+        uint4 w;
+        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(a.ninfo + g) : "memory");
+        NodeInfo ni;
+        ni.len = w.x;
+        ni.flags = w.y;
+        ni.bit_off = ((uint64_t)w.w << 32) | w.z;
+        return ni;
+    }
     __device__ __forceinline__ void add_bases(uint32_t g, int64_t v) { atomicAdd(a.bases + g, (unsigned long long)v); }
-    __device__ __forceinline__ void set_bits(uint32_t g, int64_t lo, int64_t hi, uint32_t ln) {
-        if (lo == 0 && hi == (int64_t)ln) {  // whole node: one idempotent byte store
-            a.full[g] = 1;
+    __device__ __forceinline__ void set_bits(uint32_t g, const NodeInfo& ni, int64_t lo, int64_t hi) {
+        if (lo == 0 && hi == (int64_t)ni.len) {  // whole node: one flag, set once
+            if (!(ni.flags & NI_FULL)) atomicOr(&a.ninfo[g].y, NI_FULL);
             return;
         }
-        const uint64_t base = __ldg(a.bit_off + g);
-        const uint64_t b0 = base + (uint64_t)lo, b1 = base + (uint64_t)hi - 1;  // inclusive last bit
+        if (ni.flags & NI_FULL) return;  // already fully covered: partial intervals add nothing
+        const uint64_t b0 = ni.bit_off + (uint64_t)lo, b1 = ni.bit_off + (uint64_t)hi - 1;  // inclusive last bit
         const uint64_t w0 = b0 >> 5, w1 = b1 >> 5;
         const uint32_t m0 = 0xFFFFFFFFu << (b0 & 31u), m1 = 0xFFFFFFFFu >> (31u - (uint32_t)(b1 & 31u));
         if (w0 == w1) {
@@ -397,8 +407,7 @@ struct DevSink {
     }
     __device__ __forceinline__ void trio(uint32_t x, uint32_t y, uint32_t z, int64_t s) {
         if (a.tt == nullptr) return;
-        if (!((__ldg(a.trio_mid + (y >> 5)) >> (y & 31u)) & 1u)) return;  // y is not the middle of any unique trio
-        const uint32_t lo = x < z ? x : z, hi = x < z ? z : x;            // profile.rs:672-678 / :902-904
+        const uint32_t lo = x < z ? x : z, hi = x < z ? z : x;  // profile.rs:672-678 / :902-904
         uint32_t i = trio_hash(lo, y, hi) & a.tt_mask;
         for (;;) {
             uint4 e = __ldg(a.tt + i);
@@ -958,7 +967,7 @@ __global__ void __launch_bounds__(256) k_trio_emit(const uint32_t* __restrict__ 
                                                    int64_t P, const uint32_t* __restrict__ flag, const uint64_t* __restrict__ scan,
                                                    const uint32_t* __restrict__ len, uint32_t* __restrict__ trio_key,
                                                    int64_t* __restrict__ trio_len, uint32_t* __restrict__ trio_owner, uint4* tt,
-                                                   uint32_t tt_mask, uint32_t* trio_mid, uint64_t* __restrict__ trio_start) {
+                                                   uint32_t tt_mask, uint4* ninfo, uint64_t* __restrict__ trio_start) {
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < (uint64_t)P; k += (uint64_t)gridDim.x * blockDim.x) {
         if (!flag[k]) continue;
         int64_t h;
@@ -970,7 +979,7 @@ __global__ void __launch_bounds__(256) k_trio_emit(const uint32_t* __restrict__ 
         trio_key[3 * t + 2] = hi;
         trio_len[t] = (int64_t)len[lo] + (int64_t)len[mid] + (int64_t)len[hi];  // profile.rs:712
         trio_owner[t] = (uint32_t)h;
-        atomicOr(trio_mid + (mid >> 5), 1u << (mid & 31u));
+        atomicOr(&ninfo[mid].y, NI_TRIO_MID);
         // unique keys: plain claim of an empty slot, then publish idx
         uint32_t i = trio_hash(lo, mid, hi) & tt_mask;
         const ulonglong2 empty = make_ulonglong2(0xFFFFFFFFFFFFFFFFull, 0xFFFFFFFFFFFFFFFFull);
@@ -1033,6 +1042,18 @@ __global__ void __launch_bounds__(256) k_depth(const unsigned long long* __restr
 
 __global__ void __launch_bounds__(256) k_or_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] |= src[i];
+}
+
+__global__ void __launch_bounds__(256) k_ninfo_build(const uint32_t* __restrict__ len, const uint64_t* __restrict__ bit_off, uint4* __restrict__ ninfo, int64_t N) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < N) ninfo[g] = make_uint4(len[g], 0u, (uint32_t)bit_off[g], (uint32_t)(bit_off[g] >> 32));
+}
+// mode 0: full[g] = NI_FULL flag of ninfo (finalize / cross-rank max-reduce staging); mode 1: clear the flag (reset)
+__global__ void __launch_bounds__(256) k_ninfo_full(uint4* ninfo, uint8_t* __restrict__ full, int64_t N, int mode) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    if (mode == 0) full[g] = (uint8_t)(ninfo[g].y & NI_FULL);
+    else ninfo[g].y &= ~NI_FULL;
 }
 
 __global__ void __launch_bounds__(256) k_fill_u8(uint8_t* p, uint8_t v, uint64_t n) {
@@ -1428,6 +1449,16 @@ void launch_flt_compact(const uint32_t* sel, const uint64_t* scan, const uint64_
     k_flt_compact<<<(uint32_t)((n_lines + 255) / 256), 256, 0, st>>>(sel, scan, line_off, n_lines, out, cap);
     PTX_LAUNCHED();
 }
+void launch_ninfo_build(const uint32_t* len, const uint64_t* bit_off, uint4* ninfo, int64_t N, cudaStream_t st) {
+    if (N <= 0) return;
+    k_ninfo_build<<<(uint32_t)((N + 255) / 256), 256, 0, st>>>(len, bit_off, ninfo, N);
+    PTX_LAUNCHED();
+}
+void launch_ninfo_full(uint4* ninfo, uint8_t* full, int64_t N, int mode, cudaStream_t st) {
+    if (N <= 0) return;
+    k_ninfo_full<<<(uint32_t)((N + 255) / 256), 256, 0, st>>>(ninfo, full, N, mode);
+    PTX_LAUNCHED();
+}
 void launch_fill_u8(uint8_t* p, uint8_t v, uint64_t n, cudaStream_t st) {
     k_fill_u8<<<grid_for(n, 256 * 16), 256, 0, st>>>(p, v, n);
     PTX_LAUNCHED();
@@ -1466,9 +1497,9 @@ void launch_scan_u32(const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* sc
 }
 void launch_trio_emit(const uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, const uint32_t* flag, const uint64_t* scan,
                       const uint32_t* len, uint32_t* trio_key, int64_t* trio_len, uint32_t* trio_owner, uint4* tt, uint32_t tt_mask,
-                      uint32_t* trio_mid, uint64_t* trio_start, cudaStream_t st) {
+                      uint4* ninfo, uint64_t* trio_start, cudaStream_t st) {
     k_trio_emit<<<grid_for(std::max<int64_t>(P, Htot + 1), 256), 256, 0, st>>>(pnode, poff, Htot, P, flag, scan, len, trio_key, trio_len,
-                                                                               trio_owner, tt, tt_mask, trio_mid, trio_start);
+                                                                               trio_owner, tt, tt_mask, ninfo, trio_start);
     PTX_LAUNCHED();
 }
 void launch_cov(const GraphDev& g, cudaStream_t st) {

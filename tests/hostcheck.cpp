@@ -22,10 +22,10 @@ struct HostSink {
     const std::map<std::tuple<uint32_t, uint32_t, uint32_t>, uint32_t>* tmap;
     int64_t* trio_bases;
     uint32_t* err;
-    uint32_t len(uint32_t g) const { return len_[g]; }
+    NodeInfo info(uint32_t g) const { return NodeInfo{len_[g], NI_TRIO_MID, bit_off[g]}; }
     void add_bases(uint32_t g, int64_t v) { bases[g] += v; }
-    void set_bits(uint32_t g, int64_t lo, int64_t hi, uint32_t) {
-        for (int64_t j = lo; j < hi; ++j) bytes[bit_off[g] + j] = 1;
+    void set_bits(uint32_t, const NodeInfo& ni, int64_t lo, int64_t hi) {
+        for (int64_t j = lo; j < hi; ++j) bytes[ni.bit_off + j] = 1;
     }
     void trio(uint32_t x, uint32_t y, uint32_t z, int64_t s) {
         uint32_t lo = x < z ? x : z, hi = x < z ? z : x;
