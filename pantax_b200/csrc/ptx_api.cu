@@ -623,6 +623,8 @@ int ptx_set_ranges(ptx_ctx* ctx, int S, const char* const* taxid, const int64_t*
     if (!ctx || S <= 0 || !taxid || !start || !end) return fail(ctx, PTX_E_INVALID, "ptx_set_ranges: bad arguments");
     if (!ctx->chunks.empty() || ctx->graphs_committed) return fail(ctx, PTX_E_STATE, "ranges must be set before graphs and GAF");
     cudaSetDevice(ctx->device);
+    for (int s = 0; s < S; ++s)  // node ids are u32 in the reference too (profile.rs:547-551 SpeciesRange{start: u32, end: u32})
+        if (end[s] > 0xFFFFFFFFll || start[s] < 0) return fail(ctx, PTX_E_UNSUPPORTED, "species range beyond 32-bit node ids");
     ctx->sp.assign(S, SpeciesHost());
     std::vector<uint32_t> order(S);
     for (int s = 0; s < S; ++s) {

@@ -224,6 +224,28 @@ PTX_HD int parse_int_field(const uint8_t* b, uint32_t& p, int64_t& out) {
     return skip_field(b, p);  // junk in an integer column -> null
 }
 
+// Iterates the digit runs (<= 18 digits) of b[p,end).
+struct WalkIter {
+    const uint8_t* b;
+    uint32_t p, end;
+    PTX_HD bool next(int64_t& m) {
+        for (;;) {
+            while (p < end && ((uint32_t)b[p] - (uint32_t)'0') > 9u) ++p;
+            if (p >= end) return false;
+            uint64_t v = 0;
+            uint32_t nd = 0;
+            while (p < end) {
+                uint32_t d = (uint32_t)b[p] - (uint32_t)'0';
+                if (d > 9u) break;
+                v = v * 10u + d;
+                ++nd;
+                ++p;
+            }
+            if (nd <= 18) { m = (int64_t)v; return true; }
+        }
+    }
+};
+
 // Parses columns 1..12 of the line starting at b[p].  Returns false if the columns do not end inside
 // the window b[0, lim) - the caller retries on the global-memory copy of the line.
 // `stash` (may be null): node ids of the walk are saved at stash[i * stash_stride], i < stash_cap.
@@ -262,10 +284,12 @@ PTX_HD bool parse_record(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r
     if (st == T_TAB) st = skip_fields(b, p, 3);  // columns 3,4,5
     PTX_RECONVERGE(mask);
     {  // column 6: walk.  The lanes of the warp advance one NODE per iteration, in lock-step.
+        // Node ids of up to 9 digits (< 2^32; the reference's own species ranges are u32, profile.rs:547-551)
+        // are tracked in 32-bit arithmetic; a longer run switches the column to the generic 64-bit scan below.
         const bool had6 = (st == T_TAB);
         bool done = !had6;
-        bool inc = true, dec = true, fits = (stash != nullptr);
-        int64_t prev = 0;
+        bool inc = true, dec = true, fits = (stash != nullptr), big = false;
+        uint32_t prev32 = 0, vmin32 = 0xFFFFFFFFu, vmax32 = 0;
         if (had6) r.path_pos = p;
         for (;;) {
             if (!done) {
@@ -289,32 +313,48 @@ PTX_HD bool parse_record(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r
                         c = b[++p];
                         d = (uint32_t)c - (uint32_t)'0';
                     }
-                    uint64_t v = v32;
-                    while (d <= 9u) {  // ids of 10+ digits: rare
-                        v = v * 10u + d;
-                        ++nd;
-                        c = b[++p];
-                        d = (uint32_t)c - (uint32_t)'0';
+                    if (d <= 9u) {  // 10+ digits: rare
+                        big = true;
+                        while (d <= 9u) { c = b[++p]; d = (uint32_t)c - (uint32_t)'0'; }
                     }
-                    if (nd <= 18) {  // longer runs are dropped (rcls.rs:244 parse().ok())
-                        const int64_t m = (int64_t)v;
-                        if (r.W) {
-                            if (m <= prev) inc = false;
-                            if (m >= prev) dec = false;
-                        }
-                        prev = m;
-                        if (m < r.vmin) r.vmin = m;
-                        if (m > r.vmax) r.vmax = m;
-                        if (fits && r.W < stash_cap && v <= 0xFFFFFFFFull) stash[r.W * stash_stride] = (uint32_t)v;
-                        else fits = false;
-                        ++r.W;
+                    if (r.W) {
+                        if (v32 <= prev32) inc = false;
+                        if (v32 >= prev32) dec = false;
                     }
+                    prev32 = v32;
+                    vmin32 = v32 < vmin32 ? v32 : vmin32;
+                    vmax32 = v32 > vmax32 ? v32 : vmax32;
+                    if (fits && r.W < stash_cap) stash[r.W * stash_stride] = v32;
+                    else fits = false;
+                    ++r.W;
                 }
             }
             if (PTX_WARP_ALL(mask, done)) break;
         }
         if (had6) {
             r.path_end = p;
+            if (big) {  // generic scan: ids up to 18 digits, longer runs dropped (rcls.rs:244 parse().ok())
+                WalkIter it{b, r.path_pos, r.path_end};
+                int64_t m, prev = 0;
+                r.W = 0;
+                inc = dec = true;
+                fits = (stash != nullptr);
+                while (it.next(m)) {
+                    if (r.W) {
+                        if (m <= prev) inc = false;
+                        if (m >= prev) dec = false;
+                    }
+                    prev = m;
+                    if (m < r.vmin) r.vmin = m;
+                    if (m > r.vmax) r.vmax = m;
+                    if (fits && r.W < stash_cap && m <= 0xFFFFFFFFll) stash[r.W * stash_stride] = (uint32_t)m;
+                    else fits = false;
+                    ++r.W;
+                }
+            } else if (r.W) {
+                r.vmin = (int64_t)vmin32;
+                r.vmax = (int64_t)vmax32;
+            }
             r.monotone = inc || dec;
             r.stashed = fits;
             r.path_null = (r.path_end - r.path_pos == 1u) && (b[r.path_pos] == '*');
@@ -340,28 +380,6 @@ PTX_HD bool parse_record(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r
 #undef PTX_CHECK_WINDOW
     return p + 1u < lim;
 }
-
-// Iterates the digit runs (<= 18 digits) of b[p,end).
-struct WalkIter {
-    const uint8_t* b;
-    uint32_t p, end;
-    PTX_HD bool next(int64_t& m) {
-        for (;;) {
-            while (p < end && ((uint32_t)b[p] - (uint32_t)'0') > 9u) ++p;
-            if (p >= end) return false;
-            uint64_t v = 0;
-            uint32_t nd = 0;
-            while (p < end) {
-                uint32_t d = (uint32_t)b[p] - (uint32_t)'0';
-                if (d > 9u) break;
-                v = v * 10u + d;
-                ++nd;
-                ++p;
-            }
-            if (nd <= 18) { m = (int64_t)v; return true; }
-        }
-    }
-};
 
 // profile.rs:787-919 for one coverage-eligible read of species `label`.
 // Sink concept:
