@@ -100,22 +100,21 @@ __global__ void __launch_bounds__(256) k_count_records(const uint8_t* __restrict
     if (mt < n_micro) {
         const uint8_t* tb = text + (uint64_t)mt * MICRO;
         const uint64_t base = (uint64_t)mt * MICRO;
+        constexpr int NJ = (int)(MICRO / 512);
+        uint4 q[NJ];
 #pragma unroll
-        for (int j = 0; j < (int)(MICRO / 512); ++j) {
-            const uint32_t off = (uint32_t)j * 512u + lane * 16u;
-            uint4 q = __ldg(reinterpret_cast<const uint4*>(tb + off));
-            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        for (int j = 0; j < NJ; ++j) q[j] = __ldg(reinterpret_cast<const uint4*>(tb + (uint32_t)j * 512u + lane * 16u));  // all loads in flight
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                uint32_t m = nl_mask4(w[i]);
-                while (m) {
-                    uint32_t byte = (__ffs(m) - 1) >> 3;
-                    m &= m - 1;
-                    const uint32_t qpos = off + i * 4 + byte + 1;
-                    if (base + qpos < n_bytes) {  // a line starts behind this newline (not in the padding)
-                        ++slots;
-                        cnt += valid_first(tb, qpos) ? 1u : 0u;
-                    }
+        for (int j = 0; j < NJ; ++j) {
+            uint32_t mm = (nl_mask4(q[j].x) >> 7) | (nl_mask4(q[j].y) >> 6) | (nl_mask4(q[j].z) >> 5) | (nl_mask4(q[j].w) >> 4);
+            const uint32_t off = (uint32_t)j * 512u + lane * 16u + 1u;
+            while (mm) {  // rare: one newline per ~7 pieces
+                const uint32_t bit = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const uint32_t qpos = off + ((bit & 7u) << 2) + (bit >> 3);
+                if (base + qpos < n_bytes) {  // a line starts behind this newline (not in the padding)
+                    ++slots;
+                    cnt += valid_first(tb, qpos) ? 1u : 0u;
                 }
             }
         }

@@ -297,3 +297,34 @@ def test_gpu_full_size_config2_bit_exact_and_chunk_invariant():
         np.testing.assert_array_equal(ctx.species_counts(), o.species_counts())
     finally:
         synth.lib().synth_free(buf)
+
+
+def test_gpu_config3_shape_hifi_reads_on_100_species():
+    """BASELINE configs[2] shape, scaled: 100 species, 1 M nodes (mean node ~300 bp), HiFi reads (mean 15 kb,
+    ~45-node walks, lines of ~400 B that often cross tile boundaries), secondary alignments (duplicate ids)."""
+    from gpu_common import gpu_vs_oracle
+    rng = np.random.default_rng(3)
+    n_sp = 100
+    nodes = rng.integers(5000, 15000, size=n_sp).tolist()
+    haps = rng.integers(1, 8, size=n_sp).tolist()
+    ds = synth.Dataset(20261017 + 3, nodes, haps, backbone_mean=400)
+    gaf = ds.gaf(20261017 + 3, 0, 60000, synth.GafParams(long_reads=True, id_pair_suffix=False, p_secondary=0.05))
+    ctx, o = gpu_vs_oracle(ds.ranges(), dataset_graphs(ds), gaf)
+    assert not ctx.ids_unique
+
+
+def test_gpu_config4_shape_short_reads_on_1000_species():
+    """BASELINE configs[3] shape, scaled: 1,000 species (binary-search classification), 2 M nodes, 1 M short reads,
+    graphs uploaded only for a third of the species (the rest is classified and counted but not covered)."""
+    from gpu_common import gpu_vs_oracle
+    rng = np.random.default_rng(4)
+    n_sp = 1000
+    nodes = rng.integers(500, 3500, size=n_sp).tolist()
+    haps = rng.integers(1, 6, size=n_sp).tolist()
+    ds = synth.Dataset(20261017 + 4, nodes, haps)
+    gaf = ds.gaf(20261017 + 4, 0, 1_000_000, NASTY)
+    graphs = dataset_graphs(ds)
+    for s in range(n_sp):
+        if s % 3:
+            graphs[s] = None
+    gpu_vs_oracle(ds.ranges(), graphs, gaf)
