@@ -127,7 +127,7 @@ struct ptx_ctx {
     std::vector<uint8_t> carry;
     int64_t total_records = 0;
     bool dirty = false;          // something ingested / committed since the last finalize
-    uint32_t h_flags[2] = {0, 0};
+    uint32_t h_flags[4] = {0, 0, 0, 0};  // [0] repeated id, [1] mixed-species id group, [2] exchange box overflow
     std::vector<uint32_t> h_err;
     // reuse: chunk buffers released by ptx_reset, and one grow-only scratch arena for ptx_finalize
     std::vector<Chunk> pool;
@@ -135,6 +135,12 @@ struct ptx_ctx {
     size_t scratch_cap = 0, scratch_off = 0;
     uint8_t* scratch2 = nullptr;
     size_t scratch2_cap = 0;
+    // asynchronous id-group exchange (multi-GPU): boxes filled by k_apply, sent on a side stream during the coverage pass
+    cudaStream_t xs = nullptr;
+    cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;
+    ulonglong2 *outbox = nullptr, *inbox = nullptr, *x_own = nullptr;
+    unsigned long long* out_cursor = nullptr;
+    uint64_t box_cap = 0, x_own_cap = 0;
     uint64_t xchg_box_cap = 0;  // per-owner outbox capacity of the id-group exchange (sticky)
     // timing
     std::vector<EvPair> ev_count, ev_ingest, ev_apply, ev_final;
@@ -264,6 +270,10 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.hash_lo = ch.hash_lo;
     a.nodes = ch.nodes;
     a.cursors = reinterpret_cast<uint32_t*>(ch.cursors + 1);
+    a.outbox = ctx->comm ? ctx->outbox : nullptr;
+    a.out_cursor = ctx->out_cursor;
+    a.box_cap = ctx->box_cap;
+    a.n_ranks = (uint32_t)ctx->n_ranks;
     a.ranges = ranges_view(ctx);
     a.hist = ctx->d_hist;
     a.ds = ctx->d_ds;
@@ -338,6 +348,8 @@ void chunk_free(Chunk& ch) {
     ch.copied = nullptr;
 }
 
+int xchg_ensure(ptx_ctx* ctx, int64_t records);
+
 // classify (+ optimistic coverage) pass over one chunk whose text is resident
 int chunk_process(ptx_ctx* ctx, Chunk& ch) {
     if (ctx->cov_reduced) return fail(ctx, PTX_E_STATE, "multi-GPU: coverage already reduced by ptx_finalize; ptx_reset before ingesting more");
@@ -399,8 +411,13 @@ int chunk_process(ptx_ctx* ctx, Chunk& ch) {
     int rc = ds_ensure(ctx, ch.n_records);
     if (rc) return rc;
     ctx->ds_records += ch.n_records;
+    if (ctx->comm) {
+        rc = xchg_ensure(ctx, std::max<int64_t>(ctx->ds_records, ctx->reserve_records));
+        if (rc) return rc;
+    }
     IngestArgs a = make_args(ctx, ch);
-    const bool cover = ctx->graphs_committed && ctx->g.N > 0;
+    // multi-GPU: the coverage pass is deferred to ptx_finalize, where it overlaps the id-group exchange
+    const bool cover = ctx->graphs_committed && ctx->g.N > 0 && !ctx->comm;
     ev_begin(ctx, ctx->ev_ingest);
     launch_ingest(a, ctx->st);
     ev_end(ctx, ctx->ev_ingest);
@@ -457,6 +474,104 @@ int nccl_check(ptx_ctx* ctx, int r, const char* what) {
     return fail(ctx, PTX_E_NCCL, "%s failed: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
 }
 
+
+// multi-GPU: make the per-owner boxes large enough for `records` labelled records on this rank (uniform hash:
+// records/P each, 25 % slack; k_apply flags an overflow and ptx_finalize then falls back to the table scan)
+int xchg_ensure(ptx_ctx* ctx, int64_t records) {
+    const uint64_t P = (uint64_t)ctx->n_ranks;
+    const uint64_t need = (uint64_t)records / P + (uint64_t)records / (4 * P) + 4096;
+    if (!ctx->xs) {
+        CU(cudaStreamCreateWithFlags(&ctx->xs, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->ev_x0, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_x1, cudaEventDisableTiming));
+        int rc = dalloc(ctx, &ctx->out_cursor, 64);
+        if (rc) return rc;
+    }
+    if (need <= ctx->box_cap) return PTX_OK;
+    const uint64_t cap = need + need / 8;
+    ulonglong2 *nout = nullptr, *nin = nullptr, *nown = nullptr;
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaStreamSynchronize(ctx->xs));
+    CU(cudaMalloc((void**)&nout, P * cap * sizeof(ulonglong2)));
+    CU(cudaMalloc((void**)&nin, P * cap * sizeof(ulonglong2)));
+    const uint64_t ocap = 1ull << std::max<uint32_t>(10, log2_ceil(P * cap + P * cap / 2));
+    CU(cudaMalloc((void**)&nown, ocap * sizeof(ulonglong2)));
+    if (ctx->outbox)  // keep what earlier chunks already wrote
+        for (uint64_t r = 0; r < P; ++r)
+            CU(cudaMemcpyAsync(nout + r * cap, ctx->outbox + r * ctx->box_cap, ctx->box_cap * sizeof(ulonglong2), cudaMemcpyDeviceToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    dfree(ctx->outbox); dfree(ctx->inbox); dfree(ctx->x_own);
+    ctx->outbox = nout; ctx->inbox = nin; ctx->x_own = nown;
+    ctx->box_cap = cap;
+    ctx->x_own_cap = ocap;
+    return PTX_OK;
+}
+
+// ids whose merged state on their owner rank is DS_MIXED go back to every rank (rare path; synchronising)
+int return_mixed_ids(ptx_ctx* ctx, const ulonglong2* own, uint64_t ocap, cudaStream_t st) {
+    const int P = ctx->n_ranks;
+    int rc;
+    unsigned long long* d_tmp = nullptr;
+    if ((rc = dalloc(ctx, &d_tmp, (size_t)P + 2))) return rc;
+    unsigned long long* d_nmix = d_tmp;
+    unsigned long long* d_allmix = d_tmp + 1;
+    launch_ds_collect_mixed(own, ocap, d_nmix, nullptr, 0, st);
+    if ((rc = nccl_check(ctx, g_nccl.AllGather(d_nmix, d_allmix, 1, ncclUint64, ctx->comm, st), "ncclAllGather(mixed counts)"))) return rc;
+    std::vector<unsigned long long> nmix(P);
+    CU(cudaMemcpyAsync(nmix.data(), d_allmix, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    unsigned long long mx = 0;
+    for (auto v : nmix) mx = std::max(mx, v);
+    if (mx > 0) {
+        ulonglong2* mine = nullptr;
+        ulonglong2* everyone = nullptr;
+        if ((rc = dalloc(ctx, &mine, (size_t)mx)) || (rc = dalloc(ctx, &everyone, (size_t)mx * P))) return rc;
+        CU(cudaMemsetAsync(d_nmix, 0, sizeof(unsigned long long), st));
+        launch_ds_collect_mixed(own, ocap, d_nmix, mine, mx, st);
+        if ((rc = nccl_check(ctx, g_nccl.AllGather(mine, everyone, mx * 2, ncclUint64, ctx->comm, st), "ncclAllGather(mixed ids)"))) return rc;
+        launch_ds_apply_mixed(everyone, mx * P, ctx->d_ds, 64 - log2_ceil(ctx->ds_cap), ctx->ds_cap - 1, st);
+        CU(cudaStreamSynchronize(st));
+        cudaFree(mine);
+        cudaFree(everyone);
+    }
+    CU(cudaStreamSynchronize(st));
+    cudaFree(d_tmp);
+    return PTX_OK;
+}
+
+// Asynchronous form of the exchange: every box is sent whole (its header carries the entry count, so no size
+// has to travel through the host), merged on the owner and the flags max-reduced - all on the side stream `xs`,
+// while the main stream runs the coverage pass.  ptx_finalize joins on ev_x1.
+int exchange_fast_begin(ptx_ctx* ctx) {
+    const int P = ctx->n_ranks;
+    int rc;
+    launch_box_headers(ctx->outbox, ctx->out_cursor, ctx->box_cap, (uint32_t)P, ctx->d_flags, ctx->st);
+    // all ranks send the same number of entries per box: the fullest box anywhere (one 8-byte max-reduce + readback)
+    if ((rc = nccl_check(ctx, g_nccl.AllReduce(ctx->out_cursor + P, ctx->out_cursor + P, 1, ncclUint64, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(box size)"))) return rc;
+    unsigned long long send_n = 0;
+    CU(cudaMemcpyAsync(&send_n, ctx->out_cursor + P, sizeof send_n, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    if (send_n > ctx->box_cap) {  // a peer has more ids than this rank planned for: grow the boxes (contents are kept)
+        if ((rc = xchg_ensure(ctx, (int64_t)(send_n * (uint64_t)P)))) return rc;
+    }
+    CU(cudaEventRecord(ctx->ev_x0, ctx->st));
+    CU(cudaStreamWaitEvent(ctx->xs, ctx->ev_x0, 0));
+    cudaStream_t xs = ctx->xs;
+    CU(cudaMemsetAsync(ctx->x_own, 0, ctx->x_own_cap * sizeof(ulonglong2), xs));
+    g_nccl.GroupStart();
+    for (int r = 0; r < P; ++r) {
+        if (r == ctx->rank) continue;
+        g_nccl.Send(ctx->outbox + (uint64_t)r * ctx->box_cap, send_n * 2, ncclUint64, r, ctx->comm, xs);
+        g_nccl.Recv(ctx->inbox + (uint64_t)r * ctx->box_cap, send_n * 2, ncclUint64, r, ctx->comm, xs);
+    }
+    if ((rc = nccl_check(ctx, g_nccl.GroupEnd(), "ncclSend/Recv(id boxes)"))) return rc;
+    CU(cudaMemcpyAsync(ctx->inbox + (uint64_t)ctx->rank * ctx->box_cap, ctx->outbox + (uint64_t)ctx->rank * ctx->box_cap,
+                       send_n * sizeof(ulonglong2), cudaMemcpyDeviceToDevice, xs));
+    launch_ds_merge_boxes(ctx->inbox, (uint32_t)P, ctx->box_cap, ctx->x_own, 64 - log2_ceil(ctx->x_own_cap), ctx->x_own_cap - 1, ctx->d_flags, xs);
+    if ((rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 4, ncclUint32, ncclMax, ctx->comm, xs), "ncclAllReduce(flags)"))) return rc;
+    CU(cudaEventRecord(ctx->ev_x1, xs));
+    return PTX_OK;
+}
 
 // profile.rs:369-378 / 406-437 across ranks: route every id-set entry to the rank owning its hash, merge the
 // per-rank states there, and tell every rank which ids ended up DS_MIXED.  Sets d_flags[0/1] on the ranks
@@ -586,12 +701,12 @@ int ptx_create(int device, ptx_ctx** out) {
         delete ctx;
         return PTX_E_CUDA;
     }
-    if (cudaMalloc((void**)&ctx->d_flags, 2 * sizeof(uint32_t)) != cudaSuccess ||
+    if (cudaMalloc((void**)&ctx->d_flags, 4 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_total, sizeof(uint64_t)) != cudaSuccess) {
         delete ctx;
         return PTX_E_NOMEM;
     }
-    cudaMemsetAsync(ctx->d_flags, 0, 2 * sizeof(uint32_t), ctx->st);
+    cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(uint32_t), ctx->st);
     *out = ctx;
     return PTX_OK;
 }
@@ -604,6 +719,10 @@ void ptx_destroy(ptx_ctx* ctx) {
     for (auto& ch : ctx->pool) chunk_free(ch);
     dfree(ctx->scratch);
     dfree(ctx->scratch2);
+    dfree(ctx->outbox); dfree(ctx->inbox); dfree(ctx->x_own); dfree(ctx->out_cursor);
+    if (ctx->xs) cudaStreamDestroy(ctx->xs);
+    if (ctx->ev_x0) cudaEventDestroy(ctx->ev_x0);
+    if (ctx->ev_x1) cudaEventDestroy(ctx->ev_x1);
     free_graph(ctx);
     dfree(ctx->d_rstart); dfree(ctx->d_rend); dfree(ctx->d_node_base); dfree(ctx->d_order);
     dfree(ctx->d_hist); dfree(ctx->d_hist_g); dfree(ctx->d_flags); dfree(ctx->d_err); dfree(ctx->d_ds); dfree(ctx->d_total);
@@ -953,18 +1072,31 @@ int ptx_finalize(ptx_ctx* ctx) {
     const int S = (int)ctx->sp.size();
     ev_begin(ctx, ctx->ev_final);
     Trace tr(ctx->st);
-    if (ctx->comm) {  // id groups may span ranks; a mixed id group / error seen on any rank is seen by all
-        int rc = exchange_id_groups(ctx);  // also max-reduces the flags
+    bool mixed = false;
+    if (ctx->comm) {
+        // id groups may span ranks: the boxes k_apply filled travel on the side stream while the coverage runs here
+        int rc = xchg_ensure(ctx, std::max<int64_t>(ctx->ds_records, ctx->reserve_records));
         if (rc) return rc;
+        if ((rc = exchange_fast_begin(ctx))) return rc;
+        tr.mark("final exchange issued");
+    } else {
+        CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        mixed = ctx->h_flags[1] != 0;
+        tr.mark("final flags");
     }
-    CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
-    const bool mixed = ctx->h_flags[1] != 0;
-    tr.mark("final id groups + flags");
     if (ctx->graphs_committed && g.N > 0) {
-        if (mixed) {
+        auto cover_pending = [&](bool keepmask) {
+            for (auto& ch : ctx->chunks) {
+                if (!ch.ingested || ch.covered || ch.n_tiles == 0) continue;
+                IngestArgs a = make_args(ctx, ch);
+                launch_apply(a, (uint32_t)ch.n_slots, MODE_COVER | (keepmask ? MODE_KEEPMASK : 0), ctx->st);  // from the record table: no text is re-read
+                ch.covered = true;
+            }
+        };
+        auto start_over = [&]() -> int {
             // profile.rs:406-437: some id group spans species -> its reads must not contribute.  The optimistic
-            // pass counted them: start over and replay the retained text with the keep mask.
+            // pass counted them: zero the accumulators and replay the record table with the keep mask.
             bool any_optimistic = false;
             for (auto& ch : ctx->chunks) any_optimistic |= (ch.ingested && ch.covered);
             if (any_optimistic) {
@@ -972,12 +1104,29 @@ int ptx_finalize(ptx_ctx* ctx) {
                 if (rc) return rc;
                 for (auto& ch : ctx->chunks) ch.covered = false;
             }
-        }
-        for (auto& ch : ctx->chunks) {
-            if (!ch.ingested || ch.covered || ch.n_tiles == 0) continue;
-            IngestArgs a = make_args(ctx, ch);
-            launch_apply(a, (uint32_t)ch.n_slots, MODE_COVER | (mixed ? MODE_KEEPMASK : 0), ctx->st);  // from the record table: no text is re-read
-            ch.covered = true;
+            return PTX_OK;
+        };
+        if (mixed) { int rc = start_over(); if (rc) return rc; }
+        cover_pending(mixed);
+        if (ctx->comm) {
+            CU(cudaStreamWaitEvent(ctx->st, ctx->ev_x1, 0));
+            CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));
+            CU(cudaStreamSynchronize(ctx->st));
+            if (ctx->h_flags[2]) {  // a box overflowed: exact but slower exchange from the id set itself
+                int rc = exchange_id_groups(ctx);
+                if (rc) return rc;
+                CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));
+                CU(cudaStreamSynchronize(ctx->st));
+            } else if (ctx->h_flags[1]) {
+                int rc = return_mixed_ids(ctx, ctx->x_own, ctx->x_own_cap, ctx->st);
+                if (rc) return rc;
+            }
+            mixed = ctx->h_flags[1] != 0;
+            if (mixed) {
+                int rc = start_over();
+                if (rc) return rc;
+                cover_pending(true);
+            }
         }
         tr.mark("final replay/cover");
         launch_ninfo_full(g.ninfo, g.full, g.N, 0, ctx->st);
@@ -1004,6 +1153,15 @@ int ptx_finalize(ptx_ctx* ctx) {
         launch_cov(g, ctx->st);
         launch_path_cov_sum(g, ctx->st);
         launch_hap_nz(g, ctx->st);
+    }
+    if (ctx->comm && !(ctx->graphs_committed && g.N > 0)) {  // no coverage pass ran: join the exchange here
+        CU(cudaStreamWaitEvent(ctx->st, ctx->ev_x1, 0));
+        CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        if (ctx->h_flags[2]) { int rc = exchange_id_groups(ctx); if (rc) return rc; }
+        else if (ctx->h_flags[1]) { int rc = return_mixed_ids(ctx, ctx->x_own, ctx->x_own_cap, ctx->st); if (rc) return rc; }
+        CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
     }
     if (ctx->comm) {
         if (!ctx->d_hist_g) { int rc = dalloc(ctx, &ctx->d_hist_g, (size_t)S * 4); if (rc) return rc; }
@@ -1040,10 +1198,11 @@ static int reset_impl(ptx_ctx* ctx, bool keep_buffers) {
     ctx->total_records = 0;
     ctx->ds_records = 0;
     ctx->cov_reduced = false;
-    ctx->h_flags[0] = ctx->h_flags[1] = 0;
+    ctx->h_flags[0] = ctx->h_flags[1] = ctx->h_flags[2] = 0;
     const size_t S = std::max<size_t>(ctx->sp.size(), 1);
     if (ctx->d_hist) CU(cudaMemsetAsync(ctx->d_hist, 0, S * 4 * sizeof(unsigned long long), ctx->st));
-    CU(cudaMemsetAsync(ctx->d_flags, 0, 2 * sizeof(uint32_t), ctx->st));
+    CU(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(uint32_t), ctx->st));
+    if (ctx->out_cursor) CU(cudaMemsetAsync(ctx->out_cursor, 0, 64 * sizeof(unsigned long long), ctx->st));
     if (ctx->d_ds) CU(cudaMemsetAsync(ctx->d_ds, 0, ctx->ds_cap * sizeof(ulonglong2), ctx->st));
     if (ctx->d_err) {
         int rc = zero_coverage(ctx);

@@ -79,6 +79,11 @@ struct IngestArgs {
     unsigned long long* hash_lo;  // [line slots] id hash lo of labelled records
     uint32_t* nodes;            // [<= text bytes / 2] raw node ids of eligible records' walks
     uint32_t* cursors;          // [0] next record-table entry, [1] next node slot
+    // multi-GPU: id entries routed to the rank owning their hash (written by k_apply<CLASSIFY>, sent at finalize)
+    ulonglong2* outbox;         // [n_ranks][box_cap], entry 0 of each box is its header {count, 0}; null on one GPU
+    unsigned long long* out_cursor;  // [n_ranks]
+    uint64_t box_cap;
+    uint32_t n_ranks;
     RangesView ranges;
     unsigned long long* hist;   // [S*4]
     ulonglong2* ds;             // read-id set slots
@@ -113,6 +118,9 @@ void launch_ds_owner_scatter(const ulonglong2* slots, uint64_t cap, uint32_t P, 
 void launch_sub_u64(unsigned long long* out, const unsigned long long* in, unsigned long long step, int n, cudaStream_t st);
 void launch_ds_merge_insert(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags, cudaStream_t st);
 void launch_ds_collect_mixed(const ulonglong2* slots, uint64_t cap, unsigned long long* cursor, ulonglong2* out, uint64_t out_cap, cudaStream_t st);
+void launch_box_headers(ulonglong2* outbox, const unsigned long long* cursor, uint64_t box_cap, uint32_t P, uint32_t* flags, cudaStream_t st);
+void launch_ds_merge_boxes(const ulonglong2* inbox, uint32_t P, uint64_t box_cap, ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags,
+                           cudaStream_t st);
 void launch_ds_apply_mixed(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, cudaStream_t st);
 
 // graph commit

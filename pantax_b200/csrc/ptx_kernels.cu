@@ -334,6 +334,66 @@ __global__ void __launch_bounds__(256) k_ds_merge_insert(const ulonglong2* __res
         }
     }
 }
+__global__ void __launch_bounds__(64) k_box_headers(ulonglong2* outbox, const unsigned long long* __restrict__ cursor, uint64_t box_cap, uint32_t P,
+                                                   uint32_t* flags) {
+    const uint32_t r = threadIdx.x;
+    unsigned long long n = 0;
+    if (r < P) {
+        n = cursor[r];
+        if (n > box_cap - 1) { n = box_cap - 1; atomicOr(flags + 2, 1u); }
+        outbox[(uint64_t)r * box_cap] = make_ulonglong2(n, 0ull);
+    }
+    // entries (header included) of the fullest box -> cursor[P]: every rank sends that many per box
+    unsigned long long m = n + 1;
+    for (int d = 16; d >= 1; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, d);
+        m = o > m ? o : m;
+    }
+    __shared__ unsigned long long ws[2];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) const_cast<unsigned long long*>(cursor)[P] = ws[0] > ws[1] ? ws[0] : ws[1];
+}
+// merge every received box (header = entry count) into the owner table; same state algebra as k_ds_merge_insert
+__global__ void __launch_bounds__(256) k_ds_merge_boxes(const ulonglong2* __restrict__ inbox, uint64_t box_cap, ulonglong2* slots, uint32_t shift,
+                                                        uint64_t mask, uint32_t* flags) {
+    const ulonglong2* box = inbox + (uint64_t)blockIdx.y * box_cap;
+    const uint64_t n = box[0].x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        const ulonglong2 e = box[k + 1];
+        IdHash h;
+        h.lo = e.x;
+        h.hi = (uint32_t)(e.y >> 32);
+        const uint32_t fst = (uint32_t)e.y;
+        uint64_t i = ds_home(h, shift);
+        for (;;) {
+            ulonglong2 cur = ld128(slots + i);
+            if (cur.x == 0ull && cur.y == 0ull) {
+                cur = atomic_cas128(slots + i, make_ulonglong2(0ull, 0ull), e);
+                if (cur.x == 0ull && cur.y == 0ull) {
+                    if (fst == DS_MIXED) atomicOr(flags + 1, 1u);
+                    break;
+                }
+            }
+            if (cur.x == e.x && (cur.y >> 32) == (e.y >> 32)) {
+                atomicOr(flags + 0, 1u);
+                for (;;) {
+                    const uint32_t nst = ds_merge_state((uint32_t)cur.y, fst);
+                    if (nst == (uint32_t)cur.y) break;
+                    const ulonglong2 want = make_ulonglong2(cur.x, (cur.y & 0xFFFFFFFF00000000ull) | nst);
+                    const ulonglong2 prev = atomic_cas128(slots + i, cur, want);
+                    if (prev.x == cur.x && prev.y == cur.y) {
+                        if (nst == DS_MIXED) atomicOr(flags + 1, 1u);
+                        break;
+                    }
+                    cur = prev;
+                }
+                break;
+            }
+            i = (i + 1) & mask;
+        }
+    }
+}
 __global__ void __launch_bounds__(256) k_ds_collect_mixed(const ulonglong2* __restrict__ slots, uint64_t cap, unsigned long long* cursor,
                                                           ulonglong2* __restrict__ out, uint64_t out_cap) {
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cap; k += (uint64_t)gridDim.x * blockDim.x) {
@@ -726,6 +786,22 @@ __global__ void __launch_bounds__(256) k_apply(const IngestArgs a, uint32_t n_en
     h.hi = mb.w;
     if (labelled && (MODE & (MODE_CLASSIFY | MODE_KEEPMASK))) h.lo = a.hash_lo[e];
     if ((MODE & MODE_CLASSIFY) && labelled) ds_insert(a.ds, a.ds_shift, a.ds_mask, h, eligible, label, a.flags);
+    if ((MODE & MODE_CLASSIFY) && a.outbox != nullptr) {
+        // multi-GPU: route {hash, state} to the rank that owns the hash (one atomicAdd per distinct owner per warp)
+        const ulonglong2 ent = make_ulonglong2(h.lo, ((uint64_t)h.hi << 32) | (eligible ? label : DS_NONE));
+        const uint32_t owner = labelled ? ds_owner(ent, a.n_ranks) : 0xFFFFFFFFu;
+        const unsigned peers = __match_any_sync(0xffffffffu, owner);
+        const int leader = __ffs(peers) - 1;
+        const uint32_t lane = threadIdx.x & 31u;
+        unsigned long long base = 0;
+        if (labelled && (int)lane == leader) base = atomicAdd(a.out_cursor + owner, (unsigned long long)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (labelled) {
+            const unsigned long long pos = base + __popc(peers & ((1u << lane) - 1u)) + 1ull;  // entry 0 is the header
+            if (pos < a.box_cap) a.outbox[(uint64_t)owner * a.box_cap + pos] = ent;
+            else atomicOr(a.flags + 2, 1u);  // box overflow: ptx_finalize falls back to the table-scan exchange
+        }
+    }
     if (MODE & MODE_COVER) {
         const RangesView& R = a.ranges;
         int64_t nb = -1;
@@ -1410,6 +1486,16 @@ void launch_sub_u64(unsigned long long* out, const unsigned long long* in, unsig
 void launch_ds_merge_insert(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags, cudaStream_t st) {
     if (n == 0) return;
     k_ds_merge_insert<<<grid_for(n, 256), 256, 0, st>>>(in, n, slots, shift, mask, flags);
+    PTX_LAUNCHED();
+}
+void launch_box_headers(ulonglong2* outbox, const unsigned long long* cursor, uint64_t box_cap, uint32_t P, uint32_t* flags, cudaStream_t st) {
+    k_box_headers<<<1, 64, 0, st>>>(outbox, cursor, box_cap, P, flags);
+    PTX_LAUNCHED();
+}
+void launch_ds_merge_boxes(const ulonglong2* inbox, uint32_t P, uint64_t box_cap, ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags,
+                           cudaStream_t st) {
+    dim3 grid(grid_for(box_cap, 256, 148u * 8u), P);
+    k_ds_merge_boxes<<<grid, 256, 0, st>>>(inbox, box_cap, slots, shift, mask, flags);
     PTX_LAUNCHED();
 }
 void launch_ds_collect_mixed(const ulonglong2* slots, uint64_t cap, unsigned long long* cursor, ulonglong2* out, uint64_t out_cap, cudaStream_t st) {
