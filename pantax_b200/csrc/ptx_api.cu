@@ -106,6 +106,7 @@ struct ptx_ctx {
     // ranges
     std::vector<SpeciesHost> sp;
     int64_t* d_rstart = nullptr; int64_t* d_rend = nullptr; int64_t* d_node_base = nullptr; uint32_t* d_order = nullptr;
+    uint32_t* d_sstart = nullptr;
     int disjoint = 0;
     // graph
     GraphDev g;
@@ -226,6 +227,7 @@ RangesView ranges_view(const ptx_ctx* ctx) {
     R.end = ctx->d_rend;
     R.node_base = ctx->d_node_base;
     R.order = ctx->d_order;
+    R.sstart = ctx->d_sstart;
     R.S = (int)ctx->sp.size();
     R.disjoint = ctx->disjoint;
     return R;
@@ -724,7 +726,7 @@ void ptx_destroy(ptx_ctx* ctx) {
     if (ctx->ev_x0) cudaEventDestroy(ctx->ev_x0);
     if (ctx->ev_x1) cudaEventDestroy(ctx->ev_x1);
     free_graph(ctx);
-    dfree(ctx->d_rstart); dfree(ctx->d_rend); dfree(ctx->d_node_base); dfree(ctx->d_order);
+    dfree(ctx->d_rstart); dfree(ctx->d_rend); dfree(ctx->d_node_base); dfree(ctx->d_order); dfree(ctx->d_sstart);
     dfree(ctx->d_hist); dfree(ctx->d_hist_g); dfree(ctx->d_flags); dfree(ctx->d_err); dfree(ctx->d_ds); dfree(ctx->d_total);
     ev_clear(ctx->ev_count);
     ev_clear(ctx->ev_ingest);
@@ -758,16 +760,19 @@ int ptx_set_ranges(ptx_ctx* ctx, int S, const char* const* taxid, const int64_t*
         if (end[order[i]] < start[order[i]]) ctx->disjoint = 0;
         if (i + 1 < S && end[order[i]] >= start[order[i + 1]]) ctx->disjoint = 0;
     }
-    dfree(ctx->d_rstart); dfree(ctx->d_rend); dfree(ctx->d_node_base); dfree(ctx->d_order); dfree(ctx->d_hist); dfree(ctx->d_err);
+    dfree(ctx->d_rstart); dfree(ctx->d_rend); dfree(ctx->d_node_base); dfree(ctx->d_order); dfree(ctx->d_sstart); dfree(ctx->d_hist); dfree(ctx->d_err);
     int rc;
     if ((rc = dalloc(ctx, &ctx->d_rstart, S)) || (rc = dalloc(ctx, &ctx->d_rend, S)) || (rc = dalloc(ctx, &ctx->d_node_base, S)) ||
-        (rc = dalloc(ctx, &ctx->d_order, S)) || (rc = dalloc(ctx, &ctx->d_hist, (size_t)S * 4)) || (rc = dalloc(ctx, &ctx->d_err, S)))
+        (rc = dalloc(ctx, &ctx->d_order, S)) || (rc = dalloc(ctx, &ctx->d_sstart, S)) || (rc = dalloc(ctx, &ctx->d_hist, (size_t)S * 4)) || (rc = dalloc(ctx, &ctx->d_err, S)))
         return rc;
     std::vector<int64_t> nb(S, -1);
     CU(cudaMemcpyAsync(ctx->d_rstart, start, S * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(ctx->d_rend, end, S * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(ctx->d_node_base, nb.data(), S * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(ctx->d_order, order.data(), S * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->st));
+    std::vector<uint32_t> sstart(S);
+    for (int i = 0; i < S; ++i) sstart[i] = (uint32_t)start[order[i]];
+    CU(cudaMemcpyAsync(ctx->d_sstart, sstart.data(), S * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     ctx->h_err.assign(S, 0);
     return PTX_OK;

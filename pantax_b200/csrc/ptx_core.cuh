@@ -100,21 +100,26 @@ struct RangesView {
     const int64_t* end;        // [S]
     const int64_t* node_base;  // [S] offset of the species in the concatenated node arrays, -1 = no graph
     const uint32_t* order;     // [S] species indices sorted by start (used when disjoint)
+    const uint32_t* sstart;    // [S] start[order[i]] as u32 (ids are < 2^32): the array the binary search walks
     int S;
     int disjoint;
 };
 
 // rcls.rs:253-257: FIRST range in file order with min>=start && max<=end.
-PTX_HD uint32_t classify(const RangesView& R, int64_t lo, int64_t hi) {
+// `sstart`: R.sstart or a copy of it in faster memory (the kernel keeps it in shared memory).
+PTX_HD uint32_t classify(const RangesView& R, int64_t lo, int64_t hi, const uint32_t* sstart) {
     if (R.disjoint) {
-        // ranges are pairwise disjoint: at most one can contain `lo`; binary search by start
+        // ranges are pairwise disjoint: at most one can contain `lo`; binary search over the sorted starts
+        if (lo < 0) return LABEL_U;  // no node in the walk (min = max = -1, rcls.rs:248): starts are >= 0
+        if (R.S == 1) return (lo >= R.start[0] && hi <= R.end[0]) ? 0u : LABEL_U;
+        const uint64_t ulo = (uint64_t)lo;
         int a = 0, b = R.S;  // last position with start <= lo
         while (a < b) {
-            int m = (a + b) >> 1;
-            if (R.start[R.order[m]] <= lo) a = m + 1; else b = m;
+            const int m = (a + b) >> 1;
+            if ((uint64_t)sstart[m] <= ulo) a = m + 1; else b = m;
         }
         if (a == 0) return LABEL_U;
-        uint32_t s = R.order[a - 1];
+        const uint32_t s = R.order[a - 1];
         return (hi <= R.end[s]) ? s : LABEL_U;
     }
     for (int s = 0; s < R.S; ++s)

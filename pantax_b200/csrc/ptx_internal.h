@@ -23,6 +23,8 @@ constexpr uint32_t OVER = 2048;
 constexpr uint32_t PRE = 256;  // keeps `text` 256-byte aligned inside a cudaMalloc'ed buffer
 constexpr int INGEST_THREADS = 256;
 constexpr uint32_t REC_CAP = 1024;  // record starts kept in smem per round
+constexpr uint32_t HIST_SLOTS_LOG2 = 7;  // per-tile species-count accumulators in shared memory (multi-species runs)
+constexpr uint32_t HIST_SLOTS = 1u << HIST_SLOTS_LOG2;
 constexpr uint32_t STASH_CAP = 16;  // walk nodes per record kept in smem between the parse and the coverage pass
 
 // record-table flags (IngestArgs::meta_b[e].y): walk length in the low 24 bits

@@ -502,6 +502,10 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
     uint16_t* rec_tmp = rec_start + REC_CAP;                                                 // [REC_CAP] (bin, rank in bin)
     uint16_t* order = rec_tmp + REC_CAP;                                                     // [REC_CAP] records by line length
     uint16_t* inv_pre = order + REC_CAP;                                                     // [REC_CAP] invalid line slots before slot k
+    // species-count accumulators of this tile, only when S > 1: a small open-addressed table keyed by label.
+    // Abundant species (the contended global counters) are absorbed here and flushed once per tile.
+    uint32_t* hkey = reinterpret_cast<uint32_t*>(inv_pre + REC_CAP);                         // [HIST_SLOTS]
+    uint32_t* hval = hkey + HIST_SLOTS;                                                      // [HIST_SLOTS][4]: n, less_multi, uniq, sum qlen
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t warp_tot[INGEST_THREADS / 32];
     __shared__ uint32_t bin_cnt[64];
@@ -521,6 +525,10 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
         bulk_g2s(stage, gtile, stage_bytes, &mbar);
     }
     if (tid < 4) reinterpret_cast<uint32_t*>(stage + stage_bytes)[tid] = 0x0a0a0a0au;  // sentinel behind the window
+    const bool hist_smem = a.ranges.S > 1;
+    if (hist_smem)
+        for (uint32_t i = tid; i < HIST_SLOTS * 5u; i += INGEST_THREADS) hkey[i] = i < HIST_SLOTS ? LABEL_U : 0u;
+    const uint32_t* sstart = a.ranges.sstart;  // 4 B x S, contiguous: stays in L1 across the binary searches
     mbar_wait(&mbar, 0);
 
     const uint32_t wbase_byte = warp * rows * 512u;
@@ -682,7 +690,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
                     parse_record_global(gtile, p, glim, &tmp);
                     r = tmp;
                 }
-                label = classify(R, r.W ? r.vmin : -1, r.W ? r.vmax : -1);
+                label = classify(R, r.W ? r.vmin : -1, r.W ? r.vmax : -1, sstart);
                 if (MODE & MODE_CLASSIFY) a.labels[rec_base + valid_prev + k - (inv_total ? (uint32_t)inv_pre[k] : 0u)] = label;
             }
             __syncwarp();
@@ -713,11 +721,29 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
                             if (n4) atomicAdd(hp + 3, (unsigned long long)n4);
                         }
                     } else if (cnt) {
-                        unsigned long long* hp = a.hist + 4ull * label;
-                        atomicAdd(hp + 0, 1ull);
-                        atomicAdd(hp + 1, ql);
-                        if (lm) atomicAdd(hp + 2, 1ull);
-                        if (uq) atomicAdd(hp + 3, 1ull);
+                        bool done = false;
+                        if (ql < (1ull << 16)) {  // a tile holds < 64 K lines: the 32-bit sum cannot wrap
+                            uint32_t hs = (label * 0x9E3779B1u) >> (32 - HIST_SLOTS_LOG2);
+                            for (int t = 0; t < 4 && !done; ++t) {
+                                const uint32_t old = atomicCAS(&hkey[hs], LABEL_U, label);
+                                if (old == LABEL_U || old == label) {
+                                    uint32_t* hv = hval + 4u * hs;
+                                    atomicAdd(hv + 0, 1u);
+                                    if (lm) atomicAdd(hv + 1, 1u);
+                                    if (uq) atomicAdd(hv + 2, 1u);
+                                    if (ql) atomicAdd(hv + 3, (uint32_t)ql);
+                                    done = true;
+                                }
+                                hs = (hs + 1u) & (HIST_SLOTS - 1u);
+                            }
+                        }
+                        if (!done) {  // table full around this slot (rare species) or a huge read length
+                            unsigned long long* hp = a.hist + 4ull * label;
+                            atomicAdd(hp + 0, 1ull);
+                            atomicAdd(hp + 1, ql);
+                            if (lm) atomicAdd(hp + 2, 1ull);
+                            if (uq) atomicAdd(hp + 3, 1ull);
+                        }
                     }
                 }
             }
@@ -763,6 +789,18 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
         }
         valid_prev += n_round - inv_total;
         __syncthreads();
+    }
+    if (hist_smem) {
+        for (uint32_t i = tid; i < HIST_SLOTS; i += INGEST_THREADS) {
+            const uint32_t label = hkey[i];
+            if (label == LABEL_U) continue;
+            unsigned long long* hp = a.hist + 4ull * label;
+            const uint32_t* hv = hval + 4u * i;
+            atomicAdd(hp + 0, (unsigned long long)hv[0]);
+            if (hv[3]) atomicAdd(hp + 1, (unsigned long long)hv[3]);
+            if (hv[1]) atomicAdd(hp + 2, (unsigned long long)hv[1]);
+            if (hv[2]) atomicAdd(hp + 3, (unsigned long long)hv[2]);
+        }
     }
 }
 
@@ -1443,8 +1481,10 @@ void launch_scan_tiles(const uint32_t* tile_count, uint32_t* tile_base, uint32_t
 }
 
 void launch_ingest(const IngestArgs& a, cudaStream_t st) {
-    const size_t smem_max = MAX_TILE + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 4 * REC_CAP * sizeof(uint16_t);
-    const size_t smem = (size_t)a.rows_per_warp * MICRO + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 4 * REC_CAP * sizeof(uint16_t);
+    const size_t hist_bytes = HIST_SLOTS * 5 * sizeof(uint32_t);
+    const size_t smem_max = MAX_TILE + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 4 * REC_CAP * sizeof(uint16_t) + hist_bytes;
+    const size_t smem = (size_t)a.rows_per_warp * MICRO + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 4 * REC_CAP * sizeof(uint16_t) +
+                        (a.ranges.S > 1 ? hist_bytes : 0);
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(k_ingest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);

@@ -50,7 +50,9 @@ int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, 
                   const uint32_t* order, int disjoint, int64_t N, const uint32_t* len, int64_t T, const uint32_t* trio_keys,
                   uint32_t stage_lim, int use_stash, uint32_t* labels, int64_t* n_records, int64_t* hist, int64_t* bases, uint64_t* cov,
                   int64_t* trio_bases, uint32_t* err, int* ids_unique, int64_t* n_overflow) {
-    RangesView R{rstart, rend, node_base, order, S, disjoint};
+    std::vector<uint32_t> sstart(S);
+    for (int i = 0; i < S; ++i) sstart[i] = (uint32_t)rstart[order[i]];
+    RangesView R{rstart, rend, node_base, order, sstart.data(), S, disjoint};
     std::vector<uint64_t> bit_off(N + 1, 0);
     for (int64_t i = 0; i < N; ++i) bit_off[i + 1] = bit_off[i] + len[i];
     std::vector<uint8_t> bytes(bit_off[N] + 1, 0);
@@ -84,7 +86,7 @@ int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, 
                 }
             }
             if (!ok) parse_record(buf.data(), (uint32_t)i, (uint32_t)buf.size() - 2, p.r, 1u, use_stash ? p.stash : nullptr, 1, 8);
-            p.label = classify(R, p.r.W ? p.r.vmin : -1, p.r.W ? p.r.vmax : -1);
+            p.label = classify(R, p.r.W ? p.r.vmin : -1, p.r.W ? p.r.vmax : -1, R.sstart);
             p.eligible = p.label != LABEL_U && !p.r.path_null && p.r.c7 != NULL_I64 && p.r.c8 != NULL_I64 && p.r.c9 != NULL_I64;
             recs.push_back(p);
         }
