@@ -337,11 +337,18 @@ def run_ours(args):
     if not args.no_e2e:
         ctx.reset()  # releases the resident buffer
 
+        # result arrays in pinned host memory, allocated once by the caller like the input buffer
+        n_nodes0, n_trios0 = ctx.n_nodes(0), ctx.n_trios(0)
+        res_pin = api.PinnedBuffer(8 * (2 * max(n_nodes0, 1) + max(n_trios0, 1)))
+        o_bases = res_pin.view(np.int64, max(n_nodes0, 1))
+        o_cov = res_pin.view(np.uint64, max(n_nodes0, 1), 8 * max(n_nodes0, 1))
+        o_trio = res_pin.view(np.int64, max(n_trios0, 1), 16 * max(n_nodes0, 1))
+
         def step_e2e():
             ctx.reset()
             ctx.ingest_gaf(pinned, is_last=True)
             ctx.finalize()
-            out = [ctx.species_counts(), ctx.node_bases(0), ctx.node_cov(0), ctx.trio_bases(0)]
+            out = [ctx.species_counts(), ctx.node_bases(0, out=o_bases), ctx.node_cov(0, out=o_cov), ctx.trio_bases(0, out=o_trio)]
             out += list(ctx.path_sums(0)) + list(ctx.hap_trio_counts(0))
             return out
 

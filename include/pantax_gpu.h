@@ -77,7 +77,8 @@ int ptx_commit_graphs(ptx_ctx* ctx);
 /* Optional hint: expected total number of GAF records (sizes the read-id set once). */
 int ptx_reserve(ptx_ctx* ctx, int64_t expected_records);
 
-/* Pinned host memory for the caller's GAF buffer (full-speed H2D). */
+/* Pinned host memory for the caller's GAF buffer (full-speed H2D).  The result getters below accept any host
+ * pointer; one that comes from ptx_host_alloc makes their device->host copy a direct DMA as well. */
 int ptx_host_alloc(size_t bytes, void** out);
 int ptx_host_free(void* p);
 
@@ -87,6 +88,13 @@ int ptx_host_free(void* p);
  * the integer part of species_profiling (profile.rs:208-297), group_reads_by_species
  * (profile.rs:361-463) and the read loop of get_node_abundances (profile.rs:787-919). */
 int ptx_ingest_gaf(ptx_ctx* ctx, const uint8_t* bytes, size_t n, int is_last);
+
+/* Strain-only resume (profile.rs:3365-3419: `--strain` without `--species`): the species column is read
+ * from reads_classification.tsv (column 3, row-aligned with the GAF, profile.rs:3367-3385) instead of
+ * being derived from the walk.  labels[i] = species index (order of ptx_set_ranges) or PTX_LABEL_UNCLASSIFIED for
+ * GAF row i of this ctx's input, counted over all ptx_ingest_gaf calls; successive calls append.  Must
+ * precede the ptx_ingest_gaf call that carries the row.  Cleared by ptx_reset and ptx_set_ranges. */
+int ptx_ingest_labels(ptx_ctx* ctx, const uint32_t* labels, int64_t n);
 
 /* GAF text already in DEVICE memory: obtain a padded device buffer, fill it (whole lines
  * only, e.g. cudaMemcpy or a device-side generator) and hand it over zero-copy.  The

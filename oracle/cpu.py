@@ -41,6 +41,8 @@ def lib():
         L.orc_prepare_graphs.restype = C.c_double
         L.orc_prepare_graphs.argtypes = [vp]
         L.orc_run.argtypes = [vp, C.c_void_p, C.c_size_t]
+        L.orc_set_labels.argtypes = [vp, u32p, C.c_int64]
+        L.orc_label_out_of_range.argtypes = [vp]
         L.orc_n_records.restype = C.c_int64
         L.orc_n_records.argtypes = [vp]
         L.orc_ids_unique.argtypes = [vp]
@@ -116,6 +118,15 @@ class CpuOracle:
 
     def prepare_graphs(self) -> float:
         return self._L.orc_prepare_graphs(self._h)
+
+    def set_labels(self, labels):
+        """Strain-only resume: per-row species labels replace the classifier's (profile.rs:3367-3385)."""
+        a = np.ascontiguousarray(labels, dtype=np.uint32)
+        self._L.orc_set_labels(self._h, _p(a, C.c_uint32), a.size)
+
+    @property
+    def label_out_of_range(self) -> bool:
+        return bool(self._L.orc_label_out_of_range(self._h))
 
     def run(self, data, size=None):
         """`data`: bytes or an integer address (+ size)."""

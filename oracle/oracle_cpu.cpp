@@ -91,6 +91,8 @@ struct Oracle {
     std::vector<SpeciesGraph> g;
     std::vector<Rec> recs;
     std::vector<int64_t> counts;  // S x 4
+    std::vector<uint32_t> label_override;  // strain-only resume (profile.rs:3367-3385): species column from a file
+    bool label_out_of_range = false;
     bool ids_unique = true;
     int64_t n_mixed_dropped = 0;
     double t_parse = 0, t_group = 0, t_cov = 0, t_stats = 0;
@@ -374,6 +376,23 @@ int orc_run(void* h, const uint8_t* data, size_t n) {
     O.recs.reserve(total);
     for (auto& p : part) { O.recs.insert(O.recs.end(), p.begin(), p.end()); std::vector<Rec>().swap(p); }
     const size_t R = O.recs.size();
+    if (!O.label_override.empty()) {  // profile.rs:3381-3385: hstack of the GAF columns and the species column
+        if (O.label_override.size() < R) return -2;
+        O.label_out_of_range = false;
+        for (size_t i = 0; i < R; ++i) {
+            Rec& r = O.recs[i];
+            uint32_t lab = O.label_override[i];
+            if (lab != LABEL_U && r.path) {  // a walk outside the labelled species' graph: local ids would index out of it
+                int64_t lo = 0, hi = 0;
+                bool any = false;
+                for_digit_runs(r.path, r.path_len, [&](int64_t v) {
+                    if (!any) { lo = hi = v; any = true; } else { lo = std::min(lo, v); hi = std::max(hi, v); }
+                });
+                if (any && (lo < O.rstart[lab] || hi > O.rend[lab])) { O.label_out_of_range = true; lab = LABEL_U; }
+            }
+            r.label = lab;
+        }
+    }
     // ---- a3: species counts (profile.rs:208-297, integer part)
     std::vector<std::vector<int64_t>> pc(nt, std::vector<int64_t>(S * 4, 0));
     parallel_for(nt, R, [&](int t, size_t a, size_t b) {
@@ -493,6 +512,8 @@ int orc_run(void* h, const uint8_t* data, size_t n) {
     return 0;
 }
 
+void orc_set_labels(void* h, const uint32_t* labels, int64_t n) { ((Oracle*)h)->label_override.assign(labels, labels + n); }
+int orc_label_out_of_range(void* h) { return ((Oracle*)h)->label_out_of_range ? 1 : 0; }
 int64_t orc_n_records(void* h) { return (int64_t)((Oracle*)h)->recs.size(); }
 int orc_ids_unique(void* h) { return ((Oracle*)h)->ids_unique ? 1 : 0; }
 int64_t orc_mixed_dropped(void* h) { return ((Oracle*)h)->n_mixed_dropped; }

@@ -127,12 +127,33 @@ def classify(path: Optional[bytes], ranges: Sequence[Tuple[str, int, int]]) -> s
     return UNCLASSIFIED
 
 
-def rcls_profile(data: bytes, ranges: Sequence[Tuple[str, int, int]]) -> List[Row]:
-    """rcls.rs:452-458."""
+def rcls_profile(data: bytes, ranges: Sequence[Tuple[str, int, int]], species_column: Optional[Sequence[str]] = None) -> List[Row]:
+    """rcls.rs:452-458.  With `species_column` (strain-only resume, profile.rs:3367-3385): the species of row i is
+    species_column[i], the third column of reads_classification.tsv, hstacked onto the GAF columns.  A row whose
+    walk leaves the node range of its supplied species is treated as "U" (the reference would index outside the
+    species graph); `rows.label_out_of_range` reports it."""
     rows = load_gaf(data)
-    for r in rows:
-        r.species = classify(r.path, ranges)
+    if species_column is None:
+        for r in rows:
+            r.species = classify(r.path, ranges)
+        return rows
+    if len(species_column) < len(rows):
+        raise ValueError("species column shorter than the GAF")
+    bounds = {name: (s, e) for name, s, e in ranges}
+    bad = False
+    for r, sp in zip(rows, species_column):
+        if sp != UNCLASSIFIED and r.path is not None:
+            ids = digit_runs(r.path)
+            if ids and (min(ids) < bounds[sp][0] or max(ids) > bounds[sp][1]):
+                sp, bad = UNCLASSIFIED, True
+        r.species = sp
+    rows = RowList(rows)
+    rows.label_out_of_range = bad
     return rows
+
+
+class RowList(list):
+    label_out_of_range = False
 
 
 # --------------------------------------------------------------------------
@@ -558,12 +579,13 @@ def coverage_all_species(
     data: bytes,
     ranges: Sequence[Tuple[str, int, int]],
     graphs: Dict[str, Graph],
+    species_column: Optional[Sequence[str]] = None,
 ):
     """rcls -> grouping -> per-species trio table + node coverage + path sums.
 
     Returns (rows, counts, per_species) with per_species[taxid] = dict(bases,
     trio_bases, cov, trio_len, owner, U, nz, sum_cov, sum_len, error)."""
-    rows = rcls_profile(data, ranges)
+    rows = rcls_profile(data, ranges, species_column)
     counts = species_counts(rows)
     grouped = group_reads_by_species(rows)
     start_of = {name: s for name, s, _e in ranges}

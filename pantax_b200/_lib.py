@@ -39,6 +39,7 @@ SIGNATURES = {
     "ptx_ingest_gaf": (i32, [vp, vp, C.c_size_t, i32]),
     "ptx_gaf_buffer_alloc": (i32, [vp, C.c_size_t, P(i32), P(vp)]),
     "ptx_ingest_gaf_device": (i32, [vp, i32, C.c_size_t]),
+    "ptx_ingest_labels": (i32, [vp, C.POINTER(C.c_uint32), C.c_int64]),
     "ptx_finalize": (i32, [vp]),
     "ptx_reset": (i32, [vp]),
     "ptx_rewind": (i32, [vp]),

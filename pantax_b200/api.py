@@ -44,6 +44,13 @@ class PinnedBuffer:
     def ptr(self) -> int:
         return self._ptr.value
 
+    def view(self, dtype, count: int, byte_offset: int = 0) -> np.ndarray:
+        """A typed numpy view of part of the buffer (e.g. an `out=` array for the result getters: a pinned
+        destination lets the device->host copy run at PCIe speed instead of through pageable staging)."""
+        dt = np.dtype(dtype)
+        assert byte_offset % dt.itemsize == 0 and byte_offset + count * dt.itemsize <= self.nbytes
+        return self.array[byte_offset: byte_offset + count * dt.itemsize].view(dt)
+
     def free(self):
         if self._ptr:
             self._L.ptx_host_free(self._ptr)
@@ -125,6 +132,12 @@ class PantaxGpu:
         else:
             self._ck(self._L.ptx_ingest_gaf(self._h, C.c_void_p(int(data)), size, int(is_last)))
 
+    def ingest_labels(self, labels):
+        """profile.rs:3367-3385 (strain-only resume): species label per GAF row (index into the ranges, LABEL_U = "U")
+        taken from reads_classification.tsv instead of the walk; call before ingest_gaf."""
+        a = np.ascontiguousarray(labels, dtype=np.uint32)
+        self._ck(self._L.ptx_ingest_labels(self._h, _p(a, C.c_uint32), a.size))
+
     def gaf_buffer_alloc(self, capacity: int) -> Tuple[int, int]:
         """Returns (buffer_id, device pointer) of a padded device buffer for HBM-resident GAF text."""
         bid = C.c_int()
@@ -191,36 +204,40 @@ class PantaxGpu:
     def n_trios(self, s: int) -> int:
         return self._L.ptx_species_trios(self._h, s)
 
-    def _sized(self, n: int, dtype):
+    def _sized(self, n: int, dtype, out=None):
+        if out is not None:  # caller-owned destination (may be pinned memory)
+            if out.dtype != np.dtype(dtype) or out.size < max(n, 1) or not out.flags.c_contiguous:
+                raise ValueError(f"out must be a contiguous {np.dtype(dtype)} array of >= {max(n, 1)} elements")
+            return out
         return np.zeros(max(n, 1), dtype=dtype)
 
-    def node_bases(self, s: int) -> np.ndarray:
+    def node_bases(self, s: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         n = self.n_nodes(s)
-        out = self._sized(n, np.int64)
+        out = self._sized(n, np.int64, out)
         self._ck(self._L.ptx_node_bases(self._h, s, _p(out, C.c_int64)))
         return out[:n]
 
-    def node_cov(self, s: int) -> np.ndarray:
+    def node_cov(self, s: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         n = self.n_nodes(s)
-        out = self._sized(n, np.uint64)
+        out = self._sized(n, np.uint64, out)
         self._ck(self._L.ptx_node_cov(self._h, s, _p(out, C.c_uint64)))
         return out[:n]
 
-    def node_depth(self, s: int) -> np.ndarray:
+    def node_depth(self, s: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         n = self.n_nodes(s)
-        out = self._sized(n, np.float64)
+        out = self._sized(n, np.float64, out)
         self._ck(self._L.ptx_node_depth(self._h, s, _p(out, C.c_double)))
         return out[:n]
 
-    def trio_bases(self, s: int) -> np.ndarray:
+    def trio_bases(self, s: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         n = self.n_trios(s)
-        out = self._sized(n, np.int64)
+        out = self._sized(n, np.int64, out)
         self._ck(self._L.ptx_trio_bases(self._h, s, _p(out, C.c_int64)))
         return out[:n]
 
-    def trio_depth(self, s: int) -> np.ndarray:
+    def trio_depth(self, s: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         n = self.n_trios(s)
-        out = self._sized(n, np.float64)
+        out = self._sized(n, np.float64, out)
         self._ck(self._L.ptx_trio_depth(self._h, s, _p(out, C.c_double)))
         return out[:n]
 

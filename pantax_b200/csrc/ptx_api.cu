@@ -90,6 +90,7 @@ struct Chunk {
     uint32_t tiles_cap = 0;
     int64_t labels_cap = 0;
     int64_t n_records = 0;
+    int64_t row_base = 0;  // GAF rows ingested before this chunk
     bool ingested = false;  // classify pass done
     bool covered = false;   // coverage pass done against the current graph
     cudaEvent_t copied = nullptr;
@@ -127,6 +128,8 @@ struct ptx_ctx {
     std::vector<Chunk> chunks;
     std::vector<uint8_t> carry;
     int64_t total_records = 0;
+    uint32_t* d_labels_in = nullptr;  // ptx_ingest_labels: species label of GAF rows [0, labels_in_n), row = position over all chunks
+    int64_t labels_in_n = 0, labels_in_cap = 0;
     bool dirty = false;          // something ingested / committed since the last finalize
     uint32_t h_flags[4] = {0, 0, 0, 0};  // [0] repeated id, [1] mixed-species id group, [2] exchange box overflow
     std::vector<uint32_t> h_err;
@@ -267,6 +270,7 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.rows_per_warp = ch.rows;
     a.micro_base = ch.tile_base;
     a.labels = ch.labels;
+    a.labels_in = ctx->labels_in_n > 0 ? ctx->d_labels_in + ch.row_base : nullptr;
     a.meta_b = ch.meta_b;
     a.meta_a = ch.meta_a;
     a.hash_lo = ch.hash_lo;
@@ -410,6 +414,9 @@ int chunk_process(ptx_ctx* ctx, Chunk& ch) {
         CU(cudaMalloc((void**)&ch.labels, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
         ch.labels_cap = (int64_t)std::max<uint64_t>(total, 1);
     }
+    ch.row_base = ctx->total_records;
+    if (ctx->labels_in_n > 0 && ch.row_base + ch.n_records > ctx->labels_in_n)
+        return fail(ctx, PTX_E_STATE, "ptx_ingest_labels supplied fewer labels than the GAF has rows");
     int rc = ds_ensure(ctx, ch.n_records);
     if (rc) return rc;
     ctx->ds_records += ch.n_records;
@@ -727,7 +734,7 @@ void ptx_destroy(ptx_ctx* ctx) {
     if (ctx->ev_x1) cudaEventDestroy(ctx->ev_x1);
     free_graph(ctx);
     dfree(ctx->d_rstart); dfree(ctx->d_rend); dfree(ctx->d_node_base); dfree(ctx->d_order); dfree(ctx->d_sstart);
-    dfree(ctx->d_hist); dfree(ctx->d_hist_g); dfree(ctx->d_flags); dfree(ctx->d_err); dfree(ctx->d_ds); dfree(ctx->d_total);
+    dfree(ctx->d_hist); dfree(ctx->d_hist_g); dfree(ctx->d_flags); dfree(ctx->d_err); dfree(ctx->d_ds); dfree(ctx->d_total); dfree(ctx->d_labels_in);
     ev_clear(ctx->ev_count);
     ev_clear(ctx->ev_ingest);
     ev_clear(ctx->ev_apply);
@@ -761,6 +768,7 @@ int ptx_set_ranges(ptx_ctx* ctx, int S, const char* const* taxid, const int64_t*
         if (i + 1 < S && end[order[i]] >= start[order[i + 1]]) ctx->disjoint = 0;
     }
     dfree(ctx->d_rstart); dfree(ctx->d_rend); dfree(ctx->d_node_base); dfree(ctx->d_order); dfree(ctx->d_sstart); dfree(ctx->d_hist); dfree(ctx->d_err);
+    ctx->labels_in_n = 0;  // supplied labels index the previous species list
     int rc;
     if ((rc = dalloc(ctx, &ctx->d_rstart, S)) || (rc = dalloc(ctx, &ctx->d_rend, S)) || (rc = dalloc(ctx, &ctx->d_node_base, S)) ||
         (rc = dalloc(ctx, &ctx->d_order, S)) || (rc = dalloc(ctx, &ctx->d_sstart, S)) || (rc = dalloc(ctx, &ctx->d_hist, (size_t)S * 4)) || (rc = dalloc(ctx, &ctx->d_err, S)))
@@ -1042,6 +1050,32 @@ int ptx_ingest_gaf(ptx_ctx* ctx, const uint8_t* bytes, size_t n, int is_last) {
     return PTX_OK;
 }
 
+// Strain-only resume (profile.rs:3367-3379): the species column comes from reads_classification.tsv, row-aligned
+// with the GAF, instead of from the walk.  Appends to the rows supplied so far.
+int ptx_ingest_labels(ptx_ctx* ctx, const uint32_t* labels, int64_t n) {
+    if (!ctx || (!labels && n) || n < 0) return fail(ctx, PTX_E_INVALID, "ptx_ingest_labels: bad arguments");
+    if (ctx->sp.empty()) return fail(ctx, PTX_E_STATE, "call ptx_set_ranges first");
+    if (ctx->total_records > ctx->labels_in_n) return fail(ctx, PTX_E_STATE, "ptx_ingest_labels: GAF rows were already ingested without labels");
+    const uint32_t S = (uint32_t)ctx->sp.size();
+    for (int64_t i = 0; i < n; ++i)
+        if (labels[i] != LABEL_U && labels[i] >= S) return fail(ctx, PTX_E_RANGE, "ptx_ingest_labels: label is neither a species index nor PTX_LABEL_U");
+    if (n == 0) return PTX_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->labels_in_n + n > ctx->labels_in_cap) {
+        const int64_t cap = std::max<int64_t>(ctx->labels_in_n + n, 2 * ctx->labels_in_cap);
+        uint32_t* nd = nullptr;
+        CU(cudaMalloc((void**)&nd, (size_t)cap * sizeof(uint32_t)));
+        CU(cudaStreamSynchronize(ctx->st));
+        if (ctx->labels_in_n) CU(cudaMemcpy(nd, ctx->d_labels_in, (size_t)ctx->labels_in_n * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+        dfree(ctx->d_labels_in);
+        ctx->d_labels_in = nd;
+        ctx->labels_in_cap = cap;
+    }
+    CU(cudaMemcpy(ctx->d_labels_in + ctx->labels_in_n, labels, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    ctx->labels_in_n += n;
+    return PTX_OK;
+}
+
 int ptx_gaf_buffer_alloc(ptx_ctx* ctx, size_t capacity, int* buffer_id, void** device_ptr) {
     if (!ctx || !buffer_id || !device_ptr) return PTX_E_INVALID;
     cudaSetDevice(ctx->device);
@@ -1180,6 +1214,12 @@ int ptx_finalize(ptx_ctx* ctx) {
     CU(cudaStreamSynchronize(ctx->st));
     CU(cudaGetLastError());
     ctx->dirty = false;
+    if (ctx->labels_in_n > 0) {
+        uint32_t bad = 0;
+        CU(cudaMemcpy(&bad, ctx->d_flags + 3, sizeof bad, cudaMemcpyDeviceToHost));
+        if (bad) return fail(ctx, PTX_E_RANGE, "ptx_ingest_labels: a row is labelled with a species whose node range does not contain its walk "
+                                               "(such rows were treated as unclassified; the reference indexes out of the species graph here)");
+    }
     return PTX_OK;
 }
 
@@ -1200,6 +1240,7 @@ static int reset_impl(ptx_ctx* ctx, bool keep_buffers) {
         ctx->chunks.clear();
     }
     ctx->carry.clear();
+    if (!keep_buffers) ctx->labels_in_n = 0;  // supplied labels belong to the input that is being dropped
     ctx->total_records = 0;
     ctx->ds_records = 0;
     ctx->cov_reduced = false;

@@ -75,6 +75,7 @@ struct IngestArgs {
     uint32_t rows_per_warp;      // tile = rows_per_warp * 4096 bytes
     const uint64_t* micro_base;  // [n_micro] exclusive record prefix per micro-tile within the chunk (MODE_CLASSIFY)
     uint32_t* labels;           // [chunk records]
+    const uint32_t* labels_in;  // [chunk records] caller-supplied species labels (ptx_ingest_labels), or null: classify
     // record table + CSR walks written by k_ingest, consumed by k_apply (entries in length-sorted tile order)
     uint4* meta_b;              // [line slots] {node_off, flags|W, label, id hash hi}
     longlong2* meta_a;          // [line slots] {c8, c9} of eligible records
@@ -91,7 +92,7 @@ struct IngestArgs {
     ulonglong2* ds;             // read-id set slots
     uint32_t ds_shift;          // 64 - log2(capacity)
     uint64_t ds_mask;
-    uint32_t* flags;            // [0] dup id seen, [1] mixed-species id group seen
+    uint32_t* flags;            // [0] dup id seen, [1] mixed-species id group seen, [2] exchange box overflow, [3] supplied label outside its range
     uint32_t* err;              // [S] bit0: profile.rs:854 tripped
     // coverage
     uint4* ninfo;

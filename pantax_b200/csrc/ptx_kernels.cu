@@ -690,8 +690,17 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
                     parse_record_global(gtile, p, glim, &tmp);
                     r = tmp;
                 }
-                label = classify(R, r.W ? r.vmin : -1, r.W ? r.vmax : -1, sstart);
-                if (MODE & MODE_CLASSIFY) a.labels[rec_base + valid_prev + k - (inv_total ? (uint32_t)inv_pre[k] : 0u)] = label;
+                const uint32_t row = rec_base + valid_prev + k - (inv_total ? (uint32_t)inv_pre[k] : 0u);  // GAF row within the chunk
+                if (a.labels_in) {  // strain-only resume: the species column of reads_classification.tsv
+                    label = a.labels_in[row];
+                    if (label != LABEL_U && r.W && (r.vmin < R.start[label] || r.vmax > R.end[label])) {
+                        atomicOr(a.flags + 3, 1u);  // the walk leaves the species graph: reported by ptx_finalize
+                        label = LABEL_U;
+                    }
+                } else {
+                    label = classify(R, r.W ? r.vmin : -1, r.W ? r.vmax : -1, sstart);
+                }
+                if (MODE & MODE_CLASSIFY) a.labels[row] = label;
             }
             __syncwarp();
             if (MODE & MODE_CLASSIFY) {

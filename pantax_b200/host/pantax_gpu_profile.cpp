@@ -34,7 +34,7 @@
 namespace {
 
 struct Options {
-    std::string db, gaf, wd = ".", report, range_file, len_file, designated;
+    std::string db, gaf, wd = ".", report, range_file, len_file, designated, reads_binning;
     bool species = false, strain = false, filtered = true, long_read = false, shift = false, force = false;
     double min_species_abundance = 1e-4, fr = -1, min_depth = 0;
     int mode = 2, device = 0;
@@ -187,7 +187,8 @@ std::vector<double> zscore_filter(const std::vector<double>& d, double thr) {
 double round2(double x) { return std::round(x * 100.0) / 100.0; }
 
 void usage() {
-    puts("pantax-gpu-profile --db DIR --gaf FILE [--wd DIR] [--species] [--strain] [-R reads_classification.tsv]\n"
+    puts("pantax-gpu-profile --db DIR --gaf FILE|- [--wd DIR] [--species] [--strain] [-R reads_classification.tsv]\n"
+         "                   [--reads-binning reads_classification.tsv]   (with --strain only: species column of the GAF rows)\n"
          "                   [-a MIN_SPECIES_ABUND=1e-4] [--fr F] [--long-read] [--shift] [--no-filter] [--smode 0|1|2]\n"
          "                   [--ds TAXID,TAXID] [--range-file F] [--len-file F] [--min-depth D] [--device N]\n"
          "GPU implementation of PanTax's profiling stage (read classification, species abundance, node coverage and\n"
@@ -208,6 +209,7 @@ int main(int argc, char** argv) {
         else if (a == "--strain") o.strain = true;
         else if (a == "-R" || a == "--report") o.report = next();
         else if (a == "-a") o.min_species_abundance = std::stod(next());
+        else if (a == "--reads-binning") o.reads_binning = next();
         else if (a == "--fr") o.fr = std::stod(next());
         else if (a == "--long-read") o.long_read = true;
         else if (a == "--shift") o.shift = true;
@@ -240,8 +242,30 @@ int main(int argc, char** argv) {
         ck(ctx, ptx_set_ranges(ctx, (int)ranges.size(), names.data(), st.data(), en.data()), "ptx_set_ranges");
     }
 
+    // ---- strain-only resume (profile.rs:3365-3385): the species column comes from the reads binning file
+    // (<wd>/reads_classification.tsv unless given, profile.rs:179-182), row-aligned with the GAF
+    if (o.strain && !o.species) {
+        std::string rb = !o.reads_binning.empty() && exists(o.reads_binning) ? o.reads_binning : o.wd + "/reads_classification.tsv";
+        if (!exists(rb)) die("Neither reads binning file '" + o.reads_binning + "' nor '" + o.wd + "/reads_classification.tsv' is a valid file path");
+        std::map<std::string, uint32_t> idx;
+        for (size_t i = 0; i < ranges.size(); ++i) idx.emplace(ranges[i].taxid, (uint32_t)i);  // first row wins, as in rcls.rs:253
+        std::ifstream f(rb);
+        std::string line;
+        std::vector<uint32_t> labels;
+        while (std::getline(f, line)) {
+            auto p = split(line, '\t');
+            if (p.size() < 3) die("reads binning file: a row has fewer than 3 columns: " + rb);
+            auto it = idx.find(p[2]);
+            if (it == idx.end() && p[2] != "U") die("reads binning file: species '" + p[2] + "' is not in the range file");
+            labels.push_back(it == idx.end() ? PTX_LABEL_UNCLASSIFIED : it->second);
+        }
+        ck(ctx, ptx_ingest_labels(ctx, labels.data(), (int64_t)labels.size()), "ptx_ingest_labels");
+        fprintf(stderr, "- Species column of %zu rows taken from %s\n", labels.size(), rb.c_str());
+    }
+
     // ---- read classification + species counts: stream the GAF through the library in 256 MB host chunks
-    FILE* gf = fopen(o.gaf.c_str(), "rb");
+    // ("-": the aligner's stdout, e.g. `vg giraffe -o gaf ... | pantax-gpu-profile --gaf -`, alignment.rs:18-26)
+    FILE* gf = o.gaf == "-" ? stdin : fopen(o.gaf.c_str(), "rb");
     if (!gf) die("cannot open GAF mapping file " + o.gaf);
     const size_t CH = (size_t)256 << 20;
     void* pin = nullptr;
@@ -249,13 +273,14 @@ int main(int argc, char** argv) {
     std::vector<std::string> gaf_keep;  // only needed for reads_classification.tsv
     const bool want_report = !o.report.empty();
     for (;;) {
-        size_t n = fread(pin, 1, CH, gf);
+        size_t n = 0;  // a pipe returns short reads: fill the chunk
+        while (n < CH) { size_t k = fread((char*)pin + n, 1, CH - n, gf); if (k == 0) break; n += k; }
         const bool last = n < CH;
         if (want_report) gaf_keep.emplace_back((const char*)pin, n);
         ck(ctx, ptx_ingest_gaf(ctx, (const uint8_t*)pin, n, last ? 1 : 0), "ptx_ingest_gaf");
         if (last) break;
     }
-    fclose(gf);
+    if (gf != stdin) fclose(gf);
     ck(ctx, ptx_finalize(ctx), "ptx_finalize");
     const int64_t R = ptx_num_records(ctx);
     const int S = (int)ranges.size();
@@ -327,7 +352,19 @@ int main(int argc, char** argv) {
     }
     for (auto& r : table) r.rel = r.abs / total;
     std::stable_sort(table.begin(), table.end(), [](const Row& a, const Row& b) { return a.rel > b.rel; });
-    {
+    if (o.strain && !o.species) {
+        // profile.rs:3399-3414: the strain-only run takes the species table from the existing species_abundance.txt
+        const std::string sa = o.wd + "/species_abundance.txt";
+        std::ifstream f(sa);
+        if (!f) die("strain-only run: " + sa + " does not exist (run with --species first)");
+        table.clear();
+        std::string line;
+        std::getline(f, line);  // header
+        while (std::getline(f, line)) {
+            auto p = split(line, '\t');
+            if (p.size() >= 3) table.push_back({p[0], std::stod(p[1]), std::stod(p[2])});
+        }
+    } else {
         FILE* f = fopen((o.wd + "/species_abundance.txt").c_str(), "wb");
         if (!f) die("cannot write species_abundance.txt");
         fprintf(f, "species_taxid\tpredicted_abundance\tpredicted_coverage\n");

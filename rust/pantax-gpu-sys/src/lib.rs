@@ -25,6 +25,7 @@ extern "C" {
     pub fn ptx_ingest_gaf(ctx: *mut ptx_ctx, bytes: *const u8, n: size_t, is_last: c_int) -> c_int;
     pub fn ptx_gaf_buffer_alloc(ctx: *mut ptx_ctx, capacity: size_t, buffer_id: *mut c_int, device_ptr: *mut *mut c_void) -> c_int;
     pub fn ptx_ingest_gaf_device(ctx: *mut ptx_ctx, buffer_id: c_int, n: size_t) -> c_int;
+    pub fn ptx_ingest_labels(ctx: *mut ptx_ctx, labels: *const u32, n: i64) -> c_int;
     pub fn ptx_finalize(ctx: *mut ptx_ctx) -> c_int;
     pub fn ptx_reset(ctx: *mut ptx_ctx) -> c_int;
     pub fn ptx_rewind(ctx: *mut ptx_ctx) -> c_int;

@@ -34,25 +34,31 @@ def py_graph(nodes_len, paths, names) -> "opy.Graph":
     return g
 
 
-def run_cpu_oracle(ranges, graphs, gaf: bytes, threads: int = 0) -> "ocpu.CpuOracle":
+def run_cpu_oracle(ranges, graphs, gaf: bytes, threads: int = 0, labels=None) -> "ocpu.CpuOracle":
+    """`labels`: per-row species indices replacing the classifier (strain-only resume)."""
     o = ocpu.CpuOracle(threads)
     o.set_ranges(ranges)
     for s, g in enumerate(graphs):
         if g is not None:
             o.set_graph(s, g[0], g[1])
     o.prepare_graphs()
+    if labels is not None:
+        o.set_labels(labels)
     o.run(gaf)
     return o
 
 
-def run_py_oracle(ranges, graphs, gaf: bytes):
+def run_py_oracle(ranges, graphs, gaf: bytes, labels=None):
     gd = {ranges[s][0]: py_graph(*g) for s, g in enumerate(graphs) if g is not None}
-    return opy.coverage_all_species(gaf, ranges, gd)
+    col = None if labels is None else [opy.UNCLASSIFIED if int(l) == LABEL_U else ranges[int(l)][0] for l in labels]
+    return opy.coverage_all_species(gaf, ranges, gd, col)
 
 
-def assert_cpu_matches_py(ranges, graphs, gaf: bytes):
-    rows, counts, per = run_py_oracle(ranges, graphs, gaf)
-    o = run_cpu_oracle(ranges, graphs, gaf, threads=3)
+def assert_cpu_matches_py(ranges, graphs, gaf: bytes, labels=None):
+    rows, counts, per = run_py_oracle(ranges, graphs, gaf, labels)
+    o = run_cpu_oracle(ranges, graphs, gaf, threads=3, labels=labels)
+    if labels is not None:
+        assert o.label_out_of_range == rows.label_out_of_range
     name_to_idx = {r[0]: i for i, r in enumerate(ranges)}
     lab = o.labels()
     assert len(rows) == o.n_records

@@ -125,6 +125,60 @@ def test_gpu_dialect_edges_and_start_beyond_node_error():
     assert o.species_error(0) == 1
 
 
+def test_gpu_supplied_species_column_strain_only_resume():
+    """ptx_ingest_labels (profile.rs:3367-3385): labels come from reads_classification.tsv, not from the walk."""
+    from gpu_common import assert_gpu_matches_oracle
+    from test_oracle import _supplied_labels
+    api = _api()
+    ds = synth.Dataset(62, [20000, 6000, 9000], [6, 2, 3])
+    gaf = ds.gaf(8, 0, 60000, NASTY_DUP)
+    graphs = dataset_graphs(ds)
+    lab = _supplied_labels(ds.ranges(), graphs, gaf, 3)
+    o = run_cpu_oracle(ds.ranges(), graphs, gaf, labels=lab)
+
+    def run(labels, pieces):
+        ctx = api.PantaxGpu(0)
+        ctx.set_ranges(ds.ranges())
+        for s, g in enumerate(graphs):
+            ctx.upload_graph(s, g[0], g[1])
+        ctx.commit_graphs()
+        half = labels.size // 2
+        ctx.ingest_labels(labels[:half])   # successive calls append
+        ctx.ingest_labels(labels[half:])
+        cuts = np.linspace(0, len(gaf), pieces + 1).astype(int)
+        for i in range(pieces):
+            ctx.ingest_gaf(gaf[cuts[i]:cuts[i + 1]], is_last=(i == pieces - 1))
+        return ctx
+
+    for pieces in (1, 3):
+        ctx = run(lab, pieces)
+        ctx.finalize()
+        assert_gpu_matches_oracle(ctx, o, graphs)
+    # a label whose species range does not contain the walk: row treated as "U", finalize reports it
+    lab2 = _supplied_labels(ds.ranges(), graphs, gaf, 4, p_wrong=0.01)
+    o2 = run_cpu_oracle(ds.ranges(), graphs, gaf, labels=lab2)
+    assert o2.label_out_of_range
+    ctx = run(lab2, 2)
+    with pytest.raises(api.PantaxGpuError) as e:
+        ctx.finalize()
+    assert e.value.name == "PTX_E_RANGE"
+    assert_gpu_matches_oracle(ctx, o2, graphs)
+    # too few labels for the rows / labels after rows / bad species index
+    ctx = api.PantaxGpu(0)
+    ctx.set_ranges(ds.ranges())
+    ctx.ingest_labels(lab[:10])
+    with pytest.raises(api.PantaxGpuError) as e:
+        ctx.ingest_gaf(gaf, is_last=True)
+    assert e.value.name == "PTX_E_STATE"
+    with pytest.raises(api.PantaxGpuError) as e:
+        ctx.ingest_labels(np.array([7], dtype=np.uint32))
+    assert e.value.name == "PTX_E_RANGE"
+    ctx.reset()
+    ctx.ingest_gaf(gaf, is_last=True)   # reset dropped the supplied labels: classifier again
+    ctx.finalize()
+    np.testing.assert_array_equal(ctx.read_labels(), run_cpu_oracle(ds.ranges(), graphs, gaf).labels())
+
+
 def test_gpu_overlapping_ranges_use_first_match_in_file_order():
     from gpu_common import gpu_vs_oracle
     # rcls.rs:253-257 takes the FIRST matching row; with overlapping rows the binary search is not used

@@ -118,3 +118,41 @@ def test_host_driver_end_to_end_against_oracle(tmp_path):
             if m["frequencies_mean"] is not None and p[4]:
                 assert float(p[4]) == pytest.approx(m["frequencies_mean"], rel=1e-12)
             assert float(p[5]) == float(np.float32(sc[h]) / np.float32(sl[h]))
+
+
+@pytest.mark.gpu
+def test_host_driver_strain_only_resume_and_stdin(tmp_path):
+    """`--strain` alone (profile.rs:3365-3419): the species column comes from reads_classification.tsv and the species
+    table from the existing species_abundance.txt; the GAF arrives on stdin (the aligner's stdout, alignment.rs:18-26).
+    The strain inputs must be identical to those of the full run."""
+    ds = synth.Dataset(405, [20000, 7000], [5, 2])
+    graphs = dataset_graphs(ds)
+    gaf = ds.gaf(9, 0, 40000, NASTY)
+    db, gp, _lens = make_db(str(tmp_path), ds, graphs, gaf)
+    wd = os.path.join(str(tmp_path), "wd")
+    os.makedirs(wd)
+    rep = os.path.join(wd, "reads_classification.tsv")
+    r = subprocess.run([BIN, "--db", db, "--gaf", gp, "--wd", wd, "--species", "--strain", "-R", rep, "-a", "0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    full = {f: open(os.path.join(wd, "strain_inputs", f)).read() for f in sorted(os.listdir(os.path.join(wd, "strain_inputs")))}
+    sa = open(os.path.join(wd, "species_abundance.txt")).read()
+    for f in full:
+        os.remove(os.path.join(wd, "strain_inputs", f))
+    r = subprocess.run([BIN, "--db", db, "--gaf", "-", "--wd", wd, "--strain", "-a", "0"], input=gaf, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    assert b"Species column of" in r.stderr
+    again = {f: open(os.path.join(wd, "strain_inputs", f)).read() for f in sorted(os.listdir(os.path.join(wd, "strain_inputs")))}
+    assert again == full
+    assert open(os.path.join(wd, "species_abundance.txt")).read() == sa   # not rewritten
+    # a binning file that sends every read of species 2 to "U": that species gets no coverage
+    t2 = ds.ranges()[1][0]
+    rows = [l.split("\t") for l in open(rep).read().split("\n")[:-1]]
+    with open(rep, "w") as f:
+        for x in rows:
+            f.write("\t".join([x[0], x[1], "U" if x[2] == t2 else x[2], x[3]]) + "\n")
+    r = subprocess.run([BIN, "--db", db, "--gaf", gp, "--wd", wd, "--strain", "-a", "0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    nodes2 = open(os.path.join(wd, "strain_inputs", f"{t2}.nodes.tsv")).read().split("\n")[1:]
+    assert [l for l in nodes2 if l] == []
+    t1 = ds.ranges()[0][0]
+    assert open(os.path.join(wd, "strain_inputs", f"{t1}.nodes.tsv")).read() == full[f"{t1}.nodes.tsv"]

@@ -103,6 +103,35 @@ def test_cpp_and_python_oracles_agree_long_reads_and_filter():
     assert len(ids) == len(set(ids))
 
 
+def _supplied_labels(ranges, graphs, gaf, seed, p_to_u=0.05, p_wrong=0.0):
+    """Species column for the strain-only resume: the classifier's labels with some rows set to "U" (a stricter
+    binning file) and optionally some rows moved to a wrong species (walk outside that species' range)."""
+    lab = run_cpu_oracle(ranges, graphs, gaf).labels().copy()
+    rng = np.random.default_rng(seed)
+    lab[rng.random(lab.size) < p_to_u] = LABEL_U
+    if p_wrong:
+        hit = (rng.random(lab.size) < p_wrong) & (lab != LABEL_U)
+        lab[hit] = (lab[hit] + 1) % len(ranges)
+    return lab
+
+
+def test_supplied_species_column_python_vs_cpp():
+    # profile.rs:3367-3385: --strain without --species takes column 3 of reads_classification.tsv as the species
+    ds = synth.Dataset(61, [3000, 800, 1200], [6, 1, 3])
+    gaf = ds.gaf(5, 0, 3000, NASTY_DUP)
+    graphs = dataset_graphs(ds)
+    lab = _supplied_labels(ds.ranges(), graphs, gaf, 1)
+    o, _ = assert_cpu_matches_py(ds.ranges(), graphs, gaf, labels=lab)
+    assert not o.label_out_of_range
+    np.testing.assert_array_equal(o.labels(), lab)
+    ref = run_cpu_oracle(ds.ranges(), graphs, gaf)
+    assert o.species_counts()[:, 0].sum() < ref.species_counts()[:, 0].sum()
+    # rows moved to a species whose range does not hold their walk are reported and treated as "U"
+    lab2 = _supplied_labels(ds.ranges(), graphs, gaf, 2, p_wrong=0.02)
+    o2, _ = assert_cpu_matches_py(ds.ranges(), graphs, gaf, labels=lab2)
+    assert o2.label_out_of_range
+
+
 def test_oracle_invariant_under_record_permutation_and_thread_count():
     ds = synth.Dataset(9, [2000, 600], [5, 2])
     gaf = ds.gaf(4, 0, 2000, NASTY)
