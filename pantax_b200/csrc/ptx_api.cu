@@ -91,6 +91,7 @@ struct Chunk {
     int64_t labels_cap = 0;
     int64_t n_records = 0;
     int64_t row_base = 0;  // GAF rows ingested before this chunk
+    uint32_t long_mode = 0;
     bool ingested = false;  // classify pass done
     bool covered = false;   // coverage pass done against the current graph
     cudaEvent_t copied = nullptr;
@@ -123,6 +124,7 @@ struct ptx_ctx {
     int64_t ds_records = 0;  // upper bound of ids inserted
     int64_t reserve_records = 0;
     int force_rows = 0;  // PTX_TILE_ROWS env override (tests exercise every tile size)
+    int force_long = -1; // PTX_LONG_MODE env override: 0/1 = never/always use the long-line kernel (tests)
     uint64_t* d_total = nullptr;  // scratch scalar
     // records
     std::vector<Chunk> chunks;
@@ -268,6 +270,7 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.padded_bytes = ch.padded;
     a.n_tiles = ch.n_tiles;
     a.rows_per_warp = ch.rows;
+    a.long_mode = ch.long_mode;
     a.micro_base = ch.tile_base;
     a.labels = ch.labels;
     a.labels_in = ctx->labels_in_n > 0 ? ctx->d_labels_in + ch.row_base : nullptr;
@@ -406,6 +409,9 @@ int chunk_process(ptx_ctx* ctx, Chunk& ch) {
         int rows = (int)(0.97 * INGEST_THREADS * mean_line / MICRO);
         ch.rows = (uint32_t)std::min(8, std::max(1, rows));
         if (ctx->force_rows > 0) ch.rows = (uint32_t)std::min(8, ctx->force_rows);
+        // long lines (HiFi/ONT walks): even the largest tile holds fewer lines than threads -> one warp per record
+        ch.long_mode = mean_line >= LONG_LINE_BYTES ? 1u : 0u;
+        if (ctx->force_long >= 0) ch.long_mode = (uint32_t)ctx->force_long;
         const size_t tile = (size_t)ch.rows * MICRO;
         ch.n_tiles = (uint32_t)((ch.n + tile - 1) / tile);
     }
@@ -705,6 +711,7 @@ int ptx_create(int device, ptx_ctx** out) {
     if (!ctx) return PTX_E_NOMEM;
     ctx->device = device;
     if (const char* e = getenv("PTX_TILE_ROWS")) ctx->force_rows = atoi(e);
+    if (const char* e = getenv("PTX_LONG_MODE")) ctx->force_long = atoi(e) ? 1 : 0;
     if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;

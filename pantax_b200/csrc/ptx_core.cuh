@@ -386,6 +386,45 @@ PTX_HD bool parse_record(const uint8_t* b, uint32_t p, uint32_t lim, RecParse& r
     return p + 1u < lim;
 }
 
+// parse_record in three pieces, for callers that decode column 6 themselves (the warp-cooperative walk decode of
+// the long-read kernel).  Same scanners, same results: parse_head = columns 1-5 (p ends at the first byte of
+// column 6 if T_TAB is returned), parse_tail = columns 7-12 starting at p with the terminator `st` of column 6.
+PTX_HD int parse_head(const uint8_t* b, uint32_t& p, RecParse& r, uint32_t mask) {
+    int st;
+    {
+        IdHasher H;
+        for (;;) {
+            const uint8_t c = b[p];
+            if (c <= '\r') {
+                st = term_at(b, p, c);
+                if (st >= 0) break;
+            }
+            H.byte(c);
+            ++p;
+        }
+        r.h = H.finish();
+        if (st == T_TAB) ++p;
+    }
+    PTX_RECONVERGE(mask);
+    if (st == T_TAB) st = parse_int_field(b, p, r.qlen);  // column 2
+    PTX_RECONVERGE(mask);
+    if (st == T_TAB) st = skip_fields(b, p, 3);  // columns 3,4,5
+    PTX_RECONVERGE(mask);
+    return st;
+}
+PTX_HD void parse_tail(const uint8_t* b, uint32_t& p, int st, RecParse& r, uint32_t mask) {
+    if (st == T_TAB) st = parse_int_field(b, p, r.c7);
+    PTX_RECONVERGE(mask);
+    if (st == T_TAB) st = parse_int_field(b, p, r.c8);
+    PTX_RECONVERGE(mask);
+    if (st == T_TAB) st = parse_int_field(b, p, r.c9);
+    PTX_RECONVERGE(mask);
+    if (st == T_TAB) st = skip_fields(b, p, 2);  // columns 10, 11
+    PTX_RECONVERGE(mask);
+    if (st == T_TAB) parse_int_field(b, p, r.mapq);  // column 12; anything after it is ignored
+    PTX_RECONVERGE(mask);
+}
+
 // profile.rs:787-919 for one coverage-eligible read of species `label`.
 // Sink concept:
 //   NodeInfo info(uint32_t g);  void add_bases(uint32_t g, int64_t v);

@@ -23,6 +23,7 @@ constexpr uint32_t OVER = 2048;
 constexpr uint32_t PRE = 256;  // keeps `text` 256-byte aligned inside a cudaMalloc'ed buffer
 constexpr int INGEST_THREADS = 256;
 constexpr uint32_t REC_CAP = 1024;  // record starts kept in smem per round
+constexpr double LONG_LINE_BYTES = 320.0;  // mean line length from which a chunk is parsed by k_ingest<LONG>
 constexpr uint32_t HIST_SLOTS_LOG2 = 7;  // per-tile species-count accumulators in shared memory (multi-species runs)
 constexpr uint32_t HIST_SLOTS = 1u << HIST_SLOTS_LOG2;
 constexpr uint32_t STASH_CAP = 16;  // walk nodes per record kept in smem between the parse and the coverage pass
@@ -73,6 +74,7 @@ struct IngestArgs {
     uint64_t padded_bytes; // bytes readable from `text` (text + newline padding)
     uint32_t n_tiles;
     uint32_t rows_per_warp;      // tile = rows_per_warp * 4096 bytes
+    uint32_t long_mode;          // long lines: warp-cooperative walk decode (k_ingest<true>)
     const uint64_t* micro_base;  // [n_micro] exclusive record prefix per micro-tile within the chunk (MODE_CLASSIFY)
     uint32_t* labels;           // [chunk records]
     const uint32_t* labels_in;  // [chunk records] caller-supplied species labels (ptx_ingest_labels), or null: classify

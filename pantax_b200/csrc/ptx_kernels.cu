@@ -481,6 +481,116 @@ struct DevSink {
     __device__ __forceinline__ void error_start_gt_len(uint32_t label) { atomicOr(a.err + label, 1u); }
 };
 
+// ---- warp-cooperative decode of the walk column (long reads: a tile holds few lines, each with a walk of tens
+// to hundreds of nodes).  The 32 lanes take 4 bytes each of a 128-byte window of the column; byte classes come
+// from SWAR masks, node starts from ballots, every lane that owns a start converts that digit run.
+__device__ __forceinline__ uint32_t eq_mask4(uint32_t w, uint32_t rep) {  // 0x80 in every byte of w equal to the byte of rep
+    const uint32_t y = w ^ rep;
+    return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t digit_mask4(uint32_t w) {  // 0x80 in every byte that is '0'..'9'
+    const uint32_t t = w ^ 0x30303030u;
+    const uint32_t bad = (t & 0xF0F0F0F0u) | (((t & 0x0F0F0F0Fu) + 0x06060606u) & 0x10101010u);
+    return ~(((bad & 0x7f7f7f7fu) + 0x7f7f7f7fu) | bad) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t nib4(uint32_t m) { return ((m >> 7) * 0x10204080u) >> 28; }  // bit i = byte i
+
+struct CoopCount { uint32_t W, end; int term; bool beyond; };
+// Column 6 starting at stage[p6]: number of digit runs, position and class of its terminator ('\t', '\n' or the
+// '\r' of "\r\n", as term_at), `beyond` if it is not inside the window (lim = staged bytes, sentinel '\n' behind).
+__device__ __forceinline__ CoopCount coop_walk_count(const uint8_t* stage, uint32_t p6, uint32_t lim, uint32_t lane) {
+    uint32_t pos = p6 & ~3u, W = 0, carry = 0;
+    for (;;) {
+        const uint32_t my = pos + 4u * lane;
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(stage + my);
+        uint32_t dn = nib4(digit_mask4(w));
+        uint32_t tn = nib4(eq_mask4(w, 0x09090909u) | eq_mask4(w, 0x0a0a0a0au));
+        if (my < p6) { dn &= 0xFu << (p6 - my); tn &= 0xFu << (p6 - my); }  // lane 0 of the first window only
+        const unsigned tb = __ballot_sync(0xffffffffu, tn != 0u);
+        uint32_t endpos = 0;
+        if (tb) {
+            const uint32_t L = __ffs(tb) - 1;
+            const uint32_t bit = __ffs(__shfl_sync(0xffffffffu, tn, L)) - 1;
+            endpos = pos + 4u * L + bit;
+            if (lane > L) dn = 0; else if (lane == L) dn &= (1u << bit) - 1u;
+        }
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, dn >> 3, 1);
+        const uint32_t sn = dn & ~((dn << 1) | (lane == 0 ? carry : (prev & 1u))) & 0xFu;  // first digit of a run
+        const uint32_t c = __popc(sn);
+        W += __popc(__ballot_sync(0xffffffffu, c >= 1u)) + __popc(__ballot_sync(0xffffffffu, c == 2u));
+        if (tb) {
+            CoopCount r;
+            r.W = W;
+            r.beyond = endpos + 1u >= lim;
+            r.term = stage[endpos] == '\t' ? T_TAB : T_EOL;
+            if (r.term == T_EOL && endpos > p6 && stage[endpos - 1] == '\r') --endpos;
+            r.end = endpos;
+            return r;
+        }
+        carry = __shfl_sync(0xffffffffu, dn >> 3, 31) & 1u;
+        pos += 128u;
+    }
+}
+
+struct CoopWalk { uint32_t vmin, vmax; bool monotone, big; };
+// Decodes the digit runs of stage[p6, end) to dst[0..W) in walk order (runs of <= 9 digits; `big` reports a longer
+// one, whose record is then redone by the scalar 64-bit scanner), with min, max and strict monotonicity.
+__device__ __forceinline__ CoopWalk coop_walk_decode(const uint8_t* stage, uint32_t p6, uint32_t end, uint32_t* dst, uint32_t lane) {
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t Wb = 0, carry = 0, carry_last = 0, mn = 0xFFFFFFFFu, mx = 0;
+    bool inc = true, dec = true, big = false;
+    for (uint32_t pos = p6 & ~3u; pos < end; pos += 128u) {
+        const uint32_t my = pos + 4u * lane;
+        uint32_t dn = 0;
+        if (my < end) {
+            dn = nib4(digit_mask4(*reinterpret_cast<const uint32_t*>(stage + my)));
+            if (my < p6) dn &= 0xFu << (p6 - my);
+            if (end - my < 4u) dn &= (1u << (end - my)) - 1u;
+        }
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, dn >> 3, 1);
+        uint32_t sn = dn & ~((dn << 1) | (lane == 0 ? carry : (prev & 1u))) & 0xFu;
+        const uint32_t c = __popc(sn);  // 0, 1 or 2 node ids start in these 4 bytes
+        const unsigned b1 = __ballot_sync(0xffffffffu, c >= 1u), b2 = __ballot_sync(0xffffffffu, c == 2u);
+        const uint32_t ord = Wb + __popc(b1 & lt) + __popc(b2 & lt);
+        uint32_t first_v = 0, last_v = 0;
+        for (uint32_t k = 0; k < c; ++k) {
+            uint32_t qb = my + __ffs(sn) - 1u;
+            sn &= sn - 1u;
+            uint32_t d = (uint32_t)stage[qb] - (uint32_t)'0', v = 0, nd = 0;
+            while (d <= 9u && nd < 9u) {
+                v = v * 10u + d;
+                ++nd;
+                d = (uint32_t)stage[++qb] - (uint32_t)'0';
+            }
+            if (d <= 9u) big = true;
+            dst[ord + k] = v;
+            mn = v < mn ? v : mn;
+            mx = v > mx ? v : mx;
+            if (k == 0) first_v = v;
+            else { if (v <= last_v) inc = false; if (v >= last_v) dec = false; }
+            last_v = v;
+        }
+        // the id before this lane's first one: last id of the nearest lower lane that has any, else of the previous window
+        const unsigned below = b1 & lt;
+        const uint32_t pv_lane = __shfl_sync(0xffffffffu, last_v, below ? 31u - (uint32_t)__clz(below) : 0u);
+        if (c && (below || Wb)) {
+            const uint32_t pv = below ? pv_lane : carry_last;
+            if (first_v <= pv) inc = false;
+            if (first_v >= pv) dec = false;
+        }
+        const uint32_t top = __shfl_sync(0xffffffffu, last_v, b1 ? 31u - (uint32_t)__clz(b1) : 0u);
+        if (b1) carry_last = top;
+        Wb += __popc(b1) + __popc(b2);
+        carry = __shfl_sync(0xffffffffu, dn >> 3, 31) & 1u;
+    }
+    CoopWalk r;
+    r.vmin = __reduce_min_sync(0xffffffffu, mn);
+    r.vmax = __reduce_max_sync(0xffffffffu, mx);
+    r.monotone = __all_sync(0xffffffffu, inc) || __all_sync(0xffffffffu, dec);
+    r.big = __any_sync(0xffffffffu, big);
+    return r;
+}
+
 // rare path: the record did not fit in the staged window - parse it from global memory.
 // Works on its own RecParse so that the caller's stays in registers.
 __device__ __noinline__ void parse_record_global(const uint8_t* b, uint32_t p, uint32_t lim, RecParse* out) {
@@ -489,7 +599,8 @@ __device__ __noinline__ void parse_record_global(const uint8_t* b, uint32_t p, u
     *out = r;
 }
 
-__global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a) {
+template <bool LONG>
+__global__ void __launch_bounds__(INGEST_THREADS, LONG ? 3 : 4) k_ingest(const IngestArgs a) {
     constexpr int MODE = MODE_CLASSIFY;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -673,8 +784,10 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
 
         // ---- one thread per record; the lanes of a warp move through the columns in lock-step
         for (uint32_t k0 = 0; k0 < n_round; k0 += INGEST_THREADS) {
-            const bool slot = k0 + tid < n_round;
-            const uint32_t k = slot ? order[k0 + tid] : 0u;
+            // LONG: records are dealt round-robin to the warps (a tile holds far fewer lines than threads)
+            const uint32_t q = LONG ? k0 + lane * (INGEST_THREADS / 32u) + warp : k0 + tid;
+            const bool slot = q < n_round;
+            const uint32_t k = slot ? order[q] : 0u;
             const uint32_t p = slot ? rec_start[k] : 0u;
             const bool has = slot && valid_first(stage, p);  // not an empty line / '@' comment (rcls.rs:123)
             const uint32_t pmask = __ballot_sync(0xffffffffu, has);
@@ -682,14 +795,84 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
             r.W = 0; r.mapq = NULL_I64; r.qlen = NULL_I64; r.stashed = false;
             uint32_t label = LABEL_U;
             const uint8_t* b = stage;
-            if (has) {
-                if (!parse_record(stage, p, stage_bytes, r, pmask, stash + tid, INGEST_THREADS, STASH_CAP)) {
-                    // the columns run past the staged window (at most one record per tile; long lines only)
+            uint32_t node_off = 0;
+            bool slow = false;  // LONG: this record goes through the scalar parser on the global copy of its line
+            if constexpr (LONG) {
+                // columns 1-5 per thread, column 6 by the whole warp one record at a time, columns 7-12 per thread
+                r.qlen = r.c7 = r.c8 = r.c9 = r.mapq = NULL_I64;
+                r.vmin = INT64_MAX; r.vmax = -1; r.path_null = true; r.monotone = true;
+                uint32_t pp = p;
+                int st = T_EOL;
+                if (has) {
+                    st = parse_head(stage, pp, r, pmask);
+                    if (pp + 1u >= stage_bytes) slow = true;
+                }
+                __syncwarp();
+                r.path_pos = r.path_end = pp;
+                bool want6 = has && !slow && st == T_TAB;
+                uint32_t w_up = 0, end6 = pp;
+                int term6 = st;
+                for (unsigned m = __ballot_sync(0xffffffffu, want6); m; m &= m - 1u) {
+                    const int rl = __ffs(m) - 1;
+                    const CoopCount cc = coop_walk_count(stage, __shfl_sync(0xffffffffu, pp, rl), stage_bytes, lane);
+                    if ((int)lane == rl) { w_up = cc.W; end6 = cc.end; term6 = cc.term; slow = cc.beyond; }
+                }
+                want6 = want6 && !slow;
+                {  // node slots of every record decoded here (eligible or not: a walk node takes >= 2 text bytes)
+                    const uint32_t wa = want6 ? w_up : 0u;
+                    uint32_t x = wa;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                        if (lane >= (uint32_t)d) x += y;
+                    }
+                    const uint32_t wtot = __shfl_sync(0xffffffffu, x, 31);
+                    uint32_t nbase = 0;
+                    if (lane == 0 && wtot) nbase = atomicAdd(a.cursors + 1, wtot);
+                    nbase = __shfl_sync(0xffffffffu, nbase, 0);
+                    node_off = nbase + x - wa;
+                }
+                for (unsigned m = __ballot_sync(0xffffffffu, want6 && w_up != 0u); m; m &= m - 1u) {
+                    const int rl = __ffs(m) - 1;
+                    const CoopWalk cw = coop_walk_decode(stage, __shfl_sync(0xffffffffu, pp, rl), __shfl_sync(0xffffffffu, end6, rl),
+                                                         a.nodes + __shfl_sync(0xffffffffu, node_off, rl), lane);
+                    if ((int)lane == rl) {
+                        r.W = w_up;
+                        r.vmin = (int64_t)cw.vmin; r.vmax = (int64_t)cw.vmax;
+                        r.monotone = cw.monotone;
+                        if (cw.big) slow = true;  // a digit run of 10+ digits: generic 64-bit scan
+                    }
+                }
+                want6 = want6 && !slow;
+                const uint32_t tmask = __ballot_sync(0xffffffffu, want6);
+                if (want6) {
+                    r.path_end = end6;
+                    r.path_null = (end6 - pp == 1u) && (stage[pp] == '*');
+                    uint32_t pt = end6;
+                    if (term6 == T_TAB) ++pt;
+                    parse_tail(stage, pt, term6, r, tmask);
+                    if (pt + 1u >= stage_bytes) slow = true;
+                }
+                __syncwarp();
+                if (has && slow) {
                     RecParse tmp;
                     b = gtile;
                     parse_record_global(gtile, p, glim, &tmp);
                     r = tmp;
                 }
+                __syncwarp();
+            } else {
+                if (has) {
+                    if (!parse_record(stage, p, stage_bytes, r, pmask, stash + tid, INGEST_THREADS, STASH_CAP)) {
+                        // the columns run past the staged window (at most one record per tile; long lines only)
+                        RecParse tmp;
+                        b = gtile;
+                        parse_record_global(gtile, p, glim, &tmp);
+                        r = tmp;
+                    }
+                }
+            }
+            if (has) {
                 const uint32_t row = rec_base + valid_prev + k - (inv_total ? (uint32_t)inv_pre[k] : 0u);  // GAF row within the chunk
                 if (a.labels_in) {  // strain-only resume: the species column of reads_classification.tsv
                     label = a.labels_in[row];
@@ -761,19 +944,24 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
             const bool labelled = has && label != LABEL_U;
             const bool eligible = labelled && !r.path_null && r.c7 != NULL_I64 && r.c8 != NULL_I64 && r.c9 != NULL_I64;  // profile.rs:380-399
             const uint32_t wcnt = eligible ? r.W : 0u;
-            uint32_t x = wcnt;  // node slots: warp scan, one atomicAdd per warp on the chunk's node cursor
+            if constexpr (LONG) {
+                // the cooperative decode already wrote the walk at node_off; the scalar fallback takes its own slots
+                if (slow && wcnt) node_off = atomicAdd(a.cursors + 1, wcnt);
+            } else {
+                uint32_t x = wcnt;  // node slots: warp scan, one atomicAdd per warp on the chunk's node cursor
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-                if (lane >= (uint32_t)d) x += y;
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                    if (lane >= (uint32_t)d) x += y;
+                }
+                const uint32_t wtot = __shfl_sync(0xffffffffu, x, 31);
+                uint32_t nbase = 0;
+                if (lane == 0 && wtot) nbase = atomicAdd(a.cursors + 1, wtot);
+                nbase = __shfl_sync(0xffffffffu, nbase, 0);
+                node_off = nbase + x - wcnt;
             }
-            const uint32_t wtot = __shfl_sync(0xffffffffu, x, 31);
-            uint32_t nbase = 0;
-            if (lane == 0 && wtot) nbase = atomicAdd(a.cursors + 1, wtot);
-            nbase = __shfl_sync(0xffffffffu, nbase, 0);
-            const uint32_t node_off = nbase + x - wcnt;
             if (slot) {
-                const uint32_t e = slot_base_s + k0 + tid;
+                const uint32_t e = slot_base_s + q;
                 uint32_t wf = wcnt & RM_W_MASK;
                 if (labelled) wf |= RM_LABELLED;
                 if (eligible) wf |= RM_ELIGIBLE;
@@ -784,11 +972,11 @@ __global__ void __launch_bounds__(INGEST_THREADS, 4) k_ingest(const IngestArgs a
                     if (eligible) a.meta_a[e] = make_longlong2(r.c8, r.c9);
                 }
             }
-            if (wcnt) {
+            if (wcnt && (!LONG || slow)) {
                 uint32_t* dst = a.nodes + node_off;
-                if (r.stashed) {
+                if (!LONG && r.stashed) {
                     for (uint32_t i = 0; i < wcnt; ++i) dst[i] = stash[i * INGEST_THREADS + tid];
-                } else {  // walk longer than the stash: decode it again (long reads)
+                } else {  // walk longer than the stash: decode it again
                     WalkIter it{b, r.path_pos, r.path_end};
                     int64_t m;
                     for (uint32_t i = 0; i < wcnt; ++i) { it.next(m); dst[i] = (uint32_t)m; }
@@ -1496,10 +1684,12 @@ void launch_ingest(const IngestArgs& a, cudaStream_t st) {
                         (a.ranges.S > 1 ? hist_bytes : 0);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_ingest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        cudaFuncSetAttribute(k_ingest<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        cudaFuncSetAttribute(k_ingest<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         configured = true;
     }
-    k_ingest<<<a.n_tiles, INGEST_THREADS, smem, st>>>(a);
+    if (a.long_mode) k_ingest<true><<<a.n_tiles, INGEST_THREADS, smem, st>>>(a);
+    else k_ingest<false><<<a.n_tiles, INGEST_THREADS, smem, st>>>(a);
     PTX_LAUNCHED();
 }
 void launch_apply(const IngestArgs& a, uint32_t n_entries, int mode, cudaStream_t st) {

@@ -99,8 +99,11 @@ def test_gpu_equal_length_rule_long_reads():
     assert eq is False
 
 
-def test_gpu_dialect_edges_and_start_beyond_node_error():
+@pytest.mark.parametrize("long_mode", [None, "1"])
+def test_gpu_dialect_edges_and_start_beyond_node_error(long_mode, monkeypatch):
     from gpu_common import gpu_vs_oracle
+    if long_mode:
+        monkeypatch.setenv("PTX_LONG_MODE", long_mode)   # the same lines through the warp-cooperative long-line kernel
     from test_core_host import test_core_handcrafted_dialect_edges  # noqa: F401  (same inputs)
     ranges = [("a", 1, 50), ("b", 51, 80)]
     graphs = [(np.full(50, 7, dtype=np.int64), [np.arange(50, dtype=np.uint64), np.array([3, 2, 1, 2, 3, 9], dtype=np.uint64)], ["p", "q"]),
@@ -241,17 +244,71 @@ def test_gpu_result_is_invariant_under_record_permutation():
         np.testing.assert_array_equal(a.trio_bases(s), b.trio_bases(s))
 
 
-@pytest.mark.parametrize("rows", [1, 3, 8])
-def test_gpu_every_tile_size_gives_the_same_answer(rows, monkeypatch):
+@pytest.mark.parametrize("rows,long_mode", [(1, "0"), (3, "0"), (8, "0"), (2, "1"), (8, "1")])
+def test_gpu_every_tile_size_gives_the_same_answer(rows, long_mode, monkeypatch):
     """The ingest tile is rows*4 KB (chosen from the mean line length); force the extremes.  rows=1 makes
-    tiles with ~37 records, rows=8 tiles with more records than threads (second pass)."""
+    tiles with ~37 records, rows=8 tiles with more records than threads (second pass).  long_mode forces the
+    thread-per-record kernel ("0") or the warp-cooperative long-line kernel ("1") on both read types."""
     from gpu_common import gpu_vs_oracle
     monkeypatch.setenv("PTX_TILE_ROWS", str(rows))
+    monkeypatch.setenv("PTX_LONG_MODE", long_mode)
     ds = synth.Dataset(61, [20000, 6000], [6, 3])
     gaf = ds.gaf(4, 0, 40000, NASTY_DUP)
     gpu_vs_oracle(ds.ranges(), dataset_graphs(ds), gaf)
     gl = ds.gaf(6, 0, 2000, synth.GafParams(long_reads=True, id_pair_suffix=False))
     gpu_vs_oracle(ds.ranges(), dataset_graphs(ds), gl)
+
+
+@pytest.mark.parametrize("long_mode", ["0", "1", None])
+def test_gpu_long_walks_window_edges(long_mode, monkeypatch):
+    """Walk columns built to hit the edges of the cooperative decode: runs crossing the 128-byte windows, 1-9 digit
+    ids, ids of 10-18 digits (64-bit scan), runs of more than 18 digits (dropped, rcls.rs:244), an empty column,
+    "*", a line that ends after column 6 with CRLF, separators other than <>, and lines far longer than the staged
+    window (parsed from global memory)."""
+    from gpu_common import gpu_vs_oracle
+    if long_mode is not None:
+        monkeypatch.setenv("PTX_LONG_MODE", long_mode)
+    n = 120000
+    ranges = [("a", 1, n), ("b", n + 1, n + 5000)]
+    rng = np.random.default_rng(5)
+    paths = [np.arange(0, n, 7, dtype=np.uint64), np.arange(n - 1, 0, -11).astype(np.uint64), rng.integers(0, n, 5000).astype(np.uint64)]
+    graphs = [(rng.integers(1, 30, n).astype(np.int64), paths, ["h1", "h2", "h3"]),
+              (np.full(5000, 9, dtype=np.int64), [np.arange(5000, dtype=np.uint64)], ["k"])]
+
+    def line(i, ids, c8=0, extra=b"\t60\t60\t60\ttp:A:P", seps=b"><"):
+        walk = b"".join(bytes([seps[j % len(seps)]]) + str(int(v)).encode() for j, v in enumerate(ids))
+        return b"lr%d\t15000\t0\t15000\t+\t%s\t%d\t%d\t%d%s" % (i, walk, 20 * len(ids), c8, 15 * len(ids) + 3, extra)
+
+    lines = []
+    for i in range(400):  # random walks: lengths 1..600 nodes, ids of 1-6 digits, with repeats now and then
+        w = int(rng.integers(1, 600))
+        mode = i % 4
+        if mode == 0:
+            ids = np.sort(rng.choice(n, w, replace=False)) + 1          # strictly increasing
+        elif mode == 1:
+            ids = np.sort(rng.choice(n, w, replace=False))[::-1] + 1    # strictly decreasing
+        elif mode == 2:
+            ids = rng.integers(1, 1000, w)                               # repeats: first-occurrence rule
+        else:
+            ids = rng.integers(1, 10 ** int(rng.integers(1, 6)), w)
+        lines.append(line(i, ids, c8=int(rng.integers(0, 2))))
+    lines.append(line(1000, [5, 123456789012, 7]))                       # 12-digit id: not in any range -> U
+    lines.append(line(1001, [5, 6], extra=b""))                          # line ends after column 9
+    lines.append(b"lr1002\t100\t0\t100\t+\t>5>6>7\r")                   # ends after column 6, CRLF
+    lines.append(b"lr1003\t100\t0\t100\t+\t>5>6>7")                      # ends after column 6
+    lines.append(b"lr1004\t100\t0\t100\t+\t*\t0\t0\t0\t0\t0\t60")
+    lines.append(b"lr1005\t100\t0\t100\t+\t\t0\t0\t0\t0\t0\t60")           # empty column
+    lines.append(b"lr1006\t100\t0\t100\t+\t>5>" + b"9" * 19 + b">6\t30\t0\t20\t0\t0\t60")   # 19-digit run dropped: walk 5,6
+    lines.append(line(1007, [11, 12, 13, 14], seps=b"_x"))               # other separators
+    lines.append(line(1008, rng.integers(1, n, 9000)))                   # ~60 KB line: beyond any staged window
+    lines.append(line(1009, np.arange(n + 1, n + 4000)))                 # long monotone walk in species b
+    lines.append(line(1010, [n, n + 1]))                                 # spans two species -> U
+    for pad in range(0, 130, 9):                                         # shift the walk start over every byte phase
+        lines.append(b"p%s\t100\t0\t100\t+\t%s\t900\t0\t800\t0\t0\t60" % (b"x" * pad, b"".join(b">%d" % v for v in range(100 + pad, 160 + pad))))
+    order = rng.permutation(len(lines))
+    gaf = b"\n".join(lines[i] for i in order) + b"\n"
+    ctx, o = gpu_vs_oracle(ranges, graphs, gaf)
+    assert ctx.species_counts()[0, 0] > 400 and o.species_error(0) == 0 and o.species_error(1) == 0
 
 
 def test_gpu_long_read_filter_matches_oracle():
