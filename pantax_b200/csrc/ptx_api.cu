@@ -125,6 +125,7 @@ struct ptx_ctx {
     int64_t reserve_records = 0;
     int force_rows = 0;  // PTX_TILE_ROWS env override (tests exercise every tile size)
     int force_long = -1; // PTX_LONG_MODE env override: 0/1 = never/always use the long-line kernel (tests)
+    int64_t test_box_cap = 0;  // PTX_TEST_BOX_CAP env: first outbox capacity (tests force the overflow/restart path of the exchange)
     uint64_t* d_total = nullptr;  // scratch scalar
     // records
     std::vector<Chunk> chunks;
@@ -139,15 +140,14 @@ struct ptx_ctx {
     std::vector<Chunk> pool;
     uint8_t* scratch = nullptr;
     size_t scratch_cap = 0, scratch_off = 0;
-    uint8_t* scratch2 = nullptr;
-    size_t scratch2_cap = 0;
     // asynchronous id-group exchange (multi-GPU): boxes filled by k_apply, sent on a side stream during the coverage pass
     cudaStream_t xs = nullptr;
     cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;
-    ulonglong2 *outbox = nullptr, *inbox = nullptr, *x_own = nullptr;
-    unsigned long long* out_cursor = nullptr;
-    uint64_t box_cap = 0, x_own_cap = 0;
-    uint64_t xchg_box_cap = 0;  // per-owner outbox capacity of the id-group exchange (sticky)
+    ulonglong2 *outbox = nullptr, *inbox = nullptr;
+    unsigned long long* out_cursor = nullptr;  // [P] box cursors, [P] this rank's box capacity, then exchange scratch
+    uint64_t box_cap = 0, inbox_cap = 0;
+    std::vector<unsigned long long> box_sent, recv_done;  // per peer: entries already exchanged by an earlier ptx_finalize
+    int64_t ds_entries_bound = 0;  // upper bound of the entries in the id set (own records + merged foreign ids + returned mixed ids)
     // timing
     std::vector<EvPair> ev_count, ev_ingest, ev_apply, ev_final;
     // multi-GPU
@@ -244,14 +244,15 @@ uint32_t log2_ceil(uint64_t v) {
     return l;
 }
 
-int ds_ensure(ptx_ctx* ctx, int64_t more_records) {
-    const int64_t need = std::max<int64_t>(ctx->ds_records + more_records, ctx->reserve_records);
+// grow (and rehash) the id set so that `entries` fit at load <= 1/2
+int ds_ensure_total(ptx_ctx* ctx, int64_t entries) {
+    const int64_t need = std::max<int64_t>(entries, ctx->reserve_records);
     uint64_t want = 1ull << std::max<uint32_t>(16, log2_ceil((uint64_t)need * 2 + 1));
     if (want <= ctx->ds_cap) return PTX_OK;
     ulonglong2* nd = nullptr;
     CU(cudaMalloc((void**)&nd, want * sizeof(ulonglong2)));
     CU(cudaMemsetAsync(nd, 0, want * sizeof(ulonglong2), ctx->st));
-    if (ctx->d_ds && ctx->ds_records > 0)
+    if (ctx->d_ds && (ctx->ds_records > 0 || ctx->ds_entries_bound > 0))
         launch_ds_rehash(ctx->d_ds, ctx->ds_cap, nd, 64 - log2_ceil(want), want - 1, ctx->st);
     if (ctx->d_ds) {
         CU(cudaStreamSynchronize(ctx->st));
@@ -261,6 +262,7 @@ int ds_ensure(ptx_ctx* ctx, int64_t more_records) {
     ctx->ds_cap = want;
     return PTX_OK;
 }
+int ds_ensure(ptx_ctx* ctx, int64_t more_records) { return ds_ensure_total(ctx, std::max(ctx->ds_records, ctx->ds_entries_bound) + more_records); }
 
 IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     IngestArgs a;
@@ -283,6 +285,7 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.out_cursor = ctx->out_cursor;
     a.box_cap = ctx->box_cap;
     a.n_ranks = (uint32_t)ctx->n_ranks;
+    a.rank = (uint32_t)ctx->rank;
     a.ranges = ranges_view(ctx);
     a.hist = ctx->d_hist;
     a.ds = ctx->d_ds;
@@ -494,56 +497,61 @@ int nccl_check(ptx_ctx* ctx, int r, const char* what) {
 // records/P each, 25 % slack; k_apply flags an overflow and ptx_finalize then falls back to the table scan)
 int xchg_ensure(ptx_ctx* ctx, int64_t records) {
     const uint64_t P = (uint64_t)ctx->n_ranks;
-    const uint64_t need = (uint64_t)records / P + (uint64_t)records / (4 * P) + 4096;
+    uint64_t need = (uint64_t)records / P + (uint64_t)records / (4 * P) + 4096;
+    if (ctx->test_box_cap > 0 && ctx->box_cap == 0) need = (uint64_t)ctx->test_box_cap;
     if (!ctx->xs) {
         CU(cudaStreamCreateWithFlags(&ctx->xs, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&ctx->ev_x0, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_x1, cudaEventDisableTiming));
-        int rc = dalloc(ctx, &ctx->out_cursor, 64);
+        // [0,P) box cursors, [P] "a box overflowed", then the all-gathered (P+1) x P matrix and 2P merge parameters
+        int rc = dalloc(ctx, &ctx->out_cursor, (size_t)(P + 1) * (P + 1) + 2 * P + 8);
         if (rc) return rc;
+        ctx->box_sent.assign(P, 0);
+        ctx->recv_done.assign(P, 0);
     }
     if (need <= ctx->box_cap) return PTX_OK;
     const uint64_t cap = need + need / 8;
-    ulonglong2 *nout = nullptr, *nin = nullptr, *nown = nullptr;
+    ulonglong2* nout = nullptr;
     CU(cudaStreamSynchronize(ctx->st));
     CU(cudaStreamSynchronize(ctx->xs));
     CU(cudaMalloc((void**)&nout, P * cap * sizeof(ulonglong2)));
-    CU(cudaMalloc((void**)&nin, P * cap * sizeof(ulonglong2)));
-    const uint64_t ocap = 1ull << std::max<uint32_t>(10, log2_ceil(P * cap + P * cap / 2));
-    CU(cudaMalloc((void**)&nown, ocap * sizeof(ulonglong2)));
     if (ctx->outbox)  // keep what earlier chunks already wrote
         for (uint64_t r = 0; r < P; ++r)
             CU(cudaMemcpyAsync(nout + r * cap, ctx->outbox + r * ctx->box_cap, ctx->box_cap * sizeof(ulonglong2), cudaMemcpyDeviceToDevice, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
-    dfree(ctx->outbox); dfree(ctx->inbox); dfree(ctx->x_own);
-    ctx->outbox = nout; ctx->inbox = nin; ctx->x_own = nown;
+    dfree(ctx->outbox);
+    ctx->outbox = nout;
     ctx->box_cap = cap;
-    ctx->x_own_cap = ocap;
+    // the capacity travels with the cursors in the all-gather of exchange_begin (a fill above it = entries dropped)
+    CU(cudaMemcpy(ctx->out_cursor + P, &ctx->box_cap, sizeof(unsigned long long), cudaMemcpyHostToDevice));
     return PTX_OK;
 }
 
-// ids whose merged state on their owner rank is DS_MIXED go back to every rank (rare path; synchronising)
-int return_mixed_ids(ptx_ctx* ctx, const ulonglong2* own, uint64_t ocap, cudaStream_t st) {
+// ids whose merged state on their owner rank is DS_MIXED go back to every rank (rare path; synchronising).  A rank
+// keeps only the ids it owns, so the returned ids are inserted (as MIXED) where they are not present.
+int return_mixed_ids(ptx_ctx* ctx, cudaStream_t st) {
     const int P = ctx->n_ranks;
     int rc;
     unsigned long long* d_tmp = nullptr;
     if ((rc = dalloc(ctx, &d_tmp, (size_t)P + 2))) return rc;
     unsigned long long* d_nmix = d_tmp;
     unsigned long long* d_allmix = d_tmp + 1;
-    launch_ds_collect_mixed(own, ocap, d_nmix, nullptr, 0, st);
+    launch_ds_collect_mixed(ctx->d_ds, ctx->ds_cap, d_nmix, nullptr, 0, st);
     if ((rc = nccl_check(ctx, g_nccl.AllGather(d_nmix, d_allmix, 1, ncclUint64, ctx->comm, st), "ncclAllGather(mixed counts)"))) return rc;
     std::vector<unsigned long long> nmix(P);
     CU(cudaMemcpyAsync(nmix.data(), d_allmix, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    unsigned long long mx = 0;
-    for (auto v : nmix) mx = std::max(mx, v);
+    unsigned long long mx = 0, total = 0;
+    for (auto v : nmix) { mx = std::max(mx, v); total += v; }
     if (mx > 0) {
         ulonglong2* mine = nullptr;
         ulonglong2* everyone = nullptr;
         if ((rc = dalloc(ctx, &mine, (size_t)mx)) || (rc = dalloc(ctx, &everyone, (size_t)mx * P))) return rc;
         CU(cudaMemsetAsync(d_nmix, 0, sizeof(unsigned long long), st));
-        launch_ds_collect_mixed(own, ocap, d_nmix, mine, mx, st);
+        launch_ds_collect_mixed(ctx->d_ds, ctx->ds_cap, d_nmix, mine, mx, st);
         if ((rc = nccl_check(ctx, g_nccl.AllGather(mine, everyone, mx * 2, ncclUint64, ctx->comm, st), "ncclAllGather(mixed ids)"))) return rc;
+        ctx->ds_entries_bound += (int64_t)total;
+        if ((rc = ds_ensure_total(ctx, ctx->ds_entries_bound))) return rc;
         launch_ds_apply_mixed(everyone, mx * P, ctx->d_ds, 64 - log2_ceil(ctx->ds_cap), ctx->ds_cap - 1, st);
         CU(cudaStreamSynchronize(st));
         cudaFree(mine);
@@ -554,143 +562,99 @@ int return_mixed_ids(ptx_ctx* ctx, const ulonglong2* own, uint64_t ocap, cudaStr
     return PTX_OK;
 }
 
-// Asynchronous form of the exchange: every box is sent whole (its header carries the entry count, so no size
-// has to travel through the host), merged on the owner and the flags max-reduced - all on the side stream `xs`,
-// while the main stream runs the coverage pass.  ptx_finalize joins on ev_x1.
-int exchange_fast_begin(ptx_ctx* ctx) {
+// Id groups across ranks (profile.rs:369-378 / 406-437 are keyed by read id, which ignores shard boundaries).
+// k_apply kept the ids this rank owns in its id set and appended every other record's {hash, state} to the outbox
+// of the owner.  Here: the box fills are all-gathered (one small collective + readback, the only host
+// synchronisation), then - on the side stream `xs`, while the main stream runs the coverage pass - the new part
+// of every box travels with grouped ncclSend/ncclRecv, the owner merges what it received into its id set and
+// the repeat/mixed flags are max-reduced.  ptx_finalize joins on ev_x1.
+int exchange_begin(ptx_ctx* ctx) {
     const int P = ctx->n_ranks;
     int rc;
-    launch_box_headers(ctx->outbox, ctx->out_cursor, ctx->box_cap, (uint32_t)P, ctx->d_flags, ctx->st);
-    // all ranks send the same number of entries per box: the fullest box anywhere (one 8-byte max-reduce + readback)
-    if ((rc = nccl_check(ctx, g_nccl.AllReduce(ctx->out_cursor + P, ctx->out_cursor + P, 1, ncclUint64, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(box size)"))) return rc;
-    unsigned long long send_n = 0;
-    CU(cudaMemcpyAsync(&send_n, ctx->out_cursor + P, sizeof send_n, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
-    if (send_n > ctx->box_cap) {  // a peer has more ids than this rank planned for: grow the boxes (contents are kept)
-        if ((rc = xchg_ensure(ctx, (int64_t)(send_n * (uint64_t)P)))) return rc;
+    unsigned long long* d_cur = ctx->out_cursor;           // [P] cursors + [P] overflow marker (set below)
+    unsigned long long* d_all = ctx->out_cursor + (P + 1);  // [(P+1) * P]
+    unsigned long long* d_par = d_all + (size_t)(P + 1) * P;  // [2P] merge offsets, counts
+    std::vector<unsigned long long> all((size_t)(P + 1) * P);
+    for (int attempt = 0;; ++attempt) {
+        if ((rc = nccl_check(ctx, g_nccl.AllGather(d_cur, d_all, P + 1, ncclUint64, ctx->comm, ctx->st), "ncclAllGather(box fills)"))) return rc;
+        CU(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        // all[q*(P+1) + r] = entries rank q has appended for rank r so far; a fill above q's capacity means entries
+        // were dropped there.  Every rank sees the same matrix, so all of them take the same branch.
+        unsigned long long worst = 0;
+        bool over = false;
+        for (int q = 0; q < P; ++q) {
+            const unsigned long long capq = all[(size_t)q * (P + 1) + P];
+            for (int r = 0; r < P; ++r) {
+                const unsigned long long v = all[(size_t)q * (P + 1) + r];
+                worst = std::max(worst, v);
+                if (v > capq) over = true;
+            }
+        }
+        if (!over) break;
+        if (attempt >= 2) return fail(ctx, PTX_E_STATE, "id-group exchange: outboxes still overflow after being enlarged");
+        // rare: some rank met far more foreign ids than planned.  Start the id sets over everywhere with boxes that
+        // hold the fullest one seen, and rebuild them from the record tables (no text is re-read).
+        if ((rc = xchg_ensure(ctx, (int64_t)((worst + worst / 4) * (unsigned long long)P)))) return rc;
+        CU(cudaMemsetAsync(ctx->d_ds, 0, ctx->ds_cap * sizeof(ulonglong2), ctx->st));
+        CU(cudaMemsetAsync(ctx->d_flags, 0, 3 * sizeof(uint32_t), ctx->st));
+        CU(cudaMemsetAsync(d_cur, 0, P * sizeof(unsigned long long), ctx->st));
+        std::fill(ctx->box_sent.begin(), ctx->box_sent.end(), 0ull);
+        std::fill(ctx->recv_done.begin(), ctx->recv_done.end(), 0ull);
+        for (auto& ch : ctx->chunks) {
+            if (!ch.ingested || ch.n_tiles == 0) continue;
+            IngestArgs a = make_args(ctx, ch);
+            launch_apply(a, (uint32_t)ch.n_slots, MODE_CLASSIFY, ctx->st);
+        }
     }
+    // what is new since the previous exchange (ptx_finalize may run more than once)
+    std::vector<unsigned long long> send_n(P, 0), recv_n(P, 0), roff(P, 0), par(2 * (size_t)P, 0);
+    unsigned long long n_recv = 0, max_recv = 0, recv_total = 0;
+    for (int q = 0; q < P; ++q) {
+        if (q == ctx->rank) continue;
+        send_n[q] = all[(size_t)ctx->rank * (P + 1) + q] - ctx->box_sent[q];
+        const unsigned long long cum = all[(size_t)q * (P + 1) + ctx->rank];
+        recv_n[q] = cum - ctx->recv_done[q];
+        roff[q] = n_recv;
+        n_recv += recv_n[q];
+        max_recv = std::max(max_recv, recv_n[q]);
+        recv_total += cum;
+    }
+    // the id set now also holds the foreign ids this rank owns
+    ctx->ds_entries_bound = std::max<int64_t>(ctx->ds_entries_bound, ctx->ds_records + (int64_t)recv_total);
+    if ((rc = ds_ensure_total(ctx, ctx->ds_entries_bound))) return rc;
+    if (n_recv > ctx->inbox_cap) {
+        CU(cudaStreamSynchronize(ctx->xs));
+        dfree(ctx->inbox);
+        ctx->inbox_cap = n_recv + n_recv / 8 + 1024;
+        CU(cudaMalloc((void**)&ctx->inbox, ctx->inbox_cap * sizeof(ulonglong2)));
+    }
+    int nb = 0;
+    for (int q = 0; q < P; ++q) {
+        if (q == ctx->rank || recv_n[q] == 0) continue;
+        par[nb] = roff[q];
+        par[(size_t)P + nb] = recv_n[q];
+        ++nb;
+    }
+    CU(cudaMemcpyAsync(d_par, par.data(), par.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->st));
     CU(cudaEventRecord(ctx->ev_x0, ctx->st));
     CU(cudaStreamWaitEvent(ctx->xs, ctx->ev_x0, 0));
     cudaStream_t xs = ctx->xs;
-    CU(cudaMemsetAsync(ctx->x_own, 0, ctx->x_own_cap * sizeof(ulonglong2), xs));
     g_nccl.GroupStart();
-    for (int r = 0; r < P; ++r) {
-        if (r == ctx->rank) continue;
-        g_nccl.Send(ctx->outbox + (uint64_t)r * ctx->box_cap, send_n * 2, ncclUint64, r, ctx->comm, xs);
-        g_nccl.Recv(ctx->inbox + (uint64_t)r * ctx->box_cap, send_n * 2, ncclUint64, r, ctx->comm, xs);
+    for (int q = 0; q < P; ++q) {
+        if (q == ctx->rank) continue;
+        if (send_n[q]) g_nccl.Send(ctx->outbox + (uint64_t)q * ctx->box_cap + ctx->box_sent[q], send_n[q] * 2, ncclUint64, q, ctx->comm, xs);
+        if (recv_n[q]) g_nccl.Recv(ctx->inbox + roff[q], recv_n[q] * 2, ncclUint64, q, ctx->comm, xs);
     }
     if ((rc = nccl_check(ctx, g_nccl.GroupEnd(), "ncclSend/Recv(id boxes)"))) return rc;
-    CU(cudaMemcpyAsync(ctx->inbox + (uint64_t)ctx->rank * ctx->box_cap, ctx->outbox + (uint64_t)ctx->rank * ctx->box_cap,
-                       send_n * sizeof(ulonglong2), cudaMemcpyDeviceToDevice, xs));
-    launch_ds_merge_boxes(ctx->inbox, (uint32_t)P, ctx->box_cap, ctx->x_own, 64 - log2_ceil(ctx->x_own_cap), ctx->x_own_cap - 1, ctx->d_flags, xs);
-    if ((rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 4, ncclUint32, ncclMax, ctx->comm, xs), "ncclAllReduce(flags)"))) return rc;
+    launch_ds_merge_boxes(ctx->inbox, d_par, d_par + P, (uint32_t)nb, max_recv, ctx->d_ds, 64 - log2_ceil(ctx->ds_cap), ctx->ds_cap - 1, ctx->d_flags, xs);
+    if ((rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 2, ncclUint32, ncclMax, ctx->comm, xs), "ncclAllReduce(flags)"))) return rc;
     CU(cudaEventRecord(ctx->ev_x1, xs));
-    return PTX_OK;
-}
-
-// profile.rs:369-378 / 406-437 across ranks: route every id-set entry to the rank owning its hash, merge the
-// per-rank states there, and tell every rank which ids ended up DS_MIXED.  Sets d_flags[0/1] on the ranks
-// that detect a repeat / a mixed group (the caller max-reduces the flags afterwards).
-int exchange_id_groups(ptx_ctx* ctx) {
-    const int P = ctx->n_ranks;
-    if (P <= 1 || !ctx->d_ds) return PTX_OK;
-    cudaStream_t st = ctx->st;
-    int rc;
-    Trace tr(st);
-    // Outboxes of fixed capacity per owner (the hash spreads ids uniformly), so one pass over the id set both
-    // counts and scatters; if an outbox would overflow, the capacities are raised and the pass repeated.
-    const uint64_t n_mine = (uint64_t)std::max<int64_t>(ctx->ds_records, 1);
-    uint64_t box_cap = ctx->xchg_box_cap ? ctx->xchg_box_cap : (n_mine / P + n_mine / (4 * P) + 4096);
-    std::vector<unsigned long long> all((size_t)P * P), cursor(P), roff(P);
-    unsigned long long *d_cnt = nullptr, *d_all = nullptr;
-    ulonglong2* sendbuf = nullptr;
-    for (;;) {
-        const size_t need = ((size_t)3 * P + (size_t)P * P + 64) * sizeof(unsigned long long) + ((size_t)box_cap * P + 64) * sizeof(ulonglong2) + 8192;
-        if ((rc = scratch_reserve(ctx, need))) return rc;
-        ctx->scratch_off = 0;
-        d_cnt = scratch_take<unsigned long long>(ctx, (size_t)P * 3 + 2);  // [0,P) cursors, [P,2P) counts, [2P] mixed count
-        d_all = scratch_take<unsigned long long>(ctx, (size_t)P * P);
-        sendbuf = scratch_take<ulonglong2>(ctx, (size_t)box_cap * P + 1);
-        for (int r = 0; r < P; ++r) cursor[r] = (unsigned long long)r * box_cap;
-        CU(cudaMemcpyAsync(d_cnt, cursor.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-        launch_ds_owner_scatter(ctx->d_ds, ctx->ds_cap, (uint32_t)P, d_cnt, sendbuf, box_cap, st);
-        launch_sub_u64(d_cnt + P, d_cnt, box_cap, P, st);  // counts[r] = cursor[r] - r*box_cap
-        if ((rc = nccl_check(ctx, g_nccl.AllGather(d_cnt + P, d_all, P, ncclUint64, ctx->comm, st), "ncclAllGather(id counts)"))) return rc;
-        CU(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        unsigned long long worst = 0;
-        for (auto v : all) worst = std::max(worst, v);  // every rank sees every count: all ranks retry together
-        if (worst <= box_cap) break;
-        box_cap = worst + worst / 8 + 4096;
+    for (int q = 0; q < P; ++q) {
+        if (q == ctx->rank) continue;
+        ctx->box_sent[q] += send_n[q];
+        ctx->recv_done[q] += recv_n[q];
     }
-    ctx->xchg_box_cap = box_cap;
-    tr.mark("xchg scatter + counts");
-    const unsigned long long* send_cnt = &all[(size_t)ctx->rank * P];  // all[r][q] = entries rank r sends to rank q
-    unsigned long long n_recv = 0;
-    for (int r = 0; r < P; ++r) { roff[r] = n_recv; n_recv += all[(size_t)r * P + ctx->rank]; }
-    const uint64_t ocap = 1ull << std::max<uint32_t>(10, log2_ceil(n_recv + n_recv / 2 + 1));
-    // receive buffer + owner table: a second grow-only arena (growing it must not move the outboxes, and no
-    // rank may repeat a collective the others do not)
-    {
-        const size_t need = ((size_t)n_recv + ocap + 64) * sizeof(ulonglong2) + 8192;
-        if (need > ctx->scratch2_cap) {
-            CU(cudaStreamSynchronize(st));
-            if (ctx->scratch2) cudaFree(ctx->scratch2);
-            ctx->scratch2 = nullptr;
-            ctx->scratch2_cap = 0;
-            CU(cudaMalloc((void**)&ctx->scratch2, need + need / 8));
-            ctx->scratch2_cap = need + need / 8;
-        }
-    }
-    ulonglong2* recvbuf = reinterpret_cast<ulonglong2*>(ctx->scratch2);
-    ulonglong2* own = recvbuf + (((size_t)n_recv + 16) & ~(size_t)15);
-    CU(cudaMemsetAsync(own, 0, ocap * sizeof(ulonglong2), st));
-    g_nccl.GroupStart();
-    for (int r = 0; r < P; ++r) {
-        if (r == ctx->rank) continue;
-        if (send_cnt[r]) g_nccl.Send(sendbuf + cursor[r], send_cnt[r] * 2, ncclUint64, r, ctx->comm, st);
-        const unsigned long long nr = all[(size_t)r * P + ctx->rank];
-        if (nr) g_nccl.Recv(recvbuf + roff[r], nr * 2, ncclUint64, r, ctx->comm, st);
-    }
-    if ((rc = nccl_check(ctx, g_nccl.GroupEnd(), "ncclSend/Recv(id entries)"))) return rc;
-    if (send_cnt[ctx->rank])
-        CU(cudaMemcpyAsync(recvbuf + roff[ctx->rank], sendbuf + cursor[ctx->rank], send_cnt[ctx->rank] * sizeof(ulonglong2),
-                           cudaMemcpyDeviceToDevice, st));
-    tr.mark("xchg send/recv");
-    // owner-side merge
-    launch_ds_merge_insert(recvbuf, n_recv, own, 64 - log2_ceil(ocap), ocap - 1, ctx->d_flags, st);
-    // a mixed group needs a repeated id: if no rank saw one, nothing has to be sent back
-    if ((rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 2, ncclUint32, ncclMax, ctx->comm, st), "ncclAllReduce(flags)"))) return rc;
-    uint32_t fl[2] = {0, 0};
-    CU(cudaMemcpyAsync(fl, ctx->d_flags, sizeof fl, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    tr.mark("xchg merge_insert + flags");
-    if (fl[1] == 0) return PTX_OK;
-    // mixed ids -> everyone
-    unsigned long long* d_nmix = d_cnt + 2 * P;
-    unsigned long long* d_allmix = d_all;  // reuse: P entries
-    CU(cudaMemsetAsync(d_nmix, 0, sizeof(unsigned long long), st));
-    launch_ds_collect_mixed(own, ocap, d_nmix, nullptr, 0, st);
-    if ((rc = nccl_check(ctx, g_nccl.AllGather(d_nmix, d_allmix, 1, ncclUint64, ctx->comm, st), "ncclAllGather(mixed counts)"))) return rc;
-    std::vector<unsigned long long> nmix(P);
-    CU(cudaMemcpyAsync(nmix.data(), d_allmix, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    unsigned long long mx = 0;
-    for (auto v : nmix) mx = std::max(mx, v);
-    if (mx > 0) {
-        // rare: few ids are mixed; these two small buffers are allocated ad hoc
-        ulonglong2* mine = nullptr;
-        ulonglong2* everyone = nullptr;
-        if ((rc = dalloc(ctx, &mine, (size_t)mx)) || (rc = dalloc(ctx, &everyone, (size_t)mx * P))) return rc;
-        CU(cudaMemsetAsync(d_nmix, 0, sizeof(unsigned long long), st));
-        launch_ds_collect_mixed(own, ocap, d_nmix, mine, mx, st);
-        if ((rc = nccl_check(ctx, g_nccl.AllGather(mine, everyone, mx * 2, ncclUint64, ctx->comm, st), "ncclAllGather(mixed ids)"))) return rc;
-        launch_ds_apply_mixed(everyone, mx * P, ctx->d_ds, 64 - log2_ceil(ctx->ds_cap), ctx->ds_cap - 1, st);
-        CU(cudaStreamSynchronize(st));
-        cudaFree(mine);
-        cudaFree(everyone);
-    }
-    tr.mark("xchg mixed ids back");
     return PTX_OK;
 }
 
@@ -712,6 +676,7 @@ int ptx_create(int device, ptx_ctx** out) {
     ctx->device = device;
     if (const char* e = getenv("PTX_TILE_ROWS")) ctx->force_rows = atoi(e);
     if (const char* e = getenv("PTX_LONG_MODE")) ctx->force_long = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("PTX_TEST_BOX_CAP")) ctx->test_box_cap = atoll(e);
     if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
@@ -734,8 +699,7 @@ void ptx_destroy(ptx_ctx* ctx) {
     for (auto& ch : ctx->chunks) chunk_free(ch);
     for (auto& ch : ctx->pool) chunk_free(ch);
     dfree(ctx->scratch);
-    dfree(ctx->scratch2);
-    dfree(ctx->outbox); dfree(ctx->inbox); dfree(ctx->x_own); dfree(ctx->out_cursor);
+    dfree(ctx->outbox); dfree(ctx->inbox); dfree(ctx->out_cursor);
     if (ctx->xs) cudaStreamDestroy(ctx->xs);
     if (ctx->ev_x0) cudaEventDestroy(ctx->ev_x0);
     if (ctx->ev_x1) cudaEventDestroy(ctx->ev_x1);
@@ -1123,7 +1087,7 @@ int ptx_finalize(ptx_ctx* ctx) {
         // id groups may span ranks: the boxes k_apply filled travel on the side stream while the coverage runs here
         int rc = xchg_ensure(ctx, std::max<int64_t>(ctx->ds_records, ctx->reserve_records));
         if (rc) return rc;
-        if ((rc = exchange_fast_begin(ctx))) return rc;
+        if ((rc = exchange_begin(ctx))) return rc;
         tr.mark("final exchange issued");
     } else {
         CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));
@@ -1158,13 +1122,8 @@ int ptx_finalize(ptx_ctx* ctx) {
             CU(cudaStreamWaitEvent(ctx->st, ctx->ev_x1, 0));
             CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));
             CU(cudaStreamSynchronize(ctx->st));
-            if (ctx->h_flags[2]) {  // a box overflowed: exact but slower exchange from the id set itself
-                int rc = exchange_id_groups(ctx);
-                if (rc) return rc;
-                CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));
-                CU(cudaStreamSynchronize(ctx->st));
-            } else if (ctx->h_flags[1]) {
-                int rc = return_mixed_ids(ctx, ctx->x_own, ctx->x_own_cap, ctx->st);
+            if (ctx->h_flags[1]) {
+                int rc = return_mixed_ids(ctx, ctx->st);
                 if (rc) return rc;
             }
             mixed = ctx->h_flags[1] != 0;
@@ -1204,10 +1163,7 @@ int ptx_finalize(ptx_ctx* ctx) {
         CU(cudaStreamWaitEvent(ctx->st, ctx->ev_x1, 0));
         CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaStreamSynchronize(ctx->st));
-        if (ctx->h_flags[2]) { int rc = exchange_id_groups(ctx); if (rc) return rc; }
-        else if (ctx->h_flags[1]) { int rc = return_mixed_ids(ctx, ctx->x_own, ctx->x_own_cap, ctx->st); if (rc) return rc; }
-        CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));
-        CU(cudaStreamSynchronize(ctx->st));
+        if (ctx->h_flags[1]) { int rc = return_mixed_ids(ctx, ctx->st); if (rc) return rc; }
     }
     if (ctx->comm) {
         if (!ctx->d_hist_g) { int rc = dalloc(ctx, &ctx->d_hist_g, (size_t)S * 4); if (rc) return rc; }
@@ -1255,7 +1211,12 @@ static int reset_impl(ptx_ctx* ctx, bool keep_buffers) {
     const size_t S = std::max<size_t>(ctx->sp.size(), 1);
     if (ctx->d_hist) CU(cudaMemsetAsync(ctx->d_hist, 0, S * 4 * sizeof(unsigned long long), ctx->st));
     CU(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(uint32_t), ctx->st));
-    if (ctx->out_cursor) CU(cudaMemsetAsync(ctx->out_cursor, 0, 64 * sizeof(unsigned long long), ctx->st));
+    if (ctx->out_cursor) {
+        CU(cudaMemsetAsync(ctx->out_cursor, 0, (size_t)ctx->n_ranks * sizeof(unsigned long long), ctx->st));
+        std::fill(ctx->box_sent.begin(), ctx->box_sent.end(), 0ull);
+        std::fill(ctx->recv_done.begin(), ctx->recv_done.end(), 0ull);
+    }
+    ctx->ds_entries_bound = 0;
     if (ctx->d_ds) CU(cudaMemsetAsync(ctx->d_ds, 0, ctx->ds_cap * sizeof(ulonglong2), ctx->st));
     if (ctx->d_err) {
         int rc = zero_coverage(ctx);

@@ -38,6 +38,7 @@ constexpr uint32_t RM_MONOTONE = 0x20000000u;  // strictly monotone node ids: no
 constexpr int MODE_CLASSIFY = 1;  // labels, species counts, read-id set insert
 constexpr int MODE_COVER = 2;     // node coverage / trio accumulation
 constexpr int MODE_KEEPMASK = 4;  // skip reads whose id group is DS_MIXED (replay pass)
+constexpr int MODE_REBOX = 8;     // multi-GPU, rare: fill the outboxes again after they were enlarged (no id-set insert)
 
 struct GraphDev {
     // nodes (all uploaded species concatenated; g = node_base[s] + local id)
@@ -85,10 +86,10 @@ struct IngestArgs {
     uint32_t* nodes;            // [<= text bytes / 2] raw node ids of eligible records' walks
     uint32_t* cursors;          // [0] next record-table entry, [1] next node slot
     // multi-GPU: id entries routed to the rank owning their hash (written by k_apply<CLASSIFY>, sent at finalize)
-    ulonglong2* outbox;         // [n_ranks][box_cap], entry 0 of each box is its header {count, 0}; null on one GPU
+    ulonglong2* outbox;         // [n_ranks][box_cap] {hash, state} of records whose id another rank owns; null on one GPU
     unsigned long long* out_cursor;  // [n_ranks]
     uint64_t box_cap;
-    uint32_t n_ranks;
+    uint32_t n_ranks, rank;
     RangesView ranges;
     unsigned long long* hist;   // [S*4]
     ulonglong2* ds;             // read-id set slots
@@ -117,15 +118,9 @@ void launch_fill_u8(uint8_t* p, uint8_t v, uint64_t n, cudaStream_t st);
 void launch_ninfo_build(const uint32_t* len, const uint64_t* bit_off, uint4* ninfo, int64_t N, cudaStream_t st);
 void launch_ninfo_full(uint4* ninfo, uint8_t* full, int64_t N, int mode, cudaStream_t st);
 // cross-rank id groups (multi-GPU finalize)
-void launch_ds_owner_count(const ulonglong2* slots, uint64_t cap, uint32_t P, unsigned long long* cnt, cudaStream_t st);
-void launch_ds_owner_scatter(const ulonglong2* slots, uint64_t cap, uint32_t P, unsigned long long* cursor, ulonglong2* out, uint64_t box_cap,
-                             cudaStream_t st);
-void launch_sub_u64(unsigned long long* out, const unsigned long long* in, unsigned long long step, int n, cudaStream_t st);
-void launch_ds_merge_insert(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags, cudaStream_t st);
 void launch_ds_collect_mixed(const ulonglong2* slots, uint64_t cap, unsigned long long* cursor, ulonglong2* out, uint64_t out_cap, cudaStream_t st);
-void launch_box_headers(ulonglong2* outbox, const unsigned long long* cursor, uint64_t box_cap, uint32_t P, uint32_t* flags, cudaStream_t st);
-void launch_ds_merge_boxes(const ulonglong2* inbox, uint32_t P, uint64_t box_cap, ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags,
-                           cudaStream_t st);
+void launch_ds_merge_boxes(const ulonglong2* inbox, const unsigned long long* off, const unsigned long long* cnt, uint32_t n_boxes, uint64_t max_cnt,
+                           ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags, cudaStream_t st);
 void launch_ds_apply_mixed(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, cudaStream_t st);
 
 // graph commit

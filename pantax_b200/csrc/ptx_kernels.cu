@@ -245,122 +245,20 @@ __global__ void __launch_bounds__(256) k_ds_rehash(const ulonglong2* __restrict_
 __device__ __forceinline__ uint32_t ds_owner(const ulonglong2& e, uint32_t P) {
     return ((uint32_t)(e.y >> 32) ^ (uint32_t)(e.x >> 40)) % P;
 }
-// Both kernels aggregate per warp (one atomic per distinct owner per warp): 10 M same-address atomics took
-// 4 ms each in the first version (profiles/r1_multigpu_trace.md).
-__global__ void __launch_bounds__(256) k_ds_owner_count(const ulonglong2* __restrict__ slots, uint64_t cap, uint32_t P,
-                                                        unsigned long long* cnt) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t rounds = (cap + stride - 1) / stride;
-    for (uint64_t it = 0; it < rounds; ++it) {
-        const uint64_t k = it * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        uint32_t owner = 0xFFFFFFFFu;
-        if (k < cap) {
-            ulonglong2 e = slots[k];
-            if (!(e.x == 0ull && e.y == 0ull)) owner = ds_owner(e, P);
-        }
-        const unsigned peers = __match_any_sync(0xffffffffu, owner);
-        if (owner != 0xFFFFFFFFu && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(cnt + owner, (unsigned long long)__popc(peers));
-    }
-}
-__global__ void __launch_bounds__(64) k_sub_u64(unsigned long long* out, const unsigned long long* in, unsigned long long step, int n) {
-    const int i = threadIdx.x;
-    if (i < n) out[i] = in[i] - (unsigned long long)i * step;
-}
-// out = P outboxes of box_cap entries; cursor[r] starts at r*box_cap.  Entries beyond an outbox's end are
-// counted but not written (the host then enlarges the outboxes and repeats the pass).
-__global__ void __launch_bounds__(256) k_ds_owner_scatter(const ulonglong2* __restrict__ slots, uint64_t cap, uint32_t P,
-                                                          unsigned long long* cursor, ulonglong2* __restrict__ out, uint64_t box_cap) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t rounds = (cap + stride - 1) / stride;
-    const uint32_t lane = threadIdx.x & 31u;
-    for (uint64_t it = 0; it < rounds; ++it) {
-        const uint64_t k = it * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        uint32_t owner = 0xFFFFFFFFu;
-        ulonglong2 e = make_ulonglong2(0ull, 0ull);
-        if (k < cap) {
-            e = slots[k];
-            if (!(e.x == 0ull && e.y == 0ull)) owner = ds_owner(e, P);
-        }
-        const unsigned peers = __match_any_sync(0xffffffffu, owner);
-        const int leader = __ffs(peers) - 1;
-        unsigned long long base = 0;
-        if (owner != 0xFFFFFFFFu && (int)lane == leader) base = atomicAdd(cursor + owner, (unsigned long long)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (owner != 0xFFFFFFFFu) {
-            const unsigned long long pos = base + __popc(peers & ((1u << lane) - 1u));
-            if (pos < (unsigned long long)(owner + 1) * box_cap) out[pos] = e;
-        }
-    }
-}
 __device__ __forceinline__ uint32_t ds_merge_state(uint32_t l, uint32_t f) {
     if (l == DS_NONE) return f;
     if (f == DS_NONE || l == f) return l;
     return DS_MIXED;
 }
-__global__ void __launch_bounds__(256) k_ds_merge_insert(const ulonglong2* __restrict__ in, uint64_t n, ulonglong2* slots, uint32_t shift,
-                                                         uint64_t mask, uint32_t* flags) {
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
-        const ulonglong2 e = in[k];
-        IdHash h;
-        h.lo = e.x;
-        h.hi = (uint32_t)(e.y >> 32);
-        const uint32_t fst = (uint32_t)e.y;
-        uint64_t i = ds_home(h, shift);
-        for (;;) {
-            ulonglong2 cur = ld128(slots + i);
-            if (cur.x == 0ull && cur.y == 0ull) {
-                cur = atomic_cas128(slots + i, make_ulonglong2(0ull, 0ull), e);
-                if (cur.x == 0ull && cur.y == 0ull) {
-                    if (fst == DS_MIXED) atomicOr(flags + 1, 1u);
-                    break;
-                }
-            }
-            if (cur.x == e.x && (cur.y >> 32) == (e.y >> 32)) {  // same id on two ranks (or twice on one)
-                atomicOr(flags + 0, 1u);
-                for (;;) {
-                    const uint32_t nst = ds_merge_state((uint32_t)cur.y, fst);
-                    if (nst == (uint32_t)cur.y) break;
-                    const ulonglong2 want = make_ulonglong2(cur.x, (cur.y & 0xFFFFFFFF00000000ull) | nst);
-                    const ulonglong2 prev = atomic_cas128(slots + i, cur, want);
-                    if (prev.x == cur.x && prev.y == cur.y) {
-                        if (nst == DS_MIXED) atomicOr(flags + 1, 1u);
-                        break;
-                    }
-                    cur = prev;
-                }
-                break;
-            }
-            i = (i + 1) & mask;
-        }
-    }
-}
-__global__ void __launch_bounds__(64) k_box_headers(ulonglong2* outbox, const unsigned long long* __restrict__ cursor, uint64_t box_cap, uint32_t P,
-                                                   uint32_t* flags) {
-    const uint32_t r = threadIdx.x;
-    unsigned long long n = 0;
-    if (r < P) {
-        n = cursor[r];
-        if (n > box_cap - 1) { n = box_cap - 1; atomicOr(flags + 2, 1u); }
-        outbox[(uint64_t)r * box_cap] = make_ulonglong2(n, 0ull);
-    }
-    // entries (header included) of the fullest box -> cursor[P]: every rank sends that many per box
-    unsigned long long m = n + 1;
-    for (int d = 16; d >= 1; d >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, d);
-        m = o > m ? o : m;
-    }
-    __shared__ unsigned long long ws[2];
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) const_cast<unsigned long long*>(cursor)[P] = ws[0] > ws[1] ? ws[0] : ws[1];
-}
-// merge every received box (header = entry count) into the owner table; same state algebra as k_ds_merge_insert
-__global__ void __launch_bounds__(256) k_ds_merge_boxes(const ulonglong2* __restrict__ inbox, uint64_t box_cap, ulonglong2* slots, uint32_t shift,
+// Owner side: merge the entries received from peer blockIdx.y (inbox + off[peer], cnt[peer] entries) into this rank's
+// id set - the same insert-or-merge as ds_insert, with the sender's state instead of a single record's.
+__global__ void __launch_bounds__(256) k_ds_merge_boxes(const ulonglong2* __restrict__ inbox, const unsigned long long* __restrict__ off,
+                                                        const unsigned long long* __restrict__ cnt, ulonglong2* slots, uint32_t shift,
                                                         uint64_t mask, uint32_t* flags) {
-    const ulonglong2* box = inbox + (uint64_t)blockIdx.y * box_cap;
-    const uint64_t n = box[0].x;
+    const ulonglong2* box = inbox + off[blockIdx.y];
+    const uint64_t n = cnt[blockIdx.y];
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
-        const ulonglong2 e = box[k + 1];
+        const ulonglong2 e = box[k];
         IdHash h;
         h.lo = e.x;
         h.hi = (uint32_t)(e.y >> 32);
@@ -370,13 +268,10 @@ __global__ void __launch_bounds__(256) k_ds_merge_boxes(const ulonglong2* __rest
             ulonglong2 cur = ld128(slots + i);
             if (cur.x == 0ull && cur.y == 0ull) {
                 cur = atomic_cas128(slots + i, make_ulonglong2(0ull, 0ull), e);
-                if (cur.x == 0ull && cur.y == 0ull) {
-                    if (fst == DS_MIXED) atomicOr(flags + 1, 1u);
-                    break;
-                }
+                if (cur.x == 0ull && cur.y == 0ull) break;
             }
-            if (cur.x == e.x && (cur.y >> 32) == (e.y >> 32)) {
-                atomicOr(flags + 0, 1u);
+            if (cur.x == e.x && (cur.y >> 32) == (e.y >> 32)) {  // the same read id on two ranks (or twice on one)
+                if (flags[0] == 0u) atomicOr(flags + 0, 1u);
                 for (;;) {
                     const uint32_t nst = ds_merge_state((uint32_t)cur.y, fst);
                     if (nst == (uint32_t)cur.y) break;
@@ -414,7 +309,13 @@ __global__ void __launch_bounds__(256) k_ds_apply_mixed(const ulonglong2* __rest
         uint64_t i = ds_home(h, shift);
         for (;;) {
             ulonglong2 cur = ld128(slots + i);
-            if (cur.x == 0ull && cur.y == 0ull) break;  // this rank never saw the id
+            if (cur.x == 0ull && cur.y == 0ull) {
+                // not in this rank's set (ids owned by another rank are not kept here): insert it as MIXED so that
+                // the keep-mask lookup of this rank's reads with that id finds it
+                const ulonglong2 mixed = make_ulonglong2(e.x, (e.y & 0xFFFFFFFF00000000ull) | DS_MIXED);
+                cur = atomic_cas128(slots + i, make_ulonglong2(0ull, 0ull), mixed);
+                if (cur.x == 0ull && cur.y == 0ull) break;
+            }
             if (cur.x == e.x && (cur.y >> 32) == (e.y >> 32)) {
                 for (;;) {
                     if ((uint32_t)cur.y == DS_MIXED) break;
@@ -1019,22 +920,29 @@ __global__ void __launch_bounds__(256) k_apply(const IngestArgs a, uint32_t n_en
     IdHash h;
     h.lo = 0;
     h.hi = mb.w;
-    if (labelled && (MODE & (MODE_CLASSIFY | MODE_KEEPMASK))) h.lo = a.hash_lo[e];
-    if ((MODE & MODE_CLASSIFY) && labelled) ds_insert(a.ds, a.ds_shift, a.ds_mask, h, eligible, label, a.flags);
-    if ((MODE & MODE_CLASSIFY) && a.outbox != nullptr) {
-        // multi-GPU: route {hash, state} to the rank that owns the hash (one atomicAdd per distinct owner per warp)
-        const ulonglong2 ent = make_ulonglong2(h.lo, ((uint64_t)h.hi << 32) | (eligible ? label : DS_NONE));
-        const uint32_t owner = labelled ? ds_owner(ent, a.n_ranks) : 0xFFFFFFFFu;
-        const unsigned peers = __match_any_sync(0xffffffffu, owner);
-        const int leader = __ffs(peers) - 1;
-        const uint32_t lane = threadIdx.x & 31u;
-        unsigned long long base = 0;
-        if (labelled && (int)lane == leader) base = atomicAdd(a.out_cursor + owner, (unsigned long long)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (labelled) {
-            const unsigned long long pos = base + __popc(peers & ((1u << lane) - 1u)) + 1ull;  // entry 0 is the header
-            if (pos < a.box_cap) a.outbox[(uint64_t)owner * a.box_cap + pos] = ent;
-            else atomicOr(a.flags + 2, 1u);  // box overflow: ptx_finalize falls back to the table-scan exchange
+    if (labelled && (MODE & (MODE_CLASSIFY | MODE_KEEPMASK | MODE_REBOX))) h.lo = a.hash_lo[e];
+    if (MODE & (MODE_CLASSIFY | MODE_REBOX)) {
+        if (a.outbox == nullptr) {
+            if ((MODE & MODE_CLASSIFY) && labelled) ds_insert(a.ds, a.ds_shift, a.ds_mask, h, eligible, label, a.flags);
+        } else {
+            // multi-GPU: a read id is kept only by the rank that owns its hash.  Own ids go into the local set; the
+            // others are appended to the owner's outbox as {hash, state} (one atomicAdd per distinct owner per warp)
+            // and merged there by k_ds_merge_boxes when ptx_finalize exchanges the boxes.
+            const ulonglong2 ent = make_ulonglong2(h.lo, ((uint64_t)h.hi << 32) | (eligible ? label : DS_NONE));
+            const uint32_t owner = labelled ? ds_owner(ent, a.n_ranks) : 0xFFFFFFFFu;
+            const bool mine = labelled && owner == a.rank;
+            if ((MODE & MODE_CLASSIFY) && mine) ds_insert(a.ds, a.ds_shift, a.ds_mask, h, eligible, label, a.flags);
+            const uint32_t dest = (labelled && !mine) ? owner : 0xFFFFFFFFu;
+            const unsigned peers = __match_any_sync(0xffffffffu, dest);
+            const int leader = __ffs(peers) - 1;
+            const uint32_t lane = threadIdx.x & 31u;
+            unsigned long long base = 0;
+            if (dest != 0xFFFFFFFFu && (int)lane == leader) base = atomicAdd(a.out_cursor + dest, (unsigned long long)__popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (dest != 0xFFFFFFFFu) {
+                const unsigned long long pos = base + __popc(peers & ((1u << lane) - 1u));
+                if (pos < a.box_cap) a.outbox[(uint64_t)dest * a.box_cap + pos] = ent;  // else: the cursor tells the host
+            }
         }
     }
     if (MODE & MODE_COVER) {
@@ -1700,6 +1608,7 @@ void launch_apply(const IngestArgs& a, uint32_t n_entries, int mode, cudaStream_
         case MODE_CLASSIFY | MODE_COVER: k_apply<MODE_CLASSIFY | MODE_COVER><<<grid, 256, 0, st>>>(a, n_entries); break;
         case MODE_COVER: k_apply<MODE_COVER><<<grid, 256, 0, st>>>(a, n_entries); break;
         case MODE_COVER | MODE_KEEPMASK: k_apply<MODE_COVER | MODE_KEEPMASK><<<grid, 256, 0, st>>>(a, n_entries); break;
+        case MODE_REBOX: k_apply<MODE_REBOX><<<grid, 256, 0, st>>>(a, n_entries); break;
         default: return;
     }
     PTX_LAUNCHED();
@@ -1709,32 +1618,11 @@ void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2*
     k_ds_rehash<<<grid_for(old_cap, 256), 256, 0, st>>>(old_slots, old_cap, new_slots, new_shift, new_mask);
     PTX_LAUNCHED();
 }
-void launch_ds_owner_count(const ulonglong2* slots, uint64_t cap, uint32_t P, unsigned long long* cnt, cudaStream_t st) {
-    k_ds_owner_count<<<grid_for(cap, 256), 256, 0, st>>>(slots, cap, P, cnt);
-    PTX_LAUNCHED();
-}
-void launch_ds_owner_scatter(const ulonglong2* slots, uint64_t cap, uint32_t P, unsigned long long* cursor, ulonglong2* out, uint64_t box_cap,
-                             cudaStream_t st) {
-    k_ds_owner_scatter<<<grid_for(cap, 256), 256, 0, st>>>(slots, cap, P, cursor, out, box_cap);
-    PTX_LAUNCHED();
-}
-void launch_sub_u64(unsigned long long* out, const unsigned long long* in, unsigned long long step, int n, cudaStream_t st) {
-    k_sub_u64<<<1, 64, 0, st>>>(out, in, step, n);
-    PTX_LAUNCHED();
-}
-void launch_ds_merge_insert(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags, cudaStream_t st) {
-    if (n == 0) return;
-    k_ds_merge_insert<<<grid_for(n, 256), 256, 0, st>>>(in, n, slots, shift, mask, flags);
-    PTX_LAUNCHED();
-}
-void launch_box_headers(ulonglong2* outbox, const unsigned long long* cursor, uint64_t box_cap, uint32_t P, uint32_t* flags, cudaStream_t st) {
-    k_box_headers<<<1, 64, 0, st>>>(outbox, cursor, box_cap, P, flags);
-    PTX_LAUNCHED();
-}
-void launch_ds_merge_boxes(const ulonglong2* inbox, uint32_t P, uint64_t box_cap, ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags,
-                           cudaStream_t st) {
-    dim3 grid(grid_for(box_cap, 256, 148u * 8u), P);
-    k_ds_merge_boxes<<<grid, 256, 0, st>>>(inbox, box_cap, slots, shift, mask, flags);
+void launch_ds_merge_boxes(const ulonglong2* inbox, const unsigned long long* off, const unsigned long long* cnt, uint32_t n_boxes, uint64_t max_cnt,
+                           ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags, cudaStream_t st) {
+    if (n_boxes == 0 || max_cnt == 0) return;
+    dim3 grid(grid_for(max_cnt, 256, 148u * 8u), n_boxes);
+    k_ds_merge_boxes<<<grid, 256, 0, st>>>(inbox, off, cnt, slots, shift, mask, flags);
     PTX_LAUNCHED();
 }
 void launch_ds_collect_mixed(const ulonglong2* slots, uint64_t cap, unsigned long long* cursor, ulonglong2* out, uint64_t out_cap, cudaStream_t st) {

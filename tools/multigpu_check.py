@@ -22,7 +22,12 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    for name, params, n in (("unique ids", NASTY, 200000), ("duplicate ids across shards", NASTY_DUP, 100000)):
+    for name, params, n, box in (("unique ids", NASTY, 200000, None), ("duplicate ids across shards", NASTY_DUP, 100000, None),
+                                 ("duplicate ids, outboxes too small at first (restart path)", NASTY_DUP, 100000, "64")):
+        if box:
+            os.environ["PTX_TEST_BOX_CAP"] = box
+        else:
+            os.environ.pop("PTX_TEST_BOX_CAP", None)
         ds = synth.Dataset(91, [60000, 20000, 5000], [10, 3, 1])
         gaf = ds.gaf(4, 0, n, params)
         graphs = dataset_graphs(ds)
