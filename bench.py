@@ -232,11 +232,11 @@ def run_ours(args):
     ctx.upload_graph(0, graphs[0][0], graphs[0][1])
     ctx.commit_graphs()
     t_graph = time.perf_counter() - t0
+    ctx.reserve(R)  # before comm_init: sizes the peer-memory id boxes
     if world > 1:
         uid = [api.PantaxGpu.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(world, rank, uid[0])
-    ctx.reserve(R)
 
     cudart = C.CDLL("libcudart.so")
     bid, dptr = ctx.gaf_buffer_alloc(nbytes)

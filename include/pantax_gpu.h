@@ -74,7 +74,8 @@ int ptx_upload_graph(ptx_ctx* ctx, int species, const int64_t* nodes_len, int64_
  * uploaded species at once. */
 int ptx_commit_graphs(ptx_ctx* ctx);
 
-/* Optional hint: expected total number of GAF records (sizes the read-id set once). */
+/* Optional hint: expected number of GAF records of this ctx (sizes the read-id set once).  Given on every
+ * rank BEFORE ptx_comm_init it also sizes the peer-memory id boxes of the multi-GPU exchange (below). */
 int ptx_reserve(ptx_ctx* ctx, int64_t expected_records);
 
 /* Pinned host memory for the caller's GAF buffer (full-speed H2D).  The result getters below accept any host
@@ -163,7 +164,11 @@ int ptx_filter_gaf(ptx_ctx* ctx, const uint8_t* bytes, size_t n, uint64_t* out_l
 /* ---- multi-GPU (one process per GPU) ------------------------------------------------ */
 /* NCCL bootstrap: rank 0 calls ptx_comm_unique_id, broadcasts the 128 bytes by any means,
  * every rank calls ptx_comm_init.  ptx_finalize then all-reduces the int64 accumulators
- * and OR-reduces the covered-base bitmap; every rank ends with the global result. */
+ * and OR-reduces the covered-base bitmap; every rank ends with the global result.
+ * Read-id groups (profile.rs:361-463) ignore shard boundaries: an id is kept only by the rank that owns its
+ * hash.  If every rank called ptx_reserve first, the ranks map each other's inboxes through CUDA IPC and the
+ * ingest kernels store foreign ids straight into the owner's memory over NVLink/NVSwitch (all ranks on one node);
+ * otherwise, or if an inbox slice overflows, the ids travel with ncclSend/ncclRecv inside ptx_finalize. */
 int ptx_comm_unique_id(void* out128);
 int ptx_comm_init(ptx_ctx* ctx, int n_ranks, int rank, const void* id128);
 

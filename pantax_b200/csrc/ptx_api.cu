@@ -28,6 +28,7 @@ struct NcclApi {
     int (*GetUniqueId)(ncclUniqueId*) = nullptr;
     int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;  // NCCL >= 2.18; optional
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -43,6 +44,7 @@ struct NcclApi {
         GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
         CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        CommSplit = (decltype(CommSplit))dlsym(h, "ncclCommSplit");
         AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
         AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
         GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
@@ -144,7 +146,13 @@ struct ptx_ctx {
     cudaStream_t xs = nullptr;
     cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;
     ulonglong2 *outbox = nullptr, *inbox = nullptr;
-    unsigned long long* out_cursor = nullptr;  // [P] box cursors, [P] this rank's box capacity, then exchange scratch
+    ulonglong2** d_box_ptr = nullptr;  // [P] device array handed to k_apply (see IngestArgs::box_ptr)
+    // peer-memory boxes: every rank exports one inbox of P slices through CUDA IPC; senders store straight into it
+    bool p2p = false;
+    uint64_t p2p_cap = 0;              // entries per (sender, owner) slice
+    ulonglong2* p2p_inbox = nullptr;   // [P][p2p_cap], slice q is written by rank q
+    std::vector<void*> p2p_peer;       // opened IPC mappings of the peers' inboxes
+    unsigned long long* out_cursor = nullptr;  // [P] box cursors, [P] "an entry was dropped" marker, then exchange scratch
     uint64_t box_cap = 0, inbox_cap = 0;
     std::vector<unsigned long long> box_sent, recv_done;  // per peer: entries already exchanged by an earlier ptx_finalize
     int64_t ds_entries_bound = 0;  // upper bound of the entries in the id set (own records + merged foreign ids + returned mixed ids)
@@ -152,6 +160,7 @@ struct ptx_ctx {
     std::vector<EvPair> ev_count, ev_ingest, ev_apply, ev_final;
     // multi-GPU
     ncclComm_t comm = nullptr;
+    ncclComm_t comm_x = nullptr;  // second communicator (ncclCommSplit) for the id-box exchange on the side stream; == comm if unavailable
     int n_ranks = 1, rank = 0;
 };
 
@@ -281,7 +290,7 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.hash_lo = ch.hash_lo;
     a.nodes = ch.nodes;
     a.cursors = reinterpret_cast<uint32_t*>(ch.cursors + 1);
-    a.outbox = ctx->comm ? ctx->outbox : nullptr;
+    a.box_ptr = ctx->comm ? ctx->d_box_ptr : nullptr;
     a.out_cursor = ctx->out_cursor;
     a.box_cap = ctx->box_cap;
     a.n_ranks = (uint32_t)ctx->n_ranks;
@@ -498,18 +507,19 @@ int nccl_check(ptx_ctx* ctx, int r, const char* what) {
 int xchg_ensure(ptx_ctx* ctx, int64_t records) {
     const uint64_t P = (uint64_t)ctx->n_ranks;
     uint64_t need = (uint64_t)records / P + (uint64_t)records / (4 * P) + 4096;
-    if (ctx->test_box_cap > 0 && ctx->box_cap == 0) need = (uint64_t)ctx->test_box_cap;
+    if (ctx->test_box_cap > 0 && ctx->box_cap == 0) { need = (uint64_t)ctx->test_box_cap; ctx->test_box_cap = 0; }
     if (!ctx->xs) {
         CU(cudaStreamCreateWithFlags(&ctx->xs, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&ctx->ev_x0, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_x1, cudaEventDisableTiming));
-        // [0,P) box cursors, [P] "a box overflowed", then the all-gathered (P+1) x P matrix and 2P merge parameters
+        // [0,P) box cursors, [P] "an entry was dropped", then the all-gathered (P+1) x P matrix and 2P merge parameters
         int rc = dalloc(ctx, &ctx->out_cursor, (size_t)(P + 1) * (P + 1) + 2 * P + 8);
         if (rc) return rc;
+        if (!ctx->d_box_ptr && (rc = dalloc(ctx, &ctx->d_box_ptr, (size_t)P))) return rc;
         ctx->box_sent.assign(P, 0);
         ctx->recv_done.assign(P, 0);
     }
-    if (need <= ctx->box_cap) return PTX_OK;
+    if (ctx->p2p || need <= ctx->box_cap) return PTX_OK;  // peer-memory boxes have a fixed size (overflow -> restart without them)
     const uint64_t cap = need + need / 8;
     ulonglong2* nout = nullptr;
     CU(cudaStreamSynchronize(ctx->st));
@@ -522,8 +532,9 @@ int xchg_ensure(ptx_ctx* ctx, int64_t records) {
     dfree(ctx->outbox);
     ctx->outbox = nout;
     ctx->box_cap = cap;
-    // the capacity travels with the cursors in the all-gather of exchange_begin (a fill above it = entries dropped)
-    CU(cudaMemcpy(ctx->out_cursor + P, &ctx->box_cap, sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    std::vector<ulonglong2*> ptrs(P);
+    for (uint64_t r = 0; r < P; ++r) ptrs[r] = nout + r * cap;
+    CU(cudaMemcpy(ctx->d_box_ptr, ptrs.data(), P * sizeof(ulonglong2*), cudaMemcpyHostToDevice));
     return PTX_OK;
 }
 
@@ -579,26 +590,27 @@ int exchange_begin(ptx_ctx* ctx) {
         if ((rc = nccl_check(ctx, g_nccl.AllGather(d_cur, d_all, P + 1, ncclUint64, ctx->comm, ctx->st), "ncclAllGather(box fills)"))) return rc;
         CU(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaStreamSynchronize(ctx->st));
-        // all[q*(P+1) + r] = entries rank q has appended for rank r so far; a fill above q's capacity means entries
-        // were dropped there.  Every rank sees the same matrix, so all of them take the same branch.
+        // all[q*(P+1) + r] = entries rank q has appended for rank r so far, all[q*(P+1) + P] != 0 if a box of rank q was
+        // full and entries were dropped.  Every rank sees the same matrix, so all of them take the same branch.
         unsigned long long worst = 0;
         bool over = false;
         for (int q = 0; q < P; ++q) {
-            const unsigned long long capq = all[(size_t)q * (P + 1) + P];
-            for (int r = 0; r < P; ++r) {
-                const unsigned long long v = all[(size_t)q * (P + 1) + r];
-                worst = std::max(worst, v);
-                if (v > capq) over = true;
-            }
+            if (all[(size_t)q * (P + 1) + P]) over = true;  // rank q dropped an entry
+            for (int r = 0; r < P; ++r) worst = std::max(worst, all[(size_t)q * (P + 1) + r]);
         }
         if (!over) break;
         if (attempt >= 2) return fail(ctx, PTX_E_STATE, "id-group exchange: outboxes still overflow after being enlarged");
         // rare: some rank met far more foreign ids than planned.  Start the id sets over everywhere with boxes that
         // hold the fullest one seen, and rebuild them from the record tables (no text is re-read).
+        if (ctx->p2p) {  // the peer-memory slices cannot grow: continue with local outboxes + ncclSend/ncclRecv
+            ctx->p2p = false;
+            dfree(ctx->outbox);
+            ctx->box_cap = 0;
+        }
         if ((rc = xchg_ensure(ctx, (int64_t)((worst + worst / 4) * (unsigned long long)P)))) return rc;
         CU(cudaMemsetAsync(ctx->d_ds, 0, ctx->ds_cap * sizeof(ulonglong2), ctx->st));
         CU(cudaMemsetAsync(ctx->d_flags, 0, 3 * sizeof(uint32_t), ctx->st));
-        CU(cudaMemsetAsync(d_cur, 0, P * sizeof(unsigned long long), ctx->st));
+        CU(cudaMemsetAsync(d_cur, 0, (P + 1) * sizeof(unsigned long long), ctx->st));
         std::fill(ctx->box_sent.begin(), ctx->box_sent.end(), 0ull);
         std::fill(ctx->recv_done.begin(), ctx->recv_done.end(), 0ull);
         for (auto& ch : ctx->chunks) {
@@ -615,7 +627,7 @@ int exchange_begin(ptx_ctx* ctx) {
         send_n[q] = all[(size_t)ctx->rank * (P + 1) + q] - ctx->box_sent[q];
         const unsigned long long cum = all[(size_t)q * (P + 1) + ctx->rank];
         recv_n[q] = cum - ctx->recv_done[q];
-        roff[q] = n_recv;
+        roff[q] = ctx->p2p ? (unsigned long long)q * ctx->p2p_cap + ctx->recv_done[q] : n_recv;  // entries rank q stored in its slice of my inbox
         n_recv += recv_n[q];
         max_recv = std::max(max_recv, recv_n[q]);
         recv_total += cum;
@@ -623,7 +635,7 @@ int exchange_begin(ptx_ctx* ctx) {
     // the id set now also holds the foreign ids this rank owns
     ctx->ds_entries_bound = std::max<int64_t>(ctx->ds_entries_bound, ctx->ds_records + (int64_t)recv_total);
     if ((rc = ds_ensure_total(ctx, ctx->ds_entries_bound))) return rc;
-    if (n_recv > ctx->inbox_cap) {
+    if (!ctx->p2p && n_recv > ctx->inbox_cap) {
         CU(cudaStreamSynchronize(ctx->xs));
         dfree(ctx->inbox);
         ctx->inbox_cap = n_recv + n_recv / 8 + 1024;
@@ -640,21 +652,94 @@ int exchange_begin(ptx_ctx* ctx) {
     CU(cudaEventRecord(ctx->ev_x0, ctx->st));
     CU(cudaStreamWaitEvent(ctx->xs, ctx->ev_x0, 0));
     cudaStream_t xs = ctx->xs;
-    g_nccl.GroupStart();
-    for (int q = 0; q < P; ++q) {
-        if (q == ctx->rank) continue;
-        if (send_n[q]) g_nccl.Send(ctx->outbox + (uint64_t)q * ctx->box_cap + ctx->box_sent[q], send_n[q] * 2, ncclUint64, q, ctx->comm, xs);
-        if (recv_n[q]) g_nccl.Recv(ctx->inbox + roff[q], recv_n[q] * 2, ncclUint64, q, ctx->comm, xs);
+    Trace trx(xs);
+    if (!ctx->p2p) {
+        g_nccl.GroupStart();
+        for (int q = 0; q < P; ++q) {
+            if (q == ctx->rank) continue;
+            if (send_n[q]) g_nccl.Send(ctx->outbox + (uint64_t)q * ctx->box_cap + ctx->box_sent[q], send_n[q] * 2, ncclUint64, q, ctx->comm_x, xs);
+            if (recv_n[q]) g_nccl.Recv(ctx->inbox + roff[q], recv_n[q] * 2, ncclUint64, q, ctx->comm_x, xs);
+        }
+        if ((rc = nccl_check(ctx, g_nccl.GroupEnd(), "ncclSend/Recv(id boxes)"))) return rc;
+        trx.mark("xchg send/recv");
     }
-    if ((rc = nccl_check(ctx, g_nccl.GroupEnd(), "ncclSend/Recv(id boxes)"))) return rc;
-    launch_ds_merge_boxes(ctx->inbox, d_par, d_par + P, (uint32_t)nb, max_recv, ctx->d_ds, 64 - log2_ceil(ctx->ds_cap), ctx->ds_cap - 1, ctx->d_flags, xs);
-    if ((rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 2, ncclUint32, ncclMax, ctx->comm, xs), "ncclAllReduce(flags)"))) return rc;
+    // peer-memory boxes: the entries are already here - k_apply of the other ranks stored them into this rank's inbox
+    // over NVLink; the all-gather above ordered this point behind those kernels
+    launch_ds_merge_boxes(ctx->p2p ? ctx->p2p_inbox : ctx->inbox, d_par, d_par + P, (uint32_t)nb, max_recv, ctx->d_ds, 64 - log2_ceil(ctx->ds_cap), ctx->ds_cap - 1, ctx->d_flags, xs);
+    trx.mark("xchg merge");
+    if ((rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 2, ncclUint32, ncclMax, ctx->comm_x, xs), "ncclAllReduce(flags)"))) return rc;
+    trx.mark("xchg flags");
     CU(cudaEventRecord(ctx->ev_x1, xs));
     for (int q = 0; q < P; ++q) {
         if (q == ctx->rank) continue;
         ctx->box_sent[q] += send_n[q];
         ctx->recv_done[q] += recv_n[q];
     }
+    return PTX_OK;
+}
+
+// Peer-memory id boxes (all ranks on one NVLink/NVSwitch node): every rank allocates an inbox of P slices, exports it
+// with CUDA IPC, and maps the inboxes of the others.  k_apply then stores the {hash, state} of a record straight
+// into the owner's inbox, so that nothing is left to send when ptx_finalize runs.  Needs the expected record count
+// (ptx_reserve before ptx_comm_init) on every rank; any failure leaves the ncclSend/ncclRecv path in place -
+// decided collectively, so that all ranks take the same path.
+int p2p_setup(ptx_ctx* ctx) {
+    const int P = ctx->n_ranks;
+    const int64_t test_cap = ctx->test_box_cap;
+    ctx->test_box_cap = 0;
+    int rc = xchg_ensure(ctx, 0);  // stream, events, cursors, box pointer array
+    if (rc) return rc;
+    unsigned long long* d_v = nullptr;
+    uint8_t* d_h = nullptr;
+    if ((rc = dalloc(ctx, &d_v, (size_t)P + 1)) || (rc = dalloc(ctx, &d_h, (size_t)(P + 1) * sizeof(cudaIpcMemHandle_t)))) return rc;
+    std::vector<unsigned long long> v(P, 0);
+    unsigned long long mine = (unsigned long long)std::max<int64_t>(ctx->reserve_records, 0);
+    CU(cudaMemcpyAsync(d_v + P, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->st));
+    if ((rc = nccl_check(ctx, g_nccl.AllGather(d_v + P, d_v, 1, ncclUint64, ctx->comm, ctx->st), "ncclAllGather(reserve)"))) return rc;
+    CU(cudaMemcpyAsync(v.data(), d_v, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    unsigned long long lo = ~0ull, hi = 0;
+    for (auto x : v) { lo = std::min(lo, x); hi = std::max(hi, x); }
+    bool ok = lo > 0;  // every rank gave a size hint
+    const uint64_t cap = !ok ? 0 : test_cap > 0 ? (uint64_t)test_cap : hi / P + hi / (4 * P) + 4096;
+    cudaIpcMemHandle_t hmine;
+    memset(&hmine, 0, sizeof hmine);
+    if (ok) {
+        ok = cudaMalloc((void**)&ctx->p2p_inbox, (size_t)P * cap * sizeof(ulonglong2)) == cudaSuccess &&
+             cudaIpcGetMemHandle(&hmine, ctx->p2p_inbox) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+    }
+    std::vector<cudaIpcMemHandle_t> hs(P);
+    CU(cudaMemcpyAsync(d_h + (size_t)P * sizeof hmine, &hmine, sizeof hmine, cudaMemcpyHostToDevice, ctx->st));
+    if ((rc = nccl_check(ctx, g_nccl.AllGather(d_h + (size_t)P * sizeof hmine, d_h, sizeof hmine, ncclUint8, ctx->comm, ctx->st), "ncclAllGather(ipc handles)"))) return rc;
+    CU(cudaMemcpyAsync(hs.data(), d_h, (size_t)P * sizeof hmine, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->p2p_peer.assign(P, nullptr);
+    std::vector<ulonglong2*> ptrs(P, nullptr);
+    for (int q = 0; ok && q < P; ++q) {
+        if (q == ctx->rank) continue;
+        void* base = nullptr;
+        if (cudaIpcOpenMemHandle(&base, hs[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        ctx->p2p_peer[q] = base;
+        ptrs[q] = reinterpret_cast<ulonglong2*>(base) + (uint64_t)ctx->rank * cap;  // my slice of rank q's inbox
+    }
+    // all or nothing
+    unsigned long long good = ok ? 1ull : 0ull;
+    CU(cudaMemcpyAsync(d_v + P, &good, sizeof good, cudaMemcpyHostToDevice, ctx->st));
+    if ((rc = nccl_check(ctx, g_nccl.AllReduce(d_v + P, d_v, 1, ncclUint64, ncclMin, ctx->comm, ctx->st), "ncclAllReduce(p2p ok)"))) return rc;
+    CU(cudaMemcpyAsync(&good, d_v, sizeof good, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    cudaFree(d_v);
+    cudaFree(d_h);
+    if (!good) {
+        for (void*& m : ctx->p2p_peer) { if (m) cudaIpcCloseMemHandle(m); m = nullptr; }
+        dfree(ctx->p2p_inbox);
+        return PTX_OK;
+    }
+    CU(cudaMemcpy(ctx->d_box_ptr, ptrs.data(), (size_t)P * sizeof(ulonglong2*), cudaMemcpyHostToDevice));
+    ctx->p2p = true;
+    ctx->p2p_cap = cap;
+    ctx->box_cap = cap;
     return PTX_OK;
 }
 
@@ -699,6 +784,9 @@ void ptx_destroy(ptx_ctx* ctx) {
     for (auto& ch : ctx->chunks) chunk_free(ch);
     for (auto& ch : ctx->pool) chunk_free(ch);
     dfree(ctx->scratch);
+    for (void* m : ctx->p2p_peer) if (m) cudaIpcCloseMemHandle(m);
+    ctx->p2p_peer.clear();
+    dfree(ctx->p2p_inbox); dfree(ctx->d_box_ptr);
     dfree(ctx->outbox); dfree(ctx->inbox); dfree(ctx->out_cursor);
     if (ctx->xs) cudaStreamDestroy(ctx->xs);
     if (ctx->ev_x0) cudaEventDestroy(ctx->ev_x0);
@@ -710,6 +798,7 @@ void ptx_destroy(ptx_ctx* ctx) {
     ev_clear(ctx->ev_ingest);
     ev_clear(ctx->ev_apply);
     ev_clear(ctx->ev_final);
+    if (ctx->comm_x && ctx->comm_x != ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm_x);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
@@ -1116,8 +1205,42 @@ int ptx_finalize(ptx_ctx* ctx) {
             }
             return PTX_OK;
         };
+        auto reduce_and_stats = [&]() -> int {
+            launch_ninfo_full(g.ninfo, g.full, g.N, 0, ctx->st);
+            if (ctx->comm) {
+                // int64 sums and flag maxima are order-free: bit-exact for any shard count
+                int rc;
+                if ((rc = nccl_check(ctx, g_nccl.AllReduce(g.bases, g.bases, g.N, ncclUint64, ncclSum, ctx->comm, ctx->st), "ncclAllReduce(bases)"))) return rc;
+                if (g.T > 0 && (rc = nccl_check(ctx, g_nccl.AllReduce(g.trio_bases, g.trio_bases, g.T, ncclUint64, ncclSum, ctx->comm, ctx->st), "ncclAllReduce(trio_bases)"))) return rc;
+                if ((rc = nccl_check(ctx, g_nccl.AllReduce(g.full, g.full, g.N, ncclUint8, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(full)"))) return rc;
+                if ((rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_err, ctx->d_err, S, ncclUint32, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(err)"))) return rc;
+                // bitmap OR: all-gather the packed words, OR locally (NCCL has no bitwise-or reduction)
+                if ((rc = scratch_reserve(ctx, (size_t)ctx->n_ranks * g.n_bit_words * sizeof(uint32_t) + 4096))) return rc;
+                ctx->scratch_off = 0;
+                uint32_t* all = scratch_take<uint32_t>(ctx, (size_t)ctx->n_ranks * g.n_bit_words);
+                if ((rc = nccl_check(ctx, g_nccl.AllGather(g.bits, all, g.n_bit_words, ncclUint32, ctx->comm, ctx->st), "ncclAllGather(bits)"))) return rc;
+                for (int r = 0; r < ctx->n_ranks; ++r)
+                    if (r != ctx->rank) launch_or_words(g.bits, all + (size_t)r * g.n_bit_words, g.n_bit_words, ctx->st);
+            }
+            tr.mark("final reductions");
+            CU(cudaMemsetAsync(g.path_cov_sum, 0, std::max<int64_t>(g.Htot, 1) * sizeof(unsigned long long), ctx->st));
+            CU(cudaMemsetAsync(g.hap_nz, 0, std::max<int64_t>(g.Htot, 1) * sizeof(unsigned long long), ctx->st));
+            launch_cov(g, ctx->st);
+            launch_path_cov_sum(g, ctx->st);
+            launch_hap_nz(g, ctx->st);
+            return PTX_OK;
+        };
+        if (ctx->comm && ctx->cov_reduced) return fail(ctx, PTX_E_STATE, "multi-GPU: coverage already reduced");
         if (mixed) { int rc = start_over(); if (rc) return rc; }
         cover_pending(mixed);
+        bool reduced = false;
+        if (ctx->comm && ctx->comm_x != ctx->comm) {
+            // the exchange runs on its own communicator and stream: reduce optimistically (no mixed id group is
+            // the common case) instead of idling until the owner-side merge has finished
+            int rc = reduce_and_stats();
+            if (rc) return rc;
+            reduced = true;
+        }
         if (ctx->comm) {
             CU(cudaStreamWaitEvent(ctx->st, ctx->ev_x1, 0));
             CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));
@@ -1131,33 +1254,15 @@ int ptx_finalize(ptx_ctx* ctx) {
                 int rc = start_over();
                 if (rc) return rc;
                 cover_pending(true);
+                reduced = false;
             }
         }
         tr.mark("final replay/cover");
-        launch_ninfo_full(g.ninfo, g.full, g.N, 0, ctx->st);
-        if (ctx->comm) {
-            // int64 sums and flag maxima are order-free: bit-exact for any shard count
-            if (ctx->cov_reduced) return fail(ctx, PTX_E_STATE, "multi-GPU: coverage already reduced");
-            ctx->cov_reduced = true;
-            int rc;
-            if ((rc = nccl_check(ctx, g_nccl.AllReduce(g.bases, g.bases, g.N, ncclUint64, ncclSum, ctx->comm, ctx->st), "ncclAllReduce(bases)"))) return rc;
-            if (g.T > 0 && (rc = nccl_check(ctx, g_nccl.AllReduce(g.trio_bases, g.trio_bases, g.T, ncclUint64, ncclSum, ctx->comm, ctx->st), "ncclAllReduce(trio_bases)"))) return rc;
-            if ((rc = nccl_check(ctx, g_nccl.AllReduce(g.full, g.full, g.N, ncclUint8, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(full)"))) return rc;
-            if ((rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_err, ctx->d_err, S, ncclUint32, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(err)"))) return rc;
-            // bitmap OR: all-gather the packed words, OR locally (NCCL has no bitwise-or reduction)
-            if ((rc = scratch_reserve(ctx, (size_t)ctx->n_ranks * g.n_bit_words * sizeof(uint32_t) + 4096))) return rc;
-            ctx->scratch_off = 0;
-            uint32_t* all = scratch_take<uint32_t>(ctx, (size_t)ctx->n_ranks * g.n_bit_words);
-            if ((rc = nccl_check(ctx, g_nccl.AllGather(g.bits, all, g.n_bit_words, ncclUint32, ctx->comm, ctx->st), "ncclAllGather(bits)"))) return rc;
-            for (int r = 0; r < ctx->n_ranks; ++r)
-                if (r != ctx->rank) launch_or_words(g.bits, all + (size_t)r * g.n_bit_words, g.n_bit_words, ctx->st);
+        if (!reduced) {
+            int rc = reduce_and_stats();
+            if (rc) return rc;
         }
-        tr.mark("final reductions");
-        CU(cudaMemsetAsync(g.path_cov_sum, 0, std::max<int64_t>(g.Htot, 1) * sizeof(unsigned long long), ctx->st));
-        CU(cudaMemsetAsync(g.hap_nz, 0, std::max<int64_t>(g.Htot, 1) * sizeof(unsigned long long), ctx->st));
-        launch_cov(g, ctx->st);
-        launch_path_cov_sum(g, ctx->st);
-        launch_hap_nz(g, ctx->st);
+        if (ctx->comm) ctx->cov_reduced = true;
     }
     if (ctx->comm && !(ctx->graphs_committed && g.N > 0)) {  // no coverage pass ran: join the exchange here
         CU(cudaStreamWaitEvent(ctx->st, ctx->ev_x1, 0));
@@ -1212,7 +1317,7 @@ static int reset_impl(ptx_ctx* ctx, bool keep_buffers) {
     if (ctx->d_hist) CU(cudaMemsetAsync(ctx->d_hist, 0, S * 4 * sizeof(unsigned long long), ctx->st));
     CU(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(uint32_t), ctx->st));
     if (ctx->out_cursor) {
-        CU(cudaMemsetAsync(ctx->out_cursor, 0, (size_t)ctx->n_ranks * sizeof(unsigned long long), ctx->st));
+        CU(cudaMemsetAsync(ctx->out_cursor, 0, ((size_t)ctx->n_ranks + 1) * sizeof(unsigned long long), ctx->st));
         std::fill(ctx->box_sent.begin(), ctx->box_sent.end(), 0ull);
         std::fill(ctx->recv_done.begin(), ctx->recv_done.end(), 0ull);
     }
@@ -1535,6 +1640,17 @@ int ptx_comm_init(ptx_ctx* ctx, int n_ranks, int rank, const void* id128) {
     if (rc) return rc;
     ctx->n_ranks = n_ranks;
     ctx->rank = rank;
+    // a second communicator over the same ranks carries the id-box exchange on the side stream, so that it really
+    // runs beside the reductions of the main stream (operations on ONE communicator execute in issue order)
+    ctx->comm_x = ctx->comm;
+    if (g_nccl.CommSplit && !getenv("PTX_NO_COMM_SPLIT")) {
+        ncclComm_t c2 = nullptr;
+        if (g_nccl.CommSplit(ctx->comm, 0, rank, &c2, nullptr) == 0 && c2) ctx->comm_x = c2;
+    }
+    if (n_ranks > 1 && !getenv("PTX_NO_P2P")) {
+        rc = p2p_setup(ctx);
+        if (rc) return rc;
+    }
     return PTX_OK;
 }
 
@@ -1557,10 +1673,10 @@ int ptx_stats_json(ptx_ctx* ctx, char* buf, size_t cap) {
     snprintf(buf, cap,
              "{\"records\": %lld, \"chunks\": %zu, \"text_bytes\": %zu, \"nodes\": %lld, \"paths\": %lld, \"path_steps\": %lld, "
              "\"unique_trios\": %lld, \"bit_words\": %llu, \"id_set_slots\": %llu, \"ids_unique\": %d, \"mixed_groups\": %d, "
-             "\"count_ms\": %.4f, \"ingest_ms\": %.4f, \"apply_ms\": %.4f, \"ingest_launches\": %zu, \"finalize_ms\": %.4f, \"kernel_launches\": %lld, \"ranks\": %d}",
+             "\"count_ms\": %.4f, \"ingest_ms\": %.4f, \"apply_ms\": %.4f, \"ingest_launches\": %zu, \"finalize_ms\": %.4f, \"kernel_launches\": %lld, \"ranks\": %d, \"p2p_boxes\": %d}",
              (long long)ctx->total_records, ctx->chunks.size(), text, (long long)ctx->g.N, (long long)ctx->g.Htot, (long long)ctx->g.P,
              (long long)ctx->g.T, (unsigned long long)ctx->g.n_bit_words, (unsigned long long)ctx->ds_cap, ctx->h_flags[0] == 0 ? 1 : 0,
-             ctx->h_flags[1] != 0 ? 1 : 0, ev_sum(ctx->ev_count), ev_sum(ctx->ev_ingest), ev_sum(ctx->ev_apply), ctx->ev_ingest.size(), ev_sum(ctx->ev_final), (long long)kernel_launch_count(), ctx->n_ranks);
+             ctx->h_flags[1] != 0 ? 1 : 0, ev_sum(ctx->ev_count), ev_sum(ctx->ev_ingest), ev_sum(ctx->ev_apply), ctx->ev_ingest.size(), ev_sum(ctx->ev_final), (long long)kernel_launch_count(), ctx->n_ranks, ctx->p2p ? 1 : 0);
     return PTX_OK;
 }
 

@@ -86,7 +86,10 @@ struct IngestArgs {
     uint32_t* nodes;            // [<= text bytes / 2] raw node ids of eligible records' walks
     uint32_t* cursors;          // [0] next record-table entry, [1] next node slot
     // multi-GPU: id entries routed to the rank owning their hash (written by k_apply<CLASSIFY>, sent at finalize)
-    ulonglong2* outbox;         // [n_ranks][box_cap] {hash, state} of records whose id another rank owns; null on one GPU
+    // multi-GPU (null on one GPU): box_ptr[q] = where {hash, state} of records whose id rank q owns are appended -
+    // this rank's slice of q's inbox in PEER memory (stores travel over NVLink while k_apply runs), or a local outbox
+    // that ptx_finalize sends with ncclSend when peer memory is not set up
+    ulonglong2* const* box_ptr;
     unsigned long long* out_cursor;  // [n_ranks]
     uint64_t box_cap;
     uint32_t n_ranks, rank;

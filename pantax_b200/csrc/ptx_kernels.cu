@@ -922,7 +922,7 @@ __global__ void __launch_bounds__(256) k_apply(const IngestArgs a, uint32_t n_en
     h.hi = mb.w;
     if (labelled && (MODE & (MODE_CLASSIFY | MODE_KEEPMASK | MODE_REBOX))) h.lo = a.hash_lo[e];
     if (MODE & (MODE_CLASSIFY | MODE_REBOX)) {
-        if (a.outbox == nullptr) {
+        if (a.box_ptr == nullptr) {
             if ((MODE & MODE_CLASSIFY) && labelled) ds_insert(a.ds, a.ds_shift, a.ds_mask, h, eligible, label, a.flags);
         } else {
             // multi-GPU: a read id is kept only by the rank that owns its hash.  Own ids go into the local set; the
@@ -941,7 +941,8 @@ __global__ void __launch_bounds__(256) k_apply(const IngestArgs a, uint32_t n_en
             base = __shfl_sync(0xffffffffu, base, leader);
             if (dest != 0xFFFFFFFFu) {
                 const unsigned long long pos = base + __popc(peers & ((1u << lane) - 1u));
-                if (pos < a.box_cap) a.outbox[(uint64_t)dest * a.box_cap + pos] = ent;  // else: the cursor tells the host
+                if (pos < a.box_cap) a.box_ptr[dest][pos] = ent;  // local outbox, or the owner's inbox over NVLink
+                else atomicOr(a.out_cursor + a.n_ranks, 1ull);  // entry dropped: sticky marker, all-gathered with the cursors
             }
         }
     }

@@ -22,8 +22,12 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    for name, params, n, box in (("unique ids", NASTY, 200000, None), ("duplicate ids across shards", NASTY_DUP, 100000, None),
-                                 ("duplicate ids, outboxes too small at first (restart path)", NASTY_DUP, 100000, "64")):
+    # reserve > 0 before comm_init: id boxes in peer memory (CUDA IPC, stores over NVLink); else ncclSend/ncclRecv
+    for name, params, n, box, reserve in (("unique ids", NASTY, 200000, None, 0), ("duplicate ids across shards", NASTY_DUP, 100000, None, 0),
+                                          ("duplicate ids, outboxes too small at first (restart path)", NASTY_DUP, 100000, "64", 0),
+                                          ("unique ids, peer-memory boxes", NASTY, 200000, None, 120000),
+                                          ("duplicate ids, peer-memory boxes", NASTY_DUP, 100000, None, 60000),
+                                          ("duplicate ids, peer-memory boxes too small (restart on the NCCL path)", NASTY_DUP, 100000, "64", 60000)):
         if box:
             os.environ["PTX_TEST_BOX_CAP"] = box
         else:
@@ -36,6 +40,8 @@ def main():
         for s, g in enumerate(graphs):
             ctx.upload_graph(s, g[0], g[1])
         ctx.commit_graphs()
+        if reserve:
+            ctx.reserve(reserve)
         uid = [api.PantaxGpu.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(world, rank, uid[0])
@@ -56,7 +62,7 @@ def main():
         finally:
             api.PantaxGpu.num_records = property(lambda self: self._L.ptx_num_records(self._h))
         if rank == 0:
-            print(f"[multigpu_check] {name}: {world} ranks, {o.n_records} records, ids_unique={o.ids_unique}, "
+            print(f"[multigpu_check] {name}: {world} ranks, {o.n_records} records, p2p={ctx.stats().get('p2p_boxes')}, ids_unique={o.ids_unique}, "
                   f"mixed-group reads dropped={o.mixed_dropped}: bit-exact on every rank", flush=True)
         dist.barrier()
         ctx.close()
