@@ -86,7 +86,16 @@ struct Chunk {
     longlong2* meta_a = nullptr;
     unsigned long long* hash_lo = nullptr;
     uint32_t* nodes = nullptr;
-    unsigned long long* cursors = nullptr;  // [0] total line slots (K1), then reused as 2 x uint32 cursors
+    unsigned long long* cursors = nullptr;  // 8 x u64: words [0..3] as uint32 = k_ingest cursors (entry, node, rows, abandoned); [4] = line slots (count pass)
+    uint32_t* h_cur = nullptr;              // pinned copy of the four uint32 cursors (single-pass chunks)
+    cudaEvent_t done = nullptr;             // recorded behind that copy
+    uint4* tile_info = nullptr;             // single-pass: per tile {first entry, line slots, GAF rows, 0}
+    uint16_t* row_key = nullptr;            // single-pass: row of the entry within its tile
+    unsigned long long* chunk_hist = nullptr;  // single-pass: species counts of this chunk (merged if not abandoned)
+    uint32_t tile_info_cap = 0;
+    size_t hist_cap = 0;
+    bool single_pass = false, pending = false, labels_ready = false;
+    int64_t est_records = 0;
     int64_t slots_cap = 0, nodes_cap = 0;
     int64_t n_slots = 0;
     uint32_t tiles_cap = 0;
@@ -133,6 +142,10 @@ struct ptx_ctx {
     std::vector<Chunk> chunks;
     std::vector<uint8_t> carry;
     int64_t total_records = 0;
+    // single-pass ingest: line statistics of the chunks seen so far, and records of chunks whose counts are still in flight
+    double seen_mean_line = 0, seen_slots_per_row = 1;
+    int64_t pending_records = 0;
+    bool single_pass_ok = true;  // PTX_NO_SINGLE_PASS=1 forces the count pass for every chunk
     uint32_t* d_labels_in = nullptr;  // ptx_ingest_labels: species label of GAF rows [0, labels_in_n), row = position over all chunks
     int64_t labels_in_n = 0, labels_in_cap = 0;
     bool dirty = false;          // something ingested / committed since the last finalize
@@ -289,7 +302,8 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.meta_a = ch.meta_a;
     a.hash_lo = ch.hash_lo;
     a.nodes = ch.nodes;
-    a.cursors = reinterpret_cast<uint32_t*>(ch.cursors + 1);
+    a.cursors = reinterpret_cast<uint32_t*>(ch.cursors);
+
     a.box_ptr = ctx->comm ? ctx->d_box_ptr : nullptr;
     a.out_cursor = ctx->out_cursor;
     a.box_cap = ctx->box_cap;
@@ -309,6 +323,13 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.tt = g.T > 0 ? g.tt : nullptr;
     a.tt_mask = g.tt_mask;
     a.trio_bases = g.trio_bases;
+    if (ch.single_pass) {
+        a.micro_base = nullptr;
+        a.tile_info = ch.tile_info;
+        a.row_key = ch.row_key;
+        a.slots_cap = (uint32_t)std::min<int64_t>(ch.slots_cap, 0xFFFFFFF0ll);
+        a.hist = ch.chunk_hist;
+    }
     return a;
 }
 
@@ -365,20 +386,69 @@ void chunk_free(Chunk& ch) {
     dfree(ch.scan_scratch);
     dfree(ch.labels);
     dfree(ch.meta_b); dfree(ch.meta_a); dfree(ch.hash_lo); dfree(ch.nodes); dfree(ch.cursors);
+    dfree(ch.tile_info); dfree(ch.row_key); dfree(ch.chunk_hist);
+    if (ch.h_cur) cudaFreeHost(ch.h_cur);
+    ch.h_cur = nullptr;
+    if (ch.done) cudaEventDestroy(ch.done);
+    ch.done = nullptr;
     if (ch.copied) cudaEventDestroy(ch.copied);
     ch.copied = nullptr;
 }
 
 int xchg_ensure(ptx_ctx* ctx, int64_t records);
 
-// classify (+ optimistic coverage) pass over one chunk whose text is resident
-int chunk_process(ptx_ctx* ctx, Chunk& ch) {
-    if (ctx->cov_reduced) return fail(ctx, PTX_E_STATE, "multi-GPU: coverage already reduced by ptx_finalize; ptx_reset before ingesting more");
-    if (ch.n == 0) { ch.n_tiles = 0; ch.ingested = true; ch.covered = true; return PTX_OK; }
+// (re)allocate the record table of a chunk for `slots` line slots
+int chunk_table_ensure(ptx_ctx* ctx, Chunk& ch, int64_t slots) {
+    (void)ctx;
+    if (ch.slots_cap >= slots) return PTX_OK;
+    dfree(ch.meta_b); dfree(ch.meta_a); dfree(ch.hash_lo); dfree(ch.row_key);
+    const size_t cap = (size_t)std::max<int64_t>(slots, 1);
+    CU(cudaMalloc((void**)&ch.meta_b, cap * sizeof(uint4)));
+    CU(cudaMalloc((void**)&ch.meta_a, cap * sizeof(longlong2)));
+    CU(cudaMalloc((void**)&ch.hash_lo, cap * sizeof(unsigned long long)));
+    CU(cudaMalloc((void**)&ch.row_key, cap * sizeof(uint16_t)));
+    ch.slots_cap = (int64_t)cap;
+    return PTX_OK;
+}
+
+void chunk_pick_tile(ptx_ctx* ctx, Chunk& ch, double mean_line) {
+    // tile size: about one record per thread, 4 KB granularity
+    int rows = (int)(0.97 * INGEST_THREADS * mean_line / MICRO);
+    ch.rows = (uint32_t)std::min(8, std::max(1, rows));
+    if (ctx->force_rows > 0) ch.rows = (uint32_t)std::min(8, ctx->force_rows);
+    // long lines (HiFi/ONT walks): even the largest tile holds fewer lines than threads -> one warp per record
+    ch.long_mode = mean_line >= LONG_LINE_BYTES ? 1u : 0u;
+    if (ctx->force_long >= 0) ch.long_mode = (uint32_t)ctx->force_long;
+    const size_t tile = (size_t)ch.rows * MICRO;
+    ch.n_tiles = (uint32_t)((ch.n + tile - 1) / tile);
+}
+
+int chunk_common_begin(ptx_ctx* ctx, Chunk& ch) {
     // pad behind the text with newlines (terminates an unterminated last line; padding holds no records)
     ch.padded = padded_text_bytes(ch.n);
     CU(cudaMemsetAsync(ch.buf + PRE + ch.n, '\n', ch.padded - ch.n, ctx->st));
     ch.n_micro = (uint32_t)((ch.padded - OVER) / MICRO);
+    if (ch.n >= (1ull << 32)) return fail(ctx, PTX_E_INVALID, "a chunk must be smaller than 4 GiB (split the input)");
+    if (!ch.cursors) {
+        CU(cudaMalloc((void**)&ch.cursors, 8 * sizeof(unsigned long long)));
+        CU(cudaHostAlloc((void**)&ch.h_cur, 4 * sizeof(uint32_t), cudaHostAllocDefault));
+        CU(cudaEventCreateWithFlags(&ch.done, cudaEventDisableTiming));
+    }
+    CU(cudaMemsetAsync(ch.cursors, 0, 8 * sizeof(unsigned long long), ctx->st));
+    if (ch.nodes_cap < (int64_t)(ch.n / 2 + 16)) {  // a walk node takes at least two bytes of text
+        dfree(ch.nodes);
+        ch.nodes_cap = (int64_t)(ch.n / 2 + 16);
+        CU(cudaMalloc((void**)&ch.nodes, (size_t)ch.nodes_cap * sizeof(uint32_t)));
+    }
+    return PTX_OK;
+}
+
+// Exact pass: a count kernel numbers the GAF rows first (records per 4 KB + scan), the host reads the totals back
+// and sizes everything exactly.  Used for the first chunk of a ctx, with ptx_ingest_labels, and to redo a chunk
+// whose single-pass estimate was too small.
+int chunk_process_exact(ptx_ctx* ctx, Chunk& ch) {
+    int rc = chunk_common_begin(ctx, ch);
+    if (rc) return rc;
     if (ch.tiles_cap < ch.n_micro) {
         dfree(ch.tile_count);
         dfree(ch.tile_base);
@@ -388,45 +458,20 @@ int chunk_process(ptx_ctx* ctx, Chunk& ch) {
         CU(cudaMalloc((void**)&ch.scan_scratch, ((size_t)ch.n_micro / 2048 + 4) * sizeof(uint64_t)));
         ch.tiles_cap = ch.n_micro;
     }
-    if (ch.n >= (1ull << 32)) return fail(ctx, PTX_E_INVALID, "a chunk must be smaller than 4 GiB (split the input)");
-    if (!ch.cursors) CU(cudaMalloc((void**)&ch.cursors, 2 * sizeof(unsigned long long)));
-    CU(cudaMemsetAsync(ch.cursors, 0, 2 * sizeof(unsigned long long), ctx->st));
     ev_begin(ctx, ctx->ev_count);
-    launch_count_records(ch.buf + PRE, ch.n, ch.n_micro, ch.tile_count, ch.cursors, ctx->st);
+    launch_count_records(ch.buf + PRE, ch.n, ch.n_micro, ch.tile_count, ch.cursors + 4, ctx->st);
     launch_scan_u32(ch.tile_count, ch.tile_base, ch.n_micro, ch.scan_scratch, ctx->st);
     ev_end(ctx, ctx->ev_count);
     uint64_t total = 0, slots = 0;
     CU(cudaMemcpyAsync(&total, ch.tile_base + ch.n_micro, sizeof total, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaMemcpyAsync(&slots, ch.cursors, sizeof slots, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&slots, ch.cursors + 4, sizeof slots, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     ch.n_records = (int64_t)total;
     ch.n_slots = (int64_t)slots;
     if (slots > 0xFFFFFFF0ull) return fail(ctx, PTX_E_INVALID, "more than 2^32 lines in one chunk");
-    if (ch.slots_cap < ch.n_slots) {
-        dfree(ch.meta_b); dfree(ch.meta_a); dfree(ch.hash_lo);
-        const size_t cap = (size_t)std::max<int64_t>(ch.n_slots, 1);
-        CU(cudaMalloc((void**)&ch.meta_b, cap * sizeof(uint4)));
-        CU(cudaMalloc((void**)&ch.meta_a, cap * sizeof(longlong2)));
-        CU(cudaMalloc((void**)&ch.hash_lo, cap * sizeof(unsigned long long)));
-        ch.slots_cap = (int64_t)cap;
-    }
-    if (ch.nodes_cap < (int64_t)(ch.n / 2 + 16)) {  // a walk node takes at least two bytes of text
-        dfree(ch.nodes);
-        ch.nodes_cap = (int64_t)(ch.n / 2 + 16);
-        CU(cudaMalloc((void**)&ch.nodes, (size_t)ch.nodes_cap * sizeof(uint32_t)));
-    }
-    // tile size: about one record per thread (mean line length measured by K1), 4 KB granularity
-    {
-        const double mean_line = (double)ch.n / (double)std::max<uint64_t>(total, 1);
-        int rows = (int)(0.97 * INGEST_THREADS * mean_line / MICRO);
-        ch.rows = (uint32_t)std::min(8, std::max(1, rows));
-        if (ctx->force_rows > 0) ch.rows = (uint32_t)std::min(8, ctx->force_rows);
-        // long lines (HiFi/ONT walks): even the largest tile holds fewer lines than threads -> one warp per record
-        ch.long_mode = mean_line >= LONG_LINE_BYTES ? 1u : 0u;
-        if (ctx->force_long >= 0) ch.long_mode = (uint32_t)ctx->force_long;
-        const size_t tile = (size_t)ch.rows * MICRO;
-        ch.n_tiles = (uint32_t)((ch.n + tile - 1) / tile);
-    }
+    if ((rc = chunk_table_ensure(ctx, ch, ch.n_slots))) return rc;
+    const double mean_line = (double)ch.n / (double)std::max<uint64_t>(total, 1);
+    chunk_pick_tile(ctx, ch, mean_line);
     if (!ch.labels || ch.labels_cap < (int64_t)total) {
         dfree(ch.labels);
         CU(cudaMalloc((void**)&ch.labels, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
@@ -435,13 +480,14 @@ int chunk_process(ptx_ctx* ctx, Chunk& ch) {
     ch.row_base = ctx->total_records;
     if (ctx->labels_in_n > 0 && ch.row_base + ch.n_records > ctx->labels_in_n)
         return fail(ctx, PTX_E_STATE, "ptx_ingest_labels supplied fewer labels than the GAF has rows");
-    int rc = ds_ensure(ctx, ch.n_records);
-    if (rc) return rc;
+    if ((rc = ds_ensure(ctx, ch.n_records + ctx->pending_records))) return rc;
     ctx->ds_records += ch.n_records;
     if (ctx->comm) {
-        rc = xchg_ensure(ctx, std::max<int64_t>(ctx->ds_records, ctx->reserve_records));
+        rc = xchg_ensure(ctx, std::max<int64_t>(ctx->ds_records + ctx->pending_records, ctx->reserve_records));
         if (rc) return rc;
     }
+    ch.single_pass = false;
+    ch.labels_ready = true;
     IngestArgs a = make_args(ctx, ch);
     // multi-GPU: the coverage pass is deferred to ptx_finalize, where it overlaps the id-group exchange
     const bool cover = ctx->graphs_committed && ctx->g.N > 0 && !ctx->comm;
@@ -454,9 +500,123 @@ int chunk_process(ptx_ctx* ctx, Chunk& ch) {
     CU(cudaGetLastError());
     ch.ingested = true;
     ch.covered = cover;
+    ch.pending = false;
     ctx->total_records += ch.n_records;
     ctx->dirty = true;
+    if (total > 0) { ctx->seen_mean_line = mean_line; ctx->seen_slots_per_row = (double)slots / (double)total; }
     return PTX_OK;
+}
+
+// Single pass: the text is read ONCE and the host does not wait.  Tile size and table capacity come from the line
+// statistics of the chunks seen so far; k_ingest numbers the rows per tile (tile_info + row_key) instead of needing
+// a global row prefix, k_apply takes its entry count from the device cursor.  The counts come back asynchronously
+// and are looked at by chunk_resolve (finalize / getters); a too small estimate abandons the chunk on the device
+// (nothing of it is counted) and chunk_resolve redoes it with chunk_process_exact.
+int chunk_process_single(ptx_ctx* ctx, Chunk& ch) {
+    int rc = chunk_common_begin(ctx, ch);
+    if (rc) return rc;
+    chunk_pick_tile(ctx, ch, ctx->seen_mean_line);
+    const double est_rows = (double)ch.n / ctx->seen_mean_line;
+    const int64_t est_slots = (int64_t)(est_rows * ctx->seen_slots_per_row * 1.25) + 4096;
+    if (est_slots > 0xFFFFFFF0ll) return chunk_process_exact(ctx, ch);
+    if ((rc = chunk_table_ensure(ctx, ch, est_slots))) return rc;
+    if (ch.tile_info_cap < ch.n_tiles) {
+        dfree(ch.tile_info);
+        CU(cudaMalloc((void**)&ch.tile_info, (size_t)ch.n_tiles * sizeof(uint4)));
+        ch.tile_info_cap = ch.n_tiles;
+    }
+    const size_t S4 = std::max<size_t>(ctx->sp.size(), 1) * 4;
+    if (ch.hist_cap < S4) {
+        dfree(ch.chunk_hist);
+        CU(cudaMalloc((void**)&ch.chunk_hist, S4 * sizeof(unsigned long long)));
+        ch.hist_cap = S4;
+    }
+    CU(cudaMemsetAsync(ch.chunk_hist, 0, S4 * sizeof(unsigned long long), ctx->st));
+    ch.est_records = (int64_t)(est_rows * 1.25) + 4096;
+    if ((rc = ds_ensure(ctx, ctx->pending_records + ch.est_records))) return rc;
+    if (ctx->comm) {
+        rc = xchg_ensure(ctx, std::max<int64_t>(ctx->ds_records + ctx->pending_records + ch.est_records, ctx->reserve_records));
+        if (rc) return rc;
+    }
+    ctx->pending_records += ch.est_records;
+    ch.single_pass = true;
+    ch.labels_ready = false;
+    ch.n_slots = ch.slots_cap;  // until resolved
+    IngestArgs a = make_args(ctx, ch);
+    const bool cover = ctx->graphs_committed && ctx->g.N > 0 && !ctx->comm;
+    ev_begin(ctx, ctx->ev_ingest);
+    launch_ingest(a, ctx->st);
+    ev_end(ctx, ctx->ev_ingest);
+    ev_begin(ctx, ctx->ev_apply);
+    launch_apply(a, ENTRIES_FROM_DEVICE, MODE_CLASSIFY | (cover ? MODE_COVER : 0), ctx->st);
+    ev_end(ctx, ctx->ev_apply);
+    launch_hist_merge(ch.chunk_hist, ctx->d_hist, (uint32_t)S4, a.cursors, ctx->st);
+    CU(cudaMemcpyAsync(ch.h_cur, a.cursors, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaEventRecord(ch.done, ctx->st));
+    CU(cudaGetLastError());
+    ch.ingested = true;
+    ch.covered = cover;
+    ch.pending = true;
+    ctx->dirty = true;
+    return PTX_OK;
+}
+
+// Look at the counts of the single-pass chunks (waits for them); redo abandoned ones exactly.
+int chunks_resolve(ptx_ctx* ctx) {
+    for (auto& ch : ctx->chunks) {
+        if (!ch.pending) continue;
+        CU(cudaEventSynchronize(ch.done));
+        ch.pending = false;
+        ctx->pending_records -= ch.est_records;
+        if (ch.h_cur[3]) {  // estimate too small (or a tile with more than REC_CAP lines): nothing was counted
+            ch.ingested = false;
+            ch.covered = false;
+            int rc = chunk_process_exact(ctx, ch);
+            if (rc) return rc;
+            continue;
+        }
+        ch.n_slots = (int64_t)ch.h_cur[0];
+        ch.n_records = (int64_t)ch.h_cur[2];
+        ch.row_base = ctx->total_records;
+        ctx->total_records += ch.n_records;
+        ctx->ds_records += ch.n_records;
+        if (ch.n_records > 0) {
+            ctx->seen_mean_line = (double)ch.n / (double)ch.n_records;
+            ctx->seen_slots_per_row = (double)ch.n_slots / (double)ch.n_records;
+        }
+    }
+    return PTX_OK;
+}
+
+// labels[] of a single-pass chunk in GAF row order, built from the record table on demand
+int chunk_labels_materialize(ptx_ctx* ctx, Chunk& ch) {
+    if (ch.labels_ready || ch.n_records == 0) return PTX_OK;
+    if (!ch.labels || ch.labels_cap < ch.n_records) {
+        dfree(ch.labels);
+        CU(cudaMalloc((void**)&ch.labels, (size_t)std::max<int64_t>(ch.n_records, 1) * sizeof(uint32_t)));
+        ch.labels_cap = std::max<int64_t>(ch.n_records, 1);
+    }
+    uint32_t* rows = nullptr;
+    uint64_t *off = nullptr, *scr = nullptr;
+    int rc;
+    if ((rc = dalloc(ctx, &rows, (size_t)ch.n_tiles, false)) || (rc = dalloc(ctx, &off, (size_t)ch.n_tiles + 1, false)) ||
+        (rc = dalloc(ctx, &scr, (size_t)ch.n_tiles / 2048 + 4, false)))
+        return rc;
+    launch_tile_rows(ch.tile_info, rows, ch.n_tiles, ctx->st);
+    launch_scan_u32(rows, off, ch.n_tiles, scr, ctx->st);
+    launch_labels_from_table(ch.tile_info, off, ch.meta_b, ch.row_key, ch.labels, ch.n_tiles, ctx->st);
+    CU(cudaStreamSynchronize(ctx->st));
+    cudaFree(rows); cudaFree(off); cudaFree(scr);
+    ch.labels_ready = true;
+    return PTX_OK;
+}
+
+// classify (+ optimistic coverage) pass over one chunk whose text is resident
+int chunk_process(ptx_ctx* ctx, Chunk& ch) {
+    if (ctx->cov_reduced) return fail(ctx, PTX_E_STATE, "multi-GPU: coverage already reduced by ptx_finalize; ptx_reset before ingesting more");
+    if (ch.n == 0) { ch.n_tiles = 0; ch.ingested = true; ch.covered = true; ch.pending = false; ch.n_records = 0; ch.n_slots = 0; return PTX_OK; }
+    const bool single = ctx->single_pass_ok && ctx->seen_mean_line > 0 && ctx->labels_in_n == 0;
+    return single ? chunk_process_single(ctx, ch) : chunk_process_exact(ctx, ch);
 }
 
 int zero_coverage(ptx_ctx* ctx) {
@@ -762,6 +922,7 @@ int ptx_create(int device, ptx_ctx** out) {
     if (const char* e = getenv("PTX_TILE_ROWS")) ctx->force_rows = atoi(e);
     if (const char* e = getenv("PTX_LONG_MODE")) ctx->force_long = atoi(e) ? 1 : 0;
     if (const char* e = getenv("PTX_TEST_BOX_CAP")) ctx->test_box_cap = atoll(e);
+    if (const char* e = getenv("PTX_NO_SINGLE_PASS")) ctx->single_pass_ok = atoi(e) == 0;
     if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
@@ -1107,6 +1268,8 @@ int ptx_ingest_gaf(ptx_ctx* ctx, const uint8_t* bytes, size_t n, int is_last) {
         int rc = chunk_process(ctx, ch);
         if (rc) return rc;
     }
+    // the caller may reuse its buffer when this returns: wait for the copies (not for the kernels)
+    if (!piece_idx.empty()) CU(cudaEventSynchronize(ctx->chunks[piece_idx.back()].copied));
     return PTX_OK;
 }
 
@@ -1169,6 +1332,10 @@ int ptx_finalize(ptx_ctx* ctx) {
     if (!ctx->dirty) return PTX_OK;
     GraphDev& g = ctx->g;
     const int S = (int)ctx->sp.size();
+    {
+        int rc = chunks_resolve(ctx);  // counts of the single-pass chunks (redoes the ones whose estimate was too small)
+        if (rc) return rc;
+    }
     ev_begin(ctx, ctx->ev_final);
     Trace tr(ctx->st);
     bool mixed = false;
@@ -1296,6 +1463,8 @@ static int reset_impl(ptx_ctx* ctx, bool keep_buffers) {
     cudaSetDevice(ctx->device);
     CU(cudaStreamSynchronize(ctx->st));
     CU(cudaStreamSynchronize(ctx->copy_st));
+    ctx->pending_records = 0;
+    for (auto& ch : ctx->chunks) ch.pending = false;
     if (keep_buffers) {
         for (auto& ch : ctx->chunks) { ch.ingested = false; ch.covered = false; ch.n_records = 0; }
     } else {
@@ -1348,17 +1517,27 @@ int ptx_reset(ptx_ctx* ctx) {
 // can then be ingested again with ptx_ingest_gaf_device: one more pass over the same resident text.
 int ptx_rewind(ptx_ctx* ctx) { return reset_impl(ctx, true); }
 
-int64_t ptx_num_records(const ptx_ctx* ctx) { return ctx ? ctx->total_records : PTX_E_INVALID; }
+int64_t ptx_num_records(const ptx_ctx* ctx) {
+    if (!ctx) return PTX_E_INVALID;
+    if (chunks_resolve(const_cast<ptx_ctx*>(ctx)) != PTX_OK) return PTX_E_CUDA;
+    return ctx->total_records;
+}
 int ptx_num_species(const ptx_ctx* ctx) { return ctx ? (int)ctx->sp.size() : PTX_E_INVALID; }
 int ptx_ids_unique(const ptx_ctx* ctx) { return ctx ? (ctx->h_flags[0] == 0 ? 1 : 0) : PTX_E_INVALID; }
 
 int ptx_read_labels(ptx_ctx* ctx, uint32_t* labels) {
     if (!ctx || !labels) return PTX_E_INVALID;
     cudaSetDevice(ctx->device);
+    {
+        int rc = chunks_resolve(ctx);
+        if (rc) return rc;
+    }
     CU(cudaStreamSynchronize(ctx->st));
     int64_t off = 0;
     for (auto& ch : ctx->chunks) {
         if (!ch.ingested || ch.n_records == 0) continue;
+        int rc = chunk_labels_materialize(ctx, ch);
+        if (rc) return rc;
         CU(cudaMemcpy(labels + off, ch.labels, ch.n_records * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         off += ch.n_records;
     }
@@ -1370,6 +1549,10 @@ int ptx_species_counts(ptx_ctx* ctx, int64_t* counts) {
     if (ctx->sp.empty()) return fail(ctx, PTX_E_STATE, "no ranges");
     if (ctx->dirty && ctx->comm) return fail(ctx, PTX_E_STATE, "call ptx_finalize first");
     cudaSetDevice(ctx->device);
+    {
+        int rc = chunks_resolve(ctx);
+        if (rc) return rc;
+    }
     CU(cudaStreamSynchronize(ctx->st));
     CU(cudaMemcpy(counts, ctx->comm ? ctx->d_hist_g : ctx->d_hist, ctx->sp.size() * 4 * sizeof(int64_t), cudaMemcpyDeviceToHost));
     return PTX_OK;
@@ -1379,12 +1562,20 @@ int ptx_species_counts(ptx_ctx* ctx, int64_t* counts) {
 int ptx_equal_length(ptx_ctx* ctx, int* is_equal, int64_t* read_len) {
     if (!ctx || !is_equal || !read_len) return PTX_E_INVALID;
     cudaSetDevice(ctx->device);
+    {
+        int rc = chunks_resolve(ctx);
+        if (rc) return rc;
+    }
     CU(cudaStreamSynchronize(ctx->st));
     std::vector<int64_t> distinct;  // a null read_len (NULL_I64) counts as a value, as in polars' unique()
     int64_t seen = 0;
     for (auto& ch : ctx->chunks) {
         if (seen >= 1000) break;
         if (!ch.ingested || ch.n_records == 0) continue;
+        {
+            int rc = chunk_labels_materialize(ctx, ch);
+            if (rc) return rc;
+        }
         size_t text_off = 0, win = 1u << 20;
         int64_t rec = 0;
         std::vector<uint8_t> text;
@@ -1667,6 +1858,7 @@ int ptx_timing(ptx_ctx* ctx, double* ingest_ms, double* finalize_ms, int64_t* ke
 int ptx_stats_json(ptx_ctx* ctx, char* buf, size_t cap) {
     if (!ctx || !buf || cap == 0) return PTX_E_INVALID;
     cudaSetDevice(ctx->device);
+    chunks_resolve(ctx);
     cudaStreamSynchronize(ctx->st);
     size_t text = 0;
     for (auto& ch : ctx->chunks) text += ch.n;

@@ -33,6 +33,7 @@ constexpr uint32_t RM_W_MASK = 0x00FFFFFFu;
 constexpr uint32_t RM_LABELLED = 0x80000000u;  // species label != U
 constexpr uint32_t RM_ELIGIBLE = 0x40000000u;  // path, c7, c8, c9 all non-null (profile.rs:380-399)
 constexpr uint32_t RM_MONOTONE = 0x20000000u;  // strictly monotone node ids: no node repeats in the walk
+constexpr uint32_t RM_VALID = 0x10000000u;     // the line slot is a GAF row (not an empty line / '@' comment)
 
 // mode flags of k_apply
 constexpr int MODE_CLASSIFY = 1;  // labels, species counts, read-id set insert
@@ -76,7 +77,11 @@ struct IngestArgs {
     uint32_t n_tiles;
     uint32_t rows_per_warp;      // tile = rows_per_warp * 4096 bytes
     uint32_t long_mode;          // long lines: warp-cooperative walk decode (k_ingest<true>)
-    const uint64_t* micro_base;  // [n_micro] exclusive record prefix per micro-tile within the chunk (MODE_CLASSIFY)
+    const uint64_t* micro_base;  // [n_micro] exclusive record prefix per micro-tile within the chunk, from the count pass.
+                                 // null = SINGLE-PASS mode: no count pass ran, rows are numbered later from tile_info/row_key
+    uint4* tile_info;            // single-pass: [n_tiles] {first record-table entry, line slots, GAF rows, 0} of each tile
+    uint16_t* row_key;           // single-pass: [slots_cap] index of the entry's GAF row within its tile
+    uint32_t slots_cap;          // single-pass: capacity of the record table (estimated; overflow -> cursors[3])
     uint32_t* labels;           // [chunk records]
     const uint32_t* labels_in;  // [chunk records] caller-supplied species labels (ptx_ingest_labels), or null: classify
     // record table + CSR walks written by k_ingest, consumed by k_apply (entries in length-sorted tile order)
@@ -84,7 +89,7 @@ struct IngestArgs {
     longlong2* meta_a;          // [line slots] {c8, c9} of eligible records
     unsigned long long* hash_lo;  // [line slots] id hash lo of labelled records
     uint32_t* nodes;            // [<= text bytes / 2] raw node ids of eligible records' walks
-    uint32_t* cursors;          // [0] next record-table entry, [1] next node slot
+    uint32_t* cursors;          // [0] next record-table entry, [1] next node slot, [2] GAF rows, [3] single-pass estimate too small
     // multi-GPU: id entries routed to the rank owning their hash (written by k_apply<CLASSIFY>, sent at finalize)
     // multi-GPU (null on one GPU): box_ptr[q] = where {hash, state} of records whose id rank q owns are appended -
     // this rank's slice of q's inbox in PEER memory (stores travel over NVLink while k_apply runs), or a local outbox
@@ -114,7 +119,12 @@ void launch_count_records(const uint8_t* text, uint64_t n_bytes, uint32_t n_micr
                           cudaStream_t st);
 void launch_scan_tiles(const uint32_t* tile_count, uint32_t* tile_base, uint32_t n_tiles, uint64_t* total, cudaStream_t st);
 void launch_ingest(const IngestArgs& a, cudaStream_t st);
+constexpr uint32_t ENTRIES_FROM_DEVICE = 0xFFFFFFFFu;  // launch_apply: take the entry count (and the abandon flag) from a.cursors
 void launch_apply(const IngestArgs& a, uint32_t n_entries, int mode, cudaStream_t st);
+void launch_hist_merge(const unsigned long long* chunk_hist, unsigned long long* hist, uint32_t n, const uint32_t* cursors, cudaStream_t st);
+void launch_tile_rows(const uint4* tile_info, uint32_t* rows, uint32_t n_tiles, cudaStream_t st);
+void launch_labels_from_table(const uint4* tile_info, const uint64_t* tile_off, const uint4* meta_b, const uint16_t* row_key, uint32_t* labels,
+                              uint32_t n_tiles, cudaStream_t st);
 void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2* new_slots, uint32_t new_shift,
                       uint64_t new_mask, cudaStream_t st);
 void launch_fill_u8(uint8_t* p, uint8_t v, uint64_t n, cudaStream_t st);

@@ -545,7 +545,8 @@ __global__ void __launch_bounds__(INGEST_THREADS, LONG ? 3 : 4) k_ingest(const I
 
     const uint32_t wbase_byte = warp * rows * 512u;
     const bool last_tile = t0 + tile_bytes + 1u >= a.n_bytes;
-    const uint32_t rec_base = (MODE & MODE_CLASSIFY) ? (uint32_t)a.micro_base[(uint64_t)blockIdx.x * rows] : 0u;
+    const bool single_pass = a.micro_base == nullptr;  // no count pass: rows are numbered per tile (tile_info + row_key)
+    const uint32_t rec_base = single_pass ? 0u : (uint32_t)a.micro_base[(uint64_t)blockIdx.x * rows];
     const uint32_t glim = (uint32_t)min((uint64_t)0xFFFF0000ull, a.padded_bytes - t0);
     const RangesView& R = a.ranges;
     __syncthreads();  // sentinel visible
@@ -655,8 +656,22 @@ __global__ void __launch_bounds__(INGEST_THREADS, LONG ? 3 : 4) k_ingest(const I
         // ---- order the round's records by line length (a proxy for the walk length: 4-byte bins) so that the
         // lanes of a warp carry walks of similar length; the lock-step node loops then idle much less
         if (tid < 64) bin_cnt[tid] = 0;
-        if (tid == 64) slot_base_s = atomicAdd(a.cursors + 0, n_round);  // this round's entries in the record table
+        if (tid == 64) {
+            uint32_t sb = atomicAdd(a.cursors + 0, n_round);  // this round's entries in the record table
+            if (single_pass) {
+                // the table was sized from an estimate, and row numbering per tile needs all lines of a tile in one round
+                if (sb + n_round > a.slots_cap || n_rec > REC_CAP) {
+                    atomicOr(a.cursors + 3, 1u);  // the host redoes the chunk with the count pass
+                    sb = 0xFFFFFFFFu;
+                } else {
+                    a.tile_info[blockIdx.x] = make_uint4(sb, n_round, n_round - inv_total, 0u);
+                    atomicAdd(a.cursors + 2, n_round - inv_total);
+                }
+            }
+            slot_base_s = sb;
+        }
         __syncthreads();
+        if (slot_base_s == 0xFFFFFFFFu) return;  // uniform: read after the barrier
         for (uint32_t k = tid; k < n_round; k += INGEST_THREADS) {
             const uint32_t s0 = rec_start[k];
             const uint32_t e0 = (k + 1 < n_round) ? rec_start[k + 1] : s0 + 112u;
@@ -784,7 +799,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, LONG ? 3 : 4) k_ingest(const I
                 } else {
                     label = classify(R, r.W ? r.vmin : -1, r.W ? r.vmax : -1, sstart);
                 }
-                if (MODE & MODE_CLASSIFY) a.labels[row] = label;
+                if (!single_pass) a.labels[row] = label;
             }
             __syncwarp();
             if (MODE & MODE_CLASSIFY) {
@@ -864,6 +879,8 @@ __global__ void __launch_bounds__(INGEST_THREADS, LONG ? 3 : 4) k_ingest(const I
             if (slot) {
                 const uint32_t e = slot_base_s + q;
                 uint32_t wf = wcnt & RM_W_MASK;
+                if (has) wf |= RM_VALID;
+                if (single_pass && has) a.row_key[e] = (uint16_t)(k - (inv_total ? (uint32_t)inv_pre[k] : 0u));
                 if (labelled) wf |= RM_LABELLED;
                 if (eligible) wf |= RM_ELIGIBLE;
                 if (r.monotone) wf |= RM_MONOTONE;
@@ -910,6 +927,10 @@ __global__ void __launch_bounds__(INGEST_THREADS, LONG ? 3 : 4) k_ingest(const I
 // =====================================================================================
 template <int MODE>
 __global__ void __launch_bounds__(256) k_apply(const IngestArgs a, uint32_t n_entries) {
+    if (n_entries == ENTRIES_FROM_DEVICE) {  // single-pass ingest: the host does not know the entry count yet
+        if (a.cursors[3]) return;            // the estimate was too small: nothing of this chunk counts, it is redone
+        n_entries = a.cursors[0];
+    }
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     const bool has = e < n_entries;
     uint4 mb = make_uint4(0u, 0u, LABEL_U, 0u);
@@ -968,6 +989,30 @@ __global__ void __launch_bounds__(256) k_apply(const IngestArgs a, uint32_t n_en
             DevSink sink{a};
             cover_record(nullptr, r, label, R.start[label], nb, sink, cmask, a.nodes + mb.x, 1u);
         }
+    }
+}
+
+// single-pass ingest: the species counts of a chunk go to a chunk-local buffer and are added to the totals only
+// if the chunk was not abandoned (cursors[3])
+__global__ void __launch_bounds__(256) k_hist_merge(const unsigned long long* __restrict__ chunk_hist, unsigned long long* hist, uint32_t n,
+                                                    const uint32_t* __restrict__ cursors) {
+    if (cursors[3]) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && chunk_hist[i]) atomicAdd(hist + i, chunk_hist[i]);
+}
+// single-pass ingest: labels[] in GAF row order from the record table.  tile_off = exclusive scan of tile_info[].z.
+__global__ void __launch_bounds__(256) k_tile_rows(const uint4* __restrict__ tile_info, uint32_t* __restrict__ rows, uint32_t n_tiles) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_tiles) rows[t] = tile_info[t].z;
+}
+__global__ void __launch_bounds__(256) k_labels_from_table(const uint4* __restrict__ tile_info, const uint64_t* __restrict__ tile_off,
+                                                           const uint4* __restrict__ meta_b, const uint16_t* __restrict__ row_key,
+                                                           uint32_t* __restrict__ labels) {
+    const uint4 ti = tile_info[blockIdx.x];
+    const uint64_t base = tile_off[blockIdx.x];
+    for (uint32_t i = threadIdx.x; i < ti.y; i += blockDim.x) {
+        const uint4 mb = meta_b[ti.x + i];
+        if (mb.y & RM_VALID) labels[base + row_key[ti.x + i]] = mb.z;
     }
 }
 
@@ -1601,9 +1646,24 @@ void launch_ingest(const IngestArgs& a, cudaStream_t st) {
     else k_ingest<false><<<a.n_tiles, INGEST_THREADS, smem, st>>>(a);
     PTX_LAUNCHED();
 }
+void launch_hist_merge(const unsigned long long* chunk_hist, unsigned long long* hist, uint32_t n, const uint32_t* cursors, cudaStream_t st) {
+    k_hist_merge<<<(n + 255u) / 256u, 256, 0, st>>>(chunk_hist, hist, n, cursors);
+    PTX_LAUNCHED();
+}
+void launch_tile_rows(const uint4* tile_info, uint32_t* rows, uint32_t n_tiles, cudaStream_t st) {
+    k_tile_rows<<<(n_tiles + 255u) / 256u, 256, 0, st>>>(tile_info, rows, n_tiles);
+    PTX_LAUNCHED();
+}
+void launch_labels_from_table(const uint4* tile_info, const uint64_t* tile_off, const uint4* meta_b, const uint16_t* row_key, uint32_t* labels,
+                              uint32_t n_tiles, cudaStream_t st) {
+    if (n_tiles == 0) return;
+    k_labels_from_table<<<n_tiles, 256, 0, st>>>(tile_info, tile_off, meta_b, row_key, labels);
+    PTX_LAUNCHED();
+}
 void launch_apply(const IngestArgs& a, uint32_t n_entries, int mode, cudaStream_t st) {
     if (n_entries == 0) return;
-    const uint32_t grid = (n_entries + 255u) / 256u;
+    const uint32_t grid = ((n_entries == ENTRIES_FROM_DEVICE ? a.slots_cap : n_entries) + 255u) / 256u;
+    if (grid == 0) return;
     switch (mode) {
         case MODE_CLASSIFY: k_apply<MODE_CLASSIFY><<<grid, 256, 0, st>>>(a, n_entries); break;
         case MODE_CLASSIFY | MODE_COVER: k_apply<MODE_CLASSIFY | MODE_COVER><<<grid, 256, 0, st>>>(a, n_entries); break;

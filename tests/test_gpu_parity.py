@@ -68,6 +68,47 @@ def test_gpu_chunked_ingest_splits_lines_anywhere():
     assert_gpu_matches_oracle(ctx, o2, graphs)
 
 
+@pytest.mark.parametrize("single_pass", [True, False])
+def test_gpu_single_pass_chunks_estimates_and_redo(single_pass, monkeypatch):
+    """After the first chunk of a ctx the library ingests in ONE pass over the text: tile size and record-table
+    capacity come from the line statistics seen so far, rows are numbered per tile.  A chunk that breaks the
+    estimate (short lines after long ones; tiles with more than 1024 lines) is abandoned on the device and redone
+    with the count pass - results, row order of the labels and the equal-length rule must not change."""
+    from gpu_common import assert_gpu_matches_oracle
+    api = _api()
+    if not single_pass:
+        monkeypatch.setenv("PTX_NO_SINGLE_PASS", "1")
+    ds = synth.Dataset(77, [30000, 9000], [6, 3], backbone_mean=200)
+    graphs = dataset_graphs(ds)
+    long_part = ds.gaf(5, 0, 600, synth.GafParams(long_reads=True, id_pair_suffix=False))
+    short_part = ds.gaf(6, 0, 30000, NASTY)
+    # tiny lines: every 4 KB holds hundreds of (mostly invalid-for-coverage) rows -> more than 1024 lines per tile
+    tiny = b"".join(b"t%d\t1\n" % i for i in range(40000))
+    comment = b"@CO\tcomment line\n" * 50
+    parts = [long_part, short_part, comment + tiny, short_part[: len(short_part) // 3], long_part[: len(long_part) // 2]]
+    gaf = b"".join(parts)
+    o = run_cpu_oracle(ds.ranges(), graphs, gaf)
+    ctx = api.PantaxGpu(0)
+    ctx.set_ranges(ds.ranges())
+    for s, g in enumerate(graphs):
+        ctx.upload_graph(s, g[0], g[1])
+    ctx.commit_graphs()
+    for i, part in enumerate(parts):   # one ptx_ingest_gaf call per part: parts 2.. are single-pass candidates
+        ctx.ingest_gaf(part, is_last=(i == len(parts) - 1))
+    assert ctx.num_records == o.n_records       # resolves the in-flight counts before finalize
+    ctx.finalize()
+    assert_gpu_matches_oracle(ctx, o, graphs)
+    eq, rl = ctx.equal_length()
+    rows = opy.rcls_profile(gaf, ds.ranges())
+    assert (eq, rl if eq else None) == opy.equal_length_test(rows)
+    # the same ctx again after reset: now even the first chunk is single-pass (statistics persist)
+    ctx.reset()
+    ctx.ingest_gaf(short_part, is_last=True)
+    np.testing.assert_array_equal(ctx.read_labels(), run_cpu_oracle(ds.ranges(), graphs, short_part).labels())
+    ctx.finalize()
+    assert_gpu_matches_oracle(ctx, run_cpu_oracle(ds.ranges(), graphs, short_part), graphs)
+
+
 def test_gpu_partial_graphs_and_species_only():
     from gpu_common import assert_gpu_matches_oracle, run_gpu
     api = _api()
