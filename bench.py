@@ -8,9 +8,9 @@ Workload (config.workload): BASELINE.json configs[1] - single-species synthetic 
 Under torchrun (N>1) every rank owns its own 10 M-record read batch of the same stream (weak
 scaling), the graph is replicated and ptx_finalize reduces over NCCL.
 
-A step = one pass of the hot path over the batch: zeroed accumulators -> record count per 4 KB ->
-k_ingest (parse/classify/count -> record table + CSR walks) -> k_apply (id set + node coverage +
-trio sums) -> finalize (covered bases, per-path sums,
+A step = one pass of the hot path over the batch: zeroed accumulators -> k_ingest (one pass over the
+text: parse/classify/count -> record table + CSR walks; only the very first chunk of a ctx is preceded
+by a record-count pass) -> k_apply (id set + node coverage + trio sums) -> finalize (covered bases, per-path sums,
 per-hap unique-trio counts).  The graph upload + unique-trio table build is database setup
 (SURVEY.md section 8d), timed separately and reported in config.
 
