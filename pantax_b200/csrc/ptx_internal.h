@@ -117,7 +117,6 @@ struct IngestArgs {
 // launchers (ptx_kernels.cu); all asynchronous on `st`
 void launch_count_records(const uint8_t* text, uint64_t n_bytes, uint32_t n_micro, uint32_t* micro_count, unsigned long long* total_slots,
                           cudaStream_t st);
-void launch_scan_tiles(const uint32_t* tile_count, uint32_t* tile_base, uint32_t n_tiles, uint64_t* total, cudaStream_t st);
 void launch_ingest(const IngestArgs& a, cudaStream_t st);
 constexpr uint32_t ENTRIES_FROM_DEVICE = 0xFFFFFFFFu;  // launch_apply: take the entry count (and the abandon flag) from a.cursors
 void launch_apply(const IngestArgs& a, uint32_t n_entries, int mode, cudaStream_t st);
@@ -127,7 +126,6 @@ void launch_labels_from_table(const uint4* tile_info, const uint64_t* tile_off, 
                               uint32_t n_tiles, cudaStream_t st);
 void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2* new_slots, uint32_t new_shift,
                       uint64_t new_mask, cudaStream_t st);
-void launch_fill_u8(uint8_t* p, uint8_t v, uint64_t n, cudaStream_t st);
 void launch_ninfo_build(const uint32_t* len, const uint64_t* bit_off, uint4* ninfo, int64_t N, cudaStream_t st);
 void launch_ninfo_full(uint4* ninfo, uint8_t* full, int64_t N, int mode, cudaStream_t st);
 // cross-rank id groups (multi-GPU finalize)

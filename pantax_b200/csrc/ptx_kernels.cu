@@ -1,16 +1,17 @@
 // sm_100a kernels of the PanTax alignment-to-abundance hot path.
 //
-//   K1  k_count_records / k_scan_tiles  newline index: records per 4 KB micro-tile -> record numbering
-//   K2+ k_ingest<MODE>                  one CTA per tile: TMA bulk copy of the tile's text into
-//                                       shared memory, record-start compaction, then one thread per
-//                                       GAF record: column split + integer parse + walk decode
-//                                       (rcls.rs:119-146,237-258), species label, species counts
-//                                       (profile.rs:208-297), read-id set insert (profile.rs:361-437)
-//                                       and the node-coverage scatter (profile.rs:787-919)
-//   K7  k_trio_*                        unique-trio table build (profile.rs:658-740)
-//   K6  k_cov                           covered bases per node (profile.rs:1018-1023)
-//   K9  k_path_cov_sum / k_hap_nz / k_depth   per-path / per-hap statistics (profile.rs:980-1016,
-//                                       1112-1135, 2705-2729)
+//   k_ingest<short|long>   one CTA per tile of GAF text: TMA bulk copy into shared memory, line index, sort by
+//                          line length, then one thread per record (short) or one thread per record for the scalar
+//                          columns + the whole warp for the walk column (long): column split, integers, walk decode
+//                          (rcls.rs:119-146, 237-258), species label, species counts (profile.rs:208-297) ->
+//                          record table + CSR walks
+//   k_apply<MODE>          one thread per record-table entry: read-id set insert (profile.rs:361-437), node
+//                          coverage / trio sums from the CSR walk (profile.rs:787-919); also the replay pass
+//   k_count_records        records per 4 KB (+ scan) -> GAF row numbering; first chunk of a ctx / exact redo only
+//   k_trio_*               unique-trio table build (profile.rs:658-740)
+//   k_cov                  covered bases per node (profile.rs:1018-1023)
+//   k_path_len_sum / k_hap_nz / k_depth   per-path / per-hap statistics (profile.rs:980-1016, 1112-1135, 2705-2729)
+//   k_ds_*                 cross-rank read-id groups (multi-GPU);  k_flt_*  gaf_filter.rs:22-97
 // All HBM-bound integer/byte work: no tensor cores.  See DESIGN.md for the data layout and the
 // algorithmic bytes each kernel is measured against.
 #include <atomic>
@@ -133,42 +134,6 @@ __global__ void __launch_bounds__(256) k_count_records(const uint8_t* __restrict
     }
 }
 
-__global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
-                                                     uint64_t* __restrict__ total) {
-    __shared__ uint32_t ws[32];
-    __shared__ uint64_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n; base += 1024) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t v = i < n ? in[i] : 0;
-        uint32_t x = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-            if ((threadIdx.x & 31) >= d) x += y;
-        }
-        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t s = ws[threadIdx.x];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t y = __shfl_up_sync(0xffffffffu, s, d);
-                if (threadIdx.x >= d) s += y;
-            }
-            ws[threadIdx.x] = s;
-        }
-        __syncthreads();
-        uint64_t carry = carry_s;
-        uint32_t wbase = (threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0;
-        if (i < n) out[i] = (uint32_t)(carry + wbase + x - v);
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = carry + wbase + x;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total = carry_s;
-}
 
 // =====================================================================================
 // read-id set (open addressing, 16-byte slots {hash.lo, hash.hi<<32 | state}, 128-bit CAS)
@@ -332,7 +297,7 @@ __global__ void __launch_bounds__(256) k_ds_apply_mixed(const ulonglong2* __rest
 }
 
 // =====================================================================================
-// K2..K6/K8: the fused ingest kernel
+// k_ingest: GAF text -> species counts, record table, CSR walks   (k_apply, further down, consumes them)
 // =====================================================================================
 struct DevSink {
     const IngestArgs& a;
@@ -1320,9 +1285,6 @@ __global__ void __launch_bounds__(256) k_ninfo_full(uint4* ninfo, uint8_t* __res
     else ninfo[g].y &= ~NI_FULL;
 }
 
-__global__ void __launch_bounds__(256) k_fill_u8(uint8_t* p, uint8_t v, uint64_t n) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
-}
 
 // =====================================================================================
 // K10: long-read best-alignment filter (gaf_filter.rs:22-97)
@@ -1626,10 +1588,6 @@ void launch_count_records(const uint8_t* text, uint64_t n_bytes, uint32_t n_micr
     k_count_records<<<(n_micro + 7) / 8, 256, 0, st>>>(text, n_bytes, n_micro, micro_count, total_slots);
     PTX_LAUNCHED();
 }
-void launch_scan_tiles(const uint32_t* tile_count, uint32_t* tile_base, uint32_t n_tiles, uint64_t* total, cudaStream_t st) {
-    k_scan_tiles<<<1, 1024, 0, st>>>(tile_count, tile_base, n_tiles, total);
-    PTX_LAUNCHED();
-}
 
 void launch_ingest(const IngestArgs& a, cudaStream_t st) {
     const size_t hist_bytes = HIST_SLOTS * 5 * sizeof(uint32_t);
@@ -1730,10 +1688,6 @@ void launch_ninfo_build(const uint32_t* len, const uint64_t* bit_off, uint4* nin
 void launch_ninfo_full(uint4* ninfo, uint8_t* full, int64_t N, int mode, cudaStream_t st) {
     if (N <= 0) return;
     k_ninfo_full<<<(uint32_t)((N + 255) / 256), 256, 0, st>>>(ninfo, full, N, mode);
-    PTX_LAUNCHED();
-}
-void launch_fill_u8(uint8_t* p, uint8_t v, uint64_t n, cudaStream_t st) {
-    k_fill_u8<<<grid_for(n, 256 * 16), 256, 0, st>>>(p, v, n);
     PTX_LAUNCHED();
 }
 void launch_mark_path_dups(uint32_t* pnode, const uint64_t* poff, const uint32_t* round_paths, uint32_t n_round_paths, uint64_t max_len,
