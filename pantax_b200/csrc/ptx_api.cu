@@ -349,7 +349,7 @@ int chunk_alloc(ptx_ctx* ctx, Chunk& ch, size_t cap) {
     if (best >= 0) {
         ch = ctx->pool[best];
         ctx->pool.erase(ctx->pool.begin() + best);
-        ch.n = 0; ch.n_records = 0; ch.ingested = false; ch.covered = false;
+        ch.n = 0; ch.n_records = 0; ch.ingested = false; ch.covered = false; ch.pending = false;
         return PTX_OK;
     }
     ch = Chunk();
@@ -561,11 +561,14 @@ int chunk_process_single(ptx_ctx* ctx, Chunk& ch) {
     return PTX_OK;
 }
 
-// Look at the counts of the single-pass chunks (waits for them); redo abandoned ones exactly.
-int chunks_resolve(ptx_ctx* ctx) {
-    for (auto& ch : ctx->chunks) {
+// Look at the counts of the single-pass chunks; redo abandoned ones exactly.  blocking: wait for every chunk
+// (finalize, getters); otherwise only take what has already arrived (keeps the line statistics fresh while streaming).
+int chunks_resolve(ptx_ctx* ctx, bool blocking = true) {
+    for (size_t ci = 0; ci < ctx->chunks.size(); ++ci) {
+        Chunk& ch = ctx->chunks[ci];
         if (!ch.pending) continue;
-        CU(cudaEventSynchronize(ch.done));
+        if (blocking) CU(cudaEventSynchronize(ch.done));
+        else if (cudaEventQuery(ch.done) != cudaSuccess) { cudaGetLastError(); continue; }
         ch.pending = false;
         ctx->pending_records -= ch.est_records;
         if (ch.h_cur[3]) {  // estimate too small (or a tile with more than REC_CAP lines): nothing was counted
@@ -615,6 +618,10 @@ int chunk_labels_materialize(ptx_ctx* ctx, Chunk& ch) {
 int chunk_process(ptx_ctx* ctx, Chunk& ch) {
     if (ctx->cov_reduced) return fail(ctx, PTX_E_STATE, "multi-GPU: coverage already reduced by ptx_finalize; ptx_reset before ingesting more");
     if (ch.n == 0) { ch.n_tiles = 0; ch.ingested = true; ch.covered = true; ch.pending = false; ch.n_records = 0; ch.n_slots = 0; return PTX_OK; }
+    {
+        int rc = chunks_resolve(ctx, false);
+        if (rc) return rc;
+    }
     const bool single = ctx->single_pass_ok && ctx->seen_mean_line > 0 && ctx->labels_in_n == 0;
     return single ? chunk_process_single(ctx, ch) : chunk_process_exact(ctx, ch);
 }

@@ -39,6 +39,7 @@ constexpr uint32_t RM_VALID = 0x10000000u;     // the line slot is a GAF row (no
 constexpr int MODE_CLASSIFY = 1;  // labels, species counts, read-id set insert
 constexpr int MODE_COVER = 2;     // node coverage / trio accumulation
 constexpr int MODE_KEEPMASK = 4;  // skip reads whose id group is DS_MIXED (replay pass)
+constexpr uint32_t BOX_STAGE_RANKS = 16;  // k_apply groups box entries per destination in shared memory up to this many ranks
 constexpr int MODE_REBOX = 8;     // multi-GPU, rare: fill the outboxes again after they were enlarged (no id-set insert)
 
 struct GraphDev {

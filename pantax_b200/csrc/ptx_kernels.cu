@@ -919,16 +919,47 @@ __global__ void __launch_bounds__(256) k_apply(const IngestArgs a, uint32_t n_en
             const bool mine = labelled && owner == a.rank;
             if ((MODE & MODE_CLASSIFY) && mine) ds_insert(a.ds, a.ds_shift, a.ds_mask, h, eligible, label, a.flags);
             const uint32_t dest = (labelled && !mine) ? owner : 0xFFFFFFFFu;
-            const unsigned peers = __match_any_sync(0xffffffffu, dest);
-            const int leader = __ffs(peers) - 1;
-            const uint32_t lane = threadIdx.x & 31u;
-            unsigned long long base = 0;
-            if (dest != 0xFFFFFFFFu && (int)lane == leader) base = atomicAdd(a.out_cursor + dest, (unsigned long long)__popc(peers));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (dest != 0xFFFFFFFFu) {
-                const unsigned long long pos = base + __popc(peers & ((1u << lane) - 1u));
-                if (pos < a.box_cap) a.box_ptr[dest][pos] = ent;  // local outbox, or the owner's inbox over NVLink
-                else atomicOr(a.out_cursor + a.n_ranks, 1ull);  // entry dropped: sticky marker, all-gathered with the cursors
+            if (a.n_ranks <= BOX_STAGE_RANKS) {
+                // CTA-level aggregation: the block's entries are grouped by destination in shared memory, one
+                // atomicAdd per destination reserves their slots, and the copy-out writes consecutive 16-byte
+                // entries from consecutive threads (whole 512-byte bursts per warp towards the owner's memory)
+                __shared__ ulonglong2 s_ent[256];
+                __shared__ uint32_t s_cnt[BOX_STAGE_RANKS], s_off[BOX_STAGE_RANKS + 1];
+                __shared__ unsigned long long s_base[BOX_STAGE_RANKS];
+                const uint32_t tid = threadIdx.x;
+                if (tid < BOX_STAGE_RANKS) s_cnt[tid] = 0;
+                __syncthreads();
+                uint32_t my_pos = 0;
+                if (dest != 0xFFFFFFFFu) my_pos = atomicAdd(&s_cnt[dest], 1u);
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t run = 0;
+                    for (uint32_t d = 0; d < a.n_ranks; ++d) { s_off[d] = run; run += s_cnt[d]; }
+                    s_off[a.n_ranks] = run;
+                }
+                if (tid < a.n_ranks && s_cnt[tid]) s_base[tid] = atomicAdd(a.out_cursor + tid, (unsigned long long)s_cnt[tid]);
+                __syncthreads();
+                if (dest != 0xFFFFFFFFu) s_ent[s_off[dest] + my_pos] = ent;
+                __syncthreads();
+                if (tid < s_off[a.n_ranks]) {
+                    uint32_t d = 0;
+                    while (tid >= s_off[d + 1]) ++d;  // at most n_ranks steps
+                    const unsigned long long pos = s_base[d] + (tid - s_off[d]);
+                    if (pos < a.box_cap) a.box_ptr[d][pos] = s_ent[tid];  // local outbox, or the owner's inbox over NVLink
+                    else atomicOr(a.out_cursor + a.n_ranks, 1ull);  // entry dropped: sticky marker, all-gathered with the cursors
+                }
+            } else {
+                const unsigned peers = __match_any_sync(0xffffffffu, dest);
+                const int leader = __ffs(peers) - 1;
+                const uint32_t lane = threadIdx.x & 31u;
+                unsigned long long base = 0;
+                if (dest != 0xFFFFFFFFu && (int)lane == leader) base = atomicAdd(a.out_cursor + dest, (unsigned long long)__popc(peers));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (dest != 0xFFFFFFFFu) {
+                    const unsigned long long pos = base + __popc(peers & ((1u << lane) - 1u));
+                    if (pos < a.box_cap) a.box_ptr[dest][pos] = ent;
+                    else atomicOr(a.out_cursor + a.n_ranks, 1ull);
+                }
             }
         }
     }
