@@ -86,6 +86,26 @@ int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, 
                 }
             }
             if (!ok) parse_record(buf.data(), (uint32_t)i, (uint32_t)buf.size() - 2, p.r, 1u, use_stash ? p.stash : nullptr, 1, 8);
+            {   // the split parser used by the long-read kernel (parse_head / column 6 decoded separately / parse_tail)
+                // must see the same columns as parse_record
+                RecParse q;
+                q.qlen = q.c7 = q.c8 = q.c9 = q.mapq = NULL_I64;
+                uint32_t pp = (uint32_t)i;
+                const int st = parse_head(buf.data(), pp, q, 1u);
+                bool same = q.h.lo == p.r.h.lo && q.h.hi == p.r.h.hi && q.qlen == p.r.qlen;
+                if (st == T_TAB) {
+                    uint32_t e6 = pp;
+                    while (buf[e6] != '\t' && buf[e6] != '\n') ++e6;  // what coop_walk_count finds
+                    const int term = buf[e6] == '\t' ? T_TAB : T_EOL;
+                    if (term == T_EOL && e6 > pp && buf[e6 - 1] == '\r') --e6;
+                    same = same && pp == p.r.path_pos && e6 == p.r.path_end;
+                    uint32_t pt = e6;
+                    if (term == T_TAB) ++pt;
+                    parse_tail(buf.data(), pt, term, q, 1u);
+                }
+                same = same && q.c7 == p.r.c7 && q.c8 == p.r.c8 && q.c9 == p.r.c9 && q.mapq == p.r.mapq;
+                if (!same) return 9;
+            }
             p.label = classify(R, p.r.W ? p.r.vmin : -1, p.r.W ? p.r.vmax : -1, R.sstart);
             p.eligible = p.label != LABEL_U && !p.r.path_null && p.r.c7 != NULL_I64 && p.r.c8 != NULL_I64 && p.r.c9 != NULL_I64;
             recs.push_back(p);
