@@ -890,6 +890,40 @@ __global__ void __launch_bounds__(INGEST_THREADS, LONG ? 3 : 4) k_ingest(const I
 // MODE_KEEPMASK: skipping reads whose id group is DS_MIXED.  Small register state, no text: runs at high occupancy,
 // and it is also the replay pass (mixed id groups, graphs committed after the ingest) - no text is re-read.
 // =====================================================================================
+// Block-level append of 16-byte entries to one of n_dest arrays (n_dest <= BOX_STAGE_RANKS): the block's entries are
+// grouped by destination in shared memory, one atomicAdd per destination reserves their slots, and the copy-out
+// writes consecutive entries from consecutive threads (512-byte bursts per warp).  Every thread of the block calls
+// it (dest = 0xFFFFFFFF: nothing to append).  ptr_of(d) = base of array d; an entry beyond `cap` is dropped and reported.
+template <class PtrOf, class Dropped>
+__device__ __forceinline__ void block_append(uint32_t dest, const ulonglong2& ent, uint32_t n_dest, unsigned long long* cursors, uint64_t cap,
+                                             PtrOf ptr_of, Dropped dropped) {
+    __shared__ ulonglong2 s_ent[256];
+    __shared__ uint32_t s_cnt[BOX_STAGE_RANKS], s_off[BOX_STAGE_RANKS + 1];
+    __shared__ unsigned long long s_base[BOX_STAGE_RANKS];
+    const uint32_t tid = threadIdx.x;
+    if (tid < BOX_STAGE_RANKS) s_cnt[tid] = 0;
+    __syncthreads();
+    uint32_t my_pos = 0;
+    if (dest != 0xFFFFFFFFu) my_pos = atomicAdd(&s_cnt[dest], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (uint32_t d = 0; d < n_dest; ++d) { s_off[d] = run; run += s_cnt[d]; }
+        s_off[n_dest] = run;
+    }
+    if (tid < n_dest && s_cnt[tid]) s_base[tid] = atomicAdd(cursors + tid, (unsigned long long)s_cnt[tid]);
+    __syncthreads();
+    if (dest != 0xFFFFFFFFu) s_ent[s_off[dest] + my_pos] = ent;
+    __syncthreads();
+    if (tid < s_off[n_dest]) {
+        uint32_t d = 0;
+        while (tid >= s_off[d + 1]) ++d;  // at most n_dest steps
+        const unsigned long long pos = s_base[d] + (tid - s_off[d]);
+        if (pos < cap) ptr_of(d)[pos] = s_ent[tid];
+        else dropped();
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) k_apply(const IngestArgs a, uint32_t n_entries) {
     if (n_entries == ENTRIES_FROM_DEVICE) {  // single-pass ingest: the host does not know the entry count yet
@@ -920,34 +954,8 @@ __global__ void __launch_bounds__(256) k_apply(const IngestArgs a, uint32_t n_en
             if ((MODE & MODE_CLASSIFY) && mine) ds_insert(a.ds, a.ds_shift, a.ds_mask, h, eligible, label, a.flags);
             const uint32_t dest = (labelled && !mine) ? owner : 0xFFFFFFFFu;
             if (a.n_ranks <= BOX_STAGE_RANKS) {
-                // CTA-level aggregation: the block's entries are grouped by destination in shared memory, one
-                // atomicAdd per destination reserves their slots, and the copy-out writes consecutive 16-byte
-                // entries from consecutive threads (whole 512-byte bursts per warp towards the owner's memory)
-                __shared__ ulonglong2 s_ent[256];
-                __shared__ uint32_t s_cnt[BOX_STAGE_RANKS], s_off[BOX_STAGE_RANKS + 1];
-                __shared__ unsigned long long s_base[BOX_STAGE_RANKS];
-                const uint32_t tid = threadIdx.x;
-                if (tid < BOX_STAGE_RANKS) s_cnt[tid] = 0;
-                __syncthreads();
-                uint32_t my_pos = 0;
-                if (dest != 0xFFFFFFFFu) my_pos = atomicAdd(&s_cnt[dest], 1u);
-                __syncthreads();
-                if (tid == 0) {
-                    uint32_t run = 0;
-                    for (uint32_t d = 0; d < a.n_ranks; ++d) { s_off[d] = run; run += s_cnt[d]; }
-                    s_off[a.n_ranks] = run;
-                }
-                if (tid < a.n_ranks && s_cnt[tid]) s_base[tid] = atomicAdd(a.out_cursor + tid, (unsigned long long)s_cnt[tid]);
-                __syncthreads();
-                if (dest != 0xFFFFFFFFu) s_ent[s_off[dest] + my_pos] = ent;
-                __syncthreads();
-                if (tid < s_off[a.n_ranks]) {
-                    uint32_t d = 0;
-                    while (tid >= s_off[d + 1]) ++d;  // at most n_ranks steps
-                    const unsigned long long pos = s_base[d] + (tid - s_off[d]);
-                    if (pos < a.box_cap) a.box_ptr[d][pos] = s_ent[tid];  // local outbox, or the owner's inbox over NVLink
-                    else atomicOr(a.out_cursor + a.n_ranks, 1ull);  // entry dropped: sticky marker, all-gathered with the cursors
-                }
+                block_append(dest, ent, a.n_ranks, a.out_cursor, a.box_cap, [&](uint32_t d) { return a.box_ptr[d]; },
+                             [&]() { atomicOr(a.out_cursor + a.n_ranks, 1ull); });  // dropped: sticky marker, all-gathered with the cursors
             } else {
                 const unsigned peers = __match_any_sync(0xffffffffu, dest);
                 const int leader = __ffs(peers) - 1;
