@@ -402,7 +402,9 @@ int chunk_table_ensure(ptx_ctx* ctx, Chunk& ch, int64_t slots) {
     (void)ctx;
     if (ch.slots_cap >= slots) return PTX_OK;
     dfree(ch.meta_b); dfree(ch.meta_a); dfree(ch.hash_lo); dfree(ch.row_key);
-    const size_t cap = (size_t)std::max<int64_t>(slots, 1);
+    // headroom: single-pass estimates move a little from chunk to chunk; a cudaFree/cudaMalloc in the middle of a
+    // stream of chunks would synchronise the device (measured: e2e 22.6 -> 27-70 ms per step)
+    const size_t cap = (size_t)std::max<int64_t>(slots + slots / 8, 1);
     CU(cudaMalloc((void**)&ch.meta_b, cap * sizeof(uint4)));
     CU(cudaMalloc((void**)&ch.meta_a, cap * sizeof(longlong2)));
     CU(cudaMalloc((void**)&ch.hash_lo, cap * sizeof(unsigned long long)));
