@@ -146,6 +146,7 @@ struct ptx_ctx {
     double seen_mean_line = 0, seen_slots_per_row = 1;
     int64_t pending_records = 0;
     bool single_pass_ok = true;  // PTX_NO_SINGLE_PASS=1 forces the count pass for every chunk
+    int64_t n_table_allocs = 0;  // (re)allocations of chunk record tables: must stay flat in a steady stream of chunks
     uint32_t* d_labels_in = nullptr;  // ptx_ingest_labels: species label of GAF rows [0, labels_in_n), row = position over all chunks
     int64_t labels_in_n = 0, labels_in_cap = 0;
     bool dirty = false;          // something ingested / committed since the last finalize
@@ -399,8 +400,8 @@ int xchg_ensure(ptx_ctx* ctx, int64_t records);
 
 // (re)allocate the record table of a chunk for `slots` line slots
 int chunk_table_ensure(ptx_ctx* ctx, Chunk& ch, int64_t slots) {
-    (void)ctx;
     if (ch.slots_cap >= slots) return PTX_OK;
+    ++ctx->n_table_allocs;
     dfree(ch.meta_b); dfree(ch.meta_a); dfree(ch.hash_lo); dfree(ch.row_key);
     // headroom: single-pass estimates move a little from chunk to chunk; a cudaFree/cudaMalloc in the middle of a
     // stream of chunks would synchronise the device (measured: e2e 22.6 -> 27-70 ms per step)
@@ -1874,10 +1875,10 @@ int ptx_stats_json(ptx_ctx* ctx, char* buf, size_t cap) {
     snprintf(buf, cap,
              "{\"records\": %lld, \"chunks\": %zu, \"text_bytes\": %zu, \"nodes\": %lld, \"paths\": %lld, \"path_steps\": %lld, "
              "\"unique_trios\": %lld, \"bit_words\": %llu, \"id_set_slots\": %llu, \"ids_unique\": %d, \"mixed_groups\": %d, "
-             "\"count_ms\": %.4f, \"ingest_ms\": %.4f, \"apply_ms\": %.4f, \"ingest_launches\": %zu, \"finalize_ms\": %.4f, \"kernel_launches\": %lld, \"ranks\": %d, \"p2p_boxes\": %d}",
+             "\"count_ms\": %.4f, \"ingest_ms\": %.4f, \"apply_ms\": %.4f, \"ingest_launches\": %zu, \"finalize_ms\": %.4f, \"kernel_launches\": %lld, \"ranks\": %d, \"p2p_boxes\": %d, \"table_allocs\": %lld}",
              (long long)ctx->total_records, ctx->chunks.size(), text, (long long)ctx->g.N, (long long)ctx->g.Htot, (long long)ctx->g.P,
              (long long)ctx->g.T, (unsigned long long)ctx->g.n_bit_words, (unsigned long long)ctx->ds_cap, ctx->h_flags[0] == 0 ? 1 : 0,
-             ctx->h_flags[1] != 0 ? 1 : 0, ev_sum(ctx->ev_count), ev_sum(ctx->ev_ingest), ev_sum(ctx->ev_apply), ctx->ev_ingest.size(), ev_sum(ctx->ev_final), (long long)kernel_launch_count(), ctx->n_ranks, ctx->p2p ? 1 : 0);
+             ctx->h_flags[1] != 0 ? 1 : 0, ev_sum(ctx->ev_count), ev_sum(ctx->ev_ingest), ev_sum(ctx->ev_apply), ctx->ev_ingest.size(), ev_sum(ctx->ev_final), (long long)kernel_launch_count(), ctx->n_ranks, ctx->p2p ? 1 : 0, (long long)ctx->n_table_allocs);
     return PTX_OK;
 }
 

@@ -109,6 +109,31 @@ def test_gpu_single_pass_chunks_estimates_and_redo(single_pass, monkeypatch):
     assert_gpu_matches_oracle(ctx, run_cpu_oracle(ds.ranges(), graphs, short_part), graphs)
 
 
+def test_gpu_steady_stream_of_chunks_does_not_reallocate():
+    """A cudaFree/cudaMalloc in the middle of a stream of chunks synchronises the device (it cost 5-50 ms per
+    10 M-record step when the single-pass capacity estimate moved by a fraction of a percent): after two warm-up
+    cycles, reset + ingest in pieces must not allocate record tables any more."""
+    api = _api()
+    ds = synth.Dataset(81, [20000], [6])
+    gaf = ds.gaf(2, 0, 60000)
+    graphs = dataset_graphs(ds)
+    ctx = api.PantaxGpu(0)
+    ctx.set_ranges(ds.ranges())
+    ctx.upload_graph(0, graphs[0][0], graphs[0][1])
+    ctx.commit_graphs()
+    cuts = np.linspace(0, len(gaf), 8).astype(int)
+    allocs = []
+    for cycle in range(5):
+        ctx.reset()
+        for i in range(7):
+            ctx.ingest_gaf(gaf[cuts[i]:cuts[i + 1]], is_last=(i == 6))
+        ctx.finalize()
+        allocs.append(ctx.stats()["table_allocs"])
+    assert allocs[2] == allocs[3] == allocs[4], allocs
+    from gpu_common import assert_gpu_matches_oracle
+    assert_gpu_matches_oracle(ctx, run_cpu_oracle(ds.ranges(), graphs, gaf), graphs)
+
+
 def test_gpu_partial_graphs_and_species_only():
     from gpu_common import assert_gpu_matches_oracle, run_gpu
     api = _api()
