@@ -87,7 +87,10 @@ int ptx_host_free(void* p);
  * partial last line to the next call.  is_last != 0 on the final chunk.  Replaces
  * rcls::load_gaf_file_lazy + process_reads_parallel_simple (rcls.rs:119-146, 306-323),
  * the integer part of species_profiling (profile.rs:208-297), group_reads_by_species
- * (profile.rs:361-463) and the read loop of get_node_abundances (profile.rs:787-919). */
+ * (profile.rs:361-463) and the read loop of get_node_abundances (profile.rs:787-919).
+ * Asynchronous: returns when `bytes` has been copied (the caller may reuse the buffer), not when the
+ * kernels are done.  After the first chunk of a ctx the text is read in a single pass and the record
+ * counts come back later; ptx_finalize, ptx_num_records and the getters wait for them. */
 int ptx_ingest_gaf(ptx_ctx* ctx, const uint8_t* bytes, size_t n, int is_last);
 
 /* Strain-only resume (profile.rs:3365-3419: `--strain` without `--species`): the species column is read
@@ -104,8 +107,8 @@ int ptx_gaf_buffer_alloc(ptx_ctx* ctx, size_t capacity, int* buffer_id, void** d
 int ptx_ingest_gaf_device(ptx_ctx* ctx, int buffer_id, size_t n);
 
 /* Runs what is still pending: cross-GPU reductions (if ptx_comm_init was called), the
- * duplicate-id rule (profile.rs:406-437; replays the retained text only if a mixed-species
- * id group exists), covered-base counts (profile.rs:1018-1023), per-path sums
+ * duplicate-id rule (profile.rs:406-437; replays the coverage from the record table kept on the
+ * device - no text is re-read - only if a mixed-species id group exists), covered-base counts (profile.rs:1018-1023), per-path sums
  * (profile.rs:2705-2729) and per-hap unique-trio counts (profile.rs:1112-1135). */
 int ptx_finalize(ptx_ctx* ctx);
 
@@ -116,7 +119,7 @@ int ptx_reset(ptx_ctx* ctx);
 int ptx_rewind(ptx_ctx* ctx);
 
 /* ---- outputs (caller-allocated buffers) -------------------------------------------- */
-int64_t ptx_num_records(const ptx_ctx* ctx);   /* GAF rows (non-comment, non-empty lines), this rank */
+int64_t ptx_num_records(const ptx_ctx* ctx);   /* GAF rows (non-comment, non-empty lines), this rank; waits for in-flight chunks */
 int ptx_num_species(const ptx_ctx* ctx);
 int ptx_ids_unique(const ptx_ctx* ctx);        /* profile.rs:376 `unique` over all non-U rows */
 
