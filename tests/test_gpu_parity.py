@@ -43,6 +43,19 @@ def test_gpu_short_reads_multi_species(params, seed, flow):
         assert not ctx.ids_unique and o.mixed_dropped > 0
 
 
+@pytest.mark.parametrize("flow", ["fused", "late"])
+def test_gpu_many_chunks_both_flows_with_mixed_groups(flow):
+    """Several ptx_ingest_gaf calls (chunks 2.. take the single-pass path) with duplicated ids whose groups span
+    species: the keep-mask replay runs over every chunk's record table; in the "late" flow (the reference's own
+    order: classify, then load graphs) the whole coverage is a replay."""
+    from gpu_common import gpu_vs_oracle
+    ds = synth.Dataset(333, [25000, 7000, 9000], [7, 2, 3])
+    gaf = ds.gaf(11, 0, 50000, NASTY_DUP)
+    cuts = [len(gaf) // 5, 2 * len(gaf) // 5, 3 * len(gaf) // 5, 4 * len(gaf) // 5]
+    ctx, o = gpu_vs_oracle(ds.ranges(), dataset_graphs(ds), gaf, flow=flow, split=cuts)
+    assert not ctx.ids_unique and o.mixed_dropped > 0
+
+
 def test_gpu_long_reads_hifi_dialect():
     from gpu_common import gpu_vs_oracle
     ds = synth.Dataset(8, [40000, 25000, 9000], [4, 2, 3], backbone_mean=400)
