@@ -438,9 +438,17 @@ int chunk_common_begin(ptx_ctx* ctx, Chunk& ch) {
         CU(cudaEventCreateWithFlags(&ch.done, cudaEventDisableTiming));
     }
     CU(cudaMemsetAsync(ch.cursors, 0, 8 * sizeof(unsigned long long), ctx->st));
-    if (ch.nodes_cap < (int64_t)(ch.n / 2 + 16)) {  // a walk node takes at least two bytes of text
+    return PTX_OK;
+}
+
+// CSR node slots of a chunk: a walk node takes at least two bytes of text; the long-line kernel reserves
+// (bytes from column 6 to the end of the line) / 2 + 1 slots per record instead of counting the nodes first
+int chunk_nodes_ensure(ptx_ctx* ctx, Chunk& ch) {
+    (void)ctx;
+    const int64_t need = (int64_t)(ch.n / 2 + 16) + (ch.long_mode ? ch.slots_cap : 0);
+    if (ch.nodes_cap < need) {
         dfree(ch.nodes);
-        ch.nodes_cap = (int64_t)(ch.n / 2 + 16);
+        ch.nodes_cap = need + need / 8;
         CU(cudaMalloc((void**)&ch.nodes, (size_t)ch.nodes_cap * sizeof(uint32_t)));
     }
     return PTX_OK;
@@ -475,6 +483,7 @@ int chunk_process_exact(ptx_ctx* ctx, Chunk& ch) {
     if ((rc = chunk_table_ensure(ctx, ch, ch.n_slots))) return rc;
     const double mean_line = (double)ch.n / (double)std::max<uint64_t>(total, 1);
     chunk_pick_tile(ctx, ch, mean_line);
+    if ((rc = chunk_nodes_ensure(ctx, ch))) return rc;
     if (!ch.labels || ch.labels_cap < (int64_t)total) {
         dfree(ch.labels);
         CU(cudaMalloc((void**)&ch.labels, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
@@ -523,6 +532,7 @@ int chunk_process_single(ptx_ctx* ctx, Chunk& ch) {
     const int64_t est_slots = (int64_t)(est_rows * ctx->seen_slots_per_row * 1.25) + 4096;
     if (est_slots > 0xFFFFFFF0ll) return chunk_process_exact(ctx, ch);
     if ((rc = chunk_table_ensure(ctx, ch, est_slots))) return rc;
+    if ((rc = chunk_nodes_ensure(ctx, ch))) return rc;
     if (ch.tile_info_cap < ch.n_tiles) {
         dfree(ch.tile_info);
         CU(cudaMalloc((void**)&ch.tile_info, (size_t)ch.n_tiles * sizeof(uint4)));

@@ -398,20 +398,27 @@ __device__ __forceinline__ CoopCount coop_walk_count(const uint8_t* stage, uint3
     }
 }
 
-struct CoopWalk { uint32_t vmin, vmax; bool monotone, big; };
-// Decodes the digit runs of stage[p6, end) to dst[0..W) in walk order (runs of <= 9 digits; `big` reports a longer
-// one, whose record is then redone by the scalar 64-bit scanner), with min, max and strict monotonicity.
-__device__ __forceinline__ CoopWalk coop_walk_decode(const uint8_t* stage, uint32_t p6, uint32_t end, uint32_t* dst, uint32_t lane) {
+struct CoopWalk { uint32_t W, end, vmin, vmax; int term; bool beyond, monotone, big; };
+// One sweep over column 6 starting at stage[p6]: finds its terminator (as coop_walk_count) and decodes the digit
+// runs before it to dst[0..W) in walk order (runs of <= 9 digits; `big` reports a longer one, whose record is then
+// redone by the scalar 64-bit scanner), with min, max and strict monotonicity.  dst must have room for every run
+// the line can hold ((bytes from p6 to the end of the line) / 2 + 1).
+__device__ __forceinline__ CoopWalk coop_walk_sweep(const uint8_t* stage, uint32_t p6, uint32_t lim, uint32_t* dst, uint32_t lane) {
     const uint32_t lt = (1u << lane) - 1u;
-    uint32_t Wb = 0, carry = 0, carry_last = 0, mn = 0xFFFFFFFFu, mx = 0;
+    uint32_t Wb = 0, carry = 0, carry_last = 0, mn = 0xFFFFFFFFu, mx = 0, endpos = 0;
     bool inc = true, dec = true, big = false;
-    for (uint32_t pos = p6 & ~3u; pos < end; pos += 128u) {
+    for (uint32_t pos = p6 & ~3u;; pos += 128u) {
         const uint32_t my = pos + 4u * lane;
-        uint32_t dn = 0;
-        if (my < end) {
-            dn = nib4(digit_mask4(*reinterpret_cast<const uint32_t*>(stage + my)));
-            if (my < p6) dn &= 0xFu << (p6 - my);
-            if (end - my < 4u) dn &= (1u << (end - my)) - 1u;
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(stage + my);
+        uint32_t dn = nib4(digit_mask4(w));
+        uint32_t tn = nib4(eq_mask4(w, 0x09090909u) | eq_mask4(w, 0x0a0a0a0au));
+        if (my < p6) { dn &= 0xFu << (p6 - my); tn &= 0xFu << (p6 - my); }  // lane 0 of the first window only
+        const unsigned tb = __ballot_sync(0xffffffffu, tn != 0u);
+        if (tb) {  // the column ends in this window: nothing behind the terminator counts
+            const uint32_t L = __ffs(tb) - 1;
+            const uint32_t bit = __ffs(__shfl_sync(0xffffffffu, tn, L)) - 1;
+            endpos = pos + 4u * L + bit;
+            if (lane > L) dn = 0; else if (lane == L) dn &= (1u << bit) - 1u;
         }
         const uint32_t prev = __shfl_up_sync(0xffffffffu, dn >> 3, 1);
         uint32_t sn = dn & ~((dn << 1) | (lane == 0 ? carry : (prev & 1u))) & 0xFu;
@@ -447,9 +454,15 @@ __device__ __forceinline__ CoopWalk coop_walk_decode(const uint8_t* stage, uint3
         const uint32_t top = __shfl_sync(0xffffffffu, last_v, b1 ? 31u - (uint32_t)__clz(b1) : 0u);
         if (b1) carry_last = top;
         Wb += __popc(b1) + __popc(b2);
+        if (tb) break;
         carry = __shfl_sync(0xffffffffu, dn >> 3, 31) & 1u;
     }
     CoopWalk r;
+    r.W = Wb;
+    r.beyond = endpos + 1u >= lim;
+    r.term = stage[endpos] == '\t' ? T_TAB : T_EOL;
+    if (r.term == T_EOL && endpos > p6 && stage[endpos - 1] == '\r') --endpos;
+    r.end = endpos;
     r.vmin = __reduce_min_sync(0xffffffffu, mn);
     r.vmax = __reduce_max_sync(0xffffffffu, mx);
     r.monotone = __all_sync(0xffffffffu, inc) || __all_sync(0xffffffffu, dec);
@@ -691,15 +704,20 @@ __global__ void __launch_bounds__(INGEST_THREADS, LONG ? 3 : 4) k_ingest(const I
                 __syncwarp();
                 r.path_pos = r.path_end = pp;
                 bool want6 = has && !slow && st == T_TAB;
+                // CSR slots: every digit run takes at least two bytes of the line, so (bytes from column 6 to the end
+                // of the line) / 2 + 1 slots always suffice - no counting sweep.  The end of the LAST line of the tile
+                // is not known (it lies beyond the line index): that one record is counted first.
                 uint32_t w_up = 0, end6 = pp;
                 int term6 = st;
-                for (unsigned m = __ballot_sync(0xffffffffu, want6); m; m &= m - 1u) {
+                const bool last_line = k + 1u >= n_round;
+                if (want6 && !last_line) w_up = ((uint32_t)rec_start[k + 1] - pp) / 2u + 1u;
+                for (unsigned m = __ballot_sync(0xffffffffu, want6 && last_line); m; m &= m - 1u) {
                     const int rl = __ffs(m) - 1;
                     const CoopCount cc = coop_walk_count(stage, __shfl_sync(0xffffffffu, pp, rl), stage_bytes, lane);
                     if ((int)lane == rl) { w_up = cc.W; end6 = cc.end; term6 = cc.term; slow = cc.beyond; }
                 }
                 want6 = want6 && !slow;
-                {  // node slots of every record decoded here (eligible or not: a walk node takes >= 2 text bytes)
+                {  // node slots of every record decoded here (eligible or not)
                     const uint32_t wa = want6 ? w_up : 0u;
                     uint32_t x = wa;
 #pragma unroll
@@ -715,13 +733,15 @@ __global__ void __launch_bounds__(INGEST_THREADS, LONG ? 3 : 4) k_ingest(const I
                 }
                 for (unsigned m = __ballot_sync(0xffffffffu, want6 && w_up != 0u); m; m &= m - 1u) {
                     const int rl = __ffs(m) - 1;
-                    const CoopWalk cw = coop_walk_decode(stage, __shfl_sync(0xffffffffu, pp, rl), __shfl_sync(0xffffffffu, end6, rl),
-                                                         a.nodes + __shfl_sync(0xffffffffu, node_off, rl), lane);
+                    const CoopWalk cw = coop_walk_sweep(stage, __shfl_sync(0xffffffffu, pp, rl), stage_bytes,
+                                                        a.nodes + __shfl_sync(0xffffffffu, node_off, rl), lane);
                     if ((int)lane == rl) {
-                        r.W = w_up;
-                        r.vmin = (int64_t)cw.vmin; r.vmax = (int64_t)cw.vmax;
+                        r.W = cw.W;
+                        end6 = cw.end;
+                        term6 = cw.term;
+                        if (cw.W) { r.vmin = (int64_t)cw.vmin; r.vmax = (int64_t)cw.vmax; }
                         r.monotone = cw.monotone;
-                        if (cw.big) slow = true;  // a digit run of 10+ digits: generic 64-bit scan
+                        if (cw.big || cw.beyond) slow = true;  // 10+ digit run (generic 64-bit scan) / line leaves the window
                     }
                 }
                 want6 = want6 && !slow;
