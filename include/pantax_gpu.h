@@ -19,7 +19,7 @@
  * Graphs may also be uploaded AFTER the ingest (the reference's own order: species
  * abundance first, then only the abundant species' graphs, profile.rs:3359-3363):
  *   ... ptx_ingest_gaf* -> ptx_finalize -> ptx_species_counts -> ptx_upload_graph x k
- *   -> ptx_commit_graphs -> ptx_finalize (replays the retained GAF for coverage).
+ *   -> ptx_commit_graphs -> ptx_finalize (coverage pass over the retained record tables).
  */
 #ifndef PANTAX_GPU_H
 #define PANTAX_GPU_H

@@ -404,7 +404,7 @@ int main(int argc, char** argv) {
     }
     if (chosen.empty()) { fprintf(stderr, "The filtering before strain profiling has removed all species.\n"); ptx_host_free(pin); ptx_destroy(ctx); return 0; }
     ck(ctx, ptx_commit_graphs(ctx), "ptx_commit_graphs");
-    ck(ctx, ptx_finalize(ctx), "ptx_finalize (coverage)");  // replays the GAF text kept on the device
+    ck(ctx, ptx_finalize(ctx), "ptx_finalize (coverage)");  // coverage pass over the record tables kept on the device (no text is parsed again)
 
     mkdir((o.wd + "/strain_inputs").c_str(), 0755);
     for (int s : chosen) {
