@@ -617,7 +617,7 @@ int64_t orc_filter_gaf(const uint8_t* data, size_t n, uint64_t* out_line_off, in
             bool okf = !tail.empty() && endp && *endp == 0 && tail.find_first_not_of("+-0123456789.eE") == std::string::npos;
             int32_t c3, c4;
             if (okf && parse_i32(f[9], r.matches) && parse_i32(f[11], r.mapq) && parse_i32(f[3], c4) && parse_i32(f[2], c3)) {
-                r.span = c4 - c3;
+                r.span = (int32_t)((uint32_t)c4 - (uint32_t)c3);  // i32 subtraction wraps in the reference's release build
                 recs.push_back(r);
             }
         }

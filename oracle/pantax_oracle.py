@@ -558,7 +558,8 @@ def filter_max_alignment(data: bytes) -> List[bytes]:
         a, b_ = _parse_i32(f[3]), _parse_i32(f[2])
         if None in (m, ident, q, a, b_):
             continue
-        recs.append((line, f[0], m, ident, q, a - b_))
+        span = ((a - b_ + 2 ** 31) % 2 ** 32) - 2 ** 31  # i32 subtraction: release builds wrap (Cargo.toml has no overflow-checks)
+        recs.append((line, f[0], m, ident, q, span))
     best: Dict[bytes, Tuple[int, float]] = {}
     for _l, rid, m, ident, _q, _s in recs:
         e = best.get(rid)

@@ -109,3 +109,38 @@ def test_gpu_agrees_on_hostile_lines(seed, wild_start, long_mode, monkeypatch):
     gaf = fuzz_gaf(1000 + seed, 700, wild_start)
     gpu_vs_oracle(RANGES, GRAPHS, gaf)
     gpu_vs_oracle(RANGES, GRAPHS, gaf, split=[len(gaf) // 3, 2 * len(gaf) // 3])
+
+
+# ---- gaf_filter.rs:22-97 -------------------------------------------------------------------------------------------
+IDENT = [b"id:f:0.99", b"id:f:1", b"id:f:0.5", b"id:f:.75", b"id:f:1e-1", b"id:f:9.5E-1", b"id:f:-0.1", b"id:f:+0.25", b"id:f:abc", b"id:f:",
+         b"id:f:0.123456789012345", b"0.9", b"x:y:0.8:0.7", b"id:f:inf", b"id:f:nan", b"id:f:1.", b"id:f:00.5", b"id:f:5e0"]
+I32 = [b"0", b"10", b"21", b"20", b"60", b"1500", b"3000", b"-5", b"+7", b"2147483647", b"2147483648", b"-2147483648", b"x", b"", b"1.0", b" 3"]
+
+
+def fuzz_filter_gaf(seed, n):
+    rng = np.random.default_rng(seed)
+    lines = []
+    for i in range(n):
+        rid = b"q%d" % int(rng.integers(0, n // 3 + 1))          # several alignments per read
+        p = lambda: I32[int(rng.integers(0, len(I32)))] if rng.random() < 0.15 else str(int(rng.integers(0, 4000))).encode()
+        cols = [rid, p(), p(), p(), b"+", b">1>2", p(), p(), p(), p(), p(), p(), b"NM:i:1", b"AS:f:3", b"dv:f:0.01", IDENT[int(rng.integers(0, len(IDENT)))]]
+        k = len(cols) if rng.random() < 0.9 else int(rng.integers(10, 17))
+        if k > len(cols):
+            cols = cols + [b"zz:Z:extra"]
+        line = b"\t".join(cols[:k])
+        if rng.random() < 0.05:
+            line = b" " + line + b" "                           # the reference trims the line (gaf_filter.rs:23)
+        if rng.random() < 0.05:
+            line += b"\r"
+        lines.append(line)
+    return b"\n".join(lines) + b"\n"
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_filter_oracles_agree_on_hostile_lines(seed):
+    from common import ocpu, opy
+    gaf = fuzz_filter_gaf(50 + seed, 600)
+    a = opy.filter_max_alignment(gaf)
+    b = ocpu.filter_gaf(gaf)
+    assert a == b
+    assert 0 < len(a) < 600
