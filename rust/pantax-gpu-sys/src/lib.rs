@@ -91,7 +91,23 @@ impl Gpu {
     pub fn ingest_gaf(&self, bytes: &[u8], is_last: bool) -> Result<(), GpuError> {
         self.ck(unsafe { ptx_ingest_gaf(self.raw, bytes.as_ptr(), bytes.len(), is_last as c_int) })
     }
+    /// Strain-only resume (profile.rs:3365-3385): species of every GAF row from reads_classification.tsv
+    /// (index into the ranges, u32::MAX = "U"); call before ingest_gaf.
+    pub fn ingest_labels(&self, labels: &[u32]) -> Result<(), GpuError> {
+        self.ck(unsafe { ptx_ingest_labels(self.raw, labels.as_ptr(), labels.len() as i64) })
+    }
+    /// Expected number of GAF records; before comm_init it also sizes the peer-memory id boxes.
+    pub fn reserve(&self, records: usize) -> Result<(), GpuError> { self.ck(unsafe { ptx_reserve(self.raw, records as i64) }) }
     pub fn finalize(&self) -> Result<(), GpuError> { self.ck(unsafe { ptx_finalize(self.raw) }) }
+    /// profile.rs:1112-1135: (unique trios owned, of those with depth > 0) per hap.
+    pub fn hap_trio_counts(&self, species: usize) -> Result<(Vec<i64>, Vec<i64>), GpuError> {
+        let s = species as c_int;
+        let h = unsafe { ptx_species_paths(self.raw, s) }.max(0) as usize;
+        let (mut a, mut b) = (vec![0i64; h.max(1)], vec![0i64; h.max(1)]);
+        self.ck(unsafe { ptx_hap_trio_counts(self.raw, s, a.as_mut_ptr(), b.as_mut_ptr()) })?;
+        a.truncate(h); b.truncate(h);
+        Ok((a, b))
+    }
     pub fn num_records(&self) -> usize { unsafe { ptx_num_records(self.raw) as usize } }
     pub fn read_labels(&self) -> Result<Vec<u32>, GpuError> {
         let mut v = vec![0u32; self.num_records().max(1)];
