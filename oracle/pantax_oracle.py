@@ -521,6 +521,26 @@ def path_sums(graph: Graph, node_base_cov: Sequence[int]):
     return sc, sl
 
 
+def path_cov_ratio(graph: Graph, node_base_cov: Sequence[int], f32: bool = True) -> List[float]:
+    """profile.rs:2705-2729 (highs_opt; the same block in gurobi/cplex/glpk, f64 in cbc_opt :1952-1977):
+    `RowDVector<f32>(cov) * DMatrix<f32>(incidence)` and the same with the node lengths, then component_div.
+    nalgebra 0.33 multiplies a 1 x nvert row by an nvert x npaths matrix with one gemv per output column (a
+    dimension of 1 keeps it off the matrixmultiply kernels), and gemv accumulates `y = 1*a[v]*x[v] + 1*y` over
+    v = 0..nvert in index order: a SEQUENTIAL f32 sum over the distinct nodes of the path in node-index order
+    (nodes outside the path add 0).  Once a running sum passes 2^24 it is no longer the exact integer."""
+    import numpy as np
+
+    ft = np.float32 if f32 else np.float64
+    out = []
+    for _name, p in graph.sorted_paths():
+        acc_c, acc_l = ft(0), ft(0)
+        for v in sorted(set(p)):
+            acc_c = ft(acc_c + ft(node_base_cov[v]))
+            acc_l = ft(acc_l + ft(graph.nodes_len[v]))
+        out.append(float(ft(acc_c / acc_l)) if len(p) else float("nan"))
+    return out
+
+
 # --------------------------------------------------------------------------
 # a11  long-read best-alignment filter                   gaf_filter.rs:22-97
 # --------------------------------------------------------------------------

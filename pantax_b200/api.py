@@ -312,14 +312,28 @@ def get_node_abundances(ctx: PantaxGpu, species: int):
     return ctx.node_depth(species), ctx.trio_depth(species), ctx.node_cov(species)
 
 
-def path_cov_ratio(ctx: PantaxGpu, species: int, f32: bool = True) -> np.ndarray:
-    """profile.rs:2714-2729: covered fraction of every path over its distinct nodes.  The GPU returns the
-    two exact integer sums; the quotient is formed in f32 like the reference's RowDVector<f32> product
-    (f64 for the CBC variant, profile.rs:1952-1977)."""
-    sc, sl = ctx.path_sums(species)
-    if f32:
-        return (sc.astype(np.float32) / sl.astype(np.float32)).astype(np.float64)
-    return sc.astype(np.float64) / sl.astype(np.float64)
+def path_cov_ratio(ctx: PantaxGpu, species: int, paths: Sequence[np.ndarray], nodes_len: np.ndarray, f32: bool = True) -> np.ndarray:
+    """profile.rs:2714-2729: covered fraction of every path over its distinct nodes, with the reference's arithmetic.
+    The reference multiplies `RowDVector<f32>(node_base_cov)` by the 0/1 incidence matrix: nalgebra does that as one gemv
+    per path, a SEQUENTIAL f32 accumulation over the nodes in index order - not the exact integer once a running sum
+    passes 2^24 (a path of 1 M nodes x 30 bp does).  So the quotient is formed here on the host from ptx_node_cov in
+    exactly that order (f64 for the CBC variant, profile.rs:1952-1977, where the sums stay exact).  `paths`: local node
+    ids per hap in name order (the Graph the caller uploaded), `nodes_len`: its node lengths.  ptx_path_sums still
+    returns the exact integer sums."""
+    ft = np.float32 if f32 else np.float64
+    cov = ctx.node_cov(species).astype(ft)
+    ln = np.asarray(nodes_len).astype(ft)
+    out = np.empty(len(paths), dtype=np.float64)
+    for h, p in enumerate(paths):
+        d = np.unique(np.asarray(p, dtype=np.int64))  # distinct nodes, ascending index
+        if d.size == 0:
+            out[h] = np.nan
+            continue
+        # np.add.accumulate is a strict left-to-right running sum in the given dtype
+        sc = np.add.accumulate(cov[d], dtype=ft)[-1]
+        sl = np.add.accumulate(ln[d], dtype=ft)[-1]
+        out[h] = float(ft(sc / sl))
+    return out
 
 
 def filter_max_alignment_mt(ctx: PantaxGpu, gaf: bytes):

@@ -76,7 +76,8 @@ struct Chunk {
     size_t padded = 0;       // bytes readable from text (text + '\n' padding)
     uint32_t n_micro = 0;    // 4 KB micro-tiles counted by K1 (multiple of 8, covers every ingest tile)
     uint32_t n_tiles = 0;
-    uint32_t rows = 8;       // ingest tile = rows * 4096 bytes
+    uint32_t tile_bytes = MAX_TILE;  // text bytes per ingest CTA
+    uint32_t over_bytes = OVER;      // bytes staged behind the tile (k_ingest_s)
     uint32_t* tile_count = nullptr;  // [n_micro]
     uint64_t* tile_base = nullptr;   // [n_micro + 1] exclusive record prefix, last = total
     uint64_t* scan_scratch = nullptr;
@@ -135,6 +136,9 @@ struct ptx_ctx {
     int64_t ds_records = 0;  // upper bound of ids inserted
     int64_t reserve_records = 0;
     int force_rows = 0;  // PTX_TILE_ROWS env override (tests exercise every tile size)
+    int force_tile = 0;  // PTX_TILE_BYTES env override for single-pass chunks of k_ingest_s (multiple of 512)
+    bool no_sort = false;    // PTX_NO_SORT=1: k_ingest_s keeps file order inside a tile (measurements)
+    bool old_short = false;  // PTX_OLD_INGEST=1: round 1's byte-at-a-time short-read kernel (A/B measurements)
     int force_long = -1; // PTX_LONG_MODE env override: 0/1 = never/always use the long-line kernel (tests)
     int64_t test_box_cap = 0;  // PTX_TEST_BOX_CAP env: first outbox capacity (tests force the overflow/restart path of the exchange)
     uint64_t* d_total = nullptr;  // scratch scalar
@@ -294,7 +298,10 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.n_bytes = ch.n;
     a.padded_bytes = ch.padded;
     a.n_tiles = ch.n_tiles;
-    a.rows_per_warp = ch.rows;
+    a.tile_bytes = ch.tile_bytes;
+    a.over_bytes = ch.over_bytes;
+    a.no_sort = ctx->no_sort ? 1u : 0u;
+    a.old_short = ctx->old_short ? 1u : 0u;
     a.long_mode = ch.long_mode;
     a.micro_base = ch.tile_base;
     a.labels = ch.labels;
@@ -414,15 +421,23 @@ int chunk_table_ensure(ptx_ctx* ctx, Chunk& ch, int64_t slots) {
     return PTX_OK;
 }
 
-void chunk_pick_tile(ptx_ctx* ctx, Chunk& ch, double mean_line) {
-    // tile size: about one record per thread, 4 KB granularity
-    int rows = (int)(0.97 * INGEST_THREADS * mean_line / MICRO);
-    ch.rows = (uint32_t)std::min(8, std::max(1, rows));
-    if (ctx->force_rows > 0) ch.rows = (uint32_t)std::min(8, ctx->force_rows);
+void chunk_pick_tile(ptx_ctx* ctx, Chunk& ch, double mean_line, bool exact) {
     // long lines (HiFi/ONT walks): even the largest tile holds fewer lines than threads -> one warp per record
     ch.long_mode = mean_line >= LONG_LINE_BYTES ? 1u : 0u;
     if (ctx->force_long >= 0) ch.long_mode = (uint32_t)ctx->force_long;
-    const size_t tile = (size_t)ch.rows * MICRO;
+    // tile size: about one record per thread.  k_ingest_s takes any multiple of 512 bytes; the count pass numbers the rows
+    // per 4 KB micro-tile, so a chunk that ran it (and the two older kernels) gets whole micro-tiles
+    const bool short_new = !ch.long_mode && !ctx->old_short;
+    const bool fine = !exact && short_new;
+    const uint32_t threads = short_new ? SHORT_THREADS : INGEST_THREADS;
+    const uint32_t gran = fine ? 128u : MICRO;
+    uint32_t tile = (uint32_t)(0.97 * threads * mean_line) / gran * gran;
+    tile = std::min<uint32_t>(MAX_TILE, std::max<uint32_t>(MICRO, tile));
+    if (ctx->force_rows > 0) tile = (uint32_t)std::min(8, ctx->force_rows) * MICRO;
+    if (ctx->force_tile > 0 && fine) tile = std::min<uint32_t>(MAX_TILE, std::max<uint32_t>(MICRO, (uint32_t)ctx->force_tile / 128u * 128u));
+    // the window behind the tile holds the tail of its last line: four mean lines, at least 512 bytes (longer lines are re-read from global memory)
+    ch.over_bytes = std::min<uint32_t>(OVER, std::max<uint32_t>(512u, ((uint32_t)(4.0 * mean_line) + 511u) / 512u * 512u));
+    ch.tile_bytes = tile;
     ch.n_tiles = (uint32_t)((ch.n + tile - 1) / tile);
 }
 
@@ -482,7 +497,7 @@ int chunk_process_exact(ptx_ctx* ctx, Chunk& ch) {
     if (slots > 0xFFFFFFF0ull) return fail(ctx, PTX_E_INVALID, "more than 2^32 lines in one chunk");
     if ((rc = chunk_table_ensure(ctx, ch, ch.n_slots))) return rc;
     const double mean_line = (double)ch.n / (double)std::max<uint64_t>(total, 1);
-    chunk_pick_tile(ctx, ch, mean_line);
+    chunk_pick_tile(ctx, ch, mean_line, true);
     if ((rc = chunk_nodes_ensure(ctx, ch))) return rc;
     if (!ch.labels || ch.labels_cap < (int64_t)total) {
         dfree(ch.labels);
@@ -527,7 +542,7 @@ int chunk_process_exact(ptx_ctx* ctx, Chunk& ch) {
 int chunk_process_single(ptx_ctx* ctx, Chunk& ch) {
     int rc = chunk_common_begin(ctx, ch);
     if (rc) return rc;
-    chunk_pick_tile(ctx, ch, ctx->seen_mean_line);
+    chunk_pick_tile(ctx, ch, ctx->seen_mean_line, false);
     const double est_rows = (double)ch.n / ctx->seen_mean_line;
     const int64_t est_slots = (int64_t)(est_rows * ctx->seen_slots_per_row * 1.25) + 4096;
     if (est_slots > 0xFFFFFFF0ll) return chunk_process_exact(ctx, ch);
@@ -940,6 +955,9 @@ int ptx_create(int device, ptx_ctx** out) {
     if (!ctx) return PTX_E_NOMEM;
     ctx->device = device;
     if (const char* e = getenv("PTX_TILE_ROWS")) ctx->force_rows = atoi(e);
+    if (const char* e = getenv("PTX_TILE_BYTES")) ctx->force_tile = atoi(e);
+    if (const char* e = getenv("PTX_OLD_INGEST")) ctx->old_short = atoi(e) != 0;
+    if (const char* e = getenv("PTX_NO_SORT")) ctx->no_sort = atoi(e) != 0;
     if (const char* e = getenv("PTX_LONG_MODE")) ctx->force_long = atoi(e) ? 1 : 0;
     if (const char* e = getenv("PTX_TEST_BOX_CAP")) ctx->test_box_cap = atoll(e);
     if (const char* e = getenv("PTX_NO_SINGLE_PASS")) ctx->single_pass_ok = atoi(e) == 0;

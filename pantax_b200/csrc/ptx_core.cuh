@@ -69,6 +69,10 @@ struct IdHasher {
     }
     PTX_HD IdHash finish() {
         if (nbytes & 3u) mix(word);
+        return finish_words();
+    }
+    // for callers that fed whole 4-byte words through mix() themselves (the zero-padded last one included) and set nbytes
+    PTX_HD IdHash finish_words() {
         h0 ^= nbytes; h1 ^= nbytes * 0x9e3779b9u; h2 ^= ~nbytes;
         h0 += h1; h0 += h2; h1 += h0; h2 += h0;
         h0 = fmix32(h0); h1 = fmix32(h1); h2 = fmix32(h2);

@@ -1,0 +1,236 @@
+// Word-wide fast path of the GAF record parser (host/device inline code, like ptx_core.cuh).
+//
+// parse_record (ptx_core.cuh) walks a line one byte at a time.  The code here reads the same columns from
+//   * a tab bitmap and a newline bitmap of the staged text (one bit per byte, built once per tile by all
+//     threads from 16-byte pieces: classify16),
+//   * unaligned 4/8-byte words of the text (two aligned loads + a funnel shift: ld4 / ld8),
+//   * SWAR decimal conversion (four digits per multiply-add pair: swar4) and word-wise id hashing,
+// and touches no byte individually.  It accepts the records whose columns have the plain shape every aligner
+// writes - 12+ tab-separated columns, integer columns that are 1-8 unsigned digits or any non-numeric text
+// ('*' = null), walk ids of at most 9 digits, at most `stash_cap` walk nodes, "\n" line ends - and reports
+// everything else (signs, 9+ digit integers, 10+ digit ids, "\r\n", fewer than 12 columns, lines that leave the
+// staged window) as "not handled"; those records go through parse_record, which stays the definition of the
+// dialect.  On a record it accepts, fast_parse returns exactly what parse_record returns
+// (tests/hostcheck.cpp runs both on every record of every CPU test and of the dialect fuzzer).
+//
+// Reference semantics: GAF columns 1,2,6,7,8,9,12 (rcls.rs:119-146), digit runs of the walk (rcls.rs:237-258).
+#pragma once
+#include "ptx_core.cuh"
+
+namespace ptx {
+
+PTX_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // low word of (hi:lo) >> (sh & 31)
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    sh &= 31u;
+    return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+}
+PTX_HD uint32_t ffs32(uint32_t m) {  // index of the lowest set bit, m != 0
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffs((int)m) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(m);
+#endif
+}
+
+// ---- byte classes, four bytes at a time: 0x80 in every byte of the result that belongs to the class
+PTX_HD uint32_t eq_mask4(uint32_t w, uint32_t rep) {  // bytes equal to the byte replicated in `rep`
+    const uint32_t y = w ^ rep;
+    return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y) & 0x80808080u;
+}
+PTX_HD uint32_t nondigit_mask4(uint32_t w) {  // bytes outside '0'..'9'
+    const uint32_t t = w ^ 0x30303030u;
+    return (((t & 0x7f7f7f7fu) + 0x76767676u) | t) & 0x80808080u;
+}
+// Two 0x80-per-byte masks (text bytes 0-3 and 4-7) -> 8 bits, bit i = byte i.  One multiply gathers the eight
+// flags: the partial products land on pairwise different bit positions (3,7,..,31 shifted by 0,7,14,21 fall into
+// four different residue classes mod 4), so nothing carries.
+PTX_HD uint32_t pack8(uint32_t m03, uint32_t m47) { return ((m47 | (m03 >> 4)) * 0x00204081u) >> 24; }
+
+// newline and tab flags of one 16-byte piece of text, bit i = byte i
+PTX_HD void classify16(uint32_t x, uint32_t y, uint32_t z, uint32_t w, uint32_t& nl16, uint32_t& tab16) {
+    nl16 = pack8(eq_mask4(x, 0x0a0a0a0au), eq_mask4(y, 0x0a0a0a0au)) | (pack8(eq_mask4(z, 0x0a0a0a0au), eq_mask4(w, 0x0a0a0a0au)) << 8);
+    tab16 = pack8(eq_mask4(x, 0x09090909u), eq_mask4(y, 0x09090909u)) | (pack8(eq_mask4(z, 0x09090909u), eq_mask4(w, 0x09090909u)) << 8);
+}
+
+// ---- unaligned text words.  Wd = the staged window as aligned 32-bit words (little endian)
+PTX_HD uint32_t ld4(const uint32_t* Wd, uint32_t p) {
+    const uint32_t i = p >> 2;
+    return funnel_r(Wd[i], Wd[i + 1], p << 3);
+}
+PTX_HD void ld8(const uint32_t* Wd, uint32_t p, uint32_t& lo, uint32_t& hi) {
+    const uint32_t i = p >> 2, sh = p << 3;
+    const uint32_t w0 = Wd[i], w1 = Wd[i + 1], w2 = Wd[i + 2];
+    lo = funnel_r(w0, w1, sh);
+    hi = funnel_r(w1, w2, sh);
+}
+
+// four decimal digits held as byte VALUES 0..9, byte 0 the most significant -> their number
+PTX_HD uint32_t swar4(uint32_t v) {
+    const uint32_t t = v * 10u + (v >> 8);  // byte 0 = 10 d0 + d1, byte 2 = 10 d2 + d3 (no byte exceeds 99: nothing carries)
+    return (t & 0xFFu) * 100u + ((t >> 16) & 0xFFu);
+}
+// n <= 8 digit bytes (already XORed with '0') at the low end of (hi:lo) -> right-aligned: byte 7 = last digit
+PTX_HD void align8(uint32_t lo, uint32_t hi, uint32_t n, uint32_t& xl, uint32_t& xh) {
+    const uint64_t x = (((uint64_t)hi << 32) | (uint64_t)lo) << (8u * (8u - n));
+    xl = (uint32_t)x;
+    xh = (uint32_t)(x >> 32);
+}
+
+// cursor over the set bits of a bitmap (bit i of word j = byte 32 j + i).  A word of all ones lies behind the
+// bitmap of the window, so next() always terminates; positions at or beyond the window mean "not found".
+struct BitCursor {
+    const uint32_t* w;
+    uint32_t wi, m;
+    PTX_HD void seek(const uint32_t* words, uint32_t pos) {
+        w = words;
+        wi = pos >> 5;
+        m = words[wi] & (0xFFFFFFFFu << (pos & 31u));
+    }
+    PTX_HD uint32_t next() {
+        while (m == 0u) m = w[++wi];
+        const uint32_t b = ffs32(m);
+        m &= m - 1u;
+        return (wi << 5) + b;
+    }
+};
+
+struct FastRec {
+    IdHash h;
+    uint32_t qlen, c7, c8, c9, mapq;  // valid unless the matching bit of `nulls` is set
+    uint32_t nulls;                   // bit 0 qlen, 1 c7, 2 c8, 3 c9, 4 mapq
+    uint32_t W, vmin, vmax;           // walk nodes (ids < 10^9), min / max id (W > 0)
+    uint32_t path_pos, path_end;      // bytes [pos,end) of column 6
+    bool path_null, monotone;
+};
+constexpr uint32_t FN_QLEN = 1u, FN_C7 = 2u, FN_C8 = 4u, FN_C9 = 8u, FN_MAPQ = 16u;
+
+// One integer column [a,b): `[0-9]{1,8}` -> value; empty or non-numeric text -> null (parse_int_field: junk in an
+// integer column is null); a sign or more than 8 bytes -> `slow` (the exact parser decides).  Branch-free.
+PTX_HD uint32_t fast_int(const uint32_t* Wd, uint32_t a, uint32_t b, uint32_t null_bit, uint32_t& nulls, bool& slow) {
+    const uint32_t n = b - a;
+    uint32_t lo, hi;
+    ld8(Wd, a, lo, hi);
+    lo ^= 0x30303030u;
+    hi ^= 0x30303030u;
+    const bool fits = n - 1u <= 7u;  // 1..8 bytes
+    uint32_t xl, xh;
+    align8(lo, hi, fits ? n : 8u, xl, xh);
+    const bool bad = ((((xl + 0x76767676u) | xl) | ((xh + 0x76767676u) | xh)) & 0x80808080u) != 0u;  // some byte is not 0..9
+    const uint32_t c0 = lo & 0xFFu;  // '+' ^ '0' = 0x1b, '-' ^ '0' = 0x1d
+    slow |= n > 8u;
+    slow |= fits && bad && (c0 == 0x1bu || c0 == 0x1du);
+    const bool isnull = !fits || bad;
+    if (isnull) nulls |= null_bit;
+    return isnull ? 0u : swar4(xl) * 10000u + swar4(xh);
+}
+
+// Columns 1..12 of the line [s, e] of the window, e = position of the '\n' that ends it.  lim = bytes of text in the
+// window (the tab bitmap covers exactly those, then a sentinel word of all ones; Wd is readable 128 bytes beyond).
+// `mask` = lanes that call this together.  Returns false if the record needs the exact parser.
+PTX_HD bool fast_parse(const uint32_t* Wd, const uint32_t* tabw, uint32_t s, uint32_t e, uint32_t lim, FastRec& r, uint32_t mask,
+                       uint32_t* stash, uint32_t stash_stride, uint32_t stash_cap) {
+    BitCursor tc;
+    tc.seek(tabw, s);
+    const uint32_t t1 = tc.next(), t2 = tc.next();
+    tc.next();
+    tc.next();
+    const uint32_t t5 = tc.next(), t6 = tc.next(), t7 = tc.next(), t8 = tc.next(), t9 = tc.next();
+    tc.next();
+    const uint32_t t11 = tc.next(), t12 = tc.next();
+    // 12 columns inside the window, and not a "\r\n" line (the '\r' would end the last column, term_at)
+    bool ok = e < lim && t11 < e;
+    if (ok) ok = ((Wd[(e - 1u) >> 2] >> (((e - 1u) & 3u) * 8u)) & 0xFFu) != (uint32_t)'\r';
+    r.nulls = 0;
+    r.qlen = r.c7 = r.c8 = r.c9 = r.mapq = 0;
+    r.W = 0;
+    r.vmin = 0xFFFFFFFFu;
+    r.vmax = 0;
+    r.path_pos = t5 + 1u;
+    r.path_end = t6;
+    r.path_null = false;
+    r.monotone = true;
+    r.h.lo = 1;
+    r.h.hi = 0;
+    bool slow = false;
+#if defined(__CUDA_ARCH__)
+    const uint32_t okmask = __ballot_sync(mask, ok);  // the lanes that go through the columns together
+#else
+    const uint32_t okmask = mask;
+#endif
+    if (ok) {
+        {   // column 1: the id hash over 4-byte words (same value as IdHasher::byte over the bytes)
+            IdHasher H;
+            const uint32_t n = t1 - s;
+            uint32_t p = s;
+            for (uint32_t k = n >> 2; k; --k, p += 4u) H.mix(ld4(Wd, p));
+            if (n & 3u) H.mix(ld4(Wd, p) & (0xFFFFFFFFu >> (32u - 8u * (n & 3u))));
+            H.nbytes = n;
+            H.word = 0;
+            r.h = H.finish_words();
+        }
+        PTX_RECONVERGE(okmask);
+        r.qlen = fast_int(Wd, t1 + 1u, t2, FN_QLEN, r.nulls, slow);
+        r.c7 = fast_int(Wd, t6 + 1u, t7, FN_C7, r.nulls, slow);
+        r.c8 = fast_int(Wd, t7 + 1u, t8, FN_C8, r.nulls, slow);
+        r.c9 = fast_int(Wd, t8 + 1u, t9, FN_C9, r.nulls, slow);
+        r.mapq = fast_int(Wd, t11 + 1u, t12 < e ? t12 : e, FN_MAPQ, r.nulls, slow);
+        // column 6: every non-digit byte (the closing tab included) ends the digit run in front of it
+        const uint32_t p6 = t5 + 1u, e6 = t6;
+        r.path_null = (e6 - p6 == 1u) && ((ld4(Wd, p6) & 0xFFu) == (uint32_t)'*');
+        uint32_t last_sep = t5, W = 0, prev = 0, vmin = 0xFFFFFFFFu, vmax = 0;
+        bool inc = true, dec = true;
+        for (uint32_t p = p6; p <= e6; p += 32u) {
+            const uint32_t nbits = (e6 - p + 1u) < 32u ? (e6 - p + 1u) : 32u;  // bytes of [p6, e6] in this segment
+            uint32_t nd = 0;
+            {
+                const uint32_t i0 = p >> 2, sh = p << 3;
+                uint32_t wa = Wd[i0];
+                for (uint32_t j = 0; 4u * j < nbits; j += 2u) {
+                    const uint32_t wb = Wd[i0 + j + 1u], wc = Wd[i0 + j + 2u];
+                    nd |= pack8(nondigit_mask4(funnel_r(wa, wb, sh)), nondigit_mask4(funnel_r(wb, wc, sh))) << (4u * j);
+                    wa = wc;
+                }
+            }
+            if (nbits < 32u) nd &= (1u << nbits) - 1u;
+            PTX_RECONVERGE(okmask);
+            while (nd) {
+                const uint32_t q = p + ffs32(nd);
+                nd &= nd - 1u;
+                const uint32_t n = q - last_sep - 1u;
+                uint32_t a = last_sep + 1u;
+                last_sep = q;
+                if (n) {
+                    // ids of up to 9 digits; 10-18 digit ids are valid too: the exact parser reads those
+                    slow |= n > 9u;
+                    const uint32_t d0 = (ld4(Wd, a) & 0xFFu) - (uint32_t)'0';
+                    const uint32_t top = n == 9u ? d0 * 100000000u : 0u;
+                    a += n == 9u ? 1u : 0u;
+                    uint32_t lo, hi, xl, xh;
+                    ld8(Wd, a, lo, hi);
+                    align8(lo ^ 0x30303030u, hi ^ 0x30303030u, n < 8u ? n : 8u, xl, xh);
+                    const uint32_t v = top + swar4(xl) * 10000u + swar4(xh);
+                    inc = inc && (W == 0u || v > prev);
+                    dec = dec && (W == 0u || v < prev);
+                    prev = v;
+                    vmin = v < vmin ? v : vmin;
+                    vmax = v > vmax ? v : vmax;
+                    if (W < stash_cap) stash[W * stash_stride] = v;
+                    ++W;
+                }
+            }
+            PTX_RECONVERGE(okmask);
+        }
+        slow |= W > stash_cap;  // longer walk than the stash: the exact parser decodes it again when it is written out
+        r.W = W;
+        r.vmin = vmin;
+        r.vmax = vmax;
+        r.monotone = inc || dec;
+    }
+    PTX_RECONVERGE(mask);
+    return ok && !slow;
+}
+
+}  // namespace ptx

@@ -22,6 +22,8 @@ constexpr uint32_t MAX_TILE = MAX_ROWS * MICRO;
 constexpr uint32_t OVER = 2048;
 constexpr uint32_t PRE = 256;  // keeps `text` 256-byte aligned inside a cudaMalloc'ed buffer
 constexpr int INGEST_THREADS = 256;
+constexpr int SHORT_THREADS = 128;       // k_ingest_s: small CTAs, 7 per SM - the barriers between its phases overlap across CTAs
+constexpr uint32_t SHORT_REC_CAP = 512;  // k_ingest_s: line starts kept in smem per round
 constexpr uint32_t REC_CAP = 1024;  // record starts kept in smem per round
 constexpr double LONG_LINE_BYTES = 320.0;  // mean line length from which a chunk is parsed by k_ingest<LONG>
 constexpr uint32_t HIST_SLOTS_LOG2 = 7;  // per-tile species-count accumulators in shared memory (multi-species runs)
@@ -76,8 +78,11 @@ struct IngestArgs {
     uint64_t n_bytes;      // text bytes (whole lines)
     uint64_t padded_bytes; // bytes readable from `text` (text + newline padding)
     uint32_t n_tiles;
-    uint32_t rows_per_warp;      // tile = rows_per_warp * 4096 bytes
+    uint32_t tile_bytes;         // bytes of text per CTA: a multiple of 512 (k_ingest_s) / of 4096 (k_ingest<>, and whenever micro_base is used)
+    uint32_t over_bytes;         // k_ingest_s: bytes staged behind the tile (the tail of its last line): 512..OVER, multiple of 512
+    uint32_t no_sort;            // k_ingest_s: keep the lines of a tile in file order (PTX_NO_SORT=1, measurements)
     uint32_t long_mode;          // long lines: warp-cooperative walk decode (k_ingest<true>)
+    uint32_t old_short;          // PTX_OLD_INGEST=1: the byte-at-a-time short-read kernel of round 1 (A/B measurements)
     const uint64_t* micro_base;  // [n_micro] exclusive record prefix per micro-tile within the chunk, from the count pass.
                                  // null = SINGLE-PASS mode: no count pass ran, rows are numbered later from tile_info/row_key
     uint4* tile_info;            // single-pass: [n_tiles] {first record-table entry, line slots, GAF rows, 0} of each tile

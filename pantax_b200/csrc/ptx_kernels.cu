@@ -17,6 +17,7 @@
 #include <atomic>
 
 #include "ptx_internal.h"
+#include "ptx_fast.cuh"
 
 namespace ptx {
 
@@ -350,10 +351,6 @@ struct DevSink {
 // ---- warp-cooperative decode of the walk column (long reads: a tile holds few lines, each with a walk of tens
 // to hundreds of nodes).  The 32 lanes take 4 bytes each of a 128-byte window of the column; byte classes come
 // from SWAR masks, node starts from ballots, every lane that owns a start converts that digit run.
-__device__ __forceinline__ uint32_t eq_mask4(uint32_t w, uint32_t rep) {  // 0x80 in every byte of w equal to the byte of rep
-    const uint32_t y = w ^ rep;
-    return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y) & 0x80808080u;
-}
 __device__ __forceinline__ uint32_t digit_mask4(uint32_t w) {  // 0x80 in every byte that is '0'..'9'
     const uint32_t t = w ^ 0x30303030u;
     const uint32_t bad = (t & 0xF0F0F0F0u) | (((t & 0x0F0F0F0Fu) + 0x06060606u) & 0x10101010u);
@@ -483,8 +480,8 @@ __global__ void __launch_bounds__(INGEST_THREADS, LONG ? 3 : 4) k_ingest(const I
     constexpr int MODE = MODE_CLASSIFY;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t rows = a.rows_per_warp;             // 1..8 rows of 512 B per warp
-    const uint32_t tile_bytes = rows * (INGEST_THREADS / 32u) * 512u;  // multiple of 4096
+    const uint32_t tile_bytes = a.tile_bytes;          // multiple of 4096 for this kernel
+    const uint32_t rows = tile_bytes / ((INGEST_THREADS / 32u) * 512u);  // 1..8 rows of 512 B per warp
     const uint32_t stage_bytes = tile_bytes + OVER;
     uint8_t* stage = smem;  // tile_bytes + OVER, then 16 sentinel '\n' (the column scanners stop at a newline)
     uint32_t* stash = reinterpret_cast<uint32_t*>(smem + stage_bytes + 16);                  // [STASH_CAP][INGEST_THREADS]
@@ -892,6 +889,413 @@ __global__ void __launch_bounds__(INGEST_THREADS, LONG ? 3 : 4) k_ingest(const I
     }
     if (hist_smem) {
         for (uint32_t i = tid; i < HIST_SLOTS; i += INGEST_THREADS) {
+            const uint32_t label = hkey[i];
+            if (label == LABEL_U) continue;
+            unsigned long long* hp = a.hist + 4ull * label;
+            const uint32_t* hv = hval + 4u * i;
+            atomicAdd(hp + 0, (unsigned long long)hv[0]);
+            if (hv[3]) atomicAdd(hp + 1, (unsigned long long)hv[3]);
+            if (hv[1]) atomicAdd(hp + 2, (unsigned long long)hv[1]);
+            if (hv[2]) atomicAdd(hp + 3, (unsigned long long)hv[2]);
+        }
+    }
+}
+
+// =====================================================================================
+// k_ingest_s: the short-read ingest kernel around a structural index of the tile.
+//   A. every thread classifies 16-byte pieces of the staged text (LDS.128, conflict-free): newline and tab flags,
+//      byte-ordered, into two shared-memory bitmaps (ptx_fast.cuh: classify16)
+//   B. line starts from the newline bitmap (popc + block scan), ordered by line length
+//   C. one thread per record: fast_parse (ptx_fast.cuh) finds the columns with ffs on the tab bitmap, converts integers
+//      and walk ids four digits per multiply, hashes the id from 4-byte words - no byte is loaded on its own.
+//      Records it declines (signs, "\r\n", 10+ digit ids, short rows, lines leaving the window: rare) go through the
+//      exact byte parser parse_record, first on the staged text, then on the global copy of the line.
+// Same outputs as k_ingest<false>: species counts, record table, CSR walks, labels / tile_info / row_key.
+// =====================================================================================
+constexpr uint32_t STAGE_PAD = 128;  // '\n' bytes readable behind the staged window (ld8 near its end, sentinel for parse_record)
+
+__device__ __noinline__ void parse_record_exact(const uint8_t* stage, uint32_t p, uint32_t stage_bytes, const uint8_t* gtile, uint32_t glim,
+                                                RecParse* out, uint32_t* from_global) {
+    RecParse r;
+    const uint32_t self = 1u << (threadIdx.x & 31u);
+    *from_global = 0u;
+    if (!parse_record(stage, p, stage_bytes, r, self, nullptr, 0, 0)) {  // the columns run past the staged window
+        parse_record(gtile, p, glim, r, self, nullptr, 0, 0);
+        *from_global = 1u;
+    }
+    *out = r;
+}
+
+__global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tile_bytes = a.tile_bytes;         // multiple of 512
+    const uint32_t stage_bytes = tile_bytes + a.over_bytes;   // multiple of 32
+    const uint32_t bm_words = stage_bytes / 32u;      // bitmap words of the window; a sentinel word of all ones behind them
+    uint8_t* stage = smem;                            // [stage_bytes + STAGE_PAD]
+    const uint32_t* Wd = reinterpret_cast<const uint32_t*>(smem);
+    uint32_t* nlw = reinterpret_cast<uint32_t*>(smem + stage_bytes + STAGE_PAD);
+    uint32_t* tabw = nlw + bm_words + 2u;
+    uint32_t* stash = tabw + bm_words + 2u;                                                  // [STASH_CAP][SHORT_THREADS]
+    uint16_t* rec_tmp = reinterpret_cast<uint16_t*>(stash);                                  // [SHORT_REC_CAP] sort scratch, dead before the records are parsed
+    uint16_t* rec_start = reinterpret_cast<uint16_t*>(stash + STASH_CAP * SHORT_THREADS);  // [SHORT_REC_CAP] line starts of the round
+    uint16_t* order = rec_start + SHORT_REC_CAP;                                                   // [SHORT_REC_CAP] lines by length
+    uint16_t* inv_pre = order + SHORT_REC_CAP;                                                     // [SHORT_REC_CAP] invalid line slots before slot k
+    uint32_t* hkey = reinterpret_cast<uint32_t*>(inv_pre + SHORT_REC_CAP);                         // [HIST_SLOTS] (S > 1 only)
+    uint32_t* hval = hkey + HIST_SLOTS;                                                      // [HIST_SLOTS][4]
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t warp_tot[SHORT_THREADS / 32];
+    __shared__ uint32_t bin_cnt[64];
+    __shared__ uint32_t inv_flag, inv_tot_s, slot_base_s;
+
+    const uint64_t t0 = (uint64_t)blockIdx.x * tile_bytes;
+    const uint8_t* gtile = a.text + t0;
+
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&mbar, stage_bytes);
+        bulk_g2s(stage, gtile, stage_bytes, &mbar);
+    }
+    if (tid < STAGE_PAD / 4u) reinterpret_cast<uint32_t*>(stage + stage_bytes)[tid] = 0x0a0a0a0au;
+    if (tid < 2u) { nlw[bm_words + tid] = 0xFFFFFFFFu; tabw[bm_words + tid] = 0xFFFFFFFFu; }
+    const bool hist_smem = a.ranges.S > 1;
+    if (hist_smem)
+        for (uint32_t i = tid; i < HIST_SLOTS * 5u; i += SHORT_THREADS) hkey[i] = i < HIST_SLOTS ? LABEL_U : 0u;
+    const uint32_t* sstart = a.ranges.sstart;
+    const bool single_pass = a.micro_base == nullptr;
+    const uint32_t rec_base = single_pass ? 0u : (uint32_t)a.micro_base[(uint64_t)blockIdx.x * (tile_bytes / MICRO)];
+    const uint32_t glim = (uint32_t)min((uint64_t)0xFFFF0000ull, a.padded_bytes - t0);
+    const RangesView& R = a.ranges;
+    mbar_wait(&mbar, 0);
+
+    // ---- A: structural index of the window
+    for (uint32_t pc = tid; pc < stage_bytes / 16u; pc += SHORT_THREADS) {
+        const uint4 q = reinterpret_cast<const uint4*>(stage)[pc];
+        uint32_t nl16, tab16;
+        classify16(q.x, q.y, q.z, q.w, nl16, tab16);
+        reinterpret_cast<uint16_t*>(nlw)[pc] = (uint16_t)nl16;
+        reinterpret_cast<uint16_t*>(tabw)[pc] = (uint16_t)tab16;
+    }
+    __syncthreads();
+
+    // a line belongs to the tile that holds the newline in front of it: line starts q + 1 for newlines at q < tile_bytes,
+    // as long as the start lies inside the text (what follows the last line is newline padding)
+    const uint32_t nw = tile_bytes / 32u;
+    const uint32_t wpt = (nw + SHORT_THREADS - 1u) / SHORT_THREADS;  // <= 8 bitmap words per thread, consecutive
+    const uint64_t rest = a.n_bytes - t0;                               // text bytes from the tile start (>= 1)
+    const uint32_t qmax = rest - 1u < (uint64_t)tile_bytes ? (uint32_t)(rest - 1u) : tile_bytes;  // newlines at q < qmax start a line
+    const uint32_t first_slot = (blockIdx.x == 0 && tid == 0) ? 1u : 0u;  // the line at text[0]
+
+    uint32_t n_rec = 0;
+    uint32_t valid_prev = 0;
+    for (uint32_t round = 0; round == 0 || round < n_rec; round += SHORT_REC_CAP) {
+        // ---- B: number the line starts (recomputed in the rare extra rounds of a tile with more than SHORT_REC_CAP lines)
+        {
+            uint32_t mw[8];
+            uint32_t cnt = first_slot;
+#pragma unroll
+            for (uint32_t j = 0; j < 8u; ++j) {
+                const uint32_t wi = tid * wpt + j;
+                uint32_t m = 0;
+                if (j < wpt && wi < nw) {
+                    m = nlw[wi];
+                    const uint32_t b0 = wi * 32u;
+                    if (b0 + 32u > qmax) m = b0 >= qmax ? 0u : (m & ((1u << (qmax - b0)) - 1u));
+                }
+                mw[j] = m;
+                cnt += __popc(m);
+            }
+            uint32_t x = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= (uint32_t)d) x += y;
+            }
+            if (lane == 31u) warp_tot[warp] = x;
+            if (tid == 0) inv_flag = 0;
+            __syncthreads();
+            uint32_t idx = x - cnt;
+            n_rec = 0;
+#pragma unroll
+            for (int w = 0; w < SHORT_THREADS / 32; ++w) {
+                const uint32_t t = warp_tot[w];
+                if ((uint32_t)w < warp) idx += t;
+                n_rec += t;
+            }
+            if (first_slot) {
+                if (idx >= round && idx < round + SHORT_REC_CAP) rec_start[idx - round] = 0;
+                ++idx;
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < 8u; ++j) {
+                uint32_t m = mw[j];
+                const uint32_t b0 = (tid * wpt + j) * 32u + 1u;
+                while (m) {
+                    const uint32_t bit = __ffs(m) - 1;
+                    m &= m - 1u;
+                    if (idx >= round && idx < round + SHORT_REC_CAP) rec_start[idx - round] = (uint16_t)(b0 + bit);
+                    ++idx;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t n_round = min(SHORT_REC_CAP, n_rec - round);
+
+        // ---- empty lines and '@' comments are line slots but not records (rare): inv_pre[k] = invalid slots before slot k
+        uint32_t inv_total = 0;
+        {
+            bool inv = false;
+            for (uint32_t k = tid; k < n_round; k += SHORT_THREADS) inv |= !valid_first(stage, rec_start[k]);
+            if (inv) inv_flag = 1;
+            __syncthreads();
+            if (inv_flag) {
+                if (warp == 0) {
+                    uint32_t base = 0;
+                    for (uint32_t k0 = 0; k0 < n_round; k0 += 32) {
+                        const uint32_t k = k0 + lane;
+                        const bool bad = k < n_round && !valid_first(stage, rec_start[k]);
+                        const unsigned bm = __ballot_sync(0xffffffffu, bad);
+                        if (k < n_round) inv_pre[k] = (uint16_t)(base + __popc(bm & ((1u << lane) - 1u)));
+                        base += __popc(bm);
+                    }
+                    if (lane == 0) inv_tot_s = base;
+                }
+                __syncthreads();
+                inv_total = inv_tot_s;
+            }
+        }
+
+        // ---- record-table entries of the round; lines ordered by length (a proxy for the walk length)
+        if (tid < 64) bin_cnt[tid] = 0;
+        if (tid == 64) {
+            uint32_t sb = atomicAdd(a.cursors + 0, n_round);
+            if (single_pass) {
+                if (sb + n_round > a.slots_cap || n_rec > SHORT_REC_CAP) {
+                    atomicOr(a.cursors + 3, 1u);  // the host redoes the chunk with the count pass
+                    sb = 0xFFFFFFFFu;
+                } else {
+                    a.tile_info[blockIdx.x] = make_uint4(sb, n_round, n_round - inv_total, 0u);
+                    atomicAdd(a.cursors + 2, n_round - inv_total);
+                }
+            }
+            slot_base_s = sb;
+        }
+        __syncthreads();
+        if (slot_base_s == 0xFFFFFFFFu) return;
+        if (a.no_sort) {
+            for (uint32_t k = tid; k < n_round; k += SHORT_THREADS) order[k] = (uint16_t)k;
+        } else {
+            for (uint32_t k = tid; k < n_round; k += SHORT_THREADS) {
+                const uint32_t s0 = rec_start[k];
+                const uint32_t e0 = (k + 1 < n_round) ? rec_start[k + 1] : s0 + 112u;
+                const uint32_t len = e0 - s0;
+                const uint32_t bin = len < 64u ? 0u : min((len - 64u) >> 2, 63u);
+                rec_tmp[k] = (uint16_t)((bin << 10) | atomicAdd(&bin_cnt[bin], 1u));
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t c0 = bin_cnt[2 * lane], c1 = bin_cnt[2 * lane + 1];
+                uint32_t x = c0 + c1;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                    if (lane >= (uint32_t)d) x += y;
+                }
+                bin_cnt[2 * lane] = x - c0 - c1;
+                bin_cnt[2 * lane + 1] = x - c1;
+            }
+            __syncthreads();
+            for (uint32_t k = tid; k < n_round; k += SHORT_THREADS) {
+                const uint32_t t = rec_tmp[k];
+                order[bin_cnt[t >> 10] + (t & 1023u)] = (uint16_t)k;
+            }
+        }
+        __syncthreads();
+
+        // ---- C: one thread per record
+        for (uint32_t k0 = 0; k0 < n_round; k0 += SHORT_THREADS) {
+            const uint32_t q = k0 + tid;
+            const bool slot = q < n_round;
+            const uint32_t k = slot ? order[q] : 0u;
+            const uint32_t p = slot ? rec_start[k] : 0u;
+            const bool has = slot && valid_first(stage, p);
+            const uint32_t pmask = __ballot_sync(0xffffffffu, has);
+            // what the rest of the iteration needs to know about the record
+            IdHash h;
+            h.lo = 0; h.hi = 0;
+            uint32_t W = 0, path_pos = 0, path_end = 0;
+            int64_t vmin = -1, vmax = -1, c8 = 0, c9 = 0;
+            unsigned long long ql = 0;      // read length, 0 if null
+            bool lm = false, uq = false;    // 3 <= mapq <= 60, mapq == 60
+            bool cols_ok = false;           // path, c7, c8, c9 all non-null (profile.rs:380-399)
+            bool monotone = true, stashed = false;
+            const uint8_t* b = stage;
+            bool fast = false;
+            if (has) {
+                FastRec f;
+                uint32_t e;  // the '\n' that ends the line: in front of the next line start, or (last line of the round) from the bitmap
+                if (k + 1u < n_round) e = (uint32_t)rec_start[k + 1u] - 1u;
+                else { BitCursor nc; nc.seek(nlw, p); e = nc.next(); }
+                fast = fast_parse(Wd, tabw, p, e, stage_bytes, f, pmask, stash + tid, SHORT_THREADS, STASH_CAP);
+                if (fast) {
+                    h = f.h;
+                    W = f.W;
+                    if (W) { vmin = (int64_t)f.vmin; vmax = (int64_t)f.vmax; }
+                    c8 = (int64_t)f.c8;
+                    c9 = (int64_t)f.c9;
+                    ql = (f.nulls & FN_QLEN) ? 0ull : (unsigned long long)f.qlen;
+                    lm = !(f.nulls & FN_MAPQ) && f.mapq - 3u <= 57u;
+                    uq = lm && f.mapq == 60u;
+                    cols_ok = !f.path_null && !(f.nulls & (FN_C7 | FN_C8 | FN_C9));
+                    monotone = f.monotone;
+                    stashed = true;
+                    path_pos = f.path_pos;
+                    path_end = f.path_end;
+                }
+            }
+            __syncwarp();
+            if (has && !fast) {  // rare: the exact byte parser
+                RecParse r;
+                uint32_t from_global;
+                parse_record_exact(stage, p, stage_bytes, gtile, glim, &r, &from_global);
+                if (from_global) b = gtile;
+                h = r.h;
+                W = r.W;
+                if (W) { vmin = r.vmin; vmax = r.vmax; }
+                c8 = r.c8;
+                c9 = r.c9;
+                ql = r.qlen != NULL_I64 ? (unsigned long long)r.qlen : 0ull;
+                lm = r.mapq != NULL_I64 && r.mapq >= 3 && r.mapq <= 60;
+                uq = lm && r.mapq == 60;
+                cols_ok = !r.path_null && r.c7 != NULL_I64 && r.c8 != NULL_I64 && r.c9 != NULL_I64;
+                monotone = r.monotone;
+                path_pos = r.path_pos;
+                path_end = r.path_end;
+            }
+            __syncwarp();
+            uint32_t label = LABEL_U;
+            if (has) {
+                const uint32_t row = rec_base + valid_prev + k - (inv_total ? (uint32_t)inv_pre[k] : 0u);  // GAF row within the chunk
+                if (a.labels_in) {  // strain-only resume: the species column of reads_classification.tsv
+                    label = a.labels_in[row];
+                    if (label != LABEL_U && W && (vmin < R.start[label] || vmax > R.end[label])) {
+                        atomicOr(a.flags + 3, 1u);
+                        label = LABEL_U;
+                    }
+                } else {
+                    label = classify(R, vmin, vmax, sstart);
+                }
+                if (!single_pass) a.labels[row] = label;
+            }
+            __syncwarp();
+            {   // ---- species counts (profile.rs:219-232, 264-277), warp-aggregated when the warp is one species
+                const bool cnt = has && label != LABEL_U;
+                const unsigned mm = __ballot_sync(0xffffffffu, cnt);
+                if (mm) {
+                    const int leader = __ffs(mm) - 1;
+                    const uint32_t lab0 = __shfl_sync(0xffffffffu, label, leader);
+                    const bool uniform = __all_sync(0xffffffffu, !cnt || label == lab0);
+                    const uint32_t c_lm = (cnt && lm) ? 1u : 0u, c_uq = (cnt && uq) ? 1u : 0u;
+                    const unsigned long long qv = cnt ? ql : 0ull;
+                    if (uniform) {
+                        const uint32_t n1 = __popc(mm);
+                        const uint32_t n3 = __reduce_add_sync(0xffffffffu, c_lm);
+                        const uint32_t n4 = __reduce_add_sync(0xffffffffu, c_uq);
+                        unsigned long long s;
+                        if (__all_sync(0xffffffffu, qv < (1ull << 26))) {  // 32 x 2^26 fits 32 bits: one REDUX
+                            s = (unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)qv);
+                        } else {
+                            s = qv;
+#pragma unroll
+                            for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+                        }
+                        if ((int)lane == leader) {
+                            unsigned long long* hp = a.hist + 4ull * lab0;
+                            atomicAdd(hp + 0, (unsigned long long)n1);
+                            atomicAdd(hp + 1, s);
+                            if (n3) atomicAdd(hp + 2, (unsigned long long)n3);
+                            if (n4) atomicAdd(hp + 3, (unsigned long long)n4);
+                        }
+                    } else if (cnt) {
+                        bool done = false;
+                        if (qv < (1ull << 16)) {  // a tile holds < 64 K lines: the 32-bit sum cannot wrap
+                            uint32_t hs = (label * 0x9E3779B1u) >> (32 - HIST_SLOTS_LOG2);
+                            for (int t = 0; t < 4 && !done; ++t) {
+                                const uint32_t old = atomicCAS(&hkey[hs], LABEL_U, label);
+                                if (old == LABEL_U || old == label) {
+                                    uint32_t* hv = hval + 4u * hs;
+                                    atomicAdd(hv + 0, 1u);
+                                    if (c_lm) atomicAdd(hv + 1, 1u);
+                                    if (c_uq) atomicAdd(hv + 2, 1u);
+                                    if (qv) atomicAdd(hv + 3, (uint32_t)qv);
+                                    done = true;
+                                }
+                                hs = (hs + 1u) & (HIST_SLOTS - 1u);
+                            }
+                        }
+                        if (!done) {
+                            unsigned long long* hp = a.hist + 4ull * label;
+                            atomicAdd(hp + 0, 1ull);
+                            atomicAdd(hp + 1, qv);
+                            if (c_lm) atomicAdd(hp + 2, 1ull);
+                            if (c_uq) atomicAdd(hp + 3, 1ull);
+                        }
+                    }
+                }
+            }
+            // ---- emit the record for k_apply: id hash, label, alignment interval and the walk as CSR node ids
+            const bool labelled = has && label != LABEL_U;
+            const bool eligible = labelled && cols_ok;
+            const uint32_t wcnt = eligible ? W : 0u;
+            uint32_t node_off;
+            {
+                uint32_t x = wcnt;  // node slots: warp scan, one atomicAdd per warp on the chunk's node cursor
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                    if (lane >= (uint32_t)d) x += y;
+                }
+                const uint32_t wtot = __shfl_sync(0xffffffffu, x, 31);
+                uint32_t nbase = 0;
+                if (lane == 0 && wtot) nbase = atomicAdd(a.cursors + 1, wtot);
+                nbase = __shfl_sync(0xffffffffu, nbase, 0);
+                node_off = nbase + x - wcnt;
+            }
+            if (slot) {
+                const uint32_t e = slot_base_s + q;
+                uint32_t wf = wcnt & RM_W_MASK;
+                if (has) wf |= RM_VALID;
+                if (single_pass && has) a.row_key[e] = (uint16_t)(k - (inv_total ? (uint32_t)inv_pre[k] : 0u));
+                if (labelled) wf |= RM_LABELLED;
+                if (eligible) wf |= RM_ELIGIBLE;
+                if (monotone) wf |= RM_MONOTONE;
+                a.meta_b[e] = make_uint4(node_off, wf, label, labelled ? h.hi : 0u);
+                if (labelled) {
+                    a.hash_lo[e] = h.lo;
+                    if (eligible) a.meta_a[e] = make_longlong2(c8, c9);
+                }
+            }
+            if (wcnt) {
+                uint32_t* dst = a.nodes + node_off;
+                if (stashed) {
+                    for (uint32_t i = 0; i < wcnt; ++i) dst[i] = stash[i * SHORT_THREADS + tid];
+                } else {  // exact parser: decode the walk again
+                    WalkIter it{b, path_pos, path_end};
+                    int64_t m;
+                    for (uint32_t i = 0; i < wcnt; ++i) { it.next(m); dst[i] = (uint32_t)m; }
+                }
+            }
+            __syncwarp();
+        }
+        valid_prev += n_round - inv_total;
+        __syncthreads();
+    }
+    if (hist_smem) {
+        for (uint32_t i = tid; i < HIST_SLOTS; i += SHORT_THREADS) {
             const uint32_t label = hkey[i];
             if (label == LABEL_U) continue;
             unsigned long long* hp = a.hist + 4ull * label;
@@ -1648,19 +2052,31 @@ void launch_count_records(const uint8_t* text, uint64_t n_bytes, uint32_t n_micr
     PTX_LAUNCHED();
 }
 
-void launch_ingest(const IngestArgs& a, cudaStream_t st) {
-    const size_t hist_bytes = HIST_SLOTS * 5 * sizeof(uint32_t);
-    const size_t smem_max = MAX_TILE + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 4 * REC_CAP * sizeof(uint16_t) + hist_bytes;
-    const size_t smem = (size_t)a.rows_per_warp * MICRO + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 4 * REC_CAP * sizeof(uint16_t) +
-                        (a.ranges.S > 1 ? hist_bytes : 0);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_ingest<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-        cudaFuncSetAttribute(k_ingest<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-        configured = true;
+size_t ingest_smem_bytes(uint32_t tile_bytes, uint32_t over_bytes, bool short_kernel, bool multi_species) {
+    const size_t hist_bytes = multi_species ? HIST_SLOTS * 5 * sizeof(uint32_t) : 0;
+    if (short_kernel) {
+        const size_t stage_bytes = (size_t)tile_bytes + over_bytes;
+        return stage_bytes + STAGE_PAD + 2 * (stage_bytes / 32 + 2) * sizeof(uint32_t) + STASH_CAP * SHORT_THREADS * sizeof(uint32_t) +
+               3 * SHORT_REC_CAP * sizeof(uint16_t) + hist_bytes;
     }
-    if (a.long_mode) k_ingest<true><<<a.n_tiles, INGEST_THREADS, smem, st>>>(a);
-    else k_ingest<false><<<a.n_tiles, INGEST_THREADS, smem, st>>>(a);
+    return (size_t)tile_bytes + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 4 * REC_CAP * sizeof(uint16_t) + hist_bytes;
+}
+
+void launch_ingest(const IngestArgs& a, cudaStream_t st) {
+    // the opt-in shared-memory size is a per-device attribute of the function
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaFuncSetAttribute(k_ingest<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ingest_smem_bytes(MAX_TILE, OVER, false, true));
+        cudaFuncSetAttribute(k_ingest<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ingest_smem_bytes(MAX_TILE, OVER, false, true));
+        cudaFuncSetAttribute(k_ingest_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ingest_smem_bytes(MAX_TILE, OVER, true, true));
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    const bool multi = a.ranges.S > 1;
+    if (a.long_mode) k_ingest<true><<<a.n_tiles, INGEST_THREADS, ingest_smem_bytes(a.tile_bytes, OVER, false, multi), st>>>(a);
+    else if (a.old_short) k_ingest<false><<<a.n_tiles, INGEST_THREADS, ingest_smem_bytes(a.tile_bytes, OVER, false, multi), st>>>(a);
+    else k_ingest_s<<<a.n_tiles, SHORT_THREADS, ingest_smem_bytes(a.tile_bytes, a.over_bytes, true, multi), st>>>(a);
     PTX_LAUNCHED();
 }
 void launch_hist_merge(const unsigned long long* chunk_hist, unsigned long long* hist, uint32_t n, const uint32_t* cursors, cudaStream_t st) {

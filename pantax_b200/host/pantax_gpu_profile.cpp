@@ -449,6 +449,7 @@ int main(int argc, char** argv) {
             for (double d : depth) { double x = d > o.min_depth ? d : 0.0; if (x > 0) { sum += x; ++c; } }  // profile.rs:2941-2944, 1212-1221
             nz_mean = c ? sum / (double)c : 0.0;
         }
+        std::vector<uint32_t> stamp((size_t)n, 0u);
         for (int64_t h = 0; h < H; ++h) {
             std::string frac_s = "", mean_s = "";
             bool possible = false;
@@ -471,7 +472,17 @@ int main(int argc, char** argv) {
                 possible = true;
                 mean_s = fmt_f64(round2(nz_mean));
             }
-            const float ratio = (float)sc[(size_t)h] / (float)sl[(size_t)h];  // profile.rs:2714-2728 (f32)
+            // profile.rs:2714-2728: RowDVector<f32> x 0/1 incidence = a sequential f32 accumulation over the distinct nodes
+            // of the path in node-index order (nalgebra gemv) - not the exact integer sums once they pass 2^24
+            float acc_c = 0.0f, acc_l = 0.0f;
+            {
+                auto it = g.paths.begin();
+                std::advance(it, h);
+                for (uint64_t v : it->second) stamp[(size_t)v] = (uint32_t)h + 1u;
+                for (int64_t v = 0; v < n; ++v)
+                    if (stamp[(size_t)v] == (uint32_t)h + 1u) { acc_c += (float)cov[(size_t)v]; acc_l += (float)g.nodes_len[(size_t)v]; }
+            }
+            const float ratio = acc_c / acc_l;
             fprintf(f, "%s\t%lld\t%lld\t%s\t%s\t%s\t%lld\t%lld\t%d\n", hap_names[(size_t)h].c_str(), (long long)U[(size_t)h], (long long)nz[(size_t)h],
                     frac_s.c_str(), mean_s.c_str(), fmt_f64((double)ratio).c_str(), (long long)sc[(size_t)h], (long long)sl[(size_t)h], possible ? 1 : 0);
         }

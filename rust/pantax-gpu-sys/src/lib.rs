@@ -143,3 +143,27 @@ impl Gpu {
     }
 }
 impl Drop for Gpu { fn drop(&mut self) { unsafe { ptx_destroy(self.raw) } } }
+
+/// profile.rs:2714-2729: the reference forms `path_cov_ratio` as `RowDVector<f32>(node_base_cov) * incidence` over
+/// `RowDVector<f32>(node_len) * incidence`; nalgebra evaluates each product as a gemv, i.e. a sequential f32
+/// accumulation over the nodes in index order (nodes outside the path contribute 0).  This repeats exactly that over
+/// the distinct nodes of `path`, so the value is the reference's even where the running sums pass 2^24.
+pub fn path_cov_ratio_f32(path: &[usize], node_base_cov: &[usize], node_len: &[i64]) -> f32 {
+    let mut on_path = vec![false; node_len.len()];
+    for &v in path { on_path[v] = true; }
+    let (mut cov, mut len) = (0f32, 0f32);
+    for v in 0..node_len.len() {
+        if on_path[v] { cov += node_base_cov[v] as f32; len += node_len[v] as f32; }
+    }
+    cov / len
+}
+/// The f64 twin used by cbc_opt (profile.rs:1952-1977); exact below 2^53.
+pub fn path_cov_ratio_f64(path: &[usize], node_base_cov: &[usize], node_len: &[i64]) -> f64 {
+    let mut on_path = vec![false; node_len.len()];
+    for &v in path { on_path[v] = true; }
+    let (mut cov, mut len) = (0f64, 0f64);
+    for v in 0..node_len.len() {
+        if on_path[v] { cov += node_base_cov[v] as f64; len += node_len[v] as f64; }
+    }
+    cov / len
+}

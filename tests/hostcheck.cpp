@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../pantax_b200/csrc/ptx_core.cuh"
+#include "../pantax_b200/csrc/ptx_fast.cuh"
 
 using namespace ptx;
 
@@ -49,7 +50,7 @@ extern "C" {
 int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, const int64_t* rend, const int64_t* node_base,
                   const uint32_t* order, int disjoint, int64_t N, const uint32_t* len, int64_t T, const uint32_t* trio_keys,
                   uint32_t stage_lim, int use_stash, uint32_t* labels, int64_t* n_records, int64_t* hist, int64_t* bases, uint64_t* cov,
-                  int64_t* trio_bases, uint32_t* err, int* ids_unique, int64_t* n_overflow) {
+                  int64_t* trio_bases, uint32_t* err, int* ids_unique, int64_t* n_overflow, int64_t* n_fast) {
     std::vector<uint32_t> sstart(S);
     for (int i = 0; i < S; ++i) sstart[i] = (uint32_t)rstart[order[i]];
     RangesView R{rstart, rend, node_base, order, sstart.data(), S, disjoint};
@@ -63,6 +64,23 @@ int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, 
     struct Parsed { RecParse r; uint32_t label; uint32_t pos; bool eligible; uint32_t stash[8]; };
     std::vector<Parsed> recs;
     *n_overflow = 0;
+    *n_fast = 0;
+    // the word-wide fast path (ptx_fast.cuh) sees the text as the ingest kernel stages it: aligned words, a tab and
+    // a newline bitmap built from 16-byte pieces, one sentinel word of all ones behind each bitmap
+    const uint32_t f_lim = (uint32_t)(((n + 31) / 32) * 32 + 32);
+    std::vector<uint32_t> f_words((f_lim + 128) / 4, 0x0a0a0a0au);
+    memcpy(f_words.data(), gaf, n);
+    std::vector<uint32_t> f_tab(f_lim / 32 + 2, 0xFFFFFFFFu), f_nl(f_lim / 32 + 2, 0xFFFFFFFFu);
+    for (uint32_t pc = 0; pc < f_lim / 16; ++pc) {
+        uint32_t nl16, tab16;
+        classify16(f_words[4 * pc], f_words[4 * pc + 1], f_words[4 * pc + 2], f_words[4 * pc + 3], nl16, tab16);
+        reinterpret_cast<uint16_t*>(f_nl.data())[pc] = (uint16_t)nl16;
+        reinterpret_cast<uint16_t*>(f_tab.data())[pc] = (uint16_t)tab16;
+    }
+    for (uint64_t b = 0; b < f_lim; ++b) {  // the bitmaps are what a byte loop says
+        const uint8_t c = reinterpret_cast<const uint8_t*>(f_words.data())[b];
+        if ((((f_nl[b >> 5] >> (b & 31)) & 1u) != 0) != (c == '\n') || (((f_tab[b >> 5] >> (b & 31)) & 1u) != 0) != (c == '\t')) return 11;
+    }
     uint64_t i = 0;
     while (i < n) {
         const uint8_t* nl = (const uint8_t*)memchr(buf.data() + i, '\n', buf.size() - i);
@@ -105,6 +123,27 @@ int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, 
                 }
                 same = same && q.c7 == p.r.c7 && q.c8 == p.r.c8 && q.c9 == p.r.c9 && q.mapq == p.r.mapq;
                 if (!same) return 9;
+            }
+            {   // fast path: whatever it accepts must be what parse_record read
+                FastRec f;
+                uint32_t fst[16];
+                BitCursor nc;
+                nc.seek(f_nl.data(), (uint32_t)i);
+                if (fast_parse(f_words.data(), f_tab.data(), (uint32_t)i, nc.next(), f_lim, f, 1u, fst, 1, 16)) {
+                    ++*n_fast;
+                    auto same_int = [&](int64_t exact, uint32_t v, uint32_t bit) { return (f.nulls & bit) ? exact == NULL_I64 : exact == (int64_t)v; };
+                    bool same = f.h.lo == p.r.h.lo && f.h.hi == p.r.h.hi && same_int(p.r.qlen, f.qlen, FN_QLEN) && same_int(p.r.c7, f.c7, FN_C7) &&
+                                same_int(p.r.c8, f.c8, FN_C8) && same_int(p.r.c9, f.c9, FN_C9) && same_int(p.r.mapq, f.mapq, FN_MAPQ) &&
+                                f.W == p.r.W && f.path_pos == p.r.path_pos && f.path_end == p.r.path_end && f.path_null == p.r.path_null &&
+                                f.monotone == p.r.monotone;
+                    if (same && f.W) same = (int64_t)f.vmin == p.r.vmin && (int64_t)f.vmax == p.r.vmax;
+                    if (same) {
+                        WalkIter it{buf.data(), p.r.path_pos, p.r.path_end};
+                        int64_t m;
+                        for (uint32_t k = 0; k < f.W && same; ++k) same = it.next(m) && m == (int64_t)fst[k];
+                    }
+                    if (!same) return 10;
+                }
             }
             p.label = classify(R, p.r.W ? p.r.vmin : -1, p.r.W ? p.r.vmax : -1, R.sstart);
             p.eligible = p.label != LABEL_U && !p.r.path_null && p.r.c7 != NULL_I64 && p.r.c8 != NULL_I64 && p.r.c9 != NULL_I64;

@@ -18,7 +18,7 @@ SO = os.path.join(HERE, "libhostcheck.so")
 def lib():
     src = os.path.join(HERE, "hostcheck.cpp")
     core = os.path.join(HERE, "..", "pantax_b200", "csrc", "ptx_core.cuh")
-    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(core)):
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(core), os.path.getmtime(core.replace('ptx_core', 'ptx_fast'))):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", SO, src])
     return C.CDLL(SO)
 
@@ -63,14 +63,15 @@ def run_hostcheck(ranges, graphs, gaf: bytes, oracle, stage_lim=0, use_stash=1):
     err = np.zeros(S, dtype=np.uint32)
     uniq = C.c_int(0)
     nover = C.c_int64(0)
+    nfast = C.c_int64(0)
     buf = (C.c_char * len(gaf)).from_buffer_copy(gaf)
     rc = L.hostcheck_run(buf, C.c_uint64(len(gaf)), S, _p(rstart, C.c_int64), _p(rend, C.c_int64), _p(node_base, C.c_int64),
                     _p(order, C.c_uint32), disjoint, C.c_int64(N), _p(ln, C.c_uint32), C.c_int64(T), _p(tk, C.c_uint32),
                     C.c_uint32(stage_lim), use_stash, _p(labels, C.c_uint32), C.byref(nrec), _p(hist, C.c_int64), _p(bases, C.c_int64),
-                    _p(cov, C.c_uint64), _p(tb, C.c_int64), _p(err, C.c_uint32), C.byref(uniq), C.byref(nover))
-    assert rc == 0, f"hostcheck_run failed with code {rc} (9 = parse_head/parse_tail disagree with parse_record)"
+                    _p(cov, C.c_uint64), _p(tb, C.c_int64), _p(err, C.c_uint32), C.byref(uniq), C.byref(nover), C.byref(nfast))
+    assert rc == 0, f"hostcheck_run failed with code {rc} (9 = parse_head/parse_tail disagree with parse_record, 10 = fast_parse disagrees with parse_record, 11 = classify16 bitmaps wrong)"
     return dict(labels=labels[:nrec.value], hist=hist, bases=bases, cov=cov, trio_bases=tb, err=err,
-                ids_unique=bool(uniq.value), node_base=node_base, tbase=tbase, n_overflow=nover.value)
+                ids_unique=bool(uniq.value), node_base=node_base, tbase=tbase, n_overflow=nover.value, n_fast=nfast.value)
 
 
 def assert_hostcheck_matches(ranges, graphs, gaf, stage_lim=0, use_stash=1):

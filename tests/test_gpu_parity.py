@@ -475,6 +475,20 @@ def test_gpu_full_size_config2_bit_exact_and_chunk_invariant():
         assert_gpu_matches_oracle(ctx, o, graphs)
         ref_bases, ref_cov, ref_trio = ctx.node_bases(0), ctx.node_cov(0), ctx.trio_bases(0)
         assert int(ref_bases.sum()) > 10_000_000 * 100
+        # path_cov_ratio (profile.rs:2714-2729) with the reference's arithmetic: a sequential f32 accumulation in node-index
+        # order.  These paths sum to > 2^24 bases, where that is NOT (f32)sum_cov / (f32)sum_len of the exact integers.
+        ratio = api.path_cov_ratio(ctx, 0, graphs[0][1], graphs[0][0])
+        sc, sl = ctx.path_sums(0)
+        assert int(sl.min()) > 2 ** 24
+        lens32, cov32 = graphs[0][0].astype(np.float32), ref_cov.astype(np.float32)
+        for h in (0, 17, 49):
+            acc_c = acc_l = np.float32(0)
+            for v in np.unique(graphs[0][1][h]).tolist():  # the naive loop
+                acc_c = np.float32(acc_c + cov32[v])
+                acc_l = np.float32(acc_l + lens32[v])
+            assert ratio[h] == float(np.float32(acc_c / acc_l))
+        assert np.any(ratio != (sc.astype(np.float32) / sl.astype(np.float32)).astype(np.float64))
+        np.testing.assert_array_equal(api.path_cov_ratio(ctx, 0, graphs[0][1], graphs[0][0], f32=False), sc / sl)
         # same bytes in three uneven chunks that split lines
         ctx.reset()
         cuts = [0, 333_333_337, 333_333_337 + 700_000_001, nbytes]

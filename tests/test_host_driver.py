@@ -117,7 +117,10 @@ def test_host_driver_end_to_end_against_oracle(tmp_path):
                 assert float(p[3]) == m["unique_trio_nodes_fraction"]
             if m["frequencies_mean"] is not None and p[4]:
                 assert float(p[4]) == pytest.approx(m["frequencies_mean"], rel=1e-12)
-            assert float(p[5]) == float(np.float32(sc[h]) / np.float32(sl[h]))
+        # profile.rs:2714-2728: sequential f32 accumulation in node-index order (nalgebra gemv), not (f32)sum / (f32)sum
+        ratios = opy.path_cov_ratio(py_graph(*graphs[s]), o.node_cov(s).tolist())
+        for h, p in enumerate(paths):
+            assert float(p[5]) == ratios[h]
 
 
 @pytest.mark.gpu

@@ -159,3 +159,28 @@ def test_species_profiling_tail_matches_readme_shape():
     assert [t[1] for t in table] == sorted((t[1] for t in table), reverse=True)
     eq, rl = opy.equal_length_test(rows)
     assert eq and rl == 150
+
+
+def test_path_cov_ratio_is_the_sequential_f32_sum_not_the_rounded_exact_sum():
+    """profile.rs:2714-2729: `RowDVector<f32> * DMatrix<f32>` accumulates in f32, node by node.  Once a running sum
+    passes 2^24 the result is no longer (f32)sum_cov / (f32)sum_len formed from the exact integers - the oracle (and the
+    host side of the product, pantax_b200.api.path_cov_ratio) must give the reference's value, not the better one."""
+    rng = np.random.default_rng(5)
+    n = 700_000
+    lens = rng.integers(1, 64, n).astype(np.int64) | 1  # odd lengths: every partial sum needs its low bits
+    cov = (lens - rng.integers(0, 2, n)).astype(np.int64)
+    g = opy.Graph([int(x) for x in lens])
+    g.paths = {"h1": list(range(n)), "h2": list(range(0, n, 3)) + [5, 5, 8]}
+    got = opy.path_cov_ratio(g, cov.tolist())
+    for h, p in enumerate([g.paths["h1"], g.paths["h2"]]):
+        d = sorted(set(p))
+        assert lens[d].sum() > 2 ** 24 or h == 1
+        acc_c = acc_l = np.float32(0)
+        for v in d:  # the naive loop
+            acc_c = np.float32(acc_c + np.float32(cov[v]))
+            acc_l = np.float32(acc_l + np.float32(lens[v]))
+        assert got[h] == float(np.float32(acc_c / acc_l))
+    exact = float(np.float32(cov.sum()) / np.float32(lens.sum()))
+    assert got[0] != exact, "the test graph must be large enough for f32 accumulation to deviate from the exact sums"
+    # f64 (the CBC variant, profile.rs:1952-1977) stays exact
+    assert opy.path_cov_ratio(g, cov.tolist(), f32=False)[0] == cov.sum() / lens.sum()

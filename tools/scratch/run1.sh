@@ -1,0 +1,6 @@
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+for v in "" "PTX_NO_SORT=1" "PTX_TILE_BYTES=12288" "PTX_TILE_BYTES=16384" "PTX_TILE_BYTES=27648"; do echo "== $v"; env $v python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --no-secondary 2>&1 | python -c "import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        j=json.loads(l); r=j['roofline']; print(j['value']/1e9, j['ms_per_step'], r['kernel_ms'], r['k_apply']['kernel_ms'], r['finalize_ms'], r['frac'])
+    else: print(l.rstrip())"; done
