@@ -175,6 +175,17 @@ int ptx_filter_gaf(ptx_ctx* ctx, const uint8_t* bytes, size_t n, uint64_t* out_l
 int ptx_comm_unique_id(void* out128);
 int ptx_comm_init(ptx_ctx* ctx, int n_ranks, int rank, const void* id128);
 
+/* Several GPUs from ONE process (the reference CLI, main.rs:32-58, is a single process): creates one context per
+ * device of `devices[n_devices]` into out[n_devices], already joined into one communicator group (ncclCommInitAll;
+ * rank = position in `devices`), with the id boxes in peer memory (cudaDeviceEnablePeerAccess) when
+ * expected_records_per_device > 0 and every device can reach every other one.  Each context is then fed its own read
+ * batch with ptx_ingest_gaf* (from one host thread or from one thread per context - a context is never shared between
+ * threads), graphs and ranges are set on every context, and ptx_finalize_multi runs ptx_finalize of all of them (the
+ * collectives inside need every rank at once; it uses one host thread per context).  Replaces the nested rayon loops
+ * of strain_profiling (profile.rs:3291-3323) as the unit of parallelism.  Contexts are destroyed one by one. */
+int ptx_create_multi(const int* devices, int n_devices, int64_t expected_records_per_device, ptx_ctx** out);
+int ptx_finalize_multi(ptx_ctx* const* ctxs, int n);
+
 /* ---- introspection ------------------------------------------------------------------ */
 /* JSON with per-stage device timings (ms), launch counts, bytes, table sizes. */
 int ptx_stats_json(ptx_ctx* ctx, char* buf, size_t cap);

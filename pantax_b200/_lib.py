@@ -63,6 +63,8 @@ SIGNATURES = {
     "ptx_filter_gaf": (i32, [vp, vp, C.c_size_t, P(u64), i64, P(i64)]),
     "ptx_comm_unique_id": (i32, [vp]),
     "ptx_comm_init": (i32, [vp, i32, i32, vp]),
+    "ptx_create_multi": (i32, [P(i32), i32, i64, P(vp)]),
+    "ptx_finalize_multi": (i32, [P(vp), i32]),
     "ptx_stats_json": (i32, [vp, C.c_char_p, C.c_size_t]),
     "ptx_timing": (i32, [vp, P(C.c_double), P(C.c_double), P(i64)]),
 }

@@ -74,6 +74,36 @@ class PantaxGpu:
             raise PantaxGpuError(rc, "ptx_create: no usable CUDA device (this library has no CPU fallback)")
         self.taxids: List[str] = []
 
+    @classmethod
+    def create_multi(cls, devices: Sequence[int], expected_records_per_device: int = 0) -> List["PantaxGpu"]:
+        """ptx_create_multi: one context per device, all in THIS process, already one communicator group
+        (rank = position in `devices`).  Finalize them together with `PantaxGpu.finalize_multi`."""
+        L = load_library()
+        n = len(devices)
+        devs = (C.c_int * n)(*[int(d) for d in devices])
+        out = (C.c_void_p * n)()
+        rc = L.ptx_create_multi(devs, n, int(expected_records_per_device), out)
+        if rc:
+            raise PantaxGpuError(rc, "ptx_create_multi")
+        ctxs = []
+        for i in range(n):
+            c = cls.__new__(cls)
+            c._L = L
+            c._h = C.c_void_p(out[i])
+            c.taxids = []
+            ctxs.append(c)
+        return ctxs
+
+    @staticmethod
+    def finalize_multi(ctxs: Sequence["PantaxGpu"]):
+        L = load_library()
+        n = len(ctxs)
+        arr = (C.c_void_p * n)(*[c._h for c in ctxs])
+        rc = L.ptx_finalize_multi(arr, n)
+        if rc:
+            msgs = "; ".join((L.ptx_last_error(c._h) or b"").decode() for c in ctxs)
+            raise PantaxGpuError(rc, msgs)
+
     # -- plumbing ------------------------------------------------------------------
     def _ck(self, rc: int):
         if rc:

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pantax_gpu.h"
@@ -27,6 +28,7 @@ struct NcclApi {
     void* h = nullptr;
     int (*GetUniqueId)(ncclUniqueId*) = nullptr;
     int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;  // all ranks of ONE process (ptx_create_multi)
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;  // NCCL >= 2.18; optional
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -44,6 +46,7 @@ struct NcclApi {
         GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
         CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        CommInitAll = (decltype(CommInitAll))dlsym(h, "ncclCommInitAll");
         CommSplit = (decltype(CommSplit))dlsym(h, "ncclCommSplit");
         AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
         AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
@@ -170,6 +173,7 @@ struct ptx_ctx {
     uint64_t p2p_cap = 0;              // entries per (sender, owner) slice
     ulonglong2* p2p_inbox = nullptr;   // [P][p2p_cap], slice q is written by rank q
     std::vector<void*> p2p_peer;       // opened IPC mappings of the peers' inboxes
+    bool p2p_inprocess = false;        // ptx_create_multi: the peers live in this process (peer access, no IPC mappings to close)
     unsigned long long* out_cursor = nullptr;  // [P] box cursors, [P] "an entry was dropped" marker, then exchange scratch
     uint64_t box_cap = 0, inbox_cap = 0;
     std::vector<unsigned long long> box_sent, recv_done;  // per peer: entries already exchanged by an earlier ptx_finalize
@@ -951,6 +955,7 @@ int ptx_create(int device, ptx_ctx** out) {
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return PTX_E_CUDA;  // no CPU fallback by design
     if (cudaSetDevice(device) != cudaSuccess) return PTX_E_CUDA;
+    if (const char* e = getenv("PTX_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));  // measurement knob: 32 / 64 / 128
     ptx_ctx* ctx = new (std::nothrow) ptx_ctx;
     if (!ctx) return PTX_E_NOMEM;
     ctx->device = device;
@@ -1880,6 +1885,99 @@ int ptx_comm_init(ptx_ctx* ctx, int n_ranks, int rank, const void* id128) {
         rc = p2p_setup(ctx);
         if (rc) return rc;
     }
+    return PTX_OK;
+}
+
+// ---- several GPUs driven from ONE process (the reference CLI is one process) ---------------------------------------
+// One context per device, NCCL communicators from ncclCommInitAll (two sets: reductions and the id-box exchange), and
+// the id boxes in peer memory through cudaDeviceEnablePeerAccess - the in-process twin of ptx_comm_init + CUDA IPC.
+int ptx_create_multi(const int* devices, int n_devices, int64_t expected_records_per_device, ptx_ctx** out) {
+    if (!devices || !out || n_devices < 1) return PTX_E_INVALID;
+    for (int i = 0; i < n_devices; ++i) out[i] = nullptr;
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return PTX_E_INVALID;
+    auto destroy_all = [&]() {
+        for (int i = 0; i < n_devices; ++i) { if (out[i]) ptx_destroy(out[i]); out[i] = nullptr; }
+    };
+    for (int i = 0; i < n_devices; ++i) {
+        const int rc = ptx_create(devices[i], &out[i]);
+        if (rc) { destroy_all(); return rc; }
+        out[i]->reserve_records = std::max<int64_t>(expected_records_per_device, 0);
+    }
+    if (n_devices == 1) return PTX_OK;
+    if (!g_nccl.load() || !g_nccl.CommInitAll) { destroy_all(); return PTX_E_NCCL; }
+    std::vector<ncclComm_t> c1(n_devices, nullptr), c2(n_devices, nullptr);
+    if (g_nccl.CommInitAll(c1.data(), n_devices, devices) != 0 || g_nccl.CommInitAll(c2.data(), n_devices, devices) != 0) {
+        destroy_all();
+        return PTX_E_NCCL;
+    }
+    for (int i = 0; i < n_devices; ++i) {
+        out[i]->comm = c1[i];
+        out[i]->comm_x = c2[i];
+        out[i]->n_ranks = n_devices;
+        out[i]->rank = i;
+    }
+    // peer-memory id boxes: every device must reach every other one, and a size hint is needed (as in p2p_setup)
+    bool peer_ok = expected_records_per_device > 0 && !getenv("PTX_NO_P2P");
+    for (int i = 0; peer_ok && i < n_devices; ++i)
+        for (int j = 0; peer_ok && j < n_devices; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) != cudaSuccess || !can) peer_ok = false;
+        }
+    for (int i = 0; i < n_devices; ++i) {
+        ptx_ctx* ctx = out[i];
+        cudaSetDevice(ctx->device);
+        const int rc = xchg_ensure(ctx, 0);  // side stream, events, cursors, box pointer array
+        if (rc) { destroy_all(); return rc; }
+    }
+    if (peer_ok) {
+        const uint64_t P = (uint64_t)n_devices, hint = (uint64_t)expected_records_per_device;
+        int64_t test_cap = 0;
+        for (int i = 0; i < n_devices; ++i) { test_cap = std::max(test_cap, out[i]->test_box_cap); out[i]->test_box_cap = 0; }
+        const uint64_t cap = test_cap > 0 ? (uint64_t)test_cap : hint / P + hint / (4 * P) + 4096;
+        for (int i = 0; peer_ok && i < n_devices; ++i) {
+            cudaSetDevice(devices[i]);
+            for (int j = 0; j < n_devices; ++j) {
+                if (i == j) continue;
+                const cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) peer_ok = false;
+                cudaGetLastError();
+            }
+            if (peer_ok && cudaMalloc((void**)&out[i]->p2p_inbox, (size_t)P * cap * sizeof(ulonglong2)) != cudaSuccess) { cudaGetLastError(); peer_ok = false; }
+        }
+        if (peer_ok) {
+            for (int i = 0; i < n_devices; ++i) {
+                ptx_ctx* ctx = out[i];
+                cudaSetDevice(ctx->device);
+                std::vector<ulonglong2*> ptrs(P, nullptr);
+                for (int q = 0; q < n_devices; ++q)
+                    if (q != i) ptrs[q] = out[q]->p2p_inbox + (uint64_t)i * cap;  // my slice of rank q's inbox (unified addressing)
+                if (cudaMemcpy(ctx->d_box_ptr, ptrs.data(), (size_t)P * sizeof(ulonglong2*), cudaMemcpyHostToDevice) != cudaSuccess) { destroy_all(); return PTX_E_CUDA; }
+                ctx->p2p = true;
+                ctx->p2p_inprocess = true;
+                ctx->p2p_cap = cap;
+                ctx->box_cap = cap;
+            }
+        } else {
+            for (int i = 0; i < n_devices; ++i) dfree(out[i]->p2p_inbox);
+        }
+    }
+    return PTX_OK;
+}
+
+// ptx_finalize of every context of a ptx_create_multi group.  The collectives inside need all ranks at once: each
+// context's finalize runs on its own host thread here; returns the first error code.
+int ptx_finalize_multi(ptx_ctx* const* ctxs, int n) {
+    if (!ctxs || n < 1) return PTX_E_INVALID;
+    std::vector<int> rc((size_t)n, PTX_OK);
+    std::vector<std::thread> th;
+    for (int i = 1; i < n; ++i) th.emplace_back([&, i]() { rc[(size_t)i] = ptx_finalize(ctxs[i]); });
+    rc[0] = ptx_finalize(ctxs[0]);
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n; ++i)
+        if (rc[(size_t)i]) return rc[(size_t)i];
     return PTX_OK;
 }
 

@@ -447,10 +447,18 @@ PTX_HD void cover_record(const uint8_t* b, const RecParse& r, uint32_t label, in
     WalkIter it{b, r.path_pos, r.path_end};
     const bool stashed = r.stashed;
     const uint32_t W = r.W;  // W == 0: profile.rs:794
-    // rl of node i as the trio loop sees it (:897-900): what its FIRST occurrence in this read added
+    // rl of node i as the trio loop sees it (:897-900): what its FIRST occurrence in this read added.
+    // Strictly monotone ids cannot repeat: either the parser said so (r.monotone), or it is noticed here while the walk
+    // goes by (trend: 0 = one node seen, 1 = rising so far, 2 = falling so far, 3 = neither -> search the earlier nodes).
+    uint32_t trend = 0;
+    int64_t prev_m = 0;
     auto first_occurrence = [&](uint32_t i, int64_t m, int64_t ln, int64_t aln, int64_t& rl) -> bool {
         rl = aln;
-        if (r.monotone) return true;  // strictly monotone ids cannot repeat
+        if (r.monotone) return true;
+        const uint32_t step = m > prev_m ? 1u : (m < prev_m ? 2u : 3u);
+        trend = trend == 0u ? step : (trend == step ? trend : 3u);
+        prev_m = m;
+        if (trend != 3u) return true;
         WalkIter jt{b, r.path_pos, r.path_end};
         for (uint32_t j = 0; j < i; ++j) {
             int64_t mj;
@@ -488,6 +496,7 @@ PTX_HD void cover_record(const uint8_t* b, const RecParse& r, uint32_t label, in
             if (ps >= 0 && ln > ps) sink.set_bits(g, ni, ps, ln);  // negative start wraps `as usize` -> empty
             seen = aln;
             sink.add_bases(g, aln);  // :881 (position 0 is always a first occurrence)
+            prev_m = m;
             gb = g;
             rlb = aln;
             mid_b = (ni.flags & NI_TRIO_MID) != 0;

@@ -55,14 +55,32 @@ PTX_HD void classify16(uint32_t x, uint32_t y, uint32_t z, uint32_t w, uint32_t&
     tab16 = pack8(eq_mask4(x, 0x09090909u), eq_mask4(y, 0x09090909u)) | (pack8(eq_mask4(z, 0x09090909u), eq_mask4(w, 0x09090909u)) << 8);
 }
 
-// ---- unaligned text words.  Wd = the staged window as aligned 32-bit words (little endian)
-PTX_HD uint32_t ld4(const uint32_t* Wd, uint32_t p) {
-    const uint32_t i = p >> 2;
-    return funnel_r(Wd[i], Wd[i + 1], p << 3);
+// ---- the staged window as aligned 32-bit words (little endian).  On the device it lives in shared memory and is read
+// with explicit ld.shared from a 32-bit shared address (a generic pointer made the compiler rebuild the shared base
+// inside every loop); on the host (tests/hostcheck.cpp) it is a plain array.
+struct Words {
+    uint32_t base;      // device: shared-memory address of word 0
+    const uint32_t* p;  // host: the array
+    PTX_HD uint32_t at(uint32_t byte_off) const {  // word at a 4-byte aligned byte offset
+#if defined(__CUDA_ARCH__)
+        uint32_t v;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + byte_off));
+        return v;
+#else
+        return p[byte_off >> 2];
+#endif
+    }
+    PTX_HD uint32_t word(uint32_t i) const { return at(i << 2); }
+};
+
+// unaligned text words: 4 / 8 bytes starting at byte p
+PTX_HD uint32_t ld4(const Words& W, uint32_t p) {
+    const uint32_t o = p & ~3u;
+    return funnel_r(W.at(o), W.at(o + 4u), p << 3);
 }
-PTX_HD void ld8(const uint32_t* Wd, uint32_t p, uint32_t& lo, uint32_t& hi) {
-    const uint32_t i = p >> 2, sh = p << 3;
-    const uint32_t w0 = Wd[i], w1 = Wd[i + 1], w2 = Wd[i + 2];
+PTX_HD void ld8(const Words& W, uint32_t p, uint32_t& lo, uint32_t& hi) {
+    const uint32_t o = p & ~3u, sh = p << 3;
+    const uint32_t w0 = W.at(o), w1 = W.at(o + 4u), w2 = W.at(o + 8u);
     lo = funnel_r(w0, w1, sh);
     hi = funnel_r(w1, w2, sh);
 }
@@ -82,18 +100,22 @@ PTX_HD void align8(uint32_t lo, uint32_t hi, uint32_t n, uint32_t& xl, uint32_t&
 // cursor over the set bits of a bitmap (bit i of word j = byte 32 j + i).  A word of all ones lies behind the
 // bitmap of the window, so next() always terminates; positions at or beyond the window mean "not found".
 struct BitCursor {
-    const uint32_t* w;
-    uint32_t wi, m;
-    PTX_HD void seek(const uint32_t* words, uint32_t pos) {
+    Words w;
+    uint32_t wo, m;  // byte offset of the current bitmap word, its remaining bits
+    PTX_HD void seek(const Words& words, uint32_t pos) {
         w = words;
-        wi = pos >> 5;
-        m = words[wi] & (0xFFFFFFFFu << (pos & 31u));
+        wo = (pos >> 5) << 2;
+        m = w.at(wo) & (0xFFFFFFFFu << (pos & 31u));
     }
     PTX_HD uint32_t next() {
-        while (m == 0u) m = w[++wi];
+        while (m == 0u) { wo += 4u; m = w.at(wo); }
         const uint32_t b = ffs32(m);
         m &= m - 1u;
-        return (wi << 5) + b;
+        return (wo << 3) + b;
+    }
+    PTX_HD void skip() {  // consume one set bit without locating it
+        while (m == 0u) { wo += 4u; m = w.at(wo); }
+        m &= m - 1u;
     }
 };
 
@@ -103,46 +125,46 @@ struct FastRec {
     uint32_t nulls;                   // bit 0 qlen, 1 c7, 2 c8, 3 c9, 4 mapq
     uint32_t W, vmin, vmax;           // walk nodes (ids < 10^9), min / max id (W > 0)
     uint32_t path_pos, path_end;      // bytes [pos,end) of column 6
-    bool path_null, monotone;
+    bool path_null;
 };
 constexpr uint32_t FN_QLEN = 1u, FN_C7 = 2u, FN_C8 = 4u, FN_C9 = 8u, FN_MAPQ = 16u;
 
 // One integer column [a,b): `[0-9]{1,8}` -> value; empty or non-numeric text -> null (parse_int_field: junk in an
-// integer column is null); a sign or more than 8 bytes -> `slow` (the exact parser decides).  Branch-free.
-PTX_HD uint32_t fast_int(const uint32_t* Wd, uint32_t a, uint32_t b, uint32_t null_bit, uint32_t& nulls, bool& slow) {
+// integer column is null); a sign or more than 8 bytes -> bit 0 of `slow` (the exact parser decides).  Branch-free.
+PTX_HD uint32_t fast_int(const Words& W, uint32_t a, uint32_t b, uint32_t null_bit, uint32_t& nulls, uint32_t& slow) {
     const uint32_t n = b - a;
     uint32_t lo, hi;
-    ld8(Wd, a, lo, hi);
+    ld8(W, a, lo, hi);
     lo ^= 0x30303030u;
     hi ^= 0x30303030u;
-    const bool fits = n - 1u <= 7u;  // 1..8 bytes
+    const uint32_t fits = (n - 1u <= 7u) ? 1u : 0u;  // 1..8 bytes
     uint32_t xl, xh;
     align8(lo, hi, fits ? n : 8u, xl, xh);
-    const bool bad = ((((xl + 0x76767676u) | xl) | ((xh + 0x76767676u) | xh)) & 0x80808080u) != 0u;  // some byte is not 0..9
-    const uint32_t c0 = lo & 0xFFu;  // '+' ^ '0' = 0x1b, '-' ^ '0' = 0x1d
-    slow |= n > 8u;
-    slow |= fits && bad && (c0 == 0x1bu || c0 == 0x1du);
-    const bool isnull = !fits || bad;
-    if (isnull) nulls |= null_bit;
+    const uint32_t bad = (((((xl + 0x76767676u) | xl) | ((xh + 0x76767676u) | xh)) & 0x80808080u) != 0u) ? 1u : 0u;  // some byte is not 0..9
+    const uint32_t c0 = lo & 0xFFu;                                                  // '+' ^ '0' = 0x1b, '-' ^ '0' = 0x1d
+    const uint32_t is_sign = (c0 == 0x1bu || c0 == 0x1du) ? 1u : 0u;
+    slow |= (n > 8u ? 1u : 0u) | (fits & bad & is_sign);
+    const uint32_t isnull = (fits ^ 1u) | bad;
+    nulls |= isnull ? null_bit : 0u;
     return isnull ? 0u : swar4(xl) * 10000u + swar4(xh);
 }
 
 // Columns 1..12 of the line [s, e] of the window, e = position of the '\n' that ends it.  lim = bytes of text in the
-// window (the tab bitmap covers exactly those, then a sentinel word of all ones; Wd is readable 128 bytes beyond).
+// window (the tab bitmap covers exactly those, then a sentinel word of all ones; the text is readable 128 bytes beyond).
 // `mask` = lanes that call this together.  Returns false if the record needs the exact parser.
-PTX_HD bool fast_parse(const uint32_t* Wd, const uint32_t* tabw, uint32_t s, uint32_t e, uint32_t lim, FastRec& r, uint32_t mask,
+PTX_HD bool fast_parse(const Words& W, const Words& tabw, uint32_t s, uint32_t e, uint32_t lim, FastRec& r, uint32_t mask,
                        uint32_t* stash, uint32_t stash_stride, uint32_t stash_cap) {
     BitCursor tc;
     tc.seek(tabw, s);
     const uint32_t t1 = tc.next(), t2 = tc.next();
-    tc.next();
-    tc.next();
+    tc.skip();
+    tc.skip();
     const uint32_t t5 = tc.next(), t6 = tc.next(), t7 = tc.next(), t8 = tc.next(), t9 = tc.next();
-    tc.next();
+    tc.skip();
     const uint32_t t11 = tc.next(), t12 = tc.next();
     // 12 columns inside the window, and not a "\r\n" line (the '\r' would end the last column, term_at)
     bool ok = e < lim && t11 < e;
-    if (ok) ok = ((Wd[(e - 1u) >> 2] >> (((e - 1u) & 3u) * 8u)) & 0xFFu) != (uint32_t)'\r';
+    if (ok) ok = ((W.at((e - 1u) & ~3u) >> (((e - 1u) & 3u) * 8u)) & 0xFFu) != (uint32_t)'\r';
     r.nulls = 0;
     r.qlen = r.c7 = r.c8 = r.c9 = r.mapq = 0;
     r.W = 0;
@@ -151,10 +173,9 @@ PTX_HD bool fast_parse(const uint32_t* Wd, const uint32_t* tabw, uint32_t s, uin
     r.path_pos = t5 + 1u;
     r.path_end = t6;
     r.path_null = false;
-    r.monotone = true;
     r.h.lo = 1;
     r.h.hi = 0;
-    bool slow = false;
+    uint32_t slow = 0;
 #if defined(__CUDA_ARCH__)
     const uint32_t okmask = __ballot_sync(mask, ok);  // the lanes that go through the columns together
 #else
@@ -165,37 +186,36 @@ PTX_HD bool fast_parse(const uint32_t* Wd, const uint32_t* tabw, uint32_t s, uin
             IdHasher H;
             const uint32_t n = t1 - s;
             uint32_t p = s;
-            for (uint32_t k = n >> 2; k; --k, p += 4u) H.mix(ld4(Wd, p));
-            if (n & 3u) H.mix(ld4(Wd, p) & (0xFFFFFFFFu >> (32u - 8u * (n & 3u))));
+            for (uint32_t k = n >> 2; k; --k, p += 4u) H.mix(ld4(W, p));
+            if (n & 3u) H.mix(ld4(W, p) & (0xFFFFFFFFu >> (32u - 8u * (n & 3u))));
             H.nbytes = n;
             H.word = 0;
             r.h = H.finish_words();
         }
         PTX_RECONVERGE(okmask);
-        r.qlen = fast_int(Wd, t1 + 1u, t2, FN_QLEN, r.nulls, slow);
-        r.c7 = fast_int(Wd, t6 + 1u, t7, FN_C7, r.nulls, slow);
-        r.c8 = fast_int(Wd, t7 + 1u, t8, FN_C8, r.nulls, slow);
-        r.c9 = fast_int(Wd, t8 + 1u, t9, FN_C9, r.nulls, slow);
-        r.mapq = fast_int(Wd, t11 + 1u, t12 < e ? t12 : e, FN_MAPQ, r.nulls, slow);
+        r.qlen = fast_int(W, t1 + 1u, t2, FN_QLEN, r.nulls, slow);
+        r.c7 = fast_int(W, t6 + 1u, t7, FN_C7, r.nulls, slow);
+        r.c8 = fast_int(W, t7 + 1u, t8, FN_C8, r.nulls, slow);
+        r.c9 = fast_int(W, t8 + 1u, t9, FN_C9, r.nulls, slow);
+        r.mapq = fast_int(W, t11 + 1u, t12 < e ? t12 : e, FN_MAPQ, r.nulls, slow);
         // column 6: every non-digit byte (the closing tab included) ends the digit run in front of it
         const uint32_t p6 = t5 + 1u, e6 = t6;
-        r.path_null = (e6 - p6 == 1u) && ((ld4(Wd, p6) & 0xFFu) == (uint32_t)'*');
-        uint32_t last_sep = t5, W = 0, prev = 0, vmin = 0xFFFFFFFFu, vmax = 0;
-        bool inc = true, dec = true;
+        r.path_null = (e6 - p6 == 1u) && ((ld4(W, p6) & 0xFFu) == (uint32_t)'*');
+        uint32_t last_sep = t5, Wn = 0, vmin = 0xFFFFFFFFu, vmax = 0;
         for (uint32_t p = p6; p <= e6; p += 32u) {
             const uint32_t nbits = (e6 - p + 1u) < 32u ? (e6 - p + 1u) : 32u;  // bytes of [p6, e6] in this segment
             uint32_t nd = 0;
             {
-                const uint32_t i0 = p >> 2, sh = p << 3;
-                uint32_t wa = Wd[i0];
-                for (uint32_t j = 0; 4u * j < nbits; j += 2u) {
-                    const uint32_t wb = Wd[i0 + j + 1u], wc = Wd[i0 + j + 2u];
-                    nd |= pack8(nondigit_mask4(funnel_r(wa, wb, sh)), nondigit_mask4(funnel_r(wb, wc, sh))) << (4u * j);
+                const uint32_t sh = p << 3;
+                uint32_t o = p & ~3u;
+                uint32_t wa = W.at(o);
+                for (uint32_t j = 0; j < nbits; j += 8u, o += 8u) {
+                    const uint32_t wb = W.at(o + 4u), wc = W.at(o + 8u);
+                    nd |= pack8(nondigit_mask4(funnel_r(wa, wb, sh)), nondigit_mask4(funnel_r(wb, wc, sh))) << j;
                     wa = wc;
                 }
             }
             if (nbits < 32u) nd &= (1u << nbits) - 1u;
-            PTX_RECONVERGE(okmask);
             while (nd) {
                 const uint32_t q = p + ffs32(nd);
                 nd &= nd - 1u;
@@ -203,34 +223,32 @@ PTX_HD bool fast_parse(const uint32_t* Wd, const uint32_t* tabw, uint32_t s, uin
                 uint32_t a = last_sep + 1u;
                 last_sep = q;
                 if (n) {
-                    // ids of up to 9 digits; 10-18 digit ids are valid too: the exact parser reads those
-                    slow |= n > 9u;
-                    const uint32_t d0 = (ld4(Wd, a) & 0xFFu) - (uint32_t)'0';
-                    const uint32_t top = n == 9u ? d0 * 100000000u : 0u;
-                    a += n == 9u ? 1u : 0u;
+                    uint32_t top = 0, n8 = n;
+                    if (n > 8u) {  // rare: 9 digits are read here; ids of 10-18 digits are valid too, the exact parser reads those
+                        slow |= n > 9u ? 1u : 0u;
+                        top = ((ld4(W, a) & 0xFFu) - (uint32_t)'0') * 100000000u;
+                        ++a;
+                        n8 = 8u;
+                    }
                     uint32_t lo, hi, xl, xh;
-                    ld8(Wd, a, lo, hi);
-                    align8(lo ^ 0x30303030u, hi ^ 0x30303030u, n < 8u ? n : 8u, xl, xh);
+                    ld8(W, a, lo, hi);
+                    align8(lo ^ 0x30303030u, hi ^ 0x30303030u, n8, xl, xh);
                     const uint32_t v = top + swar4(xl) * 10000u + swar4(xh);
-                    inc = inc && (W == 0u || v > prev);
-                    dec = dec && (W == 0u || v < prev);
-                    prev = v;
                     vmin = v < vmin ? v : vmin;
                     vmax = v > vmax ? v : vmax;
-                    if (W < stash_cap) stash[W * stash_stride] = v;
-                    ++W;
+                    if (Wn < stash_cap) stash[Wn * stash_stride] = v;
+                    ++Wn;
                 }
             }
-            PTX_RECONVERGE(okmask);
         }
-        slow |= W > stash_cap;  // longer walk than the stash: the exact parser decodes it again when it is written out
-        r.W = W;
+        PTX_RECONVERGE(okmask);  // (never inside the loops: their trip counts differ from lane to lane)
+        slow |= Wn > stash_cap ? 1u : 0u;  // longer walk than the stash: the exact parser decodes it again when it is written out
+        r.W = Wn;
         r.vmin = vmin;
         r.vmax = vmax;
-        r.monotone = inc || dec;
     }
     PTX_RECONVERGE(mask);
-    return ok && !slow;
+    return ok && slow == 0u;
 }
 
 }  // namespace ptx

@@ -929,31 +929,33 @@ __device__ __noinline__ void parse_record_exact(const uint8_t* stage, uint32_t p
 __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t tile_bytes = a.tile_bytes;         // multiple of 512
-    const uint32_t stage_bytes = tile_bytes + a.over_bytes;   // multiple of 32
-    const uint32_t bm_words = stage_bytes / 32u;      // bitmap words of the window; a sentinel word of all ones behind them
-    uint8_t* stage = smem;                            // [stage_bytes + STAGE_PAD]
-    const uint32_t* Wd = reinterpret_cast<const uint32_t*>(smem);
-    uint32_t* nlw = reinterpret_cast<uint32_t*>(smem + stage_bytes + STAGE_PAD);
-    uint32_t* tabw = nlw + bm_words + 2u;
-    uint32_t* stash = tabw + bm_words + 2u;                                                  // [STASH_CAP][SHORT_THREADS]
+    const uint32_t tile_bytes = a.tile_bytes;                 // multiple of 128
+    const uint32_t stage_bytes = tile_bytes + a.over_bytes;   // multiple of 128
+    const uint32_t bm_words = stage_bytes / 32u;              // bitmap words of the window; a sentinel word of all ones behind them
+    uint8_t* stage = smem;                                    // [stage_bytes + STAGE_PAD]
+    uint32_t* nlw = reinterpret_cast<uint32_t*>(smem + stage_bytes + STAGE_PAD);             // 16-byte aligned
+    uint32_t* tabw = nlw + ((bm_words + 2u + 3u) & ~3u);
+    uint32_t* stash = tabw + ((bm_words + 2u + 3u) & ~3u);                                   // [STASH_CAP][SHORT_THREADS]
     uint16_t* rec_tmp = reinterpret_cast<uint16_t*>(stash);                                  // [SHORT_REC_CAP] sort scratch, dead before the records are parsed
     uint16_t* rec_start = reinterpret_cast<uint16_t*>(stash + STASH_CAP * SHORT_THREADS);  // [SHORT_REC_CAP] line starts of the round
-    uint16_t* order = rec_start + SHORT_REC_CAP;                                                   // [SHORT_REC_CAP] lines by length
-    uint16_t* inv_pre = order + SHORT_REC_CAP;                                                     // [SHORT_REC_CAP] invalid line slots before slot k
-    uint32_t* hkey = reinterpret_cast<uint32_t*>(inv_pre + SHORT_REC_CAP);                         // [HIST_SLOTS] (S > 1 only)
+    uint16_t* order = rec_start + SHORT_REC_CAP;                                             // [SHORT_REC_CAP] lines by length
+    uint16_t* inv_pre = order + SHORT_REC_CAP;                                               // [SHORT_REC_CAP] invalid line slots before slot k
+    uint32_t* hkey = reinterpret_cast<uint32_t*>(inv_pre + SHORT_REC_CAP);                   // [HIST_SLOTS] (S > 1 only)
     uint32_t* hval = hkey + HIST_SLOTS;                                                      // [HIST_SLOTS][4]
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t warp_tot[SHORT_THREADS / 32];
     __shared__ uint32_t bin_cnt[64];
     __shared__ uint32_t inv_flag, inv_tot_s, slot_base_s;
+    const Words Wd{smem_u32(stage), nullptr}, Wtab{smem_u32(tabw), nullptr}, Wnl{smem_u32(nlw), nullptr};
 
     const uint64_t t0 = (uint64_t)blockIdx.x * tile_bytes;
     const uint8_t* gtile = a.text + t0;
 
+    // ---- stage the tile: one TMA bulk copy, completion on an mbarrier every thread waits on
     if (tid == 0) {
         mbar_init(&mbar, 1);
         fence_mbar_init();
+        inv_flag = 0;
     }
     __syncthreads();
     if (tid == 0) {
@@ -962,6 +964,7 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
     }
     if (tid < STAGE_PAD / 4u) reinterpret_cast<uint32_t*>(stage + stage_bytes)[tid] = 0x0a0a0a0au;
     if (tid < 2u) { nlw[bm_words + tid] = 0xFFFFFFFFu; tabw[bm_words + tid] = 0xFFFFFFFFu; }
+    if (tid < 64u) bin_cnt[tid] = 0;
     const bool hist_smem = a.ranges.S > 1;
     if (hist_smem)
         for (uint32_t i = tid; i < HIST_SLOTS * 5u; i += SHORT_THREADS) hkey[i] = i < HIST_SLOTS ? LABEL_U : 0u;
@@ -972,7 +975,7 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
     const RangesView& R = a.ranges;
     mbar_wait(&mbar, 0);
 
-    // ---- A: structural index of the window
+    // ---- A: structural index of the window (the pad and the sentinel words written above become visible at the barrier behind it)
     for (uint32_t pc = tid; pc < stage_bytes / 16u; pc += SHORT_THREADS) {
         const uint4 q = reinterpret_cast<const uint4*>(stage)[pc];
         uint32_t nl16, tab16;
@@ -984,8 +987,7 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
 
     // a line belongs to the tile that holds the newline in front of it: line starts q + 1 for newlines at q < tile_bytes,
     // as long as the start lies inside the text (what follows the last line is newline padding)
-    const uint32_t nw = tile_bytes / 32u;
-    const uint32_t wpt = (nw + SHORT_THREADS - 1u) / SHORT_THREADS;  // <= 8 bitmap words per thread, consecutive
+    const uint32_t nw = tile_bytes / 32u;                               // bitmap words of the tile (a multiple of 4)
     const uint64_t rest = a.n_bytes - t0;                               // text bytes from the tile start (>= 1)
     const uint32_t qmax = rest - 1u < (uint64_t)tile_bytes ? (uint32_t)(rest - 1u) : tile_bytes;  // newlines at q < qmax start a line
     const uint32_t first_slot = (blockIdx.x == 0 && tid == 0) ? 1u : 0u;  // the line at text[0]
@@ -993,99 +995,101 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
     uint32_t n_rec = 0;
     uint32_t valid_prev = 0;
     for (uint32_t round = 0; round == 0 || round < n_rec; round += SHORT_REC_CAP) {
-        // ---- B: number the line starts (recomputed in the rare extra rounds of a tile with more than SHORT_REC_CAP lines)
-        {
-            uint32_t mw[8];
-            uint32_t cnt = first_slot;
+        // ---- B: number the line starts.  Four consecutive bitmap words (one LDS.128) per thread and pass; a tile of up
+        // to 16 KB is one pass.  (Recomputed in the rare extra rounds of a tile with more than SHORT_REC_CAP lines.)
+        uint32_t idx_base = 0;  // line slots in front of this thread's words, summed over the passes
+        for (uint32_t w0 = 0; w0 < nw; w0 += 4u * SHORT_THREADS) {
+            const uint32_t wi = w0 + 4u * tid;
+            uint4 m4 = make_uint4(0u, 0u, 0u, 0u);
+            if (wi < nw) {
+                m4 = reinterpret_cast<const uint4*>(nlw)[wi >> 2];
+                if ((wi + 4u) * 32u > qmax) {  // last tile only: drop the newlines that start no line
+                    uint32_t* mm = &m4.x;
 #pragma unroll
-            for (uint32_t j = 0; j < 8u; ++j) {
-                const uint32_t wi = tid * wpt + j;
-                uint32_t m = 0;
-                if (j < wpt && wi < nw) {
-                    m = nlw[wi];
-                    const uint32_t b0 = wi * 32u;
-                    if (b0 + 32u > qmax) m = b0 >= qmax ? 0u : (m & ((1u << (qmax - b0)) - 1u));
+                    for (uint32_t j = 0; j < 4u; ++j) {
+                        const uint32_t b0 = (wi + j) * 32u;
+                        if (b0 + 32u > qmax) mm[j] = b0 >= qmax ? 0u : (mm[j] & ((1u << (qmax - b0)) - 1u));
+                    }
                 }
-                mw[j] = m;
-                cnt += __popc(m);
             }
+            const uint32_t cnt = __popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w) + (w0 == 0u ? first_slot : 0u);
             uint32_t x = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
                 if (lane >= (uint32_t)d) x += y;
             }
+            if (w0) __syncthreads();  // the previous pass has read warp_tot
             if (lane == 31u) warp_tot[warp] = x;
-            if (tid == 0) inv_flag = 0;
             __syncthreads();
-            uint32_t idx = x - cnt;
-            n_rec = 0;
+            uint32_t idx = idx_base + x - cnt, tot = 0;
 #pragma unroll
             for (int w = 0; w < SHORT_THREADS / 32; ++w) {
                 const uint32_t t = warp_tot[w];
                 if ((uint32_t)w < warp) idx += t;
-                n_rec += t;
+                tot += t;
             }
-            if (first_slot) {
+            idx_base += tot;
+            if (w0 == 0u && first_slot) {
                 if (idx >= round && idx < round + SHORT_REC_CAP) rec_start[idx - round] = 0;
                 ++idx;
             }
+            const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
-            for (uint32_t j = 0; j < 8u; ++j) {
-                uint32_t m = mw[j];
-                const uint32_t b0 = (tid * wpt + j) * 32u + 1u;
+            for (uint32_t j = 0; j < 4u; ++j) {
+                uint32_t m = mm[j];
+                const uint32_t b0 = (wi + j) * 32u + 1u;
                 while (m) {
                     const uint32_t bit = __ffs(m) - 1;
                     m &= m - 1u;
-                    if (idx >= round && idx < round + SHORT_REC_CAP) rec_start[idx - round] = (uint16_t)(b0 + bit);
+                    const uint32_t q = b0 + bit;
+                    if (idx >= round && idx < round + SHORT_REC_CAP) {
+                        rec_start[idx - round] = (uint16_t)q;
+                        if (!valid_first(stage, q)) inv_flag = 1;  // an empty line or an '@' comment: rare
+                    }
                     ++idx;
                 }
             }
         }
-        __syncthreads();
+        n_rec = idx_base;
         const uint32_t n_round = min(SHORT_REC_CAP, n_rec - round);
-
-        // ---- empty lines and '@' comments are line slots but not records (rare): inv_pre[k] = invalid slots before slot k
-        uint32_t inv_total = 0;
-        {
-            bool inv = false;
-            for (uint32_t k = tid; k < n_round; k += SHORT_THREADS) inv |= !valid_first(stage, rec_start[k]);
-            if (inv) inv_flag = 1;
-            __syncthreads();
-            if (inv_flag) {
-                if (warp == 0) {
-                    uint32_t base = 0;
-                    for (uint32_t k0 = 0; k0 < n_round; k0 += 32) {
-                        const uint32_t k = k0 + lane;
-                        const bool bad = k < n_round && !valid_first(stage, rec_start[k]);
-                        const unsigned bm = __ballot_sync(0xffffffffu, bad);
-                        if (k < n_round) inv_pre[k] = (uint16_t)(base + __popc(bm & ((1u << lane) - 1u)));
-                        base += __popc(bm);
-                    }
-                    if (lane == 0) inv_tot_s = base;
-                }
-                __syncthreads();
-                inv_total = inv_tot_s;
-            }
-        }
-
-        // ---- record-table entries of the round; lines ordered by length (a proxy for the walk length)
-        if (tid < 64) bin_cnt[tid] = 0;
-        if (tid == 64) {
+        if (tid == 0) {  // record-table entries of the round
+            if (first_slot && round == 0 && !valid_first(stage, 0)) inv_flag = 1;
             uint32_t sb = atomicAdd(a.cursors + 0, n_round);
-            if (single_pass) {
-                if (sb + n_round > a.slots_cap || n_rec > SHORT_REC_CAP) {
-                    atomicOr(a.cursors + 3, 1u);  // the host redoes the chunk with the count pass
-                    sb = 0xFFFFFFFFu;
-                } else {
-                    a.tile_info[blockIdx.x] = make_uint4(sb, n_round, n_round - inv_total, 0u);
-                    atomicAdd(a.cursors + 2, n_round - inv_total);
-                }
+            if (single_pass && (sb + n_round > a.slots_cap || n_rec > SHORT_REC_CAP)) {
+                atomicOr(a.cursors + 3, 1u);  // the table was sized from an estimate / rows are numbered per tile: the host redoes the chunk with the count pass
+                sb = 0xFFFFFFFFu;
             }
             slot_base_s = sb;
         }
         __syncthreads();
-        if (slot_base_s == 0xFFFFFFFFu) return;
+        if (slot_base_s == 0xFFFFFFFFu) return;  // uniform: read after the barrier
+
+        // ---- empty lines and '@' comments are line slots but not records (rare): inv_pre[k] = invalid slots before slot k
+        uint32_t inv_total = 0;
+        if (inv_flag) {
+            if (warp == 0) {
+                uint32_t base = 0;
+                for (uint32_t k0 = 0; k0 < n_round; k0 += 32) {
+                    const uint32_t k = k0 + lane;
+                    const bool bad = k < n_round && !valid_first(stage, rec_start[k]);
+                    const unsigned bm = __ballot_sync(0xffffffffu, bad);
+                    if (k < n_round) inv_pre[k] = (uint16_t)(base + __popc(bm & ((1u << lane) - 1u)));
+                    base += __popc(bm);
+                }
+                if (lane == 0) inv_tot_s = base;
+            }
+            __syncthreads();
+            inv_total = inv_tot_s;
+            __syncthreads();
+            if (tid == 0) inv_flag = 0;  // for the next round
+        }
+        if (tid == 0 && single_pass) {
+            a.tile_info[blockIdx.x] = make_uint4(slot_base_s, n_round, n_round - inv_total, 0u);
+            atomicAdd(a.cursors + 2, n_round - inv_total);
+        }
+
+        // ---- lines ordered by length (a proxy for the walk length): counting sort over 64 four-byte bins
         if (a.no_sort) {
             for (uint32_t k = tid; k < n_round; k += SHORT_THREADS) order[k] = (uint16_t)k;
         } else {
@@ -1097,24 +1101,24 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
                 rec_tmp[k] = (uint16_t)((bin << 10) | atomicAdd(&bin_cnt[bin], 1u));
             }
             __syncthreads();
-            if (warp == 0) {
-                const uint32_t c0 = bin_cnt[2 * lane], c1 = bin_cnt[2 * lane + 1];
-                uint32_t x = c0 + c1;
+            // every warp scans the 64 bin counts for itself (two bins per lane): no barrier around a dedicated scan step
+            const uint32_t c0 = bin_cnt[2 * lane], c1 = bin_cnt[2 * lane + 1];
+            uint32_t x = c0 + c1;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-                    if (lane >= (uint32_t)d) x += y;
-                }
-                bin_cnt[2 * lane] = x - c0 - c1;
-                bin_cnt[2 * lane + 1] = x - c1;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= (uint32_t)d) x += y;
             }
-            __syncthreads();
-            for (uint32_t k = tid; k < n_round; k += SHORT_THREADS) {
-                const uint32_t t = rec_tmp[k];
-                order[bin_cnt[t >> 10] + (t & 1023u)] = (uint16_t)k;
+            const uint32_t base_even = x - c0 - c1, base_odd = x - c1;  // first position of bins 2*lane and 2*lane + 1
+            for (uint32_t k0 = 0; k0 < n_round; k0 += SHORT_THREADS) {  // uniform trip count: the shuffles need every lane
+                const uint32_t k = k0 + tid;
+                const uint32_t t = k < n_round ? rec_tmp[k] : 0u, bin = t >> 10;
+                const uint32_t be = __shfl_sync(0xffffffffu, base_even, bin >> 1), bo = __shfl_sync(0xffffffffu, base_odd, bin >> 1);
+                if (k < n_round) order[((bin & 1u) ? bo : be) + (t & 1023u)] = (uint16_t)k;
             }
         }
         __syncthreads();
+        if (tid < 64u) bin_cnt[tid] = 0;  // for the next round (read again only behind further barriers)
 
         // ---- C: one thread per record
         for (uint32_t k0 = 0; k0 < n_round; k0 += SHORT_THREADS) {
@@ -1139,8 +1143,8 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
                 FastRec f;
                 uint32_t e;  // the '\n' that ends the line: in front of the next line start, or (last line of the round) from the bitmap
                 if (k + 1u < n_round) e = (uint32_t)rec_start[k + 1u] - 1u;
-                else { BitCursor nc; nc.seek(nlw, p); e = nc.next(); }
-                fast = fast_parse(Wd, tabw, p, e, stage_bytes, f, pmask, stash + tid, SHORT_THREADS, STASH_CAP);
+                else { BitCursor nc; nc.seek(Wnl, p); e = nc.next(); }
+                fast = fast_parse(Wd, Wtab, p, e, stage_bytes, f, pmask, stash + tid, SHORT_THREADS, STASH_CAP);
                 if (fast) {
                     h = f.h;
                     W = f.W;
@@ -1151,7 +1155,7 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
                     lm = !(f.nulls & FN_MAPQ) && f.mapq - 3u <= 57u;
                     uq = lm && f.mapq == 60u;
                     cols_ok = !f.path_null && !(f.nulls & (FN_C7 | FN_C8 | FN_C9));
-                    monotone = f.monotone;
+                    monotone = false;  // not tracked on the fast path: k_apply notices repeats while it walks (cover_record)
                     stashed = true;
                     path_pos = f.path_pos;
                     path_end = f.path_end;
@@ -2056,7 +2060,7 @@ size_t ingest_smem_bytes(uint32_t tile_bytes, uint32_t over_bytes, bool short_ke
     const size_t hist_bytes = multi_species ? HIST_SLOTS * 5 * sizeof(uint32_t) : 0;
     if (short_kernel) {
         const size_t stage_bytes = (size_t)tile_bytes + over_bytes;
-        return stage_bytes + STAGE_PAD + 2 * (stage_bytes / 32 + 2) * sizeof(uint32_t) + STASH_CAP * SHORT_THREADS * sizeof(uint32_t) +
+        return stage_bytes + STAGE_PAD + 2 * ((stage_bytes / 32 + 2 + 3) / 4 * 4) * sizeof(uint32_t) + STASH_CAP * SHORT_THREADS * sizeof(uint32_t) +
                3 * SHORT_REC_CAP * sizeof(uint16_t) + hist_bytes;
     }
     return (size_t)tile_bytes + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 4 * REC_CAP * sizeof(uint16_t) + hist_bytes;

@@ -49,6 +49,8 @@ extern "C" {
     pub fn ptx_filter_gaf(ctx: *mut ptx_ctx, bytes: *const u8, n: size_t, out_line_off: *mut u64, cap: i64, n_out: *mut i64) -> c_int;
     pub fn ptx_comm_unique_id(out128: *mut c_void) -> c_int;
     pub fn ptx_comm_init(ctx: *mut ptx_ctx, n_ranks: c_int, rank: c_int, id128: *const c_void) -> c_int;
+    pub fn ptx_create_multi(devices: *const c_int, n_devices: c_int, expected_records_per_device: i64, out: *mut *mut ptx_ctx) -> c_int;
+    pub fn ptx_finalize_multi(ctxs: *const *mut ptx_ctx, n: c_int) -> c_int;
     pub fn ptx_stats_json(ctx: *mut ptx_ctx, buf: *mut c_char, cap: size_t) -> c_int;
     pub fn ptx_timing(ctx: *mut ptx_ctx, ingest_ms: *mut c_double, finalize_ms: *mut c_double, kernel_launches: *mut i64) -> c_int;
 }
@@ -59,12 +61,31 @@ pub struct Gpu { raw: *mut ptx_ctx }
 #[derive(Debug)]
 pub struct GpuError { pub code: i32, pub msg: String }
 
+/// ptx_finalize of every context of a `Gpu::new_multi` group (the collectives inside need all of them at once).
+pub fn finalize_multi(gpus: &[Gpu]) -> Result<(), GpuError> {
+    let raw: Vec<*mut ptx_ctx> = gpus.iter().map(|g| g.raw).collect();
+    let rc = unsafe { ptx_finalize_multi(raw.as_ptr(), raw.len() as c_int) };
+    if rc == 0 { Ok(()) } else { Err(GpuError { code: rc, msg: gpus.iter().map(|g| g.last_error()).collect::<Vec<_>>().join("; ") }) }
+}
+
 impl Gpu {
+    /// One context per device, all in this process (the `pantax` CLI is one process), joined into one communicator
+    /// group: the 8-GPU form of `Gpu::new(0)`.  `strain_profiling` (profile.rs:3291) feeds context k the k-th read
+    /// batch of the GAF, calls `finalize_multi`, and reads the (identical, reduced) results from any of them.
+    pub fn new_multi(devices: &[i32], expected_records_per_device: usize) -> Result<Vec<Gpu>, GpuError> {
+        let mut raw: Vec<*mut ptx_ctx> = vec![std::ptr::null_mut(); devices.len()];
+        let rc = unsafe { ptx_create_multi(devices.as_ptr(), devices.len() as c_int, expected_records_per_device as i64, raw.as_mut_ptr()) };
+        if rc != 0 { return Err(GpuError { code: rc, msg: "ptx_create_multi".into() }); }
+        Ok(raw.into_iter().map(|r| Gpu { raw: r }).collect())
+    }
     pub fn new(device: i32) -> Result<Gpu, GpuError> {
         let mut raw = std::ptr::null_mut();
         let rc = unsafe { ptx_create(device, &mut raw) };
         if rc != PTX_OK { return Err(GpuError { code: rc, msg: "ptx_create: no CUDA device (no CPU fallback)".into() }); }
         Ok(Gpu { raw })
+    }
+    pub fn last_error(&self) -> String {
+        unsafe { std::ffi::CStr::from_ptr(ptx_last_error(self.raw)) }.to_string_lossy().into_owned()
     }
     fn ck(&self, rc: c_int) -> Result<(), GpuError> {
         if rc == PTX_OK { return Ok(()); }

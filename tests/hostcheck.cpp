@@ -127,15 +127,15 @@ int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, 
             {   // fast path: whatever it accepts must be what parse_record read
                 FastRec f;
                 uint32_t fst[16];
+                const Words fw{0u, f_words.data()}, ft{0u, f_tab.data()}, fn{0u, f_nl.data()};
                 BitCursor nc;
-                nc.seek(f_nl.data(), (uint32_t)i);
-                if (fast_parse(f_words.data(), f_tab.data(), (uint32_t)i, nc.next(), f_lim, f, 1u, fst, 1, 16)) {
+                nc.seek(fn, (uint32_t)i);
+                if (fast_parse(fw, ft, (uint32_t)i, nc.next(), f_lim, f, 1u, fst, 1, 16)) {
                     ++*n_fast;
                     auto same_int = [&](int64_t exact, uint32_t v, uint32_t bit) { return (f.nulls & bit) ? exact == NULL_I64 : exact == (int64_t)v; };
                     bool same = f.h.lo == p.r.h.lo && f.h.hi == p.r.h.hi && same_int(p.r.qlen, f.qlen, FN_QLEN) && same_int(p.r.c7, f.c7, FN_C7) &&
                                 same_int(p.r.c8, f.c8, FN_C8) && same_int(p.r.c9, f.c9, FN_C9) && same_int(p.r.mapq, f.mapq, FN_MAPQ) &&
-                                f.W == p.r.W && f.path_pos == p.r.path_pos && f.path_end == p.r.path_end && f.path_null == p.r.path_null &&
-                                f.monotone == p.r.monotone;
+                                f.W == p.r.W && f.path_pos == p.r.path_pos && f.path_end == p.r.path_end && f.path_null == p.r.path_null;
                     if (same && f.W) same = (int64_t)f.vmin == p.r.vmin && (int64_t)f.vmax == p.r.vmax;
                     if (same) {
                         WalkIter it{buf.data(), p.r.path_pos, p.r.path_end};
@@ -178,7 +178,9 @@ int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, 
     for (const Parsed& p : recs) {
         if (!p.eligible || node_base[p.label] < 0) continue;
         if (mixed && ds[HashKey{p.r.h.lo, p.r.h.hi}] == DS_MIXED) continue;
-        cover_record(buf.data(), p.r, p.label, rstart[p.label], node_base[p.label], sink, 1u, p.stash, 1);
+        RecParse rr = p.r;
+        if (!use_stash) rr.monotone = false;  // k_ingest_s does not track it: cover_record must notice repeats on its own
+        cover_record(buf.data(), rr, p.label, rstart[p.label], node_base[p.label], sink, 1u, p.stash, 1);
     }
     for (int64_t g = 0; g < N; ++g) {
         uint64_t c = 0;
