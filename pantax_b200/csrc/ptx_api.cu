@@ -138,6 +138,10 @@ struct ptx_ctx {
     uint64_t ds_cap = 0;
     int64_t ds_records = 0;  // upper bound of ids inserted
     int64_t reserve_records = 0;
+    // node-coverage scatter variant (IngestArgs::scatter_var; profiles/r2_scatter_bakeoff.md): -1 = choose (pick_scatter_variant)
+    int scatter_var = -1;
+    uint32_t* d_pair_key = nullptr; unsigned long long* d_pair_val = nullptr; uint8_t* d_pair_tmp = nullptr;  // variant 3
+    int64_t pair_cap = 0; size_t pair_tmp_cap = 0;
     int force_rows = 0;  // PTX_TILE_ROWS env override (tests exercise every tile size)
     int force_tile = 0;  // PTX_TILE_BYTES env override for single-pass chunks of k_ingest_s (multiple of 512)
     bool no_sort = false;    // PTX_NO_SORT=1: k_ingest_s keeps file order inside a tile (measurements)
@@ -295,6 +299,16 @@ int ds_ensure_total(ptx_ctx* ctx, int64_t entries) {
 }
 int ds_ensure(ptx_ctx* ctx, int64_t more_records) { return ds_ensure_total(ctx, std::max(ctx->ds_records, ctx->ds_entries_bound) + more_records); }
 
+// Which scatter variant k_apply<COVER> uses.  Measured on configs[1], configs[2], a 50 M-node graph and a 4,000-node "hot" graph
+// (profiles/r2_scatter_bakeoff.md): the plain per-lane RED.ADD.64 wins on all four.  The 32 reads of a warp almost never share a
+// node in the same step of their walks (match.any merges nothing: identical RED sector counts), a 2048-slot CTA table removes no
+// global RED on a graph of a million nodes and its shared-memory atomics cost more than the REDs it saves on a graph of 4,000,
+// and sort + segmented reduce moves 40x the DRAM bytes.  So: variant 0, unless PTX_SCATTER asks for another one (measurements).
+int pick_scatter_variant(const ptx_ctx* ctx) {
+    if (ctx->scatter_var >= 0 && ctx->scatter_var <= 3) return ctx->scatter_var;
+    return 0;
+}
+
 IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     IngestArgs a;
     memset(&a, 0, sizeof a);
@@ -326,6 +340,9 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.ds = ctx->d_ds;
     a.ds_shift = 64 - log2_ceil(ctx->ds_cap);
     a.ds_mask = ctx->ds_cap - 1;
+    a.scatter_var = (uint32_t)pick_scatter_variant(ctx);
+    a.pair_key = ctx->d_pair_key;
+    a.pair_val = ctx->d_pair_val;
     a.flags = ctx->d_flags;
     a.err = ctx->d_err;
     const GraphDev& g = ctx->g;
@@ -368,7 +385,9 @@ int chunk_alloc(ptx_ctx* ctx, Chunk& ch, size_t cap) {
     ch.cap = cap;
     const size_t total = PRE + padded_text_bytes(cap);
     CU(cudaMalloc((void**)&ch.buf, total));
-    CU(cudaMemsetAsync(ch.buf, '\n', PRE, ctx->st));
+    // the newline padding in front of the text is written once, on the COPY stream: the text copies are queued behind it
+    // there, and the kernels wait for `copied` - no host synchronisation between a call's copies and the previous call's kernels
+    CU(cudaMemsetAsync(ch.buf, '\n', PRE, ctx->copy_st));
     CU(cudaEventCreateWithFlags(&ch.copied, cudaEventDisableTiming));
     return PTX_OK;
 }
@@ -521,7 +540,7 @@ int chunk_process_exact(ptx_ctx* ctx, Chunk& ch) {
     ch.labels_ready = true;
     IngestArgs a = make_args(ctx, ch);
     // multi-GPU: the coverage pass is deferred to ptx_finalize, where it overlaps the id-group exchange
-    const bool cover = ctx->graphs_committed && ctx->g.N > 0 && !ctx->comm;
+    const bool cover = ctx->graphs_committed && ctx->g.N > 0 && !ctx->comm && a.scatter_var != 3;  // variant 3 sorts per chunk in ptx_finalize
     ev_begin(ctx, ctx->ev_ingest);
     launch_ingest(a, ctx->st);
     ev_end(ctx, ctx->ev_ingest);
@@ -575,7 +594,7 @@ int chunk_process_single(ptx_ctx* ctx, Chunk& ch) {
     ch.labels_ready = false;
     ch.n_slots = ch.slots_cap;  // until resolved
     IngestArgs a = make_args(ctx, ch);
-    const bool cover = ctx->graphs_committed && ctx->g.N > 0 && !ctx->comm;
+    const bool cover = ctx->graphs_committed && ctx->g.N > 0 && !ctx->comm && a.scatter_var != 3;
     ev_begin(ctx, ctx->ev_ingest);
     launch_ingest(a, ctx->st);
     ev_end(ctx, ctx->ev_ingest);
@@ -600,7 +619,7 @@ int chunks_resolve(ptx_ctx* ctx, bool blocking = true) {
         Chunk& ch = ctx->chunks[ci];
         if (!ch.pending) continue;
         if (blocking) CU(cudaEventSynchronize(ch.done));
-        else if (cudaEventQuery(ch.done) != cudaSuccess) { cudaGetLastError(); continue; }
+        else if (cudaEventQuery(ch.done) != cudaSuccess) { cudaGetLastError(); break; }  // chunks resolve in stream (= GAF) order: rows are numbered from it
         ch.pending = false;
         ctx->pending_records -= ch.est_records;
         if (ch.h_cur[3]) {  // estimate too small (or a tile with more than REC_CAP lines): nothing was counted
@@ -963,6 +982,7 @@ int ptx_create(int device, ptx_ctx** out) {
     if (const char* e = getenv("PTX_TILE_BYTES")) ctx->force_tile = atoi(e);
     if (const char* e = getenv("PTX_OLD_INGEST")) ctx->old_short = atoi(e) != 0;
     if (const char* e = getenv("PTX_NO_SORT")) ctx->no_sort = atoi(e) != 0;
+    if (const char* e = getenv("PTX_SCATTER")) ctx->scatter_var = atoi(e);
     if (const char* e = getenv("PTX_LONG_MODE")) ctx->force_long = atoi(e) ? 1 : 0;
     if (const char* e = getenv("PTX_TEST_BOX_CAP")) ctx->test_box_cap = atoll(e);
     if (const char* e = getenv("PTX_NO_SINGLE_PASS")) ctx->single_pass_ok = atoi(e) == 0;
@@ -997,7 +1017,7 @@ void ptx_destroy(ptx_ctx* ctx) {
     if (ctx->ev_x1) cudaEventDestroy(ctx->ev_x1);
     free_graph(ctx);
     dfree(ctx->d_rstart); dfree(ctx->d_rend); dfree(ctx->d_node_base); dfree(ctx->d_order); dfree(ctx->d_sstart);
-    dfree(ctx->d_hist); dfree(ctx->d_hist_g); dfree(ctx->d_flags); dfree(ctx->d_err); dfree(ctx->d_ds); dfree(ctx->d_total); dfree(ctx->d_labels_in);
+    dfree(ctx->d_hist); dfree(ctx->d_hist_g); dfree(ctx->d_flags); dfree(ctx->d_err); dfree(ctx->d_ds); dfree(ctx->d_pair_key); dfree(ctx->d_pair_val); dfree(ctx->d_pair_tmp); dfree(ctx->d_total); dfree(ctx->d_labels_in);
     ev_clear(ctx->ev_count);
     ev_clear(ctx->ev_ingest);
     ev_clear(ctx->ev_apply);
@@ -1292,7 +1312,6 @@ int ptx_ingest_gaf(ptx_ctx* ctx, const uint8_t* bytes, size_t n, int is_last) {
         const size_t c0 = first ? ctx->carry.size() : 0;
         int rc = chunk_alloc(ctx, ch, c0 + take);
         if (rc) return rc;
-        CU(cudaStreamSynchronize(ctx->st));  // PRE memset done before the copy stream touches the buffer
         if (c0) CU(cudaMemcpyAsync(ch.buf + PRE, ctx->carry.data(), c0, cudaMemcpyHostToDevice, ctx->copy_st));
         if (take) CU(cudaMemcpyAsync(ch.buf + PRE + c0, bytes + off, take, cudaMemcpyHostToDevice, ctx->copy_st));
         ch.n = c0 + take;
@@ -1348,7 +1367,7 @@ int ptx_gaf_buffer_alloc(ptx_ctx* ctx, size_t capacity, int* buffer_id, void** d
     Chunk ch;
     int rc = chunk_alloc(ctx, ch, capacity);
     if (rc) return rc;
-    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaStreamSynchronize(ctx->copy_st));  // the newline padding in front of the text is in place before the caller fills the buffer
     ctx->chunks.push_back(ch);
     *buffer_id = (int)ctx->chunks.size() - 1;
     *device_ptr = ch.buf + PRE;
@@ -1395,13 +1414,30 @@ int ptx_finalize(ptx_ctx* ctx) {
         tr.mark("final flags");
     }
     if (ctx->graphs_committed && g.N > 0) {
-        auto cover_pending = [&](bool keepmask) {
+        auto cover_pending = [&](bool keepmask) -> int {
             for (auto& ch : ctx->chunks) {
                 if (!ch.ingested || ch.covered || ch.n_tiles == 0) continue;
+                uint32_t n_nodes = 0;
+                if (pick_scatter_variant(ctx) == 3) {  // (node, bases) pairs beside the CSR walks, sorted and reduced per chunk
+                    CU(cudaMemcpyAsync(&n_nodes, reinterpret_cast<uint32_t*>(ch.cursors) + 1, sizeof n_nodes, cudaMemcpyDeviceToHost, ctx->st));
+                    CU(cudaStreamSynchronize(ctx->st));
+                    const size_t tb = scatter_sorted_tmp_bytes(n_nodes);
+                    if (ctx->pair_cap < (int64_t)n_nodes || ctx->pair_tmp_cap < tb) {
+                        dfree(ctx->d_pair_key); dfree(ctx->d_pair_val); dfree(ctx->d_pair_tmp);
+                        ctx->pair_cap = (int64_t)n_nodes + n_nodes / 8 + 1024;
+                        ctx->pair_tmp_cap = scatter_sorted_tmp_bytes((uint64_t)ctx->pair_cap);
+                        CU(cudaMalloc((void**)&ctx->d_pair_key, (size_t)ctx->pair_cap * sizeof(uint32_t)));
+                        CU(cudaMalloc((void**)&ctx->d_pair_val, (size_t)ctx->pair_cap * sizeof(unsigned long long)));
+                        CU(cudaMalloc((void**)&ctx->d_pair_tmp, ctx->pair_tmp_cap));
+                    }
+                    CU(cudaMemsetAsync(ctx->d_pair_key, 0xFF, (size_t)n_nodes * sizeof(uint32_t), ctx->st));  // slots of records that are not covered
+                }
                 IngestArgs a = make_args(ctx, ch);
                 launch_apply(a, (uint32_t)ch.n_slots, MODE_COVER | (keepmask ? MODE_KEEPMASK : 0), ctx->st);  // from the record table: no text is re-read
+                if (a.scatter_var == 3) launch_scatter_sorted(ctx->d_pair_key, ctx->d_pair_val, n_nodes, ctx->g.bases, ctx->d_pair_tmp, ctx->pair_tmp_cap, ctx->st);
                 ch.covered = true;
             }
+            return PTX_OK;
         };
         auto start_over = [&]() -> int {
             // profile.rs:406-437: some id group spans species -> its reads must not contribute.  The optimistic
@@ -1442,7 +1478,7 @@ int ptx_finalize(ptx_ctx* ctx) {
         };
         if (ctx->comm && ctx->cov_reduced) return fail(ctx, PTX_E_STATE, "multi-GPU: coverage already reduced");
         if (mixed) { int rc = start_over(); if (rc) return rc; }
-        cover_pending(mixed);
+        { int rc = cover_pending(mixed); if (rc) return rc; }
         bool reduced = false;
         if (ctx->comm && ctx->comm_x != ctx->comm) {
             // the exchange runs on its own communicator and stream: reduce optimistically (no mixed id group is
@@ -1463,7 +1499,7 @@ int ptx_finalize(ptx_ctx* ctx) {
             if (mixed) {
                 int rc = start_over();
                 if (rc) return rc;
-                cover_pending(true);
+                if ((rc = cover_pending(true))) return rc;
                 reduced = false;
             }
         }
@@ -1867,6 +1903,7 @@ int ptx_comm_unique_id(void* out128) {
 int ptx_comm_init(ptx_ctx* ctx, int n_ranks, int rank, const void* id128) {
     if (!ctx || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(ctx, PTX_E_INVALID, "ptx_comm_init: bad arguments");
     if (!g_nccl.load()) return fail(ctx, PTX_E_NCCL, "libnccl.so.2 not found");
+    if (ctx->total_records + ctx->pending_records > 0) return fail(ctx, PTX_E_STATE, "ptx_comm_init must precede the first ptx_ingest_gaf");
     cudaSetDevice(ctx->device);
     ncclUniqueId id;
     memcpy(&id, id128, sizeof id);

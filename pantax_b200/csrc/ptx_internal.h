@@ -109,6 +109,13 @@ struct IngestArgs {
     ulonglong2* ds;             // read-id set slots
     uint32_t ds_shift;          // 64 - log2(capacity)
     uint64_t ds_mask;
+    // node-coverage scatter variant of k_apply<COVER> (north_star stage 2; profiles/r2_scatter_bakeoff.md):
+    //   0 one RED.ADD.64 per lane and node   1 lanes of a warp that hit the same node add once (match.any)
+    //   2 per-CTA shared-memory table absorbing repeated nodes, flushed once per CTA
+    //   3 (node, bases) pairs written beside the CSR walk, then radix sort by node + segmented reduce (launch_scatter_sorted)
+    uint32_t scatter_var;
+    uint32_t* pair_key;             // variant 3: [node slots] node index per CSR slot (0xFFFFFFFF: nothing to add)
+    unsigned long long* pair_val;   // variant 3: [node slots]
     uint32_t* flags;            // [0] dup id seen, [1] mixed-species id group seen, [2] exchange box overflow, [3] supplied label outside its range
     uint32_t* err;              // [S] bit0: profile.rs:854 tripped
     // coverage
@@ -174,6 +181,12 @@ void launch_flt_pipeline(const uint8_t* text, uint64_t n, const uint64_t* line_o
                          uint32_t* flags, cudaStream_t st);
 void launch_flt_compact(const uint32_t* sel, const uint64_t* scan, const uint64_t* line_off, uint64_t n_lines, uint64_t* out, uint64_t cap,
                         cudaStream_t st);
+
+// scatter variant 3: sort the n (node, bases) pairs of a chunk by node and add every run's sum to bases[] (CUB radix sort +
+// reduce-by-key, then one kernel).  `tmp` holds tmp_bytes of scratch (scatter_sorted_tmp_bytes(n)).
+size_t scatter_sorted_tmp_bytes(uint64_t n);
+void launch_scatter_sorted(const uint32_t* key, const unsigned long long* val, uint64_t n, unsigned long long* bases, void* tmp, size_t tmp_bytes,
+                           cudaStream_t st);
 
 int64_t kernel_launch_count();
 

@@ -16,6 +16,9 @@
 // algorithmic bytes each kernel is measured against.
 #include <atomic>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
+
 #include "ptx_internal.h"
 #include "ptx_fast.cuh"
 
@@ -347,6 +350,48 @@ struct DevSink {
     }
     __device__ __forceinline__ void error_start_gt_len(uint32_t label) { atomicOr(a.err + label, 1u); }
 };
+
+// ---- the other scatter variants of north_star stage 2: same sink, add_bases replaced (profiles/r2_scatter_bakeoff.md)
+// 1: the lanes of the warp that add to the same node in this step add once (match.any + shuffles among the group)
+struct WarpAggSink : DevSink {
+    __device__ __forceinline__ void add_bases(uint32_t g, int64_t v) {
+        const unsigned act = __activemask();
+        const unsigned peers = __match_any_sync(act, g);
+        const uint32_t lane = threadIdx.x & 31u;
+        if ((peers & (peers - 1u)) == 0u) { atomicAdd(a.bases + g, (unsigned long long)v); return; }
+        const int leader = __ffs(peers) - 1;
+        long long sum = 0;
+        for (unsigned m = peers; m; m &= m - 1u) sum += __shfl_sync(peers, (long long)v, __ffs(m) - 1);  // same trip count for the whole group
+        if ((int)lane == leader) atomicAdd(a.bases + g, (unsigned long long)sum);
+    }
+};
+// 2: a per-CTA shared-memory table keyed by node absorbs the nodes a CTA meets more than once ("hot" node ranges: abundant
+// species, short graphs); a slot taken by another node falls back to the global RED.  Flushed once per CTA.
+constexpr uint32_t SC_SLOTS_LOG2 = 11, SC_SLOTS = 1u << SC_SLOTS_LOG2;
+struct SmemSink : DevSink {
+    uint32_t* tag;
+    unsigned long long* sum;
+    __device__ __forceinline__ void add_bases(uint32_t g, int64_t v) {
+        const uint32_t s = (g * 0x9E3779B1u) >> (32u - SC_SLOTS_LOG2);
+        const uint32_t old = atomicCAS(tag + s, 0xFFFFFFFFu, g);
+        if (old == 0xFFFFFFFFu || old == g) atomicAdd(sum + s, (unsigned long long)v);
+        else atomicAdd(a.bases + g, (unsigned long long)v);
+    }
+};
+// 3: nothing is added here - the (node, bases) pair goes to the record's CSR slots; launch_scatter_sorted sorts and reduces them
+struct PairSink : DevSink {
+    uint32_t pos;
+    __device__ __forceinline__ void add_bases(uint32_t g, int64_t v) {
+        a.pair_key[pos] = g;
+        a.pair_val[pos] = (unsigned long long)v;
+        ++pos;
+    }
+};
+__global__ void __launch_bounds__(256) k_add_runs(const uint32_t* __restrict__ key, const unsigned long long* __restrict__ sum,
+                                                  const unsigned long long* __restrict__ n_runs, unsigned long long* bases) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < *n_runs && key[i] != 0xFFFFFFFFu) bases[key[i]] += sum[i];  // keys are unique: no atomics
+}
 
 // ---- warp-cooperative decode of the walk column (long reads: a tile holds few lines, each with a walk of tens
 // to hundreds of nodes).  The 32 lanes take 4 bytes each of a 128-byte window of the column; byte classes come
@@ -1352,11 +1397,17 @@ __device__ __forceinline__ void block_append(uint32_t dest, const ulonglong2& en
     }
 }
 
-template <int MODE>
+template <int MODE, int VAR = 0>
 __global__ void __launch_bounds__(256, 8) k_apply(const IngestArgs a, uint32_t n_entries) {  // 32 registers, 64 warps/SM: the random id-set and node accesses want every warp they can get (0.947 -> 0.906 ms)
     if (n_entries == ENTRIES_FROM_DEVICE) {  // single-pass ingest: the host does not know the entry count yet
         if (a.cursors[3]) return;            // the estimate was too small: nothing of this chunk counts, it is redone
         n_entries = a.cursors[0];
+    }
+    __shared__ uint32_t sc_tag[VAR == 2 ? SC_SLOTS : 1];
+    __shared__ unsigned long long sc_sum[VAR == 2 ? SC_SLOTS : 1];
+    if constexpr (VAR == 2) {
+        for (uint32_t i = threadIdx.x; i < SC_SLOTS; i += blockDim.x) { sc_tag[i] = 0xFFFFFFFFu; sc_sum[i] = 0ull; }
+        __syncthreads();
     }
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     const bool has = e < n_entries;
@@ -1418,9 +1469,28 @@ __global__ void __launch_bounds__(256, 8) k_apply(const IngestArgs a, uint32_t n
             r.monotone = (mb.y & RM_MONOTONE) != 0;
             r.stashed = true;
             r.path_pos = r.path_end = 0;
-            DevSink sink{a};
-            cover_record(nullptr, r, label, R.start[label], nb, sink, cmask, a.nodes + mb.x, 1u);
+            if constexpr (VAR == 1) {
+                WarpAggSink sink{{a}};
+                cover_record(nullptr, r, label, R.start[label], nb, sink, cmask, a.nodes + mb.x, 1u);
+            } else if constexpr (VAR == 2) {
+                SmemSink sink{{a}, sc_tag, sc_sum};
+                cover_record(nullptr, r, label, R.start[label], nb, sink, cmask, a.nodes + mb.x, 1u);
+            } else if constexpr (VAR == 3) {
+                PairSink sink{{a}, mb.x};
+                cover_record(nullptr, r, label, R.start[label], nb, sink, cmask, a.nodes + mb.x, 1u);
+                for (uint32_t q = sink.pos; q < mb.x + r.W; ++q) a.pair_key[q] = 0xFFFFFFFFu;  // later visits of a node, skipped reads
+            } else {
+                DevSink sink{a};
+                cover_record(nullptr, r, label, R.start[label], nb, sink, cmask, a.nodes + mb.x, 1u);
+            }
+        } else if (VAR == 3 && eligible) {
+            for (uint32_t q = mb.x; q < mb.x + (mb.y & RM_W_MASK); ++q) a.pair_key[q] = 0xFFFFFFFFu;  // a read dropped by the keep mask / without a graph
         }
+    }
+    if constexpr (VAR == 2) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < SC_SLOTS; i += blockDim.x)
+            if (sc_tag[i] != 0xFFFFFFFFu) atomicAdd(a.bases + sc_tag[i], sc_sum[i]);
     }
 }
 
@@ -2101,15 +2171,49 @@ void launch_apply(const IngestArgs& a, uint32_t n_entries, int mode, cudaStream_
     if (n_entries == 0) return;
     const uint32_t grid = ((n_entries == ENTRIES_FROM_DEVICE ? a.slots_cap : n_entries) + 255u) / 256u;
     if (grid == 0) return;
+#define PTX_APPLY_VARIANTS(M)                                                                   \
+    switch (a.scatter_var) {                                                                   \
+        case 1: k_apply<M, 1><<<grid, 256, 0, st>>>(a, n_entries); break;                       \
+        case 2: k_apply<M, 2><<<grid, 256, 0, st>>>(a, n_entries); break;                       \
+        case 3: k_apply<M, 3><<<grid, 256, 0, st>>>(a, n_entries); break;                       \
+        default: k_apply<M, 0><<<grid, 256, 0, st>>>(a, n_entries); break;                      \
+    }
     switch (mode) {
         case MODE_CLASSIFY: k_apply<MODE_CLASSIFY><<<grid, 256, 0, st>>>(a, n_entries); break;
-        case MODE_CLASSIFY | MODE_COVER: k_apply<MODE_CLASSIFY | MODE_COVER><<<grid, 256, 0, st>>>(a, n_entries); break;
-        case MODE_COVER: k_apply<MODE_COVER><<<grid, 256, 0, st>>>(a, n_entries); break;
-        case MODE_COVER | MODE_KEEPMASK: k_apply<MODE_COVER | MODE_KEEPMASK><<<grid, 256, 0, st>>>(a, n_entries); break;
+        case MODE_CLASSIFY | MODE_COVER: PTX_APPLY_VARIANTS(MODE_CLASSIFY | MODE_COVER) break;
+        case MODE_COVER: PTX_APPLY_VARIANTS(MODE_COVER) break;
+        case MODE_COVER | MODE_KEEPMASK: PTX_APPLY_VARIANTS(MODE_COVER | MODE_KEEPMASK) break;
         case MODE_REBOX: k_apply<MODE_REBOX><<<grid, 256, 0, st>>>(a, n_entries); break;
         default: return;
     }
     PTX_LAUNCHED();
+}
+// scratch layout of launch_scatter_sorted: sorted keys | sorted values | run keys | run sums | run count | CUB temp storage
+static size_t cub_tmp_bytes(uint64_t n) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const unsigned long long*)nullptr,
+                                    (unsigned long long*)nullptr, (int64_t)n);
+    cub::DeviceReduce::ReduceByKey(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const unsigned long long*)nullptr,
+                                   (unsigned long long*)nullptr, (unsigned long long*)nullptr, cub::Sum(), (int64_t)n);
+    return std::max(a, b);
+}
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+size_t scatter_sorted_tmp_bytes(uint64_t n) { return 2 * al256(n * 4) + 2 * al256(n * 8) + 256 + al256(cub_tmp_bytes(n)) + 1024; }
+void launch_scatter_sorted(const uint32_t* key, const unsigned long long* val, uint64_t n, unsigned long long* bases, void* tmp, size_t tmp_bytes,
+                           cudaStream_t st) {
+    if (n == 0) return;
+    uint8_t* p = reinterpret_cast<uint8_t*>(tmp);
+    uint32_t* skey = reinterpret_cast<uint32_t*>(p); p += al256(n * 4);
+    unsigned long long* sval = reinterpret_cast<unsigned long long*>(p); p += al256(n * 8);
+    uint32_t* rkey = reinterpret_cast<uint32_t*>(p); p += al256(n * 4);
+    unsigned long long* rsum = reinterpret_cast<unsigned long long*>(p); p += al256(n * 8);
+    unsigned long long* nrun = reinterpret_cast<unsigned long long*>(p); p += 256;
+    size_t cb = tmp_bytes - (size_t)(p - reinterpret_cast<uint8_t*>(tmp));
+    cub::DeviceRadixSort::SortPairs(p, cb, key, skey, val, sval, (int64_t)n, 0, 32, st);
+    cb = tmp_bytes - (size_t)(p - reinterpret_cast<uint8_t*>(tmp));
+    cub::DeviceReduce::ReduceByKey(p, cb, skey, rkey, sval, rsum, nrun, cub::Sum(), (int64_t)n, st);
+    k_add_runs<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(rkey, rsum, nrun, bases);
+    for (int i = 0; i < 3; ++i) PTX_LAUNCHED();
 }
 void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2* new_slots, uint32_t new_shift, uint64_t new_mask,
                       cudaStream_t st) {

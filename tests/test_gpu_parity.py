@@ -532,3 +532,17 @@ def test_gpu_config4_shape_short_reads_on_1000_species():
         if s % 3:
             graphs[s] = None
     gpu_vs_oracle(ds.ranges(), graphs, gaf)
+
+
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("flow", ["fused", "late"])
+def test_gpu_every_scatter_variant_gives_the_same_coverage(variant, flow, monkeypatch):
+    """north_star stage 2: per-lane RED / warp-aggregated (match.any) / per-CTA shared-memory table / sort + segmented
+    reduce must all produce the oracle's integers - on a small graph (reads of one warp and one CTA do share nodes), with
+    duplicated ids across species (the keep-mask replay) and with the graphs committed before or after the ingest."""
+    from gpu_common import gpu_vs_oracle
+    monkeypatch.setenv("PTX_SCATTER", variant)
+    ds = synth.Dataset(77, [900, 300, 5000], [5, 2, 3])
+    gaf = ds.gaf(8, 0, 60000, NASTY_DUP)
+    ctx, o = gpu_vs_oracle(ds.ranges(), dataset_graphs(ds), gaf, flow=flow, split=[len(gaf) // 3, len(gaf) // 2])
+    assert not ctx.ids_unique
