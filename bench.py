@@ -547,6 +547,9 @@ def run_ours(args):
     R = args.records
     cudart = C.CDLL("libcudart.so")
 
+    # one process per GPU: stay on the cores (and the memory) of the GPU's own NUMA node before anything is allocated
+    numa_cpus = api.bind_host_thread_to_gpu(D.local_rank) if world > 1 else None
+
     # ---- synthetic inputs: graph replicated, rank r owns records [r*R, (r+1)*R)
     buf, nbytes = wl.gaf_raw(rank * R, (rank + 1) * R)
     pinned = api.PinnedBuffer(nbytes)
@@ -673,7 +676,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args, world), "records_per_gpu": int(n_rec), "gaf_bytes_per_gpu": int(nbytes),
                        "l2": f"input text {nbytes / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
-                       "graph_setup_s": t_graph_main, "unique_trios": n_trios_main, "timing": "wall clock over K steps between "
+                       "graph_setup_s": t_graph_main, "unique_trios": n_trios_main,
+                       "host_cores_rank0": (f"{len(numa_cpus)} cores of the GPU's NUMA node" if numa_cpus else "not restricted"), "timing": "wall clock over K steps between "
                        "barrier+synchronize, max over ranks; kernel times from CUDA events on the library stream"},
             "clocks": t["clocks"], "e2e": e2e, "gpu_launches": t["launches"], "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "secondary": secondary,

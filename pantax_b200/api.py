@@ -28,6 +28,33 @@ def _p(a: np.ndarray, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
+def bind_host_thread_to_gpu(device: int) -> Optional[List[int]]:
+    """Restrict the calling process to the CPU cores next to `device` (NVML cpu affinity), so that the pinned GAF buffer
+    allocated afterwards lives on the GPU's own NUMA node: with one process per GPU on a two-socket box, H2D copies from
+    the far socket share the inter-socket link (round 1: end-to-end efficiency 0.52 at 4 GPUs).  Returns the core list,
+    or None when NVML / sched_setaffinity is unavailable (nothing is changed then)."""
+    import os
+
+    try:
+        import pynvml as n
+
+        n.nvmlInit()
+        phys = device
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            phys = int(vis.split(",")[device])
+        h = n.nvmlDeviceGetHandleByIndex(phys)
+        words = n.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 class PinnedBuffer:
     """Pinned host memory from ptx_host_alloc, exposed as a numpy uint8 array."""
 

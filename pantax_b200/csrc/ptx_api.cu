@@ -132,6 +132,7 @@ struct ptx_ctx {
     unsigned long long* d_hist = nullptr;
     unsigned long long* d_hist_g = nullptr;  // all-reduced copy (multi-GPU)
     bool cov_reduced = false;               // coverage accumulators already hold the cross-rank sum
+    bool hist_reduced = false;              // this ptx_finalize already all-reduced the species counts (with the coverage sums)
     uint32_t* d_flags = nullptr;  // [0] dup, [1] mixed
     uint32_t* d_err = nullptr;    // [S]
     ulonglong2* d_ds = nullptr;
@@ -1156,7 +1157,7 @@ int ptx_commit_graphs(ptx_ctx* ctx) {
     g.n_bit_words = (bits + 31) / 32 + 1;
     int rc;
     if ((rc = dalloc(ctx, &g.len, N, false)) || (rc = dalloc(ctx, &g.bit_off, N + 1, false)) || (rc = dalloc(ctx, &g.bases, N)) ||
-        (rc = dalloc(ctx, &g.full, N)) || (rc = dalloc(ctx, &g.bits, g.n_bit_words)) || (rc = dalloc(ctx, &g.cov, N)) ||
+        (rc = dalloc(ctx, &g.full, N)) || (rc = dalloc(ctx, &g.bits, g.n_bit_words + BITS_SLICE_PAD)) || (rc = dalloc(ctx, &g.cov, N)) ||
         (rc = dalloc(ctx, &g.pnode, P, false)) || (rc = dalloc(ctx, &g.poff, Htot + 1, false)) || (rc = dalloc(ctx, &g.path_len_sum, Htot)) ||
         (rc = dalloc(ctx, &g.path_cov_sum, Htot)) || (rc = dalloc(ctx, &g.hap_nz, Htot)) || (rc = dalloc(ctx, &g.trio_start, Htot + 1)) ||
         (rc = dalloc(ctx, &g.ninfo, N, false)))
@@ -1454,24 +1455,40 @@ int ptx_finalize(ptx_ctx* ctx) {
         auto reduce_and_stats = [&]() -> int {
             launch_ninfo_full(g.ninfo, g.full, g.N, 0, ctx->st);
             if (ctx->comm) {
-                // int64 sums and flag maxima are order-free: bit-exact for any shard count
+                // int64 sums and ORs are order-free: bit-exact for any shard count.  All sums travel as ONE aggregated NCCL
+                // launch (grouped all-reduces); the covered-base bitmap - the full-node flags written into it first - is
+                // OR-reduced by slices: every rank receives the other ranks' copies of ITS slice (grouped send/recv), ORs
+                // them, and the reduced slices are all-gathered in place (NCCL has no bitwise-or reduction).
                 int rc;
-                if ((rc = nccl_check(ctx, g_nccl.AllReduce(g.bases, g.bases, g.N, ncclUint64, ncclSum, ctx->comm, ctx->st), "ncclAllReduce(bases)"))) return rc;
-                if (g.T > 0 && (rc = nccl_check(ctx, g_nccl.AllReduce(g.trio_bases, g.trio_bases, g.T, ncclUint64, ncclSum, ctx->comm, ctx->st), "ncclAllReduce(trio_bases)"))) return rc;
-                if ((rc = nccl_check(ctx, g_nccl.AllReduce(g.full, g.full, g.N, ncclUint8, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(full)"))) return rc;
-                if ((rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_err, ctx->d_err, S, ncclUint32, ncclMax, ctx->comm, ctx->st), "ncclAllReduce(err)"))) return rc;
-                // bitmap OR: all-gather the packed words, OR locally (NCCL has no bitwise-or reduction)
-                if ((rc = scratch_reserve(ctx, (size_t)ctx->n_ranks * g.n_bit_words * sizeof(uint32_t) + 4096))) return rc;
+                const int P = ctx->n_ranks;
+                launch_bits_fill_full(g, ctx->st);
+                if (!ctx->d_hist_g) { if ((rc = dalloc(ctx, &ctx->d_hist_g, (size_t)S * 4))) return rc; }
+                const uint64_t slice = (((g.n_bit_words + P - 1) / P) + 3) & ~(uint64_t)3;  // P * slice <= n_bit_words + BITS_SLICE_PAD
+                if ((rc = scratch_reserve(ctx, (size_t)(P - 1) * slice * sizeof(uint32_t) + 4096))) return rc;
                 ctx->scratch_off = 0;
-                uint32_t* all = scratch_take<uint32_t>(ctx, (size_t)ctx->n_ranks * g.n_bit_words);
-                if ((rc = nccl_check(ctx, g_nccl.AllGather(g.bits, all, g.n_bit_words, ncclUint32, ctx->comm, ctx->st), "ncclAllGather(bits)"))) return rc;
-                for (int r = 0; r < ctx->n_ranks; ++r)
-                    if (r != ctx->rank) launch_or_words(g.bits, all + (size_t)r * g.n_bit_words, g.n_bit_words, ctx->st);
+                uint32_t* got = scratch_take<uint32_t>(ctx, (size_t)(P - 1) * slice);
+                g_nccl.GroupStart();
+                g_nccl.AllReduce(g.bases, g.bases, g.N, ncclUint64, ncclSum, ctx->comm, ctx->st);
+                if (g.T > 0) g_nccl.AllReduce(g.trio_bases, g.trio_bases, g.T, ncclUint64, ncclSum, ctx->comm, ctx->st);
+                g_nccl.AllReduce(ctx->d_err, ctx->d_err, S, ncclUint32, ncclMax, ctx->comm, ctx->st);
+                g_nccl.AllReduce(ctx->d_hist, ctx->d_hist_g, (size_t)S * 4, ncclUint64, ncclSum, ctx->comm, ctx->st);
+                if ((rc = nccl_check(ctx, g_nccl.GroupEnd(), "grouped ncclAllReduce(bases, trio_bases, err, hist)"))) return rc;
+                g_nccl.GroupStart();
+                for (int q = 0, k = 0; q < P; ++q) {
+                    if (q == ctx->rank) continue;
+                    g_nccl.Send(g.bits + (uint64_t)q * slice, slice, ncclUint32, q, ctx->comm, ctx->st);
+                    g_nccl.Recv(got + (uint64_t)k * slice, slice, ncclUint32, q, ctx->comm, ctx->st);
+                    ++k;
+                }
+                if ((rc = nccl_check(ctx, g_nccl.GroupEnd(), "grouped ncclSend/ncclRecv(bitmap slices)"))) return rc;
+                launch_or_slices(g.bits + (uint64_t)ctx->rank * slice, got, (uint32_t)(P - 1), slice, ctx->st);
+                if ((rc = nccl_check(ctx, g_nccl.AllGather(g.bits + (uint64_t)ctx->rank * slice, g.bits, slice, ncclUint32, ctx->comm, ctx->st), "ncclAllGather(bitmap slices)"))) return rc;
+                ctx->hist_reduced = true;
             }
             tr.mark("final reductions");
             CU(cudaMemsetAsync(g.path_cov_sum, 0, std::max<int64_t>(g.Htot, 1) * sizeof(unsigned long long), ctx->st));
             CU(cudaMemsetAsync(g.hap_nz, 0, std::max<int64_t>(g.Htot, 1) * sizeof(unsigned long long), ctx->st));
-            launch_cov(g, ctx->st);
+            launch_cov(g, ctx->comm != nullptr, ctx->st);
             launch_path_cov_sum(g, ctx->st);
             launch_hap_nz(g, ctx->st);
             return PTX_OK;
@@ -1516,11 +1533,12 @@ int ptx_finalize(ptx_ctx* ctx) {
         CU(cudaStreamSynchronize(ctx->st));
         if (ctx->h_flags[1]) { int rc = return_mixed_ids(ctx, ctx->st); if (rc) return rc; }
     }
-    if (ctx->comm) {
+    if (ctx->comm && !ctx->hist_reduced) {  // no coverage reduction ran (no graphs): the species counts travel alone
         if (!ctx->d_hist_g) { int rc = dalloc(ctx, &ctx->d_hist_g, (size_t)S * 4); if (rc) return rc; }
         int rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_hist, ctx->d_hist_g, (size_t)S * 4, ncclUint64, ncclSum, ctx->comm, ctx->st), "ncclAllReduce(hist)");
         if (rc) return rc;
     }
+    ctx->hist_reduced = false;
     tr.mark("final cov/path/hap stats");
     ctx->h_err.assign(S, 0);
     CU(cudaMemcpyAsync(ctx->h_err.data(), ctx->d_err, S * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st));

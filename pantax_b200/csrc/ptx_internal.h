@@ -28,6 +28,7 @@ constexpr uint32_t REC_CAP = 1024;  // record starts kept in smem per round
 constexpr double LONG_LINE_BYTES = 320.0;  // mean line length from which a chunk is parsed by k_ingest<LONG>
 constexpr uint32_t HIST_SLOTS_LOG2 = 7;  // per-tile species-count accumulators in shared memory (multi-species runs)
 constexpr uint32_t HIST_SLOTS = 1u << HIST_SLOTS_LOG2;
+constexpr uint64_t BITS_SLICE_PAD = 4 * 64;  // spare bitmap words: n_bit_words rounded up to n_ranks slices of a multiple of 4 words (<= 64 ranks)
 constexpr uint32_t STASH_CAP = 16;  // walk nodes per record kept in smem between the parse and the coverage pass
 
 // record-table flags (IngestArgs::meta_b[e].y): walk length in the low 24 bits
@@ -53,7 +54,7 @@ struct GraphDev {
     uint4* ninfo = nullptr;           // [N] {len, flags (NI_FULL | NI_TRIO_MID), bit_off lo, hi}: the one gather of the coverage pass
     uint8_t* full = nullptr;          // [N] NI_FULL extracted at finalize (staging for k_cov and the cross-rank max)
     uint32_t* bits = nullptr;         // [ceil(total_bits/32)+1] packed per-base covered bitmap
-    uint64_t n_bit_words = 0;
+    uint64_t n_bit_words = 0;         // words in use; the allocation has BITS_SLICE_PAD more (the per-rank slices of the OR-reduction are rounded up)
     uint32_t* cov = nullptr;          // [N] covered bases (finalize)
     // paths
     int64_t Htot = 0, P = 0;          // paths, total steps
@@ -164,13 +165,15 @@ void launch_trio_emit(const uint32_t* pnode, const uint64_t* poff, int64_t Htot,
                       cudaStream_t st);
 
 // finalize
-void launch_cov(const GraphDev& g, cudaStream_t st);
+void launch_cov(const GraphDev& g, bool bits_only, cudaStream_t st);  // bits_only: the full-node flags were written into the bitmap (multi-GPU)
 void launch_path_cov_sum(const GraphDev& g, cudaStream_t st);
 void launch_hap_nz(const GraphDev& g, cudaStream_t st);
 void launch_depth(const unsigned long long* num, const uint32_t* den32, const int64_t* den64, double* out, uint64_t n,
                   cudaStream_t st);
 // OR-merge a peer's bitmap / full flags into ours (multi-GPU finalize)
 void launch_or_words(uint32_t* dst, const uint32_t* src, uint64_t n_words, cudaStream_t st);
+void launch_bits_fill_full(const GraphDev& g, cudaStream_t st);
+void launch_or_slices(uint32_t* dst, const uint32_t* src, uint32_t n_src, uint64_t n_words, cudaStream_t st);
 
 // K10 long-read filter
 void launch_flt_count_nl(const uint8_t* text, uint64_t n, uint32_t n_micro, uint32_t* cnt, cudaStream_t st);

@@ -1770,7 +1770,7 @@ __global__ void __launch_bounds__(256) k_cov(const uint32_t* __restrict__ len, c
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= N) return;
     const uint32_t ln = len[g];
-    if (full[g]) {
+    if (full && full[g]) {
         cov[g] = ln;
         return;
     }
@@ -1806,6 +1806,29 @@ __global__ void __launch_bounds__(256) k_depth(const unsigned long long* __restr
     out[i] = (double)(long long)num[i] / d;  // profile.rs:988 / :1014 (IEEE division, identical on host)
 }
 
+// multi-GPU finalize: a node some read covered completely carries NI_FULL instead of bits.  Before the bitmaps of the ranks are
+// OR-ed its bits are written out, so that the bitmap alone carries the coverage and the flags need no reduction of their own.
+__global__ void __launch_bounds__(256) k_bits_fill_full(const uint4* __restrict__ ninfo, uint32_t* bits, int64_t N) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    const uint4 ni = ninfo[g];
+    if (!(ni.y & NI_FULL)) return;
+    const uint64_t b0 = ((uint64_t)ni.w << 32) | ni.z, b1 = b0 + ni.x - 1;
+    const uint64_t w0 = b0 >> 5, w1 = b1 >> 5;
+    const uint32_t m0 = 0xFFFFFFFFu << (b0 & 31u), m1 = 0xFFFFFFFFu >> (31u - (uint32_t)(b1 & 31u));
+    if (w0 == w1) { atomicOr(bits + w0, m0 & m1); return; }
+    atomicOr(bits + w0, m0);  // the first and the last word are shared with the neighbours
+    for (uint64_t w = w0 + 1; w < w1; ++w) bits[w] = 0xFFFFFFFFu;
+    atomicOr(bits + w1, m1);
+}
+// dst[i] |= src[0][i] | src[1][i] | ... (n_src slices of n words behind each other)
+__global__ void __launch_bounds__(256) k_or_slices(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint32_t n_src, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t v = dst[i];
+        for (uint32_t q = 0; q < n_src; ++q) v |= src[(uint64_t)q * n + i];
+        dst[i] = v;
+    }
+}
 __global__ void __launch_bounds__(256) k_or_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] |= src[i];
 }
@@ -2312,9 +2335,9 @@ void launch_trio_emit(const uint32_t* pnode, const uint64_t* poff, int64_t Htot,
                                                                                trio_owner, tt, tt_mask, ninfo, trio_start);
     PTX_LAUNCHED();
 }
-void launch_cov(const GraphDev& g, cudaStream_t st) {
+void launch_cov(const GraphDev& g, bool bits_only, cudaStream_t st) {
     if (g.N <= 0) return;
-    k_cov<<<(uint32_t)((g.N + 255) / 256), 256, 0, st>>>(g.len, g.bit_off, g.full, g.bits, g.cov, g.N);
+    k_cov<<<(uint32_t)((g.N + 255) / 256), 256, 0, st>>>(g.len, g.bit_off, bits_only ? nullptr : g.full, g.bits, g.cov, g.N);
     PTX_LAUNCHED();
 }
 void launch_path_cov_sum(const GraphDev& g, cudaStream_t st) {
@@ -2328,6 +2351,16 @@ void launch_hap_nz(const GraphDev& g, cudaStream_t st) {
 void launch_depth(const unsigned long long* num, const uint32_t* den32, const int64_t* den64, double* out, uint64_t n, cudaStream_t st) {
     if (n == 0) return;
     k_depth<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(num, den32, den64, out, n);
+    PTX_LAUNCHED();
+}
+void launch_bits_fill_full(const GraphDev& g, cudaStream_t st) {
+    if (g.N <= 0) return;
+    k_bits_fill_full<<<(uint32_t)((g.N + 255) / 256), 256, 0, st>>>(g.ninfo, g.bits, g.N);
+    PTX_LAUNCHED();
+}
+void launch_or_slices(uint32_t* dst, const uint32_t* src, uint32_t n_src, uint64_t n_words, cudaStream_t st) {
+    if (n_words == 0 || n_src == 0) return;
+    k_or_slices<<<grid_for(n_words, 256 * 4), 256, 0, st>>>(dst, src, n_src, n_words);
     PTX_LAUNCHED();
 }
 void launch_or_words(uint32_t* dst, const uint32_t* src, uint64_t n_words, cudaStream_t st) {
