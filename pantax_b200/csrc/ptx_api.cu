@@ -110,6 +110,7 @@ struct Chunk {
     bool ingested = false;  // classify pass done
     bool covered = false;   // coverage pass done against the current graph
     cudaEvent_t copied = nullptr;
+    bool host_text = false;  // the text came through ptx_ingest_gaf (not a caller-owned device buffer): it may be released once the chunk is resolved
 };
 
 struct EvPair { cudaEvent_t a, b; };
@@ -145,6 +146,7 @@ struct ptx_ctx {
     int64_t pair_cap = 0; size_t pair_tmp_cap = 0;
     int force_rows = 0;  // PTX_TILE_ROWS env override (tests exercise every tile size)
     int force_tile = 0;  // PTX_TILE_BYTES env override for single-pass chunks of k_ingest_s (multiple of 512)
+    bool keep_text = false;  // PTX_KEEP_TEXT=1: never hand the text of resolved chunks back (debugging)
     bool no_sort = false;    // PTX_NO_SORT=1: k_ingest_s keeps file order inside a tile (measurements)
     bool old_short = false;  // PTX_OLD_INGEST=1: round 1's byte-at-a-time short-read kernel (A/B measurements)
     int force_long = -1; // PTX_LONG_MODE env override: 0/1 = never/always use the long-line kernel (tests)
@@ -166,6 +168,13 @@ struct ptx_ctx {
     std::vector<uint32_t> h_err;
     // reuse: chunk buffers released by ptx_reset, and one grow-only scratch arena for ptx_finalize
     std::vector<Chunk> pool;
+    // text buffers handed back by resolved chunks (ptx_ingest_gaf path): {buffer, text capacity, its `copied` event}.  The text of a
+    // chunk is only needed until its counts are in (an abandoned single-pass chunk is redone from it) and, for the first chunks,
+    // by ptx_equal_length - the replay passes run from the record tables.  Device memory per GAF byte drops from ~3x to ~0.6x.
+    struct TextBuf { uint8_t* buf; size_t cap; cudaEvent_t copied; };
+    std::vector<TextBuf> text_pool;
+    int64_t labelled_rows_known = 0;  // non-U rows of the chunks resolved so far (exact-mode chunks count as 0: their text is kept)
+    double seen_nodes_per_byte = 0;   // walk nodes per text byte of the last resolved chunk: sizes the CSR buffer of single-pass chunks
     uint8_t* scratch = nullptr;
     size_t scratch_cap = 0, scratch_off = 0;
     // asynchronous id-group exchange (multi-GPU): boxes filled by k_apply, sent on a side stream during the coverage pass
@@ -329,6 +338,7 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.meta_a = ch.meta_a;
     a.hash_lo = ch.hash_lo;
     a.nodes = ch.nodes;
+    a.nodes_cap = (uint32_t)std::min<int64_t>(ch.nodes_cap, 0xFFFFFFF0ll);
     a.cursors = reinterpret_cast<uint32_t*>(ch.cursors);
 
     a.box_ptr = ctx->comm ? ctx->d_box_ptr : nullptr;
@@ -370,27 +380,63 @@ size_t padded_text_bytes(size_t n) {
     return (blocks + 1) * (size_t)MAX_TILE + OVER;
 }
 
-// allocate a chunk buffer able to hold `cap` text bytes; PRE bytes of '\n' in front
-int chunk_alloc(ptx_ctx* ctx, Chunk& ch, size_t cap) {
-    // reuse a released buffer of similar size (ptx_reset keeps them): no cudaMalloc on the steady-state path
+// a text buffer able to hold `cap` bytes: [PRE '\n'][text][padding]; from the pool of released ones if one fits
+int text_alloc(ptx_ctx* ctx, Chunk& ch, size_t cap) {
     int best = -1;
-    for (size_t i = 0; i < ctx->pool.size(); ++i)
-        if (ctx->pool[i].cap >= cap && ctx->pool[i].cap <= 2 * cap + (1u << 20) && (best < 0 || ctx->pool[i].cap < ctx->pool[best].cap)) best = (int)i;
+    for (size_t i = 0; i < ctx->text_pool.size(); ++i) {
+        const auto& t = ctx->text_pool[i];
+        if (t.cap >= cap && t.cap <= 2 * cap + (1u << 20) && (best < 0 || t.cap < ctx->text_pool[best].cap)) best = (int)i;
+    }
     if (best >= 0) {
-        ch = ctx->pool[best];
-        ctx->pool.erase(ctx->pool.begin() + best);
-        ch.n = 0; ch.n_records = 0; ch.ingested = false; ch.covered = false; ch.pending = false;
+        ch.buf = ctx->text_pool[best].buf;
+        ch.cap = ctx->text_pool[best].cap;
+        ch.copied = ctx->text_pool[best].copied;
+        ctx->text_pool.erase(ctx->text_pool.begin() + best);
         return PTX_OK;
     }
-    ch = Chunk();
     ch.cap = cap;
     const size_t total = PRE + padded_text_bytes(cap);
-    CU(cudaMalloc((void**)&ch.buf, total));
+    const cudaError_t e = cudaMalloc((void**)&ch.buf, total);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        ch.buf = nullptr;
+        return fail(ctx, PTX_E_NOMEM, "out of device memory for a %zu MB GAF text buffer: the record tables of the input ingested so far stay resident "
+                                      "(about 0.6 bytes per GAF byte) - split the input over more GPUs or contexts", total >> 20);
+    }
     // the newline padding in front of the text is written once, on the COPY stream: the text copies are queued behind it
     // there, and the kernels wait for `copied` - no host synchronisation between a call's copies and the previous call's kernels
     CU(cudaMemsetAsync(ch.buf, '\n', PRE, ctx->copy_st));
     CU(cudaEventCreateWithFlags(&ch.copied, cudaEventDisableTiming));
     return PTX_OK;
+}
+
+// a chunk (record tables + text buffer) for `cap` text bytes
+int chunk_alloc(ptx_ctx* ctx, Chunk& ch, size_t cap) {
+    // reuse a released chunk of similar size (ptx_reset keeps them): no cudaMalloc on the steady-state path
+    int best = -1;
+    for (size_t i = 0; i < ctx->pool.size(); ++i) {
+        const Chunk& c = ctx->pool[i];
+        const bool fits = c.buf == nullptr ? true : (c.cap >= cap && c.cap <= 2 * cap + (1u << 20));
+        if (fits && (best < 0 || (c.buf != nullptr && ctx->pool[best].buf == nullptr))) best = (int)i;
+    }
+    if (best >= 0) {
+        ch = ctx->pool[best];
+        ctx->pool.erase(ctx->pool.begin() + best);
+        ch.n = 0; ch.n_records = 0; ch.ingested = false; ch.covered = false; ch.pending = false; ch.host_text = false;
+    } else {
+        ch = Chunk();
+    }
+    if (ch.buf == nullptr) return text_alloc(ctx, ch, cap);
+    return PTX_OK;
+}
+
+// hand the text buffer of a resolved chunk back (see ptx_ctx::text_pool)
+void chunk_release_text(ptx_ctx* ctx, Chunk& ch) {
+    if (!ch.buf) return;
+    ctx->text_pool.push_back({ch.buf, ch.cap, ch.copied});
+    ch.buf = nullptr;
+    ch.copied = nullptr;
+    ch.cap = 0;
 }
 
 // bump allocation from the grow-only finalize scratch arena (256-byte aligned); reset with scratch_off = 0
@@ -473,7 +519,7 @@ int chunk_common_begin(ptx_ctx* ctx, Chunk& ch) {
     if (ch.n >= (1ull << 32)) return fail(ctx, PTX_E_INVALID, "a chunk must be smaller than 4 GiB (split the input)");
     if (!ch.cursors) {
         CU(cudaMalloc((void**)&ch.cursors, 8 * sizeof(unsigned long long)));
-        CU(cudaHostAlloc((void**)&ch.h_cur, 4 * sizeof(uint32_t), cudaHostAllocDefault));
+        CU(cudaHostAlloc((void**)&ch.h_cur, 8 * sizeof(uint32_t), cudaHostAllocDefault));
         CU(cudaEventCreateWithFlags(&ch.done, cudaEventDisableTiming));
     }
     CU(cudaMemsetAsync(ch.cursors, 0, 8 * sizeof(unsigned long long), ctx->st));
@@ -482,13 +528,24 @@ int chunk_common_begin(ptx_ctx* ctx, Chunk& ch) {
 
 // CSR node slots of a chunk: a walk node takes at least two bytes of text; the long-line kernel reserves
 // (bytes from column 6 to the end of the line) / 2 + 1 slots per record instead of counting the nodes first
-int chunk_nodes_ensure(ptx_ctx* ctx, Chunk& ch) {
-    (void)ctx;
-    const int64_t need = (int64_t)(ch.n / 2 + 16) + (ch.long_mode ? ch.slots_cap : 0);
+int chunk_nodes_ensure(ptx_ctx* ctx, Chunk& ch, bool exact) {
+    const int64_t bound = (int64_t)(ch.n / 2 + 16) + (ch.long_mode ? ch.slots_cap : 0);  // always enough
+    int64_t need = bound;
+    // single-pass chunks of k_ingest_s: from the walk nodes per byte of the chunks seen so far, with a quarter of slack; the kernel
+    // abandons the chunk (redone exactly) instead of writing beyond the buffer
+    if (!exact && !ch.long_mode && !ctx->old_short && ctx->seen_nodes_per_byte > 0)
+        need = std::min<int64_t>(bound, (int64_t)((double)ch.n * ctx->seen_nodes_per_byte * 1.25) + 65536);
     if (ch.nodes_cap < need) {
         dfree(ch.nodes);
         ch.nodes_cap = need + need / 8;
-        CU(cudaMalloc((void**)&ch.nodes, (size_t)ch.nodes_cap * sizeof(uint32_t)));
+        const cudaError_t e = cudaMalloc((void**)&ch.nodes, (size_t)ch.nodes_cap * sizeof(uint32_t));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            ch.nodes = nullptr;
+            ch.nodes_cap = 0;
+            return fail(ctx, PTX_E_NOMEM, "out of device memory for the walk table of a chunk (%lld MB): the record tables of the input ingested so far stay "
+                                          "resident (about 0.6 bytes per GAF byte) - split the input over more GPUs or contexts", (long long)(need >> 18));
+        }
     }
     return PTX_OK;
 }
@@ -522,7 +579,7 @@ int chunk_process_exact(ptx_ctx* ctx, Chunk& ch) {
     if ((rc = chunk_table_ensure(ctx, ch, ch.n_slots))) return rc;
     const double mean_line = (double)ch.n / (double)std::max<uint64_t>(total, 1);
     chunk_pick_tile(ctx, ch, mean_line, true);
-    if ((rc = chunk_nodes_ensure(ctx, ch))) return rc;
+    if ((rc = chunk_nodes_ensure(ctx, ch, true))) return rc;
     if (!ch.labels || ch.labels_cap < (int64_t)total) {
         dfree(ch.labels);
         CU(cudaMalloc((void**)&ch.labels, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
@@ -571,7 +628,7 @@ int chunk_process_single(ptx_ctx* ctx, Chunk& ch) {
     const int64_t est_slots = (int64_t)(est_rows * ctx->seen_slots_per_row * 1.25) + 4096;
     if (est_slots > 0xFFFFFFF0ll) return chunk_process_exact(ctx, ch);
     if ((rc = chunk_table_ensure(ctx, ch, est_slots))) return rc;
-    if ((rc = chunk_nodes_ensure(ctx, ch))) return rc;
+    if ((rc = chunk_nodes_ensure(ctx, ch, false))) return rc;
     if (ch.tile_info_cap < ch.n_tiles) {
         dfree(ch.tile_info);
         CU(cudaMalloc((void**)&ch.tile_info, (size_t)ch.n_tiles * sizeof(uint4)));
@@ -603,7 +660,7 @@ int chunk_process_single(ptx_ctx* ctx, Chunk& ch) {
     launch_apply(a, ENTRIES_FROM_DEVICE, MODE_CLASSIFY | (cover ? MODE_COVER : 0), ctx->st);
     ev_end(ctx, ctx->ev_apply);
     launch_hist_merge(ch.chunk_hist, ctx->d_hist, (uint32_t)S4, a.cursors, ctx->st);
-    CU(cudaMemcpyAsync(ch.h_cur, a.cursors, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(ch.h_cur, a.cursors, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaEventRecord(ch.done, ctx->st));
     CU(cudaGetLastError());
     ch.ingested = true;
@@ -638,7 +695,12 @@ int chunks_resolve(ptx_ctx* ctx, bool blocking = true) {
         if (ch.n_records > 0) {
             ctx->seen_mean_line = (double)ch.n / (double)ch.n_records;
             ctx->seen_slots_per_row = (double)ch.n_slots / (double)ch.n_records;
+            ctx->seen_nodes_per_byte = (double)ch.h_cur[1] / (double)ch.n;
         }
+        // the chunk is complete and will never be parsed again: unless ptx_equal_length may still want its lines (the first 1000
+        // non-U rows, profile.rs:311-322), its text buffer goes back to the pool for the pieces still to come
+        if (ch.host_text && ctx->labelled_rows_known >= 1000 && !ctx->keep_text) chunk_release_text(ctx, ch);
+        ctx->labelled_rows_known += (int64_t)ch.h_cur[4];
     }
     return PTX_OK;
 }
@@ -983,6 +1045,7 @@ int ptx_create(int device, ptx_ctx** out) {
     if (const char* e = getenv("PTX_TILE_BYTES")) ctx->force_tile = atoi(e);
     if (const char* e = getenv("PTX_OLD_INGEST")) ctx->old_short = atoi(e) != 0;
     if (const char* e = getenv("PTX_NO_SORT")) ctx->no_sort = atoi(e) != 0;
+    if (const char* e = getenv("PTX_KEEP_TEXT")) ctx->keep_text = atoi(e) != 0;
     if (const char* e = getenv("PTX_SCATTER")) ctx->scatter_var = atoi(e);
     if (const char* e = getenv("PTX_LONG_MODE")) ctx->force_long = atoi(e) ? 1 : 0;
     if (const char* e = getenv("PTX_TEST_BOX_CAP")) ctx->test_box_cap = atoll(e);
@@ -1008,6 +1071,8 @@ void ptx_destroy(ptx_ctx* ctx) {
     cudaDeviceSynchronize();
     for (auto& ch : ctx->chunks) chunk_free(ch);
     for (auto& ch : ctx->pool) chunk_free(ch);
+    for (auto& t : ctx->text_pool) { if (t.buf) cudaFree(t.buf); if (t.copied) cudaEventDestroy(t.copied); }
+    ctx->text_pool.clear();
     dfree(ctx->scratch);
     for (void* m : ctx->p2p_peer) if (m) cudaIpcCloseMemHandle(m);
     ctx->p2p_peer.clear();
@@ -1316,6 +1381,7 @@ int ptx_ingest_gaf(ptx_ctx* ctx, const uint8_t* bytes, size_t n, int is_last) {
         if (c0) CU(cudaMemcpyAsync(ch.buf + PRE, ctx->carry.data(), c0, cudaMemcpyHostToDevice, ctx->copy_st));
         if (take) CU(cudaMemcpyAsync(ch.buf + PRE + c0, bytes + off, take, cudaMemcpyHostToDevice, ctx->copy_st));
         ch.n = c0 + take;
+        ch.host_text = true;
         CU(cudaEventRecord(ch.copied, ctx->copy_st));
         ctx->chunks.push_back(ch);
         piece_idx.push_back(ctx->chunks.size() - 1);
@@ -1576,6 +1642,7 @@ static int reset_impl(ptx_ctx* ctx, bool keep_buffers) {
     ctx->carry.clear();
     if (!keep_buffers) ctx->labels_in_n = 0;  // supplied labels belong to the input that is being dropped
     ctx->total_records = 0;
+    ctx->labelled_rows_known = 0;
     ctx->ds_records = 0;
     ctx->cov_reduced = false;
     ctx->h_flags[0] = ctx->h_flags[1] = ctx->h_flags[2] = 0;
@@ -1669,6 +1736,7 @@ int ptx_equal_length(ptx_ctx* ctx, int* is_equal, int64_t* read_len) {
     for (auto& ch : ctx->chunks) {
         if (seen >= 1000) break;
         if (!ch.ingested || ch.n_records == 0) continue;
+        if (!ch.buf) return fail(ctx, PTX_E_STATE, "ptx_equal_length: the text of the first rows is gone");  // cannot happen: text is kept until 1000 non-U rows are known
         {
             int rc = chunk_labels_materialize(ctx, ch);
             if (rc) return rc;
@@ -2052,14 +2120,15 @@ int ptx_stats_json(ptx_ctx* ctx, char* buf, size_t cap) {
     chunks_resolve(ctx);
     cudaStreamSynchronize(ctx->st);
     size_t text = 0;
-    for (auto& ch : ctx->chunks) text += ch.n;
+    size_t text_resident = 0;
+    for (auto& ch : ctx->chunks) { text += ch.n; if (ch.buf) text_resident += ch.n; }
     snprintf(buf, cap,
              "{\"records\": %lld, \"chunks\": %zu, \"text_bytes\": %zu, \"nodes\": %lld, \"paths\": %lld, \"path_steps\": %lld, "
              "\"unique_trios\": %lld, \"bit_words\": %llu, \"id_set_slots\": %llu, \"ids_unique\": %d, \"mixed_groups\": %d, "
-             "\"count_ms\": %.4f, \"ingest_ms\": %.4f, \"apply_ms\": %.4f, \"ingest_launches\": %zu, \"finalize_ms\": %.4f, \"kernel_launches\": %lld, \"ranks\": %d, \"p2p_boxes\": %d, \"table_allocs\": %lld}",
+             "\"count_ms\": %.4f, \"ingest_ms\": %.4f, \"apply_ms\": %.4f, \"ingest_launches\": %zu, \"finalize_ms\": %.4f, \"kernel_launches\": %lld, \"ranks\": %d, \"p2p_boxes\": %d, \"table_allocs\": %lld, \"text_buffers_released\": %zu, \"text_bytes_resident\": %zu}",
              (long long)ctx->total_records, ctx->chunks.size(), text, (long long)ctx->g.N, (long long)ctx->g.Htot, (long long)ctx->g.P,
              (long long)ctx->g.T, (unsigned long long)ctx->g.n_bit_words, (unsigned long long)ctx->ds_cap, ctx->h_flags[0] == 0 ? 1 : 0,
-             ctx->h_flags[1] != 0 ? 1 : 0, ev_sum(ctx->ev_count), ev_sum(ctx->ev_ingest), ev_sum(ctx->ev_apply), ctx->ev_ingest.size(), ev_sum(ctx->ev_final), (long long)kernel_launch_count(), ctx->n_ranks, ctx->p2p ? 1 : 0, (long long)ctx->n_table_allocs);
+             ctx->h_flags[1] != 0 ? 1 : 0, ev_sum(ctx->ev_count), ev_sum(ctx->ev_ingest), ev_sum(ctx->ev_apply), ctx->ev_ingest.size(), ev_sum(ctx->ev_final), (long long)kernel_launch_count(), ctx->n_ranks, ctx->p2p ? 1 : 0, (long long)ctx->n_table_allocs, ctx->text_pool.size(), text_resident);
     return PTX_OK;
 }
 

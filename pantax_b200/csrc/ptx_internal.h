@@ -96,7 +96,8 @@ struct IngestArgs {
     longlong2* meta_a;          // [line slots] {c8, c9} of eligible records
     unsigned long long* hash_lo;  // [line slots] id hash lo of labelled records
     uint32_t* nodes;            // [<= text bytes / 2] raw node ids of eligible records' walks
-    uint32_t* cursors;          // [0] next record-table entry, [1] next node slot, [2] GAF rows, [3] single-pass estimate too small
+    uint32_t nodes_cap;         // capacity of `nodes` (k_ingest_s abandons the chunk instead of writing beyond it)
+    uint32_t* cursors;          // [0] next record-table entry, [1] next node slot, [2] GAF rows, [3] single-pass estimate too small, [4] labelled rows
     // multi-GPU: id entries routed to the rank owning their hash (written by k_apply<CLASSIFY>, sent at finalize)
     // multi-GPU (null on one GPU): box_ptr[q] = where {hash, state} of records whose id rank q owns are appended -
     // this rank's slice of q's inbox in PEER memory (stores travel over NVLink while k_apply runs), or a local outbox
@@ -134,7 +135,7 @@ void launch_count_records(const uint8_t* text, uint64_t n_bytes, uint32_t n_micr
 void launch_ingest(const IngestArgs& a, cudaStream_t st);
 constexpr uint32_t ENTRIES_FROM_DEVICE = 0xFFFFFFFFu;  // launch_apply: take the entry count (and the abandon flag) from a.cursors
 void launch_apply(const IngestArgs& a, uint32_t n_entries, int mode, cudaStream_t st);
-void launch_hist_merge(const unsigned long long* chunk_hist, unsigned long long* hist, uint32_t n, const uint32_t* cursors, cudaStream_t st);
+void launch_hist_merge(const unsigned long long* chunk_hist, unsigned long long* hist, uint32_t n, uint32_t* cursors, cudaStream_t st);
 void launch_tile_rows(const uint4* tile_info, uint32_t* rows, uint32_t n_tiles, cudaStream_t st);
 void launch_labels_from_table(const uint4* tile_info, const uint64_t* tile_off, const uint4* meta_b, const uint16_t* row_key, uint32_t* labels,
                               uint32_t n_tiles, cudaStream_t st);

@@ -732,6 +732,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, LONG ? 3 : 4) k_ingest(const I
             uint32_t label = LABEL_U;
             const uint8_t* b = stage;
             uint32_t node_off = 0;
+            uint32_t w_res = 0;  // LONG: CSR slots this record already holds at node_off (reserved from its line length)
             bool slow = false;  // LONG: this record goes through the scalar parser on the global copy of its line
             if constexpr (LONG) {
                 // columns 1-5 per thread, column 6 by the whole warp one record at a time, columns 7-12 per thread
@@ -761,6 +762,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, LONG ? 3 : 4) k_ingest(const I
                 want6 = want6 && !slow;
                 {  // node slots of every record decoded here (eligible or not)
                     const uint32_t wa = want6 ? w_up : 0u;
+                    w_res = wa;
                     uint32_t x = wa;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
@@ -888,8 +890,11 @@ __global__ void __launch_bounds__(INGEST_THREADS, LONG ? 3 : 4) k_ingest(const I
             const bool eligible = labelled && !r.path_null && r.c7 != NULL_I64 && r.c8 != NULL_I64 && r.c9 != NULL_I64;  // profile.rs:380-399
             const uint32_t wcnt = eligible ? r.W : 0u;
             if constexpr (LONG) {
-                // the cooperative decode already wrote the walk at node_off; the scalar fallback takes its own slots
-                if (slow && wcnt) node_off = atomicAdd(a.cursors + 1, wcnt);
+                // the cooperative decode already wrote the walk at node_off.  The scalar fallback writes into the slots the record
+                // reserved from its line length (every digit run takes two bytes: they always suffice) and takes new ones only if
+                // it reserved none (its line left the window before column 6) - never both, so that the slots of a chunk stay
+                // within text bytes / 2 + one per line (chunk_nodes_ensure) whatever the ids look like
+                if (slow && wcnt > w_res) node_off = atomicAdd(a.cursors + 1, wcnt);
             } else {
                 uint32_t x = wcnt;  // node slots: warp scan, one atomicAdd per warp on the chunk's node cursor
 #pragma unroll
@@ -1301,6 +1306,7 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
             const bool eligible = labelled && cols_ok;
             const uint32_t wcnt = eligible ? W : 0u;
             uint32_t node_off;
+            bool nodes_ok = true;
             {
                 uint32_t x = wcnt;  // node slots: warp scan, one atomicAdd per warp on the chunk's node cursor
 #pragma unroll
@@ -1310,9 +1316,16 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
                 }
                 const uint32_t wtot = __shfl_sync(0xffffffffu, x, 31);
                 uint32_t nbase = 0;
-                if (lane == 0 && wtot) nbase = atomicAdd(a.cursors + 1, wtot);
+                if (lane == 0 && wtot) {
+                    nbase = atomicAdd(a.cursors + 1, wtot);
+                    if (nbase + wtot > a.nodes_cap) {  // the CSR buffer was sized from an estimate: the host redoes the chunk with exact sizes
+                        atomicOr(a.cursors + 3, 1u);
+                        nbase = 0xFFFFFFFFu;
+                    }
+                }
                 nbase = __shfl_sync(0xffffffffu, nbase, 0);
                 node_off = nbase + x - wcnt;
+                if (nbase == 0xFFFFFFFFu) nodes_ok = false;
             }
             if (slot) {
                 const uint32_t e = slot_base_s + q;
@@ -1328,7 +1341,7 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
                     if (eligible) a.meta_a[e] = make_longlong2(c8, c9);
                 }
             }
-            if (wcnt) {
+            if (wcnt && nodes_ok) {
                 uint32_t* dst = a.nodes + node_off;
                 if (stashed) {
                     for (uint32_t i = 0; i < wcnt; ++i) dst[i] = stash[i * SHORT_THREADS + tid];
@@ -1497,10 +1510,13 @@ __global__ void __launch_bounds__(256, 8) k_apply(const IngestArgs a, uint32_t n
 // single-pass ingest: the species counts of a chunk go to a chunk-local buffer and are added to the totals only
 // if the chunk was not abandoned (cursors[3])
 __global__ void __launch_bounds__(256) k_hist_merge(const unsigned long long* __restrict__ chunk_hist, unsigned long long* hist, uint32_t n,
-                                                    const uint32_t* __restrict__ cursors) {
+                                                    uint32_t* cursors) {
     if (cursors[3]) return;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && chunk_hist[i]) atomicAdd(hist + i, chunk_hist[i]);
+    if (i < n && chunk_hist[i]) {
+        atomicAdd(hist + i, chunk_hist[i]);
+        if ((i & 3u) == 0u) atomicAdd(cursors + 4, (uint32_t)min(chunk_hist[i], 0xFFFFFFFFull));  // labelled (non-U) rows of the chunk
+    }
 }
 // single-pass ingest: labels[] in GAF row order from the record table.  tile_off = exclusive scan of tile_info[].z.
 __global__ void __launch_bounds__(256) k_tile_rows(const uint4* __restrict__ tile_info, uint32_t* __restrict__ rows, uint32_t n_tiles) {
@@ -2176,7 +2192,7 @@ void launch_ingest(const IngestArgs& a, cudaStream_t st) {
     else k_ingest_s<<<a.n_tiles, SHORT_THREADS, ingest_smem_bytes(a.tile_bytes, a.over_bytes, true, multi), st>>>(a);
     PTX_LAUNCHED();
 }
-void launch_hist_merge(const unsigned long long* chunk_hist, unsigned long long* hist, uint32_t n, const uint32_t* cursors, cudaStream_t st) {
+void launch_hist_merge(const unsigned long long* chunk_hist, unsigned long long* hist, uint32_t n, uint32_t* cursors, cudaStream_t st) {
     k_hist_merge<<<(n + 255u) / 256u, 256, 0, st>>>(chunk_hist, hist, n, cursors);
     PTX_LAUNCHED();
 }

@@ -546,3 +546,62 @@ def test_gpu_every_scatter_variant_gives_the_same_coverage(variant, flow, monkey
     gaf = ds.gaf(8, 0, 60000, NASTY_DUP)
     ctx, o = gpu_vs_oracle(ds.ranges(), dataset_graphs(ds), gaf, flow=flow, split=[len(gaf) // 3, len(gaf) // 2])
     assert not ctx.ids_unique
+
+
+@pytest.mark.parametrize("long_mode", ["1", "0"])
+def test_gpu_ten_digit_node_ids_take_the_exact_parser_without_extra_csr_slots(long_mode, monkeypatch):
+    """Node ids >= 10^9 (10 digits; ptx_set_ranges allows them up to 2^32) are beyond the word-wide decoders of both ingest
+    kernels: every record goes through the exact parser.  In the long-read kernel such a record must reuse the CSR slots it
+    reserved from its line length instead of reserving again - a whole chunk of them used to outgrow the node buffer."""
+    from gpu_common import gpu_vs_oracle
+    monkeypatch.setenv("PTX_LONG_MODE", long_mode)
+    rng = np.random.default_rng(11)
+    base = 3_000_000_001
+    n_nodes = 5000
+    lens = rng.integers(1, 40, n_nodes).astype(np.int64)
+    paths = [np.arange(n_nodes, dtype=np.uint64), np.arange(0, n_nodes, 2, dtype=np.uint64)]
+    ranges = [("big", base, base + n_nodes - 1)]
+    lines = []
+    for i in range(30000):
+        w = int(rng.integers(1, 60))
+        s0 = int(rng.integers(0, n_nodes - w))
+        ids = range(s0, s0 + w) if rng.random() < 0.5 else range(s0 + w - 1, s0 - 1, -1)
+        walk = "".join((">" if rng.random() < 0.5 else "<") + str(base + v) for v in ids)
+        plen = int(sum(lens[v] for v in ids))
+        ps = int(rng.integers(0, lens[ids[0]] + 1))
+        pe = int(rng.integers(ps, plen + 1))
+        lines.append(f"r{i}\t{plen}\t0\t{plen}\t+\t{walk}\t{plen}\t{ps}\t{pe}\t{pe - ps}\t{pe - ps}\t60\ttp:A:P".encode())
+    gaf = b"\n".join(lines) + b"\n"
+    gpu_vs_oracle(ranges, [(lens, paths, ["h1", "h2"])], gaf, split=[len(gaf) // 2])
+
+
+def test_gpu_text_of_resolved_chunks_is_released_and_reused():
+    """Device memory must not grow with ~3 bytes per GAF byte: once a chunk's counts are in and the first 1000 non-U rows
+    (ptx_equal_length, profile.rs:311-322) are known to lie in earlier chunks, its text buffer is handed back and reused by
+    later pieces; the replay passes (mixed id groups, graphs committed after the ingest) run from the record tables."""
+    api = _api()
+    ds = synth.Dataset(83, [30000, 9000], [6, 3])
+    gaf = ds.gaf(3, 0, 120000, NASTY_DUP)
+    graphs = dataset_graphs(ds)
+    o = run_cpu_oracle(ds.ranges(), graphs, gaf)
+    ctx = api.PantaxGpu(0)
+    ctx.set_ranges(ds.ranges())
+    cuts = np.linspace(0, len(gaf), 25).astype(int)
+    for i in range(24):
+        ctx.ingest_gaf(gaf[cuts[i]:cuts[i + 1]], is_last=(i == 23))
+        if i % 6 == 5:
+            assert ctx.num_records > 0  # waits for the chunks so far: their text can go back to the pool
+    ctx.finalize()
+    st = ctx.stats()
+    assert st["text_buffers_released"] > 0 or st["text_bytes_resident"] < st["text_bytes"] // 2, st
+    assert st["text_bytes_resident"] < st["text_bytes"], st
+    eq, rl = ctx.equal_length()
+    assert (eq, rl) == (True, 150)
+    np.testing.assert_array_equal(ctx.read_labels(), o.labels())
+    # graphs only now (the reference's order): the coverage pass replays the record tables - no text is needed
+    for s, g in enumerate(graphs):
+        ctx.upload_graph(s, g[0], g[1])
+    ctx.commit_graphs()
+    ctx.finalize()
+    from gpu_common import assert_gpu_matches_oracle
+    assert_gpu_matches_oracle(ctx, o, graphs)
