@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <charconv>
 #include <cmath>
+#include <dlfcn.h>
+
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -94,29 +96,111 @@ struct Graph {  // types.rs:51-55
     std::map<std::string, std::vector<uint64_t>> paths;  // BTreeMap: name order
 };
 
-// bincode 1.3 default options: little-endian, fixed-width ints, u64 lengths (zip.rs:185 serialize_into)
-bool read_bin_graph(const std::string& path, Graph& g) {
+// ---- .bin / .bin.lz4 / .bin.zst (zip.rs:236-262) --------------------------------------------------------------------
+// The reference wraps the same bincode stream in an LZ4 *frame* (lz4_flex FrameEncoder, zip.rs:192-205) or a zstd frame
+// (zstd::Encoder, zip.rs:206-219).  liblz4 / libzstd are resolved with dlopen (the image ships the runtime libraries without
+// their headers); the few prototypes used are declared here.
+bool slurp(const std::string& path, std::vector<uint8_t>& out) {
     std::ifstream f(path, std::ios::binary);
     if (!f) return false;
-    auto rd64 = [&](uint64_t& v) { f.read(reinterpret_cast<char*>(&v), 8); return (bool)f; };
-    uint64_t n = 0;
-    if (!rd64(n)) return false;
+    f.seekg(0, std::ios::end);
+    const std::streamoff n = f.tellg();
+    f.seekg(0);
+    out.resize((size_t)n);
+    if (n) f.read(reinterpret_cast<char*>(out.data()), n);
+    return (bool)f;
+}
+bool lz4_frame_decode(const std::vector<uint8_t>& in, std::vector<uint8_t>& out) {
+    static void* h = dlopen("liblz4.so.1", RTLD_NOW);
+    if (!h) die("liblz4.so.1 not found: cannot read .bin.lz4 graphs");
+    typedef size_t (*create_t)(void**, unsigned);
+    typedef size_t (*free_t)(void*);
+    typedef size_t (*dec_t)(void*, void*, size_t*, const void*, size_t*, const void*);
+    typedef unsigned (*iserr_t)(size_t);
+    static create_t create = (create_t)dlsym(h, "LZ4F_createDecompressionContext");
+    static free_t release = (free_t)dlsym(h, "LZ4F_freeDecompressionContext");
+    static dec_t dec = (dec_t)dlsym(h, "LZ4F_decompress");
+    static iserr_t iserr = (iserr_t)dlsym(h, "LZ4F_isError");
+    if (!create || !release || !dec || !iserr) die("liblz4.so.1 lacks the LZ4F frame API");
+    void* ctx = nullptr;
+    if (iserr(create(&ctx, 100 /* LZ4F_VERSION */))) return false;
+    out.clear();
+    std::vector<uint8_t> buf(4u << 20);
+    size_t ip = 0;
+    bool ok = true;
+    while (ip < in.size()) {
+        size_t dn = buf.size(), sn = in.size() - ip;
+        const size_t r = dec(ctx, buf.data(), &dn, in.data() + ip, &sn, nullptr);
+        if (iserr(r)) { ok = false; break; }
+        out.insert(out.end(), buf.begin(), buf.begin() + (std::ptrdiff_t)dn);
+        ip += sn;
+        if (r == 0 && sn == 0 && dn == 0) break;  // frame complete
+    }
+    release(ctx);
+    return ok;
+}
+bool zstd_decode(const std::vector<uint8_t>& in, std::vector<uint8_t>& out) {
+    static void* h = dlopen("libzstd.so.1", RTLD_NOW);
+    if (!h) die("libzstd.so.1 not found: cannot read .bin.zst graphs");
+    struct InBuf { const void* src; size_t size, pos; };
+    struct OutBuf { void* dst; size_t size, pos; };
+    typedef void* (*create_t)();
+    typedef size_t (*free_t)(void*);
+    typedef size_t (*dec_t)(void*, OutBuf*, InBuf*);
+    typedef unsigned (*iserr_t)(size_t);
+    static create_t create = (create_t)dlsym(h, "ZSTD_createDStream");
+    static free_t release = (free_t)dlsym(h, "ZSTD_freeDStream");
+    static dec_t dec = (dec_t)dlsym(h, "ZSTD_decompressStream");
+    static iserr_t iserr = (iserr_t)dlsym(h, "ZSTD_isError");
+    if (!create || !release || !dec || !iserr) die("libzstd.so.1 lacks the streaming API");
+    void* ds = create();
+    if (!ds) return false;
+    out.clear();
+    std::vector<uint8_t> buf(4u << 20);
+    InBuf ib{in.data(), in.size(), 0};
+    bool ok = true;
+    while (ib.pos < ib.size) {
+        OutBuf ob{buf.data(), buf.size(), 0};
+        const size_t r = dec(ds, &ob, &ib);
+        if (iserr(r)) { ok = false; break; }
+        out.insert(out.end(), buf.begin(), buf.begin() + (std::ptrdiff_t)ob.pos);
+    }
+    release(ds);
+    return ok;
+}
+
+// bincode 1.3 default options: little-endian, fixed-width ints, u64 lengths (zip.rs:185 serialize_into):
+//   u64 n; i64 nodes_len[n]; u64 n_paths; repeat { u64 klen; u8 key[klen]; u64 plen; u64 node[plen] }, keys ascending (BTreeMap)
+bool parse_bin_graph(const std::vector<uint8_t>& b, Graph& g) {
+    size_t p = 0;
+    auto rd64 = [&](uint64_t& v) { if (p + 8 > b.size()) return false; memcpy(&v, b.data() + p, 8); p += 8; return true; };
+    uint64_t n = 0, np = 0;
+    if (!rd64(n) || n > (b.size() - p) / 8) return false;
     g.nodes_len.resize(n);
-    f.read(reinterpret_cast<char*>(g.nodes_len.data()), (std::streamsize)(n * 8));
-    uint64_t np = 0;
+    memcpy(g.nodes_len.data(), b.data() + p, n * 8);
+    p += n * 8;
     if (!rd64(np)) return false;
     for (uint64_t i = 0; i < np; ++i) {
         uint64_t kl = 0, pl = 0;
-        if (!rd64(kl)) return false;
-        std::string key(kl, '\0');
-        f.read(key.data(), (std::streamsize)kl);
-        if (!rd64(pl)) return false;
-        std::vector<uint64_t> p(pl);
-        f.read(reinterpret_cast<char*>(p.data()), (std::streamsize)(pl * 8));
-        if (!f) return false;
-        g.paths[key] = std::move(p);
+        if (!rd64(kl) || kl > b.size() - p) return false;
+        std::string key(reinterpret_cast<const char*>(b.data() + p), kl);
+        p += kl;
+        if (!rd64(pl) || pl > (b.size() - p) / 8) return false;
+        std::vector<uint64_t> path(pl);
+        memcpy(path.data(), b.data() + p, pl * 8);
+        p += pl * 8;
+        g.paths[key] = std::move(path);
     }
-    return true;
+    return p == b.size();
+}
+// kind: 0 = .bin, 1 = .bin.lz4, 2 = .bin.zst
+bool read_bin_graph(const std::string& path, Graph& g, int kind = 0) {
+    std::vector<uint8_t> raw, plain;
+    if (!slurp(path, raw)) return false;
+    if (kind == 1) { if (!lz4_frame_decode(raw, plain)) return false; }
+    else if (kind == 2) { if (!zstd_decode(raw, plain)) return false; }
+    else plain.swap(raw);
+    return parse_bin_graph(plain, g);
 }
 
 template <class F>
@@ -221,6 +305,22 @@ int main(int argc, char** argv) {
         else if (a == "--min-depth") o.min_depth = std::stod(next());
         else if (a == "--device") o.device = std::stoi(next());
         else if (a == "--force") o.force = true;
+        else if (a == "--dump-graph") {
+            // reader check without a GPU: parse one graph file (.bin / .bin.lz4 / .bin.zst / .gfa by its extension) and print it
+            const std::string path = next();
+            Graph g;
+            const auto ends = [&](const char* e) { const size_t n = strlen(e); return path.size() >= n && path.compare(path.size() - n, n, e) == 0; };
+            const bool ok = ends(".lz4") ? read_bin_graph(path, g, 1) : ends(".zst") ? read_bin_graph(path, g, 2) : ends(".bin") ? read_bin_graph(path, g, 0)
+                                                                                                                   : read_gfa_graph(path, g);
+            if (!ok) die("cannot read graph " + path);
+            printf("nodes %zu\n", g.nodes_len.size());
+            for (size_t i = 0; i < g.nodes_len.size(); ++i) printf("%lld%c", (long long)g.nodes_len[i], i + 1 == g.nodes_len.size() ? '\n' : ' ');
+            for (auto& kv : g.paths) {
+                printf("path %s %zu\n", kv.first.c_str(), kv.second.size());
+                for (size_t i = 0; i < kv.second.size(); ++i) printf("%llu%c", (unsigned long long)kv.second[i], i + 1 == kv.second.size() ? '\n' : ' ');
+            }
+            return 0;
+        }
         else if (a == "-h" || a == "--help") { usage(); return 0; }
         else die("unknown option " + a);
     }
@@ -392,9 +492,11 @@ int main(int argc, char** argv) {
     std::map<int, Graph> graphs;
     for (int s : chosen) {
         Graph g;
+        // profile.rs:2888-2932: <db>/species_graph_info/<taxid>.bin | .bin.lz4 | .bin.zst (zip.rs:236-262), else <db>/species_gfa/<taxid>.gfa
         const std::string bin = o.db + "/species_graph_info/" + ranges[s].taxid + ".bin";
         const std::string gfa = o.db + "/species_gfa/" + ranges[s].taxid + ".gfa";
-        if (!(exists(bin) && read_bin_graph(bin, g)) && !(exists(gfa) && read_gfa_graph(gfa, g)))
+        if (!(exists(bin) && read_bin_graph(bin, g, 0)) && !(exists(bin + ".lz4") && read_bin_graph(bin + ".lz4", g, 1)) &&
+            !(exists(bin + ".zst") && read_bin_graph(bin + ".zst", g, 2)) && !(exists(gfa) && read_gfa_graph(gfa, g)))
             die("gfa information file for " + ranges[s].taxid + " does not exist. Please check database.");  // profile.rs:2929
         std::vector<uint64_t> off{0}, flat;
         for (auto& kv : g.paths) { flat.insert(flat.end(), kv.second.begin(), kv.second.end()); off.push_back(flat.size()); }

@@ -50,6 +50,14 @@ def make_db(tmp, ds, graphs, gaf):
     for s, (t, _a, _b) in enumerate(ds.ranges()):
         if s == 1:  # one species only as text GFA: exercises the fallback reader (profile.rs:2923-2927)
             write_gfa(os.path.join(db, "species_gfa", f"{t}.gfa"), *graphs[s])
+        elif s == 2:  # compressed forms of the same bincode stream (zip.rs:248-262)
+            from golden.make_graph_fixtures import lz4_frame
+            write_bin(os.path.join(tmp, "g.bin"), *graphs[s])
+            open(os.path.join(db, "species_graph_info", f"{t}.bin.lz4"), "wb").write(lz4_frame(open(os.path.join(tmp, "g.bin"), "rb").read()))
+        elif s == 3:
+            from golden.make_graph_fixtures import zstd_frame
+            write_bin(os.path.join(tmp, "g.bin"), *graphs[s])
+            open(os.path.join(db, "species_graph_info", f"{t}.bin.zst"), "wb").write(zstd_frame(open(os.path.join(tmp, "g.bin"), "rb").read()))
         else:
             write_bin(os.path.join(db, "species_graph_info", f"{t}.bin"), *graphs[s])
     gp = os.path.join(tmp, "gfa_mapped.gaf")
@@ -65,7 +73,7 @@ def test_host_driver_help_runs_without_gpu():
 
 @pytest.mark.gpu
 def test_host_driver_end_to_end_against_oracle(tmp_path):
-    ds = synth.Dataset(404, [30000, 9000, 4000], [6, 3, 1])
+    ds = synth.Dataset(404, [30000, 9000, 4000, 2500], [6, 3, 1, 2])  # .bin, .gfa, .bin.lz4, .bin.zst
     graphs = dataset_graphs(ds)
     gaf = ds.gaf(8, 0, 60000, NASTY)
     db, gp, lens = make_db(str(tmp_path), ds, graphs, gaf)
@@ -159,3 +167,26 @@ def test_host_driver_strain_only_resume_and_stdin(tmp_path):
     assert [l for l in nodes2 if l] == []
     t1 = ds.ranges()[0][0]
     assert open(os.path.join(wd, "strain_inputs", f"{t1}.nodes.tsv")).read() == full[f"{t1}.nodes.tsv"]
+
+
+@pytest.mark.parametrize("ext", ["bin", "bin.lz4", "bin.zst"])
+def test_graph_readers_on_the_bincode_fixtures(ext):
+    """zip.rs:236-262: `.bin` (bincode), `.bin.lz4` (bincode inside an LZ4 frame), `.bin.zst` (bincode inside a zstd frame).
+    The fixtures were written by tests/golden/make_graph_fixtures.py - bincode laid out by hand with struct, independently of
+    the C++ reader - and the reader must return exactly that graph (no GPU involved: --dump-graph)."""
+    import json
+
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "graph_fixture.json")))
+    out = subprocess.run([BIN, "--dump-graph", os.path.join(ROOT, "tests", "golden", "graph_fixture." + ext)], capture_output=True, text=True, check=True).stdout
+    lines = out.split("\n")
+    assert lines[0] == f"nodes {len(g['nodes_len'])}"
+    assert [int(x) for x in lines[1].split()] == g["nodes_len"]
+    got = {}
+    i = 2
+    while i < len(lines) and lines[i].startswith("path "):
+        _p, name, n = lines[i].split(" ")
+        got[name] = [int(x) for x in lines[i + 1].split()]
+        assert len(got[name]) == int(n)
+        i += 2
+    assert list(got) == sorted(g["paths"], key=lambda s: s.encode())  # BTreeMap order
+    assert got == g["paths"]
