@@ -360,6 +360,7 @@ def new_ctx(D, wl, reserve, with_comm):
         ctx.upload_graph(s, g[0], g[1])
     ctx.commit_graphs()
     t_graph = time.perf_counter() - t0
+    ctx.graph_commit_s = ctx.stats().get("graph_commit_ms", 0.0) / 1e3
     if reserve:
         ctx.reserve(reserve)  # before comm_init: sizes the peer-memory id boxes
     if with_comm and D.world > 1:
@@ -532,7 +533,7 @@ def secondary_config(D, args, cudart):
     rf = roofline_block(t, nbytes, walk, p_hit, kernel_name, None)
     out = {"workload": f"BASELINE {wl.key}: {wl.name}, {total} records over {D.world} GPU", "value": total_records * steps / t["dt"], "unit": "records/s",
            "steps": steps, "ms_per_step": 1e3 * t["dt"] / steps, "records_per_gpu": int(t["n_rec"]), "gaf_bytes_per_gpu": int(nbytes),
-           "graph_setup_s": t_graph, "generate_s": t_gen, "roofline": rf, "parity": par, "cpu_baseline": cpu, "gpu_launches": t["launches"]}
+           "graph_setup_s": t_graph, "graph_commit_s": ctx.graph_commit_s, "generate_s": t_gen, "roofline": rf, "parity": par, "cpu_baseline": cpu, "gpu_launches": t["launches"]}
     ctx.close()
     return out
 
@@ -658,6 +659,7 @@ def run_ours(args):
         if not eq_e2e:
             parity["chunked_first_difference"] = where_e2e
 
+    graph_commit_main = ctx.graph_commit_s
     secondary = None
     if not args.no_secondary:
         t_graph_main = t_graph
@@ -676,7 +678,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args, world), "records_per_gpu": int(n_rec), "gaf_bytes_per_gpu": int(nbytes),
                        "l2": f"input text {nbytes / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
-                       "graph_setup_s": t_graph_main, "unique_trios": n_trios_main,
+                       "graph_setup_s": t_graph_main, "graph_commit_s": graph_commit_main, "unique_trios": n_trios_main,
                        "host_cores_rank0": (f"{len(numa_cpus)} cores of the GPU's NUMA node" if numa_cpus else "not restricted"), "timing": "wall clock over K steps between "
                        "barrier+synchronize, max over ranks; kernel times from CUDA events on the library stream"},
             "clocks": t["clocks"], "e2e": e2e, "gpu_launches": t["launches"], "roofline": roofline, "cpu_baseline": cpu, "parity": parity,

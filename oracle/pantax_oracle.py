@@ -630,3 +630,117 @@ def coverage_all_species(
             node_ab=node_ab, trio_ab=trio_ab, error=err,
         )
     return rows, counts, out
+
+
+# --------------------------------------------------------------------------
+# a10 / f2  PAO model rows, second filter, abundance constraint
+#           profile.rs:2699-2813, 1229-1285, 3028-3070
+# --------------------------------------------------------------------------
+def highs_rows_dense(graph: Graph, possible_paths_idx: Sequence[int], node_abundance: Sequence[float], minimization_min_cov: float = 0.0,
+                     fixed_zero: Sequence[int] = ()):
+    """The RowProblem highs_opt builds (profile.rs:2699-2813), literally: a dense nvert x npaths f32 incidence matrix
+    (`coeff_matrix[(v, pos_idx)] = 1.0`), columns x_i (0..1.05 max), binary indicators, one y per node with depth > 0
+    (objective 1/n_y); rows in the order of the `pb.add_row` calls.  Returns (c, A, lo, hi, lb, ub, integer) as numpy arrays.
+    (No node sampling: callers stay below --sample.)"""
+    import numpy as np
+
+    paths = [p for _n, p in graph.sorted_paths()]
+    nvert, npaths = len(node_abundance), len(possible_paths_idx)
+    max_val = max(node_abundance) if len(node_abundance) else float("-inf")
+    coeff = np.zeros((nvert, npaths), dtype=np.float32)
+    for i, path in enumerate(paths):
+        if i in possible_paths_idx:
+            pos = list(possible_paths_idx).index(i)
+            for v in path:
+                coeff[v, pos] = 1.0
+    valid = [v for v, ab in enumerate(node_abundance) if ab > 0.0]
+    n_y = len(valid)
+    ncol = 2 * npaths + n_y
+    c = np.zeros(ncol)
+    lb = np.zeros(ncol)
+    ub = np.full(ncol, np.inf)
+    integer = np.zeros(ncol, dtype=np.int64)
+    for i in range(npaths):
+        ub[i] = 1.05 * max_val
+        ub[npaths + i] = 1.0
+        integer[npaths + i] = 1
+    for k in range(n_y):
+        c[2 * npaths + k] = 1.0 / n_y
+    rows, lo, hi = [], [], []
+
+    def add_row(terms, rlo, rhi):
+        r = np.zeros(ncol)
+        for col, val in terms:
+            r[col] = val
+        rows.append(r)
+        lo.append(rlo)
+        hi.append(rhi)
+
+    for i in range(npaths):
+        add_row([(npaths + i, 1.0), (i, -1.0 / (2.0 * max_val))], -(minimization_min_cov / (2.0 * max_val)), np.inf)
+    add_row([(npaths + i, 1.0) for i in range(npaths)], -np.inf, float(npaths))
+    for k, v in enumerate(valid):
+        coeffs = [(j, float(val)) for j, val in enumerate(coeff[v]) if abs(val) > 1e-12]
+        add_row(coeffs + [(2 * npaths + k, -1.0)], -np.inf, node_abundance[v])
+        add_row(coeffs + [(2 * npaths + k, 1.0)], node_abundance[v], np.inf)
+    for i in fixed_zero:
+        add_row([(i, 1.0)], 0.0, 0.0)
+    return c, np.array(rows), np.array(lo), np.array(hi), lb, ub, integer
+
+
+def second_filter_paths(metrics: List[dict], possible_paths_idx: Sequence[int], orign_n_haps: int, hap2trio_nodes_m_size: int, same_path_flag: bool,
+                        fc: float = 0.46, sr: float = 0.85):
+    """profile.rs:1229-1285 on a list of dicts with the HapMetrics fields; returns (second_opt, second_possible_paths_idx)."""
+    second_opt, keep = False, []
+    if orign_n_haps != 1 and hap2trio_nodes_m_size > 0:
+        second_opt = True
+        for idx in possible_paths_idx:
+            m = metrics[idx]
+            fmean = m.get("frequencies_mean") or 0.0
+            if fmean == 0.0:
+                continue
+            sol = m["first_sol"]
+            f = abs(sol - fmean) / (sol + fmean)
+            fr = round_half_away(f * 100.0) / 100.0
+            m["divergence"] = fr
+            if fr > fc:
+                if fr <= 0.6:
+                    if m["unique_trio_nodes_fraction"] * m["path_cov_ratio"] < sr or sol == 0.0:
+                        continue
+                    m["is_rescue"] = True
+                    keep.append(idx)
+                else:
+                    continue
+            elif fr <= fc and sol != 0.0:
+                keep.append(idx)
+    elif (orign_n_haps != 1 and hap2trio_nodes_m_size == 0 and same_path_flag) or orign_n_haps == 1:
+        m = metrics[0]
+        if m["frequencies_mean"] > 0.0:
+            sol = m["first_sol"]
+            f = abs(sol - m["frequencies_mean"]) / (sol + m["frequencies_mean"])
+            m["divergence"] = round_half_away(f * 100.0) / 100.0
+            m["second_sol"] = sol
+    elif orign_n_haps != 1 and hap2trio_nodes_m_size == 0 and not same_path_flag:
+        for idx in possible_paths_idx:
+            metrics[idx]["second_sol"] = metrics[idx].get("first_sol")
+    return second_opt, keep
+
+
+def abundace_constraint(species_coverage: float, metrics: List[dict]):
+    """profile.rs:3028-3070."""
+    absab = []
+    for m in metrics:
+        if m.get("is_rescue") is True and m.get("first_sol") is not None and m.get("second_sol") is not None:
+            m["second_sol"] = min(m["first_sol"], m["second_sol"])
+        absab.append(m["second_sol"] if m.get("second_sol") is not None else 0.0)
+    total = 0.0
+    for v in absab:
+        total += v
+    diff = abs(total - species_coverage) / ((total + species_coverage) / 2.0)
+    for m in metrics:
+        m["total_cov_diff"] = diff
+    if absab and max(absab) > 1.05 * species_coverage:
+        factor = species_coverage / total
+        for m in metrics:
+            if not (m.get("is_rescue") or False) and m.get("second_sol") is not None:
+                m["second_sol"] = m["second_sol"] * factor

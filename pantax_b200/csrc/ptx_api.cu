@@ -129,6 +129,7 @@ struct ptx_ctx {
     // graph
     GraphDev g;
     bool graphs_committed = false;
+    double commit_ms = 0;  // wall time of the last ptx_commit_graphs (host concatenation + upload + path marks + trio table)
     // accumulators independent of the graph
     unsigned long long* d_hist = nullptr;
     unsigned long long* d_hist_g = nullptr;  // all-reduced copy (multi-GPU)
@@ -1176,6 +1177,7 @@ int ptx_commit_graphs(ptx_ctx* ctx) {
     if (!ctx) return PTX_E_INVALID;
     if (ctx->graphs_committed) return fail(ctx, PTX_E_STATE, "graphs already committed");
     cudaSetDevice(ctx->device);
+    const auto t_commit0 = std::chrono::steady_clock::now();
     const int S = (int)ctx->sp.size();
     GraphDev& g = ctx->g;
     int64_t N = 0, Htot = 0, P = 0;
@@ -1196,7 +1198,6 @@ int ptx_commit_graphs(ptx_ctx* ctx) {
     std::vector<uint64_t> poff((size_t)Htot + 1);
     std::vector<int64_t> node_base(S, -1);
     uint64_t bits = 0;
-    int64_t max_paths = 0;
     {
         int64_t h = 0;
         uint64_t k = 0;
@@ -1204,7 +1205,6 @@ int ptx_commit_graphs(ptx_ctx* ctx) {
             SpeciesHost& sp = ctx->sp[s];
             if (!sp.uploaded) continue;
             node_base[s] = sp.node_base;
-            max_paths = std::max(max_paths, sp.n_paths);
             for (int64_t i = 0; i < sp.n_nodes; ++i) {
                 len[sp.node_base + i] = sp.len[i];
                 bit_off[sp.node_base + i] = bits;
@@ -1234,34 +1234,27 @@ int ptx_commit_graphs(ptx_ctx* ctx) {
     CU(cudaMemcpyAsync(g.poff, poff.data(), (Htot + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(ctx->d_node_base, node_base.data(), S * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
 
-    // ---- distinct-node marks per path: round r handles the r-th path of every species
-    uint32_t* stamp = nullptr;
-    uint32_t* d_round = nullptr;
-    if ((rc = dalloc(ctx, &stamp, N)) || (rc = dalloc(ctx, &d_round, std::max<int64_t>(Htot, 1), false))) return rc;
-    {
-        std::vector<uint32_t> round_list;
-        std::vector<std::pair<uint32_t, uint32_t>> rounds;  // offset, count
-        std::vector<uint64_t> round_max;
-        for (int64_t r = 0; r < max_paths; ++r) {
-            uint32_t off = (uint32_t)round_list.size();
-            uint64_t mx = 0;
-            for (auto& sp : ctx->sp)
-                if (sp.uploaded && r < sp.n_paths) {
-                    round_list.push_back((uint32_t)(sp.hap_base + r));
-                    mx = std::max<uint64_t>(mx, sp.path_off[r + 1] - sp.path_off[r]);
+    // ---- distinct-node marks per path: one bit per (path, node of its species), one launch for all paths
+    uint64_t* d_pbm_off = nullptr;
+    uint32_t* d_pbase = nullptr;
+    uint32_t* d_pbm = nullptr;
+    if (Htot > 0 && P > 0) {
+        std::vector<uint64_t> pbm_off((size_t)Htot + 1, 0);
+        std::vector<uint32_t> pbase((size_t)Htot, 0);
+        int64_t h = 0;
+        for (auto& sp : ctx->sp)
+            if (sp.uploaded)
+                for (int64_t p = 0; p < sp.n_paths; ++p, ++h) {
+                    pbase[(size_t)h] = (uint32_t)sp.node_base;
+                    pbm_off[(size_t)h + 1] = pbm_off[(size_t)h] + (uint64_t)((sp.n_nodes + 31) / 32);
                 }
-            rounds.push_back({off, (uint32_t)round_list.size() - off});
-            round_max.push_back(mx);
-        }
-        if (!round_list.empty()) CU(cudaMemcpyAsync(d_round, round_list.data(), round_list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->st));
-        CU(cudaStreamSynchronize(ctx->st));  // host vectors above must outlive the copies
-        for (size_t r = 0; r < rounds.size(); ++r) {
-            // gridDim.y <= 65535
-            for (uint32_t o = 0; o < rounds[r].second; o += 65535u) {
-                uint32_t cnt = std::min<uint32_t>(65535u, rounds[r].second - o);
-                if (round_max[r] > 0) launch_mark_path_dups(g.pnode, g.poff, d_round + rounds[r].first + o, cnt, round_max[r], stamp, ctx->st);
-            }
-        }
+        if ((rc = dalloc(ctx, &d_pbm_off, (size_t)Htot + 1, false)) || (rc = dalloc(ctx, &d_pbase, (size_t)Htot, false)) ||
+            (rc = dalloc(ctx, &d_pbm, (size_t)pbm_off[(size_t)Htot] + 1)))
+            return rc;
+        CU(cudaMemcpyAsync(d_pbm_off, pbm_off.data(), ((size_t)Htot + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaMemcpyAsync(d_pbase, pbase.data(), (size_t)Htot * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->st));
+        launch_mark_path_dups(g.pnode, g.poff, Htot, P, d_pbm_off, d_pbase, d_pbm, ctx->st);
+        CU(cudaStreamSynchronize(ctx->st));  // the host vectors above must outlive the copies
     }
     launch_path_len_sum(g.pnode, g.poff, Htot, P, g.len, g.path_len_sum, ctx->st);
 
@@ -1312,8 +1305,9 @@ int ptx_commit_graphs(ptx_ctx* ctx) {
     }
     CU(cudaStreamSynchronize(ctx->st));
     CU(cudaGetLastError());
-    dfree(stamp);
-    dfree(d_round);
+    dfree(d_pbm_off);
+    dfree(d_pbase);
+    dfree(d_pbm);
     // per-species trio slices: trios are ordered by (global hap, position) and haps are grouped by species
     std::vector<uint64_t> tstart((size_t)Htot + 1, 0);
     if (g.T > 0) CU(cudaMemcpy(tstart.data(), g.trio_start, (Htot + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
@@ -1328,6 +1322,7 @@ int ptx_commit_graphs(ptx_ctx* ctx) {
             // path_off is kept (tiny) for ptx_species_paths consumers
         }
     ctx->graphs_committed = true;
+    ctx->commit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_commit0).count();
     for (auto& ch : ctx->chunks) ch.covered = false;
     if (!ctx->chunks.empty()) ctx->dirty = true;
     return PTX_OK;
@@ -2125,10 +2120,10 @@ int ptx_stats_json(ptx_ctx* ctx, char* buf, size_t cap) {
     snprintf(buf, cap,
              "{\"records\": %lld, \"chunks\": %zu, \"text_bytes\": %zu, \"nodes\": %lld, \"paths\": %lld, \"path_steps\": %lld, "
              "\"unique_trios\": %lld, \"bit_words\": %llu, \"id_set_slots\": %llu, \"ids_unique\": %d, \"mixed_groups\": %d, "
-             "\"count_ms\": %.4f, \"ingest_ms\": %.4f, \"apply_ms\": %.4f, \"ingest_launches\": %zu, \"finalize_ms\": %.4f, \"kernel_launches\": %lld, \"ranks\": %d, \"p2p_boxes\": %d, \"table_allocs\": %lld, \"text_buffers_released\": %zu, \"text_bytes_resident\": %zu}",
+             "\"count_ms\": %.4f, \"ingest_ms\": %.4f, \"apply_ms\": %.4f, \"ingest_launches\": %zu, \"finalize_ms\": %.4f, \"kernel_launches\": %lld, \"ranks\": %d, \"p2p_boxes\": %d, \"table_allocs\": %lld, \"text_buffers_released\": %zu, \"text_bytes_resident\": %zu, \"graph_commit_ms\": %.3f}",
              (long long)ctx->total_records, ctx->chunks.size(), text, (long long)ctx->g.N, (long long)ctx->g.Htot, (long long)ctx->g.P,
              (long long)ctx->g.T, (unsigned long long)ctx->g.n_bit_words, (unsigned long long)ctx->ds_cap, ctx->h_flags[0] == 0 ? 1 : 0,
-             ctx->h_flags[1] != 0 ? 1 : 0, ev_sum(ctx->ev_count), ev_sum(ctx->ev_ingest), ev_sum(ctx->ev_apply), ctx->ev_ingest.size(), ev_sum(ctx->ev_final), (long long)kernel_launch_count(), ctx->n_ranks, ctx->p2p ? 1 : 0, (long long)ctx->n_table_allocs, ctx->text_pool.size(), text_resident);
+             ctx->h_flags[1] != 0 ? 1 : 0, ev_sum(ctx->ev_count), ev_sum(ctx->ev_ingest), ev_sum(ctx->ev_apply), ctx->ev_ingest.size(), ev_sum(ctx->ev_final), (long long)kernel_launch_count(), ctx->n_ranks, ctx->p2p ? 1 : 0, (long long)ctx->n_table_allocs, ctx->text_pool.size(), text_resident, ctx->commit_ms);
     return PTX_OK;
 }
 

@@ -150,8 +150,8 @@ void launch_ds_merge_boxes(const ulonglong2* inbox, const unsigned long long* of
 void launch_ds_apply_mixed(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, cudaStream_t st);
 
 // graph commit
-void launch_mark_path_dups(uint32_t* pnode, const uint64_t* poff, const uint32_t* round_paths, uint32_t n_round_paths,
-                           uint64_t max_len, uint32_t* stamp, cudaStream_t st);
+void launch_mark_path_dups(uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, const uint64_t* pbm_off, const uint32_t* pbase, uint32_t* bm,
+                           cudaStream_t st);
 void launch_path_len_sum(const uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, const uint32_t* len,
                          unsigned long long* out, cudaStream_t st);
 void launch_trio_count(const uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, uint4* keys, uint32_t* cnt,

@@ -1546,15 +1546,19 @@ __device__ __forceinline__ int64_t path_of_step(const uint64_t* __restrict__ pof
     return a - 1;
 }
 
-// One launch handles at most one path per species, so the stamps of different paths never mix.
-__global__ void __launch_bounds__(256) k_mark_path_dups(uint32_t* pnode, const uint64_t* __restrict__ poff,
-                                                        const uint32_t* __restrict__ round_paths, uint32_t* stamp) {
-    const uint32_t h = round_paths[blockIdx.y];
-    const uint64_t s = poff[h], e = poff[h + 1];
-    for (uint64_t k = s + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < e; k += (uint64_t)gridDim.x * blockDim.x) {
+// Distinct-node marks of every path in ONE launch: a bit per (path, node of the path's species) - set with atomicOr; the visit
+// that finds its bit already set is a repeat and gets bit 31 of its pnode entry (which of two visits of a node stays unmarked
+// does not matter: the sums over distinct nodes are order-free).  pbm_off[h] = first bitmap word of path h, pbase[h] = first
+// global node index of its species.  Round 1 launched one kernel per path rank (thousands at 5,000 paths per species).
+__global__ void __launch_bounds__(256) k_mark_path_dups(uint32_t* pnode, const uint64_t* __restrict__ poff, int64_t Htot, int64_t P,
+                                                        const uint64_t* __restrict__ pbm_off, const uint32_t* __restrict__ pbase, uint32_t* bm) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < (uint64_t)P; k += (uint64_t)gridDim.x * blockDim.x) {
+        const int64_t h = path_of_step(poff, Htot, k);
         const uint32_t g = pnode[k] & 0x7FFFFFFFu;
-        const uint32_t old = atomicExch(stamp + g, h + 1u);
-        if (old == h + 1u) pnode[k] = g | 0x80000000u;  // node already met in this path
+        const uint32_t loc = g - pbase[h];
+        const uint32_t bit = 1u << (loc & 31u);
+        const uint32_t old = atomicOr(bm + pbm_off[h] + (loc >> 5), bit);
+        if (old & bit) pnode[k] = g | 0x80000000u;  // node already met in this path
     }
 }
 
@@ -2312,10 +2316,10 @@ void launch_ninfo_full(uint4* ninfo, uint8_t* full, int64_t N, int mode, cudaStr
     k_ninfo_full<<<(uint32_t)((N + 255) / 256), 256, 0, st>>>(ninfo, full, N, mode);
     PTX_LAUNCHED();
 }
-void launch_mark_path_dups(uint32_t* pnode, const uint64_t* poff, const uint32_t* round_paths, uint32_t n_round_paths, uint64_t max_len,
-                           uint32_t* stamp, cudaStream_t st) {
-    dim3 grid(grid_for(max_len, 256, 1024), n_round_paths);
-    k_mark_path_dups<<<grid, 256, 0, st>>>(pnode, poff, round_paths, stamp);
+void launch_mark_path_dups(uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, const uint64_t* pbm_off, const uint32_t* pbase, uint32_t* bm,
+                           cudaStream_t st) {
+    if (P <= 0) return;
+    k_mark_path_dups<<<grid_for((uint64_t)P, 256), 256, 0, st>>>(pnode, poff, Htot, P, pbm_off, pbase, bm);
     PTX_LAUNCHED();
 }
 void launch_path_len_sum(const uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, const uint32_t* val, unsigned long long* out,
