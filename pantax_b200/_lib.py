@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpantax_gpu.so")
+LIB_PATH = os.environ.get("PANTAX_GPU_LIB") or os.path.join(HERE, "libpantax_gpu.so")  # (override: A/B measurements of builds)
 
 ERRORS = {
     0: "PTX_OK", -1: "PTX_E_INVALID", -2: "PTX_E_CUDA", -3: "PTX_E_NOMEM", -4: "PTX_E_STATE", -5: "PTX_E_NODE_ORDER",

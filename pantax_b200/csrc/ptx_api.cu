@@ -149,7 +149,9 @@ struct ptx_ctx {
     int force_tile = 0;  // PTX_TILE_BYTES env override for single-pass chunks of k_ingest_s (multiple of 512)
     bool keep_text = false;  // PTX_KEEP_TEXT=1: never hand the text of resolved chunks back (debugging)
     bool no_sort = false;    // PTX_NO_SORT=1: k_ingest_s keeps file order inside a tile (measurements)
+    int l2_hints = 1;        // PTX_L2_HINTS: bit 0 = graph arrays evict-last (k_apply 0.969 -> 0.938 ms), bit 1 = GAF text evict-first (no gain), bit 2 = id-set loads evict-first (slower: 1.00 ms); IngestArgs::pol_*
     bool old_short = false;  // PTX_OLD_INGEST=1: round 1's byte-at-a-time short-read kernel (A/B measurements)
+    bool long_new = true;    // PTX_LONG_NEW=0: round 1's k_ingest<long> (warp-cooperative walk decode) instead of k_ingest_l (A/B measurements: 1.66 vs 1.40 ms on configs[2])
     int force_long = -1; // PTX_LONG_MODE env override: 0/1 = never/always use the long-line kernel (tests)
     int64_t test_box_cap = 0;  // PTX_TEST_BOX_CAP env: first outbox capacity (tests force the overflow/restart path of the exchange)
     uint64_t* d_total = nullptr;  // scratch scalar
@@ -331,6 +333,7 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.over_bytes = ch.over_bytes;
     a.no_sort = ctx->no_sort ? 1u : 0u;
     a.old_short = ctx->old_short ? 1u : 0u;
+    a.long_new = ctx->long_new ? 1u : 0u;
     a.long_mode = ch.long_mode;
     a.micro_base = ch.tile_base;
     a.labels = ch.labels;
@@ -353,6 +356,9 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.ds_shift = 64 - log2_ceil(ctx->ds_cap);
     a.ds_mask = ctx->ds_cap - 1;
     a.scatter_var = (uint32_t)pick_scatter_variant(ctx);
+    a.pol_keep = (ctx->l2_hints & 1) ? 0x14F0000000000000ull : 0x1000000000000000ull;    // createpolicy evict_last / evict_normal, fraction 1.0
+    a.pol_stream = (ctx->l2_hints & 2) ? 0x12F0000000000000ull : 0x1000000000000000ull;  // evict_first
+    a.pol_ds = (ctx->l2_hints & 4) ? 0x12F0000000000000ull : 0x1000000000000000ull;
     a.pair_key = ctx->d_pair_key;
     a.pair_val = ctx->d_pair_val;
     a.flags = ctx->d_flags;
@@ -1045,9 +1051,11 @@ int ptx_create(int device, ptx_ctx** out) {
     if (const char* e = getenv("PTX_TILE_ROWS")) ctx->force_rows = atoi(e);
     if (const char* e = getenv("PTX_TILE_BYTES")) ctx->force_tile = atoi(e);
     if (const char* e = getenv("PTX_OLD_INGEST")) ctx->old_short = atoi(e) != 0;
+    if (const char* e = getenv("PTX_LONG_NEW")) ctx->long_new = atoi(e) != 0;
     if (const char* e = getenv("PTX_NO_SORT")) ctx->no_sort = atoi(e) != 0;
     if (const char* e = getenv("PTX_KEEP_TEXT")) ctx->keep_text = atoi(e) != 0;
     if (const char* e = getenv("PTX_SCATTER")) ctx->scatter_var = atoi(e);
+    if (const char* e = getenv("PTX_L2_HINTS")) ctx->l2_hints = atoi(e);
     if (const char* e = getenv("PTX_LONG_MODE")) ctx->force_long = atoi(e) ? 1 : 0;
     if (const char* e = getenv("PTX_TEST_BOX_CAP")) ctx->test_box_cap = atoll(e);
     if (const char* e = getenv("PTX_NO_SINGLE_PASS")) ctx->single_pass_ok = atoi(e) == 0;

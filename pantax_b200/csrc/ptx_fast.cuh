@@ -7,7 +7,7 @@
 //   * SWAR decimal conversion (four digits per multiply-add pair: swar4) and word-wise id hashing,
 // and touches no byte individually.  It accepts the records whose columns have the plain shape every aligner
 // writes - 12+ tab-separated columns, integer columns that are 1-8 unsigned digits or any non-numeric text
-// ('*' = null), walk ids of at most 9 digits, at most `stash_cap` walk nodes, "\n" line ends - and reports
+// ('*' = null), walk ids of at most 9 digits, "\n" line ends - and reports
 // everything else (signs, 9+ digit integers, 10+ digit ids, "\r\n", fewer than 12 columns, lines that leave the
 // staged window) as "not handled"; those records go through parse_record, which stays the definition of the
 // dialect.  On a record it accepts, fast_parse returns exactly what parse_record returns
@@ -49,10 +49,38 @@ PTX_HD uint32_t nondigit_mask4(uint32_t w) {  // bytes outside '0'..'9'
 // four different residue classes mod 4), so nothing carries.
 PTX_HD uint32_t pack8(uint32_t m03, uint32_t m47) { return ((m47 | (m03 >> 4)) * 0x00204081u) >> 24; }
 
-// newline and tab flags of one 16-byte piece of text, bit i = byte i
-PTX_HD void classify16(uint32_t x, uint32_t y, uint32_t z, uint32_t w, uint32_t& nl16, uint32_t& tab16) {
+// sixteen 0x80-per-byte flags (four mask words, text order) -> 16 bits, bit i = byte i.  Four dot products weigh the flags
+// (128 * 2^i per byte, the second word of a pair 16 times as much), one multiply-add joins the halves: IDP.4A and IMAD run
+// on the FMA pipe, beside the LOP3/IADD3 stream that forms the masks.
+PTX_HD uint32_t dot4(uint32_t flags, uint32_t weights, uint32_t acc) {
+#if defined(__CUDA_ARCH__)
+    return __dp4a(flags, weights, acc);
+#else
+    for (int i = 0; i < 4; ++i) acc += ((flags >> (8 * i)) & 0xFFu) * ((weights >> (8 * i)) & 0xFFu);
+    return acc;
+#endif
+}
+PTX_HD uint32_t pack16(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    const uint32_t lo = dot4(b, 0x80402010u, dot4(a, 0x08040201u, 0u)), hi = dot4(d, 0x80402010u, dot4(c, 0x08040201u, 0u));
+    return (hi * 256u + lo) >> 7;
+}
+// bytes equal to the 7-bit byte replicated in `rep`: 0x80 flags (w7 = w & 0x7f7f7f7f, shared between the classes)
+PTX_HD uint32_t eq7_mask4(uint32_t w, uint32_t w7, uint32_t rep) { return ~((w7 ^ rep) + 0x7f7f7f7fu) & ~w & 0x80808080u; }
+
+PTX_HD void classify16_mul(uint32_t x, uint32_t y, uint32_t z, uint32_t w, uint32_t& nl16, uint32_t& tab16) {  // multiply-packed (A/B)
     nl16 = pack8(eq_mask4(x, 0x0a0a0a0au), eq_mask4(y, 0x0a0a0a0au)) | (pack8(eq_mask4(z, 0x0a0a0a0au), eq_mask4(w, 0x0a0a0a0au)) << 8);
     tab16 = pack8(eq_mask4(x, 0x09090909u), eq_mask4(y, 0x09090909u)) | (pack8(eq_mask4(z, 0x09090909u), eq_mask4(w, 0x09090909u)) << 8);
+}
+// newline and tab flags of one 16-byte piece of text, bit i = byte i
+PTX_HD void classify16(uint32_t x, uint32_t y, uint32_t z, uint32_t w, uint32_t& nl16, uint32_t& tab16) {
+    const uint32_t x7 = x & 0x7f7f7f7fu, y7 = y & 0x7f7f7f7fu, z7 = z & 0x7f7f7f7fu, w7 = w & 0x7f7f7f7fu;
+    nl16 = pack16(eq7_mask4(x, x7, 0x0a0a0a0au), eq7_mask4(y, y7, 0x0a0a0a0au), eq7_mask4(z, z7, 0x0a0a0a0au), eq7_mask4(w, w7, 0x0a0a0a0au));
+    tab16 = pack16(eq7_mask4(x, x7, 0x09090909u), eq7_mask4(y, y7, 0x09090909u), eq7_mask4(z, z7, 0x09090909u), eq7_mask4(w, w7, 0x09090909u));
+}
+
+// non-digit flags of one 16-byte piece (the long-read kernel finds the ends of the walk ids from them), bit i = byte i
+PTX_HD uint32_t nondigit16(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    return pack16(nondigit_mask4(x), nondigit_mask4(y), nondigit_mask4(z), nondigit_mask4(w));
 }
 
 // ---- the staged window as aligned 32-bit words (little endian).  On the device it lives in shared memory and is read
@@ -149,11 +177,11 @@ PTX_HD uint32_t fast_int(const Words& W, uint32_t a, uint32_t b, uint32_t null_b
     return isnull ? 0u : swar4(xl) * 10000u + swar4(xh);
 }
 
-// Columns 1..12 of the line [s, e] of the window, e = position of the '\n' that ends it.  lim = bytes of text in the
-// window (the tab bitmap covers exactly those, then a sentinel word of all ones; the text is readable 128 bytes beyond).
-// `mask` = lanes that call this together.  Returns false if the record needs the exact parser.
-PTX_HD bool fast_parse(const Words& W, const Words& tabw, uint32_t s, uint32_t e, uint32_t lim, FastRec& r, uint32_t mask,
-                       uint32_t* stash, uint32_t stash_stride, uint32_t stash_cap) {
+// Columns 1-5 and 7-12 of the line [s, e] of the window, e = position of the '\n' that ends it: id hash, the five integer
+// columns, the extent of column 6.  lim = bytes of text in the window (the tab bitmap covers exactly those, then a sentinel
+// word of all ones; the text is readable 128 bytes beyond).  Returns ok (12 columns inside the window, "\n" line end);
+// `slow` gets bit 0 if an integer column needs the exact parser.  `mask` = lanes that call this together.
+PTX_HD bool fast_cols(const Words& W, const Words& tabw, uint32_t s, uint32_t e, uint32_t lim, FastRec& r, uint32_t mask, uint32_t& slow) {
     BitCursor tc;
     tc.seek(tabw, s);
     const uint32_t t1 = tc.next(), t2 = tc.next();
@@ -175,7 +203,6 @@ PTX_HD bool fast_parse(const Words& W, const Words& tabw, uint32_t s, uint32_t e
     r.path_null = false;
     r.h.lo = 1;
     r.h.hi = 0;
-    uint32_t slow = 0;
 #if defined(__CUDA_ARCH__)
     const uint32_t okmask = __ballot_sync(mask, ok);  // the lanes that go through the columns together
 #else
@@ -198,10 +225,37 @@ PTX_HD bool fast_parse(const Words& W, const Words& tabw, uint32_t s, uint32_t e
         r.c8 = fast_int(W, t7 + 1u, t8, FN_C8, r.nulls, slow);
         r.c9 = fast_int(W, t8 + 1u, t9, FN_C9, r.nulls, slow);
         r.mapq = fast_int(W, t11 + 1u, t12 < e ? t12 : e, FN_MAPQ, r.nulls, slow);
+        r.path_null = (t6 - t5 - 1u == 1u) && ((ld4(W, t5 + 1u) & 0xFFu) == (uint32_t)'*');
+    }
+    PTX_RECONVERGE(mask);
+    return ok;
+}
+
+// One walk id of n (1..9) digits starting at byte a -> its value (ids < 10^9)
+PTX_HD uint32_t fast_node(const Words& W, uint32_t a, uint32_t n) {
+    uint32_t top = 0, n8 = n;
+    if (n > 8u) {  // rare
+        top = ((ld4(W, a) & 0xFFu) - (uint32_t)'0') * 100000000u;
+        ++a;
+        n8 = 8u;
+    }
+    uint32_t lo, hi, xl, xh;
+    ld8(W, a, lo, hi);
+    align8(lo ^ 0x30303030u, hi ^ 0x30303030u, n8, xl, xh);
+    return top + swar4(xl) * 10000u + swar4(xh);
+}
+
+// Columns 1..12 of the line [s, e] with the walk decoded by the calling thread (the short-read kernel: a handful of nodes
+// per record).  Returns false if the record needs the exact parser.  Only the first stash_cap walk ids are stashed; W,
+// vmin and vmax cover the whole walk (the caller decodes a longer walk again when it writes it out).
+PTX_HD bool fast_parse(const Words& W, const Words& tabw, uint32_t s, uint32_t e, uint32_t lim, FastRec& r, uint32_t mask,
+                       uint32_t* stash, uint32_t stash_stride, uint32_t stash_cap) {
+    uint32_t slow = 0;
+    const bool ok = fast_cols(W, tabw, s, e, lim, r, mask, slow);
+    if (ok) {
         // column 6: every non-digit byte (the closing tab included) ends the digit run in front of it
-        const uint32_t p6 = t5 + 1u, e6 = t6;
-        r.path_null = (e6 - p6 == 1u) && ((ld4(W, p6) & 0xFFu) == (uint32_t)'*');
-        uint32_t last_sep = t5, Wn = 0, vmin = 0xFFFFFFFFu, vmax = 0;
+        const uint32_t p6 = r.path_pos, e6 = r.path_end;
+        uint32_t last_sep = p6 - 1u, Wn = 0, vmin = 0xFFFFFFFFu, vmax = 0;
         for (uint32_t p = p6; p <= e6; p += 32u) {
             const uint32_t nbits = (e6 - p + 1u) < 32u ? (e6 - p + 1u) : 32u;  // bytes of [p6, e6] in this segment
             uint32_t nd = 0;
@@ -211,7 +265,7 @@ PTX_HD bool fast_parse(const Words& W, const Words& tabw, uint32_t s, uint32_t e
                 uint32_t wa = W.at(o);
                 for (uint32_t j = 0; j < nbits; j += 8u, o += 8u) {
                     const uint32_t wb = W.at(o + 4u), wc = W.at(o + 8u);
-                    nd |= pack8(nondigit_mask4(funnel_r(wa, wb, sh)), nondigit_mask4(funnel_r(wb, wc, sh))) << j;
+                    nd |= (dot4(nondigit_mask4(funnel_r(wb, wc, sh)), 0x80402010u, dot4(nondigit_mask4(funnel_r(wa, wb, sh)), 0x08040201u, 0u)) >> 7) << j;
                     wa = wc;
                 }
             }
@@ -220,20 +274,12 @@ PTX_HD bool fast_parse(const Words& W, const Words& tabw, uint32_t s, uint32_t e
                 const uint32_t q = p + ffs32(nd);
                 nd &= nd - 1u;
                 const uint32_t n = q - last_sep - 1u;
-                uint32_t a = last_sep + 1u;
+                const uint32_t a = last_sep + 1u;
                 last_sep = q;
                 if (n) {
-                    uint32_t top = 0, n8 = n;
-                    if (n > 8u) {  // rare: 9 digits are read here; ids of 10-18 digits are valid too, the exact parser reads those
-                        slow |= n > 9u ? 1u : 0u;
-                        top = ((ld4(W, a) & 0xFFu) - (uint32_t)'0') * 100000000u;
-                        ++a;
-                        n8 = 8u;
-                    }
-                    uint32_t lo, hi, xl, xh;
-                    ld8(W, a, lo, hi);
-                    align8(lo ^ 0x30303030u, hi ^ 0x30303030u, n8, xl, xh);
-                    const uint32_t v = top + swar4(xl) * 10000u + swar4(xh);
+                    // ids of up to 9 digits; 10-18 digit ids are valid too: the exact parser reads those
+                    slow |= n > 9u ? 1u : 0u;
+                    const uint32_t v = fast_node(W, a, n < 9u ? n : 9u);
                     vmin = v < vmin ? v : vmin;
                     vmax = v > vmax ? v : vmax;
                     if (Wn < stash_cap) stash[Wn * stash_stride] = v;
@@ -241,13 +287,11 @@ PTX_HD bool fast_parse(const Words& W, const Words& tabw, uint32_t s, uint32_t e
                 }
             }
         }
-        PTX_RECONVERGE(okmask);  // (never inside the loops: their trip counts differ from lane to lane)
-        slow |= Wn > stash_cap ? 1u : 0u;  // longer walk than the stash: the exact parser decodes it again when it is written out
         r.W = Wn;
         r.vmin = vmin;
         r.vmax = vmax;
     }
-    PTX_RECONVERGE(mask);
+    PTX_RECONVERGE(mask);  // (never inside the loops: their trip counts differ from lane to lane)
     return ok && slow == 0u;
 }
 

@@ -22,13 +22,26 @@ constexpr uint32_t MAX_TILE = MAX_ROWS * MICRO;
 constexpr uint32_t OVER = 2048;
 constexpr uint32_t PRE = 256;  // keeps `text` 256-byte aligned inside a cudaMalloc'ed buffer
 constexpr int INGEST_THREADS = 256;
-constexpr int SHORT_THREADS = 128;       // k_ingest_s: small CTAs, 7 per SM - the barriers between its phases overlap across CTAs
-constexpr uint32_t SHORT_REC_CAP = 512;  // k_ingest_s: line starts kept in smem per round
+#ifndef PTX_SHORT_THREADS
+#define PTX_SHORT_THREADS 128
+#endif
+constexpr int SHORT_THREADS = PTX_SHORT_THREADS;       // k_ingest_s: small CTAs, 7 per SM - the barriers between its phases overlap across CTAs
+#ifndef PTX_SHORT_RECCAP
+#define PTX_SHORT_RECCAP 512
+#endif
+constexpr uint32_t SHORT_REC_CAP = PTX_SHORT_RECCAP;  // k_ingest_s: line starts kept in smem per round
 constexpr uint32_t REC_CAP = 1024;  // record starts kept in smem per round
 constexpr double LONG_LINE_BYTES = 320.0;  // mean line length from which a chunk is parsed by k_ingest<LONG>
 constexpr uint32_t HIST_SLOTS_LOG2 = 7;  // per-tile species-count accumulators in shared memory (multi-species runs)
 constexpr uint32_t HIST_SLOTS = 1u << HIST_SLOTS_LOG2;
 constexpr uint64_t BITS_SLICE_PAD = 4 * 64;  // spare bitmap words: n_bit_words rounded up to n_ranks slices of a multiple of 4 words (<= 64 ranks)
+#ifndef PTX_SHORT_STASH
+#define PTX_SHORT_STASH 16
+#endif
+#ifndef PTX_SHORT_MINB
+#define PTX_SHORT_MINB 7
+#endif
+constexpr uint32_t SHORT_STASH_CAP = PTX_SHORT_STASH;  // k_ingest_s: walk nodes per record kept in smem (a longer walk is decoded again at write-out).  7 CTAs per SM: measured faster than 8 (1.05 vs 1.34 ms) and than 6 (1.12 ms)
 constexpr uint32_t STASH_CAP = 16;  // walk nodes per record kept in smem between the parse and the coverage pass
 
 // record-table flags (IngestArgs::meta_b[e].y): walk length in the low 24 bits
@@ -83,6 +96,7 @@ struct IngestArgs {
     uint32_t over_bytes;         // k_ingest_s: bytes staged behind the tile (the tail of its last line): 512..OVER, multiple of 512
     uint32_t no_sort;            // k_ingest_s: keep the lines of a tile in file order (PTX_NO_SORT=1, measurements)
     uint32_t long_mode;          // long lines: warp-cooperative walk decode (k_ingest<true>)
+    uint32_t long_new;           // PTX_LONG_NEW=1: k_ingest_l instead of k_ingest<true> for long lines (measurements)
     uint32_t old_short;          // PTX_OLD_INGEST=1: the byte-at-a-time short-read kernel of round 1 (A/B measurements)
     const uint64_t* micro_base;  // [n_micro] exclusive record prefix per micro-tile within the chunk, from the count pass.
                                  // null = SINGLE-PASS mode: no count pass ran, rows are numbered later from tile_info/row_key
@@ -127,6 +141,10 @@ struct IngestArgs {
     const uint4* tt;
     uint32_t tt_mask;
     unsigned long long* trio_bases;
+    // L2 eviction policies (createpolicy encodings) of the two kinds of traffic: what is read once - GAF text, record table,
+    // id-set slots - is fetched evict-first, the graph arrays every read gathers from (ninfo, bases, bitmap, trio table)
+    // evict-last, so that 1.7 GB of streams per step do not push 30 MB of node arrays out of the L2
+    uint64_t pol_keep, pol_stream, pol_ds;
 };
 
 // launchers (ptx_kernels.cu); all asynchronous on `st`

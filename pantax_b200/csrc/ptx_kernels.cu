@@ -40,6 +40,12 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst_smem)),
@@ -79,6 +85,23 @@ __device__ __forceinline__ ulonglong2 ld128(const ulonglong2* p) {
     ulonglong2 v;
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
     return v;
+}
+// ---- the same accesses with an L2 eviction policy (IngestArgs::pol_keep / pol_stream); atom.cas takes none
+__device__ __forceinline__ ulonglong2 ld128_hint(const ulonglong2* p, uint64_t pol) {
+    ulonglong2 v;
+    asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_v4_hint(const uint4* p, uint64_t pol) {
+    uint4 w;
+    asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p), "l"(pol) : "memory");
+    return w;
+}
+__device__ __forceinline__ void red_add64_hint(unsigned long long* p, unsigned long long v, uint64_t pol) {
+    asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_or32_hint(uint32_t* p, uint32_t v, uint64_t pol) {
+    asm volatile("red.relaxed.gpu.global.or.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 
 // 0x80 in every byte of w that equals '\n'
@@ -149,12 +172,12 @@ __device__ __forceinline__ uint64_t ds_home(const IdHash& h, uint32_t shift) {
 // profile.rs:369-378 (uniqueness over all non-U rows) + :406-437 (species set per id group,
 // over coverage-eligible rows only).
 __device__ __forceinline__ void ds_insert(ulonglong2* slots, uint32_t shift, uint64_t mask, const IdHash& h, bool eligible,
-                                          uint32_t label, uint32_t* flags) {
+                                          uint32_t label, uint32_t* flags, uint64_t pol) {
     const uint64_t hi_part = (uint64_t)h.hi << 32;
     const ulonglong2 mine = make_ulonglong2(h.lo, hi_part | (eligible ? label : DS_NONE));
     uint64_t i = ds_home(h, shift);
     for (;;) {
-        ulonglong2 cur = ld128(slots + i);
+        ulonglong2 cur = ld128_hint(slots + i, pol);
         if (cur.x == 0ull && cur.y == 0ull) {
             cur = atomic_cas128(slots + i, make_ulonglong2(0ull, 0ull), mine);
             if (cur.x == 0ull && cur.y == 0ull) return;  // inserted
@@ -181,10 +204,10 @@ __device__ __forceinline__ void ds_insert(ulonglong2* slots, uint32_t shift, uin
     }
 }
 
-__device__ __forceinline__ uint32_t ds_lookup(const ulonglong2* slots, uint32_t shift, uint64_t mask, const IdHash& h) {
+__device__ __forceinline__ uint32_t ds_lookup(const ulonglong2* slots, uint32_t shift, uint64_t mask, const IdHash& h, uint64_t pol) {
     uint64_t i = ds_home(h, shift);
     for (;;) {
-        ulonglong2 cur = ld128(slots + i);
+        ulonglong2 cur = ld128_hint(slots + i, pol);
         if (cur.x == 0ull && cur.y == 0ull) return DS_NONE;
         if (cur.x == h.lo && (cur.y >> 32) == (uint64_t)h.hi) return (uint32_t)cur.y;
         i = (i + 1) & mask;
@@ -308,18 +331,17 @@ struct DevSink {
     // one 16-byte gather: {len, flags, bit_off}.  The flags word is updated by atomics while we read it with a
     // plain load: a stale "not full" only costs a redundant atomicOr.
     __device__ __forceinline__ NodeInfo info(uint32_t g) const {
-        uint4 w;
-        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(a.ninfo + g) : "memory");
+        const uint4 w = ld_v4_hint(a.ninfo + g, a.pol_keep);
         NodeInfo ni;
         ni.len = w.x;
         ni.flags = w.y;
         ni.bit_off = ((uint64_t)w.w << 32) | w.z;
         return ni;
     }
-    __device__ __forceinline__ void add_bases(uint32_t g, int64_t v) { atomicAdd(a.bases + g, (unsigned long long)v); }
+    __device__ __forceinline__ void add_bases(uint32_t g, int64_t v) { red_add64_hint(a.bases + g, (unsigned long long)v, a.pol_keep); }
     __device__ __forceinline__ void set_bits(uint32_t g, const NodeInfo& ni, int64_t lo, int64_t hi) {
         if (lo == 0 && hi == (int64_t)ni.len) {  // whole node: one flag, set once
-            if (!(ni.flags & NI_FULL)) atomicOr(&a.ninfo[g].y, NI_FULL);
+            if (!(ni.flags & NI_FULL)) red_or32_hint(&a.ninfo[g].y, NI_FULL, a.pol_keep);
             return;
         }
         if (ni.flags & NI_FULL) return;  // already fully covered: partial intervals add nothing
@@ -327,11 +349,11 @@ struct DevSink {
         const uint64_t w0 = b0 >> 5, w1 = b1 >> 5;
         const uint32_t m0 = 0xFFFFFFFFu << (b0 & 31u), m1 = 0xFFFFFFFFu >> (31u - (uint32_t)(b1 & 31u));
         if (w0 == w1) {
-            atomicOr(a.bits + w0, m0 & m1);
+            red_or32_hint(a.bits + w0, m0 & m1, a.pol_keep);
         } else {
-            atomicOr(a.bits + w0, m0);
-            for (uint64_t w = w0 + 1; w < w1; ++w) atomicOr(a.bits + w, 0xFFFFFFFFu);
-            atomicOr(a.bits + w1, m1);
+            red_or32_hint(a.bits + w0, m0, a.pol_keep);
+            for (uint64_t w = w0 + 1; w < w1; ++w) red_or32_hint(a.bits + w, 0xFFFFFFFFu, a.pol_keep);
+            red_or32_hint(a.bits + w1, m1, a.pol_keep);
         }
     }
     __device__ __forceinline__ void trio(uint32_t x, uint32_t y, uint32_t z, int64_t s) {
@@ -976,7 +998,8 @@ __device__ __noinline__ void parse_record_exact(const uint8_t* stage, uint32_t p
     *out = r;
 }
 
-__global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs a) {
+template <bool CLS_MUL>
+__global__ void __launch_bounds__(SHORT_THREADS, PTX_SHORT_MINB) k_ingest_s(const IngestArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile_bytes = a.tile_bytes;                 // multiple of 128
@@ -985,9 +1008,9 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
     uint8_t* stage = smem;                                    // [stage_bytes + STAGE_PAD]
     uint32_t* nlw = reinterpret_cast<uint32_t*>(smem + stage_bytes + STAGE_PAD);             // 16-byte aligned
     uint32_t* tabw = nlw + ((bm_words + 2u + 3u) & ~3u);
-    uint32_t* stash = tabw + ((bm_words + 2u + 3u) & ~3u);                                   // [STASH_CAP][SHORT_THREADS]
+    uint32_t* stash = tabw + ((bm_words + 2u + 3u) & ~3u);                                   // [SHORT_STASH_CAP][SHORT_THREADS]
     uint16_t* rec_tmp = reinterpret_cast<uint16_t*>(stash);                                  // [SHORT_REC_CAP] sort scratch, dead before the records are parsed
-    uint16_t* rec_start = reinterpret_cast<uint16_t*>(stash + STASH_CAP * SHORT_THREADS);  // [SHORT_REC_CAP] line starts of the round
+    uint16_t* rec_start = reinterpret_cast<uint16_t*>(stash + SHORT_STASH_CAP * SHORT_THREADS);  // [SHORT_REC_CAP] line starts of the round
     uint16_t* order = rec_start + SHORT_REC_CAP;                                             // [SHORT_REC_CAP] lines by length
     uint16_t* inv_pre = order + SHORT_REC_CAP;                                               // [SHORT_REC_CAP] invalid line slots before slot k
     uint32_t* hkey = reinterpret_cast<uint32_t*>(inv_pre + SHORT_REC_CAP);                   // [HIST_SLOTS] (S > 1 only)
@@ -1010,7 +1033,7 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&mbar, stage_bytes);
-        bulk_g2s(stage, gtile, stage_bytes, &mbar);
+        bulk_g2s_hint(stage, gtile, stage_bytes, &mbar, a.pol_stream);  // the text is read once
     }
     if (tid < STAGE_PAD / 4u) reinterpret_cast<uint32_t*>(stage + stage_bytes)[tid] = 0x0a0a0a0au;
     if (tid < 2u) { nlw[bm_words + tid] = 0xFFFFFFFFu; tabw[bm_words + tid] = 0xFFFFFFFFu; }
@@ -1029,7 +1052,7 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
     for (uint32_t pc = tid; pc < stage_bytes / 16u; pc += SHORT_THREADS) {
         const uint4 q = reinterpret_cast<const uint4*>(stage)[pc];
         uint32_t nl16, tab16;
-        classify16(q.x, q.y, q.z, q.w, nl16, tab16);
+        if (CLS_MUL) classify16_mul(q.x, q.y, q.z, q.w, nl16, tab16); else classify16(q.x, q.y, q.z, q.w, nl16, tab16);
         reinterpret_cast<uint16_t*>(nlw)[pc] = (uint16_t)nl16;
         reinterpret_cast<uint16_t*>(tabw)[pc] = (uint16_t)tab16;
     }
@@ -1194,7 +1217,7 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
                 uint32_t e;  // the '\n' that ends the line: in front of the next line start, or (last line of the round) from the bitmap
                 if (k + 1u < n_round) e = (uint32_t)rec_start[k + 1u] - 1u;
                 else { BitCursor nc; nc.seek(Wnl, p); e = nc.next(); }
-                fast = fast_parse(Wd, Wtab, p, e, stage_bytes, f, pmask, stash + tid, SHORT_THREADS, STASH_CAP);
+                fast = fast_parse(Wd, Wtab, p, e, stage_bytes, f, pmask, stash + tid, SHORT_THREADS, SHORT_STASH_CAP);
                 if (fast) {
                     h = f.h;
                     W = f.W;
@@ -1206,7 +1229,7 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
                     uq = lm && f.mapq == 60u;
                     cols_ok = !f.path_null && !(f.nulls & (FN_C7 | FN_C8 | FN_C9));
                     monotone = false;  // not tracked on the fast path: k_apply notices repeats while it walks (cover_record)
-                    stashed = true;
+                    stashed = f.W <= SHORT_STASH_CAP;  // a longer walk (rare) is decoded again from the staged text when it is written out
                     path_pos = f.path_pos;
                     path_end = f.path_end;
                 }
@@ -1331,20 +1354,21 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
                 const uint32_t e = slot_base_s + q;
                 uint32_t wf = wcnt & RM_W_MASK;
                 if (has) wf |= RM_VALID;
-                if (single_pass && has) a.row_key[e] = (uint16_t)(k - (inv_total ? (uint32_t)inv_pre[k] : 0u));
+                // the record table streams out (k_apply reads it once): evict-first stores
+                if (single_pass && has) __stcs(a.row_key + e, (uint16_t)(k - (inv_total ? (uint32_t)inv_pre[k] : 0u)));
                 if (labelled) wf |= RM_LABELLED;
                 if (eligible) wf |= RM_ELIGIBLE;
                 if (monotone) wf |= RM_MONOTONE;
-                a.meta_b[e] = make_uint4(node_off, wf, label, labelled ? h.hi : 0u);
+                __stcs(a.meta_b + e, make_uint4(node_off, wf, label, labelled ? h.hi : 0u));
                 if (labelled) {
-                    a.hash_lo[e] = h.lo;
-                    if (eligible) a.meta_a[e] = make_longlong2(c8, c9);
+                    __stcs(a.hash_lo + e, (unsigned long long)h.lo);
+                    if (eligible) __stcs(a.meta_a + e, make_longlong2(c8, c9));
                 }
             }
             if (wcnt && nodes_ok) {
                 uint32_t* dst = a.nodes + node_off;
                 if (stashed) {
-                    for (uint32_t i = 0; i < wcnt; ++i) dst[i] = stash[i * SHORT_THREADS + tid];
+                    for (uint32_t i = 0; i < wcnt; ++i) __stcs(dst + i, stash[i * SHORT_THREADS + tid]);
                 } else {  // exact parser: decode the walk again
                     WalkIter it{b, path_pos, path_end};
                     int64_t m;
@@ -1358,6 +1382,479 @@ __global__ void __launch_bounds__(SHORT_THREADS, 7) k_ingest_s(const IngestArgs 
     }
     if (hist_smem) {
         for (uint32_t i = tid; i < HIST_SLOTS; i += SHORT_THREADS) {
+            const uint32_t label = hkey[i];
+            if (label == LABEL_U) continue;
+            unsigned long long* hp = a.hist + 4ull * label;
+            const uint32_t* hv = hval + 4u * i;
+            atomicAdd(hp + 0, (unsigned long long)hv[0]);
+            if (hv[3]) atomicAdd(hp + 1, (unsigned long long)hv[3]);
+            if (hv[1]) atomicAdd(hp + 2, (unsigned long long)hv[1]);
+            if (hv[2]) atomicAdd(hp + 3, (unsigned long long)hv[2]);
+        }
+    }
+}
+
+// =====================================================================================
+// k_ingest_l: the long-read ingest kernel (HiFi / ONT: lines of hundreds of bytes, walks of tens to hundreds of nodes).
+// Same structural index as k_ingest_s plus a non-digit bitmap; the walk column is decoded NODE-parallel:
+//   C1  one thread per line: columns 1-5 and 7-12 (fast_cols); the extent [p6, e6] of its walk column goes to shared memory
+//   C2  every thread takes four words of the bitmaps and finds the lines they meet (binary search over the line starts): a walk
+//       id ENDS where a non-digit byte inside a walk column follows a digit; popc + block scan number the ids of the tile in
+//       file order (= their CSR slots, one atomicAdd per tile); each end is converted by the thread that owns its bit (run
+//       start from the non-digit bitmap, SWAR digits) and stored at its slot - a thread's ids are consecutive slots; the
+//       smallest / largest id of each line accumulate in shared memory (atomicMin / atomicMax per thread and line)
+//   C3  one thread per line again: CSR offset and node count from the ranks of p6 and e6, label, species counts,
+//       record-table entry
+// Lines the word-wide path declines (fast_cols) or whose walk has a 10+ digit id go through the exact byte parser.
+// =====================================================================================
+__global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tile_bytes = a.tile_bytes;                 // multiple of 4096
+    const uint32_t stage_bytes = tile_bytes + a.over_bytes;   // multiple of 128
+    const uint32_t bm_words = stage_bytes / 32u;
+    const uint32_t bm_alloc = (bm_words + 2u + 3u) & ~3u;
+    uint8_t* stage = smem;                                    // [stage_bytes + STAGE_PAD]
+    uint32_t* nlw = reinterpret_cast<uint32_t*>(smem + stage_bytes + STAGE_PAD);
+    uint32_t* tabw = nlw + bm_alloc;
+    uint32_t* ndw = tabw + bm_alloc;    // non-digit bytes
+    uint32_t* ew = ndw + bm_alloc;      // the ends of the walk ids of the group's lines
+    uint32_t* epre = ew + bm_alloc;     // ids that end in front of each bitmap word (exclusive prefix over the tile)
+    uint32_t* lmin = epre + bm_alloc;                                                        // [INGEST_THREADS] smallest / largest walk id of each line of the group
+    uint32_t* lmax = lmin + INGEST_THREADS;                                                  // [INGEST_THREADS]
+    uint16_t* lp6 = reinterpret_cast<uint16_t*>(lmax + INGEST_THREADS);                      // [INGEST_THREADS] first byte of the line's walk column (line start if it has none)
+    uint16_t* lend = lp6 + INGEST_THREADS;                                                   // [INGEST_THREADS] one past its closing tab (<= lp6: no column)
+    uint16_t* rec_start = lend + INGEST_THREADS;                                             // [REC_CAP]
+    uint16_t* inv_pre = rec_start + REC_CAP;                                                 // [REC_CAP]
+    uint32_t* hkey = reinterpret_cast<uint32_t*>(inv_pre + REC_CAP);                         // [HIST_SLOTS] (S > 1 only)
+    uint32_t* hval = hkey + HIST_SLOTS;
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t warp_tot[INGEST_THREADS / 32];
+    __shared__ uint32_t inv_flag, inv_tot_s, slot_base_s, node_base_s, slow_bits[INGEST_THREADS / 32];
+    const Words Wd{smem_u32(stage), nullptr}, Wtab{smem_u32(tabw), nullptr}, Wnl{smem_u32(nlw), nullptr};
+
+    const uint64_t t0 = (uint64_t)blockIdx.x * tile_bytes;
+    const uint8_t* gtile = a.text + t0;
+
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        fence_mbar_init();
+        inv_flag = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&mbar, stage_bytes);
+        bulk_g2s_hint(stage, gtile, stage_bytes, &mbar, a.pol_stream);  // the text is read once
+    }
+    if (tid < STAGE_PAD / 4u) reinterpret_cast<uint32_t*>(stage + stage_bytes)[tid] = 0x0a0a0a0au;
+    if (tid < 2u) { nlw[bm_words + tid] = 0xFFFFFFFFu; tabw[bm_words + tid] = 0xFFFFFFFFu; ndw[bm_words + tid] = 0xFFFFFFFFu; ew[bm_words + tid] = 0u; epre[bm_words + tid] = 0u; }
+    const bool hist_smem = a.ranges.S > 1;
+    if (hist_smem)
+        for (uint32_t i = tid; i < HIST_SLOTS * 5u; i += INGEST_THREADS) hkey[i] = i < HIST_SLOTS ? LABEL_U : 0u;
+    const uint32_t* sstart = a.ranges.sstart;
+    const bool single_pass = a.micro_base == nullptr;
+    const uint32_t rec_base = single_pass ? 0u : (uint32_t)a.micro_base[(uint64_t)blockIdx.x * (tile_bytes / MICRO)];
+    const uint32_t glim = (uint32_t)min((uint64_t)0xFFFF0000ull, a.padded_bytes - t0);
+    const RangesView& R = a.ranges;
+    mbar_wait(&mbar, 0);
+
+    // ---- A: structural index of the window: newline, tab and non-digit flags
+    for (uint32_t pc = tid; pc < stage_bytes / 16u; pc += INGEST_THREADS) {
+        const uint4 q = reinterpret_cast<const uint4*>(stage)[pc];
+        uint32_t nl16, tab16;
+        classify16(q.x, q.y, q.z, q.w, nl16, tab16);
+        reinterpret_cast<uint16_t*>(nlw)[pc] = (uint16_t)nl16;
+        reinterpret_cast<uint16_t*>(tabw)[pc] = (uint16_t)tab16;
+        reinterpret_cast<uint16_t*>(ndw)[pc] = (uint16_t)nondigit16(q.x, q.y, q.z, q.w);
+    }
+    __syncthreads();
+
+    const uint32_t nw = tile_bytes / 32u;
+    const uint64_t rest = a.n_bytes - t0;
+    const uint32_t qmax = rest - 1u < (uint64_t)tile_bytes ? (uint32_t)(rest - 1u) : tile_bytes;
+    const uint32_t first_slot = (blockIdx.x == 0 && tid == 0) ? 1u : 0u;
+
+    uint32_t n_rec = 0;
+    uint32_t valid_prev = 0;
+    for (uint32_t round = 0; round == 0 || round < n_rec; round += REC_CAP) {
+        // ---- B: number the line starts (as k_ingest_s)
+        uint32_t idx_base = 0;
+        for (uint32_t w0 = 0; w0 < nw; w0 += 4u * INGEST_THREADS) {
+            const uint32_t wi = w0 + 4u * tid;
+            uint4 m4 = make_uint4(0u, 0u, 0u, 0u);
+            if (wi < nw) {
+                m4 = reinterpret_cast<const uint4*>(nlw)[wi >> 2];
+                if ((wi + 4u) * 32u > qmax) {
+                    uint32_t* mm = &m4.x;
+#pragma unroll
+                    for (uint32_t j = 0; j < 4u; ++j) {
+                        const uint32_t b0 = (wi + j) * 32u;
+                        if (b0 + 32u > qmax) mm[j] = b0 >= qmax ? 0u : (mm[j] & ((1u << (qmax - b0)) - 1u));
+                    }
+                }
+            }
+            const uint32_t cnt = __popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w) + (w0 == 0u ? first_slot : 0u);
+            uint32_t x = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= (uint32_t)d) x += y;
+            }
+            if (w0) __syncthreads();
+            if (lane == 31u) warp_tot[warp] = x;
+            __syncthreads();
+            uint32_t idx = idx_base + x - cnt, tot = 0;
+#pragma unroll
+            for (int w = 0; w < INGEST_THREADS / 32; ++w) {
+                const uint32_t t = warp_tot[w];
+                if ((uint32_t)w < warp) idx += t;
+                tot += t;
+            }
+            idx_base += tot;
+            if (w0 == 0u && first_slot) {
+                if (idx >= round && idx < round + REC_CAP) rec_start[idx - round] = 0;
+                ++idx;
+            }
+            const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+            for (uint32_t j = 0; j < 4u; ++j) {
+                uint32_t m = mm[j];
+                const uint32_t b0 = (wi + j) * 32u + 1u;
+                while (m) {
+                    const uint32_t bit = __ffs(m) - 1;
+                    m &= m - 1u;
+                    const uint32_t q = b0 + bit;
+                    if (idx >= round && idx < round + REC_CAP) {
+                        rec_start[idx - round] = (uint16_t)q;
+                        if (!valid_first(stage, q)) inv_flag = 1;
+                    }
+                    ++idx;
+                }
+            }
+        }
+        n_rec = idx_base;
+        const uint32_t n_round = min(REC_CAP, n_rec - round);
+        if (tid == 0) {
+            if (first_slot && round == 0 && !valid_first(stage, 0)) inv_flag = 1;
+            uint32_t sb = atomicAdd(a.cursors + 0, n_round);
+            if (single_pass && (sb + n_round > a.slots_cap || n_rec > REC_CAP)) {
+                atomicOr(a.cursors + 3, 1u);
+                sb = 0xFFFFFFFFu;
+            }
+            slot_base_s = sb;
+        }
+        __syncthreads();
+        if (slot_base_s == 0xFFFFFFFFu) return;
+        uint32_t inv_total = 0;
+        if (inv_flag) {
+            if (warp == 0) {
+                uint32_t base = 0;
+                for (uint32_t k0 = 0; k0 < n_round; k0 += 32) {
+                    const uint32_t k = k0 + lane;
+                    const bool bad = k < n_round && !valid_first(stage, rec_start[k]);
+                    const unsigned bm = __ballot_sync(0xffffffffu, bad);
+                    if (k < n_round) inv_pre[k] = (uint16_t)(base + __popc(bm & ((1u << lane) - 1u)));
+                    base += __popc(bm);
+                }
+                if (lane == 0) inv_tot_s = base;
+            }
+            __syncthreads();
+            inv_total = inv_tot_s;
+            __syncthreads();
+            if (tid == 0) inv_flag = 0;
+        }
+        if (tid == 0 && single_pass) {
+            a.tile_info[blockIdx.x] = make_uint4(slot_base_s, n_round, n_round - inv_total, 0u);
+            atomicAdd(a.cursors + 2, n_round - inv_total);
+        }
+
+        for (uint32_t g0 = 0; g0 < n_round; g0 += INGEST_THREADS) {  // groups of one line per thread, in file order
+            const uint32_t ng = min((uint32_t)INGEST_THREADS, n_round - g0);  // lines of the group
+            // ---- C1: the scalar columns of the line; the extent of its walk column goes to lp6 / lend
+            if (tid < INGEST_THREADS / 32) slow_bits[tid] = 0u;
+            const uint32_t k = g0 + tid;
+            const bool slot = k < n_round;
+            const uint32_t p = slot ? rec_start[k] : 0u;
+            const bool has = slot && valid_first(stage, p);
+            const uint32_t pmask = __ballot_sync(0xffffffffu, has);
+            FastRec f;
+            f.nulls = 0; f.W = 0; f.path_pos = f.path_end = 0; f.path_null = true; f.h.lo = 0; f.h.hi = 0;
+            f.qlen = f.c7 = f.c8 = f.c9 = f.mapq = 0;
+            bool walk = false;  // the word-wide path reads this line: its walk column takes part in C2
+            if (has) {
+                uint32_t e;
+                if (k + 1u < n_round) e = (uint32_t)rec_start[k + 1u] - 1u;
+                else { BitCursor nc; nc.seek(Wnl, p); e = nc.next(); }
+                uint32_t slowb = 0;
+                walk = fast_cols(Wd, Wtab, p, e, stage_bytes, f, pmask, slowb) && slowb == 0u;
+            }
+            if (slot) {
+                lp6[tid] = (uint16_t)(walk ? f.path_pos : p);
+                lend[tid] = (uint16_t)(walk ? f.path_end + 1u : p);  // [p6, e6]: the closing tab ends the last id
+                lmin[tid] = 0xFFFFFFFFu;
+                lmax[tid] = 0u;
+            }
+            __syncthreads();
+            // ---- C2: id ends = non-digit byte of a walk column behind a digit; numbered over the tile (= CSR slots); converted by the
+            // thread that owns the bitmap word.  The lines a word meets come from a binary search over the group's line starts.
+            uint32_t n_nodes_tile = 0;
+            {
+                uint32_t run = 0;  // ids ending in front of this pass
+                for (uint32_t w0 = 0; w0 < bm_words; w0 += 4u * INGEST_THREADS) {
+                    const uint32_t wi = w0 + 4u * tid;
+                    uint32_t E[4] = {0u, 0u, 0u, 0u};
+                    if (wi < bm_words) {
+                        uint32_t carry = wi ? (ndw[wi - 1u] >> 31) : 1u;  // class of the byte in front of the word
+                        uint32_t kk;                                     // last line of the group that starts at or before the word (0 if none)
+                        {
+                            const uint32_t wb0 = wi * 32u;
+                            uint32_t lo = 0, hi = ng;
+                            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((uint32_t)rec_start[g0 + mid] <= wb0) lo = mid + 1u; else hi = mid; }
+                            kk = lo ? lo - 1u : 0u;
+                        }
+#pragma unroll
+                        for (uint32_t j = 0; j < 4u; ++j) {
+                            if (wi + j < bm_words) {
+                                const uint32_t nd = ndw[wi + j], wb = (wi + j) * 32u;
+                                uint32_t col = 0;  // bytes of this word inside a walk column
+                                while (kk < ng) {
+                                    const uint32_t b0 = lp6[kk], b1 = lend[kk];
+                                    if (b0 > wb + 31u) break;
+                                    if (b1 > b0 && b1 > wb) {
+                                        const uint32_t lo = b0 > wb ? b0 - wb : 0u, hi = b1 - 1u < wb + 31u ? b1 - 1u - wb : 31u;
+                                        col |= (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31u - hi));
+                                        if (b1 > wb + 32u) break;  // the column goes on in the next word
+                                    }
+                                    ++kk;
+                                }
+                                E[j] = nd & col & ~((nd << 1) | carry);
+                                carry = nd >> 31;
+                            }
+                        }
+                    }
+                    const uint32_t cnt = __popc(E[0]) + __popc(E[1]) + __popc(E[2]) + __popc(E[3]);
+                    uint32_t x = cnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                        if (lane >= (uint32_t)d) x += y;
+                    }
+                    if (w0) __syncthreads();  // the previous pass has read warp_tot
+                    if (lane == 31u) warp_tot[warp] = x;
+                    __syncthreads();
+                    uint32_t before = run + x - cnt, tot = 0;
+#pragma unroll
+                    for (int w = 0; w < INGEST_THREADS / 32; ++w) {
+                        const uint32_t t = warp_tot[w];
+                        if ((uint32_t)w < warp) before += t;
+                        tot += t;
+                    }
+                    if (wi < bm_words) {
+                        uint32_t c = before;
+#pragma unroll
+                        for (uint32_t j = 0; j < 4u; ++j)
+                            if (wi + j < bm_words) { ew[wi + j] = E[j]; epre[wi + j] = c; c += __popc(E[j]); }
+                    }
+                    run += tot;
+                }
+                if (tid == 0) {  // the tile's CSR slots: one atomicAdd
+                    node_base_s = run ? atomicAdd(a.cursors + 1, run) : 0u;
+                    epre[bm_words] = run;
+                }
+                __syncthreads();
+                n_nodes_tile = epre[bm_words];
+                const uint32_t node_base = node_base_s;
+                // sweep: every thread converts the ids that end in its words and stores them at their CSR slots (a thread's ids are
+                // consecutive slots: its stores fill whole sectors); min / max per line through shared-memory atomics
+                for (uint32_t w0 = 0; w0 < bm_words && n_nodes_tile; w0 += 4u * INGEST_THREADS) {
+                    const uint32_t wi = w0 + 4u * tid;
+                    if (wi >= bm_words) continue;
+                    uint32_t kk;
+                    {
+                        const uint32_t wb0 = wi * 32u;
+                        uint32_t lo = 0, hi = ng;
+                        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((uint32_t)rec_start[g0 + mid] <= wb0) lo = mid + 1u; else hi = mid; }
+                        kk = lo ? lo - 1u : 0u;
+                    }
+                    uint32_t cur = 0xFFFFFFFFu, mn = 0xFFFFFFFFu, mx = 0u;
+#pragma unroll 1
+                    for (uint32_t j = 0; j < 4u && wi + j < bm_words; ++j) {
+                        uint32_t m = ew[wi + j];
+                        uint32_t ord = node_base + epre[wi + j];
+                        while (m) {
+                            const uint32_t bit = __ffs(m) - 1;
+                            m &= m - 1u;
+                            const uint32_t q = (wi + j) * 32u + bit;  // the non-digit byte behind the id
+                            while (kk + 1u < ng && (uint32_t)lp6[kk + 1u] <= q) ++kk;  // the line whose column holds q
+                            if (kk != cur) {
+                                if (cur != 0xFFFFFFFFu) { atomicMin(lmin + cur, mn); atomicMax(lmax + cur, mx); }
+                                cur = kk; mn = 0xFFFFFFFFu; mx = 0u;
+                            }
+                            // the id starts behind the previous non-digit byte (the tab in front of the column at the latest)
+                            uint32_t wq = wi + j;
+                            uint32_t below = ndw[wq] & ((1u << bit) - 1u);
+                            while (below == 0u) below = ndw[--wq];
+                            const uint32_t astart = wq * 32u + (31u - (uint32_t)__clz(below)) + 1u;
+                            const uint32_t n = q - astart;
+                            uint32_t v = 0;
+                            if (n <= 9u) v = fast_node(Wd, astart, n);
+                            else atomicOr(&slow_bits[kk >> 5], 1u << (kk & 31u));  // a 10+ digit id: the line goes through the exact parser
+                            mn = v < mn ? v : mn;
+                            mx = v > mx ? v : mx;
+                            __stcs(a.nodes + ord, v);
+                            ++ord;
+                        }
+                    }
+                    if (cur != 0xFFFFFFFFu) { atomicMin(lmin + cur, mn); atomicMax(lmax + cur, mx); }
+                }
+            }
+            __syncthreads();  // min / max and slow flags of the group's lines are complete
+            // ---- C3: per line: CSR slice, min / max, label, counts, record-table entry
+            IdHash h = f.h;
+            uint32_t W = 0, node_off = 0, w_res = 0, path_pos = f.path_pos, path_end = f.path_end;
+            int64_t vmin = -1, vmax = -1, c8 = (int64_t)f.c8, c9 = (int64_t)f.c9;
+            unsigned long long ql = (f.nulls & FN_QLEN) ? 0ull : (unsigned long long)f.qlen;
+            bool lm = !(f.nulls & FN_MAPQ) && f.mapq - 3u <= 57u, uq = false;
+            uq = lm && f.mapq == 60u;
+            bool cols_ok = !f.path_null && !(f.nulls & (FN_C7 | FN_C8 | FN_C9));
+            bool monotone = false;  // not tracked: k_apply notices repeats while it walks (cover_record)
+            const uint8_t* b = stage;
+            bool exact = has && !walk;
+            if (has && walk) {
+                const uint32_t r0 = epre[path_pos >> 5] + __popc(ew[path_pos >> 5] & ((1u << (path_pos & 31u)) - 1u));
+                const uint32_t pe1 = path_end + 1u;
+                const uint32_t r1 = epre[pe1 >> 5] + __popc(ew[pe1 >> 5] & ((1u << (pe1 & 31u)) - 1u));
+                W = r1 - r0;
+                w_res = W;
+                node_off = node_base_s + r0;
+                if ((slow_bits[tid >> 5] >> (tid & 31u)) & 1u) exact = true;
+                else if (W) {
+                    vmin = (int64_t)lmin[tid];
+                    vmax = (int64_t)lmax[tid];
+                }
+            }
+            __syncwarp();
+            if (exact) {  // rare: the exact byte parser
+                RecParse r;
+                uint32_t from_global;
+                parse_record_exact(stage, p, stage_bytes, gtile, glim, &r, &from_global);
+                if (from_global) b = gtile;
+                h = r.h;
+                W = r.W;
+                vmin = vmax = -1;
+                if (W) { vmin = r.vmin; vmax = r.vmax; }
+                c8 = r.c8;
+                c9 = r.c9;
+                ql = r.qlen != NULL_I64 ? (unsigned long long)r.qlen : 0ull;
+                lm = r.mapq != NULL_I64 && r.mapq >= 3 && r.mapq <= 60;
+                uq = lm && r.mapq == 60;
+                cols_ok = !r.path_null && r.c7 != NULL_I64 && r.c8 != NULL_I64 && r.c9 != NULL_I64;
+                monotone = r.monotone;
+                path_pos = r.path_pos;
+                path_end = r.path_end;
+            }
+            __syncwarp();
+            uint32_t label = LABEL_U;
+            if (has) {
+                const uint32_t row = rec_base + valid_prev + k - (inv_total ? (uint32_t)inv_pre[k] : 0u);
+                if (a.labels_in) {
+                    label = a.labels_in[row];
+                    if (label != LABEL_U && W && (vmin < R.start[label] || vmax > R.end[label])) {
+                        atomicOr(a.flags + 3, 1u);
+                        label = LABEL_U;
+                    }
+                } else {
+                    label = classify(R, vmin, vmax, sstart);
+                }
+                if (!single_pass) a.labels[row] = label;
+            }
+            __syncwarp();
+            {   // ---- species counts (profile.rs:219-232, 264-277)
+                const bool cnt = has && label != LABEL_U;
+                const unsigned mm = __ballot_sync(0xffffffffu, cnt);
+                if (mm) {
+                    const int leader = __ffs(mm) - 1;
+                    const uint32_t lab0 = __shfl_sync(0xffffffffu, label, leader);
+                    const bool uniform = __all_sync(0xffffffffu, !cnt || label == lab0);
+                    const uint32_t c_lm = (cnt && lm) ? 1u : 0u, c_uq = (cnt && uq) ? 1u : 0u;
+                    const unsigned long long qv = cnt ? ql : 0ull;
+                    if (uniform) {
+                        const uint32_t n1 = __popc(mm);
+                        const uint32_t n3 = __reduce_add_sync(0xffffffffu, c_lm);
+                        const uint32_t n4 = __reduce_add_sync(0xffffffffu, c_uq);
+                        unsigned long long sum = qv;
+#pragma unroll
+                        for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+                        if ((int)lane == leader) {
+                            unsigned long long* hp = a.hist + 4ull * lab0;
+                            atomicAdd(hp + 0, (unsigned long long)n1);
+                            atomicAdd(hp + 1, sum);
+                            if (n3) atomicAdd(hp + 2, (unsigned long long)n3);
+                            if (n4) atomicAdd(hp + 3, (unsigned long long)n4);
+                        }
+                    } else if (cnt) {
+                        bool done = false;
+                        if (qv < (1ull << 16)) {
+                            uint32_t hs = (label * 0x9E3779B1u) >> (32 - HIST_SLOTS_LOG2);
+                            for (int t = 0; t < 4 && !done; ++t) {
+                                const uint32_t old = atomicCAS(&hkey[hs], LABEL_U, label);
+                                if (old == LABEL_U || old == label) {
+                                    uint32_t* hv = hval + 4u * hs;
+                                    atomicAdd(hv + 0, 1u);
+                                    if (c_lm) atomicAdd(hv + 1, 1u);
+                                    if (c_uq) atomicAdd(hv + 2, 1u);
+                                    if (qv) atomicAdd(hv + 3, (uint32_t)qv);
+                                    done = true;
+                                }
+                                hs = (hs + 1u) & (HIST_SLOTS - 1u);
+                            }
+                        }
+                        if (!done) {
+                            unsigned long long* hp = a.hist + 4ull * label;
+                            atomicAdd(hp + 0, 1ull);
+                            atomicAdd(hp + 1, qv);
+                            if (c_lm) atomicAdd(hp + 2, 1ull);
+                            if (c_uq) atomicAdd(hp + 3, 1ull);
+                        }
+                    }
+                }
+            }
+            // ---- the record for k_apply
+            const bool labelled = has && label != LABEL_U;
+            const bool eligible = labelled && cols_ok;
+            const uint32_t wcnt = eligible ? W : 0u;
+            // the exact parser finds at most the ids the word-wide pass counted (it drops runs of more than 18 digits): a line that
+            // was converted reuses its slots; only a line that never took part in C2 takes new ones - the slots of a chunk stay
+            // within text bytes / 2 (chunk_nodes_ensure)
+            if (exact && wcnt > w_res) node_off = atomicAdd(a.cursors + 1, wcnt);
+            if (slot) {
+                const uint32_t e = slot_base_s + k;
+                uint32_t wf = wcnt & RM_W_MASK;
+                if (has) wf |= RM_VALID;
+                // the record table streams out (k_apply reads it once): evict-first stores
+                if (single_pass && has) __stcs(a.row_key + e, (uint16_t)(k - (inv_total ? (uint32_t)inv_pre[k] : 0u)));
+                if (labelled) wf |= RM_LABELLED;
+                if (eligible) wf |= RM_ELIGIBLE;
+                if (monotone) wf |= RM_MONOTONE;
+                __stcs(a.meta_b + e, make_uint4(node_off, wf, label, labelled ? h.hi : 0u));
+                if (labelled) {
+                    __stcs(a.hash_lo + e, (unsigned long long)h.lo);
+                    if (eligible) __stcs(a.meta_a + e, make_longlong2(c8, c9));
+                }
+            }
+            if (exact && wcnt) {
+                uint32_t* dst = a.nodes + node_off;
+                WalkIter it{b, path_pos, path_end};
+                int64_t m;
+                for (uint32_t i = 0; i < wcnt; ++i) { it.next(m); dst[i] = (uint32_t)m; }
+            }
+            __syncthreads();  // `ew`, `slow_bits`, the per-line arrays are reused by the next group
+        }
+        valid_prev += n_round - inv_total;
+        __syncthreads();
+    }
+    if (hist_smem) {
+        for (uint32_t i = tid; i < HIST_SLOTS; i += INGEST_THREADS) {
             const uint32_t label = hkey[i];
             if (label == LABEL_U) continue;
             unsigned long long* hp = a.hist + 4ull * label;
@@ -1425,17 +1922,17 @@ __global__ void __launch_bounds__(256, 8) k_apply(const IngestArgs a, uint32_t n
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     const bool has = e < n_entries;
     uint4 mb = make_uint4(0u, 0u, LABEL_U, 0u);
-    if (has) mb = a.meta_b[e];
+    if (has) mb = __ldcs(a.meta_b + e);  // the record table is read once: evict-first
     const bool labelled = has && (mb.y & RM_LABELLED);
     const bool eligible = has && (mb.y & RM_ELIGIBLE);
     const uint32_t label = mb.z;
     IdHash h;
     h.lo = 0;
     h.hi = mb.w;
-    if (labelled && (MODE & (MODE_CLASSIFY | MODE_KEEPMASK | MODE_REBOX))) h.lo = a.hash_lo[e];
+    if (labelled && (MODE & (MODE_CLASSIFY | MODE_KEEPMASK | MODE_REBOX))) h.lo = __ldcs(a.hash_lo + e);
     if (MODE & (MODE_CLASSIFY | MODE_REBOX)) {
         if (a.box_ptr == nullptr) {
-            if ((MODE & MODE_CLASSIFY) && labelled) ds_insert(a.ds, a.ds_shift, a.ds_mask, h, eligible, label, a.flags);
+            if ((MODE & MODE_CLASSIFY) && labelled) ds_insert(a.ds, a.ds_shift, a.ds_mask, h, eligible, label, a.flags, a.pol_ds);
         } else {
             // multi-GPU: a read id is kept only by the rank that owns its hash.  Own ids go into the local set; the
             // others are appended to the owner's outbox as {hash, state} (one atomicAdd per distinct owner per warp)
@@ -1443,7 +1940,7 @@ __global__ void __launch_bounds__(256, 8) k_apply(const IngestArgs a, uint32_t n
             const ulonglong2 ent = make_ulonglong2(h.lo, ((uint64_t)h.hi << 32) | (eligible ? label : DS_NONE));
             const uint32_t owner = labelled ? ds_owner(ent, a.n_ranks) : 0xFFFFFFFFu;
             const bool mine = labelled && owner == a.rank;
-            if ((MODE & MODE_CLASSIFY) && mine) ds_insert(a.ds, a.ds_shift, a.ds_mask, h, eligible, label, a.flags);
+            if ((MODE & MODE_CLASSIFY) && mine) ds_insert(a.ds, a.ds_shift, a.ds_mask, h, eligible, label, a.flags, a.pol_ds);
             const uint32_t dest = (labelled && !mine) ? owner : 0xFFFFFFFFu;
             if (a.n_ranks <= BOX_STAGE_RANKS) {
                 block_append(dest, ent, a.n_ranks, a.out_cursor, a.box_cap, [&](uint32_t d) { return a.box_ptr[d]; },
@@ -1470,11 +1967,11 @@ __global__ void __launch_bounds__(256, 8) k_apply(const IngestArgs a, uint32_t n
         if (eligible) {
             nb = R.node_base[label];
             keep = nb >= 0;
-            if ((MODE & MODE_KEEPMASK) && keep) keep = ds_lookup(a.ds, a.ds_shift, a.ds_mask, h) != DS_MIXED;  // :415-416
+            if ((MODE & MODE_KEEPMASK) && keep) keep = ds_lookup(a.ds, a.ds_shift, a.ds_mask, h, a.pol_ds) != DS_MIXED;  // :415-416
         }
         const uint32_t cmask = __ballot_sync(0xffffffffu, keep);
         if (keep) {
-            const longlong2 se = a.meta_a[e];
+            const longlong2 se = __ldcs(a.meta_a + e);
             RecParse r;
             r.W = mb.y & RM_W_MASK;
             r.c8 = se.x;
@@ -2173,10 +2670,17 @@ size_t ingest_smem_bytes(uint32_t tile_bytes, uint32_t over_bytes, bool short_ke
     const size_t hist_bytes = multi_species ? HIST_SLOTS * 5 * sizeof(uint32_t) : 0;
     if (short_kernel) {
         const size_t stage_bytes = (size_t)tile_bytes + over_bytes;
-        return stage_bytes + STAGE_PAD + 2 * ((stage_bytes / 32 + 2 + 3) / 4 * 4) * sizeof(uint32_t) + STASH_CAP * SHORT_THREADS * sizeof(uint32_t) +
+        return stage_bytes + STAGE_PAD + 2 * ((stage_bytes / 32 + 2 + 3) / 4 * 4) * sizeof(uint32_t) + SHORT_STASH_CAP * SHORT_THREADS * sizeof(uint32_t) +
                3 * SHORT_REC_CAP * sizeof(uint16_t) + hist_bytes;
     }
     return (size_t)tile_bytes + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 4 * REC_CAP * sizeof(uint16_t) + hist_bytes;
+}
+
+size_t ingest_l_smem_bytes(uint32_t tile_bytes, uint32_t over_bytes, bool multi_species) {
+    const size_t stage_bytes = (size_t)tile_bytes + over_bytes;
+    const size_t bm_alloc = (stage_bytes / 32 + 2 + 3) / 4 * 4;
+    return stage_bytes + STAGE_PAD + 5 * bm_alloc * sizeof(uint32_t) + INGEST_THREADS * (2 * sizeof(uint32_t) + 2 * sizeof(uint16_t)) +
+           2 * REC_CAP * sizeof(uint16_t) + (multi_species ? HIST_SLOTS * 5 * sizeof(uint32_t) : 0);
 }
 
 void launch_ingest(const IngestArgs& a, cudaStream_t st) {
@@ -2187,13 +2691,31 @@ void launch_ingest(const IngestArgs& a, cudaStream_t st) {
     if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaFuncSetAttribute(k_ingest<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ingest_smem_bytes(MAX_TILE, OVER, false, true));
         cudaFuncSetAttribute(k_ingest<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ingest_smem_bytes(MAX_TILE, OVER, false, true));
-        cudaFuncSetAttribute(k_ingest_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ingest_smem_bytes(MAX_TILE, OVER, true, true));
+        cudaFuncSetAttribute(k_ingest_s<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ingest_smem_bytes(MAX_TILE, OVER, true, true) + 8192);
+        cudaFuncSetAttribute(k_ingest_s<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ingest_smem_bytes(MAX_TILE, OVER, true, true) + 8192);
+        cudaFuncSetAttribute(k_ingest_l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ingest_l_smem_bytes(MAX_TILE, OVER, true));
+        // all of the SM's shared memory for these kernels: the driver's own carve-out choice flips between launches of the
+        // same configuration (measured: k_ingest_s 1.06 or 1.34 ms), and their occupancy is set by shared memory
+        static const int carve = getenv("PTX_CARVEOUT") ? atoi(getenv("PTX_CARVEOUT")) : 100;
+        if (carve >= 0) {
+            cudaFuncSetAttribute(k_ingest<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(k_ingest<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(k_ingest_s<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(k_ingest_s<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(k_ingest_l, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        }
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const bool multi = a.ranges.S > 1;
-    if (a.long_mode) k_ingest<true><<<a.n_tiles, INGEST_THREADS, ingest_smem_bytes(a.tile_bytes, OVER, false, multi), st>>>(a);
+    if (a.long_mode && !a.long_new) k_ingest<true><<<a.n_tiles, INGEST_THREADS, ingest_smem_bytes(a.tile_bytes, OVER, false, multi), st>>>(a);
+    else if (a.long_mode) k_ingest_l<<<a.n_tiles, INGEST_THREADS, ingest_l_smem_bytes(a.tile_bytes, a.over_bytes, multi), st>>>(a);
     else if (a.old_short) k_ingest<false><<<a.n_tiles, INGEST_THREADS, ingest_smem_bytes(a.tile_bytes, OVER, false, multi), st>>>(a);
-    else k_ingest_s<<<a.n_tiles, SHORT_THREADS, ingest_smem_bytes(a.tile_bytes, a.over_bytes, true, multi), st>>>(a);
+    else {
+        static const int pad = getenv("PTX_SMEM_PAD") ? atoi(getenv("PTX_SMEM_PAD")) : 0, cls = getenv("PTX_CLS_MUL") ? atoi(getenv("PTX_CLS_MUL")) : 0;  // measurement knobs
+        const size_t sm = ingest_smem_bytes(a.tile_bytes, a.over_bytes, true, multi) + (size_t)std::min(pad, 8192);
+        if (cls) k_ingest_s<true><<<a.n_tiles, SHORT_THREADS, sm, st>>>(a);
+        else k_ingest_s<false><<<a.n_tiles, SHORT_THREADS, sm, st>>>(a);
+    }
     PTX_LAUNCHED();
 }
 void launch_hist_merge(const unsigned long long* chunk_hist, unsigned long long* hist, uint32_t n, uint32_t* cursors, cudaStream_t st) {

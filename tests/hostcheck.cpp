@@ -140,7 +140,7 @@ int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, 
                     if (same) {
                         WalkIter it{buf.data(), p.r.path_pos, p.r.path_end};
                         int64_t m;
-                        for (uint32_t k = 0; k < f.W && same; ++k) same = it.next(m) && m == (int64_t)fst[k];
+                        for (uint32_t k = 0; k < f.W && k < 16u && same; ++k) same = it.next(m) && m == (int64_t)fst[k];  // (only the first 16 are stashed)
                     }
                     if (!same) return 10;
                 }
