@@ -1407,6 +1407,8 @@ __global__ void __launch_bounds__(SHORT_THREADS, PTX_SHORT_MINB) k_ingest_s(cons
 //       record-table entry
 // Lines the word-wide path declines (fast_cols) or whose walk has a 10+ digit id go through the exact byte parser.
 // =====================================================================================
+constexpr uint32_t LONG_WPT = (MAX_TILE + OVER) / 32u / INGEST_THREADS + 1u;  // bitmap words a thread of k_ingest_l takes
+
 __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -1597,113 +1599,112 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs
             __syncthreads();
             // ---- C2: id ends = non-digit byte of a walk column behind a digit; numbered over the tile (= CSR slots); converted by the
             // thread that owns the bitmap word.  The lines a word meets come from a binary search over the group's line starts.
-            uint32_t n_nodes_tile = 0;
             {
-                uint32_t run = 0;  // ids ending in front of this pass
-                for (uint32_t w0 = 0; w0 < bm_words; w0 += 4u * INGEST_THREADS) {
-                    const uint32_t wi = w0 + 4u * tid;
-                    uint32_t E[4] = {0u, 0u, 0u, 0u};
-                    if (wi < bm_words) {
-                        uint32_t carry = wi ? (ndw[wi - 1u] >> 31) : 1u;  // class of the byte in front of the word
-                        uint32_t kk;                                     // last line of the group that starts at or before the word (0 if none)
-                        {
-                            const uint32_t wb0 = wi * 32u;
-                            uint32_t lo = 0, hi = ng;
-                            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((uint32_t)rec_start[g0 + mid] <= wb0) lo = mid + 1u; else hi = mid; }
-                            kk = lo ? lo - 1u : 0u;
-                        }
+                // a thread takes `wpt` consecutive bitmap words (at most LONG_WPT: 34 KB of window / 32 / 256 threads)
+                const uint32_t wpt = (bm_words + INGEST_THREADS - 1u) / INGEST_THREADS;
+                const uint32_t wi = wpt * tid, wn = wi < bm_words ? min(wpt, bm_words - wi) : 0u;
+                uint32_t E[LONG_WPT];
 #pragma unroll
-                        for (uint32_t j = 0; j < 4u; ++j) {
-                            if (wi + j < bm_words) {
-                                const uint32_t nd = ndw[wi + j], wb = (wi + j) * 32u;
-                                uint32_t col = 0;  // bytes of this word inside a walk column
-                                while (kk < ng) {
-                                    const uint32_t b0 = lp6[kk], b1 = lend[kk];
-                                    if (b0 > wb + 31u) break;
-                                    if (b1 > b0 && b1 > wb) {
-                                        const uint32_t lo = b0 > wb ? b0 - wb : 0u, hi = b1 - 1u < wb + 31u ? b1 - 1u - wb : 31u;
-                                        col |= (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31u - hi));
-                                        if (b1 > wb + 32u) break;  // the column goes on in the next word
-                                    }
-                                    ++kk;
+                for (uint32_t j = 0; j < LONG_WPT; ++j) E[j] = 0u;
+                uint32_t kk0 = 0;  // last line of the group that starts at or before this thread's first word (0 if none)
+                if (wn) {
+                    const uint32_t wb0 = wi * 32u;
+                    uint32_t lo = 0, hi = ng;
+                    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((uint32_t)rec_start[g0 + mid] <= wb0) lo = mid + 1u; else hi = mid; }
+                    kk0 = lo ? lo - 1u : 0u;
+                    uint32_t kk = kk0;
+                    uint32_t carry = wi ? (ndw[wi - 1u] >> 31) : 1u;  // class of the byte in front of the word
+#pragma unroll
+                    for (uint32_t j = 0; j < LONG_WPT; ++j) {
+                        if (j < wn) {
+                            const uint32_t nd = ndw[wi + j], wb = (wi + j) * 32u;
+                            uint32_t col = 0;  // bytes of this word inside a walk column
+                            while (kk < ng) {
+                                const uint32_t b0 = lp6[kk], b1 = lend[kk];
+                                if (b0 > wb + 31u) break;
+                                if (b1 > b0 && b1 > wb) {
+                                    const uint32_t lo = b0 > wb ? b0 - wb : 0u, hi = b1 - 1u < wb + 31u ? b1 - 1u - wb : 31u;
+                                    col |= (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31u - hi));
+                                    if (b1 > wb + 32u) break;  // the column goes on in the next word
                                 }
-                                E[j] = nd & col & ~((nd << 1) | carry);
-                                carry = nd >> 31;
+                                ++kk;
                             }
+                            E[j] = nd & col & ~((nd << 1) | carry);
+                            carry = nd >> 31;
                         }
                     }
-                    const uint32_t cnt = __popc(E[0]) + __popc(E[1]) + __popc(E[2]) + __popc(E[3]);
-                    uint32_t x = cnt;
+                }
+                uint32_t cnt = 0;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-                        if (lane >= (uint32_t)d) x += y;
-                    }
-                    if (w0) __syncthreads();  // the previous pass has read warp_tot
-                    if (lane == 31u) warp_tot[warp] = x;
-                    __syncthreads();
-                    uint32_t before = run + x - cnt, tot = 0;
+                for (uint32_t j = 0; j < LONG_WPT; ++j) cnt += __popc(E[j]);
+                uint32_t x = cnt;
 #pragma unroll
-                    for (int w = 0; w < INGEST_THREADS / 32; ++w) {
-                        const uint32_t t = warp_tot[w];
-                        if ((uint32_t)w < warp) before += t;
-                        tot += t;
-                    }
-                    if (wi < bm_words) {
-                        uint32_t c = before;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                    if (lane >= (uint32_t)d) x += y;
+                }
+                if (lane == 31u) warp_tot[warp] = x;
+                __syncthreads();
+                uint32_t before = x - cnt, tot = 0;
 #pragma unroll
-                        for (uint32_t j = 0; j < 4u; ++j)
-                            if (wi + j < bm_words) { ew[wi + j] = E[j]; epre[wi + j] = c; c += __popc(E[j]); }
-                    }
-                    run += tot;
+                for (int w = 0; w < INGEST_THREADS / 32; ++w) {
+                    const uint32_t t = warp_tot[w];
+                    if ((uint32_t)w < warp) before += t;
+                    tot += t;
+                }
+                {   // ranks of the ends for C3 (W and CSR offset of a line from the ranks of p6 and e6 + 1)
+                    uint32_t c = before;
+#pragma unroll
+                    for (uint32_t j = 0; j < LONG_WPT; ++j)
+                        if (j < wn) { ew[wi + j] = E[j]; epre[wi + j] = c; c += __popc(E[j]); }
                 }
                 if (tid == 0) {  // the tile's CSR slots: one atomicAdd
-                    node_base_s = run ? atomicAdd(a.cursors + 1, run) : 0u;
-                    epre[bm_words] = run;
+                    node_base_s = tot ? atomicAdd(a.cursors + 1, tot) : 0u;
+                    epre[bm_words] = tot;
                 }
                 __syncthreads();
-                n_nodes_tile = epre[bm_words];
-                const uint32_t node_base = node_base_s;
                 // sweep: every thread converts the ids that end in its words and stores them at their CSR slots (a thread's ids are
                 // consecutive slots: its stores fill whole sectors); min / max per line through shared-memory atomics
-                for (uint32_t w0 = 0; w0 < bm_words && n_nodes_tile; w0 += 4u * INGEST_THREADS) {
-                    const uint32_t wi = w0 + 4u * tid;
-                    if (wi >= bm_words) continue;
-                    uint32_t kk;
-                    {
-                        const uint32_t wb0 = wi * 32u;
-                        uint32_t lo = 0, hi = ng;
-                        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((uint32_t)rec_start[g0 + mid] <= wb0) lo = mid + 1u; else hi = mid; }
-                        kk = lo ? lo - 1u : 0u;
-                    }
-                    uint32_t cur = 0xFFFFFFFFu, mn = 0xFFFFFFFFu, mx = 0u;
-#pragma unroll 1
-                    for (uint32_t j = 0; j < 4u && wi + j < bm_words; ++j) {
-                        uint32_t m = ew[wi + j];
-                        uint32_t ord = node_base + epre[wi + j];
-                        while (m) {
-                            const uint32_t bit = __ffs(m) - 1;
-                            m &= m - 1u;
-                            const uint32_t q = (wi + j) * 32u + bit;  // the non-digit byte behind the id
-                            while (kk + 1u < ng && (uint32_t)lp6[kk + 1u] <= q) ++kk;  // the line whose column holds q
-                            if (kk != cur) {
-                                if (cur != 0xFFFFFFFFu) { atomicMin(lmin + cur, mn); atomicMax(lmax + cur, mx); }
-                                cur = kk; mn = 0xFFFFFFFFu; mx = 0u;
+                if (cnt) {
+                    uint32_t ord = node_base_s + before;
+                    uint32_t kk = kk0, cur = 0xFFFFFFFFu, mn = 0xFFFFFFFFu, mx = 0u;
+                    bool pending = true;  // a line may have ended since the line of an id was last looked up
+#pragma unroll
+                    for (uint32_t j = 0; j < LONG_WPT; ++j) {
+                        uint32_t m = E[j];
+                        const uint32_t nlb = j < wn ? nlw[wi + j] : 0u;
+                        if (m) {
+                            const uint32_t nd = ndw[wi + j], wb = (wi + j) * 32u;
+                            const bool line_may_change = nlb != 0u;
+                            bool track = pending || line_may_change;  // look the line up for the first id behind a newline; for every id of a word that holds one
+                            pending = false;
+                            while (m) {
+                                const uint32_t bit = __ffs(m) - 1;
+                                m &= m - 1u;
+                                const uint32_t q = wb + bit;  // the non-digit byte behind the id
+                                if (track) {
+                                    while (kk + 1u < ng && (uint32_t)lp6[kk + 1u] <= q) ++kk;  // the line whose column holds q
+                                    if (kk != cur) {
+                                        if (cur != 0xFFFFFFFFu) { atomicMin(lmin + cur, mn); atomicMax(lmax + cur, mx); }
+                                        cur = kk; mn = 0xFFFFFFFFu; mx = 0u;
+                                    }
+                                    track = line_may_change;
+                                }
+                                // the id starts behind the previous non-digit byte (the tab in front of the column at the latest)
+                                uint32_t below = nd & ((1u << bit) - 1u), wq = wi + j;
+                                while (below == 0u) below = ndw[--wq];
+                                const uint32_t astart = wq * 32u + (31u - (uint32_t)__clz(below)) + 1u;
+                                const uint32_t n = q - astart;
+                                uint32_t v = 0;
+                                if (n <= 9u) v = fast_node(Wd, astart, n);
+                                else atomicOr(&slow_bits[kk >> 5], 1u << (kk & 31u));  // a 10+ digit id: the line goes through the exact parser
+                                mn = v < mn ? v : mn;
+                                mx = v > mx ? v : mx;
+                                __stcs(a.nodes + ord, v);
+                                ++ord;
                             }
-                            // the id starts behind the previous non-digit byte (the tab in front of the column at the latest)
-                            uint32_t wq = wi + j;
-                            uint32_t below = ndw[wq] & ((1u << bit) - 1u);
-                            while (below == 0u) below = ndw[--wq];
-                            const uint32_t astart = wq * 32u + (31u - (uint32_t)__clz(below)) + 1u;
-                            const uint32_t n = q - astart;
-                            uint32_t v = 0;
-                            if (n <= 9u) v = fast_node(Wd, astart, n);
-                            else atomicOr(&slow_bits[kk >> 5], 1u << (kk & 31u));  // a 10+ digit id: the line goes through the exact parser
-                            mn = v < mn ? v : mn;
-                            mx = v > mx ? v : mx;
-                            __stcs(a.nodes + ord, v);
-                            ++ord;
                         }
+                        if (nlb) pending = true;
                     }
                     if (cur != 0xFFFFFFFFu) { atomicMin(lmin + cur, mn); atomicMax(lmax + cur, mx); }
                 }
