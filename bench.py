@@ -24,6 +24,7 @@ graph upload + unique-trio table build is database setup,
   secondary: one more BASELINE config per run, same step definition, with its own parity check -
             N=1: configs[2] (HiFi long reads, 100 species, 5 M nodes, 1 M records);
             N>1: configs[3] (1,000 species, 20 M nodes, 200 M records sharded over the ranks)
+  tertiary: at 8 GPUs (or --config4): configs[4] (50 M nodes, 5,000 paths, 1 B records over the ranks), parity on a 1/512 prefix
 
 --impl reference times the CPU port alone (the reference itself is Rust and cannot be built in this
 image - see DESIGN.md); it never touches the GPU.
@@ -64,6 +65,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--secondary-records", type=int, default=0, help="total records of the secondary config (0 = the BASELINE size)")
+    ap.add_argument("--config4", action="store_true", help="also run BASELINE configs[4] (50 M nodes, 1 B records over the ranks); always on at 8 GPUs")
+    ap.add_argument("--config4-records", type=int, default=0, help="total records of configs[4] (0 = 1 B)")
     return ap.parse_args()
 
 
@@ -196,6 +199,13 @@ def wl_config3():
 
     return Workload("configs[3]", "multi-species synthetic graph: 1,000 species, 20 M nodes, 5,000 strain paths, short-read GAF", 20261017 + 4,
                     [20_000] * 1000, [5] * 1000, synth.GafParams())
+
+
+def wl_config4():
+    import synth
+
+    return Workload("configs[4]", "large-scale stress: 50 M-node graph (1,000 species x 50 k nodes), 5,000 strain paths, short-read GAF", 20261017 + 5,
+                    [50_000] * 1000, [5] * 1000, synth.GafParams())
 
 
 def workload_name(args, n_gpus):
@@ -475,14 +485,22 @@ def cross_rank_check(D, res):
     return all(d == ds[0] for d in ds)
 
 
-def secondary_config(D, args, cudart):
-    """One more BASELINE config, same step definition: N=1 -> configs[2] (HiFi), N>1 -> configs[3] (1,000 species, sharded)."""
+def secondary_config(D, args, cudart, which="auto"):
+    """One more BASELINE config, same step definition: N=1 -> configs[2] (HiFi), N>1 -> configs[3] (1,000 species, sharded);
+    which="config4": configs[4] (50 M nodes, 5,000 paths, 1 B records over the ranks; run at N=8 or with --config4)."""
     import synth
     from pantax_b200 import api
 
-    if D.world == 1:
+    full_stream_check = True
+    prefix_div = 64
+    if which == "config4":
+        wl, total = wl_config4(), args.config4_records or 1_000_000_000
+        kernel_name = "k_ingest_s"
+        full_stream_check = False  # streaming 1 B records through one GPU would take minutes: prefix parity + rank agreement only
+        prefix_div = 512
+    elif D.world == 1:
         wl, total = wl_config2(), args.secondary_records or 1_000_000
-        kernel_name = "k_ingest<long> (warp-cooperative walk decode)"
+        kernel_name = "k_ingest_l (node-parallel walk decode)"
     else:
         wl, total = wl_config3(), args.secondary_records or 200_000_000
         kernel_name = "k_ingest_s"
@@ -493,13 +511,13 @@ def secondary_config(D, args, cudart):
     t0 = time.perf_counter()
     bufs, nbytes, walk = load_resident(ctx, wl, r0, r1, cudart)
     t_gen = time.perf_counter() - t0
-    steps = 10 if D.world == 1 else 5
+    steps = 10 if (D.world == 1 and which == "auto") else 5
     t = timed_steps(D, ctx, bufs, steps, 3, sample_clocks=False)
     total_records = D.reduce(float(t["n_rec"]), "sum")
     res = gpu_results(ctx, S)
     ranks_equal = cross_rank_check(D, res)
     # parity: a prefix of the stream (all of it at N=1, 1/64 of the sharded 200 M) through a fresh single-GPU context and the C++ oracle
-    prefix = total if D.world == 1 else max(total // 64, 1)
+    prefix = total if (D.world == 1 and which == "auto") else max(total // prefix_div, 1)
     par = {"checked": False}
     p_hit = 0.0
     cpu = None
@@ -520,7 +538,7 @@ def secondary_config(D, args, cudart):
         par = {"checked": True, "equal": bool(eq), "first_difference": where, "what": f"first {o.n_records} records (a fresh single-GPU context) "
                f"vs the C++ oracle: species counts, bases, covered bases, trio bases, path sums, hap trio counts of all {S} species"}
         cpu = {"value": o.n_records / cdt, "unit": "records/s", "cores": o.threads, "kind": "port", "sample": f"first {o.n_records} records"}
-        if D.world > 1:  # shard invariance at full size: one GPU streaming every rank's batch must give the reduced result
+        if D.world > 1 and full_stream_check:  # shard invariance at full size: one GPU streaming every rank's batch must give the reduced result
             c2.reset()
             stream_host(c2, wl, 0, per * D.world)
             c2.finalize()
@@ -661,12 +679,15 @@ def run_ours(args):
 
     graph_commit_main = ctx.graph_commit_s
     secondary = None
+    tertiary = None
     if not args.no_secondary:
         t_graph_main = t_graph
         n_trios_main = ctx.n_trios(0)
         ctx.close()
         pinned.free()
         secondary = secondary_config(D, args, cudart)
+        if args.config4 or world == 8:
+            tertiary = secondary_config(D, args, cudart, which="config4")
     else:
         t_graph_main = t_graph
         n_trios_main = ctx.n_trios(0)
@@ -684,6 +705,8 @@ def run_ours(args):
             "clocks": t["clocks"], "e2e": e2e, "gpu_launches": t["launches"], "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "secondary": secondary,
         }
+        if tertiary is not None:
+            line["tertiary"] = tertiary
         print(json.dumps(line), flush=True)
     if D.dist:
         D.dist.destroy_process_group()

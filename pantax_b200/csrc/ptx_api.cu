@@ -149,6 +149,9 @@ struct ptx_ctx {
     int force_tile = 0;  // PTX_TILE_BYTES env override for single-pass chunks of k_ingest_s (multiple of 512)
     bool keep_text = false;  // PTX_KEEP_TEXT=1: never hand the text of resolved chunks back (debugging)
     bool no_sort = false;    // PTX_NO_SORT=1: k_ingest_s keeps file order inside a tile (measurements)
+    int pf_waves = 1;          // PTX_PF_WAVES: L2 prefetch distance of the ingest kernels in waves of resident CTAs (0: off)
+    int n_sm = 148;
+    bool ds_cas_first = false;  // PTX_DS_CAS_FIRST=1: id-set insert with the CAS before the load (measured: k_apply 0.933 vs 0.936 ms - no gain)
     int l2_hints = 1;        // PTX_L2_HINTS: bit 0 = graph arrays evict-last (k_apply 0.969 -> 0.938 ms), bit 1 = GAF text evict-first (no gain), bit 2 = id-set loads evict-first (slower: 1.00 ms); IngestArgs::pol_*
     bool old_short = false;  // PTX_OLD_INGEST=1: round 1's byte-at-a-time short-read kernel (A/B measurements)
     bool long_new = true;    // PTX_LONG_NEW=0: round 1's k_ingest<long> (warp-cooperative walk decode) instead of k_ingest_l (A/B measurements: 1.66 vs 1.40 ms on configs[2])
@@ -176,6 +179,8 @@ struct ptx_ctx {
     // by ptx_equal_length - the replay passes run from the record tables.  Device memory per GAF byte drops from ~3x to ~0.6x.
     struct TextBuf { uint8_t* buf; size_t cap; cudaEvent_t copied; };
     std::vector<TextBuf> text_pool;
+    std::vector<int64_t> first_rows;   // multi-GPU: read_len of the first 1000 non-U rows over all ranks (first_rows_exchange)
+    bool first_rows_global = false;
     int64_t labelled_rows_known = 0;  // non-U rows of the chunks resolved so far (exact-mode chunks count as 0: their text is kept)
     double seen_nodes_per_byte = 0;   // walk nodes per text byte of the last resolved chunk: sizes the CSR buffer of single-pass chunks
     uint8_t* scratch = nullptr;
@@ -332,6 +337,7 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.tile_bytes = ch.tile_bytes;
     a.over_bytes = ch.over_bytes;
     a.no_sort = ctx->no_sort ? 1u : 0u;
+    a.pf_dist = ctx->pf_waves > 0 ? (uint32_t)(ctx->pf_waves * ctx->n_sm * (ch.long_mode ? 3 : 7)) : 0u;  // resident CTAs per SM of k_ingest_l / k_ingest_s
     a.old_short = ctx->old_short ? 1u : 0u;
     a.long_new = ctx->long_new ? 1u : 0u;
     a.long_mode = ch.long_mode;
@@ -359,6 +365,7 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.pol_keep = (ctx->l2_hints & 1) ? 0x14F0000000000000ull : 0x1000000000000000ull;    // createpolicy evict_last / evict_normal, fraction 1.0
     a.pol_stream = (ctx->l2_hints & 2) ? 0x12F0000000000000ull : 0x1000000000000000ull;  // evict_first
     a.pol_ds = (ctx->l2_hints & 4) ? 0x12F0000000000000ull : 0x1000000000000000ull;
+    a.ds_cas_first = ctx->ds_cas_first ? 1u : 0u;
     a.pair_key = ctx->d_pair_key;
     a.pair_val = ctx->d_pair_val;
     a.flags = ctx->d_flags;
@@ -481,6 +488,7 @@ void chunk_free(Chunk& ch) {
 }
 
 int xchg_ensure(ptx_ctx* ctx, int64_t records);
+int first_rows_exchange(ptx_ctx* ctx, const std::vector<unsigned long long>& counts);
 
 // (re)allocate the record table of a chunk for `slots` line slots
 int chunk_table_ensure(ptx_ctx* ctx, Chunk& ch, int64_t slots) {
@@ -875,6 +883,8 @@ int exchange_begin(ptx_ctx* ctx) {
     unsigned long long* d_par = d_all + (size_t)(P + 1) * P;  // [2P] merge offsets, counts
     std::vector<unsigned long long> all((size_t)(P + 1) * P);
     for (int attempt = 0;; ++attempt) {
+        // min(non-U rows of this rank, 1000) rides in the upper bits of the overflow marker (ptx_equal_length needs the first 1000 of the whole GAF)
+        launch_count_labelled(ctx->d_hist, (uint32_t)ctx->sp.size(), d_cur + P, ctx->st);
         if ((rc = nccl_check(ctx, g_nccl.AllGather(d_cur, d_all, P + 1, ncclUint64, ctx->comm, ctx->st), "ncclAllGather(box fills)"))) return rc;
         CU(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaStreamSynchronize(ctx->st));
@@ -883,7 +893,7 @@ int exchange_begin(ptx_ctx* ctx) {
         unsigned long long worst = 0;
         bool over = false;
         for (int q = 0; q < P; ++q) {
-            if (all[(size_t)q * (P + 1) + P]) over = true;  // rank q dropped an entry
+            if (all[(size_t)q * (P + 1) + P] & 1ull) over = true;  // rank q dropped an entry
             for (int r = 0; r < P; ++r) worst = std::max(worst, all[(size_t)q * (P + 1) + r]);
         }
         if (!over) break;
@@ -906,6 +916,11 @@ int exchange_begin(ptx_ctx* ctx) {
             IngestArgs a = make_args(ctx, ch);
             launch_apply(a, (uint32_t)ch.n_slots, MODE_CLASSIFY, ctx->st);
         }
+    }
+    if (P > 1 && !ctx->first_rows_global) {  // rank 0's batch holds fewer than 1000 non-U rows (tiny inputs): the first 1000 span ranks
+        std::vector<unsigned long long> counts((size_t)P);
+        for (int q = 0; q < P; ++q) counts[(size_t)q] = all[(size_t)q * (P + 1) + P] >> 8;
+        if (counts[0] < 1000 && (rc = first_rows_exchange(ctx, counts))) return rc;
     }
     // what is new since the previous exchange (ptx_finalize may run more than once)
     std::vector<unsigned long long> send_n(P, 0), recv_n(P, 0), roff(P, 0), par(2 * (size_t)P, 0);
@@ -1056,6 +1071,9 @@ int ptx_create(int device, ptx_ctx** out) {
     if (const char* e = getenv("PTX_KEEP_TEXT")) ctx->keep_text = atoi(e) != 0;
     if (const char* e = getenv("PTX_SCATTER")) ctx->scatter_var = atoi(e);
     if (const char* e = getenv("PTX_L2_HINTS")) ctx->l2_hints = atoi(e);
+    if (const char* e = getenv("PTX_DS_CAS_FIRST")) ctx->ds_cas_first = atoi(e) != 0;
+    if (const char* e = getenv("PTX_PF_WAVES")) ctx->pf_waves = atoi(e);
+    cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (const char* e = getenv("PTX_LONG_MODE")) ctx->force_long = atoi(e) ? 1 : 0;
     if (const char* e = getenv("PTX_TEST_BOX_CAP")) ctx->test_box_cap = atoll(e);
     if (const char* e = getenv("PTX_NO_SINGLE_PASS")) ctx->single_pass_ok = atoi(e) == 0;
@@ -1646,6 +1664,8 @@ static int reset_impl(ptx_ctx* ctx, bool keep_buffers) {
     if (!keep_buffers) ctx->labels_in_n = 0;  // supplied labels belong to the input that is being dropped
     ctx->total_records = 0;
     ctx->labelled_rows_known = 0;
+    ctx->first_rows.clear();
+    ctx->first_rows_global = false;
     ctx->ds_records = 0;
     ctx->cov_reduced = false;
     ctx->h_flags[0] = ctx->h_flags[1] = ctx->h_flags[2] = 0;
@@ -1725,16 +1745,17 @@ int ptx_species_counts(ptx_ctx* ctx, int64_t* counts) {
     return PTX_OK;
 }
 
-// profile.rs:311-322, on the host: needs only the first ~1000 rows of the first chunk(s)
-int ptx_equal_length(ptx_ctx* ctx, int* is_equal, int64_t* read_len) {
-    if (!ctx || !is_equal || !read_len) return PTX_E_INVALID;
-    cudaSetDevice(ctx->device);
+}  // extern "C"
+namespace {
+// read_len (column 2; NULL_I64 if null) of the first <= 1000 non-U rows this context ingested, in GAF order (profile.rs:311-322):
+// on the host, from the first ~1000 lines of the first chunk(s)
+int local_first_rows(ptx_ctx* ctx, std::vector<int64_t>& vals) {
+    vals.clear();
     {
         int rc = chunks_resolve(ctx);
         if (rc) return rc;
     }
     CU(cudaStreamSynchronize(ctx->st));
-    std::vector<int64_t> distinct;  // a null read_len (NULL_I64) counts as a value, as in polars' unique()
     int64_t seen = 0;
     for (auto& ch : ctx->chunks) {
         if (seen >= 1000) break;
@@ -1774,13 +1795,60 @@ int ptx_equal_length(ptx_ctx* ctx, int* is_equal, int64_t* read_len) {
                 if (lab[k] == LABEL_U) continue;
                 RecParse r;
                 parse_record(text.data() + lines[k].first, 0, 0xFFFFFFF0u, r, 1u, nullptr, 0, 0);  // the line's own '\n' stops the scanners;  // same column rules as the kernel
-                if (std::find(distinct.begin(), distinct.end(), r.qlen) == distinct.end()) distinct.push_back(r.qlen);
+                vals.push_back(r.qlen);
                 ++seen;
             }
             rec += (int64_t)lines.size();
             text_off += consumed;
         }
     }
+    return PTX_OK;
+}
+
+// multi-GPU, inside ptx_finalize (a collective): the first 1000 non-U rows of the GAF are rank 0's - unless rank 0's read batch holds
+// fewer; then the ranks behind it supply the rest, in rank order.  `counts[q]` = min(non-U rows of rank q, 1000), known to every
+// rank from the fills all-gather, so all ranks take this branch together.
+int first_rows_exchange(ptx_ctx* ctx, const std::vector<unsigned long long>& counts) {
+    const int P = ctx->n_ranks;
+    const size_t SLOT = 1001;  // count + 1000 values
+    std::vector<int64_t> mine;
+    int rc = local_first_rows(ctx, mine);
+    if (rc) return rc;
+    std::vector<int64_t> host((size_t)(P + 1) * SLOT, 0);
+    host[(size_t)P * SLOT] = (int64_t)mine.size();
+    std::copy(mine.begin(), mine.end(), host.begin() + (size_t)P * SLOT + 1);
+    int64_t* d = nullptr;
+    if ((rc = dalloc(ctx, &d, (size_t)(P + 1) * SLOT, false))) return rc;
+    CU(cudaMemcpyAsync(d + (size_t)P * SLOT, host.data() + (size_t)P * SLOT, SLOT * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
+    if ((rc = nccl_check(ctx, g_nccl.AllGather(d + (size_t)P * SLOT, d, SLOT, ncclUint64, ctx->comm, ctx->st), "ncclAllGather(first rows)"))) { cudaFree(d); return rc; }
+    CU(cudaMemcpyAsync(host.data(), d, (size_t)P * SLOT * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    cudaFree(d);
+    ctx->first_rows.clear();
+    for (int q = 0; q < P && ctx->first_rows.size() < 1000; ++q) {
+        const int64_t n = std::min<int64_t>(host[(size_t)q * SLOT], 1000);
+        (void)counts;
+        for (int64_t k = 0; k < n && ctx->first_rows.size() < 1000; ++k) ctx->first_rows.push_back(host[(size_t)q * SLOT + 1 + (size_t)k]);
+    }
+    ctx->first_rows_global = true;
+    return PTX_OK;
+}
+}  // namespace
+extern "C" {
+
+// profile.rs:311-322: are the read lengths of the first 1000 non-U rows all equal?
+int ptx_equal_length(ptx_ctx* ctx, int* is_equal, int64_t* read_len) {
+    if (!ctx || !is_equal || !read_len) return PTX_E_INVALID;
+    cudaSetDevice(ctx->device);
+    std::vector<int64_t> vals;
+    if (ctx->first_rows_global) vals = ctx->first_rows;  // multi-GPU: gathered over the ranks by ptx_finalize
+    else {
+        int rc = local_first_rows(ctx, vals);
+        if (rc) return rc;
+    }
+    std::vector<int64_t> distinct;  // a null read_len (NULL_I64) counts as a value, as in polars' unique()
+    for (int64_t v : vals)
+        if (std::find(distinct.begin(), distinct.end(), v) == distinct.end()) distinct.push_back(v);
     *is_equal = distinct.size() == 1 ? 1 : 0;
     *read_len = distinct.size() == 1 ? distinct[0] : 0;
     return PTX_OK;

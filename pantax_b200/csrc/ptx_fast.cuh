@@ -113,11 +113,10 @@ PTX_HD void ld8(const Words& W, uint32_t p, uint32_t& lo, uint32_t& hi) {
     hi = funnel_r(w1, w2, sh);
 }
 
-// four decimal digits held as byte VALUES 0..9, byte 0 the most significant -> their number
-PTX_HD uint32_t swar4(uint32_t v) {
-    const uint32_t t = v * 10u + (v >> 8);  // byte 0 = 10 d0 + d1, byte 2 = 10 d2 + d3 (no byte exceeds 99: nothing carries)
-    return (t & 0xFFu) * 100u + ((t >> 16) & 0xFFu);
-}
+// four decimal digits held as byte VALUES 0..9, byte 0 the most significant -> their number: one dot product weighs the
+// first three (100, 10, 1), one multiply-add appends the fourth - both on the FMA pipe.  (Bytes that are no digits give some
+// number; the callers throw it away.)
+PTX_HD uint32_t swar4(uint32_t v) { return dot4(v, 0x00010A64u, 0u) * 10u + (v >> 24); }
 // n <= 8 digit bytes (already XORed with '0') at the low end of (hi:lo) -> right-aligned: byte 7 = last digit
 PTX_HD void align8(uint32_t lo, uint32_t hi, uint32_t n, uint32_t& xl, uint32_t& xh) {
     const uint64_t x = (((uint64_t)hi << 32) | (uint64_t)lo) << (8u * (8u - n));

@@ -94,6 +94,7 @@ struct IngestArgs {
     uint32_t n_tiles;
     uint32_t tile_bytes;         // bytes of text per CTA: a multiple of 512 (k_ingest_s) / of 4096 (k_ingest<>, and whenever micro_base is used)
     uint32_t over_bytes;         // k_ingest_s: bytes staged behind the tile (the tail of its last line): 512..OVER, multiple of 512
+    uint32_t pf_dist;            // k_ingest_s / k_ingest_l: a CTA prefetches the text of tile blockIdx + pf_dist into the L2 (0: off)
     uint32_t no_sort;            // k_ingest_s: keep the lines of a tile in file order (PTX_NO_SORT=1, measurements)
     uint32_t long_mode;          // long lines: warp-cooperative walk decode (k_ingest<true>)
     uint32_t long_new;           // PTX_LONG_NEW=1: k_ingest_l instead of k_ingest<true> for long lines (measurements)
@@ -145,6 +146,7 @@ struct IngestArgs {
     // id-set slots - is fetched evict-first, the graph arrays every read gathers from (ninfo, bases, bitmap, trio table)
     // evict-last, so that 1.7 GB of streams per step do not push 30 MB of node arrays out of the L2
     uint64_t pol_keep, pol_stream, pol_ds;
+    uint32_t ds_cas_first;  // id-set insert: CAS before looking (PTX_DS_CAS_FIRST, measurements)
 };
 
 // launchers (ptx_kernels.cu); all asynchronous on `st`
@@ -153,6 +155,7 @@ void launch_count_records(const uint8_t* text, uint64_t n_bytes, uint32_t n_micr
 void launch_ingest(const IngestArgs& a, cudaStream_t st);
 constexpr uint32_t ENTRIES_FROM_DEVICE = 0xFFFFFFFFu;  // launch_apply: take the entry count (and the abandon flag) from a.cursors
 void launch_apply(const IngestArgs& a, uint32_t n_entries, int mode, cudaStream_t st);
+void launch_count_labelled(const unsigned long long* hist, uint32_t S, unsigned long long* dst, cudaStream_t st);
 void launch_hist_merge(const unsigned long long* chunk_hist, unsigned long long* hist, uint32_t n, uint32_t* cursors, cudaStream_t st);
 void launch_tile_rows(const uint4* tile_info, uint32_t* rows, uint32_t n_tiles, cudaStream_t st);
 void launch_labels_from_table(const uint4* tile_info, const uint64_t* tile_off, const uint4* meta_b, const uint16_t* row_key, uint32_t* labels,

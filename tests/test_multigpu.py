@@ -102,3 +102,51 @@ def test_create_multi_drives_all_gpus_from_one_process(reserve):
     finally:
         for ctx in ctxs:
             ctx.close()
+
+
+@pytest.mark.gpu
+def test_equal_length_takes_the_first_1000_rows_of_the_whole_gaf_not_of_rank_0():
+    """profile.rs:311-322 looks at the first 1000 non-U rows of the GAF.  With the reads sharded by batch, rank 0 may hold
+    fewer than 1000 of them: ptx_finalize then gathers the rest from the ranks behind it, in rank order.  Here every read
+    of the first two shards is 150 bp and one read in the third shard (row ~700) is not."""
+    n = _gpu_count()
+    if n < 2:
+        pytest.skip(f"needs >= 2 GPUs on one box (found {n})")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import dataset_graphs, synth
+    from oracle import pantax_oracle as opy
+    from pantax_b200 import api
+    from pantax_b200.shard import shard_bounds_bytes
+
+    P = min(n, 4)
+    ds = synth.Dataset(94, [20000, 5000], [4, 2])
+    graphs = dataset_graphs(ds)
+    base = ds.gaf(7, 0, 900, synth.GafParams())
+    for odd_at in (700, 850):  # inside a later shard, within the first 1000 rows
+        lines = base.split(b"\n")
+        f = lines[odd_at].split(b"\t")
+        f[1] = b"149"
+        lines[odd_at] = b"\t".join(f)
+        gaf = b"\n".join(lines)
+        rows = opy.rcls_profile(gaf, ds.ranges())
+        want = opy.equal_length_test(rows)
+        assert want[0] is False  # (the odd row is classified; otherwise the case tests nothing)
+        for data, expect in ((gaf, want), (base, opy.equal_length_test(opy.rcls_profile(base, ds.ranges())))):
+            ctxs = api.PantaxGpu.create_multi(list(range(P)), 0)
+            try:
+                for ctx in ctxs:
+                    ctx.set_ranges(ds.ranges())
+                    for s, g in enumerate(graphs):
+                        ctx.upload_graph(s, g[0], g[1])
+                    ctx.commit_graphs()
+                bounds = shard_bounds_bytes(data, P)
+                assert bounds[0][1] < len(data) // 2  # rank 0 holds well under 1000 rows
+                for ctx, (lo, hi) in zip(ctxs, bounds):
+                    ctx.ingest_gaf(data[lo:hi], is_last=True)
+                api.PantaxGpu.finalize_multi(ctxs)
+                for ctx in ctxs:
+                    eq, rl = ctx.equal_length()
+                    assert (eq, rl if eq else None) == expect
+            finally:
+                for ctx in ctxs:
+                    ctx.close()
