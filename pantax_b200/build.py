@@ -54,7 +54,7 @@ HOST_BIN = os.path.join(HERE, "pantax-gpu-profile")
 def build_host(verbose: bool = False) -> str:
     """The C++ host driver over the C ABI (file formats, f64 tail, TSV writers)."""
     cmd = ["g++", "-O2", "-std=c++17", "-Wall", HOST_SRC, "-o", HOST_BIN, "-L" + HERE, "-lpantax_gpu", "-Wl,-rpath,$ORIGIN",
-           "-Wl,-rpath-link," + "/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-lcudart", "-ldl"]
+           "-Wl,-rpath-link," + "/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-lcudart", "-ldl", "-lpthread"]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)

@@ -98,6 +98,7 @@ struct Chunk {
     unsigned long long* chunk_hist = nullptr;  // single-pass: species counts of this chunk (merged if not abandoned)
     uint32_t tile_info_cap = 0;
     size_t hist_cap = 0;
+    uint32_t hist_copies = 1;
     bool single_pass = false, pending = false, labels_ready = false;
     int64_t est_records = 0;
     int64_t slots_cap = 0, nodes_cap = 0;
@@ -358,6 +359,8 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.rank = (uint32_t)ctx->rank;
     a.ranges = ranges_view(ctx);
     a.hist = ctx->d_hist;
+    a.hist_copies = 1;
+    a.hist_stride = 0;
     a.ds = ctx->d_ds;
     a.ds_shift = 64 - log2_ceil(ctx->ds_cap);
     a.ds_mask = ctx->ds_cap - 1;
@@ -383,6 +386,8 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
         a.row_key = ch.row_key;
         a.slots_cap = (uint32_t)std::min<int64_t>(ch.slots_cap, 0xFFFFFFF0ll);
         a.hist = ch.chunk_hist;
+        a.hist_copies = ch.hist_copies;
+        a.hist_stride = (uint32_t)(std::max<size_t>(ctx->sp.size(), 1) * 4);
     }
     return a;
 }
@@ -650,12 +655,15 @@ int chunk_process_single(ptx_ctx* ctx, Chunk& ch) {
         ch.tile_info_cap = ch.n_tiles;
     }
     const size_t S4 = std::max<size_t>(ctx->sp.size(), 1) * 4;
-    if (ch.hist_cap < S4) {
+    // the species counts of a chunk go to HIST_COPIES private copies (tile t adds to copy t % copies; k_hist_merge sums them): an abundant
+    // species is one hot address per copy instead of one for the whole grid
+    ch.hist_copies = (uint32_t)std::min<size_t>(64, std::max<size_t>(1, ((size_t)8 << 20) / (S4 * sizeof(unsigned long long))));
+    if (ch.hist_cap < S4 * ch.hist_copies) {
         dfree(ch.chunk_hist);
-        CU(cudaMalloc((void**)&ch.chunk_hist, S4 * sizeof(unsigned long long)));
-        ch.hist_cap = S4;
+        CU(cudaMalloc((void**)&ch.chunk_hist, S4 * ch.hist_copies * sizeof(unsigned long long)));
+        ch.hist_cap = S4 * ch.hist_copies;
     }
-    CU(cudaMemsetAsync(ch.chunk_hist, 0, S4 * sizeof(unsigned long long), ctx->st));
+    CU(cudaMemsetAsync(ch.chunk_hist, 0, S4 * ch.hist_copies * sizeof(unsigned long long), ctx->st));
     ch.est_records = (int64_t)(est_rows * 1.25) + 4096;
     if ((rc = ds_ensure(ctx, ctx->pending_records + ch.est_records))) return rc;
     if (ctx->comm) {
@@ -674,7 +682,7 @@ int chunk_process_single(ptx_ctx* ctx, Chunk& ch) {
     ev_begin(ctx, ctx->ev_apply);
     launch_apply(a, ENTRIES_FROM_DEVICE, MODE_CLASSIFY | (cover ? MODE_COVER : 0), ctx->st);
     ev_end(ctx, ctx->ev_apply);
-    launch_hist_merge(ch.chunk_hist, ctx->d_hist, (uint32_t)S4, a.cursors, ctx->st);
+    launch_hist_merge(ch.chunk_hist, ctx->d_hist, (uint32_t)S4, ch.hist_copies, a.cursors, ctx->st);
     CU(cudaMemcpyAsync(ch.h_cur, a.cursors, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaEventRecord(ch.done, ctx->st));
     CU(cudaGetLastError());

@@ -26,6 +26,9 @@ constexpr int INGEST_THREADS = 256;
 #define PTX_SHORT_THREADS 128
 #endif
 constexpr int SHORT_THREADS = PTX_SHORT_THREADS;       // k_ingest_s: small CTAs, 7 per SM - the barriers between its phases overlap across CTAs
+#ifndef PTX_APPLY_MINB
+#define PTX_APPLY_MINB 6  // k_apply: resident CTAs of 256 threads per SM the register allocation aims at: 6 -> 40 registers, no spills (0.923 ms; 8 -> 32 registers with a 48-byte stack: 0.931 ms; 4 -> 46 registers: 1.019 ms)
+#endif
 #ifndef PTX_SHORT_RECCAP
 #define PTX_SHORT_RECCAP 512
 #endif
@@ -122,7 +125,8 @@ struct IngestArgs {
     uint64_t box_cap;
     uint32_t n_ranks, rank;
     RangesView ranges;
-    unsigned long long* hist;   // [S*4]
+    unsigned long long* hist;   // [hist_copies][S*4]: tile t adds to copy t % hist_copies (single-pass chunks; 1 copy otherwise)
+    uint32_t hist_copies, hist_stride;
     ulonglong2* ds;             // read-id set slots
     uint32_t ds_shift;          // 64 - log2(capacity)
     uint64_t ds_mask;
@@ -156,7 +160,7 @@ void launch_ingest(const IngestArgs& a, cudaStream_t st);
 constexpr uint32_t ENTRIES_FROM_DEVICE = 0xFFFFFFFFu;  // launch_apply: take the entry count (and the abandon flag) from a.cursors
 void launch_apply(const IngestArgs& a, uint32_t n_entries, int mode, cudaStream_t st);
 void launch_count_labelled(const unsigned long long* hist, uint32_t S, unsigned long long* dst, cudaStream_t st);
-void launch_hist_merge(const unsigned long long* chunk_hist, unsigned long long* hist, uint32_t n, uint32_t* cursors, cudaStream_t st);
+void launch_hist_merge(const unsigned long long* chunk_hist, unsigned long long* hist, uint32_t n, uint32_t copies, uint32_t* cursors, cudaStream_t st);
 void launch_tile_rows(const uint4* tile_info, uint32_t* rows, uint32_t n_tiles, cudaStream_t st);
 void launch_labels_from_table(const uint4* tile_info, const uint64_t* tile_off, const uint4* meta_b, const uint16_t* row_key, uint32_t* labels,
                               uint32_t n_tiles, cudaStream_t st);

@@ -980,6 +980,56 @@ __global__ void __launch_bounds__(INGEST_THREADS, LONG ? 3 : 4) k_ingest(const I
     }
 }
 
+// ---- species counts of the records a warp holds (profile.rs:219-232, 264-277): reads, sum of read lengths, #(3 <= mapq <= 60),
+// #(mapq == 60).  The lanes of one species add ONCE: the whole warp when it is one species (short reads of a single-species
+// sample), otherwise the groups match.any finds.  With hundreds of species a tile's ~124 records are nearly all different species,
+// so a per-tile table in shared memory (round 1) merged nothing and cost its initialisation, a CAS per record and a flush of ~4
+// global atomics per distinct species; an abundant species still collapses to one set of REDs per warp.
+__device__ __forceinline__ void count_species_warp(unsigned long long* hist, bool cnt, uint32_t label, unsigned long long ql, bool lm, bool uq,
+                                                   uint32_t lane) {
+    const unsigned mm = __ballot_sync(0xffffffffu, cnt);
+    if (mm == 0u) return;
+    const int leader0 = __ffs(mm) - 1;
+    const uint32_t lab0 = __shfl_sync(0xffffffffu, label, leader0);
+    const bool uniform = __all_sync(0xffffffffu, !cnt || label == lab0);
+    const uint32_t c_lm = (cnt && lm) ? 1u : 0u, c_uq = (cnt && uq) ? 1u : 0u;
+    const unsigned long long qv = cnt ? ql : 0ull;
+    if (uniform) {
+        const uint32_t n1 = __popc(mm);
+        const uint32_t n3 = __reduce_add_sync(0xffffffffu, c_lm);
+        const uint32_t n4 = __reduce_add_sync(0xffffffffu, c_uq);
+        unsigned long long s;
+        if (__all_sync(0xffffffffu, qv < (1ull << 26))) {  // 32 x 2^26 fits 32 bits: one REDUX
+            s = (unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)qv);
+        } else {
+            s = qv;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        }
+        if ((int)lane == leader0) {
+            unsigned long long* hp = hist + 4ull * lab0;
+            atomicAdd(hp + 0, (unsigned long long)n1);
+            atomicAdd(hp + 1, s);
+            if (n3) atomicAdd(hp + 2, (unsigned long long)n3);
+            if (n4) atomicAdd(hp + 3, (unsigned long long)n4);
+        }
+        return;
+    }
+    const unsigned b_lm = __ballot_sync(0xffffffffu, c_lm != 0u), b_uq = __ballot_sync(0xffffffffu, c_uq != 0u);
+    const unsigned peers = __match_any_sync(0xffffffffu, cnt ? label : (0x80000000u | lane));  // (labels are species indices < 2^31; idle lanes stay alone)
+    if (!cnt) return;
+    unsigned long long s = 0;
+    for (unsigned m = peers; m; m &= m - 1u) s += __shfl_sync(peers, qv, __ffs(m) - 1);  // the lanes of a group run the same trip count
+    if ((int)lane == __ffs(peers) - 1) {
+        unsigned long long* hp = hist + 4ull * label;
+        const uint32_t n3 = __popc(b_lm & peers), n4 = __popc(b_uq & peers);
+        atomicAdd(hp + 0, (unsigned long long)__popc(peers));
+        atomicAdd(hp + 1, s);
+        if (n3) atomicAdd(hp + 2, (unsigned long long)n3);
+        if (n4) atomicAdd(hp + 3, (unsigned long long)n4);
+    }
+}
+
 // =====================================================================================
 // k_ingest_s: the short-read ingest kernel around a structural index of the tile.
 //   A. every thread classifies 16-byte pieces of the staged text (LDS.128, conflict-free): newline and tab flags,
@@ -1020,8 +1070,6 @@ __global__ void __launch_bounds__(SHORT_THREADS, PTX_SHORT_MINB) k_ingest_s(cons
     uint16_t* rec_start = reinterpret_cast<uint16_t*>(stash + SHORT_STASH_CAP * SHORT_THREADS);  // [SHORT_REC_CAP] line starts of the round
     uint16_t* order = rec_start + SHORT_REC_CAP;                                             // [SHORT_REC_CAP] lines by length
     uint16_t* inv_pre = order + SHORT_REC_CAP;                                               // [SHORT_REC_CAP] invalid line slots before slot k
-    uint32_t* hkey = reinterpret_cast<uint32_t*>(inv_pre + SHORT_REC_CAP);                   // [HIST_SLOTS] (S > 1 only)
-    uint32_t* hval = hkey + HIST_SLOTS;                                                      // [HIST_SLOTS][4]
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t warp_tot[SHORT_THREADS / 32];
     __shared__ uint32_t bin_cnt[64];
@@ -1051,10 +1099,11 @@ __global__ void __launch_bounds__(SHORT_THREADS, PTX_SHORT_MINB) k_ingest_s(cons
     if (tid < STAGE_PAD / 4u) reinterpret_cast<uint32_t*>(stage + stage_bytes)[tid] = 0x0a0a0a0au;
     if (tid < 2u) { nlw[bm_words + tid] = 0xFFFFFFFFu; tabw[bm_words + tid] = 0xFFFFFFFFu; }
     if (tid < 64u) bin_cnt[tid] = 0;
-    const bool hist_smem = a.ranges.S > 1;
-    if (hist_smem)
-        for (uint32_t i = tid; i < HIST_SLOTS * 5u; i += SHORT_THREADS) hkey[i] = i < HIST_SLOTS ? LABEL_U : 0u;
     const uint32_t* sstart = a.ranges.sstart;
+    __shared__ uint32_t pv[CLASSIFY_PIVOTS];  // every stride-th range start: the first level of the species search
+    const int pv_stride = a.ranges.S > CLASSIFY_PIVOTS ? (a.ranges.S + CLASSIFY_PIVOTS - 1) / CLASSIFY_PIVOTS : 1;
+    const int npv = (a.ranges.disjoint && a.ranges.S > 1) ? (a.ranges.S + pv_stride - 1) / pv_stride : 0;
+    for (int i = (int)tid; i < npv; i += SHORT_THREADS) pv[i] = sstart[i * pv_stride];  // (visible behind the barrier that follows the structural index)
     const bool single_pass = a.micro_base == nullptr;
     const uint32_t rec_base = single_pass ? 0u : (uint32_t)a.micro_base[(uint64_t)blockIdx.x * (tile_bytes / MICRO)];
     const uint32_t glim = (uint32_t)min((uint64_t)0xFFFF0000ull, a.padded_bytes - t0);
@@ -1268,66 +1317,12 @@ __global__ void __launch_bounds__(SHORT_THREADS, PTX_SHORT_MINB) k_ingest_s(cons
                         label = LABEL_U;
                     }
                 } else {
-                    label = classify(R, vmin, vmax, sstart);
+                    label = classify_pivots(R, vmin, vmax, sstart, pv, npv, pv_stride);
                 }
                 if (!single_pass) a.labels[row] = label;
             }
             __syncwarp();
-            {   // ---- species counts (profile.rs:219-232, 264-277), warp-aggregated when the warp is one species
-                const bool cnt = has && label != LABEL_U;
-                const unsigned mm = __ballot_sync(0xffffffffu, cnt);
-                if (mm) {
-                    const int leader = __ffs(mm) - 1;
-                    const uint32_t lab0 = __shfl_sync(0xffffffffu, label, leader);
-                    const bool uniform = __all_sync(0xffffffffu, !cnt || label == lab0);
-                    const uint32_t c_lm = (cnt && lm) ? 1u : 0u, c_uq = (cnt && uq) ? 1u : 0u;
-                    const unsigned long long qv = cnt ? ql : 0ull;
-                    if (uniform) {
-                        const uint32_t n1 = __popc(mm);
-                        const uint32_t n3 = __reduce_add_sync(0xffffffffu, c_lm);
-                        const uint32_t n4 = __reduce_add_sync(0xffffffffu, c_uq);
-                        unsigned long long s;
-                        if (__all_sync(0xffffffffu, qv < (1ull << 26))) {  // 32 x 2^26 fits 32 bits: one REDUX
-                            s = (unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)qv);
-                        } else {
-                            s = qv;
-#pragma unroll
-                            for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-                        }
-                        if ((int)lane == leader) {
-                            unsigned long long* hp = a.hist + 4ull * lab0;
-                            atomicAdd(hp + 0, (unsigned long long)n1);
-                            atomicAdd(hp + 1, s);
-                            if (n3) atomicAdd(hp + 2, (unsigned long long)n3);
-                            if (n4) atomicAdd(hp + 3, (unsigned long long)n4);
-                        }
-                    } else if (cnt) {
-                        bool done = false;
-                        if (qv < (1ull << 16)) {  // a tile holds < 64 K lines: the 32-bit sum cannot wrap
-                            uint32_t hs = (label * 0x9E3779B1u) >> (32 - HIST_SLOTS_LOG2);
-                            for (int t = 0; t < 4 && !done; ++t) {
-                                const uint32_t old = atomicCAS(&hkey[hs], LABEL_U, label);
-                                if (old == LABEL_U || old == label) {
-                                    uint32_t* hv = hval + 4u * hs;
-                                    atomicAdd(hv + 0, 1u);
-                                    if (c_lm) atomicAdd(hv + 1, 1u);
-                                    if (c_uq) atomicAdd(hv + 2, 1u);
-                                    if (qv) atomicAdd(hv + 3, (uint32_t)qv);
-                                    done = true;
-                                }
-                                hs = (hs + 1u) & (HIST_SLOTS - 1u);
-                            }
-                        }
-                        if (!done) {
-                            unsigned long long* hp = a.hist + 4ull * label;
-                            atomicAdd(hp + 0, 1ull);
-                            atomicAdd(hp + 1, qv);
-                            if (c_lm) atomicAdd(hp + 2, 1ull);
-                            if (c_uq) atomicAdd(hp + 3, 1ull);
-                        }
-                    }
-                }
-            }
+            count_species_warp(a.hist + (size_t)(blockIdx.x % a.hist_copies) * a.hist_stride, has && label != LABEL_U, label, ql, lm, uq, lane);  // species counts (profile.rs:219-232, 264-277)
             // ---- emit the record for k_apply: id hash, label, alignment interval and the walk as CSR node ids
             const bool labelled = has && label != LABEL_U;
             const bool eligible = labelled && cols_ok;
@@ -1405,18 +1400,6 @@ __global__ void __launch_bounds__(SHORT_THREADS, PTX_SHORT_MINB) k_ingest_s(cons
         valid_prev += n_round - inv_total;
         __syncthreads();
     }
-    if (hist_smem) {
-        for (uint32_t i = tid; i < HIST_SLOTS; i += SHORT_THREADS) {
-            const uint32_t label = hkey[i];
-            if (label == LABEL_U) continue;
-            unsigned long long* hp = a.hist + 4ull * label;
-            const uint32_t* hv = hval + 4u * i;
-            atomicAdd(hp + 0, (unsigned long long)hv[0]);
-            if (hv[3]) atomicAdd(hp + 1, (unsigned long long)hv[3]);
-            if (hv[1]) atomicAdd(hp + 2, (unsigned long long)hv[1]);
-            if (hv[2]) atomicAdd(hp + 3, (unsigned long long)hv[2]);
-        }
-    }
 }
 
 // =====================================================================================
@@ -1453,8 +1436,6 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs
     uint16_t* lend = lp6 + INGEST_THREADS;                                                   // [INGEST_THREADS] one past its closing tab (<= lp6: no column)
     uint16_t* rec_start = lend + INGEST_THREADS;                                             // [REC_CAP]
     uint16_t* inv_pre = rec_start + REC_CAP;                                                 // [REC_CAP]
-    uint32_t* hkey = reinterpret_cast<uint32_t*>(inv_pre + REC_CAP);                         // [HIST_SLOTS] (S > 1 only)
-    uint32_t* hval = hkey + HIST_SLOTS;
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t warp_tot[INGEST_THREADS / 32];
     __shared__ uint32_t inv_flag, inv_tot_s, slot_base_s, node_base_s, slow_bits[INGEST_THREADS / 32];
@@ -1481,10 +1462,11 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs
     }
     if (tid < STAGE_PAD / 4u) reinterpret_cast<uint32_t*>(stage + stage_bytes)[tid] = 0x0a0a0a0au;
     if (tid < 2u) { nlw[bm_words + tid] = 0xFFFFFFFFu; tabw[bm_words + tid] = 0xFFFFFFFFu; ndw[bm_words + tid] = 0xFFFFFFFFu; ew[bm_words + tid] = 0u; epre[bm_words + tid] = 0u; }
-    const bool hist_smem = a.ranges.S > 1;
-    if (hist_smem)
-        for (uint32_t i = tid; i < HIST_SLOTS * 5u; i += INGEST_THREADS) hkey[i] = i < HIST_SLOTS ? LABEL_U : 0u;
     const uint32_t* sstart = a.ranges.sstart;
+    __shared__ uint32_t pv[CLASSIFY_PIVOTS];  // every stride-th range start: the first level of the species search
+    const int pv_stride = a.ranges.S > CLASSIFY_PIVOTS ? (a.ranges.S + CLASSIFY_PIVOTS - 1) / CLASSIFY_PIVOTS : 1;
+    const int npv = (a.ranges.disjoint && a.ranges.S > 1) ? (a.ranges.S + pv_stride - 1) / pv_stride : 0;
+    for (int i = (int)tid; i < npv; i += INGEST_THREADS) pv[i] = sstart[i * pv_stride];  // (visible behind the barrier that follows the structural index)
     const bool single_pass = a.micro_base == nullptr;
     const uint32_t rec_base = single_pass ? 0u : (uint32_t)a.micro_base[(uint64_t)blockIdx.x * (tile_bytes / MICRO)];
     const uint32_t glim = (uint32_t)min((uint64_t)0xFFFF0000ull, a.padded_bytes - t0);
@@ -1803,61 +1785,12 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs
                         label = LABEL_U;
                     }
                 } else {
-                    label = classify(R, vmin, vmax, sstart);
+                    label = classify_pivots(R, vmin, vmax, sstart, pv, npv, pv_stride);
                 }
                 if (!single_pass) a.labels[row] = label;
             }
             __syncwarp();
-            {   // ---- species counts (profile.rs:219-232, 264-277)
-                const bool cnt = has && label != LABEL_U;
-                const unsigned mm = __ballot_sync(0xffffffffu, cnt);
-                if (mm) {
-                    const int leader = __ffs(mm) - 1;
-                    const uint32_t lab0 = __shfl_sync(0xffffffffu, label, leader);
-                    const bool uniform = __all_sync(0xffffffffu, !cnt || label == lab0);
-                    const uint32_t c_lm = (cnt && lm) ? 1u : 0u, c_uq = (cnt && uq) ? 1u : 0u;
-                    const unsigned long long qv = cnt ? ql : 0ull;
-                    if (uniform) {
-                        const uint32_t n1 = __popc(mm);
-                        const uint32_t n3 = __reduce_add_sync(0xffffffffu, c_lm);
-                        const uint32_t n4 = __reduce_add_sync(0xffffffffu, c_uq);
-                        unsigned long long sum = qv;
-#pragma unroll
-                        for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-                        if ((int)lane == leader) {
-                            unsigned long long* hp = a.hist + 4ull * lab0;
-                            atomicAdd(hp + 0, (unsigned long long)n1);
-                            atomicAdd(hp + 1, sum);
-                            if (n3) atomicAdd(hp + 2, (unsigned long long)n3);
-                            if (n4) atomicAdd(hp + 3, (unsigned long long)n4);
-                        }
-                    } else if (cnt) {
-                        bool done = false;
-                        if (qv < (1ull << 16)) {
-                            uint32_t hs = (label * 0x9E3779B1u) >> (32 - HIST_SLOTS_LOG2);
-                            for (int t = 0; t < 4 && !done; ++t) {
-                                const uint32_t old = atomicCAS(&hkey[hs], LABEL_U, label);
-                                if (old == LABEL_U || old == label) {
-                                    uint32_t* hv = hval + 4u * hs;
-                                    atomicAdd(hv + 0, 1u);
-                                    if (c_lm) atomicAdd(hv + 1, 1u);
-                                    if (c_uq) atomicAdd(hv + 2, 1u);
-                                    if (qv) atomicAdd(hv + 3, (uint32_t)qv);
-                                    done = true;
-                                }
-                                hs = (hs + 1u) & (HIST_SLOTS - 1u);
-                            }
-                        }
-                        if (!done) {
-                            unsigned long long* hp = a.hist + 4ull * label;
-                            atomicAdd(hp + 0, 1ull);
-                            atomicAdd(hp + 1, qv);
-                            if (c_lm) atomicAdd(hp + 2, 1ull);
-                            if (c_uq) atomicAdd(hp + 3, 1ull);
-                        }
-                    }
-                }
-            }
+            count_species_warp(a.hist + (size_t)(blockIdx.x % a.hist_copies) * a.hist_stride, has && label != LABEL_U, label, ql, lm, uq, lane);  // species counts (profile.rs:219-232, 264-277)
             // ---- the record for k_apply
             const bool labelled = has && label != LABEL_U;
             const bool eligible = labelled && cols_ok;
@@ -1891,18 +1824,6 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs
         }
         valid_prev += n_round - inv_total;
         __syncthreads();
-    }
-    if (hist_smem) {
-        for (uint32_t i = tid; i < HIST_SLOTS; i += INGEST_THREADS) {
-            const uint32_t label = hkey[i];
-            if (label == LABEL_U) continue;
-            unsigned long long* hp = a.hist + 4ull * label;
-            const uint32_t* hv = hval + 4u * i;
-            atomicAdd(hp + 0, (unsigned long long)hv[0]);
-            if (hv[3]) atomicAdd(hp + 1, (unsigned long long)hv[3]);
-            if (hv[1]) atomicAdd(hp + 2, (unsigned long long)hv[1]);
-            if (hv[2]) atomicAdd(hp + 3, (unsigned long long)hv[2]);
-        }
     }
 }
 
@@ -1947,7 +1868,7 @@ __device__ __forceinline__ void block_append(uint32_t dest, const ulonglong2& en
 }
 
 template <int MODE, int VAR = 0>
-__global__ void __launch_bounds__(256, 8) k_apply(const IngestArgs a, uint32_t n_entries) {  // 32 registers, 64 warps/SM: the random id-set and node accesses want every warp they can get (0.947 -> 0.906 ms)
+__global__ void __launch_bounds__(256, PTX_APPLY_MINB) k_apply(const IngestArgs a, uint32_t n_entries) {  // 32 registers, 64 warps/SM: the random id-set and node accesses want every warp they can get (0.947 -> 0.906 ms)
     if (n_entries == ENTRIES_FROM_DEVICE) {  // single-pass ingest: the host does not know the entry count yet
         if (a.cursors[3]) return;            // the estimate was too small: nothing of this chunk counts, it is redone
         n_entries = a.cursors[0];
@@ -2046,12 +1967,15 @@ __global__ void __launch_bounds__(256, 8) k_apply(const IngestArgs a, uint32_t n
 // single-pass ingest: the species counts of a chunk go to a chunk-local buffer and are added to the totals only
 // if the chunk was not abandoned (cursors[3])
 __global__ void __launch_bounds__(256) k_hist_merge(const unsigned long long* __restrict__ chunk_hist, unsigned long long* hist, uint32_t n,
-                                                    uint32_t* cursors) {
+                                                    uint32_t copies, uint32_t* cursors) {
     if (cursors[3]) return;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && chunk_hist[i]) {
-        atomicAdd(hist + i, chunk_hist[i]);
-        if ((i & 3u) == 0u) atomicAdd(cursors + 4, (uint32_t)min(chunk_hist[i], 0xFFFFFFFFull));  // labelled (non-U) rows of the chunk
+    if (i >= n) return;
+    unsigned long long v = 0;
+    for (uint32_t c = 0; c < copies; ++c) v += chunk_hist[(size_t)c * n + i];
+    if (v) {
+        atomicAdd(hist + i, v);
+        if ((i & 3u) == 0u) atomicAdd(cursors + 4, (uint32_t)min(v, 0xFFFFFFFFull));  // labelled (non-U) rows of the chunk
     }
 }
 // single-pass ingest: labels[] in GAF row order from the record table.  tile_off = exclusive scan of tile_info[].z.
@@ -2710,7 +2634,7 @@ size_t ingest_smem_bytes(uint32_t tile_bytes, uint32_t over_bytes, bool short_ke
     if (short_kernel) {
         const size_t stage_bytes = (size_t)tile_bytes + over_bytes;
         return stage_bytes + STAGE_PAD + 2 * ((stage_bytes / 32 + 2 + 3) / 4 * 4) * sizeof(uint32_t) + SHORT_STASH_CAP * SHORT_THREADS * sizeof(uint32_t) +
-               3 * SHORT_REC_CAP * sizeof(uint16_t) + hist_bytes;
+               3 * SHORT_REC_CAP * sizeof(uint16_t);
     }
     return (size_t)tile_bytes + OVER + 16 + STASH_CAP * INGEST_THREADS * sizeof(uint32_t) + 4 * REC_CAP * sizeof(uint16_t) + hist_bytes;
 }
@@ -2719,7 +2643,7 @@ size_t ingest_l_smem_bytes(uint32_t tile_bytes, uint32_t over_bytes, bool multi_
     const size_t stage_bytes = (size_t)tile_bytes + over_bytes;
     const size_t bm_alloc = (stage_bytes / 32 + 2 + 3) / 4 * 4;
     return stage_bytes + STAGE_PAD + 5 * bm_alloc * sizeof(uint32_t) + INGEST_THREADS * (2 * sizeof(uint32_t) + 2 * sizeof(uint16_t)) +
-           2 * REC_CAP * sizeof(uint16_t) + (multi_species ? HIST_SLOTS * 5 * sizeof(uint32_t) : 0);
+           2 * REC_CAP * sizeof(uint16_t);
 }
 
 void launch_ingest(const IngestArgs& a, cudaStream_t st) {
@@ -2775,8 +2699,8 @@ void launch_count_labelled(const unsigned long long* hist, uint32_t S, unsigned 
     k_count_labelled<<<1, 256, 0, st>>>(hist, S, dst);
     PTX_LAUNCHED();
 }
-void launch_hist_merge(const unsigned long long* chunk_hist, unsigned long long* hist, uint32_t n, uint32_t* cursors, cudaStream_t st) {
-    k_hist_merge<<<(n + 255u) / 256u, 256, 0, st>>>(chunk_hist, hist, n, cursors);
+void launch_hist_merge(const unsigned long long* chunk_hist, unsigned long long* hist, uint32_t n, uint32_t copies, uint32_t* cursors, cudaStream_t st) {
+    k_hist_merge<<<(n + 255u) / 256u, 256, 0, st>>>(chunk_hist, hist, n, copies, cursors);
     PTX_LAUNCHED();
 }
 void launch_tile_rows(const uint4* tile_info, uint32_t* rows, uint32_t n_tiles, cudaStream_t st) {

@@ -16,6 +16,11 @@
 // All arithmetic on reads/nodes/paths runs in libpantax_gpu.so; this file does file I/O, the f64 tail and TSVs.
 #include <algorithm>
 #include <charconv>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <dlfcn.h>
 
@@ -39,7 +44,7 @@ struct Options {
     std::string db, gaf, wd = ".", report, range_file, len_file, designated, reads_binning;
     bool species = false, strain = false, filtered = true, long_read = false, shift = false, force = false;
     double min_species_abundance = 1e-4, fr = -1, min_depth = 0;
-    int mode = 2, device = 0;
+    int mode = 2, device = 0, chunk_mb = 0;  // chunk_mb: size of the pinned GAF chunks (0: 64 MB)
 };
 
 [[noreturn]] void die(const std::string& m) {
@@ -274,7 +279,7 @@ void usage() {
     puts("pantax-gpu-profile --db DIR --gaf FILE|- [--wd DIR] [--species] [--strain] [-R reads_classification.tsv]\n"
          "                   [--reads-binning reads_classification.tsv]   (with --strain only: species column of the GAF rows)\n"
          "                   [-a MIN_SPECIES_ABUND=1e-4] [--fr F] [--long-read] [--shift] [--no-filter] [--smode 0|1|2]\n"
-         "                   [--ds TAXID,TAXID] [--range-file F] [--len-file F] [--min-depth D] [--device N]\n"
+         "                   [--ds TAXID,TAXID] [--range-file F] [--len-file F] [--min-depth D] [--device N] [--chunk-mb M]\n"
          "GPU implementation of PanTax's profiling stage (read classification, species abundance, node coverage and\n"
          "strain statistics).  Needs a CUDA device; there is no CPU fallback.");
 }
@@ -304,6 +309,7 @@ int main(int argc, char** argv) {
         else if (a == "--len-file") o.len_file = next();
         else if (a == "--min-depth") o.min_depth = std::stod(next());
         else if (a == "--device") o.device = std::stoi(next());
+        else if (a == "--chunk-mb") o.chunk_mb = std::stoi(next());
         else if (a == "--force") o.force = true;
         else if (a == "--dump-graph") {
             // reader check without a GPU: parse one graph file (.bin / .bin.lz4 / .bin.zst / .gfa by its extension) and print it
@@ -367,57 +373,131 @@ int main(int argc, char** argv) {
     // ("-": the aligner's stdout, e.g. `vg giraffe -o gaf ... | pantax-gpu-profile --gaf -`, alignment.rs:18-26)
     FILE* gf = o.gaf == "-" ? stdin : fopen(o.gaf.c_str(), "rb");
     if (!gf) die("cannot open GAF mapping file " + o.gaf);
-    const size_t CH = (size_t)256 << 20;
-    void* pin = nullptr;
-    if (ptx_host_alloc(CH, &pin) != PTX_OK) die("pinned allocation failed");
-    std::vector<std::string> gaf_keep;  // only needed for reads_classification.tsv
+    // Double-buffered streaming: a reader thread fills pinned chunks (a pipe returns short reads: it fills each chunk) while this
+    // thread hands the previous one to the library, whose H2D copy and kernels run asynchronously - read(), PCIe and the GPU overlap.
+    const size_t CH = (size_t)(o.chunk_mb > 0 ? o.chunk_mb : 64) << 20;
+    constexpr int NSLOT = 3;
+    struct Slot { void* pin = nullptr; size_t n = 0; bool last = false; };
+    Slot slots[NSLOT];
+    for (auto& sl : slots)
+        if (ptx_host_alloc(CH, &sl.pin) != PTX_OK) die("pinned allocation failed");
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<int> ready, freeq;
+    for (int i = 0; i < NSLOT; ++i) freeq.push_back(i);
+    const auto t_stream0 = std::chrono::steady_clock::now();
+    std::thread reader([&] {
+        for (;;) {
+            int si;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !freeq.empty(); });
+                si = freeq.front();
+                freeq.pop_front();
+            }
+            Slot& sl = slots[si];
+            sl.n = 0;
+            while (sl.n < CH) { size_t k = fread((char*)sl.pin + sl.n, 1, CH - sl.n, gf); if (k == 0) break; sl.n += k; }
+            sl.last = sl.n < CH;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                ready.push_back(si);
+            }
+            cv.notify_all();
+            if (sl.last) return;
+        }
+    });
+    // reads_classification.tsv (profile.rs:3337-3351) needs read id, mapq and read length of every row: they are cut out of each chunk
+    // while the next one is being read (about 35 bytes per row are kept, not the text)
     const bool want_report = !o.report.empty();
+    std::string rep_rows, rep_carry;  // "id\tmapq\trlen\n" per GAF row; the unterminated tail of the previous chunk
+    auto is_int = [](const char* b, size_t n) {
+        size_t k = (n && (b[0] == '+' || b[0] == '-')) ? 1 : 0;
+        if (k == n || n - k > 18) return false;
+        for (; k < n; ++k) if (!isdigit((unsigned char)b[k])) return false;
+        return true;
+    };
+    auto report_line = [&](const char* b, size_t l) {
+        if (l && b[l - 1] == '\r') --l;
+        if (!l || b[0] == '@') return;
+        const char* f[12]; size_t fl[12]; int nf = 0;
+        size_t st = 0;
+        for (size_t i = 0; i <= l && nf < 12; ++i)
+            if (i == l || b[i] == '\t') { f[nf] = b + st; fl[nf] = i - st; ++nf; st = i + 1; }
+        rep_rows.append(f[0], fl[0]);
+        rep_rows.push_back('\t');
+        if (nf > 11 && is_int(f[11], fl[11])) rep_rows.append(f[11], fl[11]);
+        rep_rows.push_back('\t');
+        if (nf > 1 && is_int(f[1], fl[1])) rep_rows.append(f[1], fl[1]);
+        rep_rows.push_back('\n');
+    };
+    size_t gaf_bytes = 0;
     for (;;) {
-        size_t n = 0;  // a pipe returns short reads: fill the chunk
-        while (n < CH) { size_t k = fread((char*)pin + n, 1, CH - n, gf); if (k == 0) break; n += k; }
-        const bool last = n < CH;
-        if (want_report) gaf_keep.emplace_back((const char*)pin, n);
-        ck(ctx, ptx_ingest_gaf(ctx, (const uint8_t*)pin, n, last ? 1 : 0), "ptx_ingest_gaf");
+        int si;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return !ready.empty(); });
+            si = ready.front();
+            ready.pop_front();
+        }
+        Slot& sl = slots[si];
+        gaf_bytes += sl.n;
+        ck(ctx, ptx_ingest_gaf(ctx, (const uint8_t*)sl.pin, sl.n, sl.last ? 1 : 0), "ptx_ingest_gaf");  // returns when the chunk is on the device
+        if (want_report) {
+            const char* b = (const char*)sl.pin;
+            size_t i = 0;
+            if (!rep_carry.empty()) {
+                const void* nl = memchr(b, '\n', sl.n);
+                const size_t e = nl ? (size_t)((const char*)nl - b) : sl.n;
+                rep_carry.append(b, e);
+                if (nl || sl.last) { report_line(rep_carry.data(), rep_carry.size()); rep_carry.clear(); }
+                i = nl ? e + 1 : sl.n;
+            }
+            while (i < sl.n) {
+                const void* nl = memchr(b + i, '\n', sl.n - i);
+                if (!nl && !sl.last) { rep_carry.assign(b + i, sl.n - i); break; }
+                const size_t e = nl ? (size_t)((const char*)nl - b) : sl.n;
+                report_line(b + i, e - i);
+                i = e + 1;
+            }
+        }
+        const bool last = sl.last;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            freeq.push_back(si);
+        }
+        cv.notify_all();
         if (last) break;
     }
+    reader.join();
     if (gf != stdin) fclose(gf);
+    const double t_stream = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_stream0).count();
     ck(ctx, ptx_finalize(ctx), "ptx_finalize");
+    for (auto& sl : slots) ptx_host_free(sl.pin);
     const int64_t R = ptx_num_records(ctx);
     const int S = (int)ranges.size();
     std::vector<int64_t> counts((size_t)S * 4);
     ck(ctx, ptx_species_counts(ctx, counts.data()), "ptx_species_counts");
     fprintf(stderr, "- Read classification: %lld GAF records, ids unique: %s\n", (long long)R, ptx_ids_unique(ctx) ? "yes" : "NO (duplicate read ids, profile.rs:460)");
+    fprintf(stderr, "- GAF stream: %.1f MB in %.3f s = %.1f MB/s (%s, %d pinned chunks of %zu MB)\n", gaf_bytes / 1e6, t_stream, gaf_bytes / 1e6 / std::max(t_stream, 1e-9),
+            o.gaf == "-" ? "stdin" : "file", NSLOT, CH >> 20);
 
     if (want_report) {  // profile.rs:3337-3351
         std::vector<uint32_t> labels((size_t)std::max<int64_t>(R, 1));
         ck(ctx, ptx_read_labels(ctx, labels.data()), "ptx_read_labels");
         FILE* rf = fopen(o.report.c_str(), "wb");
         if (!rf) die("cannot write " + o.report);
-        std::string all;
-        for (auto& s : gaf_keep) all += s;
-        std::vector<std::string>().swap(gaf_keep);
         size_t i = 0;
         int64_t rec = 0;
-        auto is_int = [](const std::string& f) {
-            size_t k = (!f.empty() && (f[0] == '+' || f[0] == '-')) ? 1 : 0;
-            if (k == f.size() || f.size() - k > 18) return false;
-            for (; k < f.size(); ++k) if (!isdigit((unsigned char)f[k])) return false;
-            return true;
-        };
-        while (i < all.size()) {
-            size_t e = all.find('\n', i);
-            if (e == std::string::npos) e = all.size();
-            size_t l = e - i;
-            if (l && all[i + l - 1] == '\r') --l;
-            if (l && all[i] != '@') {
-                std::string line = all.substr(i, l);
-                auto f = split(line, '\t');
-                const uint32_t lab = rec < R ? labels[(size_t)rec] : PTX_LABEL_UNCLASSIFIED;
-                const std::string mapq = f.size() > 11 && is_int(f[11]) ? f[11] : "";
-                const std::string rlen = f.size() > 1 && is_int(f[1]) ? f[1] : "";
-                fprintf(rf, "%s\t%s\t%s\t%s\n", f[0].c_str(), mapq.c_str(), lab == PTX_LABEL_UNCLASSIFIED ? "U" : ranges[lab].taxid.c_str(), rlen.c_str());
-                ++rec;
-            }
+        while (i < rep_rows.size()) {
+            const size_t e = rep_rows.find('\n', i);
+            const size_t t2 = rep_rows.rfind('\t', e);  // in front of the read length (ids hold no tab)
+            const uint32_t lab = rec < R ? labels[(size_t)rec] : PTX_LABEL_UNCLASSIFIED;
+            fwrite(rep_rows.data() + i, 1, t2 + 1 - i, rf);
+            fputs(lab == PTX_LABEL_UNCLASSIFIED ? "U" : ranges[lab].taxid.c_str(), rf);
+            fputc('\t', rf);
+            fwrite(rep_rows.data() + t2 + 1, 1, e - t2, rf);  // read length + '\n'
+            ++rec;
             i = e + 1;
         }
         fclose(rf);
@@ -472,7 +552,7 @@ int main(int argc, char** argv) {
         fclose(f);
     }
     fprintf(stderr, "- Species level profiling: %zu species\n", table.size());
-    if (!o.strain) { ptx_host_free(pin); ptx_destroy(ctx); return 0; }
+    if (!o.strain) { ptx_destroy(ctx); return 0; }
 
     // ---- strain level: graphs of the species that pass load_species_range (profile.rs:553-656)
     std::set<std::string> wanted;
@@ -504,7 +584,7 @@ int main(int argc, char** argv) {
         ck(ctx, ptx_upload_graph(ctx, s, g.nodes_len.data(), (int64_t)g.nodes_len.size(), off.data(), flat.data(), (int64_t)g.paths.size()), "ptx_upload_graph");
         graphs[s] = std::move(g);
     }
-    if (chosen.empty()) { fprintf(stderr, "The filtering before strain profiling has removed all species.\n"); ptx_host_free(pin); ptx_destroy(ctx); return 0; }
+    if (chosen.empty()) { fprintf(stderr, "The filtering before strain profiling has removed all species.\n"); ptx_destroy(ctx); return 0; }
     ck(ctx, ptx_commit_graphs(ctx), "ptx_commit_graphs");
     ck(ctx, ptx_finalize(ctx), "ptx_finalize (coverage)");  // coverage pass over the record tables kept on the device (no text is parsed again)
 
@@ -593,7 +673,7 @@ int main(int argc, char** argv) {
     fprintf(stderr, "- Strain level statistics: %zu species written to %s/strain_inputs/\n", chosen.size(), o.wd.c_str());
     char stats[2048];
     if (ptx_stats_json(ctx, stats, sizeof stats) == PTX_OK) fprintf(stderr, "- device: %s\n", stats);
-    ptx_host_free(pin);
+
     ptx_destroy(ctx);
     return 0;
 }

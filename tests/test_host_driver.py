@@ -147,6 +147,17 @@ def test_host_driver_strain_only_resume_and_stdin(tmp_path):
     assert r.returncode == 0, r.stderr
     full = {f: open(os.path.join(wd, "strain_inputs", f)).read() for f in sorted(os.listdir(os.path.join(wd, "strain_inputs")))}
     sa = open(os.path.join(wd, "species_abundance.txt")).read()
+    # the same run fed through a pipe in 1 MB pinned chunks (reader thread + 3 buffers; lines straddle the chunk ends): identical
+    # reads_classification.tsv and species table, and the stream throughput is reported
+    wd2 = os.path.join(str(tmp_path), "wd2")
+    os.makedirs(wd2)
+    rep2 = os.path.join(wd2, "reads_classification.tsv")
+    r = subprocess.run([BIN, "--db", db, "--gaf", "-", "--wd", wd2, "--species", "--strain", "-R", rep2, "-a", "0", "--chunk-mb", "1"], input=gaf, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    assert b"GAF stream:" in r.stderr and b"stdin" in r.stderr
+    assert open(rep2).read() == open(rep).read()
+    assert open(os.path.join(wd2, "species_abundance.txt")).read() == sa
+    assert {f: open(os.path.join(wd2, "strain_inputs", f)).read() for f in sorted(os.listdir(os.path.join(wd2, "strain_inputs")))} == full
     for f in full:
         os.remove(os.path.join(wd, "strain_inputs", f))
     r = subprocess.run([BIN, "--db", db, "--gaf", "-", "--wd", wd, "--strain", "-a", "0"], input=gaf, capture_output=True)
