@@ -155,6 +155,7 @@ struct ptx_ctx {
     bool ds_cas_first = false;  // PTX_DS_CAS_FIRST=1: id-set insert with the CAS before the load (measured: k_apply 0.933 vs 0.936 ms - no gain)
     int l2_hints = 1;        // PTX_L2_HINTS: bit 0 = graph arrays evict-last (k_apply 0.969 -> 0.938 ms), bit 1 = GAF text evict-first (no gain), bit 2 = id-set loads evict-first (slower: 1.00 ms); IngestArgs::pol_*
     bool old_short = false;  // PTX_OLD_INGEST=1: round 1's byte-at-a-time short-read kernel (A/B measurements)
+    uint32_t long_tile_max = LONG_TILE_MAX;  // PTX_LONG_TILE: largest tile of k_ingest_l in bytes (multiple of 4096; measurements)
     bool long_new = true;    // PTX_LONG_NEW=0: round 1's k_ingest<long> (warp-cooperative walk decode) instead of k_ingest_l (A/B measurements: 1.66 vs 1.40 ms on configs[2])
     int force_long = -1; // PTX_LONG_MODE env override: 0/1 = never/always use the long-line kernel (tests)
     int64_t test_box_cap = 0;  // PTX_TEST_BOX_CAP env: first outbox capacity (tests force the overflow/restart path of the exchange)
@@ -523,6 +524,7 @@ void chunk_pick_tile(ptx_ctx* ctx, Chunk& ch, double mean_line, bool exact) {
     const uint32_t gran = fine ? 128u : MICRO;
     uint32_t tile = (uint32_t)(0.97 * threads * mean_line) / gran * gran;
     tile = std::min<uint32_t>(MAX_TILE, std::max<uint32_t>(MICRO, tile));
+    if (ch.long_mode && ctx->long_new) tile = std::min<uint32_t>(tile, ctx->long_tile_max);
     if (ctx->force_rows > 0) tile = (uint32_t)std::min(8, ctx->force_rows) * MICRO;
     if (ctx->force_tile > 0 && fine) tile = std::min<uint32_t>(MAX_TILE, std::max<uint32_t>(MICRO, (uint32_t)ctx->force_tile / 128u * 128u));
     // the window behind the tile holds the tail of its last line: four mean lines, at least 512 bytes (longer lines are re-read from global memory)
@@ -1075,6 +1077,7 @@ int ptx_create(int device, ptx_ctx** out) {
     if (const char* e = getenv("PTX_TILE_BYTES")) ctx->force_tile = atoi(e);
     if (const char* e = getenv("PTX_OLD_INGEST")) ctx->old_short = atoi(e) != 0;
     if (const char* e = getenv("PTX_LONG_NEW")) ctx->long_new = atoi(e) != 0;
+    if (const char* e = getenv("PTX_LONG_TILE")) ctx->long_tile_max = std::min<uint32_t>(MAX_TILE, std::max<uint32_t>(MICRO, (uint32_t)atoi(e) / MICRO * MICRO));
     if (const char* e = getenv("PTX_NO_SORT")) ctx->no_sort = atoi(e) != 0;
     if (const char* e = getenv("PTX_KEEP_TEXT")) ctx->keep_text = atoi(e) != 0;
     if (const char* e = getenv("PTX_SCATTER")) ctx->scatter_var = atoi(e);

@@ -33,6 +33,11 @@ constexpr int SHORT_THREADS = PTX_SHORT_THREADS;       // k_ingest_s: small CTAs
 #define PTX_SHORT_RECCAP 512
 #endif
 constexpr uint32_t SHORT_REC_CAP = PTX_SHORT_RECCAP;  // k_ingest_s: line starts kept in smem per round
+#ifndef PTX_LONG_MINB
+#define PTX_LONG_MINB 4
+#endif
+constexpr uint32_t LONG_REC_CAP = 512;   // k_ingest_l: line starts kept in smem per round (4 CTAs of 55 KB per SM)
+constexpr uint32_t LONG_TILE_MAX = 7 * 4096;  // k_ingest_l: largest tile (4 resident CTAs per SM)
 constexpr uint32_t REC_CAP = 1024;  // record starts kept in smem per round
 constexpr double LONG_LINE_BYTES = 320.0;  // mean line length from which a chunk is parsed by k_ingest<LONG>
 constexpr uint32_t HIST_SLOTS_LOG2 = 7;  // per-tile species-count accumulators in shared memory (multi-species runs)

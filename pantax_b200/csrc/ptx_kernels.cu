@@ -1417,7 +1417,7 @@ __global__ void __launch_bounds__(SHORT_THREADS, PTX_SHORT_MINB) k_ingest_s(cons
 // =====================================================================================
 constexpr uint32_t LONG_WPT = (MAX_TILE + OVER) / 32u / INGEST_THREADS + 1u;  // bitmap words a thread of k_ingest_l takes
 
-__global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs a) {
+__global__ void __launch_bounds__(INGEST_THREADS, PTX_LONG_MINB) k_ingest_l(const IngestArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile_bytes = a.tile_bytes;                 // multiple of 4096
@@ -1429,13 +1429,13 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs
     uint32_t* tabw = nlw + bm_alloc;
     uint32_t* ndw = tabw + bm_alloc;    // non-digit bytes
     uint32_t* ew = ndw + bm_alloc;      // the ends of the walk ids of the group's lines
-    uint32_t* epre = ew + bm_alloc;     // ids that end in front of each bitmap word (exclusive prefix over the tile)
-    uint32_t* lmin = epre + bm_alloc;                                                        // [INGEST_THREADS] smallest / largest walk id of each line of the group
+    uint16_t* epre = reinterpret_cast<uint16_t*>(ew + bm_alloc);  // ids that end in front of each bitmap word (exclusive prefix over the tile: < 2^16, an id takes two bytes)
+    uint32_t* lmin = reinterpret_cast<uint32_t*>(epre + bm_alloc);                                                        // [INGEST_THREADS] smallest / largest walk id of each line of the group
     uint32_t* lmax = lmin + INGEST_THREADS;                                                  // [INGEST_THREADS]
     uint16_t* lp6 = reinterpret_cast<uint16_t*>(lmax + INGEST_THREADS);                      // [INGEST_THREADS] first byte of the line's walk column (line start if it has none)
     uint16_t* lend = lp6 + INGEST_THREADS;                                                   // [INGEST_THREADS] one past its closing tab (<= lp6: no column)
-    uint16_t* rec_start = lend + INGEST_THREADS;                                             // [REC_CAP]
-    uint16_t* inv_pre = rec_start + REC_CAP;                                                 // [REC_CAP]
+    uint16_t* rec_start = lend + INGEST_THREADS;                                             // [LONG_REC_CAP]
+    uint16_t* inv_pre = rec_start + LONG_REC_CAP;                                                 // [LONG_REC_CAP]
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t warp_tot[INGEST_THREADS / 32];
     __shared__ uint32_t inv_flag, inv_tot_s, slot_base_s, node_base_s, slow_bits[INGEST_THREADS / 32];
@@ -1461,7 +1461,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs
         }
     }
     if (tid < STAGE_PAD / 4u) reinterpret_cast<uint32_t*>(stage + stage_bytes)[tid] = 0x0a0a0a0au;
-    if (tid < 2u) { nlw[bm_words + tid] = 0xFFFFFFFFu; tabw[bm_words + tid] = 0xFFFFFFFFu; ndw[bm_words + tid] = 0xFFFFFFFFu; ew[bm_words + tid] = 0u; epre[bm_words + tid] = 0u; }
+    if (tid < 2u) { nlw[bm_words + tid] = 0xFFFFFFFFu; tabw[bm_words + tid] = 0xFFFFFFFFu; ndw[bm_words + tid] = 0xFFFFFFFFu; ew[bm_words + tid] = 0u; epre[bm_words + tid] = 0; }
     const uint32_t* sstart = a.ranges.sstart;
     __shared__ uint32_t pv[CLASSIFY_PIVOTS];  // every stride-th range start: the first level of the species search
     const int pv_stride = a.ranges.S > CLASSIFY_PIVOTS ? (a.ranges.S + CLASSIFY_PIVOTS - 1) / CLASSIFY_PIVOTS : 1;
@@ -1491,7 +1491,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs
 
     uint32_t n_rec = 0;
     uint32_t valid_prev = 0;
-    for (uint32_t round = 0; round == 0 || round < n_rec; round += REC_CAP) {
+    for (uint32_t round = 0; round == 0 || round < n_rec; round += LONG_REC_CAP) {
         // ---- B: number the line starts (as k_ingest_s)
         uint32_t idx_base = 0;
         for (uint32_t w0 = 0; w0 < nw; w0 += 4u * INGEST_THREADS) {
@@ -1527,7 +1527,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs
             }
             idx_base += tot;
             if (w0 == 0u && first_slot) {
-                if (idx >= round && idx < round + REC_CAP) rec_start[idx - round] = 0;
+                if (idx >= round && idx < round + LONG_REC_CAP) rec_start[idx - round] = 0;
                 ++idx;
             }
             const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w};
@@ -1539,7 +1539,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs
                     const uint32_t bit = __ffs(m) - 1;
                     m &= m - 1u;
                     const uint32_t q = b0 + bit;
-                    if (idx >= round && idx < round + REC_CAP) {
+                    if (idx >= round && idx < round + LONG_REC_CAP) {
                         rec_start[idx - round] = (uint16_t)q;
                         if (!valid_first(stage, q)) inv_flag = 1;
                     }
@@ -1548,9 +1548,9 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs
             }
         }
         n_rec = idx_base;
-        const uint32_t n_round = min(REC_CAP, n_rec - round);
+        const uint32_t n_round = min(LONG_REC_CAP, n_rec - round);
         if (tid == 0 && first_slot && round == 0 && !valid_first(stage, 0)) inv_flag = 1;
-        if (single_pass && n_rec > REC_CAP) {  // rows are numbered per tile: the host redoes the chunk with the count pass (uniform)
+        if (single_pass && n_rec > LONG_REC_CAP) {  // rows are numbered per tile: the host redoes the chunk with the count pass (uniform)
             if (tid == 0) atomicOr(a.cursors + 3, 1u);
             return;
         }
@@ -1660,7 +1660,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs
                     uint32_t c = before;
 #pragma unroll
                     for (uint32_t j = 0; j < LONG_WPT; ++j)
-                        if (j < wn) { ew[wi + j] = E[j]; epre[wi + j] = c; c += __popc(E[j]); }
+                        if (j < wn) { ew[wi + j] = E[j]; epre[wi + j] = (uint16_t)c; c += __popc(E[j]); }
                 }
                 if (tid == 0) {  // the tile's CSR slots and (first group) the record-table entries of the round: one atomicAdd on the packed cursor
                     const uint32_t n_ent = g0 == 0u ? n_round : 0u;
@@ -1679,7 +1679,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, 3) k_ingest_l(const IngestArgs
                     }
                     slot_base_s = sb;
                     node_base_s = nb;
-                    epre[bm_words] = tot;
+                    epre[bm_words] = (uint16_t)tot;
                 }
                 __syncthreads();
                 if (node_base_s == 0xFFFFFFFFu) return;  // uniform
@@ -2642,8 +2642,8 @@ size_t ingest_smem_bytes(uint32_t tile_bytes, uint32_t over_bytes, bool short_ke
 size_t ingest_l_smem_bytes(uint32_t tile_bytes, uint32_t over_bytes, bool multi_species) {
     const size_t stage_bytes = (size_t)tile_bytes + over_bytes;
     const size_t bm_alloc = (stage_bytes / 32 + 2 + 3) / 4 * 4;
-    return stage_bytes + STAGE_PAD + 5 * bm_alloc * sizeof(uint32_t) + INGEST_THREADS * (2 * sizeof(uint32_t) + 2 * sizeof(uint16_t)) +
-           2 * REC_CAP * sizeof(uint16_t);
+    return stage_bytes + STAGE_PAD + 4 * bm_alloc * sizeof(uint32_t) + bm_alloc * sizeof(uint16_t) + INGEST_THREADS * (2 * sizeof(uint32_t) + 2 * sizeof(uint16_t)) +
+           2 * LONG_REC_CAP * sizeof(uint16_t);
 }
 
 void launch_ingest(const IngestArgs& a, cudaStream_t st) {
@@ -2656,7 +2656,7 @@ void launch_ingest(const IngestArgs& a, cudaStream_t st) {
         cudaFuncSetAttribute(k_ingest<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ingest_smem_bytes(MAX_TILE, OVER, false, true));
         cudaFuncSetAttribute(k_ingest_s<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ingest_smem_bytes(MAX_TILE, OVER, true, true) + 8192);
         cudaFuncSetAttribute(k_ingest_s<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ingest_smem_bytes(MAX_TILE, OVER, true, true) + 8192);
-        cudaFuncSetAttribute(k_ingest_l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ingest_l_smem_bytes(MAX_TILE, OVER, true));
+        cudaFuncSetAttribute(k_ingest_l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ingest_l_smem_bytes(MAX_TILE, OVER, true) + 8192);
         // all of the SM's shared memory for these kernels: the driver's own carve-out choice flips between launches of the
         // same configuration (measured: k_ingest_s 1.06 or 1.34 ms), and their occupancy is set by shared memory
         static const int carve = getenv("PTX_CARVEOUT") ? atoi(getenv("PTX_CARVEOUT")) : 100;
@@ -2671,7 +2671,10 @@ void launch_ingest(const IngestArgs& a, cudaStream_t st) {
     }
     const bool multi = a.ranges.S > 1;
     if (a.long_mode && !a.long_new) k_ingest<true><<<a.n_tiles, INGEST_THREADS, ingest_smem_bytes(a.tile_bytes, OVER, false, multi), st>>>(a);
-    else if (a.long_mode) k_ingest_l<<<a.n_tiles, INGEST_THREADS, ingest_l_smem_bytes(a.tile_bytes, a.over_bytes, multi), st>>>(a);
+    else if (a.long_mode) {
+        static const int padl = getenv("PTX_SMEM_PAD_L") ? atoi(getenv("PTX_SMEM_PAD_L")) : 0;  // measurement knob: fewer resident CTAs
+        k_ingest_l<<<a.n_tiles, INGEST_THREADS, ingest_l_smem_bytes(a.tile_bytes, a.over_bytes, multi) + (size_t)std::min(padl, 8192), st>>>(a);
+    }
     else if (a.old_short) k_ingest<false><<<a.n_tiles, INGEST_THREADS, ingest_smem_bytes(a.tile_bytes, OVER, false, multi), st>>>(a);
     else {
         static const int pad = getenv("PTX_SMEM_PAD") ? atoi(getenv("PTX_SMEM_PAD")) : 0, cls = getenv("PTX_CLS_MUL") ? atoi(getenv("PTX_CLS_MUL")) : 0;  // measurement knobs
