@@ -69,6 +69,20 @@ int ptx_set_ranges(ptx_ctx* ctx, int n_species, const char* const* taxid, const 
 int ptx_upload_graph(ptx_ctx* ctx, int species, const int64_t* nodes_len, int64_t n, const uint64_t* path_off,
                      const uint64_t* path_nodes, int64_t n_paths);
 
+/* The same graph straight from the species' GFA text (species_gfa/<taxid>.gfa), parsed ON THE DEVICE: replaces
+ * profile::read_gfa (profile.rs:466-545, previous = 0) - S lines in id order give nodes_len (sequence length), the digit runs of
+ * the P (`\d+` of field 3, haplotype = field 2 up to '#') and W (`\d+` of the last field, haplotype = field 2) lines give the
+ * paths; lines of one haplotype are concatenated in file order, haplotypes in name order.  `gfa` is host memory (n bytes).
+ * Errors: PTX_E_NODE_ORDER (profile.rs:489), PTX_E_ZERO_LEN (:494), PTX_E_NVERT_MISMATCH, PTX_E_INVALID. */
+int ptx_upload_graph_gfa(ptx_ctx* ctx, int species, const uint8_t* gfa, size_t n);
+
+/* The Graph (types.rs:51-55) the library holds for a species after either upload - what profile::read_gfa returns: nodes_len[n],
+ * path_off[n_paths + 1], path_nodes[ptx_species_path_steps] (local ids); null pointers are skipped.  ptx_species_path_name: the
+ * haplotype id of path h (BTreeMap key; only known for ptx_upload_graph_gfa), returns its length. */
+int ptx_species_graph(ptx_ctx* ctx, int species, int64_t* nodes_len, uint64_t* path_off, uint64_t* path_nodes);
+int64_t ptx_species_path_steps(const ptx_ctx* ctx, int species);
+int ptx_species_path_name(ptx_ctx* ctx, int species, int64_t h, char* buf, size_t cap);
+
 /* Builds the device graph: node arrays, path CSR with distinct-node marks, and the
  * unique-trio table.  Replaces profile::trio_nodes_info (profile.rs:658-740) for all
  * uploaded species at once. */

@@ -32,6 +32,10 @@ SIGNATURES = {
     "ptx_version": (C.c_char_p, []),
     "ptx_set_ranges": (i32, [vp, i32, P(C.c_char_p), P(i64), P(i64)]),
     "ptx_upload_graph": (i32, [vp, i32, P(i64), i64, P(u64), P(u64), i64]),
+    "ptx_upload_graph_gfa": (i32, [vp, i32, vp, C.c_size_t]),
+    "ptx_species_graph": (i32, [vp, i32, P(i64), P(u64), P(u64)]),
+    "ptx_species_path_steps": (i64, [vp, i32]),
+    "ptx_species_path_name": (i32, [vp, i32, i64, C.c_char_p, C.c_size_t]),
     "ptx_commit_graphs": (i32, [vp]),
     "ptx_reserve": (i32, [vp, i64]),
     "ptx_host_alloc": (i32, [C.c_size_t, P(vp)]),

@@ -170,6 +170,25 @@ class PantaxGpu:
         self._ck(self._L.ptx_upload_graph(self._h, species, _p(nl, C.c_int64), len(nl), _p(off, C.c_uint64),
                                           _p(flat, C.c_uint64), len(paths)))
 
+    def upload_graph_gfa(self, species: int, gfa: bytes):
+        """profile.rs:466-545 read_gfa(previous = 0), parsed on the device: the species' GFA text instead of arrays."""
+        buf = (C.c_uint8 * len(gfa)).from_buffer_copy(gfa)
+        self._ck(self._L.ptx_upload_graph_gfa(self._h, species, C.cast(buf, C.c_void_p), len(gfa)))
+
+    def species_graph(self, species: int):
+        """(nodes_len int64[n], [path uint64[]...], [haplotype ids]) as the library holds them (what read_gfa returns)."""
+        n, H, P = self.n_nodes(species), self.n_paths(species), int(self._L.ptx_species_path_steps(self._h, species))
+        nl, off, flat = np.zeros(max(n, 1), np.int64), np.zeros(H + 1, np.uint64), np.zeros(max(P, 1), np.uint64)
+        self._ck(self._L.ptx_species_graph(self._h, species, _p(nl, C.c_int64), _p(off, C.c_uint64), _p(flat, C.c_uint64)))
+        names = []
+        for h in range(H):
+            buf = C.create_string_buffer(4096)
+            k = self._L.ptx_species_path_name(self._h, species, h, buf, 4096)
+            if k < 0:
+                self._ck(k)
+            names.append(buf.value.decode())
+        return nl[:n], [flat[int(off[h]):int(off[h + 1])] for h in range(H)], names
+
     def commit_graphs(self):
         self._ck(self._L.ptx_commit_graphs(self._h))
 

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <map>
 #include <vector>
 
 #include "../../include/pantax_gpu.h"
@@ -70,6 +71,7 @@ struct SpeciesHost {
     std::vector<uint32_t> len;
     std::vector<uint64_t> path_off;
     std::vector<uint32_t> path_nodes;  // local ids
+    std::vector<std::string> path_names;  // ptx_upload_graph_gfa only: haplotype ids in path order
 };
 
 struct Chunk {
@@ -1208,6 +1210,203 @@ int ptx_upload_graph(ptx_ctx* ctx, int s, const int64_t* nodes_len, int64_t n, c
     sp.n_paths = H;
     sp.uploaded = true;
     return PTX_OK;
+}
+
+// the per-species GFA (profile.rs:466-545 read_gfa, previous = 0) parsed on the device.  The text is uploaded once;
+// kernels index its lines, read the S lines into node lengths and decode the path fields of the P / W lines node-parallel; only the
+// compact arrays (4 bytes per node and per path step) and the list of path lines (their haplotype names) come back to the host,
+// which lays the lines of one haplotype out behind each other (BTreeMap order of the names) and hands everything to the same
+// staging ptx_upload_graph fills.
+int ptx_upload_graph_gfa(ptx_ctx* ctx, int s, const uint8_t* gfa, size_t n) {
+    int rc = check_species(ctx, s, false);
+    if (rc) return rc;
+    if (ctx->graphs_committed) return fail(ctx, PTX_E_STATE, "graphs already committed");
+    if (!gfa || n == 0) return fail(ctx, PTX_E_INVALID, "ptx_upload_graph_gfa: bad arguments");
+    cudaSetDevice(ctx->device);
+    SpeciesHost& sp = ctx->sp[s];
+    const int64_t n_nodes = sp.end - sp.start + 1;  // profile.rs:2938: nvert = end - start + 1 indexes nodes_len
+    cudaStream_t st = ctx->st;
+    const bool add_nl = gfa[n - 1] != '\n';
+    const uint64_t nn = n + (add_nl ? 1 : 0);
+    const uint32_t n_micro = (uint32_t)((nn + MICRO - 1) / MICRO);
+    uint8_t* d_text = nullptr;
+    uint32_t *d_cnt = nullptr, *d_len = nullptr, *d_is_s = nullptr, *d_adj = nullptr, *d_flags = nullptr, *d_pcnt = nullptr, *d_out = nullptr;
+    uint64_t *d_base = nullptr, *d_scratch = nullptr, *d_line = nullptr, *d_ord = nullptr, *d_pieces = nullptr, *d_poff = nullptr;
+    unsigned long long* d_np = nullptr;
+    uint8_t* d_plist = nullptr;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(st);
+        cudaFree(d_text); cudaFree(d_cnt); cudaFree(d_len); cudaFree(d_is_s); cudaFree(d_adj); cudaFree(d_flags); cudaFree(d_pcnt); cudaFree(d_out);
+        cudaFree(d_base); cudaFree(d_scratch); cudaFree(d_line); cudaFree(d_ord); cudaFree(d_pieces); cudaFree(d_poff); cudaFree(d_np); cudaFree(d_plist);
+    };
+#define GFA(call) do { if ((rc = (call)) != PTX_OK) { cleanup(); return rc; } } while (0)
+#define GFA_SYNC(what) do { if (cudaStreamSynchronize(st) != cudaSuccess) { cleanup(); return fail(ctx, PTX_E_CUDA, "ptx_upload_graph_gfa: %s: %s", what, cudaGetErrorString(cudaGetLastError())); } } while (0)
+    GFA(dalloc(ctx, &d_text, (size_t)n_micro * MICRO + 64, false));
+    if (cudaMemcpyAsync(d_text, gfa, n, cudaMemcpyHostToDevice, st) != cudaSuccess) { cleanup(); return fail(ctx, PTX_E_CUDA, "H2D copy failed"); }
+    cudaMemsetAsync(d_text + n, '\n', (size_t)n_micro * MICRO + 64 - n, st);
+    GFA(dalloc(ctx, &d_cnt, n_micro, false));
+    GFA(dalloc(ctx, &d_base, (size_t)n_micro + 1, false));
+    GFA(dalloc(ctx, &d_scratch, (size_t)n_micro / 2048 + 4, false));
+    launch_flt_count_nl(d_text, nn, n_micro, d_cnt, st);
+    launch_scan_u32(d_cnt, d_base, n_micro, d_scratch, st);
+    uint64_t n_lines = 0;
+    cudaMemcpyAsync(&n_lines, d_base + n_micro, sizeof n_lines, cudaMemcpyDeviceToHost, st);
+    GFA_SYNC("newline index");
+    GFA(dalloc(ctx, &d_line, (size_t)n_lines + 2, false));
+    launch_flt_line_starts(d_text, nn, n_micro, d_base, d_line, st);
+    // ---- lines: node lengths, S-line order, list of path lines
+    GFA(dalloc(ctx, &d_len, (size_t)n_nodes));
+    GFA(dalloc(ctx, &d_is_s, (size_t)n_lines + 1, false));
+    GFA(dalloc(ctx, &d_adj, (size_t)n_lines + 1, false));
+    GFA(dalloc(ctx, &d_ord, (size_t)n_lines + 2, false));
+    GFA(dalloc(ctx, &d_flags, 4));
+    GFA(dalloc(ctx, &d_np, 1));
+    uint64_t pcap = 4096;
+    std::vector<GfaPathLineHost> plines;
+    for (;;) {  // the path-line list is sized by guess and the pass repeated once if a GFA has more P / W lines than that
+        GFA(dalloc(ctx, &d_plist, (size_t)pcap * gfa_path_line_bytes(), false));
+        cudaMemsetAsync(d_np, 0, sizeof(unsigned long long), st);
+        cudaMemsetAsync(d_flags, 0, 4 * sizeof(uint32_t), st);
+        cudaMemsetAsync(d_len, 0, (size_t)n_nodes * sizeof(uint32_t), st);
+        launch_gfa_lines(d_text, d_line, n_lines, n_nodes, d_len, d_is_s, d_adj, d_plist, d_np, pcap, d_flags, st);
+        unsigned long long np = 0;
+        cudaMemcpyAsync(&np, d_np, sizeof np, cudaMemcpyDeviceToHost, st);
+        GFA_SYNC("line pass");
+        if (np <= pcap) {
+            plines.resize((size_t)np);
+            if (np) cudaMemcpy(plines.data(), d_plist, (size_t)np * sizeof(GfaPathLineHost), cudaMemcpyDeviceToHost);
+            break;
+        }
+        dfree(d_plist);
+        pcap = np;
+    }
+    dfree(d_scratch);
+    GFA(dalloc(ctx, &d_scratch, (size_t)n_lines / 2048 + 4, false));
+    launch_scan_u32(d_is_s, d_ord, n_lines, d_scratch, st);
+    launch_gfa_check_order(d_is_s, d_adj, d_ord, n_lines, d_flags, st);
+    uint64_t n_s = 0;
+    uint32_t h_flags[4] = {0, 0, 0, 0};
+    cudaMemcpyAsync(&n_s, d_ord + n_lines, sizeof n_s, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st);
+    GFA_SYNC("order check");
+    auto flag_error = [&](uint32_t f) -> int {
+        cleanup();
+        if (f & 4u) return fail(ctx, PTX_E_ZERO_LEN, "species %s: node length 0 appears in the GFA (profile.rs:494)", sp.taxid.c_str());
+        if (f & 2u) return fail(ctx, PTX_E_NODE_ORDER, "species %s: node ID out of order or mismatch (profile.rs:489)", sp.taxid.c_str());
+        if (f & 1u) return fail(ctx, PTX_E_INVALID, "species %s: an S line's id is not a number or lies outside the species' %lld nodes", sp.taxid.c_str(), (long long)n_nodes);
+        if (f & 8u) return fail(ctx, PTX_E_INVALID, "species %s: a P / W line has no name field", sp.taxid.c_str());
+        return fail(ctx, PTX_E_INVALID, "species %s: a path names a node outside the graph", sp.taxid.c_str());
+    };
+    if (h_flags[0]) return flag_error(h_flags[0]);
+    if ((int64_t)n_s != n_nodes) {
+        cleanup();
+        return fail(ctx, PTX_E_NVERT_MISMATCH, "species %s: range %lld..%lld has %lld ids but the GFA has %lld S lines", sp.taxid.c_str(), (long long)sp.start,
+                    (long long)sp.end, (long long)n_nodes, (long long)n_s);
+    }
+    // ---- path lines in file order; names from the text (tiny copies); pieces of 4 KB over their path fields
+    std::sort(plines.begin(), plines.end(), [](const GfaPathLineHost& a, const GfaPathLineHost& b) { return a.line < b.line; });
+    std::vector<std::string> names(plines.size());
+    for (size_t k = 0; k < plines.size(); ++k) {
+        names[k].resize(plines[k].name_len);
+        if (plines[k].name_len) cudaMemcpy(&names[k][0], d_text + plines[k].name_beg, plines[k].name_len, cudaMemcpyDeviceToHost);
+    }
+    std::vector<uint64_t> pbeg, pfend, pfbeg;
+    std::vector<uint32_t> first_piece(plines.size() + 1, 0);
+    for (size_t k = 0; k < plines.size(); ++k) {
+        first_piece[k] = (uint32_t)pbeg.size();
+        for (uint64_t p = plines[k].fld_beg; p < plines[k].fld_end; p += GFA_PIECE_BYTES) { pbeg.push_back(p); pfend.push_back(plines[k].fld_end); pfbeg.push_back(plines[k].fld_beg); }
+    }
+    first_piece[plines.size()] = (uint32_t)pbeg.size();
+    const uint32_t n_pieces = (uint32_t)pbeg.size();
+    std::vector<uint64_t> poff((size_t)n_pieces + 1, 0);
+    if (n_pieces) {
+        GFA(dalloc(ctx, &d_pieces, (size_t)n_pieces * 4, false));
+        GFA(dalloc(ctx, &d_pcnt, (size_t)n_pieces, false));
+        GFA(dalloc(ctx, &d_poff, (size_t)n_pieces + 2, false));
+        cudaMemcpyAsync(d_pieces, pbeg.data(), (size_t)n_pieces * 8, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_pieces + n_pieces, pfend.data(), (size_t)n_pieces * 8, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_pieces + 2 * (size_t)n_pieces, pfbeg.data(), (size_t)n_pieces * 8, cudaMemcpyHostToDevice, st);
+        launch_gfa_path_count(d_text, d_pieces, d_pieces + n_pieces, d_pcnt, n_pieces, st);
+        dfree(d_scratch);
+        GFA(dalloc(ctx, &d_scratch, (size_t)n_pieces / 2048 + 4, false));
+        launch_scan_u32(d_pcnt, d_poff, n_pieces, d_scratch, st);
+        cudaMemcpyAsync(poff.data(), d_poff, ((size_t)n_pieces + 1) * 8, cudaMemcpyDeviceToHost, st);
+        GFA_SYNC("path count");
+    }
+    // haplotypes in BTreeMap (byte) order of their names; the lines of one haplotype behind each other in file order
+    std::map<std::string, std::vector<size_t>> haps;
+    for (size_t k = 0; k < plines.size(); ++k) haps[names[k]].push_back(k);
+    const uint64_t total_steps = poff[n_pieces];
+    std::vector<uint64_t> path_off;
+    std::vector<uint64_t> line_dst(plines.size(), 0);
+    uint64_t run = 0;
+    for (auto& kv : haps) {
+        path_off.push_back(run);
+        for (size_t k : kv.second) {
+            line_dst[k] = run;
+            run += poff[first_piece[k + 1]] - poff[first_piece[k]];
+        }
+    }
+    path_off.push_back(run);
+    std::vector<uint32_t> h_nodes((size_t)total_steps);
+    if (n_pieces && total_steps) {
+        std::vector<uint64_t> pdst((size_t)n_pieces);
+        for (size_t k = 0; k < plines.size(); ++k)
+            for (uint32_t c = first_piece[k]; c < first_piece[k + 1]; ++c) pdst[c] = line_dst[k] + (poff[c] - poff[first_piece[k]]);
+        GFA(dalloc(ctx, &d_out, (size_t)total_steps, false));
+        cudaMemcpyAsync(d_pieces + 3 * (size_t)n_pieces, pdst.data(), (size_t)n_pieces * 8, cudaMemcpyHostToDevice, st);
+        launch_gfa_path_decode(d_text, d_pieces, d_pieces + n_pieces, d_pieces + 2 * (size_t)n_pieces, d_pieces + 3 * (size_t)n_pieces, n_nodes, d_out, n_pieces,
+                               d_flags, st);
+        cudaMemcpyAsync(h_nodes.data(), d_out, (size_t)total_steps * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st);
+        GFA_SYNC("path decode");
+        if (h_flags[0]) return flag_error(h_flags[0]);
+    }
+    sp.len.resize((size_t)n_nodes);
+    cudaMemcpy(sp.len.data(), d_len, (size_t)n_nodes * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cleanup();
+#undef GFA
+#undef GFA_SYNC
+    sp.path_off = path_off;
+    sp.path_nodes.swap(h_nodes);
+    sp.path_names.clear();
+    for (auto& kv : haps) sp.path_names.push_back(kv.first);
+    sp.n_nodes = n_nodes;
+    sp.n_paths = (int64_t)haps.size();
+    sp.uploaded = true;
+    return PTX_OK;
+}
+
+// The graph of a species as the library holds it (after ptx_upload_graph / ptx_upload_graph_gfa): what profile::read_gfa returned.
+// Any of the output pointers may be null.  path_off has n_paths + 1 entries, path_nodes path_off[n_paths].
+int ptx_species_graph(ptx_ctx* ctx, int s, int64_t* nodes_len, uint64_t* path_off, uint64_t* path_nodes) {
+    int rc = check_species(ctx, s, false);
+    if (rc) return rc;
+    const SpeciesHost& sp = ctx->sp[s];
+    if (!sp.uploaded && !sp.has_graph) return fail(ctx, PTX_E_NO_GRAPH, "species %s has no graph", sp.taxid.c_str());
+    if (nodes_len) for (size_t i = 0; i < sp.len.size(); ++i) nodes_len[i] = (int64_t)sp.len[i];
+    if (path_off) for (size_t i = 0; i < sp.path_off.size(); ++i) path_off[i] = sp.path_off[i];
+    if (path_nodes) for (size_t i = 0; i < sp.path_nodes.size(); ++i) path_nodes[i] = (uint64_t)sp.path_nodes[i];
+    return PTX_OK;
+}
+int64_t ptx_species_path_steps(const ptx_ctx* ctx, int s) {
+    if (!ctx || s < 0 || s >= (int)ctx->sp.size()) return PTX_E_RANGE;
+    return (int64_t)ctx->sp[s].path_nodes.size();
+}
+// Haplotype id of path h (ptx_upload_graph_gfa only; "" for graphs uploaded as arrays, whose names the caller has).  Returns the
+// length of the name; at most cap - 1 bytes and a terminating 0 are written.
+int ptx_species_path_name(ptx_ctx* ctx, int s, int64_t h, char* buf, size_t cap) {
+    int rc = check_species(ctx, s, false);
+    if (rc) return rc;
+    const SpeciesHost& sp = ctx->sp[s];
+    if (h < 0 || h >= sp.n_paths) return fail(ctx, PTX_E_RANGE, "path index out of range");
+    const std::string name = (size_t)h < sp.path_names.size() ? sp.path_names[(size_t)h] : std::string();
+    if (buf && cap) {
+        const size_t k = std::min(name.size(), cap - 1);
+        memcpy(buf, name.data(), k);
+        buf[k] = 0;
+    }
+    return (int)name.size();
 }
 
 int ptx_commit_graphs(ptx_ctx* ctx) {

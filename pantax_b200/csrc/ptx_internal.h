@@ -206,6 +206,17 @@ void launch_or_words(uint32_t* dst, const uint32_t* src, uint64_t n_words, cudaS
 void launch_bits_fill_full(const GraphDev& g, cudaStream_t st);
 void launch_or_slices(uint32_t* dst, const uint32_t* src, uint32_t n_src, uint64_t n_words, cudaStream_t st);
 
+// GFA graph text on the device (section 8f3)
+constexpr uint32_t GFA_PIECE_BYTES = 4096;
+struct GfaPathLineHost { unsigned long long line, name_beg, fld_beg, fld_end; uint32_t name_len, kind, pad0, pad1; };
+size_t gfa_path_line_bytes();
+void launch_gfa_lines(const uint8_t* text, const uint64_t* line_off, uint64_t n_lines, int64_t n_nodes, uint32_t* len, uint32_t* is_s, uint32_t* s_adj,
+                      void* plist, unsigned long long* pcount, uint64_t pcap, uint32_t* flags, cudaStream_t st);
+void launch_gfa_check_order(const uint32_t* is_s, const uint32_t* s_adj, const uint64_t* ord, uint64_t n_lines, uint32_t* flags, cudaStream_t st);
+void launch_gfa_path_count(const uint8_t* text, const uint64_t* piece_beg, const uint64_t* piece_fend, uint32_t* piece_cnt, uint32_t n_pieces, cudaStream_t st);
+void launch_gfa_path_decode(const uint8_t* text, const uint64_t* piece_beg, const uint64_t* piece_fend, const uint64_t* piece_fbeg, const uint64_t* piece_dst,
+                            int64_t n_nodes, uint32_t* out, uint32_t n_pieces, uint32_t* flags, cudaStream_t st);
+
 // K10 long-read filter
 void launch_flt_count_nl(const uint8_t* text, uint64_t n, uint32_t n_micro, uint32_t* cnt, cudaStream_t st);
 void launch_flt_line_starts(const uint8_t* text, uint64_t n, uint32_t n_micro, const uint64_t* micro_base, uint64_t* line_off, cudaStream_t st);

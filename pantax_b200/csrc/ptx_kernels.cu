@@ -31,6 +31,7 @@ int64_t kernel_launch_count() { return g_launches.load(); }
 // =====================================================================================
 // PTX helpers: mbarrier + TMA 1-D bulk copy (global -> shared), 128-bit CAS
 // =====================================================================================
+__device__ __forceinline__ uint32_t __smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -1058,6 +1059,10 @@ __device__ __noinline__ void parse_record_exact(const uint8_t* stage, uint32_t p
 template <bool CLS_MUL>
 __global__ void __launch_bounds__(SHORT_THREADS, PTX_SHORT_MINB) k_ingest_s(const IngestArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
+#ifdef PTX_DEBUG_TMA
+    long long dbg_t0 = 0;
+    const long long dbg_tk = clock64();
+#endif
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile_bytes = a.tile_bytes;                 // multiple of 128
     const uint32_t stage_bytes = tile_bytes + a.over_bytes;   // multiple of 128
@@ -1087,6 +1092,9 @@ __global__ void __launch_bounds__(SHORT_THREADS, PTX_SHORT_MINB) k_ingest_s(cons
     }
     __syncthreads();
     if (tid == 0) {
+#ifdef PTX_DEBUG_TMA
+        dbg_t0 = clock64();
+#endif
         mbar_expect_tx(&mbar, stage_bytes);
         bulk_g2s_hint(stage, gtile, stage_bytes, &mbar, a.pol_stream);  // the text is read once
         // the CTAs of a wave start together and would all wait for DRAM: fetch the tile of the CTA that takes this one's place into the L2 now
@@ -1109,6 +1117,9 @@ __global__ void __launch_bounds__(SHORT_THREADS, PTX_SHORT_MINB) k_ingest_s(cons
     const uint32_t glim = (uint32_t)min((uint64_t)0xFFFF0000ull, a.padded_bytes - t0);
     const RangesView& R = a.ranges;
     mbar_wait(&mbar, 0);
+#ifdef PTX_DEBUG_TMA
+    if (tid == 0 && (blockIdx.x % 5003u) == 7u) printf("tile %u sm %u: tma issue->ready %lld cycles, kernel start->issue %lld\n", blockIdx.x, (unsigned)__smid(), (long long)(clock64() - dbg_t0), (long long)(dbg_t0 - dbg_tk));
+#endif
 
     // ---- A: structural index of the window (the pad and the sentinel words written above become visible at the barrier behind it)
     for (uint32_t pc = tid; pc < stage_bytes / 16u; pc += SHORT_THREADS) {
@@ -2614,6 +2625,158 @@ __global__ void __launch_bounds__(256) k_flt_compact(const uint32_t* __restrict_
 }
 
 // =====================================================================================
+// GFA graph text -> node lengths + path steps on the device (profile.rs:466-545 read_gfa, previous = 0): SURVEY section 8(f3)
+//   k_gfa_lines        one thread per line: 'S' lines write len[id - 1] (the reference asserts that the S lines come in id order
+//                      without gaps: k_gfa_check_order verifies id - 1 == number of S lines before it, from a scan of the S flags);
+//                      'P' / 'W' lines are appended to a list {line, haplotype-name extent, path-field extent}
+//   k_gfa_path_count   the path fields are cut into 4 KB pieces (host table): ids ending in each piece (a digit followed by a non-digit)
+//   k_gfa_path_decode  ... and written, as id - 1, at the piece's destination + rank (the host lays the lines of one haplotype out
+//                      behind each other in file order - "chromosomes of one genome merge into one path", profile.rs:536-541)
+// Error bits (flags[0]): 1 S id not a number / out of range, 2 S lines out of order, 4 node length 0, 8 path line without a name field,
+// 16 path node id outside the graph.
+// =====================================================================================
+struct GfaPathLine { unsigned long long line, name_beg, fld_beg, fld_end; uint32_t name_len, kind, pad0, pad1; };  // 48 bytes
+constexpr uint32_t GFA_PIECE = 4096;
+
+__device__ __forceinline__ bool gfa_space(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }  // what str::trim removes (ASCII)
+
+__global__ void __launch_bounds__(256) k_gfa_lines(const uint8_t* __restrict__ text, const uint64_t* __restrict__ line_off, uint64_t n_lines,
+                                                   int64_t n_nodes, uint32_t* __restrict__ len, uint32_t* __restrict__ is_s,
+                                                   uint32_t* __restrict__ s_adj, GfaPathLine* __restrict__ plist, unsigned long long* pcount,
+                                                   uint64_t pcap, uint32_t* flags) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lines) return;
+    const uint64_t b = line_off[i];
+    uint64_t e = line_off[i + 1] - 1;  // the '\n'
+    is_s[i] = 0;
+    if (e <= b) return;
+    const uint8_t c0 = text[b];
+    if (c0 != 'S' && c0 != 'P' && c0 != 'W') return;
+    while (e > b && gfa_space(text[e - 1])) --e;  // line.trim() (the line starts with a letter: nothing to trim in front)
+    // the first three tabs
+    uint64_t t[3] = {e, e, e};
+    int nt = 0;
+    for (uint64_t p = b; p < e && nt < 3; ++p)
+        if (text[p] == '\t') t[nt++] = p;
+    if (c0 == 'S') {
+        if (nt < 2) return;  // parts.len() < 3: skipped
+        // parts[1].parse::<usize>(): digits only (a leading '+' is accepted by Rust's parser)
+        uint64_t p = t[0] + 1, v = 0;
+        uint32_t nd = 0;
+        if (p < t[1] && text[p] == '+') ++p;
+        for (; p < t[1]; ++p) {
+            const uint32_t d = (uint32_t)text[p] - (uint32_t)'0';
+            if (d > 9u || nd >= 18u) { nd = 0xFFFFu; break; }
+            v = v * 10u + d;
+            ++nd;
+        }
+        if (nd == 0u || nd == 0xFFFFu || v == 0 || (int64_t)(v - 1) >= n_nodes) { atomicOr(flags, 1u); return; }
+        const uint64_t seq_end = nt >= 3 ? t[2] : e;
+        const uint64_t l = seq_end - (t[1] + 1);
+        if (l == 0) { atomicOr(flags, 4u); return; }
+        len[v - 1] = (uint32_t)(l > 0xFFFFFFFFull ? 0xFFFFFFFFull : l);
+        is_s[i] = 1;
+        s_adj[i] = (uint32_t)(v - 1);
+        return;
+    }
+    // 'P' / 'W'
+    if (nt < 1) { atomicOr(flags, 8u); return; }  // parts[1] does not exist: the reference panics
+    const bool is_w = (t[0] == b + 1) && c0 == 'W';  // parts[0] == "W"
+    GfaPathLine pl;
+    pl.line = i;
+    pl.kind = is_w ? 2u : 1u;
+    pl.pad0 = pl.pad1 = 0;
+    pl.name_beg = t[0] + 1;
+    uint64_t name_end = t[1];  // (== e when the line has two fields)
+    if (!is_w)
+        for (uint64_t p = pl.name_beg; p < name_end; ++p)
+            if (text[p] == '#') { name_end = p; break; }  // parts[1].split('#').next()
+    pl.name_len = (uint32_t)(name_end - pl.name_beg);
+    if (is_w) {  // parts.last()
+        uint64_t last = b;
+        for (uint64_t p = e; p > b; --p)
+            if (text[p - 1] == '\t') { last = p; break; }
+        pl.fld_beg = last;
+        pl.fld_end = e;
+    } else {     // parts.get(2) or ""
+        pl.fld_beg = nt >= 2 ? t[1] + 1 : e;
+        pl.fld_end = nt >= 3 ? t[2] : e;
+    }
+    const unsigned long long k = atomicAdd(pcount, 1ull);
+    if (k < pcap) plist[k] = pl;
+}
+__global__ void __launch_bounds__(256) k_gfa_check_order(const uint32_t* __restrict__ is_s, const uint32_t* __restrict__ s_adj,
+                                                         const uint64_t* __restrict__ ord, uint64_t n_lines, uint32_t* flags) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_lines && is_s[i] && (uint64_t)s_adj[i] != ord[i]) atomicOr(flags, 2u);  // "Node ID out of order or mismatch" (profile.rs:489)
+}
+// ids ending in [pb, pe) of a path field that ends at fe: a digit whose successor (inside the field, or the byte that closes it) is none
+__device__ __forceinline__ uint32_t gfa_ends16(const uint8_t* __restrict__ text, uint64_t p0, uint64_t pe, uint64_t fe) {
+    uint32_t m = 0;
+    bool d = p0 < pe && ((uint32_t)text[p0] - (uint32_t)'0') <= 9u;
+    for (uint32_t k = 0; k < 16u && p0 + k < pe; ++k) {
+        const bool dn = (p0 + k + 1 < fe) && ((uint32_t)text[p0 + k + 1] - (uint32_t)'0') <= 9u;
+        if (d && !dn) m |= 1u << k;
+        d = dn;
+    }
+    return m;
+}
+__global__ void __launch_bounds__(256) k_gfa_path_count(const uint8_t* __restrict__ text, const uint64_t* __restrict__ piece_beg,
+                                                        const uint64_t* __restrict__ piece_fend, uint32_t* __restrict__ piece_cnt) {
+    __shared__ uint32_t wsum[8];
+    const uint64_t pb = piece_beg[blockIdx.x], fe = piece_fend[blockIdx.x];
+    const uint64_t pe = pb + GFA_PIECE < fe ? pb + GFA_PIECE : fe;
+    const uint64_t p0 = pb + 16ull * threadIdx.x;
+    uint32_t c = p0 < pe ? __popc(gfa_ends16(text, p0, pe, fe)) : 0u;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31u) == 0u) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int w = 0; w < 8; ++w) s += wsum[w];
+        piece_cnt[blockIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(256) k_gfa_path_decode(const uint8_t* __restrict__ text, const uint64_t* __restrict__ piece_beg,
+                                                         const uint64_t* __restrict__ piece_fend, const uint64_t* __restrict__ piece_fbeg,
+                                                         const uint64_t* __restrict__ piece_dst, int64_t n_nodes, uint32_t* __restrict__ out,
+                                                         uint32_t* flags) {
+    __shared__ uint32_t wsum[8];
+    const uint64_t pb = piece_beg[blockIdx.x], fe = piece_fend[blockIdx.x], fb = piece_fbeg[blockIdx.x];
+    const uint64_t pe = pb + GFA_PIECE < fe ? pb + GFA_PIECE : fe;
+    const uint64_t p0 = pb + 16ull * threadIdx.x;
+    uint32_t m = p0 < pe ? gfa_ends16(text, p0, pe, fe) : 0u;
+    const uint32_t c = __popc(m), lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t x = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= (uint32_t)d) x += y;
+    }
+    if (lane == 31u) wsum[warp] = x;
+    __syncthreads();
+    uint32_t rank = x - c;
+    for (uint32_t w = 0; w < warp; ++w) rank += wsum[w];
+    uint64_t dst = piece_dst[blockIdx.x] + rank;
+    while (m) {
+        const uint32_t k = __ffs(m) - 1;
+        m &= m - 1u;
+        uint64_t q = p0 + k;  // last digit of the id; its first digit is at most 18 bytes in front, not before the field
+        uint64_t v = 0, mul = 1;
+        uint32_t nd = 0;
+        while (q + 1 > fb && ((uint32_t)text[q] - (uint32_t)'0') <= 9u && nd < 19u) {
+            v += (uint64_t)(text[q] - '0') * mul;
+            mul *= 10u;
+            ++nd;
+            if (q == fb) break;
+            --q;
+        }
+        if (v == 0 || (int64_t)(v - 1) >= n_nodes || nd >= 19u) { atomicOr(flags, 16u); v = 1; }
+        out[dst++] = (uint32_t)(v - 1);
+    }
+}
+
+// =====================================================================================
 // launchers
 // =====================================================================================
 static inline uint32_t grid_for(uint64_t n, uint32_t per_block, uint32_t cap = 148u * 32u) {
@@ -2623,6 +2786,30 @@ static inline uint32_t grid_for(uint64_t n, uint32_t per_block, uint32_t cap = 1
     return (uint32_t)g;
 }
 
+void launch_gfa_lines(const uint8_t* text, const uint64_t* line_off, uint64_t n_lines, int64_t n_nodes, uint32_t* len, uint32_t* is_s, uint32_t* s_adj,
+                      void* plist, unsigned long long* pcount, uint64_t pcap, uint32_t* flags, cudaStream_t st) {
+    if (n_lines == 0) return;
+    k_gfa_lines<<<(uint32_t)((n_lines + 255) / 256), 256, 0, st>>>(text, line_off, n_lines, n_nodes, len, is_s, s_adj, reinterpret_cast<GfaPathLine*>(plist),
+                                                                      pcount, pcap, flags);
+    PTX_LAUNCHED();
+}
+void launch_gfa_check_order(const uint32_t* is_s, const uint32_t* s_adj, const uint64_t* ord, uint64_t n_lines, uint32_t* flags, cudaStream_t st) {
+    if (n_lines == 0) return;
+    k_gfa_check_order<<<(uint32_t)((n_lines + 255) / 256), 256, 0, st>>>(is_s, s_adj, ord, n_lines, flags);
+    PTX_LAUNCHED();
+}
+void launch_gfa_path_count(const uint8_t* text, const uint64_t* piece_beg, const uint64_t* piece_fend, uint32_t* piece_cnt, uint32_t n_pieces, cudaStream_t st) {
+    if (n_pieces == 0) return;
+    k_gfa_path_count<<<n_pieces, 256, 0, st>>>(text, piece_beg, piece_fend, piece_cnt);
+    PTX_LAUNCHED();
+}
+void launch_gfa_path_decode(const uint8_t* text, const uint64_t* piece_beg, const uint64_t* piece_fend, const uint64_t* piece_fbeg, const uint64_t* piece_dst,
+                            int64_t n_nodes, uint32_t* out, uint32_t n_pieces, uint32_t* flags, cudaStream_t st) {
+    if (n_pieces == 0) return;
+    k_gfa_path_decode<<<n_pieces, 256, 0, st>>>(text, piece_beg, piece_fend, piece_fbeg, piece_dst, n_nodes, out, flags);
+    PTX_LAUNCHED();
+}
+size_t gfa_path_line_bytes() { return sizeof(GfaPathLine); }
 void launch_count_records(const uint8_t* text, uint64_t n_bytes, uint32_t n_micro, uint32_t* micro_count, unsigned long long* total_slots,
                           cudaStream_t st) {
     k_count_records<<<(n_micro + 7) / 8, 256, 0, st>>>(text, n_bytes, n_micro, micro_count, total_slots);

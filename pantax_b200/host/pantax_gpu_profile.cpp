@@ -44,6 +44,7 @@ struct Options {
     std::string db, gaf, wd = ".", report, range_file, len_file, designated, reads_binning;
     bool species = false, strain = false, filtered = true, long_read = false, shift = false, force = false;
     double min_species_abundance = 1e-4, fr = -1, min_depth = 0;
+    bool host_gfa = false;  // --host-gfa: parse species GFAs with the C++ reader instead of on the device
     int mode = 2, device = 0, chunk_mb = 0;  // chunk_mb: size of the pinned GAF chunks (0: 64 MB)
 };
 
@@ -310,6 +311,7 @@ int main(int argc, char** argv) {
         else if (a == "--min-depth") o.min_depth = std::stod(next());
         else if (a == "--device") o.device = std::stoi(next());
         else if (a == "--chunk-mb") o.chunk_mb = std::stoi(next());
+        else if (a == "--host-gfa") o.host_gfa = true;
         else if (a == "--force") o.force = true;
         else if (a == "--dump-graph") {
             // reader check without a GPU: parse one graph file (.bin / .bin.lz4 / .bin.zst / .gfa by its extension) and print it
@@ -575,13 +577,35 @@ int main(int argc, char** argv) {
         // profile.rs:2888-2932: <db>/species_graph_info/<taxid>.bin | .bin.lz4 | .bin.zst (zip.rs:236-262), else <db>/species_gfa/<taxid>.gfa
         const std::string bin = o.db + "/species_graph_info/" + ranges[s].taxid + ".bin";
         const std::string gfa = o.db + "/species_gfa/" + ranges[s].taxid + ".gfa";
-        if (!(exists(bin) && read_bin_graph(bin, g, 0)) && !(exists(bin + ".lz4") && read_bin_graph(bin + ".lz4", g, 1)) &&
-            !(exists(bin + ".zst") && read_bin_graph(bin + ".zst", g, 2)) && !(exists(gfa) && read_gfa_graph(gfa, g)))
+        const bool have_bin = (exists(bin) && read_bin_graph(bin, g, 0)) || (exists(bin + ".lz4") && read_bin_graph(bin + ".lz4", g, 1)) ||
+                              (exists(bin + ".zst") && read_bin_graph(bin + ".zst", g, 2));
+        if (have_bin) {
+            std::vector<uint64_t> off{0}, flat;
+            for (auto& kv : g.paths) { flat.insert(flat.end(), kv.second.begin(), kv.second.end()); off.push_back(flat.size()); }
+            if (flat.empty()) flat.push_back(0);
+            ck(ctx, ptx_upload_graph(ctx, s, g.nodes_len.data(), (int64_t)g.nodes_len.size(), off.data(), flat.data(), (int64_t)g.paths.size()), "ptx_upload_graph");
+        } else if (exists(gfa) && !o.host_gfa) {
+            // the GFA text is parsed on the device (read_gfa, profile.rs:466-545); the Graph the tables below need comes back compact
+            std::vector<uint8_t> bytes;
+            if (!slurp(gfa, bytes) || bytes.empty()) die("cannot read " + gfa);
+            ck(ctx, ptx_upload_graph_gfa(ctx, s, bytes.data(), bytes.size()), "ptx_upload_graph_gfa");
+            const int64_t n = ptx_species_nodes(ctx, s), H = ptx_species_paths(ctx, s), P = ptx_species_path_steps(ctx, s);
+            g.nodes_len.resize((size_t)n);
+            std::vector<uint64_t> off((size_t)H + 1), flat((size_t)std::max<int64_t>(P, 1));
+            ck(ctx, ptx_species_graph(ctx, s, g.nodes_len.data(), off.data(), flat.data()), "ptx_species_graph");
+            for (int64_t h = 0; h < H; ++h) {
+                char name[4096];
+                if (ptx_species_path_name(ctx, s, h, name, sizeof name) < 0) die("ptx_species_path_name failed");
+                g.paths[name].assign(flat.begin() + (ptrdiff_t)off[(size_t)h], flat.begin() + (ptrdiff_t)off[(size_t)h + 1]);
+            }
+        } else if (exists(gfa) && read_gfa_graph(gfa, g)) {
+            std::vector<uint64_t> off{0}, flat;
+            for (auto& kv : g.paths) { flat.insert(flat.end(), kv.second.begin(), kv.second.end()); off.push_back(flat.size()); }
+            if (flat.empty()) flat.push_back(0);
+            ck(ctx, ptx_upload_graph(ctx, s, g.nodes_len.data(), (int64_t)g.nodes_len.size(), off.data(), flat.data(), (int64_t)g.paths.size()), "ptx_upload_graph");
+        } else {
             die("gfa information file for " + ranges[s].taxid + " does not exist. Please check database.");  // profile.rs:2929
-        std::vector<uint64_t> off{0}, flat;
-        for (auto& kv : g.paths) { flat.insert(flat.end(), kv.second.begin(), kv.second.end()); off.push_back(flat.size()); }
-        if (flat.empty()) flat.push_back(0);
-        ck(ctx, ptx_upload_graph(ctx, s, g.nodes_len.data(), (int64_t)g.nodes_len.size(), off.data(), flat.data(), (int64_t)g.paths.size()), "ptx_upload_graph");
+        }
         graphs[s] = std::move(g);
     }
     if (chosen.empty()) { fprintf(stderr, "The filtering before strain profiling has removed all species.\n"); ptx_destroy(ctx); return 0; }

@@ -18,6 +18,10 @@ extern "C" {
     pub fn ptx_set_ranges(ctx: *mut ptx_ctx, n: c_int, taxid: *const *const c_char, start: *const i64, end: *const i64) -> c_int;
     pub fn ptx_upload_graph(ctx: *mut ptx_ctx, species: c_int, nodes_len: *const i64, n: i64, path_off: *const u64,
                             path_nodes: *const u64, n_paths: i64) -> c_int;
+    pub fn ptx_upload_graph_gfa(ctx: *mut ptx_ctx, species: c_int, gfa: *const u8, n: usize) -> c_int;
+    pub fn ptx_species_graph(ctx: *mut ptx_ctx, species: c_int, nodes_len: *mut i64, path_off: *mut u64, path_nodes: *mut u64) -> c_int;
+    pub fn ptx_species_path_steps(ctx: *const ptx_ctx, species: c_int) -> i64;
+    pub fn ptx_species_path_name(ctx: *mut ptx_ctx, species: c_int, h: i64, buf: *mut c_char, cap: usize) -> c_int;
     pub fn ptx_commit_graphs(ctx: *mut ptx_ctx) -> c_int;
     pub fn ptx_reserve(ctx: *mut ptx_ctx, expected_records: i64) -> c_int;
     pub fn ptx_host_alloc(bytes: size_t, out: *mut *mut c_void) -> c_int;
@@ -107,6 +111,10 @@ impl Gpu {
         for p in paths.values() { flat.extend(p.iter().map(|&v| v as u64)); off.push(flat.len() as u64); }
         if flat.is_empty() { flat.push(0); }
         self.ck(unsafe { ptx_upload_graph(self.raw, species as c_int, nodes_len.as_ptr(), nodes_len.len() as i64, off.as_ptr(), flat.as_ptr(), paths.len() as i64) })
+    }
+    /// profile.rs:466-545 `read_gfa(&gfa_file, 0)` on the device: hand over the file's bytes instead of a parsed `Graph`.
+    pub fn upload_graph_gfa(&self, species: usize, gfa: &[u8]) -> Result<(), GpuError> {
+        self.ck(unsafe { ptx_upload_graph_gfa(self.raw, species as c_int, gfa.as_ptr(), gfa.len()) })
     }
     pub fn commit_graphs(&self) -> Result<(), GpuError> { self.ck(unsafe { ptx_commit_graphs(self.raw) }) }
     pub fn ingest_gaf(&self, bytes: &[u8], is_last: bool) -> Result<(), GpuError> {
