@@ -1226,6 +1226,7 @@ int ptx_upload_graph_gfa(ptx_ctx* ctx, int s, const uint8_t* gfa, size_t n) {
     SpeciesHost& sp = ctx->sp[s];
     const int64_t n_nodes = sp.end - sp.start + 1;  // profile.rs:2938: nvert = end - start + 1 indexes nodes_len
     cudaStream_t st = ctx->st;
+    Trace tr(st);
     const bool add_nl = gfa[n - 1] != '\n';
     const uint64_t nn = n + (add_nl ? 1 : 0);
     const uint32_t n_micro = (uint32_t)((nn + MICRO - 1) / MICRO);
@@ -1252,6 +1253,7 @@ int ptx_upload_graph_gfa(ptx_ctx* ctx, int s, const uint8_t* gfa, size_t n) {
     uint64_t n_lines = 0;
     cudaMemcpyAsync(&n_lines, d_base + n_micro, sizeof n_lines, cudaMemcpyDeviceToHost, st);
     GFA_SYNC("newline index");
+    tr.mark("gfa h2d + newline index");
     GFA(dalloc(ctx, &d_line, (size_t)n_lines + 2, false));
     launch_flt_line_starts(d_text, nn, n_micro, d_base, d_line, st);
     // ---- lines: node lengths, S-line order, list of path lines
@@ -1280,6 +1282,7 @@ int ptx_upload_graph_gfa(ptx_ctx* ctx, int s, const uint8_t* gfa, size_t n) {
         dfree(d_plist);
         pcap = np;
     }
+    tr.mark("gfa line pass");
     dfree(d_scratch);
     GFA(dalloc(ctx, &d_scratch, (size_t)n_lines / 2048 + 4, false));
     launch_scan_u32(d_is_s, d_ord, n_lines, d_scratch, st);
@@ -1303,6 +1306,7 @@ int ptx_upload_graph_gfa(ptx_ctx* ctx, int s, const uint8_t* gfa, size_t n) {
         return fail(ctx, PTX_E_NVERT_MISMATCH, "species %s: range %lld..%lld has %lld ids but the GFA has %lld S lines", sp.taxid.c_str(), (long long)sp.start,
                     (long long)sp.end, (long long)n_nodes, (long long)n_s);
     }
+    tr.mark("gfa order check");
     // ---- path lines in file order; names from the text (tiny copies); pieces of 4 KB over their path fields
     std::sort(plines.begin(), plines.end(), [](const GfaPathLineHost& a, const GfaPathLineHost& b) { return a.line < b.line; });
     std::vector<std::string> names(plines.size());
@@ -1311,12 +1315,47 @@ int ptx_upload_graph_gfa(ptx_ctx* ctx, int s, const uint8_t* gfa, size_t n) {
         if (plines[k].name_len) cudaMemcpy(&names[k][0], d_text + plines[k].name_beg, plines[k].name_len, cudaMemcpyDeviceToHost);
     }
     std::vector<uint64_t> pbeg, pfend, pfbeg;
-    std::vector<uint32_t> first_piece(plines.size() + 1, 0);
-    for (size_t k = 0; k < plines.size(); ++k) {
-        first_piece[k] = (uint32_t)pbeg.size();
-        for (uint64_t p = plines[k].fld_beg; p < plines[k].fld_end; p += GFA_PIECE_BYTES) { pbeg.push_back(p); pfend.push_back(plines[k].fld_end); pfbeg.push_back(plines[k].fld_beg); }
+    std::vector<uint32_t> first_piece(plines.size() + 1, 0), pline;
+    auto cut_pieces = [&]() {
+        pbeg.clear(); pfend.clear(); pfbeg.clear(); pline.clear();
+        for (size_t k = 0; k < plines.size(); ++k) {
+            first_piece[k] = (uint32_t)pbeg.size();
+            for (uint64_t p = plines[k].fld_beg; p < plines[k].fld_end; p += GFA_PIECE_BYTES) {
+                pbeg.push_back(p); pfend.push_back(plines[k].fld_end); pfbeg.push_back(plines[k].fld_beg); pline.push_back((uint32_t)k);
+            }
+        }
+        first_piece[plines.size()] = (uint32_t)pbeg.size();
+    };
+    cut_pieces();
+    if (!pbeg.empty()) {  // where the path field really ends: the first tab behind its start (found in parallel; a path field is megabytes long)
+        const uint32_t np0 = (uint32_t)pbeg.size();
+        uint64_t* d_tmp = nullptr;
+        uint32_t* d_pl = nullptr;
+        unsigned long long* d_tab = nullptr;
+        std::vector<unsigned long long> tab(plines.size(), ~0ull);
+        if ((rc = dalloc(ctx, &d_tmp, (size_t)np0 * 2, false)) || (rc = dalloc(ctx, &d_pl, (size_t)np0, false)) || (rc = dalloc(ctx, &d_tab, plines.size(), false))) {
+            cudaFree(d_tmp); cudaFree(d_pl); cudaFree(d_tab); cleanup(); return rc;
+        }
+        cudaMemcpyAsync(d_tmp, pbeg.data(), (size_t)np0 * 8, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_tmp + np0, pfend.data(), (size_t)np0 * 8, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_pl, pline.data(), (size_t)np0 * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_tab, tab.data(), plines.size() * 8, cudaMemcpyHostToDevice, st);
+        launch_gfa_field_end(d_text, d_tmp, d_tmp + np0, d_pl, d_tab, np0, st);
+        cudaMemcpyAsync(tab.data(), d_tab, plines.size() * 8, cudaMemcpyDeviceToHost, st);
+        const bool ok = cudaStreamSynchronize(st) == cudaSuccess;
+        cudaFree(d_tmp); cudaFree(d_pl); cudaFree(d_tab);
+        if (!ok) { cleanup(); return fail(ctx, PTX_E_CUDA, "ptx_upload_graph_gfa: field ends: %s", cudaGetErrorString(cudaGetLastError())); }
+        for (size_t k = 0; k < plines.size(); ++k) {
+            if (tab[k] == ~0ull) continue;
+            if (plines[k].kind == 2u) {
+                cleanup();
+                return fail(ctx, PTX_E_UNSUPPORTED, "species %s: a W line has fields behind its walk (the device parser takes the 7th field as the walk)", sp.taxid.c_str());
+            }
+            plines[k].fld_end = tab[k];
+        }
+        cut_pieces();
     }
-    first_piece[plines.size()] = (uint32_t)pbeg.size();
+    tr.mark("gfa names + field ends");
     const uint32_t n_pieces = (uint32_t)pbeg.size();
     std::vector<uint64_t> poff((size_t)n_pieces + 1, 0);
     if (n_pieces) {
@@ -1326,13 +1365,16 @@ int ptx_upload_graph_gfa(ptx_ctx* ctx, int s, const uint8_t* gfa, size_t n) {
         cudaMemcpyAsync(d_pieces, pbeg.data(), (size_t)n_pieces * 8, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_pieces + n_pieces, pfend.data(), (size_t)n_pieces * 8, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_pieces + 2 * (size_t)n_pieces, pfbeg.data(), (size_t)n_pieces * 8, cudaMemcpyHostToDevice, st);
-        launch_gfa_path_count(d_text, d_pieces, d_pieces + n_pieces, d_pcnt, n_pieces, st);
+        launch_gfa_path_count(d_text, d_pieces, d_pieces + n_pieces, d_pcnt, n_pieces, d_flags, st);
         dfree(d_scratch);
         GFA(dalloc(ctx, &d_scratch, (size_t)n_pieces / 2048 + 4, false));
         launch_scan_u32(d_pcnt, d_poff, n_pieces, d_scratch, st);
         cudaMemcpyAsync(poff.data(), d_poff, ((size_t)n_pieces + 1) * 8, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st);
         GFA_SYNC("path count");
+
     }
+    tr.mark("gfa path count");
     // haplotypes in BTreeMap (byte) order of their names; the lines of one haplotype behind each other in file order
     std::map<std::string, std::vector<size_t>> haps;
     for (size_t k = 0; k < plines.size(); ++k) haps[names[k]].push_back(k);
@@ -1362,6 +1404,7 @@ int ptx_upload_graph_gfa(ptx_ctx* ctx, int s, const uint8_t* gfa, size_t n) {
         GFA_SYNC("path decode");
         if (h_flags[0]) return flag_error(h_flags[0]);
     }
+    tr.mark("gfa path decode + d2h");
     sp.len.resize((size_t)n_nodes);
     cudaMemcpy(sp.len.data(), d_len, (size_t)n_nodes * sizeof(uint32_t), cudaMemcpyDeviceToHost);
     cleanup();

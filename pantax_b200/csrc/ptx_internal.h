@@ -210,10 +210,13 @@ void launch_or_slices(uint32_t* dst, const uint32_t* src, uint32_t n_src, uint64
 constexpr uint32_t GFA_PIECE_BYTES = 4096;
 struct GfaPathLineHost { unsigned long long line, name_beg, fld_beg, fld_end; uint32_t name_len, kind, pad0, pad1; };
 size_t gfa_path_line_bytes();
+void launch_gfa_field_end(const uint8_t* text, const uint64_t* piece_beg, const uint64_t* piece_fend, const uint32_t* piece_line, unsigned long long* line_tab,
+                          uint32_t n_pieces, cudaStream_t st);
 void launch_gfa_lines(const uint8_t* text, const uint64_t* line_off, uint64_t n_lines, int64_t n_nodes, uint32_t* len, uint32_t* is_s, uint32_t* s_adj,
                       void* plist, unsigned long long* pcount, uint64_t pcap, uint32_t* flags, cudaStream_t st);
 void launch_gfa_check_order(const uint32_t* is_s, const uint32_t* s_adj, const uint64_t* ord, uint64_t n_lines, uint32_t* flags, cudaStream_t st);
-void launch_gfa_path_count(const uint8_t* text, const uint64_t* piece_beg, const uint64_t* piece_fend, uint32_t* piece_cnt, uint32_t n_pieces, cudaStream_t st);
+void launch_gfa_path_count(const uint8_t* text, const uint64_t* piece_beg, const uint64_t* piece_fend, uint32_t* piece_cnt, uint32_t n_pieces, uint32_t* flags,
+                           cudaStream_t st);
 void launch_gfa_path_decode(const uint8_t* text, const uint64_t* piece_beg, const uint64_t* piece_fend, const uint64_t* piece_fbeg, const uint64_t* piece_dst,
                             int64_t n_nodes, uint32_t* out, uint32_t n_pieces, uint32_t* flags, cudaStream_t st);
 

@@ -2633,7 +2633,7 @@ __global__ void __launch_bounds__(256) k_flt_compact(const uint32_t* __restrict_
 //   k_gfa_path_decode  ... and written, as id - 1, at the piece's destination + rank (the host lays the lines of one haplotype out
 //                      behind each other in file order - "chromosomes of one genome merge into one path", profile.rs:536-541)
 // Error bits (flags[0]): 1 S id not a number / out of range, 2 S lines out of order, 4 node length 0, 8 path line without a name field,
-// 16 path node id outside the graph.
+// 16 path node id outside the graph, 32 a tab inside a W line's walk field (more than seven fields).
 // =====================================================================================
 struct GfaPathLine { unsigned long long line, name_beg, fld_beg, fld_end; uint32_t name_len, kind, pad0, pad1; };  // 48 bytes
 constexpr uint32_t GFA_PIECE = 4096;
@@ -2653,10 +2653,11 @@ __global__ void __launch_bounds__(256) k_gfa_lines(const uint8_t* __restrict__ t
     const uint8_t c0 = text[b];
     if (c0 != 'S' && c0 != 'P' && c0 != 'W') return;
     while (e > b && gfa_space(text[e - 1])) --e;  // line.trim() (the line starts with a letter: nothing to trim in front)
-    // the first three tabs
-    uint64_t t[3] = {e, e, e};
+    // the first tabs (three; six for a W line, whose walk is its 7th and last field)
+    uint64_t t[6] = {e, e, e, e, e, e};
     int nt = 0;
-    for (uint64_t p = b; p < e && nt < 3; ++p)
+    const int want = c0 == 'W' ? 6 : (c0 == 'P' ? 2 : 3);  // (the path field of a P line is megabytes long: its end is found by k_gfa_field_end)
+    for (uint64_t p = b; p < e && nt < want; ++p)
         if (text[p] == '\t') t[nt++] = p;
     if (c0 == 'S') {
         if (nt < 2) return;  // parts.len() < 3: skipped
@@ -2692,15 +2693,15 @@ __global__ void __launch_bounds__(256) k_gfa_lines(const uint8_t* __restrict__ t
         for (uint64_t p = pl.name_beg; p < name_end; ++p)
             if (text[p] == '#') { name_end = p; break; }  // parts[1].split('#').next()
     pl.name_len = (uint32_t)(name_end - pl.name_beg);
-    if (is_w) {  // parts.last()
-        uint64_t last = b;
-        for (uint64_t p = e; p > b; --p)
-            if (text[p - 1] == '\t') { last = p; break; }
-        pl.fld_beg = last;
+    if (is_w) {
+        // parts.last(): a W line is `W sample hap seq start end walk` - the walk (megabytes long) is what follows the sixth tab; that
+        // no tab hides further inside it (a line with more fields) is checked by the piece kernels, not by a serial scan here.  A W
+        // line with fewer fields: the last field starts behind its last tab.
+        pl.fld_beg = nt ? t[nt - 1] + 1 : b;
         pl.fld_end = e;
-    } else {     // parts.get(2) or ""
+    } else {     // parts.get(2) or "": from behind the second tab to the next tab (k_gfa_field_end) or the end of the line
         pl.fld_beg = nt >= 2 ? t[1] + 1 : e;
-        pl.fld_end = nt >= 3 ? t[2] : e;
+        pl.fld_end = e;
     }
     const unsigned long long k = atomicAdd(pcount, 1ull);
     if (k < pcap) plist[k] = pl;
@@ -2709,6 +2710,17 @@ __global__ void __launch_bounds__(256) k_gfa_check_order(const uint32_t* __restr
                                                          const uint64_t* __restrict__ ord, uint64_t n_lines, uint32_t* flags) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_lines && is_s[i] && (uint64_t)s_adj[i] != ord[i]) atomicOr(flags, 2u);  // "Node ID out of order or mismatch" (profile.rs:489)
+}
+// first tab inside the candidate path field of every P / W line (pieces of 4 KB, as below): the P field ends there; a W line has more
+// than seven fields then
+__global__ void __launch_bounds__(256) k_gfa_field_end(const uint8_t* __restrict__ text, const uint64_t* __restrict__ piece_beg,
+                                                       const uint64_t* __restrict__ piece_fend, const uint32_t* __restrict__ piece_line,
+                                                       unsigned long long* line_tab) {
+    const uint64_t pb = piece_beg[blockIdx.x], fe = piece_fend[blockIdx.x];
+    const uint64_t pe = pb + GFA_PIECE < fe ? pb + GFA_PIECE : fe;
+    const uint64_t p0 = pb + 16ull * threadIdx.x;
+    for (uint32_t k = 0; k < 16u && p0 + k < pe; ++k)
+        if (text[p0 + k] == '\t') { atomicMin(line_tab + piece_line[blockIdx.x], (unsigned long long)(p0 + k)); break; }
 }
 // ids ending in [pb, pe) of a path field that ends at fe: a digit whose successor (inside the field, or the byte that closes it) is none
 __device__ __forceinline__ uint32_t gfa_ends16(const uint8_t* __restrict__ text, uint64_t p0, uint64_t pe, uint64_t fe) {
@@ -2722,12 +2734,13 @@ __device__ __forceinline__ uint32_t gfa_ends16(const uint8_t* __restrict__ text,
     return m;
 }
 __global__ void __launch_bounds__(256) k_gfa_path_count(const uint8_t* __restrict__ text, const uint64_t* __restrict__ piece_beg,
-                                                        const uint64_t* __restrict__ piece_fend, uint32_t* __restrict__ piece_cnt) {
+                                                        const uint64_t* __restrict__ piece_fend, uint32_t* __restrict__ piece_cnt, uint32_t* flags) {
     __shared__ uint32_t wsum[8];
     const uint64_t pb = piece_beg[blockIdx.x], fe = piece_fend[blockIdx.x];
     const uint64_t pe = pb + GFA_PIECE < fe ? pb + GFA_PIECE : fe;
     const uint64_t p0 = pb + 16ull * threadIdx.x;
     uint32_t c = p0 < pe ? __popc(gfa_ends16(text, p0, pe, fe)) : 0u;
+    (void)flags;
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31u) == 0u) wsum[threadIdx.x >> 5] = c;
     __syncthreads();
@@ -2798,15 +2811,22 @@ void launch_gfa_check_order(const uint32_t* is_s, const uint32_t* s_adj, const u
     k_gfa_check_order<<<(uint32_t)((n_lines + 255) / 256), 256, 0, st>>>(is_s, s_adj, ord, n_lines, flags);
     PTX_LAUNCHED();
 }
-void launch_gfa_path_count(const uint8_t* text, const uint64_t* piece_beg, const uint64_t* piece_fend, uint32_t* piece_cnt, uint32_t n_pieces, cudaStream_t st) {
+void launch_gfa_path_count(const uint8_t* text, const uint64_t* piece_beg, const uint64_t* piece_fend, uint32_t* piece_cnt, uint32_t n_pieces, uint32_t* flags,
+                           cudaStream_t st) {
     if (n_pieces == 0) return;
-    k_gfa_path_count<<<n_pieces, 256, 0, st>>>(text, piece_beg, piece_fend, piece_cnt);
+    k_gfa_path_count<<<n_pieces, 256, 0, st>>>(text, piece_beg, piece_fend, piece_cnt, flags);
     PTX_LAUNCHED();
 }
 void launch_gfa_path_decode(const uint8_t* text, const uint64_t* piece_beg, const uint64_t* piece_fend, const uint64_t* piece_fbeg, const uint64_t* piece_dst,
                             int64_t n_nodes, uint32_t* out, uint32_t n_pieces, uint32_t* flags, cudaStream_t st) {
     if (n_pieces == 0) return;
     k_gfa_path_decode<<<n_pieces, 256, 0, st>>>(text, piece_beg, piece_fend, piece_fbeg, piece_dst, n_nodes, out, flags);
+    PTX_LAUNCHED();
+}
+void launch_gfa_field_end(const uint8_t* text, const uint64_t* piece_beg, const uint64_t* piece_fend, const uint32_t* piece_line, unsigned long long* line_tab,
+                          uint32_t n_pieces, cudaStream_t st) {
+    if (n_pieces == 0) return;
+    k_gfa_field_end<<<n_pieces, 256, 0, st>>>(text, piece_beg, piece_fend, piece_line, line_tab);
     PTX_LAUNCHED();
 }
 size_t gfa_path_line_bytes() { return sizeof(GfaPathLine); }

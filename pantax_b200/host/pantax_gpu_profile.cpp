@@ -312,6 +312,34 @@ int main(int argc, char** argv) {
         else if (a == "--device") o.device = std::stoi(next());
         else if (a == "--chunk-mb") o.chunk_mb = std::stoi(next());
         else if (a == "--host-gfa") o.host_gfa = true;
+        else if (a == "--time-gfa") {
+            // graph load of one species GFA both ways: the C++ reader on the host, and ptx_upload_graph_gfa (H2D + kernels + compact arrays back)
+            const std::string path = next();
+            std::vector<uint8_t> bytes;
+            if (!slurp(path, bytes) || bytes.empty()) die("cannot read " + path);
+            auto t0 = std::chrono::steady_clock::now();
+            Graph g;
+            if (!read_gfa_graph(path, g)) die("cannot parse " + path);
+            const double t_host = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            ptx_ctx* c = nullptr;
+            if (ptx_create(o.device, &c) != PTX_OK) die("no usable CUDA device");
+            const char* nm = "1";
+            const int64_t st1 = 1, en1 = (int64_t)g.nodes_len.size();
+            ck(c, ptx_set_ranges(c, 1, &nm, &st1, &en1), "ptx_set_ranges");
+            double t_dev = 0;
+            for (int rep = 0; rep < 2; ++rep) {  // the second call has the context warm
+                t0 = std::chrono::steady_clock::now();
+                ck(c, ptx_upload_graph_gfa(c, 0, bytes.data(), bytes.size()), "ptx_upload_graph_gfa");
+                t_dev = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            }
+            size_t steps = 0;
+            for (auto& kv : g.paths) steps += kv.second.size();
+            if ((size_t)ptx_species_path_steps(c, 0) != steps || ptx_species_paths(c, 0) != (int64_t)g.paths.size()) die("device and host parse disagree");
+            printf("{\"gfa_bytes\": %zu, \"nodes\": %zu, \"paths\": %zu, \"path_steps\": %zu, \"host_reader_s\": %.4f, \"device_parse_s\": %.4f}\n", bytes.size(),
+                   g.nodes_len.size(), g.paths.size(), steps, t_host, t_dev);
+            ptx_destroy(c);
+            return 0;
+        }
         else if (a == "--force") o.force = true;
         else if (a == "--dump-graph") {
             // reader check without a GPU: parse one graph file (.bin / .bin.lz4 / .bin.zst / .gfa by its extension) and print it
