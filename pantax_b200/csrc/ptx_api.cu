@@ -1079,7 +1079,7 @@ int ptx_create(int device, ptx_ctx** out) {
     if (const char* e = getenv("PTX_TILE_BYTES")) ctx->force_tile = atoi(e);
     if (const char* e = getenv("PTX_OLD_INGEST")) ctx->old_short = atoi(e) != 0;
     if (const char* e = getenv("PTX_LONG_NEW")) ctx->long_new = atoi(e) != 0;
-    if (const char* e = getenv("PTX_LONG_TILE")) ctx->long_tile_max = std::min<uint32_t>(MAX_TILE, std::max<uint32_t>(MICRO, (uint32_t)atoi(e) / MICRO * MICRO));
+    if (const char* e = getenv("PTX_LONG_TILE")) ctx->long_tile_max = std::min<uint32_t>(LONG_TILE_MAX, std::max<uint32_t>(MICRO, (uint32_t)atoi(e) / MICRO * MICRO));
     if (const char* e = getenv("PTX_NO_SORT")) ctx->no_sort = atoi(e) != 0;
     if (const char* e = getenv("PTX_KEEP_TEXT")) ctx->keep_text = atoi(e) != 0;
     if (const char* e = getenv("PTX_SCATTER")) ctx->scatter_var = atoi(e);

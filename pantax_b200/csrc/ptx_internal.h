@@ -37,7 +37,14 @@ constexpr uint32_t SHORT_REC_CAP = PTX_SHORT_RECCAP;  // k_ingest_s: line starts
 #define PTX_LONG_MINB 4
 #endif
 constexpr uint32_t LONG_REC_CAP = 512;   // k_ingest_l: line starts kept in smem per round (4 CTAs of 55 KB per SM)
-constexpr uint32_t LONG_TILE_MAX = 7 * 4096;  // k_ingest_l: largest tile (4 resident CTAs per SM)
+#ifndef PTX_LONG_THREADS
+#define PTX_LONG_THREADS 256
+#endif
+#ifndef PTX_LONG_TILE_MAX
+#define PTX_LONG_TILE_MAX (7 * 4096)
+#endif
+constexpr int LONG_THREADS = PTX_LONG_THREADS;  // k_ingest_l
+constexpr uint32_t LONG_TILE_MAX = PTX_LONG_TILE_MAX;  // k_ingest_l: largest tile (4 resident CTAs per SM)
 constexpr uint32_t REC_CAP = 1024;  // record starts kept in smem per round
 constexpr double LONG_LINE_BYTES = 320.0;  // mean line length from which a chunk is parsed by k_ingest<LONG>
 constexpr uint32_t HIST_SLOTS_LOG2 = 7;  // per-tile species-count accumulators in shared memory (multi-species runs)

@@ -1426,9 +1426,9 @@ __global__ void __launch_bounds__(SHORT_THREADS, PTX_SHORT_MINB) k_ingest_s(cons
 //       record-table entry
 // Lines the word-wide path declines (fast_cols) or whose walk has a 10+ digit id go through the exact byte parser.
 // =====================================================================================
-constexpr uint32_t LONG_WPT = (MAX_TILE + OVER) / 32u / INGEST_THREADS + 1u;  // bitmap words a thread of k_ingest_l takes
+constexpr uint32_t LONG_WPT = (LONG_TILE_MAX + OVER) / 32u / LONG_THREADS + 1u;  // bitmap words a thread of k_ingest_l takes
 
-__global__ void __launch_bounds__(INGEST_THREADS, PTX_LONG_MINB) k_ingest_l(const IngestArgs a) {
+__global__ void __launch_bounds__(LONG_THREADS, PTX_LONG_MINB) k_ingest_l(const IngestArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile_bytes = a.tile_bytes;                 // multiple of 4096
@@ -1441,15 +1441,15 @@ __global__ void __launch_bounds__(INGEST_THREADS, PTX_LONG_MINB) k_ingest_l(cons
     uint32_t* ndw = tabw + bm_alloc;    // non-digit bytes
     uint32_t* ew = ndw + bm_alloc;      // the ends of the walk ids of the group's lines
     uint16_t* epre = reinterpret_cast<uint16_t*>(ew + bm_alloc);  // ids that end in front of each bitmap word (exclusive prefix over the tile: < 2^16, an id takes two bytes)
-    uint32_t* lmin = reinterpret_cast<uint32_t*>(epre + bm_alloc);                                                        // [INGEST_THREADS] smallest / largest walk id of each line of the group
-    uint32_t* lmax = lmin + INGEST_THREADS;                                                  // [INGEST_THREADS]
-    uint16_t* lp6 = reinterpret_cast<uint16_t*>(lmax + INGEST_THREADS);                      // [INGEST_THREADS] first byte of the line's walk column (line start if it has none)
-    uint16_t* lend = lp6 + INGEST_THREADS;                                                   // [INGEST_THREADS] one past its closing tab (<= lp6: no column)
-    uint16_t* rec_start = lend + INGEST_THREADS;                                             // [LONG_REC_CAP]
+    uint32_t* lmin = reinterpret_cast<uint32_t*>(epre + bm_alloc);                                                        // [LONG_THREADS] smallest / largest walk id of each line of the group
+    uint32_t* lmax = lmin + LONG_THREADS;                                                  // [LONG_THREADS]
+    uint16_t* lp6 = reinterpret_cast<uint16_t*>(lmax + LONG_THREADS);                      // [LONG_THREADS] first byte of the line's walk column (line start if it has none)
+    uint16_t* lend = lp6 + LONG_THREADS;                                                   // [LONG_THREADS] one past its closing tab (<= lp6: no column)
+    uint16_t* rec_start = lend + LONG_THREADS;                                             // [LONG_REC_CAP]
     uint16_t* inv_pre = rec_start + LONG_REC_CAP;                                                 // [LONG_REC_CAP]
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t warp_tot[INGEST_THREADS / 32];
-    __shared__ uint32_t inv_flag, inv_tot_s, slot_base_s, node_base_s, slow_bits[INGEST_THREADS / 32];
+    __shared__ uint32_t warp_tot[LONG_THREADS / 32];
+    __shared__ uint32_t inv_flag, inv_tot_s, slot_base_s, node_base_s, slow_bits[LONG_THREADS / 32];
     const Words Wd{smem_u32(stage), nullptr}, Wtab{smem_u32(tabw), nullptr}, Wnl{smem_u32(nlw), nullptr};
 
     const uint64_t t0 = (uint64_t)blockIdx.x * tile_bytes;
@@ -1477,7 +1477,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, PTX_LONG_MINB) k_ingest_l(cons
     __shared__ uint32_t pv[CLASSIFY_PIVOTS];  // every stride-th range start: the first level of the species search
     const int pv_stride = a.ranges.S > CLASSIFY_PIVOTS ? (a.ranges.S + CLASSIFY_PIVOTS - 1) / CLASSIFY_PIVOTS : 1;
     const int npv = (a.ranges.disjoint && a.ranges.S > 1) ? (a.ranges.S + pv_stride - 1) / pv_stride : 0;
-    for (int i = (int)tid; i < npv; i += INGEST_THREADS) pv[i] = sstart[i * pv_stride];  // (visible behind the barrier that follows the structural index)
+    for (int i = (int)tid; i < npv; i += LONG_THREADS) pv[i] = sstart[i * pv_stride];  // (visible behind the barrier that follows the structural index)
     const bool single_pass = a.micro_base == nullptr;
     const uint32_t rec_base = single_pass ? 0u : (uint32_t)a.micro_base[(uint64_t)blockIdx.x * (tile_bytes / MICRO)];
     const uint32_t glim = (uint32_t)min((uint64_t)0xFFFF0000ull, a.padded_bytes - t0);
@@ -1485,7 +1485,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, PTX_LONG_MINB) k_ingest_l(cons
     mbar_wait(&mbar, 0);
 
     // ---- A: structural index of the window: newline, tab and non-digit flags
-    for (uint32_t pc = tid; pc < stage_bytes / 16u; pc += INGEST_THREADS) {
+    for (uint32_t pc = tid; pc < stage_bytes / 16u; pc += LONG_THREADS) {
         const uint4 q = reinterpret_cast<const uint4*>(stage)[pc];
         uint32_t nl16, tab16;
         classify16(q.x, q.y, q.z, q.w, nl16, tab16);
@@ -1505,7 +1505,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, PTX_LONG_MINB) k_ingest_l(cons
     for (uint32_t round = 0; round == 0 || round < n_rec; round += LONG_REC_CAP) {
         // ---- B: number the line starts (as k_ingest_s)
         uint32_t idx_base = 0;
-        for (uint32_t w0 = 0; w0 < nw; w0 += 4u * INGEST_THREADS) {
+        for (uint32_t w0 = 0; w0 < nw; w0 += 4u * LONG_THREADS) {
             const uint32_t wi = w0 + 4u * tid;
             uint4 m4 = make_uint4(0u, 0u, 0u, 0u);
             if (wi < nw) {
@@ -1531,7 +1531,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, PTX_LONG_MINB) k_ingest_l(cons
             __syncthreads();
             uint32_t idx = idx_base + x - cnt, tot = 0;
 #pragma unroll
-            for (int w = 0; w < INGEST_THREADS / 32; ++w) {
+            for (int w = 0; w < LONG_THREADS / 32; ++w) {
                 const uint32_t t = warp_tot[w];
                 if ((uint32_t)w < warp) idx += t;
                 tot += t;
@@ -1585,10 +1585,10 @@ __global__ void __launch_bounds__(INGEST_THREADS, PTX_LONG_MINB) k_ingest_l(cons
             if (tid == 0) inv_flag = 0;
         }
 
-        for (uint32_t g0 = 0; g0 < n_round; g0 += INGEST_THREADS) {  // groups of one line per thread, in file order
-            const uint32_t ng = min((uint32_t)INGEST_THREADS, n_round - g0);  // lines of the group
+        for (uint32_t g0 = 0; g0 < n_round; g0 += LONG_THREADS) {  // groups of one line per thread, in file order
+            const uint32_t ng = min((uint32_t)LONG_THREADS, n_round - g0);  // lines of the group
             // ---- C1: the scalar columns of the line; the extent of its walk column goes to lp6 / lend
-            if (tid < INGEST_THREADS / 32) slow_bits[tid] = 0u;
+            if (tid < LONG_THREADS / 32) slow_bits[tid] = 0u;
             const uint32_t k = g0 + tid;
             const bool slot = k < n_round;
             const uint32_t p = slot ? rec_start[k] : 0u;
@@ -1616,7 +1616,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, PTX_LONG_MINB) k_ingest_l(cons
             // thread that owns the bitmap word.  The lines a word meets come from a binary search over the group's line starts.
             {
                 // a thread takes `wpt` consecutive bitmap words (at most LONG_WPT: 34 KB of window / 32 / 256 threads)
-                const uint32_t wpt = (bm_words + INGEST_THREADS - 1u) / INGEST_THREADS;
+                const uint32_t wpt = (bm_words + LONG_THREADS - 1u) / LONG_THREADS;
                 const uint32_t wi = wpt * tid, wn = wi < bm_words ? min(wpt, bm_words - wi) : 0u;
                 uint32_t E[LONG_WPT];
 #pragma unroll
@@ -1662,7 +1662,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, PTX_LONG_MINB) k_ingest_l(cons
                 __syncthreads();
                 uint32_t before = x - cnt, tot = 0;
 #pragma unroll
-                for (int w = 0; w < INGEST_THREADS / 32; ++w) {
+                for (int w = 0; w < LONG_THREADS / 32; ++w) {
                     const uint32_t t = warp_tot[w];
                     if ((uint32_t)w < warp) before += t;
                     tot += t;
@@ -2849,7 +2849,7 @@ size_t ingest_smem_bytes(uint32_t tile_bytes, uint32_t over_bytes, bool short_ke
 size_t ingest_l_smem_bytes(uint32_t tile_bytes, uint32_t over_bytes, bool multi_species) {
     const size_t stage_bytes = (size_t)tile_bytes + over_bytes;
     const size_t bm_alloc = (stage_bytes / 32 + 2 + 3) / 4 * 4;
-    return stage_bytes + STAGE_PAD + 4 * bm_alloc * sizeof(uint32_t) + bm_alloc * sizeof(uint16_t) + INGEST_THREADS * (2 * sizeof(uint32_t) + 2 * sizeof(uint16_t)) +
+    return stage_bytes + STAGE_PAD + 4 * bm_alloc * sizeof(uint32_t) + bm_alloc * sizeof(uint16_t) + LONG_THREADS * (2 * sizeof(uint32_t) + 2 * sizeof(uint16_t)) +
            2 * LONG_REC_CAP * sizeof(uint16_t);
 }
 
@@ -2880,7 +2880,7 @@ void launch_ingest(const IngestArgs& a, cudaStream_t st) {
     if (a.long_mode && !a.long_new) k_ingest<true><<<a.n_tiles, INGEST_THREADS, ingest_smem_bytes(a.tile_bytes, OVER, false, multi), st>>>(a);
     else if (a.long_mode) {
         static const int padl = getenv("PTX_SMEM_PAD_L") ? atoi(getenv("PTX_SMEM_PAD_L")) : 0;  // measurement knob: fewer resident CTAs
-        k_ingest_l<<<a.n_tiles, INGEST_THREADS, ingest_l_smem_bytes(a.tile_bytes, a.over_bytes, multi) + (size_t)std::min(padl, 8192), st>>>(a);
+        k_ingest_l<<<a.n_tiles, LONG_THREADS, ingest_l_smem_bytes(a.tile_bytes, a.over_bytes, multi) + (size_t)std::min(padl, 8192), st>>>(a);
     }
     else if (a.old_short) k_ingest<false><<<a.n_tiles, INGEST_THREADS, ingest_smem_bytes(a.tile_bytes, OVER, false, multi), st>>>(a);
     else {
