@@ -2903,7 +2903,10 @@ __global__ void __launch_bounds__(256) k_count_labelled(const unsigned long long
         if (threadIdx.x < d) part[threadIdx.x] += part[threadIdx.x + d];
         __syncthreads();
     }
-    if (threadIdx.x == 0) atomicOr(dst, (part[0] < 1000ull ? part[0] : 1000ull) << 8);
+    if (threadIdx.x == 0) {  // (ptx_finalize may run again after more input: replace the count, keep the marker bit)
+        atomicAnd(dst, 0xFFull);
+        atomicOr(dst, (part[0] < 1000ull ? part[0] : 1000ull) << 8);
+    }
 }
 void launch_count_labelled(const unsigned long long* hist, uint32_t S, unsigned long long* dst, cudaStream_t st) {
     k_count_labelled<<<1, 256, 0, st>>>(hist, S, dst);

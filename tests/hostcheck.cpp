@@ -146,6 +146,14 @@ int hostcheck_run(const uint8_t* gaf, uint64_t n, int S, const int64_t* rstart, 
                 }
             }
             p.label = classify(R, p.r.W ? p.r.vmin : -1, p.r.W ? p.r.vmax : -1, R.sstart);
+            // the two-level species search the ingest kernels use (pivots of the sorted starts) must give the same label, for every
+            // pivot stride (1 = every start is a pivot ... S = a single pivot)
+            for (int stride : {1, 2, 3, 7, S > 1 ? S / 2 : 1, S}) {
+                if (stride < 1) continue;
+                std::vector<uint32_t> pv;
+                for (int i = 0; i < S; i += stride) pv.push_back(R.sstart[i]);
+                if (classify_pivots(R, p.r.W ? p.r.vmin : -1, p.r.W ? p.r.vmax : -1, R.sstart, pv.data(), (int)pv.size(), stride) != p.label) return 12;
+            }
             p.eligible = p.label != LABEL_U && !p.r.path_null && p.r.c7 != NULL_I64 && p.r.c8 != NULL_I64 && p.r.c9 != NULL_I64;
             recs.push_back(p);
         }

@@ -69,7 +69,7 @@ def run_hostcheck(ranges, graphs, gaf: bytes, oracle, stage_lim=0, use_stash=1):
                     _p(order, C.c_uint32), disjoint, C.c_int64(N), _p(ln, C.c_uint32), C.c_int64(T), _p(tk, C.c_uint32),
                     C.c_uint32(stage_lim), use_stash, _p(labels, C.c_uint32), C.byref(nrec), _p(hist, C.c_int64), _p(bases, C.c_int64),
                     _p(cov, C.c_uint64), _p(tb, C.c_int64), _p(err, C.c_uint32), C.byref(uniq), C.byref(nover), C.byref(nfast))
-    assert rc == 0, f"hostcheck_run failed with code {rc} (9 = parse_head/parse_tail disagree with parse_record, 10 = fast_parse disagrees with parse_record, 11 = classify16 bitmaps wrong)"
+    assert rc == 0, f"hostcheck_run failed with code {rc} (9 = parse_head/parse_tail disagree with parse_record, 10 = fast_parse disagrees with parse_record, 11 = classify16 bitmaps wrong, 12 = classify_pivots disagrees with classify)"
     return dict(labels=labels[:nrec.value], hist=hist, bases=bases, cov=cov, trio_bases=tb, err=err,
                 ids_unique=bool(uniq.value), node_base=node_base, tbase=tbase, n_overflow=nover.value, n_fast=nfast.value)
 
