@@ -154,7 +154,7 @@ struct ptx_ctx {
     bool no_sort = false;    // PTX_NO_SORT=1: k_ingest_s keeps file order inside a tile (measurements)
     int pf_waves = 1;          // PTX_PF_WAVES: L2 prefetch distance of the ingest kernels in waves of resident CTAs (0: off)
     int n_sm = 148;
-    bool ds_cas_first = false;  // PTX_DS_CAS_FIRST=1: id-set insert with the CAS before the load (measured: k_apply 0.933 vs 0.936 ms - no gain)
+    uint32_t ds_epoch = 1;   // id-set slots written in another epoch are empty (ds_new_pass); 1..255
     int l2_hints = 1;        // PTX_L2_HINTS: bit 0 = graph arrays evict-last (k_apply 0.969 -> 0.938 ms), bit 1 = GAF text evict-first (no gain), bit 2 = id-set loads evict-first (slower: 1.00 ms); IngestArgs::pol_*
     bool old_short = false;  // PTX_OLD_INGEST=1: round 1's byte-at-a-time short-read kernel (A/B measurements)
     uint32_t long_tile_max = LONG_TILE_MAX;  // PTX_LONG_TILE: largest tile of k_ingest_l in bytes (multiple of 4096; measurements)
@@ -310,13 +310,23 @@ int ds_ensure_total(ptx_ctx* ctx, int64_t entries) {
     CU(cudaMalloc((void**)&nd, want * sizeof(ulonglong2)));
     CU(cudaMemsetAsync(nd, 0, want * sizeof(ulonglong2), ctx->st));
     if (ctx->d_ds && (ctx->ds_records > 0 || ctx->ds_entries_bound > 0))
-        launch_ds_rehash(ctx->d_ds, ctx->ds_cap, nd, 64 - log2_ceil(want), want - 1, ctx->st);
+        launch_ds_rehash(ctx->d_ds, ctx->ds_cap, nd, 64 - log2_ceil(want), want - 1, ctx->ds_epoch, ctx->st);
     if (ctx->d_ds) {
         CU(cudaStreamSynchronize(ctx->st));
         cudaFree(ctx->d_ds);
     }
     ctx->d_ds = nd;
     ctx->ds_cap = want;
+    return PTX_OK;
+}
+// A new pass over the reads: every slot of the id set becomes empty by moving on to the next epoch; the table is cleared for real
+// only when the 8-bit epoch wraps (the memset of 512 MB per 10 M-record step was 4 % of it).
+int ds_new_pass(ptx_ctx* ctx) {
+    if (!ctx->d_ds) return PTX_OK;
+    if (++ctx->ds_epoch > 255u) {
+        ctx->ds_epoch = 1;
+        CU(cudaMemsetAsync(ctx->d_ds, 0, ctx->ds_cap * sizeof(ulonglong2), ctx->st));
+    }
     return PTX_OK;
 }
 int ds_ensure(ptx_ctx* ctx, int64_t more_records) { return ds_ensure_total(ctx, std::max(ctx->ds_records, ctx->ds_entries_bound) + more_records); }
@@ -371,7 +381,7 @@ IngestArgs make_args(ptx_ctx* ctx, const Chunk& ch) {
     a.pol_keep = (ctx->l2_hints & 1) ? 0x14F0000000000000ull : 0x1000000000000000ull;    // createpolicy evict_last / evict_normal, fraction 1.0
     a.pol_stream = (ctx->l2_hints & 2) ? 0x12F0000000000000ull : 0x1000000000000000ull;  // evict_first
     a.pol_ds = (ctx->l2_hints & 4) ? 0x12F0000000000000ull : 0x1000000000000000ull;
-    a.ds_cas_first = ctx->ds_cas_first ? 1u : 0u;
+    a.ds_epoch = ctx->ds_epoch;
     a.pair_key = ctx->d_pair_key;
     a.pair_val = ctx->d_pair_val;
     a.flags = ctx->d_flags;
@@ -855,7 +865,7 @@ int return_mixed_ids(ptx_ctx* ctx, cudaStream_t st) {
     if ((rc = dalloc(ctx, &d_tmp, (size_t)P + 2))) return rc;
     unsigned long long* d_nmix = d_tmp;
     unsigned long long* d_allmix = d_tmp + 1;
-    launch_ds_collect_mixed(ctx->d_ds, ctx->ds_cap, d_nmix, nullptr, 0, st);
+    launch_ds_collect_mixed(ctx->d_ds, ctx->ds_cap, ctx->ds_epoch, d_nmix, nullptr, 0, st);
     if ((rc = nccl_check(ctx, g_nccl.AllGather(d_nmix, d_allmix, 1, ncclUint64, ctx->comm, st), "ncclAllGather(mixed counts)"))) return rc;
     std::vector<unsigned long long> nmix(P);
     CU(cudaMemcpyAsync(nmix.data(), d_allmix, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -867,11 +877,11 @@ int return_mixed_ids(ptx_ctx* ctx, cudaStream_t st) {
         ulonglong2* everyone = nullptr;
         if ((rc = dalloc(ctx, &mine, (size_t)mx)) || (rc = dalloc(ctx, &everyone, (size_t)mx * P))) return rc;
         CU(cudaMemsetAsync(d_nmix, 0, sizeof(unsigned long long), st));
-        launch_ds_collect_mixed(ctx->d_ds, ctx->ds_cap, d_nmix, mine, mx, st);
+        launch_ds_collect_mixed(ctx->d_ds, ctx->ds_cap, ctx->ds_epoch, d_nmix, mine, mx, st);
         if ((rc = nccl_check(ctx, g_nccl.AllGather(mine, everyone, mx * 2, ncclUint64, ctx->comm, st), "ncclAllGather(mixed ids)"))) return rc;
         ctx->ds_entries_bound += (int64_t)total;
         if ((rc = ds_ensure_total(ctx, ctx->ds_entries_bound))) return rc;
-        launch_ds_apply_mixed(everyone, mx * P, ctx->d_ds, 64 - log2_ceil(ctx->ds_cap), ctx->ds_cap - 1, st);
+        launch_ds_apply_mixed(everyone, mx * P, ctx->d_ds, 64 - log2_ceil(ctx->ds_cap), ctx->ds_cap - 1, ctx->ds_epoch, ctx->d_flags, st);
         CU(cudaStreamSynchronize(st));
         cudaFree(mine);
         cudaFree(everyone);
@@ -918,7 +928,7 @@ int exchange_begin(ptx_ctx* ctx) {
             ctx->box_cap = 0;
         }
         if ((rc = xchg_ensure(ctx, (int64_t)((worst + worst / 4) * (unsigned long long)P)))) return rc;
-        CU(cudaMemsetAsync(ctx->d_ds, 0, ctx->ds_cap * sizeof(ulonglong2), ctx->st));
+        if ((rc = ds_new_pass(ctx))) return rc;
         CU(cudaMemsetAsync(ctx->d_flags, 0, 3 * sizeof(uint32_t), ctx->st));
         CU(cudaMemsetAsync(d_cur, 0, (P + 1) * sizeof(unsigned long long), ctx->st));
         std::fill(ctx->box_sent.begin(), ctx->box_sent.end(), 0ull);
@@ -980,7 +990,7 @@ int exchange_begin(ptx_ctx* ctx) {
     }
     // peer-memory boxes: the entries are already here - k_apply of the other ranks stored them into this rank's inbox
     // over NVLink; the all-gather above ordered this point behind those kernels
-    launch_ds_merge_boxes(ctx->p2p ? ctx->p2p_inbox : ctx->inbox, d_par, d_par + P, (uint32_t)nb, max_recv, ctx->d_ds, 64 - log2_ceil(ctx->ds_cap), ctx->ds_cap - 1, ctx->d_flags, xs);
+    launch_ds_merge_boxes(ctx->p2p ? ctx->p2p_inbox : ctx->inbox, d_par, d_par + P, (uint32_t)nb, max_recv, ctx->d_ds, 64 - log2_ceil(ctx->ds_cap), ctx->ds_cap - 1, ctx->ds_epoch, ctx->d_flags, xs);
     trx.mark("xchg merge");
     if ((rc = nccl_check(ctx, g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 2, ncclUint32, ncclMax, ctx->comm_x, xs), "ncclAllReduce(flags)"))) return rc;
     trx.mark("xchg flags");
@@ -1079,12 +1089,11 @@ int ptx_create(int device, ptx_ctx** out) {
     if (const char* e = getenv("PTX_TILE_BYTES")) ctx->force_tile = atoi(e);
     if (const char* e = getenv("PTX_OLD_INGEST")) ctx->old_short = atoi(e) != 0;
     if (const char* e = getenv("PTX_LONG_NEW")) ctx->long_new = atoi(e) != 0;
-    if (const char* e = getenv("PTX_LONG_TILE")) ctx->long_tile_max = std::min<uint32_t>(LONG_TILE_MAX, std::max<uint32_t>(MICRO, (uint32_t)atoi(e) / MICRO * MICRO));
+    if (const char* e = getenv("PTX_LONG_TILE")) ctx->long_tile_max = std::min<uint32_t>(MAX_TILE, std::max<uint32_t>(MICRO, (uint32_t)atoi(e) / MICRO * MICRO));
     if (const char* e = getenv("PTX_NO_SORT")) ctx->no_sort = atoi(e) != 0;
     if (const char* e = getenv("PTX_KEEP_TEXT")) ctx->keep_text = atoi(e) != 0;
     if (const char* e = getenv("PTX_SCATTER")) ctx->scatter_var = atoi(e);
     if (const char* e = getenv("PTX_L2_HINTS")) ctx->l2_hints = atoi(e);
-    if (const char* e = getenv("PTX_DS_CAS_FIRST")) ctx->ds_cas_first = atoi(e) != 0;
     if (const char* e = getenv("PTX_PF_WAVES")) ctx->pf_waves = atoi(e);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (const char* e = getenv("PTX_LONG_MODE")) ctx->force_long = atoi(e) ? 1 : 0;
@@ -1139,6 +1148,7 @@ const char* ptx_last_error(const ptx_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int ptx_set_ranges(ptx_ctx* ctx, int S, const char* const* taxid, const int64_t* start, const int64_t* end) {
     if (!ctx || S <= 0 || !taxid || !start || !end) return fail(ctx, PTX_E_INVALID, "ptx_set_ranges: bad arguments");
+    if (S >= 0xFFFFFD) return fail(ctx, PTX_E_UNSUPPORTED, "more than 2^24 - 3 species (the id-set slots keep the species in 24 bits)");
     if (!ctx->chunks.empty() || ctx->graphs_committed) return fail(ctx, PTX_E_STATE, "ranges must be set before graphs and GAF");
     cudaSetDevice(ctx->device);
     for (int s = 0; s < S; ++s)  // node ids are u32 in the reference too (profile.rs:547-551 SpeciesRange{start: u32, end: u32})
@@ -1931,7 +1941,7 @@ static int reset_impl(ptx_ctx* ctx, bool keep_buffers) {
         std::fill(ctx->recv_done.begin(), ctx->recv_done.end(), 0ull);
     }
     ctx->ds_entries_bound = 0;
-    if (ctx->d_ds) CU(cudaMemsetAsync(ctx->d_ds, 0, ctx->ds_cap * sizeof(ulonglong2), ctx->st));
+    { int rc = ds_new_pass(ctx); if (rc) return rc; }
     if (ctx->d_err) {
         int rc = zero_coverage(ctx);
         if (rc) return rc;

@@ -162,7 +162,7 @@ struct IngestArgs {
     // id-set slots - is fetched evict-first, the graph arrays every read gathers from (ninfo, bases, bitmap, trio table)
     // evict-last, so that 1.7 GB of streams per step do not push 30 MB of node arrays out of the L2
     uint64_t pol_keep, pol_stream, pol_ds;
-    uint32_t ds_cas_first;  // id-set insert: CAS before looking (PTX_DS_CAS_FIRST, measurements)
+    uint32_t ds_epoch;      // id-set slots of another epoch are empty (a new pass increments it instead of clearing the table)
 };
 
 // launchers (ptx_kernels.cu); all asynchronous on `st`
@@ -177,14 +177,14 @@ void launch_tile_rows(const uint4* tile_info, uint32_t* rows, uint32_t n_tiles, 
 void launch_labels_from_table(const uint4* tile_info, const uint64_t* tile_off, const uint4* meta_b, const uint16_t* row_key, uint32_t* labels,
                               uint32_t n_tiles, cudaStream_t st);
 void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2* new_slots, uint32_t new_shift,
-                      uint64_t new_mask, cudaStream_t st);
+                      uint64_t new_mask, uint32_t ep, cudaStream_t st);
 void launch_ninfo_build(const uint32_t* len, const uint64_t* bit_off, uint4* ninfo, int64_t N, cudaStream_t st);
 void launch_ninfo_full(uint4* ninfo, uint8_t* full, int64_t N, int mode, cudaStream_t st);
 // cross-rank id groups (multi-GPU finalize)
-void launch_ds_collect_mixed(const ulonglong2* slots, uint64_t cap, unsigned long long* cursor, ulonglong2* out, uint64_t out_cap, cudaStream_t st);
+void launch_ds_collect_mixed(const ulonglong2* slots, uint64_t cap, uint32_t ep, unsigned long long* cursor, ulonglong2* out, uint64_t out_cap, cudaStream_t st);
 void launch_ds_merge_boxes(const ulonglong2* inbox, const unsigned long long* off, const unsigned long long* cnt, uint32_t n_boxes, uint64_t max_cnt,
-                           ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags, cudaStream_t st);
-void launch_ds_apply_mixed(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, cudaStream_t st);
+                           ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t ep, uint32_t* flags, cudaStream_t st);
+void launch_ds_apply_mixed(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t ep, uint32_t* flags, cudaStream_t st);
 
 // graph commit
 void launch_mark_path_dups(uint32_t* pnode, const uint64_t* poff, int64_t Htot, int64_t P, const uint64_t* pbm_off, const uint32_t* pbase, uint32_t* bm,

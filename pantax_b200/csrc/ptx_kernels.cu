@@ -168,40 +168,55 @@ __global__ void __launch_bounds__(256) k_count_records(const uint8_t* __restrict
 
 
 // =====================================================================================
-// read-id set (open addressing, 16-byte slots {hash.lo, hash.hi<<32 | state}, 128-bit CAS)
+// read-id set (open addressing, 16-byte slots {hash.lo, hash.hi<<32 | epoch<<24 | state}, 128-bit CAS)
+//
+// Slots carry the EPOCH of the pass that wrote them (1..255, ptx_ctx::ds_epoch): a slot of another epoch is empty.  Starting a new
+// pass (ptx_rewind / ptx_reset) is an increment instead of a memset of the whole table (512 MB for 10 M reads at load 0.3, every
+// step); the table is cleared for real when the epoch wraps.  Inside a slot the state takes 24 bits: a species index (< 2^24 - 3),
+// DS_NONE or DS_MIXED; on the wire (exchange boxes, MIXED lists) entries keep the plain 32-bit state of ptx_core.cuh.
 // =====================================================================================
 __device__ __forceinline__ uint64_t ds_home(const IdHash& h, uint32_t shift) {
     return ((h.lo ^ ((uint64_t)h.hi << 17)) * 0x9E3779B97F4A7C15ull) >> shift;
 }
+__device__ __forceinline__ uint32_t ds_enc(uint32_t state, uint32_t ep) { return (ep << 24) | (state & 0xFFFFFFu); }
+__device__ __forceinline__ uint32_t ds_dec(uint32_t enc) {
+    const uint32_t v = enc & 0xFFFFFFu;
+    return v >= 0xFFFFFDu ? (0xFF000000u | v) : v;  // DS_MIXED = 0xFFFFFFFD, DS_NONE = 0xFFFFFFFE
+}
+__device__ __forceinline__ bool ds_live(const ulonglong2& cur, uint32_t ep) { return (((uint32_t)cur.y) >> 24) == ep; }
+__device__ __forceinline__ bool ds_same(const ulonglong2& a, const ulonglong2& b) { return a.x == b.x && a.y == b.y; }
 
-// profile.rs:369-378 (uniqueness over all non-U rows) + :406-437 (species set per id group,
-// over coverage-eligible rows only).
-__device__ __forceinline__ void ds_insert(ulonglong2* slots, uint32_t shift, uint64_t mask, const IdHash& h, bool eligible,
-                                          uint32_t label, uint32_t* flags, uint64_t pol, bool cas_first) {
-    const uint64_t hi_part = (uint64_t)h.hi << 32;
-    const ulonglong2 mine = make_ulonglong2(h.lo, hi_part | (eligible ? label : DS_NONE));
+// Insert-or-merge of one id with state `st` (a species, or DS_NONE for a row that is not coverage-eligible; DS_MIXED from the
+// wire): profile.rs:369-378 (uniqueness over all non-U rows) + :406-437 (species set per id group over eligible rows only).
+// Returns through flags[0] "id seen before", flags[1] "a group became mixed".
+__device__ __forceinline__ void ds_upsert(ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t ep, uint64_t lo, uint32_t hi, uint32_t st,
+                                          uint32_t* flags, uint64_t pol, bool count_repeat) {
+    const uint64_t hi_part = (uint64_t)hi << 32;
+    const ulonglong2 mine = make_ulonglong2(lo, hi_part | ds_enc(st, ep));
+    IdHash h;
+    h.lo = lo;
+    h.hi = hi;
     uint64_t i = ds_home(h, shift);
     for (;;) {
-        // optimistic: at load 0.3 seven probes of ten meet an empty slot, so the CAS goes first (one round trip to a slot that
-        // comes from DRAM instead of a load and then the CAS); a failed CAS returns the occupant, as the load would
-        ulonglong2 cur = cas_first ? atomic_cas128(slots + i, make_ulonglong2(0ull, 0ull), mine) : ld128_hint(slots + i, pol);
-        if (cur.x == 0ull && cur.y == 0ull) {
-            if (cas_first) return;  // inserted
-            cur = atomic_cas128(slots + i, make_ulonglong2(0ull, 0ull), mine);
-            if (cur.x == 0ull && cur.y == 0ull) return;  // inserted
+        ulonglong2 cur = ld128_hint(slots + i, pol);
+        if (!ds_live(cur, ep)) {  // empty (never written, or left by an earlier pass): claim it
+            const ulonglong2 prev = atomic_cas128(slots + i, cur, mine);
+            if (ds_same(prev, cur)) return;  // inserted
+            cur = prev;                       // somebody else claimed it in this pass
+            if (!ds_live(cur, ep)) continue;  // (cannot happen: a slot only changes into the current epoch; look again)
         }
-        if (cur.x == h.lo && (cur.y >> 32) == (uint64_t)h.hi) {  // same read id seen before
-            if (flags[0] == 0u) atomicOr(flags + 0, 1u);
-            if (!eligible) return;
+        if (cur.x == lo && (cur.y >> 32) == (uint64_t)hi) {  // same read id seen before in this pass
+            if (count_repeat && flags[0] == 0u) atomicOr(flags + 0, 1u);
             for (;;) {
-                uint32_t st = (uint32_t)cur.y;
+                const uint32_t old = ds_dec((uint32_t)cur.y);
                 uint32_t nst;
-                if (st == DS_NONE) nst = label;
-                else if (st == label || st == DS_MIXED) return;
+                if (old == DS_NONE) nst = st;
+                else if (st == DS_NONE || old == st || old == DS_MIXED) return;
                 else nst = DS_MIXED;
-                ulonglong2 want = make_ulonglong2(cur.x, hi_part | nst);
-                ulonglong2 prev = atomic_cas128(slots + i, cur, want);
-                if (prev.x == cur.x && prev.y == cur.y) {
+                if (nst == old) return;
+                const ulonglong2 want = make_ulonglong2(cur.x, hi_part | ds_enc(nst, ep));
+                const ulonglong2 prev = atomic_cas128(slots + i, cur, want);
+                if (ds_same(prev, cur)) {
                     if (nst == DS_MIXED) atomicOr(flags + 1, 1u);
                     return;
                 }
@@ -211,29 +226,37 @@ __device__ __forceinline__ void ds_insert(ulonglong2* slots, uint32_t shift, uin
         i = (i + 1) & mask;
     }
 }
+__device__ __forceinline__ void ds_insert(ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t ep, const IdHash& h, bool eligible,
+                                          uint32_t label, uint32_t* flags, uint64_t pol) {
+    ds_upsert(slots, shift, mask, ep, h.lo, h.hi, eligible ? label : DS_NONE, flags, pol, true);
+}
 
-__device__ __forceinline__ uint32_t ds_lookup(const ulonglong2* slots, uint32_t shift, uint64_t mask, const IdHash& h, uint64_t pol) {
+__device__ __forceinline__ uint32_t ds_lookup(const ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t ep, const IdHash& h, uint64_t pol) {
     uint64_t i = ds_home(h, shift);
     for (;;) {
         ulonglong2 cur = ld128_hint(slots + i, pol);
-        if (cur.x == 0ull && cur.y == 0ull) return DS_NONE;
-        if (cur.x == h.lo && (cur.y >> 32) == (uint64_t)h.hi) return (uint32_t)cur.y;
+        if (!ds_live(cur, ep)) return DS_NONE;
+        if (cur.x == h.lo && (cur.y >> 32) == (uint64_t)h.hi) return ds_dec((uint32_t)cur.y);
         i = (i + 1) & mask;
     }
 }
 
+// the live slots of the old table move to a new (zeroed) one, keeping their epoch
 __global__ void __launch_bounds__(256) k_ds_rehash(const ulonglong2* __restrict__ old_slots, uint64_t old_cap, ulonglong2* new_slots,
-                                                   uint32_t new_shift, uint64_t new_mask) {
+                                                   uint32_t new_shift, uint64_t new_mask, uint32_t ep) {
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < old_cap; k += (uint64_t)gridDim.x * blockDim.x) {
         ulonglong2 e = old_slots[k];
-        if (e.x == 0ull && e.y == 0ull) continue;
+        if (!ds_live(e, ep)) continue;
         IdHash h;
         h.lo = e.x;
         h.hi = (uint32_t)(e.y >> 32);
         uint64_t i = ds_home(h, new_shift);
         for (;;) {
-            ulonglong2 cur = atomic_cas128(new_slots + i, make_ulonglong2(0ull, 0ull), e);
-            if (cur.x == 0ull && cur.y == 0ull) break;
+            const ulonglong2 cur = ld128(new_slots + i);
+            if (!ds_live(cur, ep)) {
+                const ulonglong2 prev = atomic_cas128(new_slots + i, cur, e);
+                if (ds_same(prev, cur)) break;
+            }
             i = (i + 1) & new_mask;
         }
     }
@@ -245,89 +268,36 @@ __global__ void __launch_bounds__(256) k_ds_rehash(const ulonglong2* __restrict_
 __device__ __forceinline__ uint32_t ds_owner(const ulonglong2& e, uint32_t P) {
     return ((uint32_t)(e.y >> 32) ^ (uint32_t)(e.x >> 40)) % P;
 }
-__device__ __forceinline__ uint32_t ds_merge_state(uint32_t l, uint32_t f) {
-    if (l == DS_NONE) return f;
-    if (f == DS_NONE || l == f) return l;
-    return DS_MIXED;
-}
-// Owner side: merge the entries received from peer blockIdx.y (inbox + off[peer], cnt[peer] entries) into this rank's
+// Owner side: merge the entries received from peer blockIdx.y (inbox + off[peer], cnt[peer] entries; wire format) into this rank's
 // id set - the same insert-or-merge as ds_insert, with the sender's state instead of a single record's.
 __global__ void __launch_bounds__(256) k_ds_merge_boxes(const ulonglong2* __restrict__ inbox, const unsigned long long* __restrict__ off,
                                                         const unsigned long long* __restrict__ cnt, ulonglong2* slots, uint32_t shift,
-                                                        uint64_t mask, uint32_t* flags) {
+                                                        uint64_t mask, uint32_t ep, uint32_t* flags) {
     const ulonglong2* box = inbox + off[blockIdx.y];
     const uint64_t n = cnt[blockIdx.y];
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
         const ulonglong2 e = box[k];
-        IdHash h;
-        h.lo = e.x;
-        h.hi = (uint32_t)(e.y >> 32);
-        const uint32_t fst = (uint32_t)e.y;
-        uint64_t i = ds_home(h, shift);
-        for (;;) {
-            ulonglong2 cur = ld128(slots + i);
-            if (cur.x == 0ull && cur.y == 0ull) {
-                cur = atomic_cas128(slots + i, make_ulonglong2(0ull, 0ull), e);
-                if (cur.x == 0ull && cur.y == 0ull) break;
-            }
-            if (cur.x == e.x && (cur.y >> 32) == (e.y >> 32)) {  // the same read id on two ranks (or twice on one)
-                if (flags[0] == 0u) atomicOr(flags + 0, 1u);
-                for (;;) {
-                    const uint32_t nst = ds_merge_state((uint32_t)cur.y, fst);
-                    if (nst == (uint32_t)cur.y) break;
-                    const ulonglong2 want = make_ulonglong2(cur.x, (cur.y & 0xFFFFFFFF00000000ull) | nst);
-                    const ulonglong2 prev = atomic_cas128(slots + i, cur, want);
-                    if (prev.x == cur.x && prev.y == cur.y) {
-                        if (nst == DS_MIXED) atomicOr(flags + 1, 1u);
-                        break;
-                    }
-                    cur = prev;
-                }
-                break;
-            }
-            i = (i + 1) & mask;
-        }
+        ds_upsert(slots, shift, mask, ep, e.x, (uint32_t)(e.y >> 32), (uint32_t)e.y, flags, 0x1000000000000000ull, true);
     }
 }
-__global__ void __launch_bounds__(256) k_ds_collect_mixed(const ulonglong2* __restrict__ slots, uint64_t cap, unsigned long long* cursor,
+// the MIXED ids of this rank's set, in wire format
+__global__ void __launch_bounds__(256) k_ds_collect_mixed(const ulonglong2* __restrict__ slots, uint64_t cap, uint32_t ep, unsigned long long* cursor,
                                                           ulonglong2* __restrict__ out, uint64_t out_cap) {
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cap; k += (uint64_t)gridDim.x * blockDim.x) {
-        ulonglong2 e = slots[k];
-        if ((e.x == 0ull && e.y == 0ull) || (uint32_t)e.y != DS_MIXED) continue;
+        const ulonglong2 e = slots[k];
+        if (!ds_live(e, ep) || ds_dec((uint32_t)e.y) != DS_MIXED) continue;
         const unsigned long long j = atomicAdd(cursor, 1ull);
-        if (out && j < out_cap) out[j] = e;
+        if (out && j < out_cap) out[j] = make_ulonglong2(e.x, (e.y & 0xFFFFFFFF00000000ull) | DS_MIXED);
     }
 }
+// MIXED ids of all ranks (wire format; zero entries are padding of the all-gather): mark them here - an id this rank does not own is
+// inserted as MIXED so that the keep-mask lookup of this rank's reads with that id finds it
 __global__ void __launch_bounds__(256) k_ds_apply_mixed(const ulonglong2* __restrict__ in, uint64_t n, ulonglong2* slots, uint32_t shift,
-                                                        uint64_t mask) {
+                                                        uint64_t mask, uint32_t ep, uint32_t* scratch_flags) {
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
         const ulonglong2 e = in[k];
-        if (e.x == 0ull && e.y == 0ull) continue;  // padding of the all-gather
-        IdHash h;
-        h.lo = e.x;
-        h.hi = (uint32_t)(e.y >> 32);
-        uint64_t i = ds_home(h, shift);
-        for (;;) {
-            ulonglong2 cur = ld128(slots + i);
-            if (cur.x == 0ull && cur.y == 0ull) {
-                // not in this rank's set (ids owned by another rank are not kept here): insert it as MIXED so that
-                // the keep-mask lookup of this rank's reads with that id finds it
-                const ulonglong2 mixed = make_ulonglong2(e.x, (e.y & 0xFFFFFFFF00000000ull) | DS_MIXED);
-                cur = atomic_cas128(slots + i, make_ulonglong2(0ull, 0ull), mixed);
-                if (cur.x == 0ull && cur.y == 0ull) break;
-            }
-            if (cur.x == e.x && (cur.y >> 32) == (e.y >> 32)) {
-                for (;;) {
-                    if ((uint32_t)cur.y == DS_MIXED) break;
-                    const ulonglong2 want = make_ulonglong2(cur.x, (cur.y & 0xFFFFFFFF00000000ull) | DS_MIXED);
-                    const ulonglong2 prev = atomic_cas128(slots + i, cur, want);
-                    if (prev.x == cur.x && prev.y == cur.y) break;
-                    cur = prev;
-                }
-                break;
-            }
-            i = (i + 1) & mask;
-        }
+        if (e.x == 0ull && e.y == 0ull) continue;
+        ds_upsert(slots, shift, mask, ep, e.x, (uint32_t)(e.y >> 32), DS_MIXED, scratch_flags, 0x1000000000000000ull, false);
     }
 }
 
@@ -1426,7 +1396,7 @@ __global__ void __launch_bounds__(SHORT_THREADS, PTX_SHORT_MINB) k_ingest_s(cons
 //       record-table entry
 // Lines the word-wide path declines (fast_cols) or whose walk has a 10+ digit id go through the exact byte parser.
 // =====================================================================================
-constexpr uint32_t LONG_WPT = (LONG_TILE_MAX + OVER) / 32u / LONG_THREADS + 1u;  // bitmap words a thread of k_ingest_l takes
+constexpr uint32_t LONG_WPT = (MAX_TILE + OVER) / 32u / LONG_THREADS + 1u;  // bitmap words a thread of k_ingest_l takes
 
 __global__ void __launch_bounds__(LONG_THREADS, PTX_LONG_MINB) k_ingest_l(const IngestArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1903,7 +1873,7 @@ __global__ void __launch_bounds__(256, PTX_APPLY_MINB) k_apply(const IngestArgs 
     if (labelled && (MODE & (MODE_CLASSIFY | MODE_KEEPMASK | MODE_REBOX))) h.lo = __ldcs(a.hash_lo + e);
     if (MODE & (MODE_CLASSIFY | MODE_REBOX)) {
         if (a.box_ptr == nullptr) {
-            if ((MODE & MODE_CLASSIFY) && labelled) ds_insert(a.ds, a.ds_shift, a.ds_mask, h, eligible, label, a.flags, a.pol_ds, a.ds_cas_first != 0u);
+            if ((MODE & MODE_CLASSIFY) && labelled) ds_insert(a.ds, a.ds_shift, a.ds_mask, a.ds_epoch, h, eligible, label, a.flags, a.pol_ds);
         } else {
             // multi-GPU: a read id is kept only by the rank that owns its hash.  Own ids go into the local set; the
             // others are appended to the owner's outbox as {hash, state} (one atomicAdd per distinct owner per warp)
@@ -1911,7 +1881,7 @@ __global__ void __launch_bounds__(256, PTX_APPLY_MINB) k_apply(const IngestArgs 
             const ulonglong2 ent = make_ulonglong2(h.lo, ((uint64_t)h.hi << 32) | (eligible ? label : DS_NONE));
             const uint32_t owner = labelled ? ds_owner(ent, a.n_ranks) : 0xFFFFFFFFu;
             const bool mine = labelled && owner == a.rank;
-            if ((MODE & MODE_CLASSIFY) && mine) ds_insert(a.ds, a.ds_shift, a.ds_mask, h, eligible, label, a.flags, a.pol_ds, a.ds_cas_first != 0u);
+            if ((MODE & MODE_CLASSIFY) && mine) ds_insert(a.ds, a.ds_shift, a.ds_mask, a.ds_epoch, h, eligible, label, a.flags, a.pol_ds);
             const uint32_t dest = (labelled && !mine) ? owner : 0xFFFFFFFFu;
             if (a.n_ranks <= BOX_STAGE_RANKS) {
                 block_append(dest, ent, a.n_ranks, a.out_cursor, a.box_cap, [&](uint32_t d) { return a.box_ptr[d]; },
@@ -1938,7 +1908,7 @@ __global__ void __launch_bounds__(256, PTX_APPLY_MINB) k_apply(const IngestArgs 
         if (eligible) {
             nb = R.node_base[label];
             keep = nb >= 0;
-            if ((MODE & MODE_KEEPMASK) && keep) keep = ds_lookup(a.ds, a.ds_shift, a.ds_mask, h, a.pol_ds) != DS_MIXED;  // :415-416
+            if ((MODE & MODE_KEEPMASK) && keep) keep = ds_lookup(a.ds, a.ds_shift, a.ds_mask, a.ds_epoch, h, a.pol_ds) != DS_MIXED;  // :415-416
         }
         const uint32_t cmask = __ballot_sync(0xffffffffu, keep);
         if (keep) {
@@ -2974,25 +2944,26 @@ void launch_scatter_sorted(const uint32_t* key, const unsigned long long* val, u
     k_add_runs<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(rkey, rsum, nrun, bases);
     for (int i = 0; i < 3; ++i) PTX_LAUNCHED();
 }
-void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2* new_slots, uint32_t new_shift, uint64_t new_mask,
+void launch_ds_rehash(const ulonglong2* old_slots, uint64_t old_cap, ulonglong2* new_slots, uint32_t new_shift, uint64_t new_mask, uint32_t ep,
                       cudaStream_t st) {
-    k_ds_rehash<<<grid_for(old_cap, 256), 256, 0, st>>>(old_slots, old_cap, new_slots, new_shift, new_mask);
+    k_ds_rehash<<<grid_for(old_cap, 256), 256, 0, st>>>(old_slots, old_cap, new_slots, new_shift, new_mask, ep);
     PTX_LAUNCHED();
 }
 void launch_ds_merge_boxes(const ulonglong2* inbox, const unsigned long long* off, const unsigned long long* cnt, uint32_t n_boxes, uint64_t max_cnt,
-                           ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t* flags, cudaStream_t st) {
+                           ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t ep, uint32_t* flags, cudaStream_t st) {
     if (n_boxes == 0 || max_cnt == 0) return;
     dim3 grid(grid_for(max_cnt, 256, 148u * 8u), n_boxes);
-    k_ds_merge_boxes<<<grid, 256, 0, st>>>(inbox, off, cnt, slots, shift, mask, flags);
+    k_ds_merge_boxes<<<grid, 256, 0, st>>>(inbox, off, cnt, slots, shift, mask, ep, flags);
     PTX_LAUNCHED();
 }
-void launch_ds_collect_mixed(const ulonglong2* slots, uint64_t cap, unsigned long long* cursor, ulonglong2* out, uint64_t out_cap, cudaStream_t st) {
-    k_ds_collect_mixed<<<grid_for(cap, 256), 256, 0, st>>>(slots, cap, cursor, out, out_cap);
+void launch_ds_collect_mixed(const ulonglong2* slots, uint64_t cap, uint32_t ep, unsigned long long* cursor, ulonglong2* out, uint64_t out_cap, cudaStream_t st) {
+    k_ds_collect_mixed<<<grid_for(cap, 256), 256, 0, st>>>(slots, cap, ep, cursor, out, out_cap);
     PTX_LAUNCHED();
 }
-void launch_ds_apply_mixed(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, cudaStream_t st) {
+void launch_ds_apply_mixed(const ulonglong2* in, uint64_t n, ulonglong2* slots, uint32_t shift, uint64_t mask, uint32_t ep, uint32_t* scratch_flags,
+                           cudaStream_t st) {
     if (n == 0) return;
-    k_ds_apply_mixed<<<grid_for(n, 256), 256, 0, st>>>(in, n, slots, shift, mask);
+    k_ds_apply_mixed<<<grid_for(n, 256), 256, 0, st>>>(in, n, slots, shift, mask, ep, scratch_flags);
     PTX_LAUNCHED();
 }
 void launch_flt_count_nl(const uint8_t* text, uint64_t n, uint32_t n_micro, uint32_t* cnt, cudaStream_t st) {

@@ -605,3 +605,34 @@ def test_gpu_text_of_resolved_chunks_is_released_and_reused():
     ctx.finalize()
     from gpu_common import assert_gpu_matches_oracle
     assert_gpu_matches_oracle(ctx, o, graphs)
+
+
+def test_gpu_id_set_epochs_wrap_around():
+    """The read-id set is not cleared between passes: its slots carry the epoch of the pass that wrote them (1..255) and a new pass
+    only increments the epoch; the table is cleared for real when the epoch wraps.  270 passes over inputs whose duplicated ids form
+    mixed-species groups (profile.rs:406-437) - alternating between two inputs, so that a stale slot of the other input mistaken for
+    a live one would change the result - must each equal the oracle, before, at and after the wrap."""
+    from gpu_common import assert_gpu_matches_oracle
+    api = _api()
+    ds = synth.Dataset(43, [6000, 2500, 900], [4, 2, 1])
+    graphs = dataset_graphs(ds)
+    gafs = [ds.gaf(21, 0, 6000, NASTY_DUP), ds.gaf(22, 3000, 9000, NASTY_DUP)]
+    oracles = [run_cpu_oracle(ds.ranges(), graphs, g) for g in gafs]
+    ctx = api.PantaxGpu(0)
+    ctx.set_ranges(ds.ranges())
+    for s, g in enumerate(graphs):
+        ctx.upload_graph(s, g[0], g[1])
+    ctx.commit_graphs()
+    checked = 0
+    for it in range(270):
+        k = it & 1
+        ctx.ingest_gaf(gafs[k], is_last=True)
+        ctx.finalize()
+        if it < 4 or 250 <= it <= 260 or it >= 266:
+            assert_gpu_matches_oracle(ctx, oracles[k], graphs)
+            checked += 1
+        else:
+            assert ctx.num_records == oracles[k].n_records
+        ctx.reset()
+    assert checked >= 18
+    ctx.close()
