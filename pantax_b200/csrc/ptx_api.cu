@@ -10,6 +10,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <functional>
 #include <map>
 #include <vector>
 
@@ -897,7 +898,7 @@ int return_mixed_ids(ptx_ctx* ctx, cudaStream_t st) {
 // synchronisation), then - on the side stream `xs`, while the main stream runs the coverage pass - the new part
 // of every box travels with grouped ncclSend/ncclRecv, the owner merges what it received into its id set and
 // the repeat/mixed flags are max-reduced.  ptx_finalize joins on ev_x1.
-int exchange_begin(ptx_ctx* ctx) {
+int exchange_begin(ptx_ctx* ctx, const std::function<int()>& overlap) {
     const int P = ctx->n_ranks;
     int rc;
     unsigned long long* d_cur = ctx->out_cursor;           // [P] cursors + [P] overflow marker (set below)
@@ -909,7 +910,11 @@ int exchange_begin(ptx_ctx* ctx) {
         launch_count_labelled(ctx->d_hist, (uint32_t)ctx->sp.size(), d_cur + P, ctx->st);
         if ((rc = nccl_check(ctx, g_nccl.AllGather(d_cur, d_all, P + 1, ncclUint64, ctx->comm, ctx->st), "ncclAllGather(box fills)"))) return rc;
         CU(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
-        CU(cudaStreamSynchronize(ctx->st));
+        CU(cudaEventRecord(ctx->ev_x0, ctx->st));
+        // the coverage pass does not depend on the exchange: it is queued before the host waits for the fills, so the GPU goes from
+        // the all-gather straight into it while the host reads the fills and issues the merge on the side stream
+        if (attempt == 0 && overlap && (rc = overlap())) return rc;
+        CU(cudaEventSynchronize(ctx->ev_x0));
         // all[q*(P+1) + r] = entries rank q has appended for rank r so far, all[q*(P+1) + P] != 0 if a box of rank q was
         // full and entries were dropped.  Every rank sees the same matrix, so all of them take the same branch.
         unsigned long long worst = 0;
@@ -973,10 +978,11 @@ int exchange_begin(ptx_ctx* ctx) {
         par[(size_t)P + nb] = recv_n[q];
         ++nb;
     }
-    CU(cudaMemcpyAsync(d_par, par.data(), par.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->st));
-    CU(cudaEventRecord(ctx->ev_x0, ctx->st));
+    // the side stream continues behind the fills all-gather (= behind this rank's k_apply launches and, through the collective, behind
+    // the other ranks' stores into this rank's inbox), not behind the coverage pass queued after it
     CU(cudaStreamWaitEvent(ctx->xs, ctx->ev_x0, 0));
     cudaStream_t xs = ctx->xs;
+    CU(cudaMemcpyAsync(d_par, par.data(), par.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, xs));
     Trace trx(xs);
     if (!ctx->p2p) {
         g_nccl.GroupStart();
@@ -1752,11 +1758,38 @@ int ptx_finalize(ptx_ctx* ctx) {
     ev_begin(ctx, ctx->ev_final);
     Trace tr(ctx->st);
     bool mixed = false;
+    auto cover_pending = [&](bool keepmask) -> int {
+        for (auto& ch : ctx->chunks) {
+            if (!ch.ingested || ch.covered || ch.n_tiles == 0) continue;
+            uint32_t n_nodes = 0;
+            if (pick_scatter_variant(ctx) == 3) {  // (node, bases) pairs beside the CSR walks, sorted and reduced per chunk
+                CU(cudaMemcpyAsync(&n_nodes, reinterpret_cast<uint32_t*>(ch.cursors) + 1, sizeof n_nodes, cudaMemcpyDeviceToHost, ctx->st));
+                CU(cudaStreamSynchronize(ctx->st));
+                const size_t tb = scatter_sorted_tmp_bytes(n_nodes);
+                if (ctx->pair_cap < (int64_t)n_nodes || ctx->pair_tmp_cap < tb) {
+                    dfree(ctx->d_pair_key); dfree(ctx->d_pair_val); dfree(ctx->d_pair_tmp);
+                    ctx->pair_cap = (int64_t)n_nodes + n_nodes / 8 + 1024;
+                    ctx->pair_tmp_cap = scatter_sorted_tmp_bytes((uint64_t)ctx->pair_cap);
+                    CU(cudaMalloc((void**)&ctx->d_pair_key, (size_t)ctx->pair_cap * sizeof(uint32_t)));
+                    CU(cudaMalloc((void**)&ctx->d_pair_val, (size_t)ctx->pair_cap * sizeof(unsigned long long)));
+                    CU(cudaMalloc((void**)&ctx->d_pair_tmp, ctx->pair_tmp_cap));
+                }
+                CU(cudaMemsetAsync(ctx->d_pair_key, 0xFF, (size_t)n_nodes * sizeof(uint32_t), ctx->st));  // slots of records that are not covered
+            }
+            IngestArgs a = make_args(ctx, ch);
+            launch_apply(a, (uint32_t)ch.n_slots, MODE_COVER | (keepmask ? MODE_KEEPMASK : 0), ctx->st);  // from the record table: no text is re-read
+            if (a.scatter_var == 3) launch_scatter_sorted(ctx->d_pair_key, ctx->d_pair_val, n_nodes, ctx->g.bases, ctx->d_pair_tmp, ctx->pair_tmp_cap, ctx->st);
+            ch.covered = true;
+        }
+        return PTX_OK;
+    };
     if (ctx->comm) {
         // id groups may span ranks: the boxes k_apply filled travel on the side stream while the coverage runs here
         int rc = xchg_ensure(ctx, std::max<int64_t>(ctx->ds_records, ctx->reserve_records));
         if (rc) return rc;
-        if ((rc = exchange_begin(ctx))) return rc;
+        if (ctx->graphs_committed && g.N > 0 && ctx->cov_reduced) return fail(ctx, PTX_E_STATE, "multi-GPU: coverage already reduced");
+        rc = exchange_begin(ctx, [&]() -> int { return (ctx->graphs_committed && g.N > 0) ? cover_pending(false) : PTX_OK; });
+        if (rc) return rc;
         tr.mark("final exchange issued");
     } else {
         CU(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof ctx->h_flags, cudaMemcpyDeviceToHost, ctx->st));
@@ -1765,31 +1798,6 @@ int ptx_finalize(ptx_ctx* ctx) {
         tr.mark("final flags");
     }
     if (ctx->graphs_committed && g.N > 0) {
-        auto cover_pending = [&](bool keepmask) -> int {
-            for (auto& ch : ctx->chunks) {
-                if (!ch.ingested || ch.covered || ch.n_tiles == 0) continue;
-                uint32_t n_nodes = 0;
-                if (pick_scatter_variant(ctx) == 3) {  // (node, bases) pairs beside the CSR walks, sorted and reduced per chunk
-                    CU(cudaMemcpyAsync(&n_nodes, reinterpret_cast<uint32_t*>(ch.cursors) + 1, sizeof n_nodes, cudaMemcpyDeviceToHost, ctx->st));
-                    CU(cudaStreamSynchronize(ctx->st));
-                    const size_t tb = scatter_sorted_tmp_bytes(n_nodes);
-                    if (ctx->pair_cap < (int64_t)n_nodes || ctx->pair_tmp_cap < tb) {
-                        dfree(ctx->d_pair_key); dfree(ctx->d_pair_val); dfree(ctx->d_pair_tmp);
-                        ctx->pair_cap = (int64_t)n_nodes + n_nodes / 8 + 1024;
-                        ctx->pair_tmp_cap = scatter_sorted_tmp_bytes((uint64_t)ctx->pair_cap);
-                        CU(cudaMalloc((void**)&ctx->d_pair_key, (size_t)ctx->pair_cap * sizeof(uint32_t)));
-                        CU(cudaMalloc((void**)&ctx->d_pair_val, (size_t)ctx->pair_cap * sizeof(unsigned long long)));
-                        CU(cudaMalloc((void**)&ctx->d_pair_tmp, ctx->pair_tmp_cap));
-                    }
-                    CU(cudaMemsetAsync(ctx->d_pair_key, 0xFF, (size_t)n_nodes * sizeof(uint32_t), ctx->st));  // slots of records that are not covered
-                }
-                IngestArgs a = make_args(ctx, ch);
-                launch_apply(a, (uint32_t)ch.n_slots, MODE_COVER | (keepmask ? MODE_KEEPMASK : 0), ctx->st);  // from the record table: no text is re-read
-                if (a.scatter_var == 3) launch_scatter_sorted(ctx->d_pair_key, ctx->d_pair_val, n_nodes, ctx->g.bases, ctx->d_pair_tmp, ctx->pair_tmp_cap, ctx->st);
-                ch.covered = true;
-            }
-            return PTX_OK;
-        };
         auto start_over = [&]() -> int {
             // profile.rs:406-437: some id group spans species -> its reads must not contribute.  The optimistic
             // pass counted them: zero the accumulators and replay the record table with the keep mask.
