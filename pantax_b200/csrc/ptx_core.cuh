@@ -98,6 +98,13 @@ struct NodeInfo {
     uint64_t bit_off;  // first bit of the node in the packed covered-base bitmap
 };
 constexpr uint32_t NI_FULL = 1u, NI_TRIO_MID = 2u;
+// bits 8..31 of the flags: a 24-bit signature of the (lo, hi) neighbour pairs of the unique trios this node is the middle of.  A read
+// window whose pair's bit is not set cannot be a unique trio: the probe of the trio table (a dependent gather, 13 % of k_apply's
+// stall samples when every NI_TRIO_MID node probed) is skipped - 15 % of the nodes carry NI_TRIO_MID, 0.4 % of the windows hit.
+PTX_HD uint32_t trio_sig_bit(uint32_t lo, uint32_t hi) {
+    const uint32_t h = ((lo * 0x9E3779B1u) ^ (hi * 0x85EBCA77u)) * 0xC2B2AE35u;
+    return 1u << (8u + (uint32_t)(((uint64_t)h * 24u) >> 32));
+}
 
 struct RangesView {
     const int64_t* start;      // [S] 1-based inclusive, file order (species_range.txt)
@@ -456,8 +463,8 @@ PTX_HD void parse_tail(const uint8_t* b, uint32_t& p, int st, RecParse& r, uint3
 // Sink concept:
 //   NodeInfo info(uint32_t g);  void add_bases(uint32_t g, int64_t v);
 //   void set_bits(uint32_t g, const NodeInfo& ni, int64_t lo, int64_t hi);   0 <= lo < hi <= ni.len
-//   void trio(uint32_t a, uint32_t b, uint32_t c, int64_t s);   global node indices in read order; only called
-//                                                               when b carries NI_TRIO_MID
+//   void trio(uint32_t a, uint32_t b, uint32_t c, int64_t s, uint32_t b_flags);   global node indices in read order; only called
+//                                                               when b carries NI_TRIO_MID (b_flags: its flags word, for trio_sig_bit)
 //   void error_start_gt_len(uint32_t label);
 // `mask`: lanes of the warp that call this together.  The walk is processed in three phases so that the lanes
 // execute the same code at the same time: the first node of every read, then the middle nodes in lock-step,
@@ -498,7 +505,7 @@ PTX_HD void cover_record(const uint8_t* b, const RecParse& r, uint32_t label, in
     bool ok = W >= 1;
     uint32_t gb = 0, ga = 0;
     int64_t rlb = 0, rla = 0, seen = 0;
-    bool mid_b = false;  // gb is the middle node of some unique trio
+    uint32_t fl_b = 0;  // flags of gb: NI_TRIO_MID = it is the middle node of some unique trio
     if (ok) {
         int64_t m;
         if (stashed) m = (int64_t)stash[0];
@@ -522,7 +529,7 @@ PTX_HD void cover_record(const uint8_t* b, const RecParse& r, uint32_t label, in
             prev_m = m;
             gb = g;
             rlb = aln;
-            mid_b = (ni.flags & NI_TRIO_MID) != 0;
+            fl_b = ni.flags;
         }
     }
     PTX_RECONVERGE(mask);
@@ -542,10 +549,10 @@ PTX_HD void cover_record(const uint8_t* b, const RecParse& r, uint32_t label, in
             seen += ln;  // :878
             int64_t rl;
             if (first_occurrence(i, m, ln, ln, rl)) sink.add_bases(g, ln);     // :879-882
-            if (i >= 2 && mid_b) sink.trio(ga, gb, g, rla + rlb + rl);         // :890-906
+            if (i >= 2 && (fl_b & NI_TRIO_MID)) sink.trio(ga, gb, g, rla + rlb + rl, fl_b);  // :890-906
             ga = gb; rla = rlb;
             gb = g;  rlb = rl;
-            mid_b = (ni.flags & NI_TRIO_MID) != 0;
+            fl_b = ni.flags;
         }
         PTX_RECONVERGE(mask);
     }
@@ -564,7 +571,7 @@ PTX_HD void cover_record(const uint8_t* b, const RecParse& r, uint32_t label, in
         if (hi > 0) sink.set_bits(g, ni, 0, hi);
         int64_t rl;
         if (first_occurrence(i, m, ln, aln, rl)) sink.add_bases(g, aln);
-        if (W >= 3 && mid_b) sink.trio(ga, gb, g, rla + rlb + rl);
+        if (W >= 3 && (fl_b & NI_TRIO_MID)) sink.trio(ga, gb, g, rla + rlb + rl, fl_b);
     }
     PTX_RECONVERGE(mask);
 }

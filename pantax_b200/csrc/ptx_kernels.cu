@@ -334,9 +334,10 @@ struct DevSink {
             red_or32_hint(a.bits + w1, m1, a.pol_keep);
         }
     }
-    __device__ __forceinline__ void trio(uint32_t x, uint32_t y, uint32_t z, int64_t s) {
+    __device__ __forceinline__ void trio(uint32_t x, uint32_t y, uint32_t z, int64_t s, uint32_t y_flags) {
         if (a.tt == nullptr) return;
         const uint32_t lo = x < z ? x : z, hi = x < z ? z : x;  // profile.rs:672-678 / :902-904
+        if (!(y_flags & trio_sig_bit(lo, hi))) return;           // no unique trio around y has these neighbours
         uint32_t i = trio_hash(lo, y, hi) & a.tt_mask;
         for (;;) {
             uint4 e = __ldg(a.tt + i);
@@ -2206,7 +2207,7 @@ __global__ void __launch_bounds__(256) k_trio_emit(const uint32_t* __restrict__ 
         trio_key[3 * t + 2] = hi;
         trio_len[t] = (int64_t)len[lo] + (int64_t)len[mid] + (int64_t)len[hi];  // profile.rs:712
         trio_owner[t] = (uint32_t)h;
-        atomicOr(&ninfo[mid].y, NI_TRIO_MID);
+        atomicOr(&ninfo[mid].y, NI_TRIO_MID | trio_sig_bit(lo, hi));  // (lo < hi: window_at returns the canonical key)
         // unique keys: plain claim of an empty slot, then publish idx
         uint32_t i = trio_hash(lo, mid, hi) & tt_mask;
         const ulonglong2 empty = make_ulonglong2(0xFFFFFFFFFFFFFFFFull, 0xFFFFFFFFFFFFFFFFull);

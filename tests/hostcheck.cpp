@@ -28,7 +28,7 @@ struct HostSink {
     void set_bits(uint32_t, const NodeInfo& ni, int64_t lo, int64_t hi) {
         for (int64_t j = lo; j < hi; ++j) bytes[ni.bit_off + j] = 1;
     }
-    void trio(uint32_t x, uint32_t y, uint32_t z, int64_t s) {
+    void trio(uint32_t x, uint32_t y, uint32_t z, int64_t s, uint32_t /*y_flags*/) {
         uint32_t lo = x < z ? x : z, hi = x < z ? z : x;
         auto it = tmap->find(std::make_tuple(lo, y, hi));
         if (it != tmap->end()) trio_bases[it->second] += s;
