@@ -87,7 +87,7 @@ def _worker_idgroups(rank, world, port, out_dir):
     its own reads with the keep mask and the accumulators are summed."""
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from common import NASTY_DUP, opy, py_graph
-    from pantax_b200.shard import IdOwnerSet
+    from id_owner_model import IdOwnerSet
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
