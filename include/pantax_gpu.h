@@ -165,6 +165,15 @@ int ptx_trio_depth(ptx_ctx* ctx, int species, double* depth);      /* trio_node_
  * len[T] = len[a]+len[b]+len[c], owner[T] = hap index.  Any pointer may be NULL. */
 int ptx_trio_table(ptx_ctx* ctx, int species, uint64_t* keys3, int64_t* len, uint32_t* owner);
 
+/* The REFERENCE's numbering of the same unique trios: order[i] = row of ptx_trio_table that profile.rs:705-716 numbers i, i.e. the
+ * iteration order of the FxHashSet of profile.rs:659-685 (fxhash 0.2.1 over the three usize fields; the standard library's
+ * hashbrown table, x86-64 group width 16; one `extend` per haplotype in name order) restricted to the trios that occur once.
+ * Visible only in the f64 summation order of zscore_filter / frequencies_mean (profile.rs:1037-1041, 1146): a caller that wants the
+ * reference's bits visits a haplotype's trio abundances in this order.  Host-only, no ctx: path_off[n_paths + 1] / path_nodes as given
+ * to ptx_upload_graph, keys3[n_trios][3] as returned by ptx_trio_table.  PTX_E_INVALID when the two do not describe the same trios. */
+int ptx_trio_ref_order(const uint64_t* path_off, const uint64_t* path_nodes, int64_t n_paths, const uint64_t* keys3, int64_t n_trios,
+                       uint64_t* order);
+
 /* Per path (name order): sum of node_base_cov and of nodes_len over the DISTINCT nodes
  * of the path - the two products of profile.rs:2714-2724 as exact integers. */
 int ptx_path_sums(ptx_ctx* ctx, int species, int64_t* sum_cov, int64_t* sum_len);

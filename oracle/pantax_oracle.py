@@ -421,12 +421,20 @@ def get_node_abundances(
 # --------------------------------------------------------------------------
 # a8  strain statistics                                  profile.rs:1028-1227
 # --------------------------------------------------------------------------
+def seq_sum(xs) -> float:
+    """`iter().sum::<f64>()`: one addition per element in order (builtin sum() is compensated since Python 3.12)."""
+    s = 0.0
+    for x in xs:
+        s += x
+    return s
+
+
 def zscore_filter(data: Sequence[float], threshold: float = 3.0) -> List[float]:
     """profile.rs:1028-1051 (population sigma; sigma==0 -> empty)."""
     if not data:
         return []
-    mean = sum(data) / len(data)
-    std = math.sqrt(sum((x - mean) ** 2 for x in data) / len(data))
+    mean = seq_sum(data) / len(data)
+    std = math.sqrt(seq_sum((x - mean) * (x - mean) for x in data) / len(data))
     if std == 0.0:
         return []
     return [x for x in data if abs((x - mean) / std) < threshold]
@@ -469,7 +477,7 @@ def first_filter_paths(
             frac = len(nzf) / len(idxs)  # :1135
             metrics[h]["unique_trio_nodes_fraction"] = round_half_away(frac * 100.0) / 100.0
             zf = zscore_filter(nzf, 3.0)
-            fmean = (sum(zf) / len(zf)) if zf else 0.0
+            fmean = (seq_sum(zf) / len(zf)) if zf else 0.0
             if shift:  # :1140-1165
                 if fmean >= 1.0:
                     thr = min(fr + (0.8 - fr) * fmean / 100.0, 0.8)
@@ -487,14 +495,14 @@ def first_filter_paths(
         if all(v == vals[0] for v in vals[1:]):
             same_path = True
             nzf = [x for x in node_ab_opt if x > 0.0]
-            fmean = (sum(nzf) / len(nzf)) if nzf else 0.0
+            fmean = (seq_sum(nzf) / len(nzf)) if nzf else 0.0
             metrics[0]["frequencies_mean"] = round_half_away(fmean * 100.0) / 100.0
             possible.append(0)
         else:
             possible = list(range(H))
     else:  # H == 1  (:1211-1225)
         nzf = [x for x in node_ab_opt if x > 0.0]
-        fmean = (sum(nzf) / len(nzf)) if nzf else 0.0
+        fmean = (seq_sum(nzf) / len(nzf)) if nzf else 0.0
         metrics[0]["frequencies_mean"] = round_half_away(fmean * 100.0) / 100.0
         possible.append(0)
     return possible, metrics, same_path

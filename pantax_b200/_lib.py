@@ -62,6 +62,7 @@ SIGNATURES = {
     "ptx_trio_bases": (i32, [vp, i32, P(i64)]),
     "ptx_trio_depth": (i32, [vp, i32, P(C.c_double)]),
     "ptx_trio_table": (i32, [vp, i32, P(u64), P(i64), P(u32)]),
+    "ptx_trio_ref_order": (i32, [P(u64), P(u64), i64, P(u64), i64, P(u64)]),
     "ptx_path_sums": (i32, [vp, i32, P(i64), P(i64)]),
     "ptx_hap_trio_counts": (i32, [vp, i32, P(i64), P(i64)]),
     "ptx_filter_gaf": (i32, [vp, vp, C.c_size_t, P(u64), i64, P(i64)]),

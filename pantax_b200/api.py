@@ -7,6 +7,7 @@ Names follow the reference (paths relative to /root/reference/pantax/src):
   get_node_abundances     profile.rs:743-1026    (node_abundance_vec, trio_node_abundance_vec, node_base_cov)
   path_cov_ratio          profile.rs:2705-2729   covered fraction per path
   hap_trio_counts         profile.rs:1112-1135   U_h, nz_h
+  trio_ref_order          profile.rs:659-716     the reference's numbering (FxHashSet order) of the unique trio table
 
 Everything numeric is computed by libpantax_gpu.so on the GPU; this file only moves
 arrays across ctypes.
@@ -381,6 +382,26 @@ def species_counts(ctx: PantaxGpu) -> np.ndarray:
 def trio_nodes_info(ctx: PantaxGpu, species: int):
     """profile.rs:658-740: (unique trio keys[T,3] canonical local ids, unique_lengths[T], owner hap[T])."""
     return ctx.trio_table(species)
+
+
+def trio_ref_order(paths: Sequence[np.ndarray], keys3: np.ndarray) -> np.ndarray:
+    """order[i] = row of `keys3` (ptx_trio_table) that the reference numbers i: the iteration order of the FxHashSet of
+    profile.rs:659-685 restricted to the unique trios (:705-716).  Host-only (ptx_trio_ref_order); `paths` = local node ids per
+    hap in name order.  The one place the order shows is the f64 summation order of frequencies_mean (profile.rs:1037-1146)."""
+    L = load_library()
+    off = np.zeros(len(paths) + 1, dtype=np.uint64)
+    for h, p in enumerate(paths):
+        off[h + 1] = off[h] + len(p)
+    nodes = np.concatenate([np.asarray(p, dtype=np.uint64) for p in paths]) if len(paths) and off[-1] else np.zeros(1, dtype=np.uint64)
+    nodes = np.ascontiguousarray(nodes, dtype=np.uint64)
+    k = np.ascontiguousarray(np.asarray(keys3, dtype=np.uint64).reshape(-1, 3))
+    T = k.shape[0]
+    order = np.zeros(max(T, 1), dtype=np.uint64)
+    kk = k if T else np.zeros((1, 3), dtype=np.uint64)
+    rc = L.ptx_trio_ref_order(_p(off, C.c_uint64), _p(nodes, C.c_uint64), len(paths), _p(kk, C.c_uint64), T, _p(order, C.c_uint64))
+    if rc != 0:
+        raise PantaxGpuError(rc, "ptx_trio_ref_order: the paths and the trio table do not describe the same unique trios")
+    return order[:T].astype(np.int64)
 
 
 def get_node_abundances(ctx: PantaxGpu, species: int):

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpantax_gpu.so")
 SOURCES = ["ptx_kernels.cu", "ptx_api.cu"]
-HEADERS = ["ptx_core.cuh", "ptx_fast.cuh", "ptx_internal.h", os.path.join("..", "..", "include", "pantax_gpu.h")]
+HEADERS = ["ptx_core.cuh", "ptx_fast.cuh", "ptx_internal.h", "ptx_fxorder.h", os.path.join("..", "..", "include", "pantax_gpu.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -16,6 +16,7 @@
 
 #include "../../include/pantax_gpu.h"
 #include "ptx_internal.h"
+#include "ptx_fxorder.h"
 
 using namespace ptx;
 
@@ -2220,6 +2221,18 @@ int ptx_trio_table(ptx_ctx* ctx, int s, uint64_t* keys3, int64_t* len, uint32_t*
         for (int64_t i = 0; i < T; ++i) owner[i] -= (uint32_t)sp.hap_base;
     }
     return PTX_OK;
+}
+
+int ptx_trio_ref_order(const uint64_t* path_off, const uint64_t* path_nodes, int64_t n_paths, const uint64_t* keys3, int64_t n_trios,
+                       uint64_t* order) {
+    if (n_paths < 0 || n_trios < 0 || (n_paths > 0 && (!path_off || (path_off[n_paths] > 0 && !path_nodes))) ||
+        (n_trios > 0 && (!keys3 || !order)))
+        return PTX_E_INVALID;
+    try {
+        return ptx_fx::trio_ref_order(path_off, path_nodes, n_paths, keys3, n_trios, order) == 0 ? PTX_OK : PTX_E_INVALID;
+    } catch (const std::bad_alloc&) {
+        return PTX_E_NOMEM;
+    }
 }
 
 int ptx_path_sums(ptx_ctx* ctx, int s, int64_t* sum_cov, int64_t* sum_len) {

@@ -669,8 +669,23 @@ int main(int argc, char** argv) {
         FILE* f = fopen((o.wd + "/strain_inputs/" + ranges[s].taxid + ".paths.tsv").c_str(), "wb");
         fprintf(f, "hap_id\tunique_trios\tunique_trios_covered\tunique_trio_fraction\tuniq_trio_cov_mean\tpath_base_cov\tsum_cov\tsum_len\tpossible\n");
         std::vector<std::vector<double>> per_hap((size_t)H);
-        for (int64_t t = 0; t < T; ++t)
-            if (tdepth[(size_t)t] > 0.0) per_hap[owner[(size_t)t]].push_back(tdepth[(size_t)t]);  // trio index order within a hap
+        if (H > 1 && T > 0) {
+            // The f64 sums of zscore_filter / frequencies_mean run over a hap's trios in the REFERENCE's trio numbering
+            // (FxHashSet iteration order, profile.rs:659-716, 1123-1146) - ptx_trio_ref_order reproduces it on the host.
+            std::vector<uint64_t> poff{0}, pnodes, keys3((size_t)T * 3), order((size_t)T);
+            for (auto& kv : g.paths) {
+                pnodes.insert(pnodes.end(), kv.second.begin(), kv.second.end());
+                poff.push_back((uint64_t)pnodes.size());
+            }
+            if (pnodes.empty()) pnodes.push_back(0);
+            ck(ctx, ptx_trio_table(ctx, s, keys3.data(), nullptr, nullptr), "ptx_trio_table (keys)");
+            if (ptx_trio_ref_order(poff.data(), pnodes.data(), H, keys3.data(), T, order.data()) != PTX_OK)
+                die(std::string("ptx_trio_ref_order: the graph and the trio table disagree for species ") + ranges[s].taxid);
+            for (int64_t i = 0; i < T; ++i) {
+                const size_t t = (size_t)order[(size_t)i];
+                if (tdepth[t] > 0.0) per_hap[owner[t]].push_back(tdepth[t]);
+            }
+        }
         bool all_same = true;
         if (H > 1 && T == 0) {
             auto it0 = g.paths.begin();

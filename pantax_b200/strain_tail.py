@@ -80,13 +80,22 @@ def rust_round(x: float) -> float:
     return math.floor(x + 0.5) if x >= 0 else -math.floor(-x + 0.5)
 
 
+def seq_sum(xs) -> float:
+    """Iterator::sum::<f64>() of the reference: one f64 addition per element, in order.  (Python's builtin sum() is
+    Neumaier-compensated since 3.12 and np.sum is pairwise - neither gives the reference's bits.)"""
+    s = 0.0
+    for x in xs:
+        s += x
+    return s
+
+
 def zscore_filter(data: Sequence[float], threshold: float = 3.0) -> List[float]:
     """profile.rs:1028-1051: population mean / standard deviation; std == 0 -> nothing survives."""
     n = len(data)
     if n == 0:
         return []
-    mean = sum(data) / n
-    var = sum((x - mean) * (x - mean) for x in data) / n
+    mean = seq_sum(data) / n
+    var = seq_sum((x - mean) * (x - mean) for x in data) / n
     std = math.sqrt(var)
     if std == 0.0:
         return []
@@ -94,9 +103,14 @@ def zscore_filter(data: Sequence[float], threshold: float = 3.0) -> List[float]:
 
 
 def first_filter_paths(opt: OptVar, hap_names: Sequence[str], paths: Sequence[np.ndarray], trio_owner: np.ndarray, trio_depth: np.ndarray,
-                       node_depth_opt: np.ndarray, args: ProfilingArgs) -> None:
+                       node_depth_opt: np.ndarray, args: ProfilingArgs, trio_order: Optional[np.ndarray] = None) -> None:
     """profile.rs:1080-1227.  The dense trio x hap matrix of the reference is the `owner` column of ptx_trio_table here
-    (a unique trio belongs to exactly one hap); trios are visited in the library's index order (hap, position)."""
+    (a unique trio belongs to exactly one hap).  `trio_order` (api.trio_ref_order) puts the trios into the reference's own
+    numbering first, so that the f64 sums below add a hap's abundances in the reference's order; without it they are visited
+    in the library's order (hap, position) - same sets, same counts, sums equal up to the rounding of a reordered f64 sum."""
+    if trio_order is not None:
+        trio_owner = np.asarray(trio_owner)[trio_order]
+        trio_depth = np.asarray(trio_depth)[trio_order]
     for i, h in enumerate(hap_names):
         opt.hap_metrics[i].otu = opt.otu
         opt.hap_metrics[i].hap_id = h
@@ -112,7 +126,7 @@ def first_filter_paths(opt: OptVar, hap_names: Sequence[str], paths: Sequence[np
             fraction = len(nz) / len(mine)
             opt.hap_metrics[hap_idx].unique_trio_nodes_fraction = rust_round(fraction * 100.0) / 100.0
             kept = zscore_filter(nz, 3.0)
-            fmean = sum(kept) / len(kept) if kept else 0.0
+            fmean = seq_sum(kept) / len(kept) if kept else 0.0
             if args.shift:
                 if fmean >= 1.0:
                     thr = min(args.unique_trio_nodes_fraction + (0.8 - args.unique_trio_nodes_fraction) * fmean / 100.0, 0.8)
@@ -298,10 +312,11 @@ def optimize_otu(ctx: "api.PantaxGpu", species: int, otu: str, nodes_len: np.nda
                  args: ProfilingArgs) -> List[HapMetrics]:
     """profile.rs:2884-3026 after load_from_zip_graph: every read-dependent number comes from the GPU context."""
     node_depth, trio_depth, _cov = api.get_node_abundances(ctx, species)
-    _keys, _tlen, owner = api.trio_nodes_info(ctx, species)
+    keys, _tlen, owner = api.trio_nodes_info(ctx, species)
     node_depth_opt = np.where(node_depth > args.min_depth, node_depth, 0.0)
     opt = OptVar(otu=otu, hap_metrics=[HapMetrics() for _ in hap_names])
-    first_filter_paths(opt, hap_names, paths, owner, trio_depth, node_depth_opt, args)
+    order = api.trio_ref_order(paths, keys) if len(hap_names) > 1 and len(owner) else None
+    first_filter_paths(opt, hap_names, paths, owner, trio_depth, node_depth_opt, args, trio_order=order)
     if opt.possible_paths_idx:
         ratio = api.path_cov_ratio(ctx, species, paths, nodes_len, f32=True)
         highs_opt(opt, paths, node_depth, ratio, args)

@@ -48,6 +48,7 @@ extern "C" {
     pub fn ptx_trio_bases(ctx: *mut ptx_ctx, species: c_int, bases: *mut i64) -> c_int;
     pub fn ptx_trio_depth(ctx: *mut ptx_ctx, species: c_int, depth: *mut c_double) -> c_int;
     pub fn ptx_trio_table(ctx: *mut ptx_ctx, species: c_int, keys3: *mut u64, len: *mut i64, owner: *mut u32) -> c_int;
+    pub fn ptx_trio_ref_order(path_off: *const u64, path_nodes: *const u64, n_paths: i64, keys3: *const u64, n_trios: i64, order: *mut u64) -> c_int;
     pub fn ptx_path_sums(ctx: *mut ptx_ctx, species: c_int, sum_cov: *mut i64, sum_len: *mut i64) -> c_int;
     pub fn ptx_hap_trio_counts(ctx: *mut ptx_ctx, species: c_int, u: *mut i64, nz: *mut i64) -> c_int;
     pub fn ptx_filter_gaf(ctx: *mut ptx_ctx, bytes: *const u8, n: size_t, out_line_off: *mut u64, cap: i64, n_out: *mut i64) -> c_int;
@@ -172,6 +173,23 @@ impl Gpu {
     }
 }
 impl Drop for Gpu { fn drop(&mut self) { unsafe { ptx_destroy(self.raw) } } }
+
+/// order[i] = row of `keys3` (ptx_trio_table, `n_trios` x 3 canonical local ids) that `trio_nodes_info` numbers i
+/// (profile.rs:659-716: FxHashSet iteration order restricted to the trios that occur once).  Inside the reference crate the
+/// real FxHashSet is at hand and this is not needed; it exists for callers that want the reference's f64 summation
+/// order of `frequencies_mean` (profile.rs:1123-1146) without building that set.  `None`: the paths and the table disagree.
+pub fn trio_ref_order(paths: &std::collections::BTreeMap<String, Vec<usize>>, keys3: &[u64]) -> Option<Vec<usize>> {
+    let mut off = vec![0u64];
+    let mut flat: Vec<u64> = Vec::new();
+    for p in paths.values() { flat.extend(p.iter().map(|&v| v as u64)); off.push(flat.len() as u64); }
+    if flat.is_empty() { flat.push(0); }
+    let t = keys3.len() / 3;
+    let mut order = vec![0u64; t.max(1)];
+    let rc = unsafe { ptx_trio_ref_order(off.as_ptr(), flat.as_ptr(), paths.len() as i64, keys3.as_ptr(), t as i64, order.as_mut_ptr()) };
+    if rc != 0 { return None; }
+    order.truncate(t);
+    Some(order.into_iter().map(|x| x as usize).collect())
+}
 
 /// profile.rs:2714-2729: the reference forms `path_cov_ratio` as `RowDVector<f32>(node_base_cov) * incidence` over
 /// `RowDVector<f32>(node_len) * incidence`; nalgebra evaluates each product as a gemv, i.e. a sequential f32
