@@ -337,6 +337,24 @@ def trio_nodes_info(graph: Graph):
     return trio_map, trio_len, owner
 
 
+def trio_nodes_info_reference_order(graph: Graph):
+    """profile.rs:658-740 with the reference's OWN numbering: unique trios in the iteration order of the
+    FxHashSet of :659-685 (oracle/fx_hashset.py restates fxhash 0.2.1 + std's hashbrown table).  Same return shape as
+    trio_nodes_info; only the index order differs - visible in the f64 sums of first_filter_paths (:1123-1146)."""
+    from . import fx_hashset
+
+    paths = [p for _name, p in graph.sorted_paths()]
+    _all, uniq = fx_hashset.reference_trio_numbering(paths)
+    owner_of: Dict[Tuple[int, int, int], int] = {}
+    for h, path in enumerate(paths):
+        for i in range(len(path) - 2):
+            owner_of[canon(path[i], path[i + 1], path[i + 2])] = h  # unique trios have exactly one owner
+    trio_map = {k: i for i, k in enumerate(uniq)}
+    trio_len = [graph.nodes_len[k[0]] + graph.nodes_len[k[1]] + graph.nodes_len[k[2]] for k in uniq]
+    owner = [owner_of[k] for k in uniq]
+    return trio_map, trio_len, owner
+
+
 # --------------------------------------------------------------------------
 # a7  node coverage                                      profile.rs:743-1026
 # --------------------------------------------------------------------------

@@ -154,3 +154,36 @@ def test_first_filter_sums_in_reference_order():
         assert abs(ma.frequencies_mean - mb.frequencies_mean) <= 1e-12 * max(1.0, abs(mb.frequencies_mean))
         differs += ma.frequencies_mean != mb.frequencies_mean
     assert differs > 0  # the order is visible in the last bits, which is why it is reproduced
+
+
+def test_oracle_in_reference_order_equals_strain_tail_bit_for_bit():
+    """The restatement numbered like the reference (trio_nodes_info_reference_order) and the product's tail fed with
+    ptx_trio_ref_order give the same frequencies_mean to the last bit."""
+    from oracle import pantax_oracle as opy
+
+    rng = random.Random(23)
+    paths = random_paths(rng, 4000, 6, 2500)
+    names = [f"hap{i:02d}" for i in range(len(paths))]
+    lens = [rng.randrange(1, 60) for _ in range(4000)]
+    g = opy.Graph(nodes_len=lens, paths={n: list(p) for n, p in zip(names, paths)})
+    trio_map, _tlen, owner_ref = opy.trio_nodes_info_reference_order(g)
+    lib_map, _l2, owner_lib = opy.trio_nodes_info(g)
+    assert set(trio_map) == set(lib_map)
+    keys = np.array(sorted(lib_map, key=lib_map.get), dtype=np.uint64).reshape(-1, 3)
+    np.testing.assert_array_equal(keys, unique_table_in_library_order(paths))
+    nprng = np.random.default_rng(9)
+    depth_by_key = {k: float(nprng.lognormal(0.5, 1.2)) * float(nprng.random() > 0.15) for k in lib_map}
+    # restatement, reference numbering
+    ref_keys = sorted(trio_map, key=trio_map.get)
+    possible, om, _same = opy.first_filter_paths(g, owner_ref, [depth_by_key[k] for k in ref_keys], [0.0] * 4000, fr=0.3)
+    # product tail: library numbering + permutation
+    lib_keys = [tuple(int(x) for x in k) for k in keys]
+    order = api.trio_ref_order([np.array(p) for p in paths], keys)
+    assert [lib_keys[i] for i in order] == ref_keys
+    opt = strain_tail.OptVar(otu="x", hap_metrics=[strain_tail.HapMetrics() for _ in names])
+    strain_tail.first_filter_paths(opt, names, paths, np.array(owner_lib, dtype=np.uint32), np.array([depth_by_key[k] for k in lib_keys]),
+                                   np.zeros(4000), strain_tail.ProfilingArgs(), trio_order=order)
+    assert opt.possible_paths_idx == possible
+    for h in possible:
+        assert opt.hap_metrics[h].frequencies_mean == om[h]["frequencies_mean"]
+        assert opt.hap_metrics[h].unique_trio_nodes_fraction == om[h]["unique_trio_nodes_fraction"]
