@@ -16,9 +16,9 @@ Stage 4 of north_star - the ILP itself - stays in a host solver; this module onl
 layout the reference builds, and carries the post-solver rules.  Everything numeric that depends on the reads comes from
 libpantax_gpu.so (`pantax_b200.api`); the CPU restatements used by the tests are never imported here.
 
-Not reproducible bit for bit, and said so: `sample_sorted` (profile.rs:1287-1295) draws with rand 0.9 `StdRng` +
-`choose_multiple` when a species has more than `--sample` (500 000) covered nodes - here a numpy generator with the same
-seed draws a different subset; float columns are printed in ryu's format (what polars' CSV writer uses) by `fmt_f64`.
+`sample_sorted` (profile.rs:1287-1295: rand 0.9 `StdRng(42)` + `choose_multiple` when a species has more than `--sample`
+= 500 000 covered nodes) draws through `rand09.py`, a restatement of that generator and sampler; float columns are printed in
+ryu's format (what polars' CSV writer uses) by `fmt_f64`.
 """
 from __future__ import annotations
 
@@ -157,10 +157,11 @@ def first_filter_paths(opt: OptVar, hap_names: Sequence[str], paths: Sequence[np
 
 
 def sample_sorted(valid_nodes: np.ndarray, sample_size: int, seed: int) -> np.ndarray:
-    """profile.rs:1287-1295.  The reference draws with rand 0.9 StdRng(seed).choose_multiple; that generator is not
-    re-created here, so above `sample_size` covered nodes the subset (and with it the ILP) differs from the reference's."""
-    rng = np.random.default_rng(seed)
-    return np.sort(rng.choice(valid_nodes, size=sample_size, replace=False))
+    """profile.rs:1287-1295: `StdRng::seed_from_u64(seed)` + `choose_multiple` + `sort_unstable`, with rand 0.9.2's generator and
+    index sampler restated in rand09.py - the same seed draws the same nodes as the reference (unpinned: restated, not run)."""
+    from . import rand09
+
+    return rand09.choose_multiple_sorted(np.asarray(valid_nodes), sample_size, seed)
 
 
 @dataclass
