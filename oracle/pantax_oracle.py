@@ -528,7 +528,10 @@ def first_filter_paths(
 
 def round_half_away(x: float) -> float:
     """Rust f64::round (half away from zero)."""
-    return math.floor(x + 0.5) if x >= 0 else -math.floor(-x + 0.5)
+    if math.isnan(x) or math.isinf(x):
+        return x
+    t = float(math.trunc(x))
+    return t + math.copysign(1.0, x) if abs(x - t) >= 0.5 else t
 
 
 # --------------------------------------------------------------------------

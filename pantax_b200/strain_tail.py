@@ -76,8 +76,11 @@ class OptVar:  # GurobiOptVar, profile.rs:1053-1063
 
 
 def rust_round(x: float) -> float:
-    """f64::round: half away from zero."""
-    return math.floor(x + 0.5) if x >= 0 else -math.floor(-x + 0.5)
+    """f64::round: half away from zero.  (Not floor(x + 0.5): that addition rounds, e.g. 0.49999999999999994 + 0.5 == 1.0.)"""
+    if math.isnan(x) or math.isinf(x):
+        return x
+    t = float(math.trunc(x))
+    return t + math.copysign(1.0, x) if abs(x - t) >= 0.5 else t  # x - trunc(x) is exact
 
 
 def seq_sum(xs) -> float:
@@ -389,18 +392,23 @@ def abundance_est(args: ProfilingArgs, metrics: Sequence[HapMetrics], genomes_in
                   ori_path: Optional[str] = None) -> List[List[str]]:
     """profile.rs:3091-3289: joins the hap metrics with genomes_info.txt rows (genome_ID, strain_taxid, species_taxid, organism_name, id),
     predicted_abundance = coverage / sum, the two filters, sort by abundance (descending, stable), 11-column TSV.  Returns the rows."""
-    by_hap: Dict[str, Tuple[str, str]] = {}
+    by_hap: Dict[str, List[Tuple[str, str]]] = {}
     for gid, strain, _sp, _name, pid in genomes_info:
-        by_hap.setdefault(hap_id_of_genome(pid), (gid, strain))
+        by_hap.setdefault(hap_id_of_genome(pid), []).append((gid, strain))
     header = ["species_taxid", "strain_taxid", "genome_ID", "predicted_coverage", "predicted_abundance", "path_base_cov", "unique_trio_fraction",
               "uniq_trio_cov_mean", "first_sol", "strain_cov_diff", "total_cov_diff"]
-    cov_sum = 0.0
+    # :3176-3183 left join on hap_id: one row per matching genomes_info line (none -> one row with null genome columns)
+    merged: List[Tuple[HapMetrics, Optional[str], Optional[str]]] = []
     for m in metrics:
+        for gid, strain in by_hap.get(m.hap_id, [(None, None)]):
+            merged.append((m, gid, strain))
+    cov_sum = 0.0
+    for m, _g, _s in merged:
         if m.second_sol is not None:
             cov_sum += m.second_sol
 
-    def row(m: HapMetrics, total: float):
-        gid, strain = by_hap.get(m.hap_id, (None, None))
+    def row(e: Tuple[HapMetrics, Optional[str], Optional[str]], total: float):
+        m, gid, strain = e
         ab = None if m.second_sol is None else (m.second_sol / total if total != 0 else float("nan"))
         return [m.otu, strain or "", gid or "", fmt_f64(m.second_sol), fmt_f64(ab), fmt_f64(m.path_cov_ratio), fmt_f64(m.unique_trio_nodes_fraction),
                 fmt_f64(m.frequencies_mean), fmt_f64(m.first_sol), fmt_f64(m.divergence), fmt_f64(m.total_cov_diff)]
@@ -408,19 +416,20 @@ def abundance_est(args: ProfilingArgs, metrics: Sequence[HapMetrics], genomes_in
     if ori_path:
         with open(ori_path, "w") as f:
             f.write("\t".join(header) + "\n")
-            for m in metrics:
-                f.write("\t".join(row(m, cov_sum)) + "\n")
+            for e in merged:
+                f.write("\t".join(row(e, cov_sum)) + "\n")
     group: Dict[str, int] = {}
-    for m in metrics:
-        group[m.otu] = group.get(m.otu, 0) + 1
-    kept = [m for m in metrics
-            if (group[m.otu] > 1 or (m.total_cov_diff is not None and m.total_cov_diff <= args.single_cov_diff))
-            and m.second_sol is not None and m.second_sol >= args.min_cov and m.second_sol != 0.0]
+    for m, _g, _s in merged:
+        if m.hap_id is not None:  # count() skips nulls
+            group[m.otu] = group.get(m.otu, 0) + 1
+    kept = [e for e in merged
+            if (group.get(e[0].otu, 0) > 1 or (e[0].total_cov_diff is not None and e[0].total_cov_diff <= args.single_cov_diff))
+            and e[0].second_sol is not None and e[0].second_sol >= args.min_cov and e[0].second_sol != 0.0]
     total = 0.0
-    for m in kept:
+    for m, _g, _s in kept:
         total += m.second_sol
-    kept.sort(key=lambda m: -(m.second_sol / total))
-    rows = [row(m, total) for m in kept]
+    kept.sort(key=lambda e: -(e[0].second_sol / total))
+    rows = [row(e, total) for e in kept]
     with open(out_path, "w") as f:
         f.write("\t".join(header) + "\n")
         for r in rows:

@@ -124,3 +124,26 @@ def test_gaf_to_strain_abundance_table_end_to_end(tmp_path):
     ab = [float(r[4]) for r in rows]
     assert ab == sorted(ab, reverse=True) and abs(sum(ab) - 1.0) < 1e-9
     assert all(r[2].startswith("G") and r[1].startswith("T") for r in rows)
+
+
+def test_rust_round_is_exact_at_the_half_boundaries():
+    assert st.rust_round(0.49999999999999994) == 0.0  # floor(x + 0.5) would say 1.0
+    assert st.rust_round(0.5) == 1.0 and st.rust_round(-0.5) == -1.0 and st.rust_round(2.5) == 3.0 and st.rust_round(-2.5) == -3.0
+    assert st.rust_round(4503599627370497.0) == 4503599627370497.0  # 2^52 + 1: x + 0.5 is not representable
+    assert opy.round_half_away(0.49999999999999994) == 0.0 and opy.round_half_away(-1.5) == -2.0
+
+
+def test_abundance_est_left_join_repeats_a_hap_with_two_genome_rows(tmp_path):
+    """profile.rs:3176-3183: the left join on hap_id yields one row per matching genomes_info line; the abundance sum and the
+    group size are taken over the joined rows."""
+    args = st.ProfilingArgs()
+    ms = []
+    for i, sol in enumerate((3.0, 1.0)):
+        m = st.HapMetrics(otu="562", hap_id=f"GCF_{i}", second_sol=sol, first_sol=sol, total_cov_diff=0.1)
+        ms.append(m)
+    info = [("G0", "T0", "562", "o", "/x/GCF_0_genomic.fna"), ("G0b", "T0b", "562", "o", "/y/GCF_0_other.fna.gz"), ("G1", "T1", "562", "o", "/x/GCF_1.fa")]
+    rows = st.abundance_est(args, ms, info, str(tmp_path / "s.txt"), str(tmp_path / "o.txt"))
+    assert [r[2] for r in rows] == ["G0", "G0b", "G1"]
+    assert [float(r[4]) for r in rows] == [3.0 / 7.0, 3.0 / 7.0, 1.0 / 7.0]
+    ori = open(tmp_path / "o.txt").read().split("\n")
+    assert len(ori) == 1 + 3 + 1
