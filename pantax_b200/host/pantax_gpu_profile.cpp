@@ -12,7 +12,9 @@
 //   <wd>/species_abundance.txt        species_taxid predicted_abundance predicted_coverage  (profile.rs:338-347)
 //   <wd>/strain_inputs/<t>.nodes.tsv / .paths.tsv   what optimize_otu hands to the ILP (profile.rs:2936-2967):
 //        node depth, covered bases; per path: unique-trio fraction, frequencies_mean, path_cov_ratio, kept by
-//        first_filter_paths.  The ILP itself (profile.rs:1297-2882) stays in the reference's solvers.
+//        first_filter_paths; <wd>/strain_graphs/<t>.bin (plain bincode Graph) when the species' graph was not a plain .bin in the db.
+//        `python -m pantax_b200.strain_tail --db DB --wd WD` reads these and carries the run to strain_abundance.txt
+//        (PAO model -> HiGHS, second filter, abundance constraint; profile.rs:2689-2882, 1229-1285, 3028-3289).
 // All arithmetic on reads/nodes/paths runs in libpantax_gpu.so; this file does file I/O, the f64 tail and TSVs.
 #include <algorithm>
 #include <charconv>
@@ -209,6 +211,25 @@ bool read_bin_graph(const std::string& path, Graph& g, int kind = 0) {
     return parse_bin_graph(plain, g);
 }
 
+// The plain bincode layout of zip.rs:185 / types.rs:51-55 (u64 n; i64 nodes_len[n]; u64 n_paths; per path in key order: u64 klen, key,
+// u64 plen, u64 node[plen]) - written to <wd>/strain_graphs for the strain tail (strain_tail.py) when the species' graph did not come from a plain .bin.
+bool write_bin_graph(const std::string& path, const Graph& g) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    bool ok = true;
+    const auto w64 = [&](uint64_t v) { ok = ok && fwrite(&v, 8, 1, f) == 1; };
+    w64((uint64_t)g.nodes_len.size());
+    if (!g.nodes_len.empty()) ok = ok && fwrite(g.nodes_len.data(), 8, g.nodes_len.size(), f) == g.nodes_len.size();
+    w64((uint64_t)g.paths.size());
+    for (auto& kv : g.paths) {
+        w64((uint64_t)kv.first.size());
+        if (!kv.first.empty()) ok = ok && fwrite(kv.first.data(), 1, kv.first.size(), f) == kv.first.size();
+        w64((uint64_t)kv.second.size());
+        if (!kv.second.empty()) ok = ok && fwrite(kv.second.data(), 8, kv.second.size(), f) == kv.second.size();
+    }
+    return fclose(f) == 0 && ok;
+}
+
 template <class F>
 void for_digit_runs(const std::string& s, bool allow_minus, F fn) {
     size_t i = 0;
@@ -355,6 +376,17 @@ int main(int argc, char** argv) {
                 printf("path %s %zu\n", kv.first.c_str(), kv.second.size());
                 for (size_t i = 0; i < kv.second.size(); ++i) printf("%llu%c", (unsigned long long)kv.second[i], i + 1 == kv.second.size() ? '\n' : ' ');
             }
+            return 0;
+        }
+        else if (a == "--convert-graph") {
+            // no GPU: any graph file (.bin / .bin.lz4 / .bin.zst / .gfa by its extension) -> plain .bin (what <wd>/strain_graphs/<taxid>.bin is)
+            const std::string path = next(), out = next();
+            Graph g;
+            const auto ends = [&](const char* e) { const size_t n = strlen(e); return path.size() >= n && path.compare(path.size() - n, n, e) == 0; };
+            const bool ok = ends(".lz4") ? read_bin_graph(path, g, 1) : ends(".zst") ? read_bin_graph(path, g, 2) : ends(".bin") ? read_bin_graph(path, g, 0)
+                                                                                                                   : read_gfa_graph(path, g);
+            if (!ok) die("cannot read graph " + path);
+            if (!write_bin_graph(out, g)) die("cannot write " + out);
             return 0;
         }
         else if (a == "-h" || a == "--help") { usage(); return 0; }
@@ -600,13 +632,16 @@ int main(int argc, char** argv) {
         chosen.push_back(s);
     }
     std::map<int, Graph> graphs;
+    std::set<int> not_plain;  // species whose Graph was decoded from .bin.lz4 / .bin.zst / GFA: the strain tail gets it as a plain .bin
     for (int s : chosen) {
         Graph g;
         // profile.rs:2888-2932: <db>/species_graph_info/<taxid>.bin | .bin.lz4 | .bin.zst (zip.rs:236-262), else <db>/species_gfa/<taxid>.gfa
         const std::string bin = o.db + "/species_graph_info/" + ranges[s].taxid + ".bin";
         const std::string gfa = o.db + "/species_gfa/" + ranges[s].taxid + ".gfa";
-        const bool have_bin = (exists(bin) && read_bin_graph(bin, g, 0)) || (exists(bin + ".lz4") && read_bin_graph(bin + ".lz4", g, 1)) ||
+        const bool plain_bin = exists(bin) && read_bin_graph(bin, g, 0);
+        const bool have_bin = plain_bin || (exists(bin + ".lz4") && read_bin_graph(bin + ".lz4", g, 1)) ||
                               (exists(bin + ".zst") && read_bin_graph(bin + ".zst", g, 2));
+        if (!plain_bin) not_plain.insert(s);
         if (have_bin) {
             std::vector<uint64_t> off{0}, flat;
             for (auto& kv : g.paths) { flat.insert(flat.end(), kv.second.begin(), kv.second.end()); off.push_back(flat.size()); }
@@ -662,6 +697,10 @@ int main(int argc, char** argv) {
             for (int64_t i = 0; i < n; ++i)
                 if (depth[(size_t)i] > 0) fprintf(f, "%lld\t%lld\t%s\t%llu\n", (long long)i, (long long)g.nodes_len[(size_t)i], fmt_f64(depth[(size_t)i]).c_str(), (unsigned long long)cov[(size_t)i]);
             fclose(f);
+        }
+        if (not_plain.count(s)) {
+            mkdir((o.wd + "/strain_graphs").c_str(), 0755);
+            if (!write_bin_graph(o.wd + "/strain_graphs/" + ranges[s].taxid + ".bin", g)) die("cannot write strain_graphs/" + ranges[s].taxid + ".bin");
         }
         // first_filter_paths (profile.rs:1080-1227)
         std::vector<std::string> hap_names;

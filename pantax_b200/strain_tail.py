@@ -435,3 +435,136 @@ def abundance_est(args: ProfilingArgs, metrics: Sequence[HapMetrics], genomes_in
         for r in rows:
             f.write("\t".join(r) + "\n")
     return rows
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# File-level strain stage: the tables pantax-gpu-profile wrote (GPU numbers) -> strain_abundance.txt
+# ---------------------------------------------------------------------------------------------------------------------
+def read_bin_graph(path: str) -> Tuple[np.ndarray, List[str], List[np.ndarray]]:
+    """zip.rs:236-247 for a plain `.bin`: bincode 1.3 (little endian, fixed ints) of types.rs:51-55 - u64 n, i64 nodes_len[n], u64 n_paths,
+    per path in key order: u64 klen, key, u64 plen, u64 node[plen].  Returns (nodes_len, hap names, paths as local node ids)."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    pos = 0
+
+    def u64() -> int:
+        nonlocal pos
+        if pos + 8 > len(raw):
+            raise ValueError(f"{path}: truncated bincode graph")
+        v = int(raw[pos:pos + 8].view("<u8")[0])
+        pos += 8
+        return v
+
+    def take(nbytes: int) -> np.ndarray:
+        nonlocal pos
+        if nbytes < 0 or pos + nbytes > len(raw):
+            raise ValueError(f"{path}: truncated bincode graph")
+        v = raw[pos:pos + nbytes]
+        pos += nbytes
+        return v
+
+    n = u64()
+    nodes_len = take(8 * n).view("<i8").astype(np.int64)
+    names, paths = [], []
+    for _ in range(u64()):
+        names.append(bytes(take(u64())).decode())
+        paths.append(take(8 * u64()).view("<u8").astype(np.int64))
+    if pos != len(raw):
+        raise ValueError(f"{path}: {len(raw) - pos} bytes behind the graph")
+    return nodes_len, names, paths
+
+
+def _tsv(path: str) -> List[List[str]]:
+    with open(path) as f:
+        return [l.split("\t") for l in f.read().split("\n")[1:] if l]
+
+
+def load_strain_inputs(wd: str, db: str, taxid: str, args: ProfilingArgs):
+    """One species as pantax-gpu-profile left it in <wd>/strain_inputs: the Graph, node depths, and the state of GurobiOptVar after
+    first_filter_paths (profile.rs:2936-2967).  Returns (opt, paths, node_depth, path_cov_ratio) or None when no node was covered."""
+    si = os.path.join(wd, "strain_inputs")
+    own = os.path.join(wd, "strain_graphs", f"{taxid}.bin")  # written by the driver when the db holds .bin.lz4 / .bin.zst / a GFA
+    nodes_len, names, paths = read_bin_graph(own if os.path.exists(own) else os.path.join(db, "species_graph_info", f"{taxid}.bin"))
+    node_rows = _tsv(os.path.join(si, f"{taxid}.nodes.tsv"))
+    if not node_rows:
+        return None  # no read of this species survived: the reference has no read cluster for it and skips optimize_otu (profile.rs:3300-3302)
+    node_depth = np.zeros(len(nodes_len), dtype=np.float64)
+    for r in node_rows:
+        node_depth[int(r[0])] = float(r[2])
+    rows = _tsv(os.path.join(si, f"{taxid}.paths.tsv"))
+    if [r[0] for r in rows] != names:
+        raise ValueError(f"{taxid}: paths.tsv and the graph list different haplotypes")
+    H = len(rows)
+    T = sum(int(r[1]) for r in rows)
+    opt = OptVar(otu=taxid, hap_metrics=[HapMetrics(otu=taxid, hap_id=r[0]) for r in rows])
+    opt.orign_n_haps = H
+    opt.hap2trio_nodes_m_size = H * T
+    ratio = np.full(H, np.nan)
+    for h, r in enumerate(rows):
+        m = opt.hap_metrics[h]
+        if r[3] != "":
+            m.unique_trio_nodes_fraction = float(r[3])
+        if r[5] != "":
+            ratio[h] = float(r[5])
+        if r[8] == "1":
+            opt.possible_paths_idx.append(h)
+            if r[4] != "":
+                m.frequencies_mean = float(r[4])
+    if H > 1 and T == 0:
+        opt.same_path_flag = all(len(p) == len(paths[0]) and np.array_equal(p, paths[0]) for p in paths[1:])
+    return opt, paths, node_depth, ratio
+
+
+def run_strain_stage(db: str, wd: str, args: ProfilingArgs, ori_path: Optional[str] = None) -> List[List[str]]:
+    """profile.rs:3291-3323 (strain_profiling) from the files of a pantax-gpu-profile run: per species (species_range.txt order)
+    highs_opt + abundace_constraint, then abundance_est -> <wd>/strain_abundance.txt.  Everything read-dependent in those files was
+    computed on the GPU; this stage is the host solver and the joins."""
+    species_cov: Dict[str, float] = {}
+    for r in _tsv(os.path.join(wd, "species_abundance.txt")):
+        species_cov[r[0]] = float(r[2])
+    with open(os.path.join(db, "species_range.txt")) as f:
+        order = [l.split("\t")[0] for l in f.read().split("\n") if l]
+    metrics: List[HapMetrics] = []
+    for taxid in order:
+        if not os.path.exists(os.path.join(wd, "strain_inputs", f"{taxid}.paths.tsv")):
+            continue
+        loaded = load_strain_inputs(wd, db, taxid, args)
+        if loaded is None:
+            continue
+        opt, paths, node_depth, ratio = loaded
+        if opt.possible_paths_idx:
+            highs_opt(opt, paths, node_depth, ratio, args)
+        abundace_constraint(species_cov[taxid], opt.hap_metrics)
+        metrics.extend(opt.hap_metrics)
+    info = [tuple((r + [""] * 5)[:5]) for r in _tsv(os.path.join(db, "genomes_info.txt"))]
+    return abundance_est(args, metrics, info, os.path.join(wd, "strain_abundance.txt"), ori_path)
+
+
+def main(argv: Optional[Sequence[str]] = None) -> int:
+    import argparse
+
+    ap = argparse.ArgumentParser(prog="python -m pantax_b200.strain_tail",
+                                 description="Strain stage after `pantax-gpu-profile --species --strain`: strain_inputs/ -> strain_abundance.txt")
+    ap.add_argument("--db", "-d", required=True)
+    ap.add_argument("--wd", "-T", default=".")
+    ap.add_argument("--fr", type=float, default=None, help="fstrain (default 0.3, long reads 0.5)")
+    ap.add_argument("--fc", type=float, default=0.46, help="dstrain")
+    ap.add_argument("--sr", type=float, default=0.85)
+    ap.add_argument("--sd", type=float, default=0.2)
+    ap.add_argument("--long-read", action="store_true")
+    ap.add_argument("--shift", action="store_true", help="must equal the --shift given to pantax-gpu-profile (first filter)")
+    ap.add_argument("--min_cov", type=float, default=0.0)
+    ap.add_argument("--min_depth", type=float, default=0.0)
+    ap.add_argument("--sample", type=int, default=500_000)
+    ap.add_argument("--sample-test", action="store_true")
+    ap.add_argument("--ori", default="ori_strain_abundance.txt", help="profile.rs:3217 writes it to the current directory")
+    a = ap.parse_args(argv)
+    args = ProfilingArgs(unique_trio_nodes_fraction=a.fr if a.fr is not None else (0.5 if a.long_read else 0.3), unique_trio_nodes_mean_count_f=a.fc,
+                         single_cov_ratio=a.sr, single_cov_diff=a.sd, min_cov=a.min_cov, min_depth=a.min_depth, sample_nodes=a.sample,
+                         sample_test=a.sample_test, shift=a.shift)
+    rows = run_strain_stage(a.db, a.wd, args, a.ori)
+    print(f"- Strain level profiling: {len(rows)} strains written to {os.path.join(a.wd, 'strain_abundance.txt')}")
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
