@@ -21,7 +21,7 @@ fn main() {
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=dylib=pantax_gpu");
     println!("cargo:rustc-link-arg=-Wl,-rpath,{}", out.display());
-    for f in ["ptx_kernels.cu", "ptx_api.cu", "ptx_core.cuh", "ptx_internal.h"] {
+    for f in ["ptx_kernels.cu", "ptx_api.cu", "ptx_core.cuh", "ptx_fast.cuh", "ptx_fxorder.h", "ptx_internal.h"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", root.join("include/pantax_gpu.h").display());
