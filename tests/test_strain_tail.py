@@ -147,3 +147,15 @@ def test_abundance_est_left_join_repeats_a_hap_with_two_genome_rows(tmp_path):
     assert [float(r[4]) for r in rows] == [3.0 / 7.0, 3.0 / 7.0, 1.0 / 7.0]
     ori = open(tmp_path / "o.txt").read().split("\n")
     assert len(ori) == 1 + 3 + 1
+
+
+def test_float_columns_print_like_the_readme_examples():
+    """The only output rows the reference publishes (README.md:341-354, written by polars' CSV writer): every float there must be
+    reproduced digit for digit by fmt_f64 from the parsed value."""
+    readme = ["0.5005489240249426", "6.723225501680235", "16.0", "0.39983790355261384", "0.9967217217217217", "1.0", "15.54", "0.01",
+              "0.0010005002501250622"]
+    for s in readme:
+        assert st.fmt_f64(float(s)) == s
+    header = "species_taxid\tstrain_taxid\tgenome_ID\tpredicted_coverage\tpredicted_abundance\tpath_base_cov\tunique_trio_fraction\tuniq_trio_cov_mean\tfirst_sol\tstrain_cov_diff\ttotal_cov_diff"
+    import inspect
+    assert all(c in inspect.getsource(st.abundance_est) for c in header.split("\t"))
