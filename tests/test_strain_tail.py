@@ -159,3 +159,15 @@ def test_float_columns_print_like_the_readme_examples():
     header = "species_taxid\tstrain_taxid\tgenome_ID\tpredicted_coverage\tpredicted_abundance\tpath_base_cov\tunique_trio_fraction\tuniq_trio_cov_mean\tfirst_sol\tstrain_cov_diff\ttotal_cov_diff"
     import inspect
     assert all(c in inspect.getsource(st.abundance_est) for c in header.split("\t"))
+
+
+def test_hap_id_of_the_reference_example_genomes():
+    """profile.rs:3106-3145 on the `id` column of the reference's own example tables (example/example_genomes_info.txt,
+    genomes_info.txt): Path::file_stem drops ONE extension, then the first two `_` pieces are kept."""
+    cases = {"../genomes/GCF_002012065.1_ASM201206v1_genomic.fna": "GCF_002012065.1",
+             "../genomes/GCF_006400955.1_ASM640095v1_genomic.fna.gz": "GCF_006400955.1",
+             "../genomes/MGYG000002538_genomic.fna": "MGYG000002538_genomic",
+             "/path/to/GCF_009730575.1_ASM973057v1_genomic.fna": "GCF_009730575.1",
+             "plain.fa": "plain"}
+    for path, hap in cases.items():
+        assert st.hap_id_of_genome(path) == hap
