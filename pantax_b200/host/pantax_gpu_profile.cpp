@@ -619,7 +619,11 @@ int main(int argc, char** argv) {
     // ---- strain level: graphs of the species that pass load_species_range (profile.rs:553-656)
     std::set<std::string> wanted;
     if (!o.designated.empty() && o.designated != "None")
-        for (auto& t : split(o.designated, ',')) if (!t.empty()) wanted.insert(t);
+        for (auto t : split(o.designated, ',')) {  // profile.rs:581-585: pieces are trimmed, empty ones dropped
+            while (!t.empty() && isspace((unsigned char)t.back())) t.pop_back();
+            while (!t.empty() && isspace((unsigned char)t.front())) t.erase(t.begin());
+            if (!t.empty()) wanted.insert(t);
+        }
     std::map<std::string, double> rel_of;
     for (auto& r : table) rel_of[r.taxid] = r.rel;
     std::vector<int> chosen;
