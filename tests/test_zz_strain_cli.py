@@ -1,7 +1,7 @@
 """File-level strain stage (`python -m pantax_b200.strain_tail --db DB --wd WD`): the tables pantax-gpu-profile leaves in
 <wd>/strain_inputs -> strain_abundance.txt.  CPU part: the files are written here from the restatement's numbers in the
 driver's formats (pantax_gpu_profile.cpp), the stage must give what the in-memory tail gives; the plain-.bin writer of the driver
-is checked through --convert-graph.  GPU part (last in the suite): the real driver, then the stage, against the in-process flow."""
+is checked through --convert-graph.  GPU part (this file sorts last in the suite): the real driver, then the stage, against the in-process flow."""
 import filecmp
 import os
 import subprocess
