@@ -486,7 +486,15 @@ int main(int argc, char** argv) {
         size_t st = 0;
         for (size_t i = 0; i <= l && nf < 12; ++i)
             if (i == l || b[i] == '\t') { f[nf] = b + st; fl[nf] = i - st; ++nf; st = i + 1; }
-        rep_rows.append(f[0], fl[0]);
+        // polars' CsvWriter (rcls.rs:415-418, QuoteStyle::Necessary): a string holding the quote character or a line break is
+        // written between quotes with its quotes doubled (a read id cannot hold the separator)
+        if (memchr(f[0], '"', fl[0]) || memchr(f[0], '\r', fl[0])) {
+            rep_rows.push_back('"');
+            for (size_t k = 0; k < fl[0]; ++k) { if (f[0][k] == '"') rep_rows.push_back('"'); rep_rows.push_back(f[0][k]); }
+            rep_rows.push_back('"');
+        } else {
+            rep_rows.append(f[0], fl[0]);
+        }
         rep_rows.push_back('\t');
         if (nf > 11 && is_int(f[11], fl[11])) rep_rows.append(f[11], fl[11]);
         rep_rows.push_back('\t');
