@@ -251,8 +251,11 @@ bool read_gfa_graph(const std::string& path, Graph& g) {
     if (!f) return false;
     std::string line;
     size_t idx = 0;
+    const auto space = [](char c) { return c == ' ' || (c >= 9 && c <= 13); };  // what str::trim removes (ASCII)
     while (std::getline(f, line)) {
         if (line.empty()) continue;
+        if (line[0] == 'S' || line[0] == 'W' || line[0] == 'P')
+            while (!line.empty() && space(line.back())) line.pop_back();  // line.trim() (profile.rs:483, 497); nothing to trim in front
         if (line[0] == 'S') {
             auto p = split(line, '\t');
             if (p.size() < 3) continue;
@@ -262,7 +265,6 @@ bool read_gfa_graph(const std::string& path, Graph& g) {
             if (p[2].empty()) die("Node length 0 appears in the GFA (profile.rs:494): " + path);
             g.nodes_len.push_back((int64_t)p[2].size());
         } else if (line[0] == 'W' || line[0] == 'P') {
-            while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
             auto p = split(line, '\t');
             std::string hap;
             std::vector<uint64_t> nodes;

@@ -67,7 +67,7 @@ def assert_cpu_matches_py(ranges, graphs, gaf: bytes, labels=None):
     cnt = o.species_counts()
     for sp, c in counts.items():
         np.testing.assert_array_equal(cnt[name_to_idx[sp]], np.array(c, dtype=np.int64))
-    assert cnt.sum() == sum(sum(c) for c in counts.values())
+    assert sum(int(x) for x in cnt.ravel()) == sum(sum(c) for c in counts.values())  # Python ints: the total over species may pass 2^63 in the fuzzer
     for s, g in enumerate(graphs):
         if g is None:
             continue

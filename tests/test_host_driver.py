@@ -201,3 +201,17 @@ def test_graph_readers_on_the_bincode_fixtures(ext):
         i += 2
     assert list(got) == sorted(g["paths"], key=lambda s: s.encode())  # BTreeMap order
     assert got == g["paths"]
+
+
+def test_host_gfa_reader_trims_lines_like_the_reference(tmp_path):
+    """profile.rs:483, 497: `line.trim()` before the split - CRLF files, trailing blanks behind a sequence and a trailing tab behind
+    a walk must not change node lengths or hide the walk (the fallback C++ reader, --dump-graph; the device parser has its own test)."""
+    txt = ("H\tVN:Z:1.1\r\nS\t1\tACGT\r\nS\t2\tAC \r\nS\t3\tA\t*\r\nS\t4\tGGG\t\r\n"
+           "W\thap#B\t0\tchr0\t0\t100\t>3>1<2\t\r\nP\tGCF_1.1#1#chr1\t4+,1-\t* \r\nW\thap#B\t0\tchr1\t0\t100\t<4")
+    p = str(tmp_path / "g.gfa")
+    open(p, "w", newline="").write(txt)
+    g = opy.read_gfa(txt.replace("\r\n", "\n"))
+    assert g.nodes_len == [4, 2, 1, 3] and dict(g.paths) == {"GCF_1.1": [3, 0], "hap#B": [2, 0, 1, 3]}
+    out = subprocess.run([BIN, "--dump-graph", p], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert out[0] == "nodes 4" and out[1] == "4 2 1 3"
+    assert out[2:6] == ["path GCF_1.1 2", "3 0", "path hap#B 4", "2 0 1 3"]
