@@ -187,3 +187,29 @@ def test_oracle_in_reference_order_equals_strain_tail_bit_for_bit():
     for h in possible:
         assert opt.hap_metrics[h].frequencies_mean == om[h]["frequencies_mean"]
         assert opt.hap_metrics[h].unique_trio_nodes_fraction == om[h]["unique_trio_nodes_fraction"]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_colliding_keys_walk_the_triangular_probe_sequence(seed):
+    """Trios chosen so that a third of all keys start probing in the same 16-byte group of the final table: the chain runs over
+    many groups (16, 32, 48, ... apart) and through every resize.  The simplified emulation and the structural restatement must
+    still agree slot for slot."""
+    rng = random.Random(seed)
+    chosen = []
+    while len(chosen) < 300:
+        a, b, c = rng.randrange(1 << 20), rng.randrange(1 << 20), rng.randrange(1 << 20)
+        if a > c:
+            a, c = c, a
+        if fx.fx_hash_words((a, b, c)) & 0x7FF < 16:
+            chosen.append((a, b, c))
+    paths = [[v for t in chosen[k::3] for v in t] for k in range(3)]  # the windows across two triples add ~600 ordinary keys
+    keys = unique_table_in_library_order(paths)
+    allt, uniq = fx.reference_trio_numbering(paths)
+    s = fx.FxHashSet()
+    for p in paths:
+        s.extend(fx.canonical_windows(p))
+    assert s.t.buckets in (1024, 2048)
+    starts = [fx.fx_hash_words(k) & s.t.bucket_mask for k in allt]
+    assert sum(1 for v in starts if v < 16) >= 300  # 300 keys for the 16 slots of one group
+    order = api.trio_ref_order([np.array(p, dtype=np.int64) for p in paths], keys)
+    assert [tuple(int(x) for x in keys[i]) for i in order] == uniq
