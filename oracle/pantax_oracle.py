@@ -304,6 +304,47 @@ def read_gfa(text: str, previous: int = 0) -> Graph:
     return g
 
 
+def read_and_zip_gfa(text: str, previous: int = 0):
+    """zip.rs:78-171: read_gfa plus what the database step does before it serialises the Graph - a W line whose walk starts with
+    `<` and a P line whose first step ends with `-` are stored reversed (:124, :137, :147-149); returns (Graph, min + 1, max + 1,
+    is_pan) = the row `zip` appends to the range file (:316-327)."""
+    nodes_len: List[int] = []
+    paths: Dict[str, List[int]] = {}
+    mins: List[int] = []
+    maxs: List[int] = []
+    idx = 0
+    for line in text.split("\n"):
+        if line.startswith("S"):
+            parts = line.strip().split("\t")
+            if len(parts) < 3:
+                continue
+            if int(parts[1]) - 1 - previous != idx:
+                raise ValueError("Node ID out of order or mismatch")
+            idx += 1
+            if len(parts[2]) == 0:
+                raise ValueError("Node length 0 appears in the GFA")
+            nodes_len.append(len(parts[2]))
+        elif line.startswith("W") or line.startswith("P"):
+            parts = line.strip().split("\t")
+            if parts[0] == "W":
+                hap = parts[1]
+                rev = parts[-1].startswith("<")
+                p = [int(m) - 1 - previous for m in re.findall(r"-?\d+", parts[-1])]
+            else:
+                hap = parts[1].split("#")[0]
+                fld = parts[2] if len(parts) > 2 else ""
+                rev = fld.split(",")[0].endswith("-")
+                p = [int(m) - 1 - previous for m in re.findall(r"\d+", fld)]
+            if rev:
+                p.reverse()
+            mins.append(min(p))  # :151 unwrap: an empty path is a panic
+            maxs.append(max(p))
+            paths.setdefault(hap, []).extend(p)
+    g = Graph(nodes_len)
+    g.paths = OrderedDict(sorted(paths.items(), key=lambda kv: kv[0].encode()))
+    return g, min(mins) + 1, max(maxs) + 1, 1 if len(paths) > 1 else 0
+
+
 # --------------------------------------------------------------------------
 # a6  unique trio nodes                                  profile.rs:658-740
 # --------------------------------------------------------------------------

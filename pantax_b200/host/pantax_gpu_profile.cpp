@@ -246,7 +246,10 @@ void for_digit_runs(const std::string& s, bool allow_minus, F fn) {
 }
 
 // profile.rs:466-545 (previous = 0)
-bool read_gfa_graph(const std::string& path, Graph& g) {
+// `zip` (zip.rs:78-171 read_and_zip_gfa, what the reference's database step writes into the .bin): a W line whose walk starts
+// with '<' and a P line whose first step ends with '-' are stored reversed; min / max node id over all path lines come back 1-based.
+struct ZipInfo { bool on = false; uint64_t min1 = ~0ull, max1 = 0; bool any = false; };
+bool read_gfa_graph(const std::string& path, Graph& g, ZipInfo* zip = nullptr) {
     std::ifstream f(path);
     if (!f) return false;
     std::string line;
@@ -274,6 +277,14 @@ bool read_gfa_graph(const std::string& path, Graph& g) {
             } else {
                 hap = p.size() > 1 ? split(p[1], '#')[0] : "";
                 for_digit_runs(p.size() > 2 ? p[2] : "", false, [&](int64_t v) { nodes.push_back((uint64_t)(v - 1)); });
+            }
+            if (zip && zip->on) {
+                const std::string& fld = p[0] == "W" ? p.back() : (p.size() > 2 ? p[2] : std::string());
+                const bool rev = p[0] == "W" ? (!fld.empty() && fld[0] == '<') : [&] { const std::string first = fld.substr(0, fld.find(',')); return !first.empty() && first.back() == '-'; }();
+                if (rev) std::reverse(nodes.begin(), nodes.end());  // zip.rs:124, 137, 147-149
+                if (nodes.empty()) die("path line without nodes in " + path + " (zip.rs:151 unwraps the minimum)");
+                for (uint64_t v : nodes) { zip->min1 = std::min(zip->min1, v + 1); zip->max1 = std::max(zip->max1, v + 1); }
+                zip->any = true;
             }
             auto& dst = g.paths[hap];  // same hap id: chromosomes are concatenated (profile.rs:540)
             dst.insert(dst.end(), nodes.begin(), nodes.end());
@@ -304,6 +315,7 @@ void usage() {
          "                   [--reads-binning reads_classification.tsv]   (with --strain only: species column of the GAF rows)\n"
          "                   [-a MIN_SPECIES_ABUND=1e-4] [--fr F] [--long-read] [--shift] [--no-filter] [--smode 0|1|2]\n"
          "                   [--ds TAXID,TAXID] [--range-file F] [--len-file F] [--min-depth D] [--device N] [--chunk-mb M]\n"
+         "                   --dump-graph FILE | --convert-graph FILE OUT.bin | --zip-gfa FILE.gfa OUTDIR RANGE_FILE   (graph files, no GPU)\n"
          "GPU implementation of PanTax's profiling stage (read classification, species abundance, node coverage and\n"
          "strain statistics).  Needs a CUDA device; there is no CPU fallback.");
 }
@@ -389,6 +401,25 @@ int main(int argc, char** argv) {
                                                                                                                    : read_gfa_graph(path, g);
             if (!ok) die("cannot read graph " + path);
             if (!write_bin_graph(out, g)) die("cannot write " + out);
+            return 0;
+        }
+        else if (a == "--zip-gfa") {
+            // no GPU: zip::zip (zip.rs:316-327) for one species GFA - <outdir>/<stem>.bin in the reference's bincode layout (kept if it
+            // exists) and the row `stem \t min \t max \t is_pan` appended to the range file
+            const std::string path = next(), outdir = next(), range_out = next();
+            Graph g;
+            ZipInfo z;
+            z.on = true;
+            if (!read_gfa_graph(path, g, &z)) die("cannot read graph " + path);
+            if (!z.any) die("no path lines in " + path + " (zip.rs:159 unwraps the minimum)");
+            std::string stem = path.substr(path.find_last_of('/') == std::string::npos ? 0 : path.find_last_of('/') + 1);
+            if (stem.find('.') != std::string::npos && stem.find_last_of('.') > 0) stem = stem.substr(0, stem.find_last_of('.'));
+            const std::string out = outdir + "/" + stem + ".bin";
+            if (!exists(out) && !write_bin_graph(out, g)) die("cannot write " + out);
+            FILE* rf = fopen(range_out.c_str(), "ab");
+            if (!rf) die("cannot append to " + range_out);
+            fprintf(rf, "%s\t%llu\t%llu\t%d\n", stem.c_str(), (unsigned long long)z.min1, (unsigned long long)z.max1, g.paths.size() > 1 ? 1 : 0);
+            fclose(rf);
             return 0;
         }
         else if (a == "-h" || a == "--help") { usage(); return 0; }

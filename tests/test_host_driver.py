@@ -215,3 +215,43 @@ def test_host_gfa_reader_trims_lines_like_the_reference(tmp_path):
     out = subprocess.run([BIN, "--dump-graph", p], capture_output=True, text=True, check=True).stdout.split("\n")
     assert out[0] == "nodes 4" and out[1] == "4 2 1 3"
     assert out[2:6] == ["path GCF_1.1 2", "3 0", "path hap#B 4", "2 0 1 3"]
+
+
+def test_zip_gfa_writes_the_reference_bin_and_range_row(tmp_path):
+    """zip.rs:78-171, 316-327: species GFA -> <stem>.bin (bincode Graph; W walks starting with '<' and P paths whose first step
+    ends with '-' stored reversed) + the range row `stem, min, max, is_pan`; no GPU involved."""
+    import random
+
+    from pantax_b200 import strain_tail as st
+
+    rng = random.Random(5)
+    for trial in range(30):
+        n = rng.randrange(3, 15)
+        lines = ["H\tVN:Z:1.1"]
+        for i in range(n):
+            lines.append(f"S\t{i + 1}\t{''.join(rng.choice('ACGT') for _ in range(rng.randrange(1, 9)))}")
+        for h in range(rng.randrange(1, 5)):
+            name = rng.choice(["hapA", "hapB", "GCF_1.1"])
+            ids = [rng.randrange(1, n + 1) for _ in range(rng.randrange(1, 8))]
+            if rng.random() < 0.5:
+                lines.append(f"W\t{name}\t0\tchr{h}\t0\t100\t" + "".join(rng.choice("<>") + str(v) for v in ids))
+            else:
+                lines.append(f"P\t{name}#1#chr{h}\t" + ",".join(str(v) + rng.choice("+-") for v in ids) + "\t*")
+        txt = "\n".join(lines) + "\n"
+        d = tmp_path / f"t{trial}"
+        d.mkdir()
+        gfa = str(d / "562.gfa")
+        open(gfa, "w").write(txt)
+        rf = str(d / "species_range.txt")
+        subprocess.run([BIN, "--zip-gfa", gfa, str(d), rf], check=True)
+        g, mn, mx, is_pan = opy.read_and_zip_gfa(txt)
+        assert open(rf).read() == f"562\t{mn}\t{mx}\t{is_pan}\n"
+        lens, names, paths = st.read_bin_graph(str(d / "562.bin"))
+        assert lens.tolist() == g.nodes_len and names == list(g.paths)
+        assert [p.tolist() for p in paths] == [g.paths[k] for k in names]
+        # the byte stream is the bincode layout the independent writer of this file produces
+        write_bin(str(d / "want.bin"), g.nodes_len, [g.paths[k] for k in names], names)
+        assert open(str(d / "want.bin"), "rb").read() == open(str(d / "562.bin"), "rb").read()
+        # a second run keeps the .bin (zip.rs:182) and appends another row
+        subprocess.run([BIN, "--zip-gfa", gfa, str(d), rf], check=True)
+        assert open(rf).read().count("\n") == 2
