@@ -43,7 +43,7 @@
 namespace {
 
 struct Options {
-    std::string db, gaf, wd = ".", report, range_file, len_file, designated, reads_binning;
+    std::string db, gaf, wd = ".", report, range_file, len_file, designated, reads_binning, filter_gaf;
     bool species = false, strain = false, filtered = true, long_read = false, shift = false, force = false;
     double min_species_abundance = 1e-4, fr = -1, min_depth = 0;
     bool host_gfa = false;  // --host-gfa: parse species GFAs with the C++ reader instead of on the device
@@ -315,6 +315,7 @@ void usage() {
          "                   [--reads-binning reads_classification.tsv]   (with --strain only: species column of the GAF rows)\n"
          "                   [-a MIN_SPECIES_ABUND=1e-4] [--fr F] [--long-read] [--shift] [--no-filter] [--smode 0|1|2]\n"
          "                   [--ds TAXID,TAXID] [--range-file F] [--len-file F] [--min-depth D] [--device N] [--chunk-mb M]\n"
+         "                   --filter-gaf FILE [--device N]   (long reads: FILE -> <stem>_filtered.gaf, gaf_filter.rs:44-97)\n"
          "                   --dump-graph FILE | --convert-graph FILE OUT.bin | --zip-gfa FILE.gfa OUTDIR RANGE_FILE   (graph files, no GPU)\n"
          "GPU implementation of PanTax's profiling stage (read classification, species abundance, node coverage and\n"
          "strain statistics).  Needs a CUDA device; there is no CPU fallback.");
@@ -347,6 +348,7 @@ int main(int argc, char** argv) {
         else if (a == "--device") o.device = std::stoi(next());
         else if (a == "--chunk-mb") o.chunk_mb = std::stoi(next());
         else if (a == "--host-gfa") o.host_gfa = true;
+        else if (a == "--filter-gaf") o.filter_gaf = next();
         else if (a == "--time-gfa") {
             // graph load of one species GFA both ways: the C++ reader on the host, and ptx_upload_graph_gfa (H2D + kernels + compact arrays back)
             const std::string path = next();
@@ -424,6 +426,37 @@ int main(int argc, char** argv) {
         }
         else if (a == "-h" || a == "--help") { usage(); return 0; }
         else die("unknown option " + a);
+    }
+    if (!o.filter_gaf.empty()) {
+        // gaf_filter::filter_max_alignment_mt (gaf_filter.rs:44-97) as alignment.rs:171 uses it: <dir>/<stem>_filtered.gaf holds, per read
+        // id, the first line that is its best alignment (max matches, then identity) with mapq > 20 and a span > 1000
+        std::vector<uint8_t> bytes;
+        if (!slurp(o.filter_gaf, bytes)) die("cannot read " + o.filter_gaf);
+        ptx_ctx* fc = nullptr;
+        if (ptx_create(o.device, &fc) != PTX_OK) die("no usable CUDA device (this tool has no CPU fallback)");
+        int64_t cap = 1, n_out = 0;
+        for (uint8_t c : bytes) cap += c == '\n';
+        std::vector<uint64_t> off((size_t)cap);
+        if (!bytes.empty()) ck(fc, ptx_filter_gaf(fc, bytes.data(), bytes.size(), off.data(), cap, &n_out), "ptx_filter_gaf");
+        const size_t slash = o.filter_gaf.find_last_of('/');
+        const std::string dir = slash == std::string::npos ? "" : o.filter_gaf.substr(0, slash + 1);
+        std::string stem = slash == std::string::npos ? o.filter_gaf : o.filter_gaf.substr(slash + 1);
+        if (stem.find_last_of('.') != std::string::npos && stem.find_last_of('.') > 0) stem = stem.substr(0, stem.find_last_of('.'));
+        const std::string out = dir + stem + "_filtered.gaf";
+        FILE* f = fopen(out.c_str(), "wb");
+        if (!f) die("cannot write " + out);
+        for (int64_t k = 0; k < n_out; ++k) {
+            const size_t b = (size_t)off[(size_t)k];
+            const void* nl = memchr(bytes.data() + b, '\n', bytes.size() - b);
+            size_t e = nl ? (size_t)((const uint8_t*)nl - bytes.data()) : bytes.size();
+            if (e > b && bytes[e - 1] == '\r') --e;  // BufRead::lines drops "\r\n"
+            fwrite(bytes.data() + b, 1, e - b, f);
+            fputc('\n', f);
+        }
+        fclose(f);
+        printf("Filtered GAF file written to: %s\n", out.c_str());  // gaf_filter.rs:95
+        ptx_destroy(fc);
+        return 0;
     }
     if (!o.species && !o.strain) die("Please choose profiling level with --species or/and --strain.");  // profile.rs:73-75
     if (o.db.empty() || o.gaf.empty()) { usage(); return 1; }

@@ -213,3 +213,21 @@ def test_zz_driver_then_strain_stage_on_the_gpu(tmp_path):
     for a, b in zip(rows, want):
         for x, y in zip(a[3:], b[3:]):
             assert (x == "" and y == "") or float(x) == pytest.approx(float(y), rel=1e-9, abs=1e-12)
+
+
+@pytest.mark.gpu
+def test_zz_filter_gaf_file_mode(tmp_path):
+    """alignment.rs:171 at file level: `pantax-gpu-profile --filter-gaf gfa_mapped.gaf` writes gfa_mapped_filtered.gaf next to it with
+    the lines gaf_filter::filter_max_alignment_mt keeps (CRLF input included)."""
+    ds = synth.Dataset(8, [40000, 25000], [4, 2], backbone_mean=400)
+    gl = ds.gaf(6, 0, 3000, synth.GafParams(long_reads=True, id_pair_suffix=False, p_secondary=0.3))
+    exp = opy.filter_max_alignment(gl)
+    assert 0 < len(exp) < gl.count(b"\n")
+    for name, data in (("gfa_mapped.gaf", gl), ("crlf.gaf", gl.replace(b"\n", b"\r\n"))):
+        p = str(tmp_path / name)
+        open(p, "wb").write(data)
+        r = subprocess.run([BIN, "--filter-gaf", p], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out = str(tmp_path / (name[:-4] + "_filtered.gaf"))
+        assert out in r.stdout
+        assert open(out, "rb").read() == b"".join(l + b"\n" for l in exp)
