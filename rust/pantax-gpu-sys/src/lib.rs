@@ -162,6 +162,16 @@ impl Gpu {
         depth.truncate(n); tdepth.truncate(t); cov.truncate(n);
         Ok((depth, tdepth, cov.into_iter().map(|x| x as usize).collect()))
     }
+    /// gaf_filter::filter_max_alignment_mt (gaf_filter.rs:44-97) on a GAF held in memory: byte offsets of the kept lines, file order.
+    /// alignment.rs:171 becomes: read the file, call this, write `&bytes[off..line_end]` + '\n' per offset to `<stem>_filtered.gaf`.
+    pub fn filter_gaf(&self, bytes: &[u8]) -> Result<Vec<u64>, GpuError> {
+        let cap = bytes.iter().filter(|&&c| c == b'\n').count() + 1;
+        let mut off = vec![0u64; cap];
+        let mut n_out: i64 = 0;
+        self.ck(unsafe { ptx_filter_gaf(self.raw, bytes.as_ptr(), bytes.len(), off.as_mut_ptr(), cap as i64, &mut n_out) })?;
+        off.truncate(n_out as usize);
+        Ok(off)
+    }
     /// (sum of node_base_cov, sum of nodes_len) over the distinct nodes of every path (profile.rs:2714-2724).
     pub fn path_sums(&self, species: usize) -> Result<(Vec<i64>, Vec<i64>), GpuError> {
         let s = species as c_int;
