@@ -231,3 +231,19 @@ def test_zz_filter_gaf_file_mode(tmp_path):
         out = str(tmp_path / (name[:-4] + "_filtered.gaf"))
         assert out in r.stdout
         assert open(out, "rb").read() == b"".join(l + b"\n" for l in exp)
+
+
+def test_profile_orchestrator_plan():
+    """`python -m pantax_b200 profile`: filter (long reads, on request) -> pantax-gpu-profile -> strain stage, options routed to the
+    stage that reads them, unknown ones handed to the driver."""
+    from pantax_b200.__main__ import BIN as B, plan
+
+    c = plan(["--db", "DB", "--gaf", "x/gfa_mapped.gaf", "--wd", "OUT", "--long-read", "--filter", "--fr", "0.5", "--fc", "0.4", "-a", "0", "--ds", "562,34"])
+    assert c[0] == [B, "--filter-gaf", "x/gfa_mapped.gaf"]
+    assert c[1][:8] == [B, "--db", "DB", "--gaf", "x/gfa_mapped_filtered.gaf", "--wd", "OUT", "--species"]
+    assert "--strain" in c[1] and "--long-read" in c[1] and c[1][-4:] == ["-a", "0", "--ds", "562,34"] and "--fc" not in c[1]
+    assert c[2][1:3] == ["-m", "pantax_b200.strain_tail"] and c[2][c[2].index("--fc") + 1] == "0.4" and c[2][c[2].index("--fr") + 1] == "0.5"
+    c = plan(["--db", "DB", "--gaf", "-", "--species-only"])
+    assert len(c) == 1 and "--strain" not in c[0] and c[0][c[0].index("--gaf") + 1] == "-"
+    r = subprocess.run([sys.executable, "-m", "pantax_b200"], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 2 and "profile --db" in r.stdout
