@@ -323,7 +323,17 @@ void usage() {
 
 }  // namespace
 
+int run(int argc, char** argv);
 int main(int argc, char** argv) {
+    // a malformed number in an option or an input table (std::stod / stoull / ...) ends the run with a message, not with an abort
+    try {
+        return run(argc, argv);
+    } catch (const std::exception& e) {
+        fprintf(stderr, "pantax-gpu-profile: malformed number or allocation failure (%s)\n", e.what());
+        return 1;
+    }
+}
+int run(int argc, char** argv) {
     Options o;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
