@@ -315,6 +315,7 @@ void usage() {
          "                   [--reads-binning reads_classification.tsv]   (with --strain only: species column of the GAF rows)\n"
          "                   [-a MIN_SPECIES_ABUND=1e-4] [--fr F] [--long-read] [--shift] [--no-filter] [--smode 0|1|2]\n"
          "                   [--ds TAXID,TAXID] [--range-file F] [--len-file F] [--min-depth D] [--device N] [--chunk-mb M]\n"
+         "                   [--force]   (run a stage although its table exists in --wd; default: skip it as the reference does)\n"
          "                   --filter-gaf FILE [--device N]   (long reads: FILE -> <stem>_filtered.gaf, gaf_filter.rs:44-97)\n"
          "                   --dump-graph FILE | --convert-graph FILE OUT.bin | --zip-gfa FILE.gfa OUTDIR RANGE_FILE   (graph files, no GPU)\n"
          "GPU implementation of PanTax's profiling stage (read classification, species abundance, node coverage and\n"
@@ -470,6 +471,20 @@ int run(int argc, char** argv) {
     }
     if (!o.species && !o.strain) die("Please choose profiling level with --species or/and --strain.");  // profile.rs:73-75
     if (o.db.empty() || o.gaf.empty()) { usage(); return 1; }
+    if (!o.force) {
+        // profile.rs:3333-3425: a stage whose table exists is not run again - `--species` is skipped when species_abundance.txt exists
+        // (a `--strain` request then resumes from reads_classification.tsv, :3365), `--strain` when strain_abundance.txt exists
+        const bool sp_done = exists(o.wd + "/species_abundance.txt"), st_done = exists(o.wd + "/strain_abundance.txt");
+        if (o.species && !sp_done) {
+            if (o.strain && st_done) o.strain = false;  // :3361
+        } else if (o.strain && !st_done) {
+            o.species = false;
+        } else {
+            fprintf(stderr, "%s\n", o.species && o.strain ? "Species and strain profiling abundance files both exist." :
+                                    o.species ? "Species profiling abundance file exists." : "Strain profiling abundance file exists.");
+            return 0;  // :3414-3422 (--force runs the stages anyway)
+        }
+    }
     if (o.fr < 0) o.fr = o.long_read ? 0.5 : 0.3;  // main.rs:107-113
     if (o.range_file.empty()) o.range_file = o.db + "/species_range.txt";
     if (o.len_file.empty()) o.len_file = o.db + "/species_genomes_stats.txt";

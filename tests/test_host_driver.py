@@ -255,3 +255,15 @@ def test_zip_gfa_writes_the_reference_bin_and_range_row(tmp_path):
         # a second run keeps the .bin (zip.rs:182) and appends another row
         subprocess.run([BIN, "--zip-gfa", gfa, str(d), rf], check=True)
         assert open(rf).read().count("\n") == 2
+
+
+def test_existing_tables_are_not_recomputed(tmp_path):
+    """profile.rs:3333-3425: a stage whose output table exists in the working directory is skipped; with both tables present the run
+    ends at once (no GPU is touched, so this runs anywhere)."""
+    wd = str(tmp_path)
+    open(os.path.join(wd, "species_abundance.txt"), "w").write("species_taxid\tpredicted_abundance\tpredicted_coverage\n")
+    open(os.path.join(wd, "strain_abundance.txt"), "w").write("x\n")
+    r = subprocess.run([BIN, "--db", wd, "--gaf", os.path.join(wd, "none.gaf"), "--wd", wd, "--species", "--strain"], capture_output=True, text=True)
+    assert r.returncode == 0 and "both exist" in r.stderr
+    r = subprocess.run([BIN, "--db", wd, "--gaf", os.path.join(wd, "none.gaf"), "--wd", wd, "--species"], capture_output=True, text=True)
+    assert r.returncode == 0 and "Species profiling abundance file exists" in r.stderr
